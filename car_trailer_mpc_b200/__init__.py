@@ -1,0 +1,38 @@
+"""B200-native batched NMPC solver for the truck-trailer tracking controller of
+Avan1ko/car-trailer-mpc (drop-in for ``controller.solve`` of mpc_control.py / mpc_control_nmpc.py).
+
+Public surface:
+  * :class:`BatchSolver`           -- thin ctypes front end of the C ABI in ``include/ttmpc.h`` (CUDA only).
+  * :class:`MPCTrackingControl`, :class:`TruckTrailerNMPC`, :class:`TruckTrailerModel` -- shims with
+    the reference's constructor / ``solve`` signatures.
+  * :mod:`problem`                 -- trajectory, windows, layouts, synthetic scenario batches.
+  * :mod:`closed_loop`, :mod:`batch_driver` -- headless closed loop and the sweep/CSV driver.
+"""
+from .config import (  # noqa: F401
+    Config,
+    STATUS_NAMES,
+    nmpc_preset,
+    tracking_preset,
+)
+
+__all__ = ["Config", "tracking_preset", "nmpc_preset", "STATUS_NAMES"]
+
+
+def __getattr__(name):  # lazy: importing the package must not require the CUDA library
+    if name == "BatchSolver":
+        from .solver import BatchSolver
+
+        return BatchSolver
+    if name == "MPCTrackingControl":
+        from .mpc_control import MPCTrackingControl
+
+        return MPCTrackingControl
+    if name == "TruckTrailerNMPC":
+        from .mpc_control_nmpc import TruckTrailerNMPC
+
+        return TruckTrailerNMPC
+    if name == "TruckTrailerModel":
+        from .truck_trailer_model import TruckTrailerModel
+
+        return TruckTrailerModel
+    raise AttributeError(name)

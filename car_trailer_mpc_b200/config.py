@@ -1,0 +1,128 @@
+"""Solver configuration: the ctypes mirror of ``ttmpc_config`` (include/ttmpc.h) and the presets
+of the reference's two controllers.
+
+Numbers follow the reference drivers:
+  * ``MPCTrackingControl`` preset  -- python-files/simulation.py:388-414 (Q=I6, R=10*I2, bounds) with
+    Ipopt defaults + ``max_iter 5000`` (python-files/mpc_control.py:35-39).
+  * ``TruckTrailerNMPC`` preset    -- python-files/simulation_nmpc.py:124-148 (Q=diag(1,1,2,3,1,1),
+    R=diag(5,8), v in [-8,8], a in [-4,4]) with ``tol 1e-3, acceptable_tol 1e-2, acceptable_iter 5,
+    max_iter 2000`` (python-files/mpc_control_nmpc.py:36-45).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+NX = 6
+NU = 2
+MAX_HORIZON = 128
+
+# status codes (include/ttmpc.h)
+ST_CONVERGED, ST_ACCEPTABLE, ST_MAX_ITER, ST_LINESEARCH, ST_NUMERIC, ST_INFEASIBLE_X0 = range(6)
+STATUS_NAMES = {
+    ST_CONVERGED: "converged",
+    ST_ACCEPTABLE: "acceptable",
+    ST_MAX_ITER: "max_iter",
+    ST_LINESEARCH: "linesearch",
+    ST_NUMERIC: "numeric",
+    ST_INFEASIBLE_X0: "infeasible_x0",
+}
+
+FLAG_HOST_POINTERS = 0x1
+FLAG_SYNC = 0x2
+FLAG_SHIFT_REFERENCE_BUG = 0x4
+
+
+class Config(ctypes.Structure):
+    """Plain-old-data twin of ``struct ttmpc_config``; field order and types must match the header."""
+
+    _fields_ = [
+        ("horizon", ctypes.c_int32),
+        ("max_iter", ctypes.c_int32),
+        ("acceptable_iter", ctypes.c_int32),
+        ("flags", ctypes.c_uint32),
+        ("dt", ctypes.c_double),
+        ("L1", ctypes.c_double),
+        ("L2", ctypes.c_double),
+        ("M", ctypes.c_double),
+        ("Q", ctypes.c_double * 36),
+        ("R", ctypes.c_double * 4),
+        ("x_lb", ctypes.c_double * 6),
+        ("x_ub", ctypes.c_double * 6),
+        ("u_lb", ctypes.c_double * 2),
+        ("u_ub", ctypes.c_double * 2),
+        ("tol", ctypes.c_double),
+        ("acceptable_tol", ctypes.c_double),
+        ("mu_init", ctypes.c_double),
+    ]
+
+    # -- helpers -------------------------------------------------------------------------------
+    def set_weights(self, Q, R) -> None:
+        Q = np.asarray(Q, dtype=np.float64).reshape(6, 6)
+        R = np.asarray(R, dtype=np.float64).reshape(2, 2)
+        self.Q[:] = Q.ravel().tolist()
+        self.R[:] = R.ravel().tolist()
+
+    def set_bounds(self, x_lb, x_ub, u_lb, u_ub) -> None:
+        self.x_lb[:] = np.asarray(x_lb, dtype=np.float64).ravel().tolist()
+        self.x_ub[:] = np.asarray(x_ub, dtype=np.float64).ravel().tolist()
+        self.u_lb[:] = np.asarray(u_lb, dtype=np.float64).ravel().tolist()
+        self.u_ub[:] = np.asarray(u_ub, dtype=np.float64).ravel().tolist()
+
+    @property
+    def nz(self) -> int:
+        """Length of the reference's decision vector, 8N+6 (trajectory_planning.py:38-60)."""
+        return 8 * self.horizon + 6
+
+    def Qm(self) -> np.ndarray:
+        return np.array(self.Q[:], dtype=np.float64).reshape(6, 6)
+
+    def Rm(self) -> np.ndarray:
+        return np.array(self.R[:], dtype=np.float64).reshape(2, 2)
+
+    def copy(self) -> "Config":
+        c = Config()
+        ctypes.memmove(ctypes.byref(c), ctypes.byref(self), ctypes.sizeof(Config))
+        return c
+
+
+def tracking_preset(horizon: int = 40, dt: float = 0.05, max_iter: int = 5000) -> Config:
+    """``MPCTrackingControl`` as configured by simulation.py:388-414 (Ipopt defaults, tol 1e-8)."""
+    c = Config()
+    c.horizon = horizon
+    c.max_iter = max_iter
+    c.acceptable_iter = 15
+    c.flags = 0
+    c.dt = dt
+    c.L1, c.L2, c.M = 7.05, 12.45, 0.15
+    c.set_weights(np.eye(6), 10.0 * np.eye(2))
+    inf = math.inf
+    c.set_bounds(
+        [-inf, -inf, -math.pi, -math.pi / 3.0, -math.pi / 4.0, -10.0],
+        [inf, inf, math.pi, math.pi / 3.0, math.pi / 4.0, 10.0],
+        [-5.0, -math.pi / 2.0],
+        [5.0, math.pi / 2.0],
+    )
+    c.tol = 1e-8
+    c.acceptable_tol = 1e-6
+    c.mu_init = 0.1
+    return c
+
+
+def nmpc_preset(horizon: int = 30, dt: float = 0.05, max_iter: int = 2000) -> Config:
+    """``TruckTrailerNMPC`` as configured by simulation_nmpc.py:124-148 + mpc_control_nmpc.py:36-45."""
+    c = tracking_preset(horizon, dt, max_iter)
+    c.acceptable_iter = 5
+    c.set_weights(np.diag([1.0, 1.0, 2.0, 3.0, 1.0, 1.0]), np.diag([5.0, 8.0]))
+    inf = math.inf
+    c.set_bounds(
+        [-inf, -inf, -math.pi, -math.pi / 3.0, -math.pi / 4.0, -8.0],
+        [inf, inf, math.pi, math.pi / 3.0, math.pi / 4.0, 8.0],
+        [-4.0, -math.pi / 2.0],
+        [4.0, math.pi / 2.0],
+    )
+    c.tol = 1e-3
+    c.acceptable_tol = 1e-2
+    return c

@@ -1,0 +1,155 @@
+/*
+ * ttmpc.h -- C ABI of the B200-native batched truck-trailer NMPC solver.
+ *
+ * This is the drop-in boundary for ONE path of Avan1ko/car-trailer-mpc: the
+ * per-timestep `controller.solve(initial_state, reference_states,
+ * reference_inputs) -> (states, inputs)` call.  The reference has no FFI; every
+ * entry point below replaces a piece of Python that sits in front of
+ * `ca.nlpsol('solver','ipopt',...)`:
+ *
+ *   ttmpc_create            <- MPCTrackingControl.__init__ / _build_solver
+ *                              (python-files/mpc_control.py:6-56), TruckTrailerNMPC.__init__
+ *                              (python-files/mpc_control_nmpc.py:11-58): model constants,
+ *                              Q/R, box bounds, Ipopt option preset.
+ *   ttmpc_solve_batch       <- MPCTrackingControl.solve (mpc_control.py:67-110) and
+ *                              TruckTrailerNMPC.solve (mpc_control_nmpc.py:90-113),
+ *                              B independent problems per call instead of one.
+ *   ttmpc_solve_batch_shared<- the window extraction of the closed-loop drivers
+ *                              (simulation.py:485-499, simulation_nmpc.py:193-204) fused
+ *                              with the solve: every problem tracks the same trajectory.
+ *   ttmpc_shift_warm_start  <- TruckTrailerNMPC._shift_solution (mpc_control_nmpc.py:69-88).
+ *   ttmpc_plant_step        <- update()/f_dyn of the drivers (simulation.py:34-48,167-199,
+ *                              simulation_nmpc.py:94-105) for on-device closed loops.
+ *
+ * Layouts are the reference's own:
+ *   decision vector  z = [x_0;u_0;x_1;u_1;...;x_{N-1};u_{N-1};x_N], 8N+6 doubles
+ *                       (trajectory_planning.py:38-60), x=(x,y,theta,psi,phi,v), u=(a,omega);
+ *   reference window ref_states[N+1][6], ref_inputs[N][2]: stage-major, i.e. exactly the
+ *                       parameter vector p of mpc_control.py:48-50 / :71-72 without x_init.
+ *
+ * All arithmetic is IEEE double.  No torch types, no C++ types: plain pointers and sizes.
+ * Unless TTMPC_FLAG_HOST_POINTERS is set, every array pointer is a CUDA device pointer
+ * owned by the caller (e.g. torch.Tensor.data_ptr()); the library only owns its private
+ * scratch.  Calls are asynchronous on the supplied stream unless TTMPC_FLAG_SYNC is set
+ * (host-pointer calls are always synchronous).  A handle must not be used concurrently
+ * from several threads; distinct handles are independent.
+ *
+ * Return value: 0 on success, negative TTMPC_E_* otherwise; never throws, never exits.
+ */
+#ifndef TTMPC_H
+#define TTMPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTMPC_NX 6
+#define TTMPC_NU 2
+#define TTMPC_MAX_HORIZON 128
+
+/* error codes */
+#define TTMPC_OK 0
+#define TTMPC_E_INVAL (-22)   /* bad argument / config                         */
+#define TTMPC_E_NOMEM (-12)   /* device scratch allocation failed              */
+#define TTMPC_E_CUDA (-5)     /* CUDA runtime error, see ttmpc_last_error()    */
+#define TTMPC_E_NODEV (-19)   /* no usable CUDA device (there is NO CPU fallback) */
+
+/* per-problem status codes (status_out) */
+#define TTMPC_ST_CONVERGED 0      /* Ipopt "Solve_Succeeded": scaled KKT error <= tol            */
+#define TTMPC_ST_ACCEPTABLE 1     /* Ipopt "Solved_To_Acceptable_Level"                          */
+#define TTMPC_ST_MAX_ITER 2       /* iteration limit; z_out holds the last iterate               */
+#define TTMPC_ST_LINESEARCH 3     /* step rejected repeatedly (Ipopt would enter restoration)    */
+#define TTMPC_ST_NUMERIC 4        /* NaN/Inf encountered, z_out holds the last finite iterate    */
+#define TTMPC_ST_INFEASIBLE_X0 5  /* x_init violates a state bound: reference NLP is infeasible  */
+
+/* flags */
+#define TTMPC_FLAG_HOST_POINTERS 0x1u /* array arguments are host pointers (B=1 shim path)      */
+#define TTMPC_FLAG_SYNC 0x2u          /* cudaStreamSynchronize before returning                 */
+#define TTMPC_FLAG_SHIFT_REFERENCE_BUG 0x4u /* ttmpc_shift_warm_start reproduces the mis-sliced
+                                               tail of mpc_control_nmpc.py:83-87 bit for bit    */
+
+typedef struct ttmpc_config {
+  int32_t horizon;          /* N, params['horizon'] (simulation.py:390), 1..TTMPC_MAX_HORIZON   */
+  int32_t max_iter;         /* Ipopt max_iter (mpc_control.py:35 = 5000, nmpc :38 = 2000)       */
+  int32_t acceptable_iter;  /* Ipopt acceptable_iter (default 15, nmpc :42 = 5)                 */
+  uint32_t flags;           /* TTMPC_FLAG_*                                                     */
+  double dt;                /* params['dt']  (simulation.py:389)                                */
+  double L1, L2, M;         /* params['L1'],['L2'],['M'] (simulation.py:391-393)                */
+  double Q[36];             /* row-major 6x6 state weight (simulation.py:400-406)               */
+  double R[4];              /* row-major 2x2 input weight (simulation.py:407-409)               */
+  double x_lb[6], x_ub[6];  /* state_bound (simulation.py:411-412); +-INFINITY = unbounded       */
+  double u_lb[2], u_ub[2];  /* input_bound (simulation.py:413-414)                              */
+  double tol;               /* Ipopt tol (default 1e-8, nmpc 1e-3)                              */
+  double acceptable_tol;    /* Ipopt acceptable_tol (default 1e-6, nmpc 1e-2)                   */
+  double mu_init;           /* Ipopt mu_init (default 0.1)                                      */
+} ttmpc_config;
+
+typedef struct ttmpc_handle ttmpc_handle;
+
+/* Fill cfg with the MPCTrackingControl preset of simulation.py:388-414 (N as given). */
+void ttmpc_default_config(ttmpc_config* cfg, int32_t horizon);
+
+/* Create a solver bound to CUDA device `device`.  Fails with TTMPC_E_NODEV when no CUDA
+ * device is usable -- there is no CPU path in this library. */
+int ttmpc_create(const ttmpc_config* cfg, int device, ttmpc_handle** out);
+int ttmpc_destroy(ttmpc_handle* h);
+const char* ttmpc_last_error(const ttmpc_handle* h);
+const char* ttmpc_version(void);
+
+/* Solve B independent NLPs.
+ *   x_init     [B][6]
+ *   ref_states [B][N+1][6]      ref_inputs [B][N][2]
+ *   z_warm     [B][8N+6] or NULL (NULL = cold start at the reference window, mpc_control.py:58-65)
+ *   z_out      [B][8N+6] or NULL
+ *   u0_out     [B][2]    or NULL  first control (what the caller applies, simulation.py:525)
+ *   obj_out    [B]       or NULL  objective J(z*)
+ *   kkt_out    [B][3]    or NULL  unscaled (dual infeasibility, constraint violation, complementarity)
+ *   iters_out  [B]       or NULL  interior-point iterations used
+ *   status_out [B]       or NULL  TTMPC_ST_*
+ *   cuda_stream: cudaStream_t (NULL = legacy default stream)
+ */
+int ttmpc_solve_batch(ttmpc_handle* h, int64_t B, const double* x_init, const double* ref_states,
+                      const double* ref_inputs, const double* z_warm, double* z_out,
+                      double* u0_out, double* obj_out, double* kkt_out, int32_t* iters_out,
+                      int32_t* status_out, void* cuda_stream);
+
+/* Same, but every problem tracks one shared trajectory traj_states[T+1][6], traj_inputs[T][2];
+ * problem i uses the window starting at k_index[i] with the three padding regimes of
+ * simulation.py:485-499 (full slice / pad with last state + last input / past the end =
+ * last state + zero input). */
+int ttmpc_solve_batch_shared(ttmpc_handle* h, int64_t B, const double* x_init,
+                             const int32_t* k_index, const double* traj_states,
+                             const double* traj_inputs, int32_t T, const double* z_warm,
+                             double* z_out, double* u0_out, double* obj_out, double* kkt_out,
+                             int32_t* iters_out, int32_t* status_out, void* cuda_stream);
+
+/* Warm-start shift of B decision vectors (device pointers unless HOST flag in cfg):
+ * z_shift[i] = shift(z[i]) as TruckTrailerNMPC._shift_solution. `mode` 0 = intended shift
+ * (last stage repeated), 1 = the reference's mis-sliced tail. */
+int ttmpc_shift_warm_start(ttmpc_handle* h, int64_t B, const double* z, double* z_shift,
+                           int32_t mode, void* cuda_stream);
+
+/* One explicit-Euler plant step for B states, q_next = update(q, u) of simulation.py:167-199.
+ * disturb = NULL: nominal plant.  Otherwise disturb = {friction_coeff, slippage_coeff,
+ * lateral_slip_gain, slip_angle_max}; additive noise [B][6] (may be NULL) is added as
+ * q_next += noise_scale*noise (simulation_nmpc.py:100 uses noise_scale = dt). */
+int ttmpc_plant_step(ttmpc_handle* h, int64_t B, const double* q, const double* u,
+                     const double* disturb, const double* noise, double noise_scale,
+                     double* q_next, void* cuda_stream);
+
+/* Number of kernel launches issued through this handle so far (bench accounting). */
+int64_t ttmpc_launch_count(const ttmpc_handle* h);
+
+/* Name + accumulated launch count of kernel i (0-based); returns NULL past the end. */
+const char* ttmpc_kernel_name(const ttmpc_handle* h, int32_t i, int64_t* launches);
+
+/* Measure the non-tensor FP64 FMA peak of the device (independent DFMA chains on every SM),
+ * returns GFLOP/s (2 flop per FMA) or a negative error. Used as the roofline denominator. */
+double ttmpc_measure_fp64_peak(ttmpc_handle* h, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTMPC_H */
