@@ -1,0 +1,630 @@
+// ttmpc.cu -- CUDA kernels (sm_100a) and the C ABI of include/ttmpc.h.
+//
+// Kernels:
+//   ttmpc_pack_kernel    AoS problem data (the reference's p / z layouts) -> slot-interleaved scratch,
+//                        transposed through shared memory so both sides are coalesced; also builds the
+//                        starting point (mpc_control.py:58-65 cold start or caller's warm start, pushed
+//                        into the interior like Ipopt does) and, in shared-trajectory mode, the window of
+//                        simulation.py:485-499.
+//   ttmpc_solve_kernel   the interior-point solve, one thread per problem (ttmpc_core.cuh).
+//   ttmpc_unpack_kernel  scratch -> z_out in the reference's decision-vector layout
+//                        (trajectory_planning.py:38-60).
+//   ttmpc_shift_kernel   TruckTrailerNMPC._shift_solution (mpc_control_nmpc.py:69-88).
+//   ttmpc_plant_kernel   update()/f_dyn of the closed-loop drivers (simulation.py:34-48,167-199).
+//   ttmpc_dfma_kernel    FP64 FMA peak microbenchmark (roofline denominator).
+//
+// There is NO CPU fallback in this library: without a CUDA device ttmpc_create fails with TTMPC_E_NODEV.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/ttmpc.h"
+#include "ttmpc_core.cuh"
+
+using namespace ttmpc;
+
+namespace {
+
+constexpr int kSolveThreads = 128;
+constexpr int kTileSlots = 32;    // slots per CTA in pack/unpack
+constexpr int kTileStages = 8;    // stages per shared-memory tile
+constexpr int kPackThreads = 256;
+constexpr int kTileW = kTileStages * NW + 1;  // +1: odd stride, conflict-free transposition
+
+// ------------------------------------------------------------------------------------------------
+// pack: problem data -> scratch
+// ------------------------------------------------------------------------------------------------
+struct PackIn {
+  const double* x_init;      // [B][6]
+  const double* ref_states;  // [B][N+1][6] or null (shared mode)
+  const double* ref_inputs;  // [B][N][2]
+  const double* z_warm;      // [B][8N+6] or null
+  const int32_t* k_index;    // [B] (shared mode)
+  const double* traj_states; // [T+1][6]
+  const double* traj_inputs; // [T][2]
+  int T;
+};
+
+__global__ void __launch_bounds__(kPackThreads) ttmpc_pack_kernel(const __grid_constant__ Params p, double* __restrict__ scratch,
+                                                                 size_t cap, long long B, PackIn in) {
+  __shared__ double t_ref[kTileSlots][kTileW];
+  __shared__ double t_gs[kTileSlots][kTileW];
+  const int N = p.N;
+  const long long slot0 = (long long)blockIdx.x * kTileSlots;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = kPackThreads >> 5;
+  const long long nz = 8LL * N + 6;
+  const bool shared_mode = (in.ref_states == nullptr);
+
+  for (int k0 = 0; k0 <= N; k0 += kTileStages) {
+    const int ns = min(kTileStages, N + 1 - k0);  // stages in this tile
+    // ---- phase A: gather AoS -> tile (lanes run along the contiguous per-problem data)
+    for (int sl = warp; sl < kTileSlots; sl += nwarps) {
+      const long long b = slot0 + sl;
+      if (b >= B) continue;
+      if (!shared_mode) {
+        const double* rs = in.ref_states + b * (long long)(N + 1) * NX + (long long)k0 * NX;
+        for (int e = lane; e < ns * NX; e += 32) t_ref[sl][(e / NX) * NW + (e % NX)] = rs[e];
+        const double* ru = in.ref_inputs + b * (long long)N * NU + (long long)k0 * NU;
+        const int nu_e = min(ns, N - k0) * NU;
+        for (int e = lane; e < ns * NU; e += 32) t_ref[sl][(e / NU) * NW + NX + (e % NU)] = (e < nu_e) ? ru[e] : 0.0;
+      } else {
+        // window regimes of simulation.py:485-499 on the shared trajectory
+        const int kk = in.k_index[b], T = in.T;
+        for (int e = lane; e < ns * NW; e += 32) {
+          const int st = k0 + e / NW, j = e % NW;
+          double v;
+          if (j < NX) {
+            const int idx = (kk < T) ? min(kk + st, T) : T;
+            v = in.traj_states[(long long)idx * NX + j];
+          } else if (st >= N || kk >= T) {
+            v = 0.0;
+          } else {
+            v = in.traj_inputs[(long long)min(kk + st, T - 1) * NU + (j - NX)];
+          }
+          t_ref[sl][e] = v;
+        }
+      }
+      if (in.z_warm) {
+        const double* zw = in.z_warm + b * nz + (long long)k0 * NW;
+        const int ne = (int)min((long long)ns * NW, nz - (long long)k0 * NW);
+        for (int e = lane; e < ns * NW; e += 32) t_gs[sl][e] = (e < ne) ? zw[e] : 0.0;
+      }
+    }
+    __syncthreads();
+    // ---- phase B: tile -> scratch (lanes run along slots: 256 B coalesced rows)
+    const long long b = slot0 + lane;
+    if (b < B) {
+      for (int e = warp; e < ns * NW; e += nwarps) {
+        const int st = k0 + e / NW, j = e % NW;
+        if (j >= NX && st >= N) continue;  // no input at the terminal stage
+        const double r = t_ref[lane][e];
+        const double g = in.z_warm ? t_gs[lane][e] : r;
+        double w;
+        const bool hl = (j < NX) ? ((p.xhl >> j) & 1u) : ((p.uhl >> (j - NX)) & 1u);
+        const bool hu = (j < NX) ? ((p.xhu >> j) & 1u) : ((p.uhu >> (j - NX)) & 1u);
+        if (st == 0 && j < NX) {
+          w = in.x_init[b * NX + j];  // x_0 is data
+        } else {
+          const double lo = (j < NX) ? p.xl[j] : p.ul[j - NX];
+          const double up = (j < NX) ? p.xu[j] : p.uu[j - NX];
+          w = push_inside(g, lo, up, hl, hu);
+          if (hl) scratch[(size_t)(p.oZL + st * wZ + j) * cap + b] = 1.0;
+          if (hu) scratch[(size_t)(p.oZU + st * wZ + j) * cap + b] = 1.0;
+        }
+        scratch[(size_t)(p.oW + st * wW + j) * cap + b] = w;
+        scratch[(size_t)(p.oREF + st * wREF + j) * cap + b] = r;
+        if (j < NX) scratch[(size_t)(p.oLAM + st * wLAM + j) * cap + b] = 0.0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// solve
+// ------------------------------------------------------------------------------------------------
+struct SolveOut {
+  double* u0;      // [B][2]
+  double* obj;     // [B]
+  double* kkt;     // [B][3]
+  int32_t* iters;  // [B]
+  int32_t* status; // [B]
+};
+
+__global__ void __launch_bounds__(kSolveThreads) ttmpc_solve_kernel(const __grid_constant__ Params p, double* __restrict__ scratch,
+                                                                   size_t cap, long long B, SolveOut out) {
+  const long long b = (long long)blockIdx.x * kSolveThreads + threadIdx.x;
+  if (b >= B) return;
+  Slot s{scratch, cap, (size_t)b};
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < NX; j++) {
+    const double x = s.ld(p.oW + j);
+    if (((p.xhl >> j) & 1u) && x < p.xl[j]) bad = true;
+    if (((p.xhu >> j) & 1u) && x > p.xu[j]) bad = true;
+  }
+  Result r;
+  solve_slot(p, s, bad, r);
+  if (out.u0) {
+    out.u0[b * 2 + 0] = r.u0a;
+    out.u0[b * 2 + 1] = r.u0w;
+  }
+  if (out.obj) out.obj[b] = r.obj;
+  if (out.kkt) {
+    out.kkt[b * 3 + 0] = r.dual_inf;
+    out.kkt[b * 3 + 1] = r.constr_viol;
+    out.kkt[b * 3 + 2] = r.compl_inf;
+  }
+  if (out.iters) out.iters[b] = r.iters;
+  if (out.status) out.status[b] = r.status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// unpack: scratch -> z_out (reference decision-vector layout)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPackThreads) ttmpc_unpack_kernel(const __grid_constant__ Params p, const double* __restrict__ scratch,
+                                                                   size_t cap, long long B, double* __restrict__ z_out) {
+  __shared__ double t[kTileSlots][kTileW];
+  const int N = p.N;
+  const long long slot0 = (long long)blockIdx.x * kTileSlots;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = kPackThreads >> 5;
+  const long long nz = 8LL * N + 6;
+  for (int k0 = 0; k0 <= N; k0 += kTileStages) {
+    const int ns = min(kTileStages, N + 1 - k0);
+    const long long b = slot0 + lane;
+    if (b < B) {
+      for (int e = warp; e < ns * NW; e += nwarps) {
+        const int st = k0 + e / NW, j = e % NW;
+        t[lane][e] = (j >= NX && st >= N) ? 0.0 : scratch[(size_t)(p.oW + st * wW + j) * cap + b];
+      }
+    }
+    __syncthreads();
+    for (int sl = warp; sl < kTileSlots; sl += nwarps) {
+      const long long bb = slot0 + sl;
+      if (bb >= B) continue;
+      double* zo = z_out + bb * nz + (long long)k0 * NW;
+      const int ne = (int)min((long long)ns * NW, nz - (long long)k0 * NW);
+      for (int e = lane; e < ne; e += 32) zo[e] = t[sl][e];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// callers' helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void ttmpc_shift_kernel(int N, long long B, const double* __restrict__ z, double* __restrict__ out, int mode) {
+  const long long nz = 8LL * N + 6;
+  const long long total = B * nz;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / nz;
+    const int e = (int)(i - b * nz);
+    const double* zb = z + b * nz;
+    int src;
+    if (e < 8 * (N - 1)) {
+      src = e + 8;  // stages 1..N-1 move to 0..N-2
+    } else if (mode == 1) {
+      // the reference's slicing (mpc_control_nmpc.py:83-87): "last_state" = z[-8:-2], "last_input" = z[-2:]
+      const int r = e - 8 * (N - 1);
+      if (r < 6) src = (int)nz - 8 + r;
+      else if (r < 8) src = (int)nz - 2 + (r - 6);
+      else src = (int)nz - 8 + (r - 8);
+    } else {
+      const int r = e - 8 * (N - 1);
+      if (r < 6) src = 8 * N + r;                 // x_N
+      else if (r < 8) src = 8 * (N - 1) + r;      // u_{N-1}
+      else src = 8 * N + (r - 8);                 // x_N
+    }
+    out[i] = zb[src];
+  }
+}
+
+__global__ void ttmpc_plant_kernel(const __grid_constant__ Params p, long long B, const double* __restrict__ q, const double* __restrict__ u,
+                                   int has_dist, double fric, double slipc, double lat_gain, double slip_max,
+                                   const double* __restrict__ noise, double noise_scale, double* __restrict__ q_next) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[NX], f[4];
+#pragma unroll
+  for (int j = 0; j < NX; j++) x[j] = q[b * NX + j];
+  double a = u[b * 2 + 0], w = u[b * 2 + 1];
+  if (has_dist) {
+    a *= fric;
+    w *= slipc;
+  }
+  stage_f(p, x, f);
+  double fd[NX] = {f[0], f[1], f[2], f[3], w, a};
+  if (has_dist) {
+    const double slip = 1.0 - fmin(fabs(x[4]) * fabs(x[5]) * slip_max, 0.3);
+    fd[2] *= slip;
+    fd[3] *= slip;
+  }
+  double y[NX];
+#pragma unroll
+  for (int j = 0; j < NX; j++) y[j] = x[j] + fd[j] * p.dt;
+  if (noise) {
+#pragma unroll
+    for (int j = 0; j < NX; j++) y[j] += noise[b * NX + j] * noise_scale;
+  }
+  if (has_dist) {
+    const double mag = lat_gain * fabs(x[5]) * fabs(x[4]);
+    double sn, cs;
+    sincos(x[2] + 1.5707963267948966, &sn, &cs);
+    y[0] += mag * cs * p.dt;
+    y[1] += mag * sn * p.dt;
+  }
+#pragma unroll
+  for (int j = 0; j < NX; j++) q_next[b * NX + j] = y[j];
+}
+
+// FP64 FMA peak: 8 independent dependent-chains per thread, 2 flop per FMA.
+constexpr int kDfmaIters = 4096, kDfmaChains = 8;
+__global__ void __launch_bounds__(256) ttmpc_dfma_kernel(double* out, double a, double b) {
+  double acc[kDfmaChains];
+#pragma unroll
+  for (int i = 0; i < kDfmaChains; i++) acc[i] = (double)(threadIdx.x + i);
+  for (int it = 0; it < kDfmaIters; it++) {
+#pragma unroll
+    for (int i = 0; i < kDfmaChains; i++) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < kDfmaChains; i++) s += acc[i];
+  if (s == 123.456) out[0] = s;  // never true; keeps the chains alive
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+struct ttmpc_handle {
+  ttmpc_config cfg;
+  Params p;
+  int device;
+  double* scratch;
+  size_t cap;
+  // staging for the host-pointer path
+  void* stage;
+  size_t stage_bytes;
+  char err[256];
+  long long launches[6];
+};
+
+static const char* kKernelNames[6] = {"ttmpc_pack_kernel", "ttmpc_solve_kernel", "ttmpc_unpack_kernel",
+                                      "ttmpc_shift_kernel", "ttmpc_plant_kernel", "ttmpc_dfma_kernel"};
+
+static int set_err(ttmpc_handle* h, int code, const char* what, cudaError_t ce) {
+  if (h) snprintf(h->err, sizeof h->err, "%s%s%s", what, ce != cudaSuccess ? ": " : "", ce != cudaSuccess ? cudaGetErrorString(ce) : "");
+  return code;
+}
+
+extern "C" {
+
+const char* ttmpc_version(void) { return "ttmpc 0.1 (sm_100a, thread-per-problem IPM/Riccati)"; }
+
+void ttmpc_default_config(ttmpc_config* c, int32_t horizon) {
+  memset(c, 0, sizeof *c);
+  c->horizon = horizon;
+  c->max_iter = 5000;
+  c->acceptable_iter = 15;
+  c->dt = 0.05;
+  c->L1 = 7.05;
+  c->L2 = 12.45;
+  c->M = 0.15;
+  for (int i = 0; i < 6; i++) c->Q[i * 6 + i] = 1.0;
+  c->R[0] = c->R[3] = 10.0;
+  const double pi = 3.141592653589793;
+  const double xl[6] = {-INFINITY, -INFINITY, -pi, -pi / 3.0, -pi / 4.0, -10.0};
+  for (int i = 0; i < 6; i++) {
+    c->x_lb[i] = xl[i];
+    c->x_ub[i] = -xl[i];
+  }
+  c->u_lb[0] = -5.0;
+  c->u_ub[0] = 5.0;
+  c->u_lb[1] = -pi / 2.0;
+  c->u_ub[1] = pi / 2.0;
+  c->tol = 1e-8;
+  c->acceptable_tol = 1e-6;
+  c->mu_init = 0.1;
+}
+
+int ttmpc_create(const ttmpc_config* cfg, int device, ttmpc_handle** out) {
+  if (!cfg || !out) return TTMPC_E_INVAL;
+  *out = nullptr;
+  Params p;
+  int rc = build_params(cfg, &p);
+  if (rc) return rc;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return TTMPC_E_NODEV;
+  if (cudaSetDevice(device) != cudaSuccess) return TTMPC_E_NODEV;
+  ttmpc_handle* h = new (std::nothrow) ttmpc_handle;
+  if (!h) return TTMPC_E_NOMEM;
+  memset(h, 0, sizeof *h);
+  h->cfg = *cfg;
+  h->p = p;
+  h->device = device;
+  *out = h;
+  return TTMPC_OK;
+}
+
+int ttmpc_destroy(ttmpc_handle* h) {
+  if (!h) return TTMPC_OK;
+  cudaSetDevice(h->device);
+  if (h->scratch) cudaFree(h->scratch);
+  if (h->stage) cudaFree(h->stage);
+  delete h;
+  return TTMPC_OK;
+}
+
+const char* ttmpc_last_error(const ttmpc_handle* h) { return h ? h->err : "null handle"; }
+
+int64_t ttmpc_launch_count(const ttmpc_handle* h) {
+  long long n = 0;
+  if (h)
+    for (int i = 0; i < 6; i++) n += h->launches[i];
+  return n;
+}
+
+const char* ttmpc_kernel_name(const ttmpc_handle* h, int32_t i, int64_t* launches) {
+  if (!h || i < 0 || i >= 6) return nullptr;
+  if (launches) *launches = h->launches[i];
+  return kKernelNames[i];
+}
+
+static int ensure_scratch(ttmpc_handle* h, long long B) {
+  size_t need = (size_t)((B + 127) / 128) * 128;
+  if (need <= h->cap) return TTMPC_OK;
+  if (h->scratch) cudaFree(h->scratch);
+  h->scratch = nullptr;
+  h->cap = 0;
+  cudaError_t ce = cudaMalloc(&h->scratch, need * (size_t)h->p.rows * sizeof(double));
+  if (ce != cudaSuccess) return set_err(h, TTMPC_E_NOMEM, "scratch cudaMalloc", ce);
+  h->cap = need;
+  return TTMPC_OK;
+}
+
+static int solve_device(ttmpc_handle* h, long long B, const PackIn& in, double* z_out, const SolveOut& so, cudaStream_t st) {
+  int rc = ensure_scratch(h, B);
+  if (rc) return rc;
+  const unsigned gp = (unsigned)((B + kTileSlots - 1) / kTileSlots);
+  ttmpc_pack_kernel<<<gp, kPackThreads, 0, st>>>(h->p, h->scratch, h->cap, B, in);
+  h->launches[0]++;
+  const unsigned gs = (unsigned)((B + kSolveThreads - 1) / kSolveThreads);
+  ttmpc_solve_kernel<<<gs, kSolveThreads, 0, st>>>(h->p, h->scratch, h->cap, B, so);
+  h->launches[1]++;
+  if (z_out) {
+    ttmpc_unpack_kernel<<<gp, kPackThreads, 0, st>>>(h->p, h->scratch, h->cap, B, z_out);
+    h->launches[2]++;
+  }
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "kernel launch", ce);
+  return TTMPC_OK;
+}
+
+// host-pointer path: stage everything through one device buffer
+struct StagePlan {
+  size_t off_x, off_rs, off_ru, off_zw, off_k, off_ts, off_tu, off_z, off_u0, off_obj, off_kkt, off_it, off_st, total;
+};
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int solve_any(ttmpc_handle* h, int64_t B, const double* x_init, const double* ref_states, const double* ref_inputs,
+                     const int32_t* k_index, const double* traj_states, const double* traj_inputs, int32_t T,
+                     const double* z_warm, double* z_out, double* u0_out, double* obj_out, double* kkt_out,
+                     int32_t* iters_out, int32_t* status_out, void* stream) {
+  if (!h) return TTMPC_E_INVAL;
+  h->err[0] = 0;
+  if (B < 0 || !x_init) return set_err(h, TTMPC_E_INVAL, "bad batch arguments", cudaSuccess);
+  const bool shared = (ref_states == nullptr);
+  if (shared && (!k_index || !traj_states || !traj_inputs || T < 1)) return set_err(h, TTMPC_E_INVAL, "bad trajectory arguments", cudaSuccess);
+  if (!shared && !ref_inputs) return set_err(h, TTMPC_E_INVAL, "ref_inputs is null", cudaSuccess);
+  if (B == 0) return TTMPC_OK;
+  if (cudaSetDevice(h->device) != cudaSuccess) return set_err(h, TTMPC_E_NODEV, "cudaSetDevice", cudaGetLastError());
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = h->p.N;
+  const size_t nz = 8 * (size_t)N + 6;
+  const bool host = (h->cfg.flags & TTMPC_FLAG_HOST_POINTERS) != 0;
+  if (!host) {
+    PackIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T};
+    SolveOut so{u0_out, obj_out, kkt_out, iters_out, status_out};
+    int rc = solve_device(h, B, in, z_out, so, st);
+    if (rc) return rc;
+    if (h->cfg.flags & TTMPC_FLAG_SYNC) {
+      cudaError_t ce = cudaStreamSynchronize(st);
+      if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "stream synchronize", ce);
+    }
+    return TTMPC_OK;
+  }
+  // ---- host pointers
+  StagePlan pl;
+  size_t o = 0;
+  pl.off_x = o; o += al((size_t)B * NX * 8);
+  pl.off_rs = o; o += shared ? 0 : al((size_t)B * (N + 1) * NX * 8);
+  pl.off_ru = o; o += shared ? 0 : al((size_t)B * N * NU * 8);
+  pl.off_zw = o; o += z_warm ? al((size_t)B * nz * 8) : 0;
+  pl.off_k = o; o += shared ? al((size_t)B * 4) : 0;
+  pl.off_ts = o; o += shared ? al((size_t)(T + 1) * NX * 8) : 0;
+  pl.off_tu = o; o += shared ? al((size_t)T * NU * 8) : 0;
+  pl.off_z = o; o += al((size_t)B * nz * 8);
+  pl.off_u0 = o; o += al((size_t)B * 2 * 8);
+  pl.off_obj = o; o += al((size_t)B * 8);
+  pl.off_kkt = o; o += al((size_t)B * 3 * 8);
+  pl.off_it = o; o += al((size_t)B * 4);
+  pl.off_st = o; o += al((size_t)B * 4);
+  pl.total = o;
+  if (pl.total > h->stage_bytes) {
+    if (h->stage) cudaFree(h->stage);
+    h->stage = nullptr;
+    h->stage_bytes = 0;
+    cudaError_t ce = cudaMalloc(&h->stage, pl.total);
+    if (ce != cudaSuccess) return set_err(h, TTMPC_E_NOMEM, "staging cudaMalloc", ce);
+    h->stage_bytes = pl.total;
+  }
+  char* d = (char*)h->stage;
+#define H2D(off, src, bytes) cudaMemcpyAsync(d + (off), (src), (bytes), cudaMemcpyHostToDevice, st)
+#define D2H(dst, off, bytes) cudaMemcpyAsync((dst), d + (off), (bytes), cudaMemcpyDeviceToHost, st)
+  H2D(pl.off_x, x_init, (size_t)B * NX * 8);
+  if (!shared) {
+    H2D(pl.off_rs, ref_states, (size_t)B * (N + 1) * NX * 8);
+    H2D(pl.off_ru, ref_inputs, (size_t)B * N * NU * 8);
+  } else {
+    H2D(pl.off_k, k_index, (size_t)B * 4);
+    H2D(pl.off_ts, traj_states, (size_t)(T + 1) * NX * 8);
+    H2D(pl.off_tu, traj_inputs, (size_t)T * NU * 8);
+  }
+  if (z_warm) H2D(pl.off_zw, z_warm, (size_t)B * nz * 8);
+  PackIn in{(const double*)(d + pl.off_x),
+            shared ? nullptr : (const double*)(d + pl.off_rs),
+            shared ? nullptr : (const double*)(d + pl.off_ru),
+            z_warm ? (const double*)(d + pl.off_zw) : nullptr,
+            shared ? (const int32_t*)(d + pl.off_k) : nullptr,
+            shared ? (const double*)(d + pl.off_ts) : nullptr,
+            shared ? (const double*)(d + pl.off_tu) : nullptr,
+            T};
+  SolveOut so{(double*)(d + pl.off_u0), (double*)(d + pl.off_obj), (double*)(d + pl.off_kkt), (int32_t*)(d + pl.off_it),
+              (int32_t*)(d + pl.off_st)};
+  int rc = solve_device(h, B, in, z_out ? (double*)(d + pl.off_z) : nullptr, so, st);
+  if (rc) return rc;
+  if (z_out) D2H(z_out, pl.off_z, (size_t)B * nz * 8);
+  if (u0_out) D2H(u0_out, pl.off_u0, (size_t)B * 2 * 8);
+  if (obj_out) D2H(obj_out, pl.off_obj, (size_t)B * 8);
+  if (kkt_out) D2H(kkt_out, pl.off_kkt, (size_t)B * 3 * 8);
+  if (iters_out) D2H(iters_out, pl.off_it, (size_t)B * 4);
+  if (status_out) D2H(status_out, pl.off_st, (size_t)B * 4);
+#undef H2D
+#undef D2H
+  cudaError_t ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "host-pointer solve", ce);
+  return TTMPC_OK;
+}
+
+int ttmpc_solve_batch(ttmpc_handle* h, int64_t B, const double* x_init, const double* ref_states, const double* ref_inputs,
+                      const double* z_warm, double* z_out, double* u0_out, double* obj_out, double* kkt_out,
+                      int32_t* iters_out, int32_t* status_out, void* cuda_stream) {
+  if (h && !ref_states) return set_err(h, TTMPC_E_INVAL, "ref_states is null", cudaSuccess);
+  return solve_any(h, B, x_init, ref_states, ref_inputs, nullptr, nullptr, nullptr, 0, z_warm, z_out, u0_out, obj_out,
+                   kkt_out, iters_out, status_out, cuda_stream);
+}
+
+int ttmpc_solve_batch_shared(ttmpc_handle* h, int64_t B, const double* x_init, const int32_t* k_index,
+                             const double* traj_states, const double* traj_inputs, int32_t T, const double* z_warm,
+                             double* z_out, double* u0_out, double* obj_out, double* kkt_out, int32_t* iters_out,
+                             int32_t* status_out, void* cuda_stream) {
+  return solve_any(h, B, x_init, nullptr, nullptr, k_index, traj_states, traj_inputs, T, z_warm, z_out, u0_out, obj_out,
+                   kkt_out, iters_out, status_out, cuda_stream);
+}
+
+// The two helpers below take device pointers unless the handle was created with TTMPC_FLAG_HOST_POINTERS.
+static int with_staging(ttmpc_handle* h, size_t bytes) {
+  if (bytes > h->stage_bytes) {
+    if (h->stage) cudaFree(h->stage);
+    h->stage = nullptr;
+    h->stage_bytes = 0;
+    cudaError_t ce = cudaMalloc(&h->stage, bytes);
+    if (ce != cudaSuccess) return set_err(h, TTMPC_E_NOMEM, "staging cudaMalloc", ce);
+    h->stage_bytes = bytes;
+  }
+  return TTMPC_OK;
+}
+
+int ttmpc_shift_warm_start(ttmpc_handle* h, int64_t B, const double* z, double* z_shift, int32_t mode, void* cuda_stream) {
+  if (!h || B < 0 || !z || !z_shift || (mode != 0 && mode != 1)) return h ? set_err(h, TTMPC_E_INVAL, "bad shift arguments", cudaSuccess) : TTMPC_E_INVAL;
+  if (B == 0) return TTMPC_OK;
+  if (cudaSetDevice(h->device) != cudaSuccess) return set_err(h, TTMPC_E_NODEV, "cudaSetDevice", cudaGetLastError());
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int N = h->p.N;
+  const size_t bytes = (size_t)B * (8 * (size_t)N + 6) * 8;
+  const bool host = (h->cfg.flags & TTMPC_FLAG_HOST_POINTERS) != 0;
+  const double* zi = z;
+  double* zo = z_shift;
+  if (host) {
+    int rc = with_staging(h, 2 * al(bytes));
+    if (rc) return rc;
+    zi = (const double*)h->stage;
+    zo = (double*)((char*)h->stage + al(bytes));
+    cudaMemcpyAsync((void*)zi, z, bytes, cudaMemcpyHostToDevice, st);
+  }
+  const long long total = (long long)B * (8LL * N + 6);
+  const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  ttmpc_shift_kernel<<<grid, 256, 0, st>>>(N, B, zi, zo, mode);
+  h->launches[3]++;
+  if (host) cudaMemcpyAsync(z_shift, zo, bytes, cudaMemcpyDeviceToHost, st);
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess && (host || (h->cfg.flags & TTMPC_FLAG_SYNC))) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "shift", ce);
+  return TTMPC_OK;
+}
+
+int ttmpc_plant_step(ttmpc_handle* h, int64_t B, const double* q, const double* u, const double* disturb,
+                     const double* noise, double noise_scale, double* q_next, void* cuda_stream) {
+  if (!h || B < 0 || !q || !u || !q_next) return h ? set_err(h, TTMPC_E_INVAL, "bad plant arguments", cudaSuccess) : TTMPC_E_INVAL;
+  if (B == 0) return TTMPC_OK;
+  if (cudaSetDevice(h->device) != cudaSuccess) return set_err(h, TTMPC_E_NODEV, "cudaSetDevice", cudaGetLastError());
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const bool host = (h->cfg.flags & TTMPC_FLAG_HOST_POINTERS) != 0;
+  const double *dq = q, *du = u, *dn = noise;
+  double* dy = q_next;
+  const size_t bq = (size_t)B * NX * 8, bu = (size_t)B * NU * 8;
+  if (host) {
+    int rc = with_staging(h, 3 * al(bq) + al(bu));
+    if (rc) return rc;
+    char* d = (char*)h->stage;
+    dq = (const double*)d;
+    du = (const double*)(d + al(bq));
+    dy = (double*)(d + al(bq) + al(bu));
+    cudaMemcpyAsync((void*)dq, q, bq, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync((void*)du, u, bu, cudaMemcpyHostToDevice, st);
+    if (noise) {
+      dn = (const double*)(d + 2 * al(bq) + al(bu));
+      cudaMemcpyAsync((void*)dn, noise, bq, cudaMemcpyHostToDevice, st);
+    }
+  }
+  // disturb is always a HOST array of 4 doubles (configuration, not data)
+  const int has = disturb != nullptr;
+  ttmpc_plant_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(h->p, B, dq, du, has, has ? disturb[0] : 1.0, has ? disturb[1] : 1.0,
+                                                               has ? disturb[2] : 0.0, has ? disturb[3] : 0.0, dn, noise_scale, dy);
+  h->launches[4]++;
+  if (host) cudaMemcpyAsync(q_next, dy, bq, cudaMemcpyDeviceToHost, st);
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess && (host || (h->cfg.flags & TTMPC_FLAG_SYNC))) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "plant step", ce);
+  return TTMPC_OK;
+}
+
+double ttmpc_measure_fp64_peak(ttmpc_handle* h, void* cuda_stream) {
+  if (!h) return (double)TTMPC_E_INVAL;
+  if (cudaSetDevice(h->device) != cudaSuccess) return (double)TTMPC_E_NODEV;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  double* dout = nullptr;
+  if (cudaMalloc(&dout, 8) != cudaSuccess) return (double)TTMPC_E_NOMEM;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = sms * 8;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0, st);
+    ttmpc_dfma_kernel<<<blocks, 256, 0, st>>>(dout, 0.999999, 1e-9);
+    h->launches[5]++;
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 2.0 * (double)blocks * 256.0 * kDfmaIters * kDfmaChains;
+    if (rep > 0 && ms > 0.f) best = fmax(best, flop / (ms * 1e-3) * 1e-9);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dout);
+  if (cudaGetLastError() != cudaSuccess) return (double)TTMPC_E_CUDA;
+  return best;
+}
+
+}  // extern "C"

@@ -1,0 +1,237 @@
+"""`BatchSolver`: Python front end of the C ABI (include/ttmpc.h) -- the new batched driver surface.
+
+One instance = one CUDA device.  Inputs may be
+
+* **torch CUDA tensors** (float64, contiguous): zero-copy, pointers go straight to the kernels and the call
+  is asynchronous on the current torch stream; outputs are torch tensors on the same device;
+* **numpy arrays**: the library stages them through its own device buffer (host-pointer mode, the path the
+  B=1 shim classes use); outputs are numpy arrays; the call is synchronous.
+
+Array layouts are the reference's (stage-major): ``x_init [B,6]``, ``ref_states [B,N+1,6]``,
+``ref_inputs [B,N,2]``, ``z [B,8N+6]`` (trajectory_planning.py:38-60).  There is no CPU compute path here.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .config import FLAG_HOST_POINTERS, Config
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class BatchSolver:
+    def __init__(self, cfg: Config, device: int = 0):
+        self.cfg = cfg.copy()
+        self.device = int(device)
+        self._L = _lib.load()
+        self._h = {}  # flags -> handle
+        self._handle(0)  # fail early and loudly when no CUDA device is usable
+
+    # ------------------------------------------------------------------ handles
+    def _handle(self, flags: int):
+        h = self._h.get(flags)
+        if h is None:
+            c = self.cfg.copy()
+            c.flags = flags
+            h = ctypes.c_void_p()
+            rc = self._L.ttmpc_create(ctypes.byref(c), self.device, ctypes.byref(h))
+            if rc == _lib.E_NODEV:
+                raise _lib.TTMPCError(
+                    f"ttmpc_create: no usable CUDA device {self.device} (rc={rc}); this solver has no CPU fallback"
+                )
+            if rc != 0:
+                raise _lib.TTMPCError(f"ttmpc_create failed (rc={rc}): invalid configuration")
+            self._h[flags] = h
+        return h
+
+    def close(self):
+        for h in self._h.values():
+            self._L.ttmpc_destroy(h)
+        self._h = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, h, rc: int, what: str):
+        if rc != 0:
+            msg = self._L.ttmpc_last_error(h)
+            raise _lib.TTMPCError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+    # ------------------------------------------------------------------ accounting
+    def launch_count(self) -> int:
+        return int(sum(self._L.ttmpc_launch_count(h) for h in self._h.values()))
+
+    def kernel_launches(self) -> dict:
+        out = {}
+        for h in self._h.values():
+            i = 0
+            while True:
+                n = ctypes.c_int64()
+                name = self._L.ttmpc_kernel_name(h, i, ctypes.byref(n))
+                if not name:
+                    break
+                out[name.decode()] = out.get(name.decode(), 0) + n.value
+                i += 1
+        return out
+
+    def measure_fp64_peak(self) -> float:
+        """Non-tensor FP64 FMA peak of this device in GFLOP/s (roofline denominator)."""
+        v = self._L.ttmpc_measure_fp64_peak(self._handle(0), None)
+        if v < 0:
+            raise _lib.TTMPCError(f"ttmpc_measure_fp64_peak failed ({v})")
+        return float(v)
+
+    # ------------------------------------------------------------------ solve
+    def solve(self, x_init, ref_states, ref_inputs, z_warm=None, want_z: bool = True, stream=None) -> dict:
+        """Solve B problems with per-problem reference windows (MPCTrackingControl.solve semantics)."""
+        return self._solve(x_init, ref_states, ref_inputs, None, None, None, z_warm, want_z, stream)
+
+    def solve_shared(self, x_init, k_index, traj_states, traj_inputs, z_warm=None, want_z: bool = True, stream=None) -> dict:
+        """All problems track one trajectory ``traj_states [T+1,6]``, ``traj_inputs [T,2]``; problem i uses the
+        window starting at ``k_index[i]`` with the padding rules of simulation.py:485-499."""
+        return self._solve(x_init, None, None, k_index, traj_states, traj_inputs, z_warm, want_z, stream)
+
+    def _solve(self, x_init, ref_states, ref_inputs, k_index, traj_states, traj_inputs, z_warm, want_z, stream):
+        N = self.cfg.horizon
+        nz = 8 * N + 6
+        shared = ref_states is None
+        if _is_torch(x_init):
+            import torch
+
+            dev = x_init.device
+            assert dev.type == "cuda" and dev.index == self.device, "tensors must live on the solver's device"
+
+            def chk(t, shape, dtype=torch.float64):
+                assert t.dtype == dtype and t.is_contiguous() and t.device == dev and tuple(t.shape) == shape, (
+                    f"expected contiguous {dtype} tensor of shape {shape} on {dev}, got {t.dtype} {tuple(t.shape)}")
+                return t.data_ptr()
+
+            B = x_init.shape[0]
+            px = chk(x_init, (B, 6))
+            if shared:
+                T = traj_inputs.shape[0]
+                pk = chk(k_index, (B,), torch.int32)
+                pts, ptu = chk(traj_states, (T + 1, 6)), chk(traj_inputs, (T, 2))
+            else:
+                prs, pru = chk(ref_states, (B, N + 1, 6)), chk(ref_inputs, (B, N, 2))
+            pzw = chk(z_warm, (B, nz)) if z_warm is not None else None
+            out = dict(
+                z=torch.empty((B, nz), dtype=torch.float64, device=dev) if want_z else None,
+                u0=torch.empty((B, 2), dtype=torch.float64, device=dev),
+                obj=torch.empty(B, dtype=torch.float64, device=dev),
+                kkt=torch.empty((B, 3), dtype=torch.float64, device=dev),
+                iters=torch.empty(B, dtype=torch.int32, device=dev),
+                status=torch.empty(B, dtype=torch.int32, device=dev),
+            )
+            ptr = lambda t: None if t is None else t.data_ptr()
+            if stream is None:
+                stream = torch.cuda.current_stream(dev).cuda_stream
+            h = self._handle(0)
+        else:
+            x_init = np.ascontiguousarray(x_init, dtype=np.float64).reshape(-1, 6)
+            B = x_init.shape[0]
+            px = x_init.ctypes.data
+            keep = [x_init]
+            if shared:
+                traj_states = np.ascontiguousarray(traj_states, dtype=np.float64)
+                traj_inputs = np.ascontiguousarray(traj_inputs, dtype=np.float64)
+                k_index = np.ascontiguousarray(k_index, dtype=np.int32).reshape(B)
+                T = traj_inputs.shape[0]
+                assert traj_states.shape == (T + 1, 6) and traj_inputs.shape == (T, 2)
+                pk, pts, ptu = k_index.ctypes.data, traj_states.ctypes.data, traj_inputs.ctypes.data
+                keep += [traj_states, traj_inputs, k_index]
+            else:
+                ref_states = np.ascontiguousarray(ref_states, dtype=np.float64).reshape(B, N + 1, 6)
+                ref_inputs = np.ascontiguousarray(ref_inputs, dtype=np.float64).reshape(B, N, 2)
+                prs, pru = ref_states.ctypes.data, ref_inputs.ctypes.data
+                keep += [ref_states, ref_inputs]
+            pzw = None
+            if z_warm is not None:
+                z_warm = np.ascontiguousarray(z_warm, dtype=np.float64).reshape(B, nz)
+                pzw = z_warm.ctypes.data
+                keep.append(z_warm)
+            out = dict(
+                z=np.empty((B, nz)) if want_z else None,
+                u0=np.empty((B, 2)),
+                obj=np.empty(B),
+                kkt=np.empty((B, 3)),
+                iters=np.empty(B, dtype=np.int32),
+                status=np.empty(B, dtype=np.int32),
+            )
+            ptr = lambda a: None if a is None else a.ctypes.data
+            stream = None
+            h = self._handle(FLAG_HOST_POINTERS)
+        if shared:
+            rc = self._L.ttmpc_solve_batch_shared(
+                h, B, px, pk, pts, ptu, T, pzw, ptr(out["z"]), ptr(out["u0"]), ptr(out["obj"]), ptr(out["kkt"]),
+                ptr(out["iters"]), ptr(out["status"]), stream)
+        else:
+            rc = self._L.ttmpc_solve_batch(
+                h, B, px, prs, pru, pzw, ptr(out["z"]), ptr(out["u0"]), ptr(out["obj"]), ptr(out["kkt"]),
+                ptr(out["iters"]), ptr(out["status"]), stream)
+        self._check(h, rc, "ttmpc_solve_batch")
+        return out
+
+    # ------------------------------------------------------------------ helpers of the closed-loop drivers
+    def shift_warm_start(self, z, reference_bug: bool = False, stream=None):
+        """``TruckTrailerNMPC._shift_solution`` (mpc_control_nmpc.py:69-88) for a batch ``z [B,8N+6]``."""
+        nz = 8 * self.cfg.horizon + 6
+        if _is_torch(z):
+            import torch
+
+            assert z.dtype == torch.float64 and z.is_contiguous() and z.shape[-1] == nz
+            out = torch.empty_like(z)
+            if stream is None:
+                stream = torch.cuda.current_stream(z.device).cuda_stream
+            h = self._handle(0)
+            rc = self._L.ttmpc_shift_warm_start(h, z.numel() // nz, z.data_ptr(), out.data_ptr(), int(reference_bug), stream)
+        else:
+            z = np.ascontiguousarray(z, dtype=np.float64)
+            out = np.empty_like(z)
+            h = self._handle(FLAG_HOST_POINTERS)
+            rc = self._L.ttmpc_shift_warm_start(h, z.size // nz, z.ctypes.data, out.ctypes.data, int(reference_bug), None)
+        self._check(h, rc, "ttmpc_shift_warm_start")
+        return out
+
+    def plant_step(self, q, u, disturb: Optional[dict] = None, noise=None, noise_scale: float = 0.0, stream=None):
+        """One Euler plant step ``update(q,u)`` of simulation.py:167-199 for ``q [B,6]``, ``u [B,2]``.
+
+        ``disturb``: dict with keys friction_coeff, slippage_coeff, lateral_slip_gain, slip_angle_max
+        (DISTURBANCE_PARAMS of simulation.py:26-32) or None for the nominal plant.
+        """
+        d = None
+        if disturb is not None:
+            d = (ctypes.c_double * 4)(
+                disturb.get("friction_coeff", 1.0), disturb.get("slippage_coeff", 1.0),
+                disturb.get("lateral_slip_gain", 0.0), disturb.get("slip_angle_max", 0.0))
+        dptr = ctypes.cast(d, ctypes.c_void_p) if d is not None else None
+        if _is_torch(q):
+            import torch
+
+            assert q.dtype == torch.float64 and q.is_contiguous() and u.is_contiguous()
+            out = torch.empty_like(q)
+            if stream is None:
+                stream = torch.cuda.current_stream(q.device).cuda_stream
+            h = self._handle(0)
+            rc = self._L.ttmpc_plant_step(h, q.shape[0], q.data_ptr(), u.data_ptr(), dptr,
+                                          None if noise is None else noise.data_ptr(), noise_scale, out.data_ptr(), stream)
+        else:
+            q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, 6)
+            u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1, 2)
+            if noise is not None:
+                noise = np.ascontiguousarray(noise, dtype=np.float64).reshape(-1, 6)
+            out = np.empty_like(q)
+            h = self._handle(FLAG_HOST_POINTERS)
+            rc = self._L.ttmpc_plant_step(h, q.shape[0], q.ctypes.data, u.ctypes.data, dptr,
+                                          None if noise is None else noise.ctypes.data, noise_scale, out.ctypes.data, None)
+        self._check(h, rc, "ttmpc_plant_step")
+        return out

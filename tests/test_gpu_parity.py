@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libttmpc.so), against the CPU oracle
+on the same seeded inputs and against the committed golden fixtures, plus size-independent properties at
+the full BASELINE sizes.  Tolerances are the north star's (tests/parity.py): u0 1e-4 abs, objective 1e-6
+rel, constraint violation 1e-6."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from parity import U0_ABS_TOL, VIOL_TOL, assert_parity
+from test_golden_oracle import GOLD, load_golden
+
+from car_trailer_mpc_b200 import nmpc_preset, tracking_preset
+from car_trailer_mpc_b200 import problem as pb
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def make_solver(cfg):
+    from car_trailer_mpc_b200 import BatchSolver
+    return BatchSolver(cfg, 0)
+
+
+def to_np(r):
+    return {k: (None if v is None else (v.cpu().numpy() if hasattr(v, "cpu") else v)) for k, v in r.items()}
+
+
+# ----------------------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "*.npz"))), ids=os.path.basename)
+def test_gpu_matches_golden(path, torch_cuda):
+    cfg, g = load_golden(path)
+    s = make_solver(cfg)
+    r = s.solve(g["x_init"], g["ref_states"], g["ref_inputs"], z_warm=g.get("z_warm"))
+    if cfg.tol < 1e-6:
+        assert_parity(cfg, r, g, g["x_init"], label=os.path.basename(path))
+        assert (r["iters"] == g["iters"]).mean() >= 0.9
+    else:
+        assert np.array_equal(r["status"], g["status"])
+        assert np.abs(r["u0"] - g["u0"]).max() < 1e-6
+
+
+# ----------------------------------------------------------------------------- config 2: B=4096, N=40
+@pytest.mark.parametrize("sigma_name", ["narrow", "wide"])
+def test_config2_4096_vs_oracle(sigma_name, torch_cuda):
+    from oracle import oracle
+    cfg = tracking_preset(40); cfg.max_iter = 200
+    sc = pb.make_scenarios(cfg, 4096, sigma=pb.SIGMA_NARROW if sigma_name == "narrow" else pb.SIGMA_WIDE)
+    ref = oracle.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs, nthreads=os.cpu_count() or 1)
+    s = make_solver(cfg)
+    # device-resident (torch, zero-copy) path
+    t = torch_cuda
+    dev = t.device("cuda:0")
+    r = s.solve(t.from_numpy(sc.x_init).to(dev), t.from_numpy(sc.ref_states).to(dev), t.from_numpy(sc.ref_inputs).to(dev))
+    t.cuda.synchronize()
+    r = to_np(r)
+    assert (ref["status"] == 0).all()
+    du0, drel = assert_parity(cfg, r, ref, sc.x_init, label=sigma_name)
+    assert (r["iters"] == ref["iters"]).mean() > 0.98
+    # host-pointer path gives bit-identical results
+    rh = s.solve(sc.x_init, sc.ref_states, sc.ref_inputs)
+    assert np.array_equal(rh["z"], r["z"]) and np.array_equal(rh["status"], r["status"]) and np.array_equal(rh["obj"], r["obj"])
+    # the reported KKT residuals are honest: recompute the constraint violation from z
+    X, U = pb.unpack_z(r["z"], 40)
+    viol = np.abs(pb.dynamics_defect(cfg, X, U)).reshape(4096, -1).max(1)
+    assert np.abs(viol - r["kkt"][:, 1]).max() < 1e-12
+    assert (r["kkt"][:, 0] <= 1e-6).all() and (r["kkt"][:, 2] <= 1e-7).all()
+    assert np.abs(pb.objective(cfg, X, U, sc.ref_states, sc.ref_inputs) - r["obj"]).max() < 1e-10
+
+
+# ----------------------------------------------------------------------------- config 3: horizon sweep
+@pytest.mark.parametrize("N", [10, 20, 30, 50, 60, 80, 100, 128])
+def test_horizon_sweep_vs_oracle(N, torch_cuda):
+    from oracle import oracle
+    cfg = tracking_preset(N); cfg.max_iter = 200
+    sc = pb.make_scenarios(cfg, 257, seed=1000 + N)   # ragged: not a multiple of the warp / CTA size
+    ref = oracle.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs, nthreads=os.cpu_count() or 1)
+    r = make_solver(cfg).solve(sc.x_init, sc.ref_states, sc.ref_inputs)
+    assert_parity(cfg, r, ref, sc.x_init, label=f"N={N}")
+
+
+# ----------------------------------------------------------------------------- shared-trajectory mode
+def test_shared_trajectory_mode_equals_window_mode(traj, torch_cuda):
+    S, U = traj
+    cfg = tracking_preset(40)
+    rng = np.random.default_rng(5)
+    k = np.concatenate([rng.integers(0, 460, size=500), [0, 360, 361, 399, 400, 401, 1000]]).astype(np.int32)
+    xs, us = pb.windows_batch(S, U, k, 40)
+    x = xs[:, 0, :] + rng.normal(0, 0.02, size=(len(k), 6))
+    s = make_solver(cfg)
+    a = s.solve(x, xs, us)
+    b = s.solve_shared(x, k, S, U)
+    for key in ("z", "u0", "obj", "iters", "status"):
+        assert np.array_equal(a[key], b[key]), key
+
+
+# ----------------------------------------------------------------------------- presets / warm start / weights
+def test_nmpc_preset_and_warm_start(torch_cuda):
+    from oracle import oracle
+    cfg = nmpc_preset(30)
+    sc = pb.make_scenarios(cfg, 300, seed=77, families=False)
+    s = make_solver(cfg)
+    ref = oracle.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs, nthreads=4)
+    r = s.solve(sc.x_init, sc.ref_states, sc.ref_inputs)
+    assert np.array_equal(r["status"], ref["status"])
+    assert np.abs(r["u0"] - ref["u0"]).max() < 1e-6     # same algorithm, same stopping iterate
+    # warm start with both shift flavours, device shift kernel vs host twin
+    for bug in (False, True):
+        zw = s.shift_warm_start(r["z"], reference_bug=bug)
+        assert np.array_equal(zw, pb.shift_warm_start(r["z"], 30, reference_bug=bug))
+        refw = oracle.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs, z_warm=zw, nthreads=4)
+        rw = s.solve(sc.x_init, sc.ref_states, sc.ref_inputs, z_warm=zw)
+        assert np.array_equal(rw["status"], refw["status"])
+        assert np.abs(rw["u0"] - refw["u0"]).max() < 1e-6
+    # tight preset of the same problems: the loose solve is within ~1e-3 of the true minimiser
+    tight = tracking_preset(30); tight.set_weights(cfg.Qm(), cfg.Rm())
+    tight.set_bounds(cfg.x_lb[:], cfg.x_ub[:], cfg.u_lb[:], cfg.u_ub[:])
+    rt = make_solver(tight).solve(sc.x_init, sc.ref_states, sc.ref_inputs)
+    assert np.abs(rt["u0"] - r["u0"]).max() < 5e-2
+
+
+def test_general_dense_weights_and_bounds(torch_cuda):
+    from oracle import oracle
+    cfg = tracking_preset(25)
+    Q = np.diag([2.0, 1.0, 2.0, 3.0, 1.0, 0.5]); Q[0, 1] = Q[1, 0] = 0.3; Q[2, 5] = Q[5, 2] = -0.2
+    R = np.array([[5.0, 0.7], [0.7, 8.0]])
+    cfg.set_weights(Q, R)
+    # bound x,y too, drop the theta bounds, one-sided v: exercises the general bound masks
+    cfg.set_bounds([-200.0, -200.0, -np.inf, -1.0, -0.7, -np.inf], [200.0, 200.0, np.inf, 1.0, 0.7, 6.0], [-4.0, -1.0], [4.0, 1.0])
+    sc = pb.make_scenarios(cfg, 200, seed=21, families=False)
+    ref = oracle.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs, nthreads=4)
+    r = make_solver(cfg).solve(sc.x_init, sc.ref_states, sc.ref_inputs)
+    assert_parity(cfg, r, ref, sc.x_init)
+
+
+# ----------------------------------------------------------------------------- edge cases
+def test_edge_batches_and_infeasible_x0(torch_cuda):
+    from oracle import oracle
+    cfg = tracking_preset(40)
+    s = make_solver(cfg)
+    sc = pb.make_scenarios(cfg, 33, seed=3)
+    ref = oracle.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs)
+    full = s.solve(sc.x_init, sc.ref_states, sc.ref_inputs)
+    for B in (1, 2, 31, 32, 33):
+        r = s.solve(sc.x_init[:B], sc.ref_states[:B], sc.ref_inputs[:B])
+        for key in ("z", "u0", "obj", "iters", "status"):
+            assert np.array_equal(r[key], full[key][:B]), (B, key)   # independent problems: batch size must not matter
+    assert_parity(cfg, full, ref, sc.x_init)
+    e = s.solve(sc.x_init[:0], sc.ref_states[:0], sc.ref_inputs[:0])
+    assert e["z"].shape == (0, 326)
+    bad = sc.x_init.copy(); bad[5, 4] = 0.9; bad[7, 3] = -1.2      # phi / psi outside the box
+    rb = s.solve(bad, sc.ref_states, sc.ref_inputs)
+    refb = oracle.solve_batch(cfg, bad, sc.ref_states, sc.ref_inputs)
+    assert rb["status"][5] == 5 and rb["status"][7] == 5 and np.array_equal(rb["status"], refb["status"])
+    ok = np.ones(33, bool); ok[[5, 7]] = False
+    assert np.array_equal(rb["z"][ok], full["z"][ok])
+    want_none = s.solve(sc.x_init, sc.ref_states, sc.ref_inputs, want_z=False)
+    assert want_none["z"] is None and np.array_equal(want_none["u0"], full["u0"])
+
+
+# ----------------------------------------------------------------------------- full size, property based
+def test_full_size_65536_properties(torch_cuda):
+    t = torch_cuda
+    dev = t.device("cuda:0")
+    cfg = tracking_preset(40); cfg.max_iter = 200
+    B = 65536
+    sc = pb.make_scenarios(cfg, B)
+    s = make_solver(cfg)
+    x = t.from_numpy(sc.x_init).to(dev); xs = t.from_numpy(sc.ref_states).to(dev); us = t.from_numpy(sc.ref_inputs).to(dev)
+    r = to_np(s.solve(x, xs, us))
+    assert (r["status"] == 0).all()
+    X, U = pb.unpack_z(r["z"], 40)
+    assert np.abs(pb.dynamics_defect(cfg, X, U)).max() <= VIOL_TOL
+    assert np.array_equal(X[:, 0, :], sc.x_init)
+    assert (r["kkt"][:, 0] <= 1e-6).all() and (r["kkt"][:, 1] <= 1e-8).all() and (r["kkt"][:, 2] <= 1e-7).all()
+    assert (np.abs(X[:, 1:, 3]) <= np.pi / 3 + 2e-8).all() and (np.abs(X[:, 1:, 4]) <= np.pi / 4 + 2e-8).all()
+    assert (np.abs(U[:, :, 0]) <= 5 + 6e-8).all() and (np.abs(U[:, :, 1]) <= np.pi / 2 + 2e-8).all()
+    # permutation invariance: problems are independent, so any slot assignment gives the same bits
+    perm = np.random.default_rng(0).permutation(B)
+    pt = t.from_numpy(perm).to(dev)
+    rp = to_np(s.solve(x[pt].contiguous(), xs[pt].contiguous(), us[pt].contiguous(), want_z=False))
+    assert np.array_equal(rp["u0"], r["u0"][perm]) and np.array_equal(rp["iters"], r["iters"][perm])
+    # SE(2) invariance of the NLP: move problem + reference rigidly (x,y are unbounded; keep theta inside its box)
+    sub = np.nonzero(np.abs(sc.ref_states[:, :, 2]).max(1) < 2.0)[0][:4096]
+    d = 0.7
+    c_, s_ = np.cos(d), np.sin(d)
+    def move(a):
+        b = a.copy()
+        b[..., 0] = 5.0 + c_ * a[..., 0] - s_ * a[..., 1]
+        b[..., 1] = -9.0 + s_ * a[..., 0] + c_ * a[..., 1]
+        b[..., 2] = a[..., 2] + d
+        return b
+    rm = s.solve(move(sc.x_init[sub]), move(sc.ref_states[sub]), sc.ref_inputs[sub], want_z=False)
+    assert (rm["status"] == 0).all()
+    assert np.abs(rm["u0"] - r["u0"][sub]).max() <= U0_ABS_TOL
+    assert (np.abs(rm["obj"] - r["obj"][sub]) <= 1e-6 * np.maximum(1.0, np.abs(r["obj"][sub]))).all()
+    # oracle spot check on a random subsample of the full batch
+    from oracle import oracle
+    idx = np.random.default_rng(1).choice(B, 512, replace=False)
+    ref = oracle.solve_batch(cfg, sc.x_init[idx], sc.ref_states[idx], sc.ref_inputs[idx], nthreads=os.cpu_count() or 1)
+    sub_r = {k: (None if v is None else v[idx]) for k, v in r.items()}
+    assert_parity(cfg, sub_r, ref, sc.x_init[idx])
+
+
+# ----------------------------------------------------------------------------- shims and helpers
+def test_shim_classes_drop_in(traj, torch_cuda):
+    from oracle import oracle
+    from car_trailer_mpc_b200 import MPCTrackingControl, TruckTrailerModel, TruckTrailerNMPC
+    S, U = traj
+    N = 50
+    params = {"M": 0.15, "L1": 7.05, "L2": 12.45, "W1": 3.05, "W2": 2.95, "dt": 0.05, "horizon": N}
+    model = TruckTrailerModel(params)
+    Q = np.eye(6); R = 10 * np.eye(2)
+    sb = {"lb": [-np.inf, -np.inf, -np.pi, -np.pi / 3, -np.pi / 4, -10.0], "ub": [np.inf, np.inf, np.pi, np.pi / 3, np.pi / 4, 10.0]}
+    ib = {"lb": [-5, -np.pi / 2], "ub": [5, np.pi / 2]}
+    ctl = MPCTrackingControl(model, params, Q, R, sb, ib)
+    cfg = tracking_preset(N)
+    state = S[0].copy()
+    ref_s = np.zeros((6, N + 1)); ref_u = np.zeros((2, N))   # reused buffers, mutated in place like simulation.py:463-464
+    for step, k in enumerate(pb.time_indices(0.5, 0.05)):
+        xs, us = pb.window(S, U, int(k), N)
+        ref_s[:, :] = xs.T; ref_u[:, :] = us.T
+        states, inputs = ctl.solve(state, ref_s, ref_u)
+        assert states.shape == (6, N + 1) and inputs.shape == (2, N) and states.dtype == np.float64
+        ro = oracle.solve(cfg, state, xs, us)
+        assert ctl.last_status == 0 and ro["status"] == 0
+        assert np.abs(inputs[:, 0] - ro["u0"]).max() <= U0_ABS_TOL
+        assert np.array_equal(states[:, 0], state)
+        state = model.compute_next_state(state, inputs[:, 0])
+    if True:  # survey probe values, N=50 nominal closed loop from S[:,0]
+        states, inputs = ctl.solve(S[0], pb.window(S, U, 0, N)[0].T, pb.window(S, U, 0, N)[1].T)
+        assert np.abs(inputs[:, 0] - np.array([-4.968355, 1.499396])).max() < 2e-6
+    Qn = np.diag([1.0, 1.0, 2.0, 3.0, 1.0, 1.0]); Rn = np.diag([5.0, 8.0])
+    sbn = {"lb": [-np.inf, -np.inf, -np.pi, -np.pi / 3, -np.pi / 4, -8.0], "ub": [np.inf, np.inf, np.pi, np.pi / 3, np.pi / 4, 8.0]}
+    ibn = {"lb": [-4, -np.pi / 2], "ub": [4, np.pi / 2]}
+    p30 = dict(params, horizon=30)
+    nm = TruckTrailerNMPC(TruckTrailerModel(p30), p30, Qn, Rn, sbn, ibn, shift_reference_bug=True)
+    xs, us = pb.window(S, U, 0, 30)
+    a = nm.solve(S[0], xs.T, us.T)
+    assert a[0] is not None and nm._last_solution is not None
+    b = nm.solve(model.compute_next_state(S[0], a[1][:, 0]), pb.window(S, U, 1, 30)[0].T, pb.window(S, U, 1, 30)[1].T)
+    assert b[0] is not None
+    keep = nm._last_solution.copy()
+    bad = S[0].copy(); bad[4] = 1.2
+    assert nm.solve(bad, xs.T, us.T) == (None, None)            # failure: (None, None), warm start untouched
+    assert np.array_equal(nm._last_solution, keep)
+
+
+def test_plant_step_kernel_vs_oracle(torch_cuda):
+    from oracle import oracle
+    cfg = tracking_preset(40)
+    s = make_solver(cfg)
+    rng = np.random.default_rng(8)
+    q = rng.normal(size=(100, 6)) * np.array([10, 10, 1.0, 0.4, 0.3, 3.0]); u = rng.normal(size=(100, 2))
+    n = rng.normal(size=(100, 6))
+    dist = {"friction_coeff": 0.9, "slippage_coeff": 0.9, "lateral_slip_gain": 0.01, "slip_angle_max": 0.05}
+    for d, noise, sc_ in ((None, None, 0.0), (dist, None, 0.0), (dist, n, 0.05)):
+        got = s.plant_step(q, u, d, noise, sc_)
+        dl = None if d is None else [d["friction_coeff"], d["slippage_coeff"], d["lateral_slip_gain"], d["slip_angle_max"]]
+        exp = np.array([oracle.plant_step(cfg, q[i], u[i], dl, None if noise is None else noise[i], sc_) for i in range(100)])
+        assert np.abs(got - exp).max() < 1e-13

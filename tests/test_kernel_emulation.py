@@ -1,0 +1,61 @@
+"""The device solver core (csrc/ttmpc_core.cuh: fused backward sweep with costate recursion, structured
+Riccati, forward and trial sweeps), compiled for the host by tools/kernel_emu.cpp, must agree with the
+oracle -- two independently written implementations of the same algorithm.  Runs without a GPU."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import emu  # noqa: E402
+from parity import assert_parity  # noqa: E402
+
+from car_trailer_mpc_b200 import nmpc_preset, tracking_preset  # noqa: E402
+from car_trailer_mpc_b200 import problem as pb  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+
+def test_emulated_kernel_matches_oracle_narrow_and_wide():
+    cfg = tracking_preset(40); cfg.max_iter = 200
+    for sig in (pb.SIGMA_NARROW, pb.SIGMA_WIDE):
+        sc = pb.make_scenarios(cfg, 256, sigma=sig)
+        r0 = oracle.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs, nthreads=4)
+        r1 = emu.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs)
+        assert_parity(cfg, r1, r0, sc.x_init)
+        assert (r0["iters"] == r1["iters"]).mean() > 0.98
+
+
+def test_emulated_kernel_other_horizons_and_presets():
+    for cfg in (tracking_preset(10), tracking_preset(73), nmpc_preset(30)):
+        sc = pb.make_scenarios(cfg, 48, seed=5)
+        r0 = oracle.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs, nthreads=4)
+        r1 = emu.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs)
+        if cfg.tol < 1e-6:
+            assert_parity(cfg, r1, r0, sc.x_init)
+        else:  # tol 1e-3: both stop within ~1e-3 of the KKT point; compare loosely
+            assert np.array_equal(r0["status"], r1["status"])
+            assert np.abs(r0["u0"] - r1["u0"]).max() < 1e-6
+
+
+def test_emulated_kernel_warm_start_and_general_weights():
+    cfg = nmpc_preset(30)
+    Q = np.diag([1.0, 1.0, 2.0, 3.0, 1.0, 1.0]); Q[0, 1] = Q[1, 0] = 0.3; Q[2, 5] = Q[5, 2] = -0.2
+    R = np.array([[5.0, 0.7], [0.7, 8.0]])
+    cfg.set_weights(Q, R); cfg.tol = 1e-8; cfg.acceptable_tol = 1e-6; cfg.acceptable_iter = 15
+    sc = pb.make_scenarios(cfg, 32, seed=9, families=False)
+    r0 = oracle.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs)
+    zw = pb.shift_warm_start(r0["z"], 30, reference_bug=True)
+    r0w = oracle.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs, z_warm=zw)
+    r1w = emu.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs, z_warm=zw)
+    assert_parity(cfg, r1w, r0w, sc.x_init)
+    assert_parity(cfg, r1w, r0, sc.x_init)   # warm and cold starts reach the same minimiser
+
+
+def test_infeasible_x0_policy():
+    cfg = tracking_preset(20)
+    sc = pb.make_scenarios(cfg, 4, seed=2, families=False)
+    sc.x_init[1, 4] = 0.9   # phi beyond pi/4: reference NLP infeasible
+    r0 = oracle.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs)
+    r1 = emu.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs)
+    assert r0["status"][1] == 5 and r1["status"][1] == 5
+    assert np.array_equal(r0["status"], r1["status"])
