@@ -1,14 +1,11 @@
 // ttmpc.cu -- CUDA kernels (sm_100a) and the C ABI of include/ttmpc.h.
 //
 // Kernels:
-//   ttmpc_pack_kernel    AoS problem data (the reference's p / z layouts) -> slot-interleaved scratch,
-//                        transposed through shared memory so both sides are coalesced; also builds the
-//                        starting point (mpc_control.py:58-65 cold start or caller's warm start, pushed
-//                        into the interior like Ipopt does) and, in shared-trajectory mode, the window of
-//                        simulation.py:485-499.
-//   ttmpc_solve_kernel   the interior-point solve, one thread per problem (ttmpc_core.cuh).
-//   ttmpc_unpack_kernel  scratch -> z_out in the reference's decision-vector layout
-//                        (trajectory_planning.py:38-60).
+//   ttmpc_solve_kernel   the interior-point solve (ttmpc_core.cuh): persistent lanes, one problem per lane at
+//                        a time, work refill from a global queue.  Loading a problem (cold start of
+//                        mpc_control.py:58-65 or the caller's warm start, Ipopt-style push into the interior,
+//                        the window rules of simulation.py:485-499 in shared-trajectory mode) and writing
+//                        z_out in the reference's layout (trajectory_planning.py:38-60) happen inside it.
 //   ttmpc_shift_kernel   TruckTrailerNMPC._shift_solution (mpc_control_nmpc.py:69-88).
 //   ttmpc_plant_kernel   update()/f_dyn of the closed-loop drivers (simulation.py:34-48,167-199).
 //   ttmpc_dfma_kernel    FP64 FMA peak microbenchmark (roofline denominator).
@@ -28,105 +25,15 @@ using namespace ttmpc;
 namespace {
 
 constexpr int kSolveThreads = 128;
-constexpr int kTileSlots = 32;    // slots per CTA in pack/unpack
-constexpr int kTileStages = 8;    // stages per shared-memory tile
-constexpr int kPackThreads = 256;
-constexpr int kTileW = kTileStages * NW + 1;  // +1: odd stride, conflict-free transposition
+#ifndef TTMPC_MIN_BLOCKS
+#define TTMPC_MIN_BLOCKS 2
+#endif
 
 // ------------------------------------------------------------------------------------------------
-// pack: problem data -> scratch
-// ------------------------------------------------------------------------------------------------
-struct PackIn {
-  const double* x_init;      // [B][6]
-  const double* ref_states;  // [B][N+1][6] or null (shared mode)
-  const double* ref_inputs;  // [B][N][2]
-  const double* z_warm;      // [B][8N+6] or null
-  const int32_t* k_index;    // [B] (shared mode)
-  const double* traj_states; // [T+1][6]
-  const double* traj_inputs; // [T][2]
-  int T;
-};
-
-__global__ void __launch_bounds__(kPackThreads) ttmpc_pack_kernel(const __grid_constant__ Params p, double* __restrict__ scratch,
-                                                                 size_t cap, long long B, PackIn in) {
-  __shared__ double t_ref[kTileSlots][kTileW];
-  __shared__ double t_gs[kTileSlots][kTileW];
-  const int N = p.N;
-  const long long slot0 = (long long)blockIdx.x * kTileSlots;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = kPackThreads >> 5;
-  const long long nz = 8LL * N + 6;
-  const bool shared_mode = (in.ref_states == nullptr);
-
-  for (int k0 = 0; k0 <= N; k0 += kTileStages) {
-    const int ns = min(kTileStages, N + 1 - k0);  // stages in this tile
-    // ---- phase A: gather AoS -> tile (lanes run along the contiguous per-problem data)
-    for (int sl = warp; sl < kTileSlots; sl += nwarps) {
-      const long long b = slot0 + sl;
-      if (b >= B) continue;
-      if (!shared_mode) {
-        const double* rs = in.ref_states + b * (long long)(N + 1) * NX + (long long)k0 * NX;
-        for (int e = lane; e < ns * NX; e += 32) t_ref[sl][(e / NX) * NW + (e % NX)] = rs[e];
-        const double* ru = in.ref_inputs + b * (long long)N * NU + (long long)k0 * NU;
-        const int nu_e = min(ns, N - k0) * NU;
-        for (int e = lane; e < ns * NU; e += 32) t_ref[sl][(e / NU) * NW + NX + (e % NU)] = (e < nu_e) ? ru[e] : 0.0;
-      } else {
-        // window regimes of simulation.py:485-499 on the shared trajectory
-        const int kk = in.k_index[b], T = in.T;
-        for (int e = lane; e < ns * NW; e += 32) {
-          const int st = k0 + e / NW, j = e % NW;
-          double v;
-          if (j < NX) {
-            const int idx = (kk < T) ? min(kk + st, T) : T;
-            v = in.traj_states[(long long)idx * NX + j];
-          } else if (st >= N || kk >= T) {
-            v = 0.0;
-          } else {
-            v = in.traj_inputs[(long long)min(kk + st, T - 1) * NU + (j - NX)];
-          }
-          t_ref[sl][e] = v;
-        }
-      }
-      if (in.z_warm) {
-        const double* zw = in.z_warm + b * nz + (long long)k0 * NW;
-        const int ne = (int)min((long long)ns * NW, nz - (long long)k0 * NW);
-        for (int e = lane; e < ns * NW; e += 32) t_gs[sl][e] = (e < ne) ? zw[e] : 0.0;
-      }
-    }
-    __syncthreads();
-    // ---- phase B: tile -> scratch (lanes run along slots: 256 B coalesced rows)
-    const long long b = slot0 + lane;
-    if (b < B) {
-      for (int e = warp; e < ns * NW; e += nwarps) {
-        const int st = k0 + e / NW, j = e % NW;
-        if (j >= NX && st >= N) continue;  // no input at the terminal stage
-        const double r = t_ref[lane][e];
-        const double g = in.z_warm ? t_gs[lane][e] : r;
-        double w;
-        const bool hl = (j < NX) ? ((p.xhl >> j) & 1u) : ((p.uhl >> (j - NX)) & 1u);
-        const bool hu = (j < NX) ? ((p.xhu >> j) & 1u) : ((p.uhu >> (j - NX)) & 1u);
-        if (st == 0 && j < NX) {
-          w = in.x_init[b * NX + j];  // x_0 is data
-        } else {
-          const double lo = (j < NX) ? p.xl[j] : p.ul[j - NX];
-          const double up = (j < NX) ? p.xu[j] : p.uu[j - NX];
-          w = push_inside(g, lo, up, hl, hu);
-          if (hl) scratch[(size_t)(p.oZL + st * wZ + j) * cap + b] = 1.0;
-          if (hu) scratch[(size_t)(p.oZU + st * wZ + j) * cap + b] = 1.0;
-        }
-        scratch[(size_t)(p.oW + st * wW + j) * cap + b] = w;
-        scratch[(size_t)(p.oREF + st * wREF + j) * cap + b] = r;
-        if (j < NX) scratch[(size_t)(p.oLAM + st * wLAM + j) * cap + b] = 0.0;
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// solve
+// solve: persistent lanes with per-lane work refill
 // ------------------------------------------------------------------------------------------------
 struct SolveOut {
+  double* z;       // [B][8N+6]
   double* u0;      // [B][2]
   double* obj;     // [B]
   double* kkt;     // [B][3]
@@ -134,63 +41,58 @@ struct SolveOut {
   int32_t* status; // [B]
 };
 
-__global__ void __launch_bounds__(kSolveThreads) ttmpc_solve_kernel(const __grid_constant__ Params p, double* __restrict__ scratch,
-                                                                   size_t cap, long long B, SolveOut out) {
-  const long long b = (long long)blockIdx.x * kSolveThreads + threadIdx.x;
-  if (b >= B) return;
-  Slot s{scratch, cap, (size_t)b};
-  bool bad = false;
-#pragma unroll
-  for (int j = 0; j < NX; j++) {
-    const double x = s.ld(p.oW + j);
-    if (((p.xhl >> j) & 1u) && x < p.xl[j]) bad = true;
-    if (((p.xhu >> j) & 1u) && x > p.xu[j]) bad = true;
-  }
-  Result r;
-  solve_slot(p, s, bad, r);
-  if (out.u0) {
-    out.u0[b * 2 + 0] = r.u0a;
-    out.u0[b * 2 + 1] = r.u0w;
-  }
-  if (out.obj) out.obj[b] = r.obj;
-  if (out.kkt) {
-    out.kkt[b * 3 + 0] = r.dual_inf;
-    out.kkt[b * 3 + 1] = r.constr_viol;
-    out.kkt[b * 3 + 2] = r.compl_inf;
-  }
-  if (out.iters) out.iters[b] = r.iters;
-  if (out.status) out.status[b] = r.status;
-}
-
-// ------------------------------------------------------------------------------------------------
-// unpack: scratch -> z_out (reference decision-vector layout)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPackThreads) ttmpc_unpack_kernel(const __grid_constant__ Params p, const double* __restrict__ scratch,
-                                                                   size_t cap, long long B, double* __restrict__ z_out) {
-  __shared__ double t[kTileSlots][kTileW];
-  const int N = p.N;
-  const long long slot0 = (long long)blockIdx.x * kTileSlots;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = kPackThreads >> 5;
-  const long long nz = 8LL * N + 6;
-  for (int k0 = 0; k0 <= N; k0 += kTileStages) {
-    const int ns = min(kTileStages, N + 1 - k0);
-    const long long b = slot0 + lane;
-    if (b < B) {
-      for (int e = warp; e < ns * NW; e += nwarps) {
-        const int st = k0 + e / NW, j = e % NW;
-        t[lane][e] = (j >= NX && st >= N) ? 0.0 : scratch[(size_t)(p.oW + st * wW + j) * cap + b];
+// Every thread owns one scratch slot for the whole launch and works through problems taken from a global
+// queue: when its problem terminates it writes the result, pulls the next problem index (one warp-aggregated
+// atomic), loads that problem into its slot and joins the other lanes at the next iteration boundary.  The
+// lanes of a warp therefore always run the same sweep on consecutive slots (coalesced, convergent) although
+// their problems are at different interior-point iterations -- iteration-count divergence costs nothing.
+template <bool G>
+__global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
+    ttmpc_solve_kernel(const __grid_constant__ Params p, double* __restrict__ scratch, long long B, ProblemIn in, SolveOut out,
+                       unsigned long long* __restrict__ counter) {
+  const size_t slot = (size_t)blockIdx.x * kSolveThreads + threadIdx.x;
+  double* s0 = slot_ptr(scratch, p.N, slot);
+  const unsigned lane = threadIdx.x & 31u;
+  const long long nz = 8LL * p.N + 6;
+  long long prob = -1;
+  bool active = false, exhausted = false;
+  Ipm st;
+  Result res;
+  for (;;) {
+    const unsigned need = __ballot_sync(0xffffffffu, !active);
+    if (need && !exhausted) {
+      const int leader = __ffs(need) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(need));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (!active) {
+        const long long cand = (long long)base + __popc(need & ((1u << lane) - 1u));
+        if (cand < B) {
+          prob = cand;
+          active = true;
+          const bool bad = pack_slot(p, s0, in, prob);
+          ipm_begin(p, st, bad);
+        }
       }
+      if ((long long)base + __popc(need) >= B) exhausted = true;
     }
-    __syncthreads();
-    for (int sl = warp; sl < kTileSlots; sl += nwarps) {
-      const long long bb = slot0 + sl;
-      if (bb >= B) continue;
-      double* zo = z_out + bb * nz + (long long)k0 * NW;
-      const int ne = (int)min((long long)ns * NW, nz - (long long)k0 * NW);
-      for (int e = lane; e < ne; e += 32) zo[e] = t[sl][e];
+    if (!__any_sync(0xffffffffu, active)) break;
+    if (active && ipm_iteration<G>(p, s0, st, res)) {
+      if (out.z) unpack_slot(p, s0, out.z + prob * nz);
+      if (out.u0) {
+        out.u0[prob * 2 + 0] = ldr(s0, rW + 6);
+        out.u0[prob * 2 + 1] = ldr(s0, rW + 7);
+      }
+      if (out.obj) out.obj[prob] = res.obj;
+      if (out.kkt) {
+        out.kkt[prob * 3 + 0] = res.dual_inf;
+        out.kkt[prob * 3 + 1] = res.constr_viol;
+        out.kkt[prob * 3 + 2] = res.compl_inf;
+      }
+      if (out.iters) out.iters[prob] = res.iters;
+      if (out.status) out.status[prob] = res.status;
+      active = false;
     }
-    __syncthreads();
   }
 }
 
@@ -282,21 +184,24 @@ __global__ void __launch_bounds__(256) ttmpc_dfma_kernel(double* out, double a, 
 // ================================================================================================
 // C ABI
 // ================================================================================================
+constexpr int kNumKernels = 4;
 struct ttmpc_handle {
   ttmpc_config cfg;
   Params p;
   int device;
+  int max_blocks;          // resident CTAs of the persistent solve kernel on this device
   double* scratch;
-  size_t cap;
+  size_t banks;            // scratch capacity in banks of kBank slots
+  unsigned long long* counter;  // work queue head
   // staging for the host-pointer path
   void* stage;
   size_t stage_bytes;
   char err[256];
-  long long launches[6];
+  long long launches[kNumKernels];
 };
 
-static const char* kKernelNames[6] = {"ttmpc_pack_kernel", "ttmpc_solve_kernel", "ttmpc_unpack_kernel",
-                                      "ttmpc_shift_kernel", "ttmpc_plant_kernel", "ttmpc_dfma_kernel"};
+static const char* kKernelNames[kNumKernels] = {"ttmpc_solve_kernel", "ttmpc_shift_kernel", "ttmpc_plant_kernel",
+                                                "ttmpc_dfma_kernel"};
 
 static int set_err(ttmpc_handle* h, int code, const char* what, cudaError_t ce) {
   if (h) snprintf(h->err, sizeof h->err, "%s%s%s", what, ce != cudaSuccess ? ": " : "", ce != cudaSuccess ? cudaGetErrorString(ce) : "");
@@ -349,6 +254,21 @@ int ttmpc_create(const ttmpc_config* cfg, int device, ttmpc_handle** out) {
   h->cfg = *cfg;
   h->p = p;
   h->device = device;
+  int sms = 0, per_sm = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (p.generic)
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ttmpc_solve_kernel<true>, kSolveThreads, 0);
+  else
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ttmpc_solve_kernel<false>, kSolveThreads, 0);
+  if (ce != cudaSuccess || sms <= 0 || per_sm <= 0) {
+    delete h;
+    return TTMPC_E_CUDA;
+  }
+  h->max_blocks = sms * per_sm;
+  if (cudaMalloc(&h->counter, sizeof(unsigned long long)) != cudaSuccess) {
+    delete h;
+    return TTMPC_E_NOMEM;
+  }
   *out = h;
   return TTMPC_OK;
 }
@@ -358,6 +278,7 @@ int ttmpc_destroy(ttmpc_handle* h) {
   cudaSetDevice(h->device);
   if (h->scratch) cudaFree(h->scratch);
   if (h->stage) cudaFree(h->stage);
+  if (h->counter) cudaFree(h->counter);
   delete h;
   return TTMPC_OK;
 }
@@ -367,41 +288,39 @@ const char* ttmpc_last_error(const ttmpc_handle* h) { return h ? h->err : "null 
 int64_t ttmpc_launch_count(const ttmpc_handle* h) {
   long long n = 0;
   if (h)
-    for (int i = 0; i < 6; i++) n += h->launches[i];
+    for (int i = 0; i < kNumKernels; i++) n += h->launches[i];
   return n;
 }
 
 const char* ttmpc_kernel_name(const ttmpc_handle* h, int32_t i, int64_t* launches) {
-  if (!h || i < 0 || i >= 6) return nullptr;
+  if (!h || i < 0 || i >= kNumKernels) return nullptr;
   if (launches) *launches = h->launches[i];
   return kKernelNames[i];
 }
 
-static int ensure_scratch(ttmpc_handle* h, long long B) {
-  size_t need = (size_t)((B + 127) / 128) * 128;
-  if (need <= h->cap) return TTMPC_OK;
+static int ensure_scratch(ttmpc_handle* h, size_t slots) {
+  const size_t need = (slots + kBank - 1) / kBank;
+  if (need <= h->banks) return TTMPC_OK;
   if (h->scratch) cudaFree(h->scratch);
   h->scratch = nullptr;
-  h->cap = 0;
-  cudaError_t ce = cudaMalloc(&h->scratch, need * (size_t)h->p.rows * sizeof(double));
+  h->banks = 0;
+  cudaError_t ce = cudaMalloc(&h->scratch, scratch_doubles(h->p.N, need) * sizeof(double));
   if (ce != cudaSuccess) return set_err(h, TTMPC_E_NOMEM, "scratch cudaMalloc", ce);
-  h->cap = need;
+  h->banks = need;
   return TTMPC_OK;
 }
 
-static int solve_device(ttmpc_handle* h, long long B, const PackIn& in, double* z_out, const SolveOut& so, cudaStream_t st) {
-  int rc = ensure_scratch(h, B);
+static int solve_device(ttmpc_handle* h, long long B, const ProblemIn& in, const SolveOut& so, cudaStream_t st) {
+  long long blocks = (B + kSolveThreads - 1) / kSolveThreads;
+  if (blocks > h->max_blocks) blocks = h->max_blocks;
+  int rc = ensure_scratch(h, (size_t)blocks * kSolveThreads);
   if (rc) return rc;
-  const unsigned gp = (unsigned)((B + kTileSlots - 1) / kTileSlots);
-  ttmpc_pack_kernel<<<gp, kPackThreads, 0, st>>>(h->p, h->scratch, h->cap, B, in);
+  cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st);
+  if (h->p.generic)
+    ttmpc_solve_kernel<true><<<(unsigned)blocks, kSolveThreads, 0, st>>>(h->p, h->scratch, B, in, so, h->counter);
+  else
+    ttmpc_solve_kernel<false><<<(unsigned)blocks, kSolveThreads, 0, st>>>(h->p, h->scratch, B, in, so, h->counter);
   h->launches[0]++;
-  const unsigned gs = (unsigned)((B + kSolveThreads - 1) / kSolveThreads);
-  ttmpc_solve_kernel<<<gs, kSolveThreads, 0, st>>>(h->p, h->scratch, h->cap, B, so);
-  h->launches[1]++;
-  if (z_out) {
-    ttmpc_unpack_kernel<<<gp, kPackThreads, 0, st>>>(h->p, h->scratch, h->cap, B, z_out);
-    h->launches[2]++;
-  }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "kernel launch", ce);
   return TTMPC_OK;
@@ -430,9 +349,9 @@ static int solve_any(ttmpc_handle* h, int64_t B, const double* x_init, const dou
   const size_t nz = 8 * (size_t)N + 6;
   const bool host = (h->cfg.flags & TTMPC_FLAG_HOST_POINTERS) != 0;
   if (!host) {
-    PackIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T};
-    SolveOut so{u0_out, obj_out, kkt_out, iters_out, status_out};
-    int rc = solve_device(h, B, in, z_out, so, st);
+    ProblemIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T};
+    SolveOut so{z_out, u0_out, obj_out, kkt_out, iters_out, status_out};
+    int rc = solve_device(h, B, in, so, st);
     if (rc) return rc;
     if (h->cfg.flags & TTMPC_FLAG_SYNC) {
       cudaError_t ce = cudaStreamSynchronize(st);
@@ -478,7 +397,7 @@ static int solve_any(ttmpc_handle* h, int64_t B, const double* x_init, const dou
     H2D(pl.off_tu, traj_inputs, (size_t)T * NU * 8);
   }
   if (z_warm) H2D(pl.off_zw, z_warm, (size_t)B * nz * 8);
-  PackIn in{(const double*)(d + pl.off_x),
+  ProblemIn in{(const double*)(d + pl.off_x),
             shared ? nullptr : (const double*)(d + pl.off_rs),
             shared ? nullptr : (const double*)(d + pl.off_ru),
             z_warm ? (const double*)(d + pl.off_zw) : nullptr,
@@ -486,9 +405,9 @@ static int solve_any(ttmpc_handle* h, int64_t B, const double* x_init, const dou
             shared ? (const double*)(d + pl.off_ts) : nullptr,
             shared ? (const double*)(d + pl.off_tu) : nullptr,
             T};
-  SolveOut so{(double*)(d + pl.off_u0), (double*)(d + pl.off_obj), (double*)(d + pl.off_kkt), (int32_t*)(d + pl.off_it),
-              (int32_t*)(d + pl.off_st)};
-  int rc = solve_device(h, B, in, z_out ? (double*)(d + pl.off_z) : nullptr, so, st);
+  SolveOut so{z_out ? (double*)(d + pl.off_z) : nullptr, (double*)(d + pl.off_u0), (double*)(d + pl.off_obj),
+              (double*)(d + pl.off_kkt), (int32_t*)(d + pl.off_it), (int32_t*)(d + pl.off_st)};
+  int rc = solve_device(h, B, in, so, st);
   if (rc) return rc;
   if (z_out) D2H(z_out, pl.off_z, (size_t)B * nz * 8);
   if (u0_out) D2H(u0_out, pl.off_u0, (size_t)B * 2 * 8);
@@ -552,7 +471,7 @@ int ttmpc_shift_warm_start(ttmpc_handle* h, int64_t B, const double* z, double* 
   const long long total = (long long)B * (8LL * N + 6);
   const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   ttmpc_shift_kernel<<<grid, 256, 0, st>>>(N, B, zi, zo, mode);
-  h->launches[3]++;
+  h->launches[1]++;
   if (host) cudaMemcpyAsync(z_shift, zo, bytes, cudaMemcpyDeviceToHost, st);
   cudaError_t ce = cudaGetLastError();
   if (ce == cudaSuccess && (host || (h->cfg.flags & TTMPC_FLAG_SYNC))) ce = cudaStreamSynchronize(st);
@@ -588,7 +507,7 @@ int ttmpc_plant_step(ttmpc_handle* h, int64_t B, const double* q, const double* 
   const int has = disturb != nullptr;
   ttmpc_plant_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(h->p, B, dq, du, has, has ? disturb[0] : 1.0, has ? disturb[1] : 1.0,
                                                                has ? disturb[2] : 0.0, has ? disturb[3] : 0.0, dn, noise_scale, dy);
-  h->launches[4]++;
+  h->launches[2]++;
   if (host) cudaMemcpyAsync(q_next, dy, bq, cudaMemcpyDeviceToHost, st);
   cudaError_t ce = cudaGetLastError();
   if (ce == cudaSuccess && (host || (h->cfg.flags & TTMPC_FLAG_SYNC))) ce = cudaStreamSynchronize(st);
@@ -612,7 +531,7 @@ double ttmpc_measure_fp64_peak(ttmpc_handle* h, void* cuda_stream) {
   for (int rep = 0; rep < 5; rep++) {
     cudaEventRecord(e0, st);
     ttmpc_dfma_kernel<<<blocks, 256, 0, st>>>(dout, 0.999999, 1e-9);
-    h->launches[5]++;
+    h->launches[3]++;
     cudaEventRecord(e1, st);
     cudaEventSynchronize(e1);
     float ms = 0.f;

@@ -1,15 +1,16 @@
-// ttmpc_core.cuh -- per-problem interior-point solver, one CUDA thread per MPC problem.
+// ttmpc_core.cuh -- per-problem interior-point solver, one CUDA thread ("lane") per MPC problem.
 //
 // Replaces the arithmetic behind `self._solver(x0, lbx, ubx, lbg, ubg, p)` of the reference
 // (python-files/mpc_control.py:80-89, mpc_control_nmpc.py:98-105: CasADi -> Ipopt -> MUMPS) for the
 // NLP defined by truck_trailer_model.py:8-29 (kinematics + Euler), trajectory_planning.py:28-60
 // (multiple-shooting equalities, box bounds) and mpc_control.py:17-25 (tracking cost).
 //
-// Mapping: thread = problem slot.  All per-stage data of a slot lives in HBM in a
-// slot-interleaved layout  scratch[row * cap + slot]  so that the 32 lanes of a warp always touch 256
-// contiguous bytes (fully coalesced, no shared memory, no shuffles).  The 6x6 / 6x2 / 2x2 block algebra of
-// the Riccati recursion is unrolled into registers and exploits the sparsity of A = I + dt*df/dx
-// (14 non-zeros) and B (2 non-zeros).
+// Mapping: lane = problem slot.  All per-stage data of a slot lives in HBM in a
+// slot-interleaved layout, banks of kBank slots:  addr(bank, stage, row, lane) =
+// ((bank*(N+1) + stage)*kRows + row)*kBank + lane, so the 32 lanes of a warp always touch 256 contiguous
+// bytes (coalesced, no shuffles) and every row of a stage is a compile-time immediate offset from one
+// per-stage pointer.  The 6x6 / 6x2 / 2x2 block algebra of the Riccati recursion is unrolled into registers and
+// exploits the sparsity of A = I + dt*df/dx (14 non-zeros) and B (2 non-zeros).
 //
 // One interior-point iteration = ONE backward sweep + ONE forward sweep + (usually one) trial sweep:
 //   backward (k = N..0), fused:  (i)   apply the previous step: costate recursion for the new equality
@@ -18,8 +19,12 @@
 //                                (iii) Riccati factorisation at the new iterate.  The barrier parameter
 //                                      enters only the affine terms, which are carried as p = p0 + mu*p1,
 //                                      so mu can be updated AFTER the sweep from the statistics of (ii).
-//   forward  (k = 0..N-1):       search direction, fraction-to-boundary step sizes, grad(phi)'d.
-//   trial    (any order):        theta and phi at w + alpha*dw for the filter line search.
+//   forward  (k = 0..N):         search direction, fraction-to-boundary step sizes, grad(phi)'d.
+//   trial    (k = N..0):         theta and phi at w + alpha*dw for the filter line search.
+//
+// Template parameter G ("generic bounds"): G=false compiles the reference's bound pattern in (x,y free;
+// theta, psi, phi, v, a, omega two-sided -- simulation.py:411-414) so that no bound test survives in the
+// code; G=true reads per-variable masks from Params (any mix of one-/two-sided/absent bounds).
 //
 // The same functions compile for the host (plain g++) for a test-only emulation harness
 // (tools/kernel_emu.cpp); the shipped library contains the device path only.
@@ -36,6 +41,10 @@
 #else
 #define TT_HD inline __attribute__((always_inline))
 #define TT_UNROLL
+#endif
+
+#ifndef TTMPC_BANK
+#define TTMPC_BANK 16384
 #endif
 
 namespace ttmpc {
@@ -56,44 +65,50 @@ constexpr double kEps = 2.220446049250313e-16;
 // status codes: keep in sync with include/ttmpc.h
 enum : int { ST_CONVERGED = 0, ST_ACCEPTABLE = 1, ST_MAX_ITER = 2, ST_LINESEARCH = 3, ST_NUMERIC = 4, ST_INFEASIBLE_X0 = 5 };
 
+// ---- scratch layout: rows of one stage ----
+constexpr int kBank = TTMPC_BANK;  // slots per bank = element stride between rows
+constexpr int rW = 0;              // w_k = (x_k, u_k)                       8
+constexpr int rDW = 8;             // search direction                       8
+constexpr int rREF = 16;           // reference (xbar_k, ubar_k)             8
+constexpr int rLAM = 24;           // multiplier of c_k (defect into x_k)    6
+constexpr int rZL = 30;            // lower-bound multipliers (x 0..5, u 6..7) 8
+constexpr int rZU = 38;            // upper-bound multipliers                8
+constexpr int rKF = 46;            // K (2x6), kff0 (2), kff1 (2)            16
+constexpr int kRows = 62;
+constexpr size_t kStageStride = (size_t)kRows * kBank;
+
 struct Params {
   int N, max_iter, acc_iter;
-  int n_b, m_eq;             // number of bound multipliers / equality multipliers (scaling factors s_d, s_c)
-  unsigned xhl, xhu, uhl, uhu;  // bit i set: variable i has a lower / upper bound
-  double dt, iL1, iL2, cML;     // 1/L1, 1/L2, M/L2
-  double Q2[21];                // 2*Q, symmetric packed (SY)
-  double R2[3];                 // 2*R: (a,a), (a,w), (w,w)
-  double xl[NX], xu[NX], ul[NU], uu[NU];  // relaxed bounds (bound_relax_factor)
+  int n_b, m_eq;       // number of bound multipliers / equality multipliers (scaling factors s_d, s_c)
+  unsigned bl, bu;     // bit j set: variable j (x: 0..5, u: 6..7) has a lower / upper bound
+  int generic;         // 0: the bound pattern is the compiled-in default (G=false kernels are valid)
+  double dt, iL1, iL2, cML;  // 1/L1, 1/L2, M/L2
+  double Q2[21];             // 2*Q, symmetric packed (SY)
+  double R2[3];              // 2*R: (a,a), (a,w), (w,w)
+  double lo[NW], up[NW];     // relaxed bounds (bound_relax_factor), x then u
   double tol, acc_tol, mu_init, mu_floor;
-  // scratch layout: row offsets of the sections, rows are [stage][component]
-  int oW, oLAM, oZL, oZU, oREF, oDW, oKF, rows;
 };
 
 TT_HD constexpr int SY(int i, int j) { return i <= j ? (i * (13 - i)) / 2 + (j - i) : (j * (13 - j)) / 2 + (i - j); }
 
-// section widths (rows per stage)
-constexpr int wW = 8, wLAM = 6, wZ = 8, wREF = 8, wDW = 8, wKF = 16;
-
-inline void layout_rows(Params& p) {
-  const int S = p.N + 1;
-  p.oW = 0;
-  p.oLAM = p.oW + S * wW;
-  p.oZL = p.oLAM + S * wLAM;
-  p.oZU = p.oZL + S * wZ;
-  p.oREF = p.oZU + S * wZ;
-  p.oDW = p.oREF + S * wREF;
-  p.oKF = p.oDW + S * wDW;
-  p.rows = p.oKF + S * wKF;
+template <bool G>
+TT_HD bool has_lo(const Params& p, int j) {
+  return G ? (((p.bl >> j) & 1u) != 0) : (j >= 2);
+}
+template <bool G>
+TT_HD bool has_up(const Params& p, int j) {
+  return G ? (((p.bu >> j) & 1u) != 0) : (j >= 2);
 }
 
-// One problem slot of the slot-interleaved scratch.
-struct Slot {
-  double* base;
-  size_t cap;
-  size_t slot;
-  TT_HD double ld(int row) const { return base[(size_t)row * cap + slot]; }
-  TT_HD void st(int row, double v) const { base[(size_t)row * cap + slot] = v; }
-};
+TT_HD double ldr(const double* ps, int row) { return ps[(size_t)row * kBank]; }
+TT_HD void str(double* ps, int row, double v) { ps[(size_t)row * kBank] = v; }
+
+// pointer to (stage 0, row 0) of a slot inside a scratch allocation of `nbanks` banks
+TT_HD double* slot_ptr(double* scratch, int N, size_t slot) {
+  const size_t bank = slot / kBank, lane = slot % kBank;
+  return scratch + bank * (size_t)(N + 1) * kStageStride + lane;
+}
+inline size_t scratch_doubles(int N, size_t nbanks) { return nbanks * (size_t)(N + 1) * kStageStride; }
 
 TT_HD void tt_sincos(double x, double& s, double& c) {
 #if defined(__CUDA_ARCH__)
@@ -205,89 +220,77 @@ struct Stats {
   double cmax, cmin;              // max / min of slack*multiplier
 };
 
-// bound bookkeeping of one scalar variable at the new iterate; returns Sigma contribution.
-struct BoundAcc {
-  double sigma, g1, slog;
-};
-
 // ------------------------------------------------------------------------------------------------
 // backward sweep
 // ------------------------------------------------------------------------------------------------
 // do_update: apply the step stored in DW with primal step alpha / dual step alpha_du; mu_step, delta_step are the
 // barrier parameter and Hessian regularisation the step was computed with.  delta: regularisation for the new
 // factorisation.  Returns false when some 2x2 pivot block is not positive definite (wrong inertia).
-TT_HD bool backward_sweep(const Params& p, const Slot& s, bool do_update, double alpha, double alpha_du,
-                          double mu_step, double delta_step, double mu_clip, double delta, Stats& st) {
+template <bool G>
+TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double alpha, double alpha_du, double mu_step,
+                          double delta_step, double delta, Stats& st) {
   const int N = p.N;
   const double dt = p.dt;
   double P[21], p0[NX], p1[NX];
-  double xn[NX];            // new x_{k+1}
-  double lnew[NX];          // new lambda_{k+1}
-  double lold[NX];          // old lambda_{k+1}
-  double lplus[NX];         // full-step multiplier lambda^+_{k+1}
+  double xn[NX];     // new x_{k+1}
+  double lnew[NX];   // new lambda_{k+1}
+  double lold[4];    // old lambda_{k+1} (components entering the Hessian)
+  double lplus[NX];  // full-step multiplier lambda^+_{k+1}
   bool ok = true;
-  st.J = 0.0;
-  st.sumlog = 0.0;
-  st.theta = 0.0;
-  st.cinf = 0.0;
-  st.rd_inf = 0.0;
-  st.lam1 = 0.0;
-  st.z1 = 0.0;
-  st.cmax = 0.0;
-  st.cmin = INFINITY;
+  double J = 0.0, sumlog = 0.0, theta = 0.0, cinf = 0.0, rd_inf = 0.0, lam1 = 0.0, z1 = 0.0, cmax = 0.0, cmin = INFINITY;
+  const double kmu_hi = kKappaSigma * mu_step, kmu_lo = mu_step / kKappaSigma;
 
   for (int k = N; k >= 0; k--) {
+    double* ps = s0 + (size_t)k * kStageStride;
     const bool has_x = (k >= 1);  // x_0 is data
     const bool has_u = (k < N);
-    double w[NW], ref[NW], zl[NW], zu[NW], lam[NX];
+    double w[NW], ref[NW], dw[NW], zl[NW], zu[NW], lam[NX];
     TT_UNROLL
     for (int j = 0; j < NW; j++) {
-      w[j] = (j < NX || has_u) ? s.ld(p.oW + k * wW + j) : 0.0;
-      ref[j] = (j < NX || has_u) ? s.ld(p.oREF + k * wREF + j) : 0.0;
-      zl[j] = 0.0;
-      zu[j] = 0.0;
+      const bool on = (j < NX) || has_u;
+      const bool var = (j < NX) ? has_x : has_u;
+      w[j] = on ? ldr(ps, rW + j) : 0.0;
+      ref[j] = on ? ldr(ps, rREF + j) : 0.0;
+      dw[j] = (do_update && var) ? ldr(ps, rDW + j) : 0.0;
+      zl[j] = (var && has_lo<G>(p, j)) ? ldr(ps, rZL + j) : 0.0;
+      zu[j] = (var && has_up<G>(p, j)) ? ldr(ps, rZU + j) : 0.0;
     }
     TT_UNROLL
-    for (int j = 0; j < NX; j++) {
-      lam[j] = has_x ? s.ld(p.oLAM + k * wLAM + j) : 0.0;
-      if (has_x && ((p.xhl >> j) & 1u)) zl[j] = s.ld(p.oZL + k * wZ + j);
-      if (has_x && ((p.xhu >> j) & 1u)) zu[j] = s.ld(p.oZU + k * wZ + j);
-    }
-    TT_UNROLL
-    for (int j = 0; j < NU; j++) {
-      if (has_u && ((p.uhl >> j) & 1u)) zl[NX + j] = s.ld(p.oZL + k * wZ + NX + j);
-      if (has_u && ((p.uhu >> j) & 1u)) zu[NX + j] = s.ld(p.oZU + k * wZ + NX + j);
-    }
+    for (int j = 0; j < NX; j++) lam[j] = has_x ? ldr(ps, rLAM + j) : 0.0;
 
     // ---------------------------------------------------------------- (i) apply the previous step
     if (do_update) {
-      double dw[NW];
+      // old-point barrier terms and dual steps of every bounded variable of this stage
+      double sigd[NW], gb[NW];  // (Sigma + delta) * dw  and  mu * (1/su - 1/sl)
       TT_UNROLL
-      for (int j = 0; j < NW; j++) dw[j] = (j < NX ? has_x : has_u) ? s.ld(p.oDW + k * wDW + j) : 0.0;
-      double lp[NX];
+      for (int j = 0; j < NW; j++) {
+        const bool var = (j < NX) ? has_x : has_u;
+        double sig = delta_step, g = 0.0;
+        if (var && has_lo<G>(p, j)) {
+          const double rl = 1.0 / (w[j] - p.lo[j]);
+          sig += zl[j] * rl;
+          g -= mu_step * rl;
+          zl[j] += alpha_du * (rl * (mu_step - zl[j] * dw[j]) - zl[j]);
+        }
+        if (var && has_up<G>(p, j)) {
+          const double ru = 1.0 / (p.up[j] - w[j]);
+          sig += zu[j] * ru;
+          g += mu_step * ru;
+          zu[j] += alpha_du * (ru * (mu_step + zu[j] * dw[j]) - zu[j]);
+        }
+        sigd[j] = sig * dw[j];
+        gb[j] = g;
+      }
       if (has_x) {
         // costate recursion at the OLD iterate:  lambda+_k = A_k' lambda+_{k+1} - (Hx_k dx_k + ghat_k)
-        double hx[NX];
+        double hx[NX], g[NX], d6[NX];
         Q2_mul(p, dw, hx);
-        double g[NX], d6[NX];
         TT_UNROLL
         for (int j = 0; j < NX; j++) d6[j] = w[j] - ref[j];
         Q2_mul(p, d6, g);
         TT_UNROLL
-        for (int j = 0; j < NX; j++) {
-          double sig = delta_step;
-          if ((p.xhl >> j) & 1u) {
-            const double sl = w[j] - p.xl[j];
-            sig += zl[j] / sl;
-            g[j] -= mu_step / sl;
-          }
-          if ((p.xhu >> j) & 1u) {
-            const double su = p.xu[j] - w[j];
-            sig += zu[j] / su;
-            g[j] += mu_step / su;
-          }
-          hx[j] += sig * dw[j];
-        }
+        for (int j = 0; j < NX; j++) hx[j] += sigd[j] + g[j] + gb[j];
+        double lp[NX];
         if (has_u) {
           Lin mo;
           stage_lin(p, w, mo);
@@ -297,126 +300,94 @@ TT_HD bool backward_sweep(const Params& p, const Slot& s, bool do_update, double
           hx[3] += ho.h33 * dw[3] + ho.h34 * dw[4] + ho.h35 * dw[5];
           hx[4] += ho.h34 * dw[3] + ho.h44 * dw[4] + ho.h45 * dw[5];
           hx[5] += ho.h25 * dw[2] + ho.h35 * dw[3] + ho.h45 * dw[4];
-          double al[NX];
-          At_mul(mo, lplus, al);
+          At_mul(mo, lplus, lp);
           TT_UNROLL
-          for (int j = 0; j < NX; j++) lp[j] = al[j] - hx[j] - g[j];
+          for (int j = 0; j < NX; j++) lp[j] -= hx[j];
         } else {
           TT_UNROLL
-          for (int j = 0; j < NX; j++) lp[j] = -hx[j] - g[j];
+          for (int j = 0; j < NX; j++) lp[j] = -hx[j];
         }
-      }
-      // bound multipliers (old slack, old multiplier), then primal, then the kappa_sigma safeguard
-      TT_UNROLL
-      for (int j = 0; j < NW; j++) {
-        const bool on = (j < NX) ? has_x : has_u;
-        const unsigned hl = (j < NX) ? ((p.xhl >> j) & 1u) : ((p.uhl >> (j - NX)) & 1u);
-        const unsigned hu = (j < NX) ? ((p.xhu >> j) & 1u) : ((p.uhu >> (j - NX)) & 1u);
-        const double lo = (j < NX) ? p.xl[j] : p.ul[j - NX];
-        const double up = (j < NX) ? p.xu[j] : p.uu[j - NX];
-        if (on) {
-          const double wo = w[j];
-          const double wn = wo + alpha * dw[j];
-          if (hl) {
-            const double sl = wo - lo;
-            double z = zl[j] + alpha_du * (mu_step / sl - zl[j] - zl[j] / sl * dw[j]);
-            const double sn = wn - lo;
-            z = fmax(fmin(z, kKappaSigma * mu_clip / sn), mu_clip / (kKappaSigma * sn));
-            zl[j] = z;
-            s.st(p.oZL + k * wZ + j, z);
-          }
-          if (hu) {
-            const double su = up - wo;
-            double z = zu[j] + alpha_du * (mu_step / su - zu[j] + zu[j] / su * dw[j]);
-            const double sn = up - wn;
-            z = fmax(fmin(z, kKappaSigma * mu_clip / sn), mu_clip / (kKappaSigma * sn));
-            zu[j] = z;
-            s.st(p.oZU + k * wZ + j, z);
-          }
-          w[j] = wn;
-          s.st(p.oW + k * wW + j, wn);
-        }
-      }
-      if (has_x) {
+        TT_UNROLL
+        for (int j = 0; j < 4; j++) lold[j] = lam[j];
         TT_UNROLL
         for (int j = 0; j < NX; j++) {
-          lold[j] = lam[j];
           lplus[j] = lp[j];
           lam[j] += alpha * (lp[j] - lam[j]);
-          s.st(p.oLAM + k * wLAM + j, lam[j]);
+          str(ps, rLAM + j, lam[j]);
+        }
+      }
+      TT_UNROLL
+      for (int j = 0; j < NW; j++) {
+        const bool var = (j < NX) ? has_x : has_u;
+        if (var) {
+          w[j] += alpha * dw[j];
+          str(ps, rW + j, w[j]);
         }
       }
     } else if (has_x) {
       TT_UNROLL
-      for (int j = 0; j < NX; j++) lold[j] = lam[j];
+      for (int j = 0; j < 4; j++) lold[j] = lam[j];
     }
 
     // ---------------------------------------------------------------- (ii) statistics at the new iterate
-    double gx0[NX], gx1[NX], sigx[NX];  // grad J, d(barrier)/dmu coefficient, Sigma
-    double gu0[NU], gu1[NU], sigu[NU];
+    double g0[NW], g1[NW], sig[NW];  // grad J, d(barrier gradient)/d(mu), Sigma (+delta)
     {
       double d6[NX];
       TT_UNROLL
       for (int j = 0; j < NX; j++) d6[j] = w[j] - ref[j];
-      Q2_mul(p, d6, gx0);
+      Q2_mul(p, d6, g0);
       double jq = 0.0;
       TT_UNROLL
-      for (int j = 0; j < NX; j++) jq += gx0[j] * d6[j];
-      st.J += 0.5 * jq;
-      TT_UNROLL
-      for (int j = 0; j < NX; j++) {
-        gx1[j] = 0.0;
-        sigx[j] = 0.0;
-        if (has_x) {
-          if ((p.xhl >> j) & 1u) {
-            const double sl = w[j] - p.xl[j];
-            gx1[j] -= 1.0 / sl;
-            sigx[j] += zl[j] / sl;
-            st.sumlog += log(sl);
-            st.z1 += zl[j];
-            st.cmax = fmax(st.cmax, sl * zl[j]);
-            st.cmin = fmin(st.cmin, sl * zl[j]);
-          }
-          if ((p.xhu >> j) & 1u) {
-            const double su = p.xu[j] - w[j];
-            gx1[j] += 1.0 / su;
-            sigx[j] += zu[j] / su;
-            st.sumlog += log(su);
-            st.z1 += zu[j];
-            st.cmax = fmax(st.cmax, su * zu[j]);
-            st.cmin = fmin(st.cmin, su * zu[j]);
-          }
-          st.lam1 += fabs(lam[j]);
-        }
-      }
+      for (int j = 0; j < NX; j++) jq += g0[j] * d6[j];
       if (has_u) {
         const double da = w[6] - ref[6], dw_ = w[7] - ref[7];
-        gu0[0] = p.R2[0] * da + p.R2[1] * dw_;
-        gu0[1] = p.R2[1] * da + p.R2[2] * dw_;
-        st.J += 0.5 * (gu0[0] * da + gu0[1] * dw_);
-        TT_UNROLL
-        for (int j = 0; j < NU; j++) {
-          gu1[j] = 0.0;
-          sigu[j] = 0.0;
-          if ((p.uhl >> j) & 1u) {
-            const double sl = w[NX + j] - p.ul[j];
-            gu1[j] -= 1.0 / sl;
-            sigu[j] += zl[NX + j] / sl;
-            st.sumlog += log(sl);
-            st.z1 += zl[NX + j];
-            st.cmax = fmax(st.cmax, sl * zl[NX + j]);
-            st.cmin = fmin(st.cmin, sl * zl[NX + j]);
+        g0[6] = p.R2[0] * da + p.R2[1] * dw_;
+        g0[7] = p.R2[1] * da + p.R2[2] * dw_;
+        jq += g0[6] * da + g0[7] * dw_;
+      } else {
+        g0[6] = g0[7] = 0.0;
+      }
+      J += 0.5 * jq;
+      double prod = 1.0;
+      TT_UNROLL
+      for (int j = 0; j < NW; j++) {
+        const bool var = (j < NX) ? has_x : has_u;
+        double sg = delta, gg = 0.0;
+        if (var && has_lo<G>(p, j)) {
+          const double sl = w[j] - p.lo[j], rl = 1.0 / sl;
+          if (do_update) {  // kappa_sigma safeguard, Waechter & Biegler eq. (16)
+            zl[j] = fmax(fmin(zl[j], kmu_hi * rl), kmu_lo * rl);
+            str(ps, rZL + j, zl[j]);
           }
-          if ((p.uhu >> j) & 1u) {
-            const double su = p.uu[j] - w[NX + j];
-            gu1[j] += 1.0 / su;
-            sigu[j] += zu[NX + j] / su;
-            st.sumlog += log(su);
-            st.z1 += zu[NX + j];
-            st.cmax = fmax(st.cmax, su * zu[NX + j]);
-            st.cmin = fmin(st.cmin, su * zu[NX + j]);
-          }
+          sg += zl[j] * rl;
+          gg -= rl;
+          prod *= sl;
+          z1 += zl[j];
+          const double c = sl * zl[j];
+          cmax = fmax(cmax, c);
+          cmin = fmin(cmin, c);
         }
+        if (var && has_up<G>(p, j)) {
+          const double su = p.up[j] - w[j], ru = 1.0 / su;
+          if (do_update) {
+            zu[j] = fmax(fmin(zu[j], kmu_hi * ru), kmu_lo * ru);
+            str(ps, rZU + j, zu[j]);
+          }
+          sg += zu[j] * ru;
+          gg += ru;
+          prod *= su;
+          z1 += zu[j];
+          const double c = su * zu[j];
+          cmax = fmax(cmax, c);
+          cmin = fmin(cmin, c);
+        }
+        sig[j] = sg;
+        g1[j] = gg;
+      }
+      sumlog += log(prod);
+      if (has_x) {
+        TT_UNROLL
+        for (int j = 0; j < NX; j++) lam1 += fabs(lam[j]);
       }
     }
 
@@ -426,12 +397,11 @@ TT_HD bool backward_sweep(const Params& p, const Slot& s, bool do_update, double
       for (int i = 0; i < NX; i++) {
         TT_UNROLL
         for (int j = i; j < NX; j++) P[SY(i, j)] = p.Q2[SY(i, j)];
-        P[SY(i, i)] += sigx[i] + delta;
-        p0[i] = gx0[i];
-        p1[i] = gx1[i];
-        // dual residual of x_N
-        const double r = gx0[i] + lam[i] - zl[i] + zu[i];
-        st.rd_inf = fmax(st.rd_inf, fabs(r));
+        P[SY(i, i)] += sig[i];
+        p0[i] = g0[i];
+        p1[i] = g1[i];
+        const double r = g0[i] + lam[i] - zl[i] + zu[i];  // dual residual of x_N
+        rd_inf = fmax(rd_inf, fabs(r));
       }
     } else {
       // ------------------------------------------------------------ (iii) stage k < N
@@ -447,21 +417,21 @@ TT_HD bool backward_sweep(const Params& p, const Slot& s, bool do_update, double
       c[5] = xn[5] - w[5] - dt * w[6];
       TT_UNROLL
       for (int j = 0; j < NX; j++) {
-        st.theta += fabs(c[j]);
-        st.cinf = fmax(st.cinf, fabs(c[j]));
+        theta += fabs(c[j]);
+        cinf = fmax(cinf, fabs(c[j]));
       }
       // dual residuals
       {
-        const double ra = gu0[0] - dt * lnew[5] - zl[6] + zu[6];
-        const double rw = gu0[1] - dt * lnew[4] - zl[7] + zu[7];
-        st.rd_inf = fmax(st.rd_inf, fmax(fabs(ra), fabs(rw)));
+        const double ra = g0[6] - dt * lnew[5] - zl[6] + zu[6];
+        const double rw = g0[7] - dt * lnew[4] - zl[7] + zu[7];
+        rd_inf = fmax(rd_inf, fmax(fabs(ra), fabs(rw)));
         if (has_x) {
           double al[NX];
           At_mul(m, lnew, al);
           TT_UNROLL
           for (int j = 0; j < NX; j++) {
-            const double r = gx0[j] + lam[j] - al[j] - zl[j] + zu[j];
-            st.rd_inf = fmax(st.rd_inf, fabs(r));
+            const double r = g0[j] + lam[j] - al[j] - zl[j] + zu[j];
+            rd_inf = fmax(rd_inf, fabs(r));
           }
         }
       }
@@ -488,9 +458,9 @@ TT_HD bool backward_sweep(const Params& p, const Slot& s, bool do_update, double
       }
       // Rhat = 2R + Sigma_u + delta + B'PB
       const double dt2 = dt * dt;
-      const double r00 = p.R2[0] + sigu[0] + delta + dt2 * P[SY(5, 5)];
+      const double r00 = p.R2[0] + sig[6] + dt2 * P[SY(5, 5)];
       const double r01 = p.R2[1] + dt2 * P[SY(5, 4)];
-      const double r11 = p.R2[2] + sigu[1] + delta + dt2 * P[SY(4, 4)];
+      const double r11 = p.R2[2] + sig[7] + dt2 * P[SY(4, 4)];
       const double det = r00 * r11 - r01 * r01;
       if (!(r00 > 0.0) || !(det > 0.0)) ok = false;
       const double idet = 1.0 / det;
@@ -504,19 +474,19 @@ TT_HD bool backward_sweep(const Params& p, const Slot& s, bool do_update, double
         K0[j] = i00 * S0[j] + i01 * S1[j];
         K1[j] = i01 * S0[j] + i11 * S1[j];
       }
-      const double b0a = gu0[0] + dt * h0[5], b0w = gu0[1] + dt * h0[4];
-      const double b1a = gu1[0] + dt * p1[5], b1w = gu1[1] + dt * p1[4];
+      const double b0a = g0[6] + dt * h0[5], b0w = g0[7] + dt * h0[4];
+      const double b1a = g1[6] + dt * p1[5], b1w = g1[7] + dt * p1[4];
       const double k0a = i00 * b0a + i01 * b0w, k0w = i01 * b0a + i11 * b0w;
       const double k1a = i00 * b1a + i01 * b1w, k1w = i01 * b1a + i11 * b1w;
       TT_UNROLL
       for (int j = 0; j < NX; j++) {
-        s.st(p.oKF + k * wKF + j, K0[j]);
-        s.st(p.oKF + k * wKF + NX + j, K1[j]);
+        str(ps, rKF + j, K0[j]);
+        str(ps, rKF + NX + j, K1[j]);
       }
-      s.st(p.oKF + k * wKF + 12, k0a);
-      s.st(p.oKF + k * wKF + 13, k0w);
-      s.st(p.oKF + k * wKF + 14, k1a);
-      s.st(p.oKF + k * wKF + 15, k1w);
+      str(ps, rKF + 12, k0a);
+      str(ps, rKF + 13, k0w);
+      str(ps, rKF + 14, k1a);
+      str(ps, rKF + 15, k1w);
 
       if (has_x) {
         Hes hs;
@@ -538,7 +508,7 @@ TT_HD bool backward_sweep(const Params& p, const Slot& s, bool do_update, double
         for (int i = 0; i < NX; i++) {
           TT_UNROLL
           for (int j = i; j < NX; j++) Pn[SY(i, j)] += p.Q2[SY(i, j)] - (S0[i] * K0[j] + S1[i] * K1[j]);
-          Pn[SY(i, i)] += sigx[i] + delta;
+          Pn[SY(i, i)] += sig[i];
         }
         Pn[SY(2, 2)] += hs.h22;
         Pn[SY(2, 5)] += hs.h25;
@@ -552,8 +522,8 @@ TT_HD bool backward_sweep(const Params& p, const Slot& s, bool do_update, double
         At_mul(m, p1, a1);
         TT_UNROLL
         for (int i = 0; i < NX; i++) {
-          p0[i] = gx0[i] + a0[i] - (S0[i] * k0a + S1[i] * k0w);
-          p1[i] = gx1[i] + a1[i] - (S0[i] * k1a + S1[i] * k1w);
+          p0[i] = g0[i] + a0[i] - (S0[i] * k0a + S1[i] * k0w);
+          p1[i] = g1[i] + a1[i] - (S0[i] * k1a + S1[i] * k1w);
         }
         TT_UNROLL
         for (int i = 0; i < 21; i++) P[i] = Pn[i];
@@ -566,6 +536,15 @@ TT_HD bool backward_sweep(const Params& p, const Slot& s, bool do_update, double
       lnew[j] = lam[j];
     }
   }
+  st.J = J;
+  st.sumlog = sumlog;
+  st.theta = theta;
+  st.cinf = cinf;
+  st.rd_inf = rd_inf;
+  st.lam1 = lam1;
+  st.z1 = z1;
+  st.cmax = cmax;
+  st.cmin = cmin;
   return ok;
 }
 
@@ -576,108 +555,105 @@ struct StepInfo {
   double a_pr, a_du, gphi_d;
 };
 
-TT_HD void forward_sweep(const Params& p, const Slot& s, double mu, double tau, StepInfo& si) {
+template <bool G>
+TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, StepInfo& si) {
   const int N = p.N;
   const double dt = p.dt;
   double dx[NX] = {0, 0, 0, 0, 0, 0};
   double x[NX], xnext[NX];
-  double a_pr = 1.0, a_du = 1.0, gd = 0.0;
+  // fraction-to-boundary: alpha = min(1, tau / max_i(-ds_i/s_i)); the dual maximum is kept as a ratio bn/bd
+  double qmax = 0.0, bn = 0.0, bd = 1.0, gd = 0.0;
   TT_UNROLL
-  for (int j = 0; j < NX; j++) x[j] = s.ld(p.oW + j);
+  for (int j = 0; j < NX; j++) x[j] = ldr(s0, rW + j);
   for (int k = 0; k <= N; k++) {
+    double* ps = s0 + (size_t)k * kStageStride;
     const bool has_x = (k >= 1), has_u = (k < N);
-    double ref[NW];
+    double w[NW], d[NW], ref[NW];
     TT_UNROLL
-    for (int j = 0; j < NW; j++) ref[j] = (j < NX || has_u) ? s.ld(p.oREF + k * wREF + j) : 0.0;
-    // state part: step limits and directional derivative
-    if (has_x) {
-      double d6[NX], g[NX];
-      TT_UNROLL
-      for (int j = 0; j < NX; j++) d6[j] = x[j] - ref[j];
-      Q2_mul(p, d6, g);
-      TT_UNROLL
-      for (int j = 0; j < NX; j++) {
-        const double d = dx[j];
-        double gj = g[j];
-        if ((p.xhl >> j) & 1u) {
-          const double sl = x[j] - p.xl[j], z = s.ld(p.oZL + k * wZ + j);
-          gj -= mu / sl;
-          if (d < 0.0) a_pr = fmin(a_pr, -tau * sl / d);
-          const double dz = mu / sl - z - z / sl * d;
-          if (dz < 0.0) a_du = fmin(a_du, -tau * z / dz);
+    for (int j = 0; j < NX; j++) {
+      w[j] = x[j];
+      d[j] = dx[j];
+    }
+    w[6] = has_u ? ldr(ps, rW + 6) : 0.0;
+    w[7] = has_u ? ldr(ps, rW + 7) : 0.0;
+    TT_UNROLL
+    for (int j = 0; j < NW; j++) ref[j] = ((j < NX) || has_u) ? ldr(ps, rREF + j) : 0.0;
+    // du = -K dx - (kff0 + mu*kff1)
+    d[6] = d[7] = 0.0;
+    if (has_u) {
+      double du0 = -(ldr(ps, rKF + 12) + mu * ldr(ps, rKF + 14));
+      double du1 = -(ldr(ps, rKF + 13) + mu * ldr(ps, rKF + 15));
+      if (has_x) {
+        TT_UNROLL
+        for (int j = 0; j < NX; j++) {
+          du0 -= ldr(ps, rKF + j) * dx[j];
+          du1 -= ldr(ps, rKF + NX + j) * dx[j];
         }
-        if ((p.xhu >> j) & 1u) {
-          const double su = p.xu[j] - x[j], z = s.ld(p.oZU + k * wZ + j);
-          gj += mu / su;
-          if (d > 0.0) a_pr = fmin(a_pr, tau * su / d);
-          const double dz = mu / su - z + z / su * d;
-          if (dz < 0.0) a_du = fmin(a_du, -tau * z / dz);
-        }
-        gd += gj * d;
-        s.st(p.oDW + k * wDW + j, d);
       }
+      d[6] = du0;
+      d[7] = du1;
+      TT_UNROLL
+      for (int j = 0; j < NX; j++) xnext[j] = ldr(ps + kStageStride, rW + j);
+    }
+    // gradient of the barrier objective along the step, step limits, store the direction
+    double g[NW];
+    {
+      double d6[NX];
+      TT_UNROLL
+      for (int j = 0; j < NX; j++) d6[j] = w[j] - ref[j];
+      Q2_mul(p, d6, g);
+      const double da = w[6] - ref[6], dw_ = w[7] - ref[7];
+      g[6] = p.R2[0] * da + p.R2[1] * dw_;
+      g[7] = p.R2[1] * da + p.R2[2] * dw_;
+    }
+    TT_UNROLL
+    for (int j = 0; j < NW; j++) {
+      const bool var = (j < NX) ? has_x : has_u;
+      if (!var) continue;
+      double gj = g[j];
+      if (has_lo<G>(p, j)) {
+        const double rl = 1.0 / (w[j] - p.lo[j]), z = ldr(ps, rZL + j);
+        gj -= mu * rl;
+        qmax = fmax(qmax, -d[j] * rl);
+        const double ndz = z - rl * (mu - z * d[j]);  // -dz
+        if (ndz * bd > bn * z) {
+          bn = ndz;
+          bd = z;
+        }
+      }
+      if (has_up<G>(p, j)) {
+        const double ru = 1.0 / (p.up[j] - w[j]), z = ldr(ps, rZU + j);
+        gj += mu * ru;
+        qmax = fmax(qmax, d[j] * ru);
+        const double ndz = z - ru * (mu + z * d[j]);
+        if (ndz * bd > bn * z) {
+          bn = ndz;
+          bd = z;
+        }
+      }
+      gd += gj * d[j];
+      str(ps, rDW + j, d[j]);
     }
     if (!has_u) break;
-    double u[NU];
-    u[0] = s.ld(p.oW + k * wW + 6);
-    u[1] = s.ld(p.oW + k * wW + 7);
-    TT_UNROLL
-    for (int j = 0; j < NX; j++) xnext[j] = s.ld(p.oW + (k + 1) * wW + j);
-    // du = -K dx - (kff0 + mu*kff1)
-    double du0 = -(s.ld(p.oKF + k * wKF + 12) + mu * s.ld(p.oKF + k * wKF + 14));
-    double du1 = -(s.ld(p.oKF + k * wKF + 13) + mu * s.ld(p.oKF + k * wKF + 15));
-    if (has_x) {
-      TT_UNROLL
-      for (int j = 0; j < NX; j++) {
-        du0 -= s.ld(p.oKF + k * wKF + j) * dx[j];
-        du1 -= s.ld(p.oKF + k * wKF + NX + j) * dx[j];
-      }
-    }
-    const double du[NU] = {du0, du1};
-    {
-      const double da = u[0] - ref[6], dw_ = u[1] - ref[7];
-      const double g0[NU] = {p.R2[0] * da + p.R2[1] * dw_, p.R2[1] * da + p.R2[2] * dw_};
-      TT_UNROLL
-      for (int j = 0; j < NU; j++) {
-        const double d = du[j];
-        double gj = g0[j];
-        if ((p.uhl >> j) & 1u) {
-          const double sl = u[j] - p.ul[j], z = s.ld(p.oZL + k * wZ + NX + j);
-          gj -= mu / sl;
-          if (d < 0.0) a_pr = fmin(a_pr, -tau * sl / d);
-          const double dz = mu / sl - z - z / sl * d;
-          if (dz < 0.0) a_du = fmin(a_du, -tau * z / dz);
-        }
-        if ((p.uhu >> j) & 1u) {
-          const double su = p.uu[j] - u[j], z = s.ld(p.oZU + k * wZ + NX + j);
-          gj += mu / su;
-          if (d > 0.0) a_pr = fmin(a_pr, tau * su / d);
-          const double dz = mu / su - z + z / su * d;
-          if (dz < 0.0) a_du = fmin(a_du, -tau * z / dz);
-        }
-        gd += gj * d;
-        s.st(p.oDW + k * wDW + NX + j, d);
-      }
-    }
     // dx_{k+1} = A dx + B du - c_{k+1}
     Lin m;
-    stage_lin(p, x, m);
+    stage_lin(p, w, m);
     double y[NX];
     A_mul(m, dx, y);
-    y[0] -= xnext[0] - x[0] - dt * m.f0;
-    y[1] -= xnext[1] - x[1] - dt * m.f1;
-    y[2] -= xnext[2] - x[2] - dt * m.f2;
-    y[3] -= xnext[3] - x[3] - dt * m.f3;
-    y[4] += dt * du1 - (xnext[4] - x[4] - dt * u[1]);
-    y[5] += dt * du0 - (xnext[5] - x[5] - dt * u[0]);
+    y[0] -= xnext[0] - w[0] - dt * m.f0;
+    y[1] -= xnext[1] - w[1] - dt * m.f1;
+    y[2] -= xnext[2] - w[2] - dt * m.f2;
+    y[3] -= xnext[3] - w[3] - dt * m.f3;
+    y[4] += dt * d[7] - (xnext[4] - w[4] - dt * w[7]);
+    y[5] += dt * d[6] - (xnext[5] - w[5] - dt * w[6]);
     TT_UNROLL
     for (int j = 0; j < NX; j++) {
       dx[j] = y[j];
       x[j] = xnext[j];
     }
   }
-  si.a_pr = a_pr;
-  si.a_du = a_du;
+  si.a_pr = (qmax > tau) ? tau / qmax : 1.0;
+  si.a_du = (bn > tau * bd) ? tau * bd / bn : 1.0;
   si.gphi_d = gd;
 }
 
@@ -688,21 +664,23 @@ struct Trial {
   double J, sumlog, theta;
 };
 
-TT_HD void trial_sweep(const Params& p, const Slot& s, double alpha, Trial& tr) {
+template <bool G>
+TT_HD void trial_sweep(const Params& p, const double* s0, double alpha, Trial& tr) {
   const int N = p.N;
   const double dt = p.dt;
-  double J = 0.0, sl_ = 0.0, th = 0.0;
+  double J = 0.0, sl_ = 0.0, th = 0.0, smin = INFINITY;
   double xn[NX];
   for (int k = N; k >= 0; k--) {
+    const double* ps = s0 + (size_t)k * kStageStride;
     const bool has_x = (k >= 1), has_u = (k < N);
     double w[NW], ref[NW];
     TT_UNROLL
     for (int j = 0; j < NW; j++) {
       const bool on = (j < NX) ? true : has_u;
-      const bool stepped = (j < NX) ? has_x : has_u;
-      w[j] = on ? s.ld(p.oW + k * wW + j) : 0.0;
-      if (stepped) w[j] += alpha * s.ld(p.oDW + k * wDW + j);
-      ref[j] = on ? s.ld(p.oREF + k * wREF + j) : 0.0;
+      const bool var = (j < NX) ? has_x : has_u;
+      w[j] = on ? ldr(ps, rW + j) : 0.0;
+      if (var) w[j] += alpha * ldr(ps, rDW + j);
+      ref[j] = on ? ldr(ps, rREF + j) : 0.0;
     }
     double d6[NX], g[NX];
     TT_UNROLL
@@ -711,21 +689,25 @@ TT_HD void trial_sweep(const Params& p, const Slot& s, double alpha, Trial& tr) 
     double jq = 0.0;
     TT_UNROLL
     for (int j = 0; j < NX; j++) jq += g[j] * d6[j];
-    if (has_x) {
-      TT_UNROLL
-      for (int j = 0; j < NX; j++) {
-        if ((p.xhl >> j) & 1u) sl_ += log(w[j] - p.xl[j]);
-        if ((p.xhu >> j) & 1u) sl_ += log(p.xu[j] - w[j]);
+    double prod = 1.0;
+    TT_UNROLL
+    for (int j = 0; j < NW; j++) {
+      const bool var = (j < NX) ? has_x : has_u;
+      if (var && has_lo<G>(p, j)) {
+        const double s = w[j] - p.lo[j];
+        prod *= s;
+        smin = fmin(smin, s);
+      }
+      if (var && has_up<G>(p, j)) {
+        const double s = p.up[j] - w[j];
+        prod *= s;
+        smin = fmin(smin, s);
       }
     }
+    sl_ += log(prod);
     if (has_u) {
       const double da = w[6] - ref[6], dw_ = w[7] - ref[7];
       jq += (p.R2[0] * da + p.R2[1] * dw_) * da + (p.R2[1] * da + p.R2[2] * dw_) * dw_;
-      TT_UNROLL
-      for (int j = 0; j < NU; j++) {
-        if ((p.uhl >> j) & 1u) sl_ += log(w[NX + j] - p.ul[j]);
-        if ((p.uhu >> j) & 1u) sl_ += log(p.uu[j] - w[NX + j]);
-      }
       double f[4];
       stage_f(p, w, f);
       th += fabs(xn[0] - w[0] - dt * f[0]) + fabs(xn[1] - w[1] - dt * f[1]) + fabs(xn[2] - w[2] - dt * f[2]) +
@@ -736,161 +718,181 @@ TT_HD void trial_sweep(const Params& p, const Slot& s, double alpha, Trial& tr) 
     for (int j = 0; j < NX; j++) xn[j] = w[j];
   }
   tr.J = J;
-  tr.sumlog = sl_;
+  tr.sumlog = (smin > 0.0) ? sl_ : NAN;  // a non-positive slack must never pass as a product of two negatives
   tr.theta = th;
 }
 
 // ------------------------------------------------------------------------------------------------
-// the interior-point driver for one slot
+// the interior-point driver for one lane: state that lives across iterations + one iteration
 // ------------------------------------------------------------------------------------------------
 struct Result {
-  double obj, dual_inf, constr_viol, compl_inf, u0a, u0w;
+  double obj, dual_inf, constr_viol, compl_inf;
   int iters, status;
+};
+
+struct Ipm {
+  double mu, tau, theta_max, theta_min, delta_last;
+  double alpha, alpha_du, mu_step, delta_step;
+  double f_theta[kFilterMax], f_phi[kFilterMax];
+  int f_n, acc_count, ls_fail, iter;
+  bool do_update, x0_infeasible;
 };
 
 TT_HD bool tt_finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
 
-TT_HD void solve_slot(const Params& p, const Slot& s, bool x0_infeasible, Result& res) {
-  double mu = p.mu_init;
-  double tau = fmax(kTauMin, 1.0 - mu);
-  double f_theta[kFilterMax], f_phi[kFilterMax];
-  int f_n = 0;
-  double theta_max = 0.0, theta_min = 0.0, delta_last = 0.0;
-  double alpha = 0.0, alpha_du = 0.0, mu_step = mu, delta_step = 0.0;
-  bool do_update = false;
-  int acc_count = 0, ls_fail = 0, iter = 0, status = -1;
-  Stats st;
+TT_HD void ipm_begin(const Params& p, Ipm& s, bool x0_infeasible) {
+  s.mu = p.mu_init;
+  s.tau = fmax(kTauMin, 1.0 - s.mu);
+  s.theta_max = s.theta_min = 0.0;
+  s.delta_last = 0.0;
+  s.alpha = s.alpha_du = 0.0;
+  s.mu_step = s.mu;
+  s.delta_step = 0.0;
+  s.f_n = 0;
+  s.acc_count = s.ls_fail = s.iter = 0;
+  s.do_update = false;
+  s.x0_infeasible = x0_infeasible;
+}
 
-  for (;; iter++) {
-    bool ok = backward_sweep(p, s, do_update, alpha, alpha_du, mu_step, delta_step, mu, 0.0, st);
-    if (!(tt_finite(st.J) && tt_finite(st.sumlog) && tt_finite(st.theta) && tt_finite(st.rd_inf))) {
-      status = ST_NUMERIC;
-      break;
-    }
-    if (iter == 0) {
-      theta_max = kThetaMaxFact * fmax(1.0, st.theta);
-      theta_min = kThetaMinFact * fmax(1.0, st.theta);
-    }
-    const double cmin = p.n_b ? st.cmin : 0.0;
-    const double s_d = fmax(kSMax, (st.lam1 + st.z1) / (double)(p.m_eq + p.n_b)) / kSMax;
-    const double s_c = p.n_b ? fmax(kSMax, st.z1 / (double)p.n_b) / kSMax : 1.0;
-    const double e_dc = fmax(st.rd_inf / s_d, st.cinf);
-    const double E0 = fmax(e_dc, (p.n_b ? fmax(st.cmax, -cmin) : 0.0) / s_c);
-    if (E0 <= p.tol && st.rd_inf <= kDualInfTol && st.cinf <= kConstrViolTol && st.cmax <= kComplInfTol) {
-      status = ST_CONVERGED;
-      break;
-    }
-    if (E0 <= p.acc_tol && st.rd_inf <= kAccDualInfTol && st.cinf <= kAccConstrViolTol && st.cmax <= kAccComplInfTol)
-      acc_count++;
-    else
-      acc_count = 0;
-    if (p.acc_iter > 0 && acc_count >= p.acc_iter) {
-      status = ST_ACCEPTABLE;
-      break;
-    }
-    if (iter >= p.max_iter) {
-      status = ST_MAX_ITER;
-      break;
-    }
-    if (x0_infeasible) {
-      status = ST_INFEASIBLE_X0;
-      break;
-    }
-    // monotone barrier update (Ipopt MonotoneMuUpdate, fast decrease allowed)
-    for (;;) {
-      const double e_mu = fmax(e_dc, (p.n_b ? fmax(st.cmax - mu, mu - cmin) : 0.0) / s_c);
-      if (!(mu > p.mu_floor && e_mu <= kKappaEps * mu)) break;
-      mu = fmax(p.mu_floor, fmin(kKappaMu * mu, mu * sqrt(mu)));
-      tau = fmax(kTauMin, 1.0 - mu);
-      f_n = 0;
-    }
-    // inertia correction: refactor with growing delta until every 2x2 pivot block is positive definite
-    double delta = 0.0;
-    for (int attempt = 0; !ok && attempt < 40; attempt++) {
-      if (delta == 0.0)
-        delta = (delta_last == 0.0) ? 1e-4 : fmax(1e-20, delta_last / 3.0);
-      else
-        delta *= (delta_last == 0.0) ? 100.0 : 8.0;
-      Stats st2;
-      ok = backward_sweep(p, s, false, 0.0, 0.0, mu, 0.0, mu, delta, st2);
-    }
-    if (!ok) {
-      status = ST_NUMERIC;
-      break;
-    }
-    if (delta > 0.0) delta_last = delta;
-
-    StepInfo si;
-    forward_sweep(p, s, mu, tau, si);
-
-    // filter line search (Waechter & Biegler 2006, Algorithm A)
-    const double theta = st.theta;
-    const double phi = st.J - mu * st.sumlog;
-    double a = si.a_pr;
-    bool accepted = false;
-    for (int bt = 0; bt <= kMaxBacktrack; bt++, a *= kAlphaRed) {
-      Trial tr;
-      trial_sweep(p, s, a, tr);
-      if (!(tt_finite(tr.J) && tt_finite(tr.sumlog) && tt_finite(tr.theta))) continue;
-      const double phi_t = tr.J - mu * tr.sumlog;
-      if (tr.theta > theta_max) continue;
-      bool dominated = false;
-      for (int i = 0; i < f_n; i++)
-        if (tr.theta >= f_theta[i] && phi_t >= f_phi[i]) dominated = true;
-      if (dominated) continue;
-      const bool switching =
-          (si.gphi_d < 0.0) && (a * pow(-si.gphi_d, kSPhi) > kDeltaSw * pow(theta, kSTheta));
-      bool good, ftype = false;
-      if (theta <= theta_min && switching) {
-        good = (phi_t - phi - 10.0 * kEps * fabs(phi) <= kEtaPhi * a * si.gphi_d);
-        ftype = true;
+// One interior-point iteration.  Returns true when the lane is finished (res filled in).
+template <bool G>
+TT_HD bool ipm_iteration(const Params& p, double* s0, Ipm& s, Result& res) {
+  Stats st, st2;
+  bool ok = false;
+  int status = -1;
+  double mu = s.mu, delta = 0.0;
+  // attempt 0: apply the previous step + statistics + factorisation.  attempts >= 1 (rare): inertia correction,
+  // refactor with growing delta until every 2x2 pivot block is positive definite.  One call site on purpose:
+  // the sweep is the bulk of the kernel's code and must not be instantiated twice.
+  for (int attempt = 0; attempt <= 40; attempt++) {
+    const bool first = (attempt == 0);
+    ok = backward_sweep<G>(p, s0, first && s.do_update, s.alpha, s.alpha_du, first ? s.mu_step : mu, s.delta_step, delta,
+                           first ? st : st2);
+    if (first) {
+      const double cmin = p.n_b ? st.cmin : 0.0;
+      const double s_d = fmax(kSMax, (st.lam1 + st.z1) / (double)(p.m_eq + p.n_b)) / kSMax;
+      const double s_c = p.n_b ? fmax(kSMax, st.z1 / (double)p.n_b) / kSMax : 1.0;
+      const double e_dc = fmax(st.rd_inf / s_d, st.cinf);
+      const double E0 = fmax(e_dc, (p.n_b ? fmax(st.cmax, -cmin) : 0.0) / s_c);
+      if (!(tt_finite(st.J) && tt_finite(st.sumlog) && tt_finite(st.theta) && tt_finite(st.rd_inf))) {
+        status = ST_NUMERIC;
       } else {
-        good = (tr.theta - (1.0 - kGammaTheta) * theta <= 10.0 * kEps * fabs(theta)) ||
-               (phi_t - (phi - kGammaPhi * theta) <= 10.0 * kEps * fabs(phi));
+        if (s.iter == 0) {
+          s.theta_max = kThetaMaxFact * fmax(1.0, st.theta);
+          s.theta_min = kThetaMinFact * fmax(1.0, st.theta);
+        }
+        if (E0 <= p.acc_tol && st.rd_inf <= kAccDualInfTol && st.cinf <= kAccConstrViolTol && st.cmax <= kAccComplInfTol)
+          s.acc_count++;
+        else
+          s.acc_count = 0;
+        if (E0 <= p.tol && st.rd_inf <= kDualInfTol && st.cinf <= kConstrViolTol && st.cmax <= kComplInfTol)
+          status = ST_CONVERGED;
+        else if (p.acc_iter > 0 && s.acc_count >= p.acc_iter)
+          status = ST_ACCEPTABLE;
+        else if (s.iter >= p.max_iter)
+          status = ST_MAX_ITER;
+        else if (s.x0_infeasible)
+          status = ST_INFEASIBLE_X0;
       }
-      if (!good) continue;
-      if (!ftype) {
-        const double ft = (1.0 - kGammaTheta) * theta, fp = phi - kGammaPhi * theta;
-        int m = 0;
-        for (int i = 0; i < f_n; i++)
-          if (!(f_theta[i] >= ft && f_phi[i] >= fp)) {
-            f_theta[m] = f_theta[i];
-            f_phi[m] = f_phi[i];
-            m++;
-          }
-        if (m == kFilterMax) m--;
-        f_theta[m] = ft;
-        f_phi[m] = fp;
-        f_n = m + 1;
+      if (status >= 0) break;
+      // monotone barrier update (Ipopt MonotoneMuUpdate, fast decrease allowed)
+      for (;;) {
+        const double e_mu = fmax(e_dc, (p.n_b ? fmax(st.cmax - mu, mu - cmin) : 0.0) / s_c);
+        if (!(mu > p.mu_floor && e_mu <= kKappaEps * mu)) break;
+        mu = fmax(p.mu_floor, fmin(kKappaMu * mu, mu * sqrt(mu)));
+        s.f_n = 0;
       }
-      accepted = true;
-      break;
+      s.mu = mu;
+      s.tau = fmax(kTauMin, 1.0 - mu);
     }
-    if (!accepted) {
-      // Ipopt would enter feasibility restoration; policy: shortest trial step, cleared filter, give up after 3
-      if (++ls_fail >= 3) {
-        status = ST_LINESEARCH;
-        break;
-      }
-      a = si.a_pr * pow(kAlphaRed, (double)kMaxBacktrack);
-      f_n = 0;
-    } else {
-      ls_fail = 0;
-    }
-    alpha = a;
-    alpha_du = si.a_du;
-    mu_step = mu;
-    delta_step = delta;
-    do_update = true;
+    if (ok) break;
+    if (delta == 0.0)
+      delta = (s.delta_last == 0.0) ? 1e-4 : fmax(1e-20, s.delta_last / 3.0);
+    else
+      delta *= (s.delta_last == 0.0) ? 100.0 : 8.0;
   }
-  res.obj = st.J;
-  res.dual_inf = st.rd_inf;
-  res.constr_viol = st.cinf;
-  res.compl_inf = st.cmax;
-  res.iters = iter;
-  res.status = status;
-  res.u0a = s.ld(p.oW + 6);
-  res.u0w = s.ld(p.oW + 7);
+  if (status < 0 && !ok) status = ST_NUMERIC;
+  if (delta > 0.0 && ok) s.delta_last = delta;
+  if (status >= 0) {
+    res.obj = st.J;
+    res.dual_inf = st.rd_inf;
+    res.constr_viol = st.cinf;
+    res.compl_inf = st.cmax;
+    res.iters = s.iter;
+    res.status = status;
+    return true;
+  }
+
+  StepInfo si;
+  forward_sweep<G>(p, s0, mu, s.tau, si);
+
+  // filter line search (Waechter & Biegler 2006, Algorithm A)
+  const double theta = st.theta;
+  const double phi = st.J - mu * st.sumlog;
+  double a = si.a_pr;
+  bool accepted = false;
+  for (int bt = 0; bt <= kMaxBacktrack; bt++, a *= kAlphaRed) {
+    Trial tr;
+    trial_sweep<G>(p, s0, a, tr);
+    if (!(tt_finite(tr.J) && tt_finite(tr.sumlog) && tt_finite(tr.theta))) continue;
+    const double phi_t = tr.J - mu * tr.sumlog;
+    if (tr.theta > s.theta_max) continue;
+    bool dominated = false;
+    for (int i = 0; i < s.f_n; i++)
+      if (tr.theta >= s.f_theta[i] && phi_t >= s.f_phi[i]) dominated = true;
+    if (dominated) continue;
+    // switching condition  a*(-g)^s_phi > delta*theta^s_theta, evaluated in logs (theta = 0: always true)
+    bool good, ftype = false;
+    if (theta <= s.theta_min && si.gphi_d < 0.0 &&
+        (theta <= 0.0 || log(a) + kSPhi * log(-si.gphi_d) > log(kDeltaSw) + kSTheta * log(theta))) {
+      good = (phi_t - phi - 10.0 * kEps * fabs(phi) <= kEtaPhi * a * si.gphi_d);
+      ftype = true;
+    } else {
+      good = (tr.theta - (1.0 - kGammaTheta) * theta <= 10.0 * kEps * fabs(theta)) ||
+             (phi_t - (phi - kGammaPhi * theta) <= 10.0 * kEps * fabs(phi));
+    }
+    if (!good) continue;
+    if (!ftype) {
+      const double ft = (1.0 - kGammaTheta) * theta, fp = phi - kGammaPhi * theta;
+      int m = 0;
+      for (int i = 0; i < s.f_n; i++)
+        if (!(s.f_theta[i] >= ft && s.f_phi[i] >= fp)) {
+          s.f_theta[m] = s.f_theta[i];
+          s.f_phi[m] = s.f_phi[i];
+          m++;
+        }
+      if (m == kFilterMax) m--;
+      s.f_theta[m] = ft;
+      s.f_phi[m] = fp;
+      s.f_n = m + 1;
+    }
+    accepted = true;
+    break;
+  }
+  if (!accepted) {
+    // Ipopt would enter feasibility restoration; policy: shortest trial step, cleared filter, give up after 3
+    if (++s.ls_fail >= 3) {
+      // the iterate is unchanged since the last backward sweep: report it
+      res.obj = st.J;
+      res.dual_inf = st.rd_inf;
+      res.constr_viol = st.cinf;
+      res.compl_inf = st.cmax;
+      res.iters = s.iter;
+      res.status = ST_LINESEARCH;
+      return true;
+    }
+    a = si.a_pr * 9.313225746154785e-10;  // kAlphaRed^kMaxBacktrack = 2^-30
+    s.f_n = 0;
+  } else {
+    s.ls_fail = 0;
+  }
+  s.alpha = a;
+  s.alpha_du = si.a_du;
+  s.mu_step = mu;
+  s.delta_step = delta;
+  s.do_update = true;
+  s.iter++;
+  return false;
 }
 
 // Ipopt's initial push into the interior of the relaxed box (bound_push / bound_frac)
@@ -907,8 +909,74 @@ TT_HD double push_inside(double w, double l, double u, bool hl, bool hu) {
   return w;
 }
 
+// Problem data of one lane -> its scratch slot.  Reads the reference's AoS layouts directly (each lane walks its
+// own contiguous problem record) or, in shared-trajectory mode, applies the window rules of simulation.py:485-499.
+struct ProblemIn {
+  const double* x_init;       // [B][6]
+  const double* ref_states;   // [B][N+1][6] or null (shared-trajectory mode)
+  const double* ref_inputs;   // [B][N][2]
+  const double* z_warm;       // [B][8N+6] or null: cold start at the reference window (mpc_control.py:58-65)
+  const int32_t* k_index;     // [B]   (shared mode)
+  const double* traj_states;  // [T+1][6]
+  const double* traj_inputs;  // [T][2]
+  int T;
+};
+
+TT_HD bool pack_slot(const Params& p, double* s0, const ProblemIn& in, long long b) {
+  const int N = p.N;
+  const long long nz = 8LL * N + 6;
+  const bool shared_mode = (in.ref_states == nullptr);
+  const int kk = shared_mode ? in.k_index[b] : 0;
+  bool bad = false;
+  for (int k = 0; k <= N; k++) {
+    double* ps = s0 + (size_t)k * kStageStride;
+    TT_UNROLL
+    for (int j = 0; j < NW; j++) {
+      if (j >= NX && k >= N) continue;  // no input at the terminal stage
+      double r;
+      if (!shared_mode) {
+        r = (j < NX) ? in.ref_states[(b * (N + 1) + k) * NX + j] : in.ref_inputs[(b * N + k) * NU + (j - NX)];
+      } else {
+        const int T = in.T;
+        if (j < NX)
+          r = in.traj_states[(long long)((kk < T) ? ((kk + k < T) ? kk + k : T) : T) * NX + j];
+        else
+          r = (kk >= T) ? 0.0 : in.traj_inputs[(long long)((kk + k < T) ? kk + k : T - 1) * NU + (j - NX)];
+      }
+      const double g = in.z_warm ? in.z_warm[b * nz + (long long)k * NW + j] : r;
+      const bool hl = ((p.bl >> j) & 1u) != 0, hu = ((p.bu >> j) & 1u) != 0;
+      double w;
+      if (k == 0 && j < NX) {
+        w = in.x_init[b * NX + j];  // x_0 is data
+        if ((hl && w < p.lo[j]) || (hu && w > p.up[j])) bad = true;
+      } else {
+        w = push_inside(g, p.lo[j], p.up[j], hl, hu);
+        if (hl) str(ps, rZL + j, 1.0);
+        if (hu) str(ps, rZU + j, 1.0);
+      }
+      str(ps, rW + j, w);
+      str(ps, rREF + j, r);
+      if (j < NX) str(ps, rLAM + j, 0.0);
+    }
+  }
+  return bad;
+}
+
+// slot -> z_out in the reference's decision-vector layout (trajectory_planning.py:38-60)
+TT_HD void unpack_slot(const Params& p, const double* s0, double* z) {
+  const int N = p.N;
+  for (int k = 0; k <= N; k++) {
+    const double* ps = s0 + (size_t)k * kStageStride;
+    TT_UNROLL
+    for (int j = 0; j < NW; j++) {
+      if (j >= NX && k >= N) continue;
+      z[k * NW + j] = ldr(ps, rW + j);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
-// host side: ttmpc_config -> Params (bound relaxation, packed weights, scratch layout)
+// host side: ttmpc_config -> Params (bound relaxation, packed weights)
 // ------------------------------------------------------------------------------------------------
 inline void relax(double lb, double ub, double* l, double* u, unsigned* hl, unsigned* hu, int bit) {
   const bool bl = (lb > -kNlpInf) && isfinite(lb), bu = (ub < kNlpInf) && isfinite(ub);
@@ -938,21 +1006,20 @@ inline int build_params(const ttmpc_config* c, Params* p) {
   if (!(p->R2[0] > 0.0) || !(p->R2[0] * p->R2[2] - p->R2[1] * p->R2[1] > 0.0)) return TTMPC_E_INVAL;  // R must be PD
   for (int i = 0; i < NX; i++) {
     if (c->x_lb[i] > c->x_ub[i]) return TTMPC_E_INVAL;
-    relax(c->x_lb[i], c->x_ub[i], &p->xl[i], &p->xu[i], &p->xhl, &p->xhu, i);
+    relax(c->x_lb[i], c->x_ub[i], &p->lo[i], &p->up[i], &p->bl, &p->bu, i);
   }
   for (int i = 0; i < NU; i++) {
     if (c->u_lb[i] > c->u_ub[i]) return TTMPC_E_INVAL;
-    relax(c->u_lb[i], c->u_ub[i], &p->ul[i], &p->uu[i], &p->uhl, &p->uhu, i);
+    relax(c->u_lb[i], c->u_ub[i], &p->lo[NX + i], &p->up[NX + i], &p->bl, &p->bu, NX + i);
   }
-  p->n_b = p->N * (__builtin_popcount(p->xhl) + __builtin_popcount(p->xhu) + __builtin_popcount(p->uhl) + __builtin_popcount(p->uhu));
+  p->generic = !(p->bl == 0xFCu && p->bu == 0xFCu);
+  p->n_b = p->N * (__builtin_popcount(p->bl) + __builtin_popcount(p->bu));
   p->m_eq = NX * p->N;
   p->tol = c->tol;
   p->acc_tol = c->acceptable_tol;
   p->mu_init = c->mu_init;
   p->mu_floor = fmin(c->tol, kComplInfTol) / (kKappaEps + 1.0);
-  layout_rows(*p);
   return TTMPC_OK;
 }
-
 
 }  // namespace ttmpc

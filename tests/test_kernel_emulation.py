@@ -59,3 +59,31 @@ def test_infeasible_x0_policy():
     r1 = emu.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs)
     assert r0["status"][1] == 5 and r1["status"][1] == 5
     assert np.array_equal(r0["status"], r1["status"])
+
+
+def test_generic_bound_code_path_equals_specialised_one():
+    cfg = tracking_preset(40)
+    sc = pb.make_scenarios(cfg, 64, seed=13, sigma=pb.SIGMA_WIDE)
+    a = emu.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs)
+    b = emu.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs, force_generic=True)
+    for key in ("z", "u0", "obj", "iters", "status"):
+        assert np.array_equal(a[key], b[key]), key
+    # general masks: x,y bounded, theta free, v one-sided
+    cfg.set_bounds([-200.0, -200.0, -np.inf, -1.0, -0.7, -np.inf], [200.0, 200.0, np.inf, 1.0, 0.7, 6.0], [-4.0, -1.0], [4.0, 1.0])
+    sc = pb.make_scenarios(cfg, 64, seed=14, families=False)
+    r0 = oracle.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs)
+    r1 = emu.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs)
+    assert_parity(cfg, r1, r0, sc.x_init)
+
+
+def test_shared_trajectory_mode_in_emulation(traj):
+    S, U = traj
+    cfg = tracking_preset(40)
+    rng = np.random.default_rng(5)
+    k = np.concatenate([rng.integers(0, 460, size=40), [0, 360, 361, 399, 400, 401, 1000]]).astype(np.int32)
+    xs, us = pb.windows_batch(S, U, k, 40)
+    x = xs[:, 0, :] + rng.normal(0, 0.02, size=(len(k), 6))
+    a = emu.solve_batch(cfg, x, xs, us)
+    b = emu.solve_batch(cfg, x, k_index=k, traj_states=S, traj_inputs=U)
+    for key in ("z", "u0", "obj", "iters", "status"):
+        assert np.array_equal(a[key], b[key]), key

@@ -16,24 +16,34 @@ def lib():
         src = os.path.join(_HERE, "kernel_emu.cpp")
         core = os.path.join(_HERE, "..", "car_trailer_mpc_b200", "csrc", "ttmpc_core.cuh")
         if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(core)):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", _SO, src, "-lm"])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-DTTMPC_BANK=64", "-fPIC", "-shared", "-o", _SO, src, "-lm"])
         _lib = ctypes.CDLL(_SO)
     return _lib
 
 
-def solve_batch(cfg, x_init, ref_states, ref_inputs, z_warm=None):
+def solve_batch(cfg, x_init, ref_states=None, ref_inputs=None, z_warm=None, k_index=None, traj_states=None,
+                traj_inputs=None, force_generic=False):
     N = cfg.horizon
     x = np.ascontiguousarray(x_init, dtype=np.float64).reshape(-1, 6)
     B = x.shape[0]
-    xs = np.ascontiguousarray(ref_states, dtype=np.float64).reshape(B, N + 1, 6)
-    us = np.ascontiguousarray(ref_inputs, dtype=np.float64).reshape(B, N, 2)
+    xs = us = ki = ts = tu = None
+    T = 0
+    if ref_states is not None:
+        xs = np.ascontiguousarray(ref_states, dtype=np.float64).reshape(B, N + 1, 6)
+        us = np.ascontiguousarray(ref_inputs, dtype=np.float64).reshape(B, N, 2)
+    else:
+        ki = np.ascontiguousarray(k_index, dtype=np.int32).reshape(B)
+        ts = np.ascontiguousarray(traj_states, dtype=np.float64)
+        tu = np.ascontiguousarray(traj_inputs, dtype=np.float64)
+        T = tu.shape[0]
     zw = None if z_warm is None else np.ascontiguousarray(z_warm, dtype=np.float64).reshape(B, 8 * N + 6)
     z = np.empty((B, 8 * N + 6)); u0 = np.empty((B, 2)); obj = np.empty(B); kkt = np.empty((B, 3))
     it = np.empty(B, np.int32); st = np.empty(B, np.int32)
     dp = ctypes.POINTER(ctypes.c_double); ip = ctypes.POINTER(ctypes.c_int32)
     P = lambda a, t=dp: None if a is None else a.ctypes.data_as(t)
-    rc = lib().ttmpc_emu_solve_batch(ctypes.byref(cfg), ctypes.c_int64(B), P(x), P(xs), P(us), P(zw), P(z), P(u0), P(obj),
-                                     P(kkt), P(it, ip), P(st, ip))
+    rc = lib().ttmpc_emu_solve_batch(ctypes.byref(cfg), ctypes.c_int64(B), P(x), P(xs), P(us), P(ki, ip), P(ts), P(tu),
+                                     ctypes.c_int32(T), P(zw), P(z), P(u0), P(obj), P(kkt), P(it, ip), P(st, ip),
+                                     ctypes.c_int(int(force_generic)))
     if rc:
         raise RuntimeError(f"emu rc={rc}")
     return dict(z=z, u0=u0, obj=obj, kkt=kkt, iters=it, status=st)

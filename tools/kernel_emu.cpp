@@ -1,9 +1,10 @@
 // kernel_emu.cpp -- TEST-ONLY host build of the device solver core (ttmpc_core.cuh).
 //
-// Compiles the exact per-slot functions the CUDA solve kernel runs (backward/forward/trial sweeps and the
-// interior-point driver) with plain g++, over the same slot-interleaved scratch layout, so that the kernel's
-// logic can be compared with the oracle on a machine without a GPU (tests/test_kernel_emulation.py).
-// It is NOT part of the product: libttmpc.so does not contain it and has no CPU path.
+// Compiles the exact per-lane functions the CUDA solve kernel runs (pack_slot, the backward/forward/trial sweeps,
+// ipm_iteration, unpack_slot) with plain g++, over the same bank-interleaved scratch layout (with a small bank,
+// -DTTMPC_BANK=64), so that the kernel's logic can be compared with the oracle on a machine without a GPU
+// (tests/test_kernel_emulation.py).  It is NOT part of the product: libttmpc.so does not contain it and has
+// no CPU path.
 #include <math.h>
 #include <stdlib.h>
 
@@ -13,60 +14,44 @@
 
 using namespace ttmpc;
 
+template <bool G>
+static void run(const Params& p, std::vector<double>& scratch, int64_t B, const ProblemIn& in, double* z_out, double* u0_out,
+                double* obj_out, double* kkt_out, int32_t* iters_out, int32_t* status_out) {
+  const size_t nz = 8 * (size_t)p.N + 6;
+  // emulate a few persistent lanes with refill: lane l takes problems l, l+L, l+2L, ...
+  const int64_t L = B < 48 ? B : 48;
+  for (int64_t l = 0; l < L; l++) {
+    double* s0 = slot_ptr(scratch.data(), p.N, (size_t)l);
+    for (int64_t b = l; b < B; b += L) {
+      Ipm st;
+      Result r;
+      const bool bad = pack_slot(p, s0, in, b);
+      ipm_begin(p, st, bad);
+      while (!ipm_iteration<G>(p, s0, st, r)) {
+      }
+      if (z_out) unpack_slot(p, s0, z_out + b * nz);
+      if (u0_out) { u0_out[b * 2] = ldr(s0, rW + 6); u0_out[b * 2 + 1] = ldr(s0, rW + 7); }
+      if (obj_out) obj_out[b] = r.obj;
+      if (kkt_out) { kkt_out[b * 3] = r.dual_inf; kkt_out[b * 3 + 1] = r.constr_viol; kkt_out[b * 3 + 2] = r.compl_inf; }
+      if (iters_out) iters_out[b] = r.iters;
+      if (status_out) status_out[b] = r.status;
+    }
+  }
+}
+
 extern "C" int ttmpc_emu_solve_batch(const ttmpc_config* cfg, int64_t B, const double* x_init, const double* ref_states,
-                                     const double* ref_inputs, const double* z_warm, double* z_out, double* u0_out,
-                                     double* obj_out, double* kkt_out, int32_t* iters_out, int32_t* status_out) {
+                                     const double* ref_inputs, const int32_t* k_index, const double* traj_states,
+                                     const double* traj_inputs, int32_t T, const double* z_warm, double* z_out,
+                                     double* u0_out, double* obj_out, double* kkt_out, int32_t* iters_out,
+                                     int32_t* status_out, int force_generic) {
   Params p;
   int rc = build_params(cfg, &p);
   if (rc) return rc;
-  const int N = p.N;
-  const size_t cap = (size_t)B;  // same interleaving as on the device
-  const size_t nz = 8 * (size_t)N + 6;
-  std::vector<double> scratch((size_t)p.rows * cap, NAN);
-  // pack (same values as ttmpc_pack_kernel)
-  for (int64_t b = 0; b < B; b++) {
-    Slot s{scratch.data(), cap, (size_t)b};
-    for (int k = 0; k <= N; k++)
-      for (int j = 0; j < NW; j++) {
-        if (j >= NX && k >= N) continue;
-        const double r = (j < NX) ? ref_states[(b * (N + 1) + k) * NX + j] : ref_inputs[(b * N + k) * NU + (j - NX)];
-        const double g = z_warm ? z_warm[b * nz + k * NW + j] : r;
-        const bool hl = (j < NX) ? ((p.xhl >> j) & 1u) : ((p.uhl >> (j - NX)) & 1u);
-        const bool hu = (j < NX) ? ((p.xhu >> j) & 1u) : ((p.uhu >> (j - NX)) & 1u);
-        double w;
-        if (k == 0 && j < NX) {
-          w = x_init[b * NX + j];
-        } else {
-          w = push_inside(g, (j < NX) ? p.xl[j] : p.ul[j - NX], (j < NX) ? p.xu[j] : p.uu[j - NX], hl, hu);
-          if (hl) s.st(p.oZL + k * wZ + j, 1.0);
-          if (hu) s.st(p.oZU + k * wZ + j, 1.0);
-        }
-        s.st(p.oW + k * wW + j, w);
-        s.st(p.oREF + k * wREF + j, r);
-        if (j < NX) s.st(p.oLAM + k * wLAM + j, 0.0);
-      }
-  }
-  for (int64_t b = 0; b < B; b++) {
-    Slot s{scratch.data(), cap, (size_t)b};
-    bool bad = false;
-    for (int j = 0; j < NX; j++) {
-      const double x = s.ld(p.oW + j);
-      if (((p.xhl >> j) & 1u) && x < p.xl[j]) bad = true;
-      if (((p.xhu >> j) & 1u) && x > p.xu[j]) bad = true;
-    }
-    Result r;
-    solve_slot(p, s, bad, r);
-    if (u0_out) { u0_out[b * 2] = r.u0a; u0_out[b * 2 + 1] = r.u0w; }
-    if (obj_out) obj_out[b] = r.obj;
-    if (kkt_out) { kkt_out[b * 3] = r.dual_inf; kkt_out[b * 3 + 1] = r.constr_viol; kkt_out[b * 3 + 2] = r.compl_inf; }
-    if (iters_out) iters_out[b] = r.iters;
-    if (status_out) status_out[b] = r.status;
-    if (z_out)
-      for (int k = 0; k <= N; k++)
-        for (int j = 0; j < NW; j++) {
-          if (j >= NX && k >= N) continue;
-          z_out[b * nz + k * NW + j] = s.ld(p.oW + k * wW + j);
-        }
-  }
+  std::vector<double> scratch(scratch_doubles(p.N, 1), NAN);
+  ProblemIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T};
+  if (p.generic || force_generic)
+    run<true>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
+  else
+    run<false>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
   return 0;
 }
