@@ -10,7 +10,7 @@ import os
 
 from .config import Config
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libttmpc.so")
+_LIB_PATH = os.environ.get("TTMPC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libttmpc.so")
 _lib = None
 
 c_dp = ctypes.c_void_p  # raw device/host pointers are passed as integers

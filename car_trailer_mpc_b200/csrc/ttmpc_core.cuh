@@ -103,6 +103,17 @@ TT_HD bool has_up(const Params& p, int j) {
 TT_HD double ldr(const double* ps, int row) { return ps[(size_t)row * kBank]; }
 TT_HD void str(double* ps, int row, double v) { ps[(size_t)row * kBank] = v; }
 
+// L1 prefetch of rows [row0, row0+n) of a stage: the sweeps walk the stages sequentially with fully predictable
+// addresses, so the next stage is requested while the current one is being computed (no registers tied up).
+TT_HD void prefetch_rows(const double* ps, int row0, int n) {
+#if defined(__CUDA_ARCH__)
+  TT_UNROLL
+  for (int r = 0; r < n; r++) asm volatile("prefetch.global.L1 [%0];" ::"l"(ps + (size_t)(row0 + r) * kBank));
+#else
+  (void)ps; (void)row0; (void)n;
+#endif
+}
+
 // pointer to (stage 0, row 0) of a slot inside a scratch allocation of `nbanks` banks
 TT_HD double* slot_ptr(double* scratch, int N, size_t slot) {
   const size_t bank = slot / kBank, lane = slot % kBank;
@@ -110,13 +121,60 @@ TT_HD double* slot_ptr(double* scratch, int N, size_t slot) {
 }
 inline size_t scratch_doubles(int N, size_t nbanks) { return nbanks * (size_t)(N + 1) * kStageStride; }
 
-TT_HD void tt_sincos(double x, double& s, double& c) {
+// ------------------------------------------------------------------------------------------------
+// lean math: the library sincos / division are ~100 / ~15 instructions each with 64-bit constants materialised by
+// MOV pairs and slow-path branches; the solver evaluates 12 sincos and ~40 reciprocals per stage and iteration.
+// ------------------------------------------------------------------------------------------------
+// 1/x for normal positive-or-negative x (slacks, pivots, cos(phi)): hardware seed + 2 Newton steps (|err| ~ 1 ulp).
+TT_HD double tt_rcp(double x) {
 #if defined(__CUDA_ARCH__)
-  sincos(x, &s, &c);
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
 #else
-  s = sin(x);
-  c = cos(x);
+  return 1.0 / x;
 #endif
+}
+
+// sin and cos on [-pi/4, pi/4]: fdlibm kernel polynomials (k_sin.c / k_cos.c), Horner with FMA
+TT_HD void sincos_kernel(double r, double& s, double& c) {
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = fma(ps, z, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  s = fma(r * z, ps, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, z, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  c = fma(z * z, pc, fma(-0.5, z, 1.0));
+}
+
+// sin and cos for |x| < ~1e5 (angles; theta is box-bounded to [-pi,pi] in the reference): two-term Cody-Waite
+// reduction by pi/2 with the round-to-nearest magic constant, then the kernels above.
+TT_HD void tt_sincos(double x, double& s, double& c) {
+  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+  const double t = fma(x, 6.36619772367581382433e-01, kMagic);
+  const double kf = t - kMagic;
+  int64_t tb;
+  memcpy(&tb, &t, sizeof tb);
+  const int k = (int)(uint32_t)tb;  // low mantissa bits hold the integer
+  double r = fma(-kf, 1.57079632679489655800e+00, x);
+  r = fma(-kf, 6.12323399573676603587e-17, r);
+  double s0, c0;
+  sincos_kernel(r, s0, c0);
+  const double ss = (k & 1) ? c0 : s0;
+  const double cc = (k & 1) ? s0 : c0;
+  s = (k & 2) ? -ss : ss;
+  c = ((k + 1) & 2) ? -cc : cc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -133,7 +191,7 @@ TT_HD void stage_lin(const Params& p, const double* x, Lin& m) {
   tt_sincos(x[3], m.sps, m.cps);
   double sph, cph;
   tt_sincos(x[4], sph, cph);
-  m.t = sph / cph;
+  m.t = sph * tt_rcp(cph);
   m.s2 = 1.0 + m.t * m.t;
   m.v = x[5];
   m.g1 = 1.0 + p.cML * m.cps;
@@ -159,7 +217,7 @@ TT_HD void stage_f(const Params& p, const double* x, double* f) {
   tt_sincos(x[2], sth, cth);
   tt_sincos(x[3], sps, cps);
   tt_sincos(x[4], sph, cph);
-  const double t = sph / cph, v = x[5];
+  const double t = sph * tt_rcp(cph), v = x[5];
   f[0] = v * cth;
   f[1] = v * sth;
   f[2] = v * t * p.iL1;
@@ -257,6 +315,12 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
     }
     TT_UNROLL
     for (int j = 0; j < NX; j++) lam[j] = has_x ? ldr(ps, rLAM + j) : 0.0;
+    if (has_x) {  // request stage k-1 now
+      const double* pn = ps - kStageStride;
+      prefetch_rows(pn, rW, do_update ? 2 * NW : NW);  // W (and DW, adjacent rows)
+      prefetch_rows(pn, rREF, NW + NX);                // REF and LAM (adjacent rows)
+      prefetch_rows(pn, rZL + (G ? 0 : 2), G ? 2 * NW : 14);  // ZL, ZU (default pattern: rows 2..7 of each)
+    }
 
     // ---------------------------------------------------------------- (i) apply the previous step
     if (do_update) {
@@ -267,13 +331,13 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
         const bool var = (j < NX) ? has_x : has_u;
         double sig = delta_step, g = 0.0;
         if (var && has_lo<G>(p, j)) {
-          const double rl = 1.0 / (w[j] - p.lo[j]);
+          const double rl = tt_rcp(w[j] - p.lo[j]);
           sig += zl[j] * rl;
           g -= mu_step * rl;
           zl[j] += alpha_du * (rl * (mu_step - zl[j] * dw[j]) - zl[j]);
         }
         if (var && has_up<G>(p, j)) {
-          const double ru = 1.0 / (p.up[j] - w[j]);
+          const double ru = tt_rcp(p.up[j] - w[j]);
           sig += zu[j] * ru;
           g += mu_step * ru;
           zu[j] += alpha_du * (ru * (mu_step + zu[j] * dw[j]) - zu[j]);
@@ -354,7 +418,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
         const bool var = (j < NX) ? has_x : has_u;
         double sg = delta, gg = 0.0;
         if (var && has_lo<G>(p, j)) {
-          const double sl = w[j] - p.lo[j], rl = 1.0 / sl;
+          const double sl = w[j] - p.lo[j], rl = tt_rcp(sl);
           if (do_update) {  // kappa_sigma safeguard, Waechter & Biegler eq. (16)
             zl[j] = fmax(fmin(zl[j], kmu_hi * rl), kmu_lo * rl);
             str(ps, rZL + j, zl[j]);
@@ -368,7 +432,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
           cmin = fmin(cmin, c);
         }
         if (var && has_up<G>(p, j)) {
-          const double su = p.up[j] - w[j], ru = 1.0 / su;
+          const double su = p.up[j] - w[j], ru = tt_rcp(su);
           if (do_update) {
             zu[j] = fmax(fmin(zu[j], kmu_hi * ru), kmu_lo * ru);
             str(ps, rZU + j, zu[j]);
@@ -463,7 +527,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
       const double r11 = p.R2[2] + sig[7] + dt2 * P[SY(4, 4)];
       const double det = r00 * r11 - r01 * r01;
       if (!(r00 > 0.0) || !(det > 0.0)) ok = false;
-      const double idet = 1.0 / det;
+      const double idet = tt_rcp(det);
       const double i00 = r11 * idet, i01 = -r01 * idet, i11 = r00 * idet;
       // S = B' T: row a = dt*T[5][:], row omega = dt*T[4][:]
       double S0[NX], S1[NX], K0[NX], K1[NX];
@@ -578,6 +642,14 @@ TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, Ste
     w[7] = has_u ? ldr(ps, rW + 7) : 0.0;
     TT_UNROLL
     for (int j = 0; j < NW; j++) ref[j] = ((j < NX) || has_u) ? ldr(ps, rREF + j) : 0.0;
+    if (has_u) {  // request stage k+1 (and the states of k+2, read one stage ahead)
+      const double* pn = ps + kStageStride;
+      prefetch_rows(pn, rW + NX, NU);
+      prefetch_rows(pn + kStageStride, rW, NX);
+      prefetch_rows(pn, rREF, NW);
+      prefetch_rows(pn, rZL + (G ? 0 : 2), G ? 2 * NW : 14);
+      prefetch_rows(pn, rKF, 16);
+    }
     // du = -K dx - (kff0 + mu*kff1)
     d[6] = d[7] = 0.0;
     if (has_u) {
@@ -612,7 +684,7 @@ TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, Ste
       if (!var) continue;
       double gj = g[j];
       if (has_lo<G>(p, j)) {
-        const double rl = 1.0 / (w[j] - p.lo[j]), z = ldr(ps, rZL + j);
+        const double rl = tt_rcp(w[j] - p.lo[j]), z = ldr(ps, rZL + j);
         gj -= mu * rl;
         qmax = fmax(qmax, -d[j] * rl);
         const double ndz = z - rl * (mu - z * d[j]);  // -dz
@@ -622,7 +694,7 @@ TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, Ste
         }
       }
       if (has_up<G>(p, j)) {
-        const double ru = 1.0 / (p.up[j] - w[j]), z = ldr(ps, rZU + j);
+        const double ru = tt_rcp(p.up[j] - w[j]), z = ldr(ps, rZU + j);
         gj += mu * ru;
         qmax = fmax(qmax, d[j] * ru);
         const double ndz = z - ru * (mu + z * d[j]);
@@ -682,6 +754,7 @@ TT_HD void trial_sweep(const Params& p, const double* s0, double alpha, Trial& t
       if (var) w[j] += alpha * ldr(ps, rDW + j);
       ref[j] = on ? ldr(ps, rREF + j) : 0.0;
     }
+    if (has_x) prefetch_rows(ps - kStageStride, rW, 3 * NW);  // W, DW, REF of stage k-1 (adjacent rows)
     double d6[NX], g[NX];
     TT_UNROLL
     for (int j = 0; j < NX; j++) d6[j] = w[j] - ref[j];
