@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: batched NMPC solves/sec (horizon 40, 65 536 scenarios per step and GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--horizon H]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); every rank owns an independent shard of B scenarios
+(weak scaling, no data-path collective: the solve has no exchange step) and NCCL only gathers the per-scenario
+first controls / status after each step, as BASELINE.json's north star prescribes.  Rank 0 prints ONE JSON line.
+
+A "step" = one pass of the hot path over one batch of synthetic scenarios (SURVEY.md section 8(d) config 2 at
+B = 65 536): perturbed initial states around the shipped reference trajectory, per-problem reference windows,
+`MPCTrackingControl` preset (Ipopt defaults, tol 1e-8), cold start.
+
+  value     whole-job solves/s with inputs already resident in HBM (CUDA events, max over ranks).
+  e2e       same metric through the public API with HOST (pinned) buffers: H2D of x_init/ref windows, solve,
+            D2H of the full decision vectors + u0/status, all inside the timed region.
+  roofline  dominant kernel = ttmpc_solve_kernel.  It is bound by the non-tensor FP64 pipe / dependent-issue
+            latency, not by HBM or tensor cores; `achieved` = algorithmic FP64 flop
+            (mean_iters * (2500 N + 500) per solve) / kernel time, `peak` = the FP64 FMA peak measured in this run
+            by the library's DFMA microbenchmark (MEASURED_PEAKS.json has no FP64 figure).  The HBM view
+            (algorithmic bytes 5304 B/solve against the measured copy bandwidth) is reported beside it.
+  cpu_baseline  the CPU oracle (C port of the same algorithm -- CasADi/Ipopt cannot be installed here) on all
+            host cores over a bounded sample of the same workload.
+
+--impl reference times that CPU oracle as the stand-in for the reference's Ipopt path (kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "nmpc_solves_per_sec_N40_B65536"
+UNIT = "solves/s"
+FLOP_STAGE, FLOP_TERM = 2500.0, 500.0  # algorithmic FP64 flop per stage / terminal per IPM iteration
+
+
+def algorithmic_bytes_per_solve(N: int) -> int:
+    """read p = (8N+12) doubles, write z* = (8N+6) doubles + 40 B of scalars."""
+    return (8 * N + 12) * 8 + (8 * N + 6) * 8 + 40
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self._halt = threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def finish(self) -> dict:
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def workload_config(N: int, B: int, world: int) -> dict:
+    return {
+        "workload": f"batched NMPC tracking (SURVEY 8(d) config 2 at full size): horizon {N}, {B} perturbed initial "
+                    "states per step and GPU around the shipped trajectory (test_cases.json SE(2) families), "
+                    "per-problem reference windows, MPCTrackingControl preset (tol 1e-8), cold start",
+        "horizon": N, "batch_per_gpu": B, "tol": 1e-8,
+        "sharding": f"scenario-parallel x{world}, NCCL gather of u0/status only",
+        "cache": f"inputs+outputs ({(B * (16 * N + 18) * 8) >> 20} MiB) and solver scratch (>1 GiB) exceed the 126 MB L2; no flush needed",
+    }
+
+
+def make_batch(cfg, B: int, rank: int):
+    from car_trailer_mpc_b200 import problem as pb
+
+    return pb.make_scenarios(cfg, B, seed=20251018 + 7919 * rank)
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    """CPU arm: the oracle port on all host threads, bounded sample per step. Rank 0 only."""
+    if rank != 0:
+        return
+    from car_trailer_mpc_b200 import tracking_preset
+    from oracle import oracle
+
+    cores = os.cpu_count() or 1
+    cfg = tracking_preset(args.horizon)
+    cfg.max_iter = 200
+    sample = min(args.batch, 8192)
+    sc = make_batch(cfg, sample, 0)
+    oracle.build()
+    times = []
+    iters = None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = oracle.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs, nthreads=cores)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+        iters = r["iters"]
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": dict(workload_config(args.horizon, args.batch, args.gpus),
+                       cpu_sample=f"each CPU step solves the first {sample} scenarios of the batch"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} scenarios per step x {args.steps} steps, CPU oracle (C, pthreads); "
+                                   "CasADi/Ipopt (the reference's solver) is not installable in this image"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mean_iters": float(np.mean(iters)),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="scenarios per step and GPU")
+    ap.add_argument("--horizon", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from car_trailer_mpc_b200 import BatchSolver, tracking_preset
+    from car_trailer_mpc_b200 import problem as pb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the solver has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, B = args.horizon, args.batch
+    cfg = tracking_preset(N)
+    cfg.max_iter = 200
+    sc = make_batch(cfg, B, rank)
+    solver = BatchSolver(cfg, local_rank)
+    fp64_peak_gflops = solver.measure_fp64_peak()
+
+    # ---- device-resident inputs (value) and pinned host buffers (e2e)
+    x_d = torch.from_numpy(sc.x_init).to(dev)
+    xs_d = torch.from_numpy(sc.ref_states).to(dev)
+    us_d = torch.from_numpy(sc.ref_inputs).to(dev)
+    x_h = torch.from_numpy(sc.x_init).pin_memory()
+    xs_h = torch.from_numpy(sc.ref_states).pin_memory()
+    us_h = torch.from_numpy(sc.ref_inputs).pin_memory()
+    nz = 8 * N + 6
+    z_h = torch.empty((B, nz), dtype=torch.float64).pin_memory()
+    u0_h = torch.empty((B, 2), dtype=torch.float64).pin_memory()
+    st_h = torch.empty(B, dtype=torch.int32).pin_memory()
+    gather_u0 = torch.empty((world * B, 2), dtype=torch.float64, device=dev) if world > 1 else None
+    gather_st = torch.empty(world * B, dtype=torch.int32, device=dev) if world > 1 else None
+
+    def step_resident():
+        r = solver.solve(x_d, xs_d, us_d)
+        if world > 1:  # NCCL only gathers per-scenario results (no exchange inside the solve)
+            dist.all_gather_into_tensor(gather_u0, r["u0"])
+            dist.all_gather_into_tensor(gather_st, r["status"])
+        return r
+
+    def step_e2e():
+        xa = x_h.to(dev, non_blocking=True)
+        xsa = xs_h.to(dev, non_blocking=True)
+        usa = us_h.to(dev, non_blocking=True)
+        r = solver.solve(xa, xsa, usa)
+        z_h.copy_(r["z"], non_blocking=True)
+        u0_h.copy_(r["u0"], non_blocking=True)
+        st_h.copy_(r["status"], non_blocking=True)
+        return r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l_before = solver.launch_count()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record()
+        r = None
+        for i in range(steps):
+            r = fn()
+            ev[i + 1].record()
+        barrier()
+        per = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)])
+        total = ev[0].elapsed_time(ev[steps])
+        return total, per, r, solver.launch_count() - l_before
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms, per_ms, r, launches = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.finish()
+    e2e_total_ms, _, _, _ = timed(step_e2e, max(3, min(args.steps, 10)), 2)
+    e2e_steps = max(3, min(args.steps, 10))
+
+    iters = r["iters"].cpu().numpy()
+    status = r["status"].cpu().numpy()
+    kkt = r["kkt"].cpu().numpy()
+
+    # max over ranks (device time)
+    t = torch.tensor([total_ms, e2e_total_ms, float(np.percentile(per_ms, 99)), float(np.percentile(per_ms, 50))],
+                     dtype=torch.float64, device=dev)
+    agg = torch.tensor([float(iters.sum()), float((status <= 1).sum()), float(B)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    total_ms, e2e_total_ms, p99_ms, p50_ms = [float(v) for v in t.cpu()]
+    iters_sum, ok_sum, b_sum = [float(v) for v in agg.cpu()]
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        solves_per_step = world * B
+        value = solves_per_step / (ms_per_step * 1e-3)
+        e2e_value = solves_per_step / (e2e_total_ms / e2e_steps * 1e-3)
+        mean_iters = iters_sum / b_sum
+        # roofline of the dominant kernel (per GPU, rank 0's launch times; one launch per step)
+        kernel_ms = float(np.mean(per_ms))
+        flop_per_launch = B * mean_iters * (FLOP_STAGE * N + FLOP_TERM)
+        achieved_tf = flop_per_launch / (kernel_ms * 1e-3) * 1e-12
+        peak_tf = fp64_peak_gflops * 1e-3
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        bytes_per_launch = B * algorithmic_bytes_per_solve(N)
+        hbm_achieved = bytes_per_launch / (kernel_ms * 1e-3) * 1e-9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_kernel_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(N, B, world),
+            "p50_step_ms": p50_ms, "p99_step_ms": p99_ms, "control_period_ms": 50.0,
+            "mean_iters": mean_iters, "max_iters": int(iters.max()), "frac_success": ok_sum / b_sum,
+            "kkt_max": {"dual_inf": float(kkt[status == 0, 0].max()), "constr_viol": float(kkt[status == 0, 1].max()),
+                        "compl": float(kkt[status == 0, 2].max())},
+            "roofline": {
+                "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "traffic": traffic,
+                "note": "non-tensor FP64 pipe; algorithmic flop = mean_iters*(2500*N+500) per solve (SURVEY 8(d)); peak = "
+                        "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                        "algorithmic_bytes_per_solve": algorithmic_bytes_per_solve(N), "peak_source": hbm_src},
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(x_h.numel() + xs_h.numel() + us_h.numel()) * 8,
+                    "d2h_bytes_per_step": int(z_h.numel() + u0_h.numel()) * 8 + int(st_h.numel()) * 4,
+                    "ms_per_step": e2e_total_ms / e2e_steps, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "kernels": {k: v for k, v in solver.kernel_launches().items() if v},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import oracle
+
+            cores = os.cpu_count() or 1
+            sample = min(B, 16384)
+            oracle.build()
+            oracle.solve_batch(cfg, sc.x_init[:256], sc.ref_states[:256], sc.ref_inputs[:256], nthreads=cores)
+            t0 = time.perf_counter()
+            ro = oracle.solve_batch(cfg, sc.x_init[:sample], sc.ref_states[:sample], sc.ref_inputs[:sample], nthreads=cores)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"first {sample} scenarios of the batch, CPU oracle (C, pthreads, all host threads); "
+                                              "stand-in for CasADi/Ipopt, which is not installable in this image",
+                                    "mean_iters": float(ro["iters"].mean())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

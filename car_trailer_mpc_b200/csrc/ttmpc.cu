@@ -13,6 +13,7 @@
 // There is NO CPU fallback in this library: without a CUDA device ttmpc_create fails with TTMPC_E_NODEV.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -263,6 +264,10 @@ int ttmpc_create(const ttmpc_config* cfg, int device, ttmpc_handle** out) {
   if (ce != cudaSuccess || sms <= 0 || per_sm <= 0) {
     delete h;
     return TTMPC_E_CUDA;
+  }
+  if (const char* e = getenv("TTMPC_BLOCKS_PER_SM")) {  // tuning aid: cap the resident CTAs per SM
+    const int v = atoi(e);
+    if (v >= 1 && v < per_sm) per_sm = v;
   }
   h->max_blocks = sms * per_sm;
   if (cudaMalloc(&h->counter, sizeof(unsigned long long)) != cudaSuccess) {
