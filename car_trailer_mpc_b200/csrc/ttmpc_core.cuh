@@ -903,8 +903,11 @@ TT_HD bool ipm_iteration(const Params& p, double* s0, Ipm& s, Result& res) {
   const double theta = st.theta;
   const double phi = st.J - mu * st.sumlog;
   double a = si.a_pr;
-  bool accepted = false;
-  for (int bt = 0; bt <= kMaxBacktrack; bt++, a *= kAlphaRed) {
+  // Round-off regime (analogue of Ipopt's tiny-step rule in function values): predicted change of phi below its
+  // resolution and constraint violation far below tol -> theta/phi comparisons are noise; take the full step.
+  const bool roundoff_step = (fabs(si.gphi_d) <= 100.0 * kEps * fmax(1.0, fabs(phi))) && (theta <= 1e-2 * p.tol);
+  bool accepted = roundoff_step;
+  for (int bt = 0; !roundoff_step && bt <= kMaxBacktrack; bt++, a *= kAlphaRed) {
     Trial tr;
     trial_sweep<G>(p, s0, a, tr);
     if (!(tt_finite(tr.J) && tt_finite(tr.sumlog) && tt_finite(tr.theta))) continue;

@@ -36,6 +36,7 @@
  *   the reference NLP is feasible; z_out[0:6] = x_init.
  */
 #include <math.h>
+#include <stdio.h>
 #include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -648,7 +649,13 @@ int ttmpc_oracle_solve(const ttmpc_config* cfg, const double* x_init, const doub
     double alpha = a_pr;
     int accepted = 0;
     eval_t tr;
-    for (int bt = 0; bt <= MAX_BACKTRACK; bt++, alpha *= ALPHA_RED) {
+    /* Round-off regime (the analogue of Ipopt's tiny-step rule, expressed in function values): when the
+     * predicted change of the barrier objective is below the resolution of phi and the constraint violation
+     * is already far below the tolerance, neither theta nor phi can be compared reliably (c'lambda terms of
+     * size eps*|x| make grad(phi)'d come out with either sign) -- take the full fraction-to-boundary step. */
+    const int roundoff_step = (fabs(gphi_d) <= 100.0 * MACH_EPS * fmax(1.0, fabs(phi))) && (theta <= 1e-2 * p->tol);
+    if (roundoff_step) accepted = 1;
+    for (int bt = 0; !roundoff_step && bt <= MAX_BACKTRACK; bt++, alpha *= ALPHA_RED) {
       for (int i = 0; i < NX; i++) w->tx[0][i] = it->x[0][i];
       for (int k = 0; k <= N; k++) {
         if (k >= 1)
@@ -676,6 +683,11 @@ int ttmpc_oracle_solve(const ttmpc_config* cfg, const double* x_init, const doub
       accepted = 1;
       break;
     }
+#ifdef ORACLE_DEBUG
+    { double ms=0; for (int k=0;k<=N;k++){ if(k>=1) for(int i=0;i<NX;i++) ms=fmax(ms,fabs(w->dx[k][i])/(1+fabs(it->x[k][i]))); if(k<N) for(int i=0;i<NU;i++) ms=fmax(ms,fabs(w->du[k][i])/(1+fabs(it->u[k][i]))); }
+      fprintf(stderr, "   max rel step %.3e\n", ms); }
+    fprintf(stderr, "it %d mu %.2e theta %.3e phi %.12e gphi_d %.3e a_pr %.3e a_du %.3e alpha %.3e acc %d rd %.2e\n", iter, mu, theta, phi, gphi_d, a_pr, a_du, alpha, accepted, rd_inf);
+#endif
     if (!accepted) {
       /* Ipopt would switch to feasibility restoration here.  Policy: take the shortest trial
        * step anyway, clear the filter, and give up after 3 consecutive failures. */
