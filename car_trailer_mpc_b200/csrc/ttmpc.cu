@@ -26,6 +26,8 @@ using namespace ttmpc;
 namespace {
 
 constexpr int kSolveThreads = 128;
+constexpr int kCopyUnroll = 6;
+constexpr size_t kSolveSmem = (size_t)kCarry * kSolveThreads * sizeof(double);  // 56 320 B of dynamic shared memory  // problem load / result store: global loads in flight per lane
 #ifndef TTMPC_MIN_BLOCKS
 #define TTMPC_MIN_BLOCKS 2
 #endif
@@ -47,39 +49,73 @@ struct SolveOut {
 // atomic), loads that problem into its slot and joins the other lanes at the next iteration boundary.  The
 // lanes of a warp therefore always run the same sweep on consecutive slots (coalesced, convergent) although
 // their problems are at different interior-point iterations -- iteration-count divergence costs nothing.
-template <bool G>
+template <bool G, bool DQ>
 __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
     ttmpc_solve_kernel(const __grid_constant__ Params p, double* __restrict__ scratch, long long B, ProblemIn in, SolveOut out,
                        unsigned long long* __restrict__ counter) {
+  constexpr unsigned kFull = 0xffffffffu;
+  extern __shared__ double carried[];  // loop-carried state of the backward sweep, [kCarry entries][thread]
+  const Carry cy{carried + threadIdx.x, kSolveThreads};
   const size_t slot = (size_t)blockIdx.x * kSolveThreads + threadIdx.x;
   double* s0 = slot_ptr(scratch, p.N, slot);
   const unsigned lane = threadIdx.x & 31u;
-  const long long nz = 8LL * p.N + 6;
+  double* s_warp = s0 - lane;  // slot of lane 0 of this warp (a warp never straddles a bank: kBank % 32 == 0)
+  const int nz = 8 * p.N + 6;
   long long prob = -1;
   bool active = false, exhausted = false;
   Ipm st;
   Result res;
   for (;;) {
-    const unsigned need = __ballot_sync(0xffffffffu, !active);
+    // ---- refill: lanes without work take the next problems from the queue (one atomic per warp) ...
+    const unsigned need = __ballot_sync(kFull, !active);
+    unsigned fresh = 0;
     if (need && !exhausted) {
       const int leader = __ffs(need) - 1;
       unsigned long long base = 0;
       if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(need));
-      base = __shfl_sync(0xffffffffu, base, leader);
+      base = __shfl_sync(kFull, base, leader);
       if (!active) {
         const long long cand = (long long)base + __popc(need & ((1u << lane) - 1u));
         if (cand < B) {
           prob = cand;
           active = true;
-          const bool bad = pack_slot(p, s0, in, prob);
-          ipm_begin(p, st, bad);
         }
       }
+      fresh = need & __ballot_sync(kFull, active);
       if ((long long)base + __popc(need) >= B) exhausted = true;
     }
-    if (!__any_sync(0xffffffffu, active)) break;
-    if (active && ipm_iteration<G>(p, s0, st, res)) {
-      if (out.z) unpack_slot(p, s0, out.z + prob * nz);
+    // ... and the whole warp loads each new problem into its lane's slot: coalesced reads of the problem record
+    // (the reference's p / z layouts), scattered 8-byte writes down the slot column.
+    for (unsigned m = fresh; m; m &= m - 1) {
+      const int l = __ffs(m) - 1;
+      const long long pb = __shfl_sync(kFull, prob, l);
+      bool bad = false;
+      for (int e0 = (int)lane; e0 < nz; e0 += 32 * kCopyUnroll) {  // kCopyUnroll loads in flight per lane
+        PackVal v[kCopyUnroll];
+#pragma unroll
+        for (int u = 0; u < kCopyUnroll; u++) {
+          const int e = e0 + 32 * u;
+          if (e < nz) v[u] = pack_load(p, in, pb, e >> 3, e & 7);
+        }
+#pragma unroll
+        for (int u = 0; u < kCopyUnroll; u++) {
+          const int e = e0 + 32 * u;
+          if (e < nz) bad |= pack_store(p, s_warp + l, e >> 3, e & 7, v[u]);
+        }
+      }
+      bad = __any_sync(kFull, bad);
+      if ((int)lane == l) ipm_begin(p, st, bad);
+    }
+    __syncwarp();
+    if (!__any_sync(kFull, active)) break;
+
+    // ---- one interior-point iteration for every lane that has a problem
+    bool done = false;
+    if (active) done = ipm_iteration<G, DQ>(p, s0, cy, st, res);
+    __syncwarp();
+
+    // ---- finished lanes: scalars by the owner, the decision vector by the whole warp (coalesced z_out rows)
+    if (done) {
       if (out.u0) {
         out.u0[prob * 2 + 0] = ldr(s0, rW + 6);
         out.u0[prob * 2 + 1] = ldr(s0, rW + 7);
@@ -93,6 +129,28 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
       if (out.iters) out.iters[prob] = res.iters;
       if (out.status) out.status[prob] = res.status;
       active = false;
+    }
+    const unsigned fin = __ballot_sync(kFull, done);
+    if (out.z) {
+      for (unsigned m = fin; m; m &= m - 1) {
+        const int l = __ffs(m) - 1;
+        const long long pb = __shfl_sync(kFull, prob, l);
+        const double* sl = s_warp + l;
+        double* zo = out.z + pb * nz;
+        for (int e0 = (int)lane; e0 < nz; e0 += 32 * kCopyUnroll) {
+          double v[kCopyUnroll];
+#pragma unroll
+          for (int u = 0; u < kCopyUnroll; u++) {
+            const int e = e0 + 32 * u;
+            if (e < nz) v[u] = ldr(sl + (size_t)(e >> 3) * kStageStride, rW + (e & 7));
+          }
+#pragma unroll
+          for (int u = 0; u < kCopyUnroll; u++) {
+            const int e = e0 + 32 * u;
+            if (e < nz) zo[e] = v[u];
+          }
+        }
+      }
     }
   }
 }
@@ -185,6 +243,13 @@ __global__ void __launch_bounds__(256) ttmpc_dfma_kernel(double* out, double a, 
 // ================================================================================================
 // C ABI
 // ================================================================================================
+// kernel variant for a configuration: bound pattern (G) x weight structure (DQ)
+typedef void (*solve_kernel_t)(const Params, double*, long long, ProblemIn, SolveOut, unsigned long long*);
+static solve_kernel_t solve_kernel_for(const Params& p) {
+  if (p.generic) return p.diag ? ttmpc_solve_kernel<true, true> : ttmpc_solve_kernel<true, false>;
+  return p.diag ? ttmpc_solve_kernel<false, true> : ttmpc_solve_kernel<false, false>;
+}
+
 constexpr int kNumKernels = 4;
 struct ttmpc_handle {
   ttmpc_config cfg;
@@ -257,10 +322,8 @@ int ttmpc_create(const ttmpc_config* cfg, int device, ttmpc_handle** out) {
   h->device = device;
   int sms = 0, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  if (p.generic)
-    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ttmpc_solve_kernel<true>, kSolveThreads, 0);
-  else
-    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ttmpc_solve_kernel<false>, kSolveThreads, 0);
+  ce = cudaFuncSetAttribute(solve_kernel_for(p), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmem);
+  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel_for(p), kSolveThreads, kSolveSmem);
   if (ce != cudaSuccess || sms <= 0 || per_sm <= 0) {
     delete h;
     return TTMPC_E_CUDA;
@@ -321,10 +384,7 @@ static int solve_device(ttmpc_handle* h, long long B, const ProblemIn& in, const
   int rc = ensure_scratch(h, (size_t)blocks * kSolveThreads);
   if (rc) return rc;
   cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st);
-  if (h->p.generic)
-    ttmpc_solve_kernel<true><<<(unsigned)blocks, kSolveThreads, 0, st>>>(h->p, h->scratch, B, in, so, h->counter);
-  else
-    ttmpc_solve_kernel<false><<<(unsigned)blocks, kSolveThreads, 0, st>>>(h->p, h->scratch, B, in, so, h->counter);
+  solve_kernel_for(h->p)<<<(unsigned)blocks, kSolveThreads, kSolveSmem, st>>>(h->p, h->scratch, B, in, so, h->counter);
   h->launches[0]++;
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "kernel launch", ce);

@@ -82,6 +82,7 @@ struct Params {
   int n_b, m_eq;       // number of bound multipliers / equality multipliers (scaling factors s_d, s_c)
   unsigned bl, bu;     // bit j set: variable j (x: 0..5, u: 6..7) has a lower / upper bound
   int generic;         // 0: the bound pattern is the compiled-in default (G=false kernels are valid)
+  int diag;            // 1: Q and R are diagonal (DQ=true kernels are valid)
   double dt, iL1, iL2, cML;  // 1/L1, 1/L2, M/L2
   double Q2[21];             // 2*Q, symmetric packed (SY)
   double R2[3];              // 2*R: (a,a), (a,w), (w,w)
@@ -106,7 +107,7 @@ TT_HD void str(double* ps, int row, double v) { ps[(size_t)row * kBank] = v; }
 // L1 prefetch of rows [row0, row0+n) of a stage: the sweeps walk the stages sequentially with fully predictable
 // addresses, so the next stage is requested while the current one is being computed (no registers tied up).
 TT_HD void prefetch_rows(const double* ps, int row0, int n) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(TTMPC_NO_PREFETCH)
   TT_UNROLL
   for (int r = 0; r < n; r++) asm volatile("prefetch.global.L1 [%0];" ::"l"(ps + (size_t)(row0 + r) * kBank));
 #else
@@ -125,6 +126,11 @@ inline size_t scratch_doubles(int N, size_t nbanks) { return nbanks * (size_t)(N
 // lean math: the library sincos / division are ~100 / ~15 instructions each with 64-bit constants materialised by
 // MOV pairs and slow-path branches; the solver evaluates 12 sincos and ~40 reciprocals per stage and iteration.
 // ------------------------------------------------------------------------------------------------
+// max/min by compare+select (3 instructions); fmax/fmin on doubles expand to ~10 because of their NaN rules.
+// NaNs are not propagated by these -- the sums J / theta / sumlog carry them to the finite check instead.
+TT_HD double tt_max(double a, double b) { return a > b ? a : b; }
+TT_HD double tt_min(double a, double b) { return a < b ? a : b; }
+
 // 1/x for normal positive-or-negative x (slacks, pivots, cos(phi)): hardware seed + 2 Newton steps (|err| ~ 1 ulp).
 TT_HD double tt_rcp(double x) {
 #if defined(__CUDA_ARCH__)
@@ -173,8 +179,14 @@ TT_HD void tt_sincos(double x, double& s, double& c) {
   sincos_kernel(r, s0, c0);
   const double ss = (k & 1) ? c0 : s0;
   const double cc = (k & 1) ? s0 : c0;
-  s = (k & 2) ? -ss : ss;
-  c = ((k + 1) & 2) ? -cc : cc;
+  // sign flips as XOR on the sign bit: sin flips in quadrants 2,3; cos in quadrants 1,2
+  uint64_t sb, cb;
+  memcpy(&sb, &ss, sizeof sb);
+  memcpy(&cb, &cc, sizeof cb);
+  sb ^= (uint64_t)(uint32_t)(k & 2) << 62;
+  cb ^= (uint64_t)(uint32_t)((k + 1) & 2) << 62;
+  memcpy(&s, &sb, sizeof sb);
+  memcpy(&c, &cb, sizeof cb);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -258,8 +270,14 @@ TT_HD void A_mul(const Lin& m, const double* d, double* y) {
   y[4] = d[4];
   y[5] = d[5];
 }
-// y = Q2 * d  (symmetric packed 6x6)
+// y = Q2 * d  (symmetric packed 6x6; DQ: Q and R are diagonal, as in every driver of the reference)
+template <bool DQ>
 TT_HD void Q2_mul(const Params& p, const double* d, double* y) {
+  if (DQ) {
+    TT_UNROLL
+    for (int i = 0; i < NX; i++) y[i] = p.Q2[SY(i, i)] * d[i];
+    return;
+  }
   TT_UNROLL
   for (int i = 0; i < NX; i++) {
     double s = 0.0;
@@ -281,22 +299,29 @@ struct Stats {
 // ------------------------------------------------------------------------------------------------
 // backward sweep
 // ------------------------------------------------------------------------------------------------
+// Loop-carried state of the backward sweep (value function P, p0, p1; x_{k+1}; multipliers of stage k+1).  It is kept
+// OUT of registers on purpose: each piece is needed in one short section of the stage body only, and holding all 55
+// doubles live across the body forces ~900 B of local-memory spills per thread that thrash L1.  On the device this
+// storage is shared memory ([entry][thread], conflict-free); the host emulation uses a plain array.
+constexpr int cP = 0, cP0 = 21, cP1 = 27, cXN = 33, cLNEW = 39, cLOLD = 45, cLPLUS = 49, kCarry = 55;
+struct Carry {
+  double* base;
+  int stride;
+  TT_HD double ld(int i) const { return base[i * stride]; }
+  TT_HD void st(int i, double v) const { base[i * stride] = v; }
+};
+
 // do_update: apply the step stored in DW with primal step alpha / dual step alpha_du; mu_step, delta_step are the
 // barrier parameter and Hessian regularisation the step was computed with.  delta: regularisation for the new
 // factorisation.  Returns false when some 2x2 pivot block is not positive definite (wrong inertia).
-template <bool G>
-TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double alpha, double alpha_du, double mu_step,
-                          double delta_step, double delta, Stats& st) {
+template <bool G, bool DQ>
+TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, bool do_update, double alpha, double alpha_du,
+                          double mu_step, double delta_step, double delta, Stats& st) {
   const int N = p.N;
   const double dt = p.dt;
-  double P[21], p0[NX], p1[NX];
-  double xn[NX];     // new x_{k+1}
-  double lnew[NX];   // new lambda_{k+1}
-  double lold[4];    // old lambda_{k+1} (components entering the Hessian)
-  double lplus[NX];  // full-step multiplier lambda^+_{k+1}
   bool ok = true;
   double J = 0.0, sumlog = 0.0, theta = 0.0, cinf = 0.0, rd_inf = 0.0, lam1 = 0.0, z1 = 0.0, cmax = 0.0, cmin = INFINITY;
-  const double kmu_hi = kKappaSigma * mu_step, kmu_lo = mu_step / kKappaSigma;
+  const double kmu_hi = kKappaSigma * mu_step, kmu_lo = mu_step * (1.0 / kKappaSigma);
 
   for (int k = N; k >= 0; k--) {
     double* ps = s0 + (size_t)k * kStageStride;
@@ -348,10 +373,10 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
       if (has_x) {
         // costate recursion at the OLD iterate:  lambda+_k = A_k' lambda+_{k+1} - (Hx_k dx_k + ghat_k)
         double hx[NX], g[NX], d6[NX];
-        Q2_mul(p, dw, hx);
+        Q2_mul<DQ>(p, dw, hx);
         TT_UNROLL
         for (int j = 0; j < NX; j++) d6[j] = w[j] - ref[j];
-        Q2_mul(p, d6, g);
+        Q2_mul<DQ>(p, d6, g);
         TT_UNROLL
         for (int j = 0; j < NX; j++) hx[j] += sigd[j] + g[j] + gb[j];
         double lp[NX];
@@ -359,6 +384,11 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
           Lin mo;
           stage_lin(p, w, mo);
           Hes ho;
+          double lold[4], lplus[NX];  // old lambda_{k+1} (Hessian part) and full-step multiplier lambda+_{k+1}
+          TT_UNROLL
+          for (int j = 0; j < 4; j++) lold[j] = cy.ld(cLOLD + j);
+          TT_UNROLL
+          for (int j = 0; j < NX; j++) lplus[j] = cy.ld(cLPLUS + j);
           stage_hess(p, mo, lold, ho);
           hx[2] += ho.h22 * dw[2] + ho.h25 * dw[5];
           hx[3] += ho.h33 * dw[3] + ho.h34 * dw[4] + ho.h35 * dw[5];
@@ -372,10 +402,10 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
           for (int j = 0; j < NX; j++) lp[j] = -hx[j];
         }
         TT_UNROLL
-        for (int j = 0; j < 4; j++) lold[j] = lam[j];
+        for (int j = 0; j < 4; j++) cy.st(cLOLD + j, lam[j]);
         TT_UNROLL
         for (int j = 0; j < NX; j++) {
-          lplus[j] = lp[j];
+          cy.st(cLPLUS + j, lp[j]);
           lam[j] += alpha * (lp[j] - lam[j]);
           str(ps, rLAM + j, lam[j]);
         }
@@ -388,9 +418,6 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
           str(ps, rW + j, w[j]);
         }
       }
-    } else if (has_x) {
-      TT_UNROLL
-      for (int j = 0; j < 4; j++) lold[j] = lam[j];
     }
 
     // ---------------------------------------------------------------- (ii) statistics at the new iterate
@@ -399,14 +426,14 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
       double d6[NX];
       TT_UNROLL
       for (int j = 0; j < NX; j++) d6[j] = w[j] - ref[j];
-      Q2_mul(p, d6, g0);
+      Q2_mul<DQ>(p, d6, g0);
       double jq = 0.0;
       TT_UNROLL
       for (int j = 0; j < NX; j++) jq += g0[j] * d6[j];
       if (has_u) {
         const double da = w[6] - ref[6], dw_ = w[7] - ref[7];
-        g0[6] = p.R2[0] * da + p.R2[1] * dw_;
-        g0[7] = p.R2[1] * da + p.R2[2] * dw_;
+        g0[6] = DQ ? p.R2[0] * da : p.R2[0] * da + p.R2[1] * dw_;
+        g0[7] = DQ ? p.R2[2] * dw_ : p.R2[1] * da + p.R2[2] * dw_;
         jq += g0[6] * da + g0[7] * dw_;
       } else {
         g0[6] = g0[7] = 0.0;
@@ -420,7 +447,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
         if (var && has_lo<G>(p, j)) {
           const double sl = w[j] - p.lo[j], rl = tt_rcp(sl);
           if (do_update) {  // kappa_sigma safeguard, Waechter & Biegler eq. (16)
-            zl[j] = fmax(fmin(zl[j], kmu_hi * rl), kmu_lo * rl);
+            zl[j] = tt_max(tt_min(zl[j], kmu_hi * rl), kmu_lo * rl);
             str(ps, rZL + j, zl[j]);
           }
           sg += zl[j] * rl;
@@ -428,13 +455,13 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
           prod *= sl;
           z1 += zl[j];
           const double c = sl * zl[j];
-          cmax = fmax(cmax, c);
-          cmin = fmin(cmin, c);
+          cmax = tt_max(cmax, c);
+          cmin = tt_min(cmin, c);
         }
         if (var && has_up<G>(p, j)) {
           const double su = p.up[j] - w[j], ru = tt_rcp(su);
           if (do_update) {
-            zu[j] = fmax(fmin(zu[j], kmu_hi * ru), kmu_lo * ru);
+            zu[j] = tt_max(tt_min(zu[j], kmu_hi * ru), kmu_lo * ru);
             str(ps, rZU + j, zu[j]);
           }
           sg += zu[j] * ru;
@@ -442,8 +469,8 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
           prod *= su;
           z1 += zu[j];
           const double c = su * zu[j];
-          cmax = fmax(cmax, c);
-          cmin = fmin(cmin, c);
+          cmax = tt_max(cmax, c);
+          cmin = tt_min(cmin, c);
         }
         sig[j] = sg;
         g1[j] = gg;
@@ -460,17 +487,23 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
       TT_UNROLL
       for (int i = 0; i < NX; i++) {
         TT_UNROLL
-        for (int j = i; j < NX; j++) P[SY(i, j)] = p.Q2[SY(i, j)];
-        P[SY(i, i)] += sig[i];
-        p0[i] = g0[i];
-        p1[i] = g1[i];
+        for (int j = i; j < NX; j++)
+          cy.st(cP + SY(i, j), ((DQ && j != i) ? 0.0 : p.Q2[SY(i, j)]) + (j == i ? sig[i] : 0.0));
+        cy.st(cP0 + i, g0[i]);
+        cy.st(cP1 + i, g1[i]);
         const double r = g0[i] + lam[i] - zl[i] + zu[i];  // dual residual of x_N
-        rd_inf = fmax(rd_inf, fabs(r));
+        rd_inf = tt_max(rd_inf, fabs(r));
       }
     } else {
       // ------------------------------------------------------------ (iii) stage k < N
       Lin m;
       stage_lin(p, w, m);
+      double xn[NX], lnew[NX];  // new x_{k+1}, new lambda_{k+1}
+      TT_UNROLL
+      for (int j = 0; j < NX; j++) {
+        xn[j] = cy.ld(cXN + j);
+        lnew[j] = cy.ld(cLNEW + j);
+      }
       // defect c_{k+1} = x_{k+1} - x_k - dt f(x_k,u_k)   (trajectory_planning.py:31-32)
       double c[NX];
       c[0] = xn[0] - w[0] - dt * m.f0;
@@ -482,24 +515,32 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
       TT_UNROLL
       for (int j = 0; j < NX; j++) {
         theta += fabs(c[j]);
-        cinf = fmax(cinf, fabs(c[j]));
+        cinf = tt_max(cinf, fabs(c[j]));
       }
       // dual residuals
       {
         const double ra = g0[6] - dt * lnew[5] - zl[6] + zu[6];
         const double rw = g0[7] - dt * lnew[4] - zl[7] + zu[7];
-        rd_inf = fmax(rd_inf, fmax(fabs(ra), fabs(rw)));
+        rd_inf = tt_max(rd_inf, tt_max(fabs(ra), fabs(rw)));
         if (has_x) {
           double al[NX];
           At_mul(m, lnew, al);
           TT_UNROLL
           for (int j = 0; j < NX; j++) {
             const double r = g0[j] + lam[j] - al[j] - zl[j] + zu[j];
-            rd_inf = fmax(rd_inf, fabs(r));
+            rd_inf = tt_max(rd_inf, fabs(r));
           }
         }
       }
       // ---- Riccati step.  T = P A
+      double P[21], p0[NX], p1[NX];
+      TT_UNROLL
+      for (int i = 0; i < 21; i++) P[i] = cy.ld(cP + i);
+      TT_UNROLL
+      for (int i = 0; i < NX; i++) {
+        p0[i] = cy.ld(cP0 + i);
+        p1[i] = cy.ld(cP1 + i);
+      }
       double T[NX][NX];
       TT_UNROLL
       for (int r = 0; r < NX; r++) {
@@ -523,7 +564,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
       // Rhat = 2R + Sigma_u + delta + B'PB
       const double dt2 = dt * dt;
       const double r00 = p.R2[0] + sig[6] + dt2 * P[SY(5, 5)];
-      const double r01 = p.R2[1] + dt2 * P[SY(5, 4)];
+      const double r01 = (DQ ? 0.0 : p.R2[1]) + dt2 * P[SY(5, 4)];
       const double r11 = p.R2[2] + sig[7] + dt2 * P[SY(4, 4)];
       const double det = r00 * r11 - r01 * r01;
       if (!(r00 > 0.0) || !(det > 0.0)) ok = false;
@@ -571,8 +612,12 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
         TT_UNROLL
         for (int i = 0; i < NX; i++) {
           TT_UNROLL
-          for (int j = i; j < NX; j++) Pn[SY(i, j)] += p.Q2[SY(i, j)] - (S0[i] * K0[j] + S1[i] * K1[j]);
-          Pn[SY(i, i)] += sig[i];
+          for (int j = i; j < NX; j++) Pn[SY(i, j)] -= S0[i] * K0[j] + S1[i] * K1[j];
+          if (!DQ) {
+            TT_UNROLL
+            for (int j = i + 1; j < NX; j++) Pn[SY(i, j)] += p.Q2[SY(i, j)];
+          }
+          Pn[SY(i, i)] += p.Q2[SY(i, i)] + sig[i];
         }
         Pn[SY(2, 2)] += hs.h22;
         Pn[SY(2, 5)] += hs.h25;
@@ -586,18 +631,20 @@ TT_HD bool backward_sweep(const Params& p, double* s0, bool do_update, double al
         At_mul(m, p1, a1);
         TT_UNROLL
         for (int i = 0; i < NX; i++) {
-          p0[i] = g0[i] + a0[i] - (S0[i] * k0a + S1[i] * k0w);
-          p1[i] = g1[i] + a1[i] - (S0[i] * k1a + S1[i] * k1w);
+          cy.st(cP0 + i, g0[i] + a0[i] - (S0[i] * k0a + S1[i] * k0w));
+          cy.st(cP1 + i, g1[i] + a1[i] - (S0[i] * k1a + S1[i] * k1w));
         }
         TT_UNROLL
-        for (int i = 0; i < 21; i++) P[i] = Pn[i];
+        for (int i = 0; i < 21; i++) cy.st(cP + i, Pn[i]);
       }
     }
     // carry to stage k-1
-    TT_UNROLL
-    for (int j = 0; j < NX; j++) {
-      xn[j] = w[j];
-      lnew[j] = lam[j];
+    if (has_x) {
+      TT_UNROLL
+      for (int j = 0; j < NX; j++) {
+        cy.st(cXN + j, w[j]);
+        cy.st(cLNEW + j, lam[j]);
+      }
     }
   }
   st.J = J;
@@ -619,7 +666,7 @@ struct StepInfo {
   double a_pr, a_du, gphi_d;
 };
 
-template <bool G>
+template <bool G, bool DQ>
 TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, StepInfo& si) {
   const int N = p.N;
   const double dt = p.dt;
@@ -650,22 +697,32 @@ TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, Ste
       prefetch_rows(pn, rZL + (G ? 0 : 2), G ? 2 * NW : 14);
       prefetch_rows(pn, rKF, 16);
     }
+    // all loads of the stage first (one batch in flight), then the arithmetic
+    double zl[NW], zu[NW], kf[16];
+    TT_UNROLL
+    for (int j = 0; j < NW; j++) {
+      const bool var = (j < NX) ? has_x : has_u;
+      zl[j] = (var && has_lo<G>(p, j)) ? ldr(ps, rZL + j) : 0.0;
+      zu[j] = (var && has_up<G>(p, j)) ? ldr(ps, rZU + j) : 0.0;
+    }
+    TT_UNROLL
+    for (int j = 0; j < 16; j++) kf[j] = (has_u && (has_x || j >= 12)) ? ldr(ps, rKF + j) : 0.0;
+    if (has_u) {
+      TT_UNROLL
+      for (int j = 0; j < NX; j++) xnext[j] = ldr(ps + kStageStride, rW + j);
+    }
     // du = -K dx - (kff0 + mu*kff1)
     d[6] = d[7] = 0.0;
     if (has_u) {
-      double du0 = -(ldr(ps, rKF + 12) + mu * ldr(ps, rKF + 14));
-      double du1 = -(ldr(ps, rKF + 13) + mu * ldr(ps, rKF + 15));
-      if (has_x) {
-        TT_UNROLL
-        for (int j = 0; j < NX; j++) {
-          du0 -= ldr(ps, rKF + j) * dx[j];
-          du1 -= ldr(ps, rKF + NX + j) * dx[j];
-        }
+      double du0 = -(kf[12] + mu * kf[14]);
+      double du1 = -(kf[13] + mu * kf[15]);
+      TT_UNROLL
+      for (int j = 0; j < NX; j++) {
+        du0 -= kf[j] * dx[j];
+        du1 -= kf[NX + j] * dx[j];
       }
       d[6] = du0;
       d[7] = du1;
-      TT_UNROLL
-      for (int j = 0; j < NX; j++) xnext[j] = ldr(ps + kStageStride, rW + j);
     }
     // gradient of the barrier objective along the step, step limits, store the direction
     double g[NW];
@@ -673,10 +730,10 @@ TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, Ste
       double d6[NX];
       TT_UNROLL
       for (int j = 0; j < NX; j++) d6[j] = w[j] - ref[j];
-      Q2_mul(p, d6, g);
+      Q2_mul<DQ>(p, d6, g);
       const double da = w[6] - ref[6], dw_ = w[7] - ref[7];
-      g[6] = p.R2[0] * da + p.R2[1] * dw_;
-      g[7] = p.R2[1] * da + p.R2[2] * dw_;
+      g[6] = DQ ? p.R2[0] * da : p.R2[0] * da + p.R2[1] * dw_;
+      g[7] = DQ ? p.R2[2] * dw_ : p.R2[1] * da + p.R2[2] * dw_;
     }
     TT_UNROLL
     for (int j = 0; j < NW; j++) {
@@ -684,9 +741,9 @@ TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, Ste
       if (!var) continue;
       double gj = g[j];
       if (has_lo<G>(p, j)) {
-        const double rl = tt_rcp(w[j] - p.lo[j]), z = ldr(ps, rZL + j);
+        const double rl = tt_rcp(w[j] - p.lo[j]), z = zl[j];
         gj -= mu * rl;
-        qmax = fmax(qmax, -d[j] * rl);
+        qmax = tt_max(qmax, -d[j] * rl);
         const double ndz = z - rl * (mu - z * d[j]);  // -dz
         if (ndz * bd > bn * z) {
           bn = ndz;
@@ -694,9 +751,9 @@ TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, Ste
         }
       }
       if (has_up<G>(p, j)) {
-        const double ru = tt_rcp(p.up[j] - w[j]), z = ldr(ps, rZU + j);
+        const double ru = tt_rcp(p.up[j] - w[j]), z = zu[j];
         gj += mu * ru;
-        qmax = fmax(qmax, d[j] * ru);
+        qmax = tt_max(qmax, d[j] * ru);
         const double ndz = z - ru * (mu + z * d[j]);
         if (ndz * bd > bn * z) {
           bn = ndz;
@@ -736,7 +793,7 @@ struct Trial {
   double J, sumlog, theta;
 };
 
-template <bool G>
+template <bool G, bool DQ>
 TT_HD void trial_sweep(const Params& p, const double* s0, double alpha, Trial& tr) {
   const int N = p.N;
   const double dt = p.dt;
@@ -758,7 +815,7 @@ TT_HD void trial_sweep(const Params& p, const double* s0, double alpha, Trial& t
     double d6[NX], g[NX];
     TT_UNROLL
     for (int j = 0; j < NX; j++) d6[j] = w[j] - ref[j];
-    Q2_mul(p, d6, g);
+    Q2_mul<DQ>(p, d6, g);
     double jq = 0.0;
     TT_UNROLL
     for (int j = 0; j < NX; j++) jq += g[j] * d6[j];
@@ -769,18 +826,19 @@ TT_HD void trial_sweep(const Params& p, const double* s0, double alpha, Trial& t
       if (var && has_lo<G>(p, j)) {
         const double s = w[j] - p.lo[j];
         prod *= s;
-        smin = fmin(smin, s);
+        smin = tt_min(smin, s);
       }
       if (var && has_up<G>(p, j)) {
         const double s = p.up[j] - w[j];
         prod *= s;
-        smin = fmin(smin, s);
+        smin = tt_min(smin, s);
       }
     }
     sl_ += log(prod);
     if (has_u) {
       const double da = w[6] - ref[6], dw_ = w[7] - ref[7];
-      jq += (p.R2[0] * da + p.R2[1] * dw_) * da + (p.R2[1] * da + p.R2[2] * dw_) * dw_;
+      jq += DQ ? p.R2[0] * da * da + p.R2[2] * dw_ * dw_
+               : (p.R2[0] * da + p.R2[1] * dw_) * da + (p.R2[1] * da + p.R2[2] * dw_) * dw_;
       double f[4];
       stage_f(p, w, f);
       th += fabs(xn[0] - w[0] - dt * f[0]) + fabs(xn[1] - w[1] - dt * f[1]) + fabs(xn[2] - w[2] - dt * f[2]) +
@@ -828,8 +886,8 @@ TT_HD void ipm_begin(const Params& p, Ipm& s, bool x0_infeasible) {
 }
 
 // One interior-point iteration.  Returns true when the lane is finished (res filled in).
-template <bool G>
-TT_HD bool ipm_iteration(const Params& p, double* s0, Ipm& s, Result& res) {
+template <bool G, bool DQ>
+TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, Ipm& s, Result& res) {
   Stats st, st2;
   bool ok = false;
   int status = -1;
@@ -839,7 +897,7 @@ TT_HD bool ipm_iteration(const Params& p, double* s0, Ipm& s, Result& res) {
   // the sweep is the bulk of the kernel's code and must not be instantiated twice.
   for (int attempt = 0; attempt <= 40; attempt++) {
     const bool first = (attempt == 0);
-    ok = backward_sweep<G>(p, s0, first && s.do_update, s.alpha, s.alpha_du, first ? s.mu_step : mu, s.delta_step, delta,
+    ok = backward_sweep<G, DQ>(p, s0, cy, first && s.do_update, s.alpha, s.alpha_du, first ? s.mu_step : mu, s.delta_step, delta,
                            first ? st : st2);
     if (first) {
       const double cmin = p.n_b ? st.cmin : 0.0;
@@ -897,7 +955,7 @@ TT_HD bool ipm_iteration(const Params& p, double* s0, Ipm& s, Result& res) {
   }
 
   StepInfo si;
-  forward_sweep<G>(p, s0, mu, s.tau, si);
+  forward_sweep<G, DQ>(p, s0, mu, s.tau, si);
 
   // filter line search (Waechter & Biegler 2006, Algorithm A)
   const double theta = st.theta;
@@ -909,7 +967,7 @@ TT_HD bool ipm_iteration(const Params& p, double* s0, Ipm& s, Result& res) {
   bool accepted = roundoff_step;
   for (int bt = 0; !roundoff_step && bt <= kMaxBacktrack; bt++, a *= kAlphaRed) {
     Trial tr;
-    trial_sweep<G>(p, s0, a, tr);
+    trial_sweep<G, DQ>(p, s0, a, tr);
     if (!(tt_finite(tr.J) && tt_finite(tr.sumlog) && tt_finite(tr.theta))) continue;
     const double phi_t = tr.J - mu * tr.sumlog;
     if (tr.theta > s.theta_max) continue;
@@ -998,57 +1056,63 @@ struct ProblemIn {
   int T;
 };
 
-TT_HD bool pack_slot(const Params& p, double* s0, const ProblemIn& in, long long b) {
+// Loading one element (stage k, component j) of problem b is split into the global loads (reference value and
+// starting guess) and the stores into the slot, so that callers can put several loads in flight first.
+struct PackVal {
+  double r, g;
+};
+TT_HD PackVal pack_load(const Params& p, const ProblemIn& in, long long b, int k, int j) {
   const int N = p.N;
-  const long long nz = 8LL * N + 6;
-  const bool shared_mode = (in.ref_states == nullptr);
-  const int kk = shared_mode ? in.k_index[b] : 0;
-  bool bad = false;
-  for (int k = 0; k <= N; k++) {
-    double* ps = s0 + (size_t)k * kStageStride;
-    TT_UNROLL
-    for (int j = 0; j < NW; j++) {
-      if (j >= NX && k >= N) continue;  // no input at the terminal stage
-      double r;
-      if (!shared_mode) {
-        r = (j < NX) ? in.ref_states[(b * (N + 1) + k) * NX + j] : in.ref_inputs[(b * N + k) * NU + (j - NX)];
-      } else {
-        const int T = in.T;
-        if (j < NX)
-          r = in.traj_states[(long long)((kk < T) ? ((kk + k < T) ? kk + k : T) : T) * NX + j];
-        else
-          r = (kk >= T) ? 0.0 : in.traj_inputs[(long long)((kk + k < T) ? kk + k : T - 1) * NU + (j - NX)];
-      }
-      const double g = in.z_warm ? in.z_warm[b * nz + (long long)k * NW + j] : r;
-      const bool hl = ((p.bl >> j) & 1u) != 0, hu = ((p.bu >> j) & 1u) != 0;
-      double w;
-      if (k == 0 && j < NX) {
-        w = in.x_init[b * NX + j];  // x_0 is data
-        if ((hl && w < p.lo[j]) || (hu && w > p.up[j])) bad = true;
-      } else {
-        w = push_inside(g, p.lo[j], p.up[j], hl, hu);
-        if (hl) str(ps, rZL + j, 1.0);
-        if (hu) str(ps, rZU + j, 1.0);
-      }
-      str(ps, rW + j, w);
-      str(ps, rREF + j, r);
-      if (j < NX) str(ps, rLAM + j, 0.0);
-    }
+  PackVal v;
+  if (in.ref_states != nullptr) {
+    v.r = (j < NX) ? in.ref_states[(b * (N + 1) + k) * NX + j] : in.ref_inputs[(b * N + k) * NU + (j - NX)];
+  } else {
+    const int T = in.T, kk = in.k_index[b];
+    if (j < NX)
+      v.r = in.traj_states[(long long)((kk < T) ? ((kk + k < T) ? kk + k : T) : T) * NX + j];
+    else
+      v.r = (kk >= T) ? 0.0 : in.traj_inputs[(long long)((kk + k < T) ? kk + k : T - 1) * NU + (j - NX)];
   }
+  if (k == 0 && j < NX)
+    v.g = in.x_init[b * NX + j];  // x_0 is data
+  else
+    v.g = in.z_warm ? in.z_warm[b * (8LL * N + 6) + (long long)k * NW + j] : v.r;
+  return v;
+}
+// returns true when x_init violates a state bound (the reference NLP is then infeasible)
+TT_HD bool pack_store(const Params& p, double* s0, int k, int j, const PackVal& v) {
+  double* ps = s0 + (size_t)k * kStageStride;
+  const bool hl = ((p.bl >> j) & 1u) != 0, hu = ((p.bu >> j) & 1u) != 0;
+  bool bad = false;
+  double w = v.g;
+  if (k == 0 && j < NX) {
+    bad = (hl && w < p.lo[j]) || (hu && w > p.up[j]);
+  } else {
+    w = push_inside(w, p.lo[j], p.up[j], hl, hu);
+    if (hl) str(ps, rZL + j, 1.0);
+    if (hu) str(ps, rZU + j, 1.0);
+  }
+  str(ps, rW + j, w);
+  str(ps, rREF + j, v.r);
+  if (j < NX) str(ps, rLAM + j, 0.0);
+  return bad;
+}
+TT_HD bool pack_elem(const Params& p, double* s0, const ProblemIn& in, long long b, int k, int j) {
+  return pack_store(p, s0, k, j, pack_load(p, in, b, k, j));
+}
+
+// single-lane versions (host emulation; the CUDA kernel does the same element loop with 32 cooperating lanes)
+TT_HD bool pack_slot(const Params& p, double* s0, const ProblemIn& in, long long b) {
+  const int nz = 8 * p.N + 6;
+  bool bad = false;
+  for (int e = 0; e < nz; e++) bad |= pack_elem(p, s0, in, b, e >> 3, e & 7);
   return bad;
 }
 
-// slot -> z_out in the reference's decision-vector layout (trajectory_planning.py:38-60)
+// slot -> z_out in the reference's decision-vector layout (trajectory_planning.py:38-60): z[8k+j] = w_k[j]
 TT_HD void unpack_slot(const Params& p, const double* s0, double* z) {
-  const int N = p.N;
-  for (int k = 0; k <= N; k++) {
-    const double* ps = s0 + (size_t)k * kStageStride;
-    TT_UNROLL
-    for (int j = 0; j < NW; j++) {
-      if (j >= NX && k >= N) continue;
-      z[k * NW + j] = ldr(ps, rW + j);
-    }
-  }
+  const int nz = 8 * p.N + 6;
+  for (int e = 0; e < nz; e++) z[e] = ldr(s0 + (size_t)(e >> 3) * kStageStride, rW + (e & 7));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1089,6 +1153,10 @@ inline int build_params(const ttmpc_config* c, Params* p) {
     relax(c->u_lb[i], c->u_ub[i], &p->lo[NX + i], &p->up[NX + i], &p->bl, &p->bu, NX + i);
   }
   p->generic = !(p->bl == 0xFCu && p->bu == 0xFCu);
+  p->diag = (p->R2[1] == 0.0);
+  for (int i = 0; i < NX; i++)
+    for (int j = i + 1; j < NX; j++)
+      if (p->Q2[SY(i, j)] != 0.0) p->diag = 0;
   p->n_b = p->N * (__builtin_popcount(p->bl) + __builtin_popcount(p->bu));
   p->m_eq = NX * p->N;
   p->tol = c->tol;

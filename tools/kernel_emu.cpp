@@ -14,7 +14,7 @@
 
 using namespace ttmpc;
 
-template <bool G>
+template <bool G, bool DQ>
 static void run(const Params& p, std::vector<double>& scratch, int64_t B, const ProblemIn& in, double* z_out, double* u0_out,
                 double* obj_out, double* kkt_out, int32_t* iters_out, int32_t* status_out) {
   const size_t nz = 8 * (size_t)p.N + 6;
@@ -25,9 +25,11 @@ static void run(const Params& p, std::vector<double>& scratch, int64_t B, const 
     for (int64_t b = l; b < B; b += L) {
       Ipm st;
       Result r;
+      double carried[kCarry];
+      const Carry cy{carried, 1};
       const bool bad = pack_slot(p, s0, in, b);
       ipm_begin(p, st, bad);
-      while (!ipm_iteration<G>(p, s0, st, r)) {
+      while (!ipm_iteration<G, DQ>(p, s0, cy, st, r)) {
       }
       if (z_out) unpack_slot(p, s0, z_out + b * nz);
       if (u0_out) { u0_out[b * 2] = ldr(s0, rW + 6); u0_out[b * 2 + 1] = ldr(s0, rW + 7); }
@@ -49,9 +51,10 @@ extern "C" int ttmpc_emu_solve_batch(const ttmpc_config* cfg, int64_t B, const d
   if (rc) return rc;
   std::vector<double> scratch(scratch_doubles(p.N, 1), NAN);
   ProblemIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T};
-  if (p.generic || force_generic)
-    run<true>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
-  else
-    run<false>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
+  const bool g = p.generic || (force_generic & 1), dq = p.diag && !(force_generic & 2);
+  if (g && dq) run<true, true>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
+  else if (g) run<true, false>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
+  else if (dq) run<false, true>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
+  else run<false, false>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
   return 0;
 }
