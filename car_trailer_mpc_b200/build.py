@@ -18,7 +18,7 @@ LIB = os.path.join(PKG_DIR, "libttmpc.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
+    "-O3", "-lineinfo", "-std=c++17", "-diag-suppress", "128",
     "-shared", "-Xcompiler", "-fPIC",
     "-cudart", "static",
 ]

@@ -6,10 +6,10 @@
 // (multiple-shooting equalities, box bounds) and mpc_control.py:17-25 (tracking cost).
 //
 // Mapping: lane = problem slot.  All per-stage data of a slot lives in HBM in a
-// slot-interleaved layout, banks of kBank slots:  addr(bank, stage, row, lane) =
-// ((bank*(N+1) + stage)*kRows + row)*kBank + lane, so the 32 lanes of a warp always touch 256 contiguous
-// bytes (coalesced, no shuffles) and every row of a stage is a compile-time immediate offset from one
-// per-stage pointer.  The 6x6 / 6x2 / 2x2 block algebra of the Riccati recursion is unrolled into registers and
+// slot-interleaved layout in tiles of kBank = 32 slots (one warp):  addr(tile, stage, row, lane) =
+// ((tile*(N+1) + stage)*kRows + row)*32 + lane, so the 32 lanes of a warp always touch 256 contiguous bytes
+// (coalesced, no shuffles), every row of a stage is a small compile-time immediate offset from one per-stage
+// pointer, and a warp's whole working set (N=40: 650 KB) is one contiguous, TLB/DRAM-page friendly range.  The 6x6 / 6x2 / 2x2 block algebra of the Riccati recursion is unrolled into registers and
 // exploits the sparsity of A = I + dt*df/dx (14 non-zeros) and B (2 non-zeros).
 //
 // One interior-point iteration = ONE backward sweep + ONE forward sweep + (usually one) trial sweep:
@@ -44,7 +44,7 @@
 #endif
 
 #ifndef TTMPC_BANK
-#define TTMPC_BANK 16384
+#define TTMPC_BANK 32
 #endif
 
 namespace ttmpc {
@@ -666,12 +666,36 @@ struct StepInfo {
   double a_pr, a_du, gphi_d;
 };
 
+// inputs of one stage of the forward sweep
+struct FwdIn {
+  double u[NU], ref[NW], zl[NW], zu[NW], kf[16], xnext[NX];
+};
+template <bool G>
+TT_HD void fwd_load(const Params& p, const double* s0, int k, FwdIn& f) {
+  const int N = p.N;
+  const double* ps = s0 + (size_t)k * kStageStride;
+  const bool has_x = (k >= 1), has_u = (k < N);
+  f.u[0] = has_u ? ldr(ps, rW + 6) : 0.0;
+  f.u[1] = has_u ? ldr(ps, rW + 7) : 0.0;
+  TT_UNROLL
+  for (int j = 0; j < NW; j++) {
+    const bool var = (j < NX) ? has_x : has_u;
+    f.ref[j] = ((j < NX) || has_u) ? ldr(ps, rREF + j) : 0.0;
+    f.zl[j] = (var && has_lo<G>(p, j)) ? ldr(ps, rZL + j) : 0.0;
+    f.zu[j] = (var && has_up<G>(p, j)) ? ldr(ps, rZU + j) : 0.0;
+  }
+  TT_UNROLL
+  for (int j = 0; j < 16; j++) f.kf[j] = (has_u && (has_x || j >= 12)) ? ldr(ps, rKF + j) : 0.0;
+  TT_UNROLL
+  for (int j = 0; j < NX; j++) f.xnext[j] = has_u ? ldr(ps + kStageStride, rW + j) : 0.0;
+}
+
 template <bool G, bool DQ>
 TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, StepInfo& si) {
   const int N = p.N;
   const double dt = p.dt;
   double dx[NX] = {0, 0, 0, 0, 0, 0};
-  double x[NX], xnext[NX];
+  double x[NX];
   // fraction-to-boundary: alpha = min(1, tau / max_i(-ds_i/s_i)); the dual maximum is kept as a ratio bn/bd
   double qmax = 0.0, bn = 0.0, bd = 1.0, gd = 0.0;
   TT_UNROLL
@@ -679,16 +703,8 @@ TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, Ste
   for (int k = 0; k <= N; k++) {
     double* ps = s0 + (size_t)k * kStageStride;
     const bool has_x = (k >= 1), has_u = (k < N);
-    double w[NW], d[NW], ref[NW];
-    TT_UNROLL
-    for (int j = 0; j < NX; j++) {
-      w[j] = x[j];
-      d[j] = dx[j];
-    }
-    w[6] = has_u ? ldr(ps, rW + 6) : 0.0;
-    w[7] = has_u ? ldr(ps, rW + 7) : 0.0;
-    TT_UNROLL
-    for (int j = 0; j < NW; j++) ref[j] = ((j < NX) || has_u) ? ldr(ps, rREF + j) : 0.0;
+    FwdIn cur;  // all loads of the stage first (one batch in flight), then the arithmetic
+    fwd_load<G>(p, s0, k, cur);
     if (has_u) {  // request stage k+1 (and the states of k+2, read one stage ahead)
       const double* pn = ps + kStageStride;
       prefetch_rows(pn, rW + NX, NU);
@@ -697,29 +713,23 @@ TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, Ste
       prefetch_rows(pn, rZL + (G ? 0 : 2), G ? 2 * NW : 14);
       prefetch_rows(pn, rKF, 16);
     }
-    // all loads of the stage first (one batch in flight), then the arithmetic
-    double zl[NW], zu[NW], kf[16];
+    double w[NW], d[NW];
     TT_UNROLL
-    for (int j = 0; j < NW; j++) {
-      const bool var = (j < NX) ? has_x : has_u;
-      zl[j] = (var && has_lo<G>(p, j)) ? ldr(ps, rZL + j) : 0.0;
-      zu[j] = (var && has_up<G>(p, j)) ? ldr(ps, rZU + j) : 0.0;
+    for (int j = 0; j < NX; j++) {
+      w[j] = x[j];
+      d[j] = dx[j];
     }
-    TT_UNROLL
-    for (int j = 0; j < 16; j++) kf[j] = (has_u && (has_x || j >= 12)) ? ldr(ps, rKF + j) : 0.0;
-    if (has_u) {
-      TT_UNROLL
-      for (int j = 0; j < NX; j++) xnext[j] = ldr(ps + kStageStride, rW + j);
-    }
+    w[6] = cur.u[0];
+    w[7] = cur.u[1];
     // du = -K dx - (kff0 + mu*kff1)
     d[6] = d[7] = 0.0;
     if (has_u) {
-      double du0 = -(kf[12] + mu * kf[14]);
-      double du1 = -(kf[13] + mu * kf[15]);
+      double du0 = -(cur.kf[12] + mu * cur.kf[14]);
+      double du1 = -(cur.kf[13] + mu * cur.kf[15]);
       TT_UNROLL
       for (int j = 0; j < NX; j++) {
-        du0 -= kf[j] * dx[j];
-        du1 -= kf[NX + j] * dx[j];
+        du0 -= cur.kf[j] * dx[j];
+        du1 -= cur.kf[NX + j] * dx[j];
       }
       d[6] = du0;
       d[7] = du1;
@@ -729,9 +739,9 @@ TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, Ste
     {
       double d6[NX];
       TT_UNROLL
-      for (int j = 0; j < NX; j++) d6[j] = w[j] - ref[j];
+      for (int j = 0; j < NX; j++) d6[j] = w[j] - cur.ref[j];
       Q2_mul<DQ>(p, d6, g);
-      const double da = w[6] - ref[6], dw_ = w[7] - ref[7];
+      const double da = w[6] - cur.ref[6], dw_ = w[7] - cur.ref[7];
       g[6] = DQ ? p.R2[0] * da : p.R2[0] * da + p.R2[1] * dw_;
       g[7] = DQ ? p.R2[2] * dw_ : p.R2[1] * da + p.R2[2] * dw_;
     }
@@ -741,7 +751,7 @@ TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, Ste
       if (!var) continue;
       double gj = g[j];
       if (has_lo<G>(p, j)) {
-        const double rl = tt_rcp(w[j] - p.lo[j]), z = zl[j];
+        const double rl = tt_rcp(w[j] - p.lo[j]), z = cur.zl[j];
         gj -= mu * rl;
         qmax = tt_max(qmax, -d[j] * rl);
         const double ndz = z - rl * (mu - z * d[j]);  // -dz
@@ -751,7 +761,7 @@ TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, Ste
         }
       }
       if (has_up<G>(p, j)) {
-        const double ru = tt_rcp(p.up[j] - w[j]), z = zu[j];
+        const double ru = tt_rcp(p.up[j] - w[j]), z = cur.zu[j];
         gj += mu * ru;
         qmax = tt_max(qmax, d[j] * ru);
         const double ndz = z - ru * (mu + z * d[j]);
@@ -769,16 +779,16 @@ TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, Ste
     stage_lin(p, w, m);
     double y[NX];
     A_mul(m, dx, y);
-    y[0] -= xnext[0] - w[0] - dt * m.f0;
-    y[1] -= xnext[1] - w[1] - dt * m.f1;
-    y[2] -= xnext[2] - w[2] - dt * m.f2;
-    y[3] -= xnext[3] - w[3] - dt * m.f3;
-    y[4] += dt * d[7] - (xnext[4] - w[4] - dt * w[7]);
-    y[5] += dt * d[6] - (xnext[5] - w[5] - dt * w[6]);
+    y[0] -= cur.xnext[0] - w[0] - dt * m.f0;
+    y[1] -= cur.xnext[1] - w[1] - dt * m.f1;
+    y[2] -= cur.xnext[2] - w[2] - dt * m.f2;
+    y[3] -= cur.xnext[3] - w[3] - dt * m.f3;
+    y[4] += dt * d[7] - (cur.xnext[4] - w[4] - dt * w[7]);
+    y[5] += dt * d[6] - (cur.xnext[5] - w[5] - dt * w[6]);
     TT_UNROLL
     for (int j = 0; j < NX; j++) {
       dx[j] = y[j];
-      x[j] = xnext[j];
+      x[j] = cur.xnext[j];
     }
   }
   si.a_pr = (qmax > tau) ? tau / qmax : 1.0;
@@ -793,6 +803,23 @@ struct Trial {
   double J, sumlog, theta;
 };
 
+// inputs of one stage of the trial sweep
+struct TrialIn {
+  double w[NW], dw[NW], ref[NW];
+};
+TT_HD void trial_load(const Params& p, const double* s0, int k, TrialIn& t) {
+  const double* ps = s0 + (size_t)k * kStageStride;
+  const bool has_x = (k >= 1), has_u = (k < p.N);
+  TT_UNROLL
+  for (int j = 0; j < NW; j++) {
+    const bool on = (j < NX) ? true : has_u;
+    const bool var = (j < NX) ? has_x : has_u;
+    t.w[j] = on ? ldr(ps, rW + j) : 0.0;
+    t.dw[j] = var ? ldr(ps, rDW + j) : 0.0;
+    t.ref[j] = on ? ldr(ps, rREF + j) : 0.0;
+  }
+}
+
 template <bool G, bool DQ>
 TT_HD void trial_sweep(const Params& p, const double* s0, double alpha, Trial& tr) {
   const int N = p.N;
@@ -800,21 +827,16 @@ TT_HD void trial_sweep(const Params& p, const double* s0, double alpha, Trial& t
   double J = 0.0, sl_ = 0.0, th = 0.0, smin = INFINITY;
   double xn[NX];
   for (int k = N; k >= 0; k--) {
-    const double* ps = s0 + (size_t)k * kStageStride;
     const bool has_x = (k >= 1), has_u = (k < N);
-    double w[NW], ref[NW];
+    TrialIn cur;
+    trial_load(p, s0, k, cur);
+    if (has_x) prefetch_rows(s0 + (size_t)(k - 1) * kStageStride, rW, 3 * NW);  // W, DW, REF of stage k-1
+    double w[NW];
     TT_UNROLL
-    for (int j = 0; j < NW; j++) {
-      const bool on = (j < NX) ? true : has_u;
-      const bool var = (j < NX) ? has_x : has_u;
-      w[j] = on ? ldr(ps, rW + j) : 0.0;
-      if (var) w[j] += alpha * ldr(ps, rDW + j);
-      ref[j] = on ? ldr(ps, rREF + j) : 0.0;
-    }
-    if (has_x) prefetch_rows(ps - kStageStride, rW, 3 * NW);  // W, DW, REF of stage k-1 (adjacent rows)
+    for (int j = 0; j < NW; j++) w[j] = cur.w[j] + alpha * cur.dw[j];
     double d6[NX], g[NX];
     TT_UNROLL
-    for (int j = 0; j < NX; j++) d6[j] = w[j] - ref[j];
+    for (int j = 0; j < NX; j++) d6[j] = w[j] - cur.ref[j];
     Q2_mul<DQ>(p, d6, g);
     double jq = 0.0;
     TT_UNROLL
@@ -836,7 +858,7 @@ TT_HD void trial_sweep(const Params& p, const double* s0, double alpha, Trial& t
     }
     sl_ += log(prod);
     if (has_u) {
-      const double da = w[6] - ref[6], dw_ = w[7] - ref[7];
+      const double da = w[6] - cur.ref[6], dw_ = w[7] - cur.ref[7];
       jq += DQ ? p.R2[0] * da * da + p.R2[2] * dw_ * dw_
                : (p.R2[0] * da + p.R2[1] * dw_) * da + (p.R2[1] * da + p.R2[2] * dw_) * dw_;
       double f[4];
@@ -1060,6 +1082,7 @@ struct ProblemIn {
 // starting guess) and the stores into the slot, so that callers can put several loads in flight first.
 struct PackVal {
   double r, g;
+  bool g_is_r;  // cold start: the guess IS the reference value (no copy: a copy would wait for the load)
 };
 TT_HD PackVal pack_load(const Params& p, const ProblemIn& in, long long b, int k, int j) {
   const int N = p.N;
@@ -1073,10 +1096,14 @@ TT_HD PackVal pack_load(const Params& p, const ProblemIn& in, long long b, int k
     else
       v.r = (kk >= T) ? 0.0 : in.traj_inputs[(long long)((kk + k < T) ? kk + k : T - 1) * NU + (j - NX)];
   }
+  v.g = 0.0;
+  v.g_is_r = false;
   if (k == 0 && j < NX)
     v.g = in.x_init[b * NX + j];  // x_0 is data
+  else if (in.z_warm)
+    v.g = in.z_warm[b * (8LL * N + 6) + (long long)k * NW + j];
   else
-    v.g = in.z_warm ? in.z_warm[b * (8LL * N + 6) + (long long)k * NW + j] : v.r;
+    v.g_is_r = true;
   return v;
 }
 // returns true when x_init violates a state bound (the reference NLP is then infeasible)
@@ -1084,7 +1111,7 @@ TT_HD bool pack_store(const Params& p, double* s0, int k, int j, const PackVal& 
   double* ps = s0 + (size_t)k * kStageStride;
   const bool hl = ((p.bl >> j) & 1u) != 0, hu = ((p.bu >> j) & 1u) != 0;
   bool bad = false;
-  double w = v.g;
+  double w = v.g_is_r ? v.r : v.g;
   if (k == 0 && j < NX) {
     bad = (hl && w < p.lo[j]) || (hu && w > p.up[j]);
   } else {
