@@ -109,7 +109,11 @@ TT_HD void str(double* ps, int row, double v) { ps[(size_t)row * kBank] = v; }
 TT_HD void prefetch_rows(const double* ps, int row0, int n) {
 #if defined(__CUDA_ARCH__) && !defined(TTMPC_NO_PREFETCH)
   TT_UNROLL
+#ifdef TTMPC_PREFETCH_L2
+  for (int r = 0; r < n; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + (size_t)(row0 + r) * kBank));
+#else
   for (int r = 0; r < n; r++) asm volatile("prefetch.global.L1 [%0];" ::"l"(ps + (size_t)(row0 + r) * kBank));
+#endif
 #else
   (void)ps; (void)row0; (void)n;
 #endif

@@ -1,0 +1,77 @@
+"""Closed-loop parity on the GPU: identical jackknife / no-jackknife outcomes and final errors between the CUDA
+path (shim classes and the batched on-device driver) and the CPU oracle over full simulation.py-style runs."""
+import math
+
+import numpy as np
+import pytest
+
+from test_closed_loop_cpu import PARAMS, OracleController
+
+from car_trailer_mpc_b200 import closed_loop as cl
+from car_trailer_mpc_b200 import problem as pb
+from car_trailer_mpc_b200 import tracking_preset
+
+pytestmark = pytest.mark.gpu
+
+SB = {"lb": [-np.inf, -np.inf, -np.pi, -np.pi / 3, -np.pi / 4, -10.0], "ub": [np.inf, np.inf, np.pi, np.pi / 3, np.pi / 4, 10.0]}
+IB = {"lb": [-5, -np.pi / 2], "ub": [5, np.pi / 2]}
+
+
+def test_full_simulation_run_shim_vs_oracle(traj):
+    """Config 1: B=1, N=50, T_sim=40 s (801 steps), nominal plant, start on the trajectory."""
+    import torch
+    assert torch.cuda.is_available()
+    from car_trailer_mpc_b200 import MPCTrackingControl, TruckTrailerModel
+    S, U = traj
+    N = 50
+    params = dict(PARAMS, horizon=N)
+    ctl = MPCTrackingControl(TruckTrailerModel(params), params, np.eye(6), 10 * np.eye(2), SB, IB)
+    gpu = cl.simulate_single(ctl, S, U, S[0], 40.0, 0.05, N, params)
+    ref = cl.simulate_single(OracleController(tracking_preset(N)), S, U, S[0], 40.0, 0.05, N, params)
+    mg, mr = gpu.metrics(S[-1]), ref.metrics(S[-1])
+    assert mg["jackknife"] == mr["jackknife"] == False and mg["failures"] == mr["failures"] == 0
+    assert np.abs(gpu.controls - ref.controls).max() <= 1e-4          # every applied control, all 801 steps
+    assert np.abs(gpu.states - ref.states).max() <= 1e-5
+    for key in ("distance_error", "heading_error", "hitch_error", "max_abs_psi"):
+        assert abs(mg[key] - mr[key]) <= 1e-5, key
+    assert abs(mg["distance_error"] - 0.0720) < 2e-4 and abs(mg["max_abs_psi"] - 0.7488) < 2e-4
+    assert gpu.iterations == ref.iterations
+
+
+def test_batched_closed_loop_vs_single_episodes(traj):
+    """The on-device batch driver (shared-trajectory windows in-kernel, plant kernel, counter-based noise) against
+    per-scenario host loops with the oracle, nominal and disturbed, incl. a start that jackknifes."""
+    import torch
+    from car_trailer_mpc_b200 import BatchSolver
+    S, U = traj
+    N = 40
+    cfg = tracking_preset(N)
+    params = dict(PARAMS, horizon=N)
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(4)
+    B = 6
+    x0 = S[0][None] + rng.normal(0, 0.05, size=(B, 6)) * np.array([1, 1, 0.2, 0.2, 0.1, 1])
+    solver = BatchSolver(cfg, 0)
+    T_sim = 6.0
+    for dist in (None, cl.DEFAULT_DISTURBANCE):
+        out = cl.simulate_batch(solver, S, U, torch.from_numpy(x0).to(dev), T_sim, 0.05, dist, seed=11, record_every=1)
+        hist = out["history"].cpu().numpy()          # [steps, B, 6]
+        ks = pb.time_indices(T_sim, 0.05)
+        for b in range(B):
+            # host replica with the same counter-based measurement noise
+            class NoisyOracle(OracleController):
+                step = 0
+            ctl = OracleController(cfg)
+            state = x0[b].copy()
+            for step, k in enumerate(ks):
+                xs, us = pb.window(S, U, int(k), N)
+                meas = state
+                if dist is not None:
+                    n = cl.counter_normal(11, 2 * step, torch.tensor([b]), 6)[0].numpy()
+                    meas = state + dist["process_noise_std"] * n
+                r = ctl.solve(meas, xs.T, us.T)
+                state = cl.plant_update(state, r[1][:, 0], params, dist)
+                assert np.abs(state - hist[step, b]).max() <= 1e-5, (dist is not None, b, step)
+            assert bool(out["jackknife"][b]) == bool(np.abs(hist[:, b, 3]).max() > cl.JACKKNIFE_LIMIT)
+        assert int(out["failures"].sum()) == 0
+    assert out["steps"] == len(ks)
