@@ -59,7 +59,7 @@ constexpr double kAccDualInfTol = 1e10, kAccConstrViolTol = 1e-2, kAccComplInfTo
 constexpr double kGammaTheta = 1e-5, kGammaPhi = 1e-8, kEtaPhi = 1e-8;
 constexpr double kSTheta = 1.1, kSPhi = 2.3, kDeltaSw = 1.0;
 constexpr double kThetaMaxFact = 1e4, kThetaMinFact = 1e-4, kAlphaRed = 0.5;
-constexpr int kMaxBacktrack = 30, kFilterMax = 8;
+constexpr int kMaxBacktrack = 30, kFilterMax = 8, kX0InfeasibleIters = 30;
 constexpr double kEps = 2.220446049250313e-16;
 
 // status codes: keep in sync with include/ttmpc.h
@@ -948,8 +948,8 @@ TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, Ipm& s, R
           status = ST_ACCEPTABLE;
         else if (s.iter >= p.max_iter)
           status = ST_MAX_ITER;
-        else if (s.x0_infeasible)
-          status = ST_INFEASIBLE_X0;
+        else if (s.x0_infeasible && s.iter >= kX0InfeasibleIters)
+          status = ST_INFEASIBLE_X0;  // x_0 is data: keep solving; give up on the instance after this many iterations
       }
       if (status >= 0) break;
       // monotone barrier update (Ipopt MonotoneMuUpdate, fast decrease allowed)
@@ -976,7 +976,8 @@ TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, Ipm& s, R
     res.constr_viol = st.cinf;
     res.compl_inf = st.cmax;
     res.iters = s.iter;
-    res.status = status;
+    // any failure of an instance whose x_init violates a bound is reported as "infeasible x_0"
+    res.status = (s.x0_infeasible && status >= ST_MAX_ITER) ? (int)ST_INFEASIBLE_X0 : status;
     return true;
   }
 
@@ -1038,7 +1039,7 @@ TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, Ipm& s, R
       res.constr_viol = st.cinf;
       res.compl_inf = st.cmax;
       res.iters = s.iter;
-      res.status = ST_LINESEARCH;
+      res.status = s.x0_infeasible ? (int)ST_INFEASIBLE_X0 : (int)ST_LINESEARCH;
       return true;
     }
     a = si.a_pr * 9.313225746154785e-10;  // kAlphaRed^kMaxBacktrack = 2^-30

@@ -62,7 +62,8 @@ extern "C" {
 #define TTMPC_ST_MAX_ITER 2       /* iteration limit; z_out holds the last iterate               */
 #define TTMPC_ST_LINESEARCH 3     /* step rejected repeatedly (Ipopt would enter restoration)    */
 #define TTMPC_ST_NUMERIC 4        /* NaN/Inf encountered, z_out holds the last finite iterate    */
-#define TTMPC_ST_INFEASIBLE_X0 5  /* x_init violates a state bound: reference NLP is infeasible  */
+#define TTMPC_ST_INFEASIBLE_X0 5  /* x_init violates a state bound (reference NLP infeasible) and the
+                                     solve with x_0 as data did not converge within 30 iterations   */
 
 /* flags */
 #define TTMPC_FLAG_HOST_POINTERS 0x1u /* array arguments are host pointers (B=1 shim path)      */

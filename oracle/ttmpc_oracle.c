@@ -66,6 +66,7 @@ static const double S_THETA = 1.1, S_PHI = 2.3, DELTA_SW = 1.0;
 static const double THETA_MAX_FACT = 1e4, THETA_MIN_FACT = 1e-4;
 static const double ALPHA_RED = 0.5;
 static const int MAX_BACKTRACK = 30;
+static const int X0_INFEASIBLE_ITERS = 30;
 static const double MACH_EPS = 2.220446049250313e-16;
 
 typedef struct {
@@ -454,7 +455,11 @@ int ttmpc_oracle_solve(const ttmpc_config* cfg, const double* x_init, const doub
       status = TTMPC_ST_MAX_ITER;
       break;
     }
-    if (x0_infeasible) {
+    /* x_init outside a state bound: the reference NLP (x_0 bounded AND pinned) is infeasible.
+     * Deterministic policy: x_0 is data here, so the solve goes on -- a slightly violated measurement (noise on a
+     * state that rides its bound) still yields a feasible x_1..x_N and converges normally; if it has not converged
+     * after X0_INFEASIBLE_ITERS iterations the instance is reported as infeasible. */
+    if (x0_infeasible && iter >= X0_INFEASIBLE_ITERS) {
       status = TTMPC_ST_INFEASIBLE_X0;
       break;
     }
@@ -750,6 +755,9 @@ int ttmpc_oracle_solve(const ttmpc_config* cfg, const double* x_init, const doub
         }
     }
   }
+
+  /* any failure of an instance whose x_init violates a bound is reported as "infeasible x_0" */
+  if (x0_infeasible && status >= TTMPC_ST_MAX_ITER) status = TTMPC_ST_INFEASIBLE_X0;
 
   /* ---------- pack result in the reference's decision-vector layout ---------- */
   if (z_out) {
