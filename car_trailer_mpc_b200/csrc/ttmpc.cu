@@ -49,10 +49,60 @@ struct SolveOut {
 // atomic), loads that problem into its slot and joins the other lanes at the next iteration boundary.  The
 // lanes of a warp therefore always run the same sweep on consecutive slots (coalesced, convergent) although
 // their problems are at different interior-point iterations -- iteration-count divergence costs nothing.
+// ------------------------------------------------------------------------------------------------
+// scheduling order: hardest problems first
+// ------------------------------------------------------------------------------------------------
+// A batch of 65 536 is only ~1.7 problems per resident lane and iteration counts range from 5 to ~17, so the launch
+// time is set by WHEN the hard problems start (measured: arrival order 12.1 ms, sorted by true iteration count
+// 8.4 ms).  Hardness is predicted from the data: the number of reference entries that lie within 5 % of one of their
+// bounds (those get pushed off the bound at the start and ride it at the solution -- the degenerate, slowly
+// converging case); on the benchmark batch the top 20 % by this score contain 99.6 % of the >= 10-iteration problems.
+// Two tiny kernels build a permutation, classes in descending hardness; the order within a class is arbitrary
+// (atomics) -- problems are independent, so results do not depend on it.
+constexpr int kNumClasses = 4;
+TT_HD int hardness_class(int near_count) { return near_count >= 24 ? 3 : near_count >= 8 ? 2 : near_count >= 1 ? 1 : 0; }
+
+__global__ void __launch_bounds__(256) ttmpc_classify_kernel(const __grid_constant__ Params p, long long B, ProblemIn in,
+                                                             int32_t* __restrict__ cls, unsigned long long* __restrict__ hist) {
+  const unsigned lane = threadIdx.x & 31u;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nz = 8 * p.N + 6;
+  for (long long b = warp; b < B; b += nwarps) {
+    int near = 0;
+    for (int e = (int)lane; e < nz; e += 32) {
+      const int k = e >> 3, j = e & 7;
+      const bool hl = ((p.bl >> j) & 1u) != 0, hu = ((p.bu >> j) & 1u) != 0;
+      if (!(hl && hu) || k == 0) continue;  // two-sided boxes only; x_0 is data
+      const double r = ref_value(p, in, b, k, j);
+      const double margin = 0.05 * (p.up[j] - p.lo[j]);
+      near += (r - p.lo[j] < margin) || (p.up[j] - r < margin);
+    }
+    near = __reduce_add_sync(0xffffffffu, near);
+    if (lane == 0) {
+      const int c = hardness_class(near);
+      cls[b] = c;
+      atomicAdd(&hist[c], 1ull);
+    }
+  }
+}
+
+// hist[0..3] = class counts, hist[4..7] = running cursors (zeroed by the host)
+__global__ void __launch_bounds__(256) ttmpc_order_kernel(long long B, const int32_t* __restrict__ cls,
+                                                          unsigned long long* __restrict__ hist, int32_t* __restrict__ order) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int c = cls[b];
+  unsigned long long base = 0;
+  for (int h = kNumClasses - 1; h > c; h--) base += hist[h];  // harder classes go first
+  const unsigned long long pos = base + atomicAdd(&hist[kNumClasses + c], 1ull);
+  order[pos] = (int32_t)b;
+}
+
 template <bool G, bool DQ>
 __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
     ttmpc_solve_kernel(const __grid_constant__ Params p, double* __restrict__ scratch, long long B, ProblemIn in, SolveOut out,
-                       unsigned long long* __restrict__ counter) {
+                       unsigned long long* __restrict__ counter, const int32_t* __restrict__ order) {
   constexpr unsigned kFull = 0xffffffffu;
   extern __shared__ double carried[];  // loop-carried state of the backward sweep, [kCarry entries][thread]
   const Carry cy{carried + threadIdx.x, kSolveThreads};
@@ -77,7 +127,7 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
       if (!active) {
         const long long cand = (long long)base + __popc(need & ((1u << lane) - 1u));
         if (cand < B) {
-          prob = cand;
+          prob = order ? (long long)order[cand] : cand;  // queue position -> problem (hardest first)
           active = true;
         }
       }
@@ -244,13 +294,13 @@ __global__ void __launch_bounds__(256) ttmpc_dfma_kernel(double* out, double a, 
 // C ABI
 // ================================================================================================
 // kernel variant for a configuration: bound pattern (G) x weight structure (DQ)
-typedef void (*solve_kernel_t)(const Params, double*, long long, ProblemIn, SolveOut, unsigned long long*);
+typedef void (*solve_kernel_t)(const Params, double*, long long, ProblemIn, SolveOut, unsigned long long*, const int32_t*);
 static solve_kernel_t solve_kernel_for(const Params& p) {
   if (p.generic) return p.diag ? ttmpc_solve_kernel<true, true> : ttmpc_solve_kernel<true, false>;
   return p.diag ? ttmpc_solve_kernel<false, true> : ttmpc_solve_kernel<false, false>;
 }
 
-constexpr int kNumKernels = 4;
+constexpr int kNumKernels = 6;
 struct ttmpc_handle {
   ttmpc_config cfg;
   Params p;
@@ -258,7 +308,9 @@ struct ttmpc_handle {
   int max_blocks;          // resident CTAs of the persistent solve kernel on this device
   double* scratch;
   size_t banks;            // scratch capacity in banks of kBank slots
-  unsigned long long* counter;  // work queue head
+  unsigned long long* counter;  // [0] work queue head, [1..8] class histogram + cursors of the ordering pass
+  int32_t* order_buf;           // [2][order_cap]: class per problem, then the permutation
+  size_t order_cap;
   // staging for the host-pointer path
   void* stage;
   size_t stage_bytes;
@@ -267,7 +319,7 @@ struct ttmpc_handle {
 };
 
 static const char* kKernelNames[kNumKernels] = {"ttmpc_solve_kernel", "ttmpc_shift_kernel", "ttmpc_plant_kernel",
-                                                "ttmpc_dfma_kernel"};
+                                                "ttmpc_dfma_kernel", "ttmpc_classify_kernel", "ttmpc_order_kernel"};
 
 static int set_err(ttmpc_handle* h, int code, const char* what, cudaError_t ce) {
   if (h) snprintf(h->err, sizeof h->err, "%s%s%s", what, ce != cudaSuccess ? ": " : "", ce != cudaSuccess ? cudaGetErrorString(ce) : "");
@@ -333,7 +385,7 @@ int ttmpc_create(const ttmpc_config* cfg, int device, ttmpc_handle** out) {
     if (v >= 1 && v < per_sm) per_sm = v;
   }
   h->max_blocks = sms * per_sm;
-  if (cudaMalloc(&h->counter, sizeof(unsigned long long)) != cudaSuccess) {
+  if (cudaMalloc(&h->counter, 16 * sizeof(unsigned long long)) != cudaSuccess) {
     delete h;
     return TTMPC_E_NOMEM;
   }
@@ -347,6 +399,7 @@ int ttmpc_destroy(ttmpc_handle* h) {
   if (h->scratch) cudaFree(h->scratch);
   if (h->stage) cudaFree(h->stage);
   if (h->counter) cudaFree(h->counter);
+  if (h->order_buf) cudaFree(h->order_buf);
   delete h;
   return TTMPC_OK;
 }
@@ -383,8 +436,28 @@ static int solve_device(ttmpc_handle* h, long long B, const ProblemIn& in, const
   if (blocks > h->max_blocks) blocks = h->max_blocks;
   int rc = ensure_scratch(h, (size_t)blocks * kSolveThreads);
   if (rc) return rc;
-  cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st);
-  solve_kernel_for(h->p)<<<(unsigned)blocks, kSolveThreads, kSolveSmem, st>>>(h->p, h->scratch, B, in, so, h->counter);
+  cudaMemsetAsync(h->counter, 0, 16 * sizeof(unsigned long long), st);
+  const int32_t* order = nullptr;
+  if (B > blocks * kSolveThreads && B < (1ll << 31) && !getenv("TTMPC_NO_ORDER")) {
+    // more problems than resident lanes: start the (predicted) hardest ones first
+    if ((size_t)B > h->order_cap) {
+      if (h->order_buf) cudaFree(h->order_buf);
+      h->order_buf = nullptr;
+      h->order_cap = 0;
+      if (cudaMalloc(&h->order_buf, 2 * (size_t)B * sizeof(int32_t)) != cudaSuccess)
+        return set_err(h, TTMPC_E_NOMEM, "order cudaMalloc", cudaGetLastError());
+      h->order_cap = (size_t)B;
+    }
+    int32_t* cls = h->order_buf;
+    int32_t* ord = h->order_buf + h->order_cap;
+    const unsigned gc = (unsigned)((B * 32 + 255) / 256 < 148 * 8 ? (B * 32 + 255) / 256 : 148 * 8);
+    ttmpc_classify_kernel<<<gc, 256, 0, st>>>(h->p, B, in, cls, h->counter + 1);
+    h->launches[4]++;
+    ttmpc_order_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, cls, h->counter + 1, ord);
+    h->launches[5]++;
+    order = ord;
+  }
+  solve_kernel_for(h->p)<<<(unsigned)blocks, kSolveThreads, kSolveSmem, st>>>(h->p, h->scratch, B, in, so, h->counter, order);
   h->launches[0]++;
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "kernel launch", ce);

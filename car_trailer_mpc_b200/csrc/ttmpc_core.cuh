@@ -132,6 +132,14 @@ inline size_t scratch_doubles(int N, size_t nbanks) { return nbanks * (size_t)(N
 // ------------------------------------------------------------------------------------------------
 // max/min by compare+select (3 instructions); fmax/fmin on doubles expand to ~10 because of their NaN rules.
 // NaNs are not propagated by these -- the sums J / theta / sumlog carry them to the finite check instead.
+// compiler-only scheduling fence between the phases of a stage: keeps the optimiser from hoisting every load of the
+// stage to its top and thereby holding ~250 values live (register pressure decides the occupancy of this kernel)
+#if defined(__CUDA_ARCH__) && defined(TTMPC_PHASE_FENCE)
+#define TT_FENCE() asm volatile("" ::: "memory")
+#else
+#define TT_FENCE() ((void)0)
+#endif
+
 TT_HD double tt_max(double a, double b) { return a > b ? a : b; }
 TT_HD double tt_min(double a, double b) { return a < b ? a : b; }
 
@@ -424,6 +432,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, bool do_
       }
     }
 
+    TT_FENCE();
     // ---------------------------------------------------------------- (ii) statistics at the new iterate
     double g0[NW], g1[NW], sig[NW];  // grad J, d(barrier gradient)/d(mu), Sigma (+delta)
     {
@@ -536,6 +545,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, bool do_
           }
         }
       }
+      TT_FENCE();
       // ---- Riccati step.  T = P A
       double P[21], p0[NX], p1[NX];
       TT_UNROLL
@@ -1089,18 +1099,20 @@ struct PackVal {
   double r, g;
   bool g_is_r;  // cold start: the guess IS the reference value (no copy: a copy would wait for the load)
 };
+// reference value (stage k, component j) of problem b: the caller's window, or the window rules of
+// simulation.py:485-499 applied to the shared trajectory
+TT_HD double ref_value(const Params& p, const ProblemIn& in, long long b, int k, int j) {
+  const int N = p.N;
+  if (in.ref_states != nullptr)
+    return (j < NX) ? in.ref_states[(b * (N + 1) + k) * NX + j] : in.ref_inputs[(b * N + k) * NU + (j - NX)];
+  const int T = in.T, kk = in.k_index[b];
+  if (j < NX) return in.traj_states[(long long)((kk < T) ? ((kk + k < T) ? kk + k : T) : T) * NX + j];
+  return (kk >= T) ? 0.0 : in.traj_inputs[(long long)((kk + k < T) ? kk + k : T - 1) * NU + (j - NX)];
+}
 TT_HD PackVal pack_load(const Params& p, const ProblemIn& in, long long b, int k, int j) {
   const int N = p.N;
   PackVal v;
-  if (in.ref_states != nullptr) {
-    v.r = (j < NX) ? in.ref_states[(b * (N + 1) + k) * NX + j] : in.ref_inputs[(b * N + k) * NU + (j - NX)];
-  } else {
-    const int T = in.T, kk = in.k_index[b];
-    if (j < NX)
-      v.r = in.traj_states[(long long)((kk < T) ? ((kk + k < T) ? kk + k : T) : T) * NX + j];
-    else
-      v.r = (kk >= T) ? 0.0 : in.traj_inputs[(long long)((kk + k < T) ? kk + k : T - 1) * NU + (j - NX)];
-  }
+  v.r = ref_value(p, in, b, k, j);
   v.g = 0.0;
   v.g_is_r = false;
   if (k == 0 && j < NX)
