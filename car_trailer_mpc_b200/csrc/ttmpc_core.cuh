@@ -999,8 +999,10 @@ TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, Ipm& s, R
   const double phi = st.J - mu * st.sumlog;
   double a = si.a_pr;
   // Round-off regime (analogue of Ipopt's tiny-step rule in function values): predicted change of phi below its
-  // resolution and constraint violation far below tol -> theta/phi comparisons are noise; take the full step.
-  const bool roundoff_step = (fabs(si.gphi_d) <= 100.0 * kEps * fmax(1.0, fabs(phi))) && (theta <= 1e-2 * p.tol);
+  // resolution (or below the c'lambda evaluation noise theta*||lambda||_1) and constraint violation far below tol
+  // -> theta/phi comparisons are noise; take the full step.
+  const bool roundoff_step = (theta <= 1e-2 * p.tol) &&
+                             (fabs(si.gphi_d) <= fmax(100.0 * kEps * fmax(1.0, fabs(phi)), theta * st.lam1));
   bool accepted = roundoff_step;
   for (int bt = 0; !roundoff_step && bt <= kMaxBacktrack; bt++, a *= kAlphaRed) {
     Trial tr;

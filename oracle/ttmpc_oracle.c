@@ -656,9 +656,11 @@ int ttmpc_oracle_solve(const ttmpc_config* cfg, const double* x_init, const doub
     eval_t tr;
     /* Round-off regime (the analogue of Ipopt's tiny-step rule, expressed in function values): when the
      * predicted change of the barrier objective is below the resolution of phi and the constraint violation
-     * is already far below the tolerance, neither theta nor phi can be compared reliably (c'lambda terms of
-     * size eps*|x| make grad(phi)'d come out with either sign) -- take the full fraction-to-boundary step. */
-    const int roundoff_step = (fabs(gphi_d) <= 100.0 * MACH_EPS * fmax(1.0, fabs(phi))) && (theta <= 1e-2 * p->tol);
+     * is already far below the tolerance, neither theta nor phi can be compared reliably: grad(phi)'d =
+     * -d'Hd + c'lambda+ and the second term is pure evaluation noise bounded by theta*||lambda||_1, so it comes out
+     * with either sign -- take the full fraction-to-boundary step. */
+    const int roundoff_step = (theta <= 1e-2 * p->tol) &&
+                              (fabs(gphi_d) <= fmax(100.0 * MACH_EPS * fmax(1.0, fabs(phi)), theta * lam1));
     if (roundoff_step) accepted = 1;
     for (int bt = 0; !roundoff_step && bt <= MAX_BACKTRACK; bt++, alpha *= ALPHA_RED) {
       for (int i = 0; i < NX; i++) w->tx[0][i] = it->x[0][i];
