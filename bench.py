@@ -31,7 +31,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -49,36 +48,40 @@ def algorithmic_bytes_per_solve(N: int) -> int:
     return (8 * N + 12) * 8 + (8 * N + 6) * 8 + 40
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+class ClockSampler:
+    """Samples SM clocks / throttle reasons of one GPU while the timed region runs: one long-lived
+    `nvidia-smi -lms 50` process (a fresh nvidia-smi per sample would take longer than a whole timed region)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
         self.index = index
-        self.samples = []
-        self._halt = threading.Event()
+        self.proc = None
 
-    def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc.stdout.readline()  # first sample = process is up; the timed region starts after this
+        except Exception:
+            self.proc = None
 
     def finish(self) -> dict:
-        self._halt.set()
-        self.join(timeout=6)
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        samples = []
+        if self.proc is not None:
+            time.sleep(0.06)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            samples = [[c.strip() for c in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+        sm = [float(s[0]) for s in samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for s in samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -211,6 +214,51 @@ def main() -> None:
         st_h.copy_(r["status"], non_blocking=True)
         return r
 
+    # e2e, pipelined over steps: copy-in / solve / copy-out on three streams with double-buffered device tensors, so
+    # step s+1's H2D and step s-1's D2H overlap step s's kernel.  Every step still moves its full inputs from pinned
+    # host memory and its full outputs back inside the timed region.
+    s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+    din = [tuple(torch.empty_like(t, device=dev) for t in (x_h, xs_h, us_h)) for _ in range(2)]
+
+    def run_e2e_pipelined(steps: int) -> float:
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_cmp = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        cur = torch.cuda.current_stream(dev)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(cur)
+        for st_ in (s_in, s_cmp, s_out):
+            st_.wait_event(t0)
+        for i in range(steps):
+            b = i % 2
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(ev_cmp[b])  # the solve that read this input buffer is done
+                for d_, h_ in zip(din[b], (x_h, xs_h, us_h)):
+                    d_.copy_(h_, non_blocking=True)
+                ev_in[b].record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in[b])
+                r_ = solver.solve(*din[b], stream=s_cmp.cuda_stream)
+                ev_cmp[b].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[b])
+                if i >= 1:
+                    s_out.wait_event(ev_out[1 - b])
+                for t_ in (r_["z"], r_["u0"], r_["status"]):
+                    t_.record_stream(s_out)
+                z_h.copy_(r_["z"], non_blocking=True)
+                u0_h.copy_(r_["u0"], non_blocking=True)
+                st_h.copy_(r_["status"], non_blocking=True)
+                ev_out[b].record(s_out)
+        for st_ in (s_in, s_cmp, s_out):
+            e = torch.cuda.Event()
+            e.record(st_)
+            cur.wait_event(e)
+        t1.record(cur)
+        torch.cuda.synchronize(dev)
+        return t0.elapsed_time(t1)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -236,8 +284,12 @@ def main() -> None:
     sampler.start()
     total_ms, per_ms, r, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.finish()
-    e2e_total_ms, _, _, _ = timed(step_e2e, max(3, min(args.steps, 10)), 2)
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(4, min(args.steps, 12))
+    e2e_serial_ms, _, _, _ = timed(step_e2e, e2e_steps, 2)   # one stream: copy-in, solve, copy-out back to back
+    run_e2e_pipelined(2)
+    barrier()
+    e2e_total_ms = run_e2e_pipelined(e2e_steps)
+    barrier()
 
     iters = r["iters"].cpu().numpy()
     status = r["status"].cpu().numpy()
@@ -298,7 +350,9 @@ def main() -> None:
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(x_h.numel() + xs_h.numel() + us_h.numel()) * 8,
                     "d2h_bytes_per_step": int(z_h.numel() + u0_h.numel()) * 8 + int(st_h.numel()) * 4,
-                    "ms_per_step": e2e_total_ms / e2e_steps, "steps": e2e_steps},
+                    "ms_per_step": e2e_total_ms / e2e_steps, "steps": e2e_steps,
+                    "mode": "3-stream pipeline over steps (copy-in | solve | copy-out), double-buffered",
+                    "serial_ms_per_step": e2e_serial_ms / e2e_steps},
             "gpu_launches": int(launches),
             "kernels": {k: v for k, v in solver.kernel_launches().items() if v},
             "clocks": clocks,
