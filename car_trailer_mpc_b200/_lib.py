@@ -56,6 +56,9 @@ def load():
     L.ttmpc_shift_warm_start.restype = ctypes.c_int
     L.ttmpc_plant_step.argtypes = [H, ctypes.c_int64, c_dp, c_dp, c_dp, c_dp, ctypes.c_double, c_dp, ctypes.c_void_p]
     L.ttmpc_plant_step.restype = ctypes.c_int
+    L.ttmpc_episode_batch.argtypes = [H, ctypes.c_int64, c_dp, c_dp, c_dp, c_dp, ctypes.c_int32, c_dp, ctypes.c_int32, c_dp,
+                                      ctypes.c_int32, ctypes.c_uint64, c_dp, c_dp, ctypes.c_void_p]
+    L.ttmpc_episode_batch.restype = ctypes.c_int
     L.ttmpc_launch_count.argtypes = [H]
     L.ttmpc_launch_count.restype = ctypes.c_int64
     L.ttmpc_kernel_name.argtypes = [H, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]
@@ -68,6 +71,6 @@ def load():
 
 EXPORTS = [
     "ttmpc_default_config", "ttmpc_create", "ttmpc_destroy", "ttmpc_last_error", "ttmpc_version",
-    "ttmpc_solve_batch", "ttmpc_solve_batch_shared", "ttmpc_shift_warm_start", "ttmpc_plant_step",
+    "ttmpc_solve_batch", "ttmpc_solve_batch_shared", "ttmpc_shift_warm_start", "ttmpc_plant_step", "ttmpc_episode_batch",
     "ttmpc_launch_count", "ttmpc_kernel_name", "ttmpc_measure_fp64_peak",
 ]

@@ -234,42 +234,229 @@ __global__ void ttmpc_shift_kernel(int N, long long B, const double* __restrict_
   }
 }
 
-__global__ void ttmpc_plant_kernel(const __grid_constant__ Params p, long long B, const double* __restrict__ q, const double* __restrict__ u,
-                                   int has_dist, double fric, double slipc, double lat_gain, double slip_max,
-                                   const double* __restrict__ noise, double noise_scale, double* __restrict__ q_next) {
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  double x[NX], f[4];
-#pragma unroll
-  for (int j = 0; j < NX; j++) x[j] = q[b * NX + j];
-  double a = u[b * 2 + 0], w = u[b * 2 + 1];
-  if (has_dist) {
-    a *= fric;
-    w *= slipc;
+// update()/f_dyn of the closed-loop drivers (simulation.py:34-48,167-199; noise term of simulation_nmpc.py:100)
+struct Disturb {
+  int on;
+  double fric, slipc, lat_gain, slip_max;
+};
+__device__ __forceinline__ void plant_step_dev(const Params& p, const double* x, double a, double w, const Disturb& d,
+                                               const double* noise, double noise_scale, double* y) {
+  double f[4];
+  if (d.on) {
+    a *= d.fric;
+    w *= d.slipc;
   }
   stage_f(p, x, f);
   double fd[NX] = {f[0], f[1], f[2], f[3], w, a};
-  if (has_dist) {
-    const double slip = 1.0 - fmin(fabs(x[4]) * fabs(x[5]) * slip_max, 0.3);
+  if (d.on) {
+    const double slip = 1.0 - fmin(fabs(x[4]) * fabs(x[5]) * d.slip_max, 0.3);
     fd[2] *= slip;
     fd[3] *= slip;
   }
-  double y[NX];
 #pragma unroll
   for (int j = 0; j < NX; j++) y[j] = x[j] + fd[j] * p.dt;
   if (noise) {
 #pragma unroll
-    for (int j = 0; j < NX; j++) y[j] += noise[b * NX + j] * noise_scale;
+    for (int j = 0; j < NX; j++) y[j] += noise[j] * noise_scale;
   }
-  if (has_dist) {
-    const double mag = lat_gain * fabs(x[5]) * fabs(x[4]);
+  if (d.on) {
+    const double mag = d.lat_gain * fabs(x[5]) * fabs(x[4]);
     double sn, cs;
     sincos(x[2] + 1.5707963267948966, &sn, &cs);
     y[0] += mag * cs * p.dt;
     y[1] += mag * sn * p.dt;
   }
+}
+
+__global__ void ttmpc_plant_kernel(const __grid_constant__ Params p, long long B, const double* __restrict__ q, const double* __restrict__ u,
+                                   Disturb d, const double* __restrict__ noise, double noise_scale, double* __restrict__ q_next) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[NX], y[NX], nz_[NX];
+#pragma unroll
+  for (int j = 0; j < NX; j++) x[j] = q[b * NX + j];
+  if (noise) {
+#pragma unroll
+    for (int j = 0; j < NX; j++) nz_[j] = noise[b * NX + j];
+  }
+  plant_step_dev(p, x, u[b * 2 + 0], u[b * 2 + 1], d, noise ? nz_ : nullptr, noise_scale, y);
 #pragma unroll
   for (int j = 0; j < NX; j++) q_next[b * NX + j] = y[j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// closed-loop episodes entirely on the device
+// ------------------------------------------------------------------------------------------------
+// Counter-based standard normal keyed on (seed, step, scenario id, component): splitmix64 -> Box-Muller.  The host
+// twin is closed_loop.counter_normal (same integer hash; the transcendental tail may differ in the last ulp).
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double counter_normal(unsigned long long seed, unsigned long long step, unsigned long long id, int comp) {
+  const unsigned long long key = seed * 0x2545F4914F6CDD1Dull + step * 0x1B03738712FAD5C9ull;
+  const unsigned long long x = id * 0x9E3779B97F4A7C15ull + (unsigned long long)comp * 0x632BE59BD9B4E019ull + key;
+  const unsigned long long a = mix64(x), b = mix64(a ^ 0x5851F42D4C957F2Dull);
+  const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+}
+
+struct EpisodeArgs {
+  const double* x0;           // [B][6] initial states
+  const long long* ids;       // [B] global scenario ids (noise keys) or null = 0..B-1
+  const double* traj_states;  // [T+1][6]
+  const double* traj_inputs;  // [T][2]
+  int T;
+  const int32_t* k_seq;       // [steps] window index per control step (float-accumulated floor(t/dt), host-built)
+  int steps;
+  Disturb dist;
+  double noise_std;           // process_noise_std of simulation.py:29
+  int variant;                // 0: simulation.py (measurement noise), 1: simulation_nmpc.py (plant noise*dt, zero u on failure)
+  unsigned long long seed;
+  double* xmeas;              // [B][6] scratch: measured state handed to the solve
+  int32_t* kcur;              // [B]    scratch: window index handed to the solve
+  double* metrics;            // [B][8]: dist err, |heading err|, |hitch err|, max|psi|, jackknife, failures, mean iters, rms track err
+  double* final_state;        // [B][6] or null
+};
+
+// Same persistent-lane machinery as ttmpc_solve_kernel, but a lane keeps its scenario for all `steps` control steps:
+// when a solve terminates the lane applies u_0 to the plant (disturbance model included), updates the episode
+// metrics, forms the next measurement and re-enters the queue of lanes whose slot must be (re)loaded.  No host
+// round trip per step and no per-step barrier across scenarios: stragglers only delay their own lane.
+template <bool G, bool DQ>
+__global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
+    ttmpc_episode_kernel(const __grid_constant__ Params p, double* __restrict__ scratch, long long B, EpisodeArgs ea,
+                         unsigned long long* __restrict__ counter) {
+  constexpr unsigned kFull = 0xffffffffu;
+  extern __shared__ double carried[];
+  const Carry cy{carried + threadIdx.x, kSolveThreads};
+  const size_t slot = (size_t)blockIdx.x * kSolveThreads + threadIdx.x;
+  double* s0 = slot_ptr(scratch, p.N, slot);
+  const unsigned lane = threadIdx.x & 31u;
+  double* s_warp = s0 - lane;
+  const int nz = 8 * p.N + 6;
+  const ProblemIn in{ea.xmeas, nullptr, nullptr, nullptr, ea.kcur, ea.traj_states, ea.traj_inputs, ea.T};
+  long long scen = -1;
+  unsigned long long sid = 0;
+  bool active = false, exhausted = false, need_pack = false;
+  int step = 0, fails = 0;
+  long long iters_sum = 0;
+  double x[NX], max_psi = 0.0, sq_err = 0.0;
+  Ipm st;
+  Result res;
+  for (;;) {
+    const unsigned need = __ballot_sync(kFull, !active);
+    if (need && !exhausted) {
+      const int leader = __ffs(need) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(need));
+      base = __shfl_sync(kFull, base, leader);
+      if (!active) {
+        const long long cand = (long long)base + __popc(need & ((1u << lane) - 1u));
+        if (cand < B) {
+          scen = cand;
+          sid = ea.ids ? (unsigned long long)ea.ids[scen] : (unsigned long long)scen;
+          active = true;
+          step = 0;
+          fails = 0;
+          iters_sum = 0;
+          sq_err = 0.0;
+#pragma unroll
+          for (int j = 0; j < NX; j++) x[j] = ea.x0[scen * NX + j];
+          max_psi = fabs(x[3]);
+          need_pack = true;
+        }
+      }
+      if ((long long)base + __popc(need) >= B) exhausted = true;
+    }
+    // lanes about to solve publish their measurement and window index, then the warp loads the slots
+    if (need_pack) {
+      const bool meas_noise = (ea.variant == 0) && ea.dist.on && ea.noise_std > 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; j++)
+        ea.xmeas[scen * NX + j] = x[j] + (meas_noise ? ea.noise_std * counter_normal(ea.seed, 2ull * step, sid, j) : 0.0);
+      ea.kcur[scen] = ea.k_seq[step];
+    }
+    __syncwarp();
+    const unsigned fresh = __ballot_sync(kFull, need_pack);
+    for (unsigned m = fresh; m; m &= m - 1) {
+      const int l = __ffs(m) - 1;
+      const long long pb = __shfl_sync(kFull, scen, l);
+      bool bad = false;
+      for (int e0 = (int)lane; e0 < nz; e0 += 32 * kCopyUnroll) {
+        PackVal v[kCopyUnroll];
+#pragma unroll
+        for (int u = 0; u < kCopyUnroll; u++) {
+          const int e = e0 + 32 * u;
+          if (e < nz) v[u] = pack_load(p, in, pb, e >> 3, e & 7);
+        }
+#pragma unroll
+        for (int u = 0; u < kCopyUnroll; u++) {
+          const int e = e0 + 32 * u;
+          if (e < nz) bad |= pack_store(p, s_warp + l, e >> 3, e & 7, v[u]);
+        }
+      }
+      bad = __any_sync(kFull, bad);
+      if ((int)lane == l) ipm_begin(p, st, bad);
+    }
+    need_pack = false;
+    __syncwarp();
+    if (!__any_sync(kFull, active)) break;
+
+    bool done = false;
+    if (active) done = ipm_iteration<G, DQ>(p, s0, cy, st, res);
+    __syncwarp();
+
+    if (done) {
+      const bool ok = res.status <= ST_ACCEPTABLE;
+      double ua = ldr(s0, rW + 6), uw = ldr(s0, rW + 7);
+      if (!ok) {
+        fails++;
+        if (ea.variant == 1) ua = uw = 0.0;  // simulation_nmpc.py:211: zero control on failure
+      }
+      iters_sum += res.iters;
+      double nz6[NX], y[NX];
+      const bool plant_noise = (ea.variant == 1) && ea.dist.on && ea.noise_std > 0.0;
+      if (plant_noise) {
+#pragma unroll
+        for (int j = 0; j < NX; j++) nz6[j] = ea.noise_std * counter_normal(ea.seed, 2ull * step + 1ull, sid, j);
+      }
+      plant_step_dev(p, x, ua, uw, ea.dist, plant_noise ? nz6 : nullptr, p.dt, y);
+#pragma unroll
+      for (int j = 0; j < NX; j++) x[j] = y[j];
+      max_psi = fmax(max_psi, fabs(x[3]));
+      const int kn = min(ea.k_seq[step] + 1, ea.T);
+      const double ex = x[0] - ea.traj_states[(long long)kn * NX + 0], ey = x[1] - ea.traj_states[(long long)kn * NX + 1];
+      sq_err += ex * ex + ey * ey;
+      step++;
+      if (step < ea.steps) {
+        need_pack = true;
+      } else {
+        const double* goal = ea.traj_states + (long long)ea.T * NX;
+        const double kPi = 3.141592653589793, k2Pi = 6.283185307179586;
+        double he = fmod(x[2] - goal[2] + kPi, k2Pi);
+        if (he < 0.0) he += k2Pi;
+        double hi = fmod(x[3] - goal[3] + kPi, k2Pi);
+        if (hi < 0.0) hi += k2Pi;
+        double* mo = ea.metrics + scen * 8;
+        mo[0] = hypot(x[0] - goal[0], x[1] - goal[1]);
+        mo[1] = fabs(he - kPi);
+        mo[2] = fabs(hi - kPi);
+        mo[3] = max_psi;
+        mo[4] = (max_psi > 1.0471975511965976 + 1e-6) ? 1.0 : 0.0;  // builder-defined jackknife flag
+        mo[5] = (double)fails;
+        mo[6] = (double)iters_sum / (double)ea.steps;
+        mo[7] = sqrt(sq_err / (double)ea.steps);
+        if (ea.final_state) {
+#pragma unroll
+          for (int j = 0; j < NX; j++) ea.final_state[scen * NX + j] = x[j];
+        }
+        active = false;
+      }
+    }
+  }
 }
 
 // FP64 FMA peak: 8 independent dependent-chains per thread, 2 flop per FMA.
@@ -300,7 +487,13 @@ static solve_kernel_t solve_kernel_for(const Params& p) {
   return p.diag ? ttmpc_solve_kernel<false, true> : ttmpc_solve_kernel<false, false>;
 }
 
-constexpr int kNumKernels = 6;
+typedef void (*episode_kernel_t)(const Params, double*, long long, EpisodeArgs, unsigned long long*);
+static episode_kernel_t episode_kernel_for(const Params& p) {
+  if (p.generic) return p.diag ? ttmpc_episode_kernel<true, true> : ttmpc_episode_kernel<true, false>;
+  return p.diag ? ttmpc_episode_kernel<false, true> : ttmpc_episode_kernel<false, false>;
+}
+
+constexpr int kNumKernels = 7;
 struct ttmpc_handle {
   ttmpc_config cfg;
   Params p;
@@ -311,6 +504,8 @@ struct ttmpc_handle {
   unsigned long long* counter;  // [0] work queue head, [1..8] class histogram + cursors of the ordering pass
   int32_t* order_buf;           // [2][order_cap]: class per problem, then the permutation
   size_t order_cap;
+  void* ep_buf;                 // episode scratch: xmeas [B][6] doubles + kcur [B] int32
+  size_t ep_cap;
   // staging for the host-pointer path
   void* stage;
   size_t stage_bytes;
@@ -319,7 +514,8 @@ struct ttmpc_handle {
 };
 
 static const char* kKernelNames[kNumKernels] = {"ttmpc_solve_kernel", "ttmpc_shift_kernel", "ttmpc_plant_kernel",
-                                                "ttmpc_dfma_kernel", "ttmpc_classify_kernel", "ttmpc_order_kernel"};
+                                                "ttmpc_dfma_kernel", "ttmpc_classify_kernel", "ttmpc_order_kernel",
+                                                "ttmpc_episode_kernel"};
 
 static int set_err(ttmpc_handle* h, int code, const char* what, cudaError_t ce) {
   if (h) snprintf(h->err, sizeof h->err, "%s%s%s", what, ce != cudaSuccess ? ": " : "", ce != cudaSuccess ? cudaGetErrorString(ce) : "");
@@ -400,6 +596,7 @@ int ttmpc_destroy(ttmpc_handle* h) {
   if (h->stage) cudaFree(h->stage);
   if (h->counter) cudaFree(h->counter);
   if (h->order_buf) cudaFree(h->order_buf);
+  if (h->ep_buf) cudaFree(h->ep_buf);
   delete h;
   return TTMPC_OK;
 }
@@ -442,6 +639,7 @@ static int solve_device(ttmpc_handle* h, long long B, const ProblemIn& in, const
     // more problems than resident lanes: start the (predicted) hardest ones first
     if ((size_t)B > h->order_cap) {
       if (h->order_buf) cudaFree(h->order_buf);
+  if (h->ep_buf) cudaFree(h->ep_buf);
       h->order_buf = nullptr;
       h->order_cap = 0;
       if (cudaMalloc(&h->order_buf, 2 * (size_t)B * sizeof(int32_t)) != cudaSuccess)
@@ -643,13 +841,64 @@ int ttmpc_plant_step(ttmpc_handle* h, int64_t B, const double* q, const double* 
   }
   // disturb is always a HOST array of 4 doubles (configuration, not data)
   const int has = disturb != nullptr;
-  ttmpc_plant_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(h->p, B, dq, du, has, has ? disturb[0] : 1.0, has ? disturb[1] : 1.0,
-                                                               has ? disturb[2] : 0.0, has ? disturb[3] : 0.0, dn, noise_scale, dy);
+  const Disturb dd{has, has ? disturb[0] : 1.0, has ? disturb[1] : 1.0, has ? disturb[2] : 0.0, has ? disturb[3] : 0.0};
+  ttmpc_plant_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(h->p, B, dq, du, dd, dn, noise_scale, dy);
   h->launches[2]++;
   if (host) cudaMemcpyAsync(q_next, dy, bq, cudaMemcpyDeviceToHost, st);
   cudaError_t ce = cudaGetLastError();
   if (ce == cudaSuccess && (host || (h->cfg.flags & TTMPC_FLAG_SYNC))) ce = cudaStreamSynchronize(st);
   if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "plant step", ce);
+  return TTMPC_OK;
+}
+
+int ttmpc_episode_batch(ttmpc_handle* h, int64_t B, const double* x0, const int64_t* ids, const double* traj_states,
+                        const double* traj_inputs, int32_t T, const int32_t* k_seq, int32_t steps, const double* disturb,
+                        int32_t variant, uint64_t seed, double* metrics_out, double* final_state_out, void* cuda_stream) {
+  if (!h) return TTMPC_E_INVAL;
+  h->err[0] = 0;
+  if (B < 0 || !x0 || !traj_states || !traj_inputs || T < 1 || !k_seq || steps < 1 || !metrics_out || (variant != 0 && variant != 1))
+    return set_err(h, TTMPC_E_INVAL, "bad episode arguments", cudaSuccess);
+  if (h->cfg.flags & TTMPC_FLAG_HOST_POINTERS) return set_err(h, TTMPC_E_INVAL, "episodes need device pointers", cudaSuccess);
+  if (B == 0) return TTMPC_OK;
+  if (cudaSetDevice(h->device) != cudaSuccess) return set_err(h, TTMPC_E_NODEV, "cudaSetDevice", cudaGetLastError());
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  cudaError_t ce = cudaFuncSetAttribute(episode_kernel_for(h->p), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmem);
+  if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "episode kernel attribute", ce);
+  long long blocks = (B + kSolveThreads - 1) / kSolveThreads;
+  if (blocks > h->max_blocks) blocks = h->max_blocks;
+  int rc = ensure_scratch(h, (size_t)blocks * kSolveThreads);
+  if (rc) return rc;
+  const size_t need = (size_t)B * (NX * sizeof(double) + sizeof(int32_t));
+  if (need > h->ep_cap) {
+    if (h->ep_buf) cudaFree(h->ep_buf);
+    h->ep_buf = nullptr;
+    h->ep_cap = 0;
+    if (cudaMalloc(&h->ep_buf, need) != cudaSuccess) return set_err(h, TTMPC_E_NOMEM, "episode cudaMalloc", cudaGetLastError());
+    h->ep_cap = need;
+  }
+  EpisodeArgs ea;
+  ea.x0 = x0;
+  ea.ids = (const long long*)ids;
+  ea.traj_states = traj_states;
+  ea.traj_inputs = traj_inputs;
+  ea.T = T;
+  ea.k_seq = k_seq;
+  ea.steps = steps;
+  const int has = disturb != nullptr;  // disturb: HOST array {friction, slippage, lateral_slip_gain, slip_angle_max, process_noise_std}
+  ea.dist = Disturb{has, has ? disturb[0] : 1.0, has ? disturb[1] : 1.0, has ? disturb[2] : 0.0, has ? disturb[3] : 0.0};
+  ea.noise_std = has ? disturb[4] : 0.0;
+  ea.variant = variant;
+  ea.seed = seed;
+  ea.xmeas = (double*)h->ep_buf;
+  ea.kcur = (int32_t*)((char*)h->ep_buf + (size_t)B * NX * sizeof(double));
+  ea.metrics = metrics_out;
+  ea.final_state = final_state_out;
+  cudaMemsetAsync(h->counter, 0, 16 * sizeof(unsigned long long), st);
+  episode_kernel_for(h->p)<<<(unsigned)blocks, kSolveThreads, kSolveSmem, st>>>(h->p, h->scratch, B, ea, h->counter);
+  h->launches[6]++;
+  ce = cudaGetLastError();
+  if (ce == cudaSuccess && (h->cfg.flags & TTMPC_FLAG_SYNC)) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "episode launch", ce);
   return TTMPC_OK;
 }
 

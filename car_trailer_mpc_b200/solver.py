@@ -202,6 +202,39 @@ class BatchSolver:
         self._check(h, rc, "ttmpc_shift_warm_start")
         return out
 
+    def episodes(self, x0, traj_states, traj_inputs, k_seq, disturb: Optional[dict] = None, variant: str = "tracking",
+                 seed: int = 0, scenario_ids=None, stream=None) -> dict:
+        """B closed-loop episodes entirely on the device (``ttmpc_episode_batch``): ``x0 [B,6]`` torch CUDA tensor,
+        ``k_seq`` the host-built window-index sequence (``problem.time_indices``).  Returns ``metrics [B,8]`` (columns:
+        distance error, |heading error|, |hitch error|, max|psi|, jackknife, failed solves, mean iterations, RMS
+        tracking error) and ``final_state [B,6]``."""
+        import torch
+
+        dev = x0.device
+        assert x0.dtype == torch.float64 and x0.is_contiguous() and x0.shape[1] == 6
+        B = x0.shape[0]
+        S = torch.as_tensor(traj_states, dtype=torch.float64, device=dev).contiguous()
+        U = torch.as_tensor(traj_inputs, dtype=torch.float64, device=dev).contiguous()
+        ks = torch.as_tensor(np.asarray(k_seq, dtype=np.int32), device=dev).contiguous()
+        ids = None if scenario_ids is None else scenario_ids.to(device=dev, dtype=torch.int64).contiguous()
+        d = None
+        if disturb is not None:
+            d = (ctypes.c_double * 5)(disturb.get("friction_coeff", 1.0), disturb.get("slippage_coeff", 1.0),
+                                      disturb.get("lateral_slip_gain", 0.0), disturb.get("slip_angle_max", 0.0),
+                                      disturb.get("process_noise_std", 0.0))
+        metrics = torch.empty((B, 8), dtype=torch.float64, device=dev)
+        final = torch.empty((B, 6), dtype=torch.float64, device=dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        h = self._handle(0)
+        rc = self._L.ttmpc_episode_batch(
+            h, B, x0.data_ptr(), None if ids is None else ids.data_ptr(), S.data_ptr(), U.data_ptr(), U.shape[0], ks.data_ptr(),
+            int(ks.numel()), ctypes.cast(d, ctypes.c_void_p) if d is not None else None, 0 if variant == "tracking" else 1,
+            ctypes.c_uint64(int(seed) & ((1 << 64) - 1)), metrics.data_ptr(), final.data_ptr(), stream)
+        self._check(h, rc, "ttmpc_episode_batch")
+        self._keepalive = (S, U, ks, ids)
+        return {"metrics": metrics, "final_state": final}
+
     def plant_step(self, q, u, disturb: Optional[dict] = None, noise=None, noise_scale: float = 0.0, stream=None):
         """One Euler plant step ``update(q,u)`` of simulation.py:167-199 for ``q [B,6]``, ``u [B,2]``.
 

@@ -20,6 +20,8 @@
  *   ttmpc_shift_warm_start  <- TruckTrailerNMPC._shift_solution (mpc_control_nmpc.py:69-88).
  *   ttmpc_plant_step        <- update()/f_dyn of the drivers (simulation.py:34-48,167-199,
  *                              simulation_nmpc.py:94-105) for on-device closed loops.
+ *   ttmpc_episode_batch     <- the whole closed loop of simulation.py:484-560 /
+ *                              simulation_nmpc.py:192-255 for B vehicles, on the device.
  *
  * Layouts are the reference's own:
  *   decision vector  z = [x_0;u_0;x_1;u_1;...;x_{N-1};u_{N-1};x_N], 8N+6 doubles
@@ -139,6 +141,21 @@ int ttmpc_shift_warm_start(ttmpc_handle* h, int64_t B, const double* z, double* 
 int ttmpc_plant_step(ttmpc_handle* h, int64_t B, const double* q, const double* u,
                      const double* disturb, const double* noise, double noise_scale,
                      double* q_next, void* cuda_stream);
+
+/* B closed-loop episodes entirely on the device: the `while t <= T_sim` loop of simulation.py:484-560 (variant 0:
+ * measurement noise on the state handed to the controller, simulation.py:513-517) or simulation_nmpc.py:192-255
+ * (variant 1: plant noise*dt, zero control on a failed solve) for B independent vehicles tracking one trajectory.
+ * Per control step s the window starts at k_seq[s] (the float-accumulated floor(t/dt) sequence, built on the host);
+ * every solve is a cold start at the window (mpc_control.py:58-65).  disturb = HOST array {friction_coeff,
+ * slippage_coeff, lateral_slip_gain, slip_angle_max, process_noise_std} (DISTURBANCE_PARAMS, simulation.py:26-32) or
+ * NULL for the nominal plant; noise is counter-based on (seed, step, ids[i]) so results do not depend on sharding.
+ * metrics_out [B][8] = {final distance error, |heading error|, |hitch error| (simulation.py:574-580), max|psi|,
+ * jackknife flag (|psi| > pi/3 + 1e-6 at any step), failed solves, mean iterations, RMS position tracking error};
+ * final_state_out [B][6] optional.  Device pointers only. */
+int ttmpc_episode_batch(ttmpc_handle* h, int64_t B, const double* x0, const int64_t* ids,
+                        const double* traj_states, const double* traj_inputs, int32_t T,
+                        const int32_t* k_seq, int32_t steps, const double* disturb, int32_t variant,
+                        uint64_t seed, double* metrics_out, double* final_state_out, void* cuda_stream);
 
 /* Number of kernel launches issued through this handle so far (bench accounting). */
 int64_t ttmpc_launch_count(const ttmpc_handle* h);

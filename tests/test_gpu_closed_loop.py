@@ -75,3 +75,35 @@ def test_batched_closed_loop_vs_single_episodes(traj):
             assert bool(out["jackknife"][b]) == bool(np.abs(hist[:, b, 3]).max() > cl.JACKKNIFE_LIMIT)
             assert int(out["failures"][b]) == host_fail
     assert out["steps"] == len(ks)
+
+
+def test_device_episode_kernel_vs_host_driven_loop(traj):
+    """ttmpc_episode_batch (whole closed loop inside one persistent kernel, in-kernel counter-based noise) against the
+    host-driven batched loop (one solve + plant launch per step, torch noise): same metrics for every scenario."""
+    import torch
+    from car_trailer_mpc_b200 import BatchSolver
+    S, U = traj
+    cfg = tracking_preset(40); cfg.max_iter = 100
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(9)
+    B = 200   # more scenarios than one warp, ragged
+    x0 = S[0][None] + rng.normal(0, 0.03, size=(B, 6)) * np.array([1, 1, 0.2, 0.2, 0.1, 1])
+    x0_d = torch.from_numpy(x0).to(dev)
+    ids = torch.arange(1000, 1000 + B, device=dev, dtype=torch.int64)
+    solver = BatchSolver(cfg, 0)
+    T_sim = 4.0
+    ks = pb.time_indices(T_sim, 0.05)
+    for dist, variant in ((None, "tracking"), (cl.DEFAULT_DISTURBANCE, "tracking"), (cl.DEFAULT_DISTURBANCE, "nmpc")):
+        host = cl.simulate_batch(solver, S, U, x0_d, T_sim, 0.05, dist, seed=21, scenario_ids=ids, variant=variant)
+        devr = solver.episodes(x0_d, S, U, ks, dist, variant=variant, seed=21, scenario_ids=ids)
+        torch.cuda.synchronize()
+        m = devr["metrics"].cpu().numpy()
+        assert np.abs(devr["final_state"].cpu().numpy() - host["final_state"].cpu().numpy()).max() < 1e-6
+        assert np.abs(m[:, 0] - host["distance_error"].cpu().numpy()).max() < 1e-6
+        assert np.abs(m[:, 1] - host["heading_error"].abs().cpu().numpy()).max() < 1e-6
+        assert np.abs(m[:, 2] - host["hitch_error"].abs().cpu().numpy()).max() < 1e-6
+        assert np.abs(m[:, 3] - host["max_abs_psi"].cpu().numpy()).max() < 1e-6
+        assert np.array_equal(m[:, 4] > 0.5, host["jackknife"].cpu().numpy())
+        assert np.array_equal(m[:, 5].astype(int), host["failures"].cpu().numpy())
+        assert np.abs(m[:, 6] - host["mean_iters"].cpu().numpy()).max() < 0.05
+        assert np.abs(m[:, 7] - host["rms_tracking_error"].cpu().numpy()).max() < 1e-6

@@ -20,6 +20,8 @@ ap.add_argument("--nominal", action="store_true", help="disturbances off")
 ap.add_argument("--sigma0", type=float, default=0.02, help="std of the initial-state perturbation around S[0]")
 ap.add_argument("--seed", type=int, default=2025)
 ap.add_argument("--out", default="")
+ap.add_argument("--device-loop", action="store_true", help="run whole episodes inside one persistent kernel (ttmpc_episode_batch)")
+ap.add_argument("--max-iter", type=int, default=100)
 args = ap.parse_args()
 
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
@@ -29,7 +31,7 @@ if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
 
-cfg = tracking_preset(args.horizon); cfg.max_iter = 100
+cfg = tracking_preset(args.horizon); cfg.max_iter = args.max_iter
 S, U = pb.load_reference_trajectory(dt=cfg.dt)
 lo, hi = sharding.shard_range(args.scenarios, rank, world)
 ids = torch.arange(lo, hi, device=dev, dtype=torch.int64)
@@ -39,13 +41,23 @@ x0[:, 2:] = torch.minimum(torch.maximum(x0[:, 2:], lb[2:] + 1e-3), ub[2:] - 1e-3
 solver = BatchSolver(cfg, local)
 if world > 1: dist.barrier()
 torch.cuda.synchronize(); t0 = time.time()
-out = cl.simulate_batch(solver, S, U, x0.contiguous(), args.t_sim, cfg.dt, None if args.nominal else cl.DEFAULT_DISTURBANCE,
-                        seed=args.seed, scenario_ids=ids)
-torch.cuda.synchronize()
-if world > 1: dist.barrier()
-wall = time.time() - t0
-rows = torch.stack([out["distance_error"], out["heading_error"].abs(), out["hitch_error"].abs(), out["max_abs_psi"],
-                    out["jackknife"].double(), out["failures"].double(), out["mean_iters"], out["rms_tracking_error"]], 1)
+dist_params = None if args.nominal else cl.DEFAULT_DISTURBANCE
+if args.device_loop:
+    ks = pb.time_indices(args.t_sim, cfg.dt)
+    r = solver.episodes(x0.contiguous(), S, U, ks, dist_params, variant="tracking", seed=args.seed, scenario_ids=ids)
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    wall = time.time() - t0
+    rows = r["metrics"]
+    out = {"steps": len(ks), "jackknife": rows[:, 4] > 0.5, "failures": rows[:, 5], "max_abs_psi": rows[:, 3],
+           "max_iters": rows[:, 6]}
+else:
+    out = cl.simulate_batch(solver, S, U, x0.contiguous(), args.t_sim, cfg.dt, dist_params, seed=args.seed, scenario_ids=ids)
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    wall = time.time() - t0
+    rows = torch.stack([out["distance_error"], out["heading_error"].abs(), out["hitch_error"].abs(), out["max_abs_psi"],
+                        out["jackknife"].double(), out["failures"].double(), out["mean_iters"], out["rms_tracking_error"]], 1)
 allrows = sharding.gather_rows(rows, args.scenarios)          # NCCL all-gather of the per-scenario metric rows
 red = sharding.reduce_metrics({"jackknife": float(out["jackknife"].sum()), "failures": float(out["failures"].sum()),
                                "psi_max": float(out["max_abs_psi"].max()), "iters_max": float(out["max_iters"].max())})
@@ -55,7 +67,7 @@ if rank == 0:
     q = lambda c: [float(np.percentile(a[:, c], p)) for p in (50, 99, 100)]
     goal = S[-1]
     P = cl.lqr_riccati(cfg, cfg.Qm(), cfg.Rm(), goal, np.zeros(2)) if False else None
-    summary = {"scenarios": args.scenarios, "gpus": world, "steps": steps, "horizon": args.horizon, "disturbances": not args.nominal,
+    summary = {"scenarios": args.scenarios, "gpus": world, "steps": steps, "horizon": args.horizon, "disturbances": not args.nominal, "device_loop": bool(args.device_loop),
                "solves": args.scenarios * steps, "wall_s": wall, "solves_per_s": args.scenarios * steps / wall,
                "jackknife_rate": red["jackknife"] / args.scenarios, "solver_failures": red["failures"], "max_abs_psi": red["psi_max"],
                "max_iters": red["iters_max"], "distance_error_p50_p99_max": q(0), "heading_error_p50_p99_max": q(1),
