@@ -92,3 +92,34 @@ def test_lqr_score_matches_definition(traj):
     h = 1e-6
     Afd = np.stack([(f(xg + h * e, ug) - f(xg - h * e, ug)) / (2 * h) for e in np.eye(6)], 1)
     assert np.abs(A - Afd).max() < 1e-8
+
+
+class OracleNMPC(OracleController):
+    """TruckTrailerNMPC semantics on the oracle: shifted warm start (reference slicing by default), (None, None) on
+    failure without touching the stored solution (mpc_control_nmpc.py:90-113)."""
+
+    def __init__(self, cfg, reference_bug=True):
+        super().__init__(cfg, none_on_failure=True)
+        self._last, self.bug = None, reference_bug
+
+    def solve(self, x, ref_s, ref_u):
+        zw = None if self._last is None else pb.shift_warm_start(self._last, self.cfg.horizon, self.bug)
+        r = oracle.solve(self.cfg, np.asarray(x), np.ascontiguousarray(ref_s.T), np.ascontiguousarray(ref_u.T), z_warm=zw)
+        self.last_status, self.last_iterations = int(r["status"]), int(r["iters"])
+        if self.last_status > 1:
+            return None, None
+        self._last = r["z"]
+        X, U = pb.unpack_z(r["z"], self.cfg.horizon)
+        return X.T.copy(), U.T.copy()
+
+
+def test_nmpc_closed_loop_runs_clean(traj):
+    """simulation_nmpc.py configuration (N=30, T_sim=25 s, Q=diag(1,1,2,3,1,1), R=diag(5,8), tol 1e-3, warm start)."""
+    S, U = traj
+    N = 30
+    cfg = nmpc_preset(N)
+    for bug in (True, False):
+        ep = cl.simulate_single(OracleNMPC(cfg, bug), S, U, S[0], 25.0, 0.05, N, dict(PARAMS, horizon=N), variant="nmpc")
+        m = ep.metrics(S[-1])
+        assert m["steps"] == 500 and m["failures"] == 0 and not m["jackknife"] and not ep.aborted
+        assert m["distance_error"] < 0.2 and m["max_abs_psi"] < 0.75

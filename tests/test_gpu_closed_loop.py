@@ -107,3 +107,26 @@ def test_device_episode_kernel_vs_host_driven_loop(traj):
         assert np.array_equal(m[:, 5].astype(int), host["failures"].cpu().numpy())
         assert np.abs(m[:, 6] - host["mean_iters"].cpu().numpy()).max() < 0.05
         assert np.abs(m[:, 7] - host["rms_tracking_error"].cpu().numpy()).max() < 1e-6
+
+
+def test_nmpc_shim_closed_loop_vs_oracle(traj):
+    """simulation_nmpc.py run (N=30, 500 steps, warm start with the reference's slicing) through the TruckTrailerNMPC
+    shim vs the oracle under the same driver: same outcome.  At tol 1e-3 both stop at the same iterate because they run
+    the same algorithm; a flipped termination would show up as a 1e-3-level control difference."""
+    from test_closed_loop_cpu import OracleNMPC
+    from car_trailer_mpc_b200 import TruckTrailerModel, TruckTrailerNMPC, nmpc_preset
+    S, U = traj
+    N = 30
+    params = dict(PARAMS, horizon=N)
+    Qn, Rn = np.diag([1.0, 1.0, 2.0, 3.0, 1.0, 1.0]), np.diag([5.0, 8.0])
+    sbn = {"lb": [-np.inf, -np.inf, -np.pi, -np.pi / 3, -np.pi / 4, -8.0], "ub": [np.inf, np.inf, np.pi, np.pi / 3, np.pi / 4, 8.0]}
+    ibn = {"lb": [-4, -np.pi / 2], "ub": [4, np.pi / 2]}
+    for dist in (None, cl.DEFAULT_DISTURBANCE):
+        ctl = TruckTrailerNMPC(TruckTrailerModel(params), params, Qn, Rn, sbn, ibn, shift_reference_bug=True)
+        gpu = cl.simulate_single(ctl, S, U, S[0], 25.0, 0.05, N, params, dist, np.random.RandomState(5), variant="nmpc")
+        ref = cl.simulate_single(OracleNMPC(nmpc_preset(N), True), S, U, S[0], 25.0, 0.05, N, params, dist,
+                                 np.random.RandomState(5), variant="nmpc")
+        mg, mr = gpu.metrics(S[-1]), ref.metrics(S[-1])
+        assert mg["jackknife"] == mr["jackknife"] and mg["failures"] == mr["failures"] and mg["steps"] == mr["steps"] == 500
+        assert np.abs(gpu.controls - ref.controls).max() < 1e-4
+        assert np.abs(gpu.states - ref.states).max() < 1e-4
