@@ -903,6 +903,8 @@ struct Ipm {
   double f_theta[kFilterMax], f_phi[kFilterMax];
   int f_n, acc_count, ls_fail, iter;
   bool do_update, x0_infeasible;
+  // hand-over from the backward half of an iteration to its forward / line-search half
+  double cur_J, cur_sumlog, cur_theta, cur_cinf, cur_rd, cur_cmax, cur_lam1, cur_delta;
 };
 
 TT_HD bool tt_finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
@@ -921,9 +923,11 @@ TT_HD void ipm_begin(const Params& p, Ipm& s, bool x0_infeasible) {
   s.x0_infeasible = x0_infeasible;
 }
 
-// One interior-point iteration.  Returns true when the lane is finished (res filled in).
+// One interior-point iteration = ipm_backward (apply previous step, statistics, termination tests, barrier update,
+// factorisation) + ipm_step (search direction, line search).  Both return true when the lane is finished (res filled
+// in).  They are separate so that the CUDA kernel can align the two halves across the warps of a CTA.
 template <bool G, bool DQ>
-TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, Ipm& s, Result& res) {
+TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, Ipm& s, Result& res) {
   Stats st, st2;
   bool ok = false;
   int status = -1;
@@ -990,19 +994,32 @@ TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, Ipm& s, R
     res.status = (s.x0_infeasible && status >= ST_MAX_ITER) ? (int)ST_INFEASIBLE_X0 : status;
     return true;
   }
+  s.cur_J = st.J;
+  s.cur_sumlog = st.sumlog;
+  s.cur_theta = st.theta;
+  s.cur_cinf = st.cinf;
+  s.cur_rd = st.rd_inf;
+  s.cur_cmax = st.cmax;
+  s.cur_lam1 = st.lam1;
+  s.cur_delta = delta;
+  return false;
+}
 
+template <bool G, bool DQ>
+TT_HD bool ipm_step(const Params& p, double* s0, Ipm& s, Result& res) {
+  const double mu = s.mu, delta = s.cur_delta;
   StepInfo si;
   forward_sweep<G, DQ>(p, s0, mu, s.tau, si);
 
   // filter line search (Waechter & Biegler 2006, Algorithm A)
-  const double theta = st.theta;
-  const double phi = st.J - mu * st.sumlog;
+  const double theta = s.cur_theta;
+  const double phi = s.cur_J - mu * s.cur_sumlog;
   double a = si.a_pr;
   // Round-off regime (analogue of Ipopt's tiny-step rule in function values): predicted change of phi below its
   // resolution (or below the c'lambda evaluation noise theta*||lambda||_1) and constraint violation far below tol
   // -> theta/phi comparisons are noise; take the full step.
   const bool roundoff_step = (theta <= 1e-2 * p.tol) &&
-                             (fabs(si.gphi_d) <= fmax(100.0 * kEps * fmax(1.0, fabs(phi)), theta * st.lam1));
+                             (fabs(si.gphi_d) <= fmax(100.0 * kEps * fmax(1.0, fabs(phi)), theta * s.cur_lam1));
   bool accepted = roundoff_step;
   for (int bt = 0; !roundoff_step && bt <= kMaxBacktrack; bt++, a *= kAlphaRed) {
     Trial tr;
@@ -1046,10 +1063,10 @@ TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, Ipm& s, R
     // Ipopt would enter feasibility restoration; policy: shortest trial step, cleared filter, give up after 3
     if (++s.ls_fail >= 3) {
       // the iterate is unchanged since the last backward sweep: report it
-      res.obj = st.J;
-      res.dual_inf = st.rd_inf;
-      res.constr_viol = st.cinf;
-      res.compl_inf = st.cmax;
+      res.obj = s.cur_J;
+      res.dual_inf = s.cur_rd;
+      res.constr_viol = s.cur_cinf;
+      res.compl_inf = s.cur_cmax;
       res.iters = s.iter;
       res.status = s.x0_infeasible ? (int)ST_INFEASIBLE_X0 : (int)ST_LINESEARCH;
       return true;
@@ -1066,6 +1083,12 @@ TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, Ipm& s, R
   s.do_update = true;
   s.iter++;
   return false;
+}
+
+template <bool G, bool DQ>
+TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, Ipm& s, Result& res) {
+  if (ipm_backward<G, DQ>(p, s0, cy, s, res)) return true;
+  return ipm_step<G, DQ>(p, s0, s, res);
 }
 
 // Ipopt's initial push into the interior of the relaxed box (bound_push / bound_frac)
