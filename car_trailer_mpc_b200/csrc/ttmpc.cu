@@ -119,9 +119,8 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
   Ipm st;
   Result res;
   for (;;) {
-    // ---- refill: lanes without work take the next problems from the queue (one atomic per warp) ...
+    // ---- refill: lanes without work take the next problems from the queue (one atomic per warp)
     const unsigned need = __ballot_sync(kFull, !active);
-    unsigned fresh = 0;
     if (need && !exhausted) {
       const int leader = __ffs(need) - 1;
       unsigned long long base = 0;
@@ -132,32 +131,10 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
         if (cand < B) {
           prob = order ? (long long)order[cand] : cand;  // queue position -> problem (hardest first)
           active = true;
+          ipm_begin(p, st);  // the problem's data is picked up by its first backward sweep
         }
       }
-      fresh = need & __ballot_sync(kFull, active);
       if ((long long)base + __popc(need) >= B) exhausted = true;
-    }
-    // ... and the whole warp loads each new problem into its lane's slot: coalesced reads of the problem record
-    // (the reference's p / z layouts), scattered 8-byte writes down the slot column.
-    for (unsigned m = fresh; m; m &= m - 1) {
-      const int l = __ffs(m) - 1;
-      const long long pb = __shfl_sync(kFull, prob, l);
-      bool bad = false;
-      for (int e0 = (int)lane; e0 < nz; e0 += 32 * kCopyUnroll) {  // kCopyUnroll loads in flight per lane
-        PackVal v[kCopyUnroll];
-#pragma unroll
-        for (int u = 0; u < kCopyUnroll; u++) {
-          const int e = e0 + 32 * u;
-          if (e < nz) v[u] = pack_load(p, in, pb, e >> 3, e & 7);
-        }
-#pragma unroll
-        for (int u = 0; u < kCopyUnroll; u++) {
-          const int e = e0 + 32 * u;
-          if (e < nz) bad |= pack_store(p, s_warp + l, e >> 3, e & 7, v[u]);
-        }
-      }
-      bad = __any_sync(kFull, bad);
-      if ((int)lane == l) ipm_begin(p, st, bad);
     }
     __syncwarp();
     // Rounds (and their two halves) are aligned across the CTA: all warps of an SM then run the same sweep at the
@@ -166,7 +143,8 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
 
     // ---- one interior-point iteration for every lane that has a problem
     bool done = false;
-    if (active) done = ipm_backward<G, DQ>(p, s0, cy, st, res);
+    const bool warp_fresh = __any_sync(kFull, active && st.fresh);
+    if (active) done = ipm_backward<G, DQ>(p, s0, cy, in, prob, warp_fresh, st, res);
     __syncthreads();
     if (active && !done) done = ipm_step<G, DQ>(p, s0, st, res);
     __syncwarp();
@@ -386,34 +364,15 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
         ea.xmeas[scen * NX + j] = x[j] + (meas_noise ? ea.noise_std * counter_normal(ea.seed, 2ull * step, sid, j) : 0.0);
       ea.kcur[scen] = ea.k_seq[step];
     }
+    if (need_pack) ipm_begin(p, st);
     __syncwarp();
-    const unsigned fresh = __ballot_sync(kFull, need_pack);
-    for (unsigned m = fresh; m; m &= m - 1) {
-      const int l = __ffs(m) - 1;
-      const long long pb = __shfl_sync(kFull, scen, l);
-      bool bad = false;
-      for (int e0 = (int)lane; e0 < nz; e0 += 32 * kCopyUnroll) {
-        PackVal v[kCopyUnroll];
-#pragma unroll
-        for (int u = 0; u < kCopyUnroll; u++) {
-          const int e = e0 + 32 * u;
-          if (e < nz) v[u] = pack_load(p, in, pb, e >> 3, e & 7);
-        }
-#pragma unroll
-        for (int u = 0; u < kCopyUnroll; u++) {
-          const int e = e0 + 32 * u;
-          if (e < nz) bad |= pack_store(p, s_warp + l, e >> 3, e & 7, v[u]);
-        }
-      }
-      bad = __any_sync(kFull, bad);
-      if ((int)lane == l) ipm_begin(p, st, bad);
-    }
     need_pack = false;
     __syncwarp();
     if (!__syncthreads_or(active ? 1 : 0)) break;
 
     bool done = false;
-    if (active) done = ipm_backward<G, DQ>(p, s0, cy, st, res);
+    const bool warp_fresh = __any_sync(kFull, active && st.fresh);
+    if (active) done = ipm_backward<G, DQ>(p, s0, cy, in, scen, warp_fresh, st, res);
     __syncthreads();
     if (active && !done) done = ipm_step<G, DQ>(p, s0, st, res);
     __syncwarp();

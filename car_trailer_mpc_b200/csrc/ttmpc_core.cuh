@@ -299,6 +299,44 @@ TT_HD void Q2_mul(const Params& p, const double* d, double* y) {
   }
 }
 
+// Ipopt's initial push into the interior of the relaxed box (bound_push / bound_frac)
+TT_HD double push_inside(double w, double l, double u, bool hl, bool hu) {
+  if (hl && hu) {
+    const double pl = fmin(kBoundPush * fmax(1.0, fabs(l)), kBoundFrac * (u - l));
+    const double pu = fmin(kBoundPush * fmax(1.0, fabs(u)), kBoundFrac * (u - l));
+    w = fmin(fmax(w, l + pl), u - pu);
+  } else if (hl) {
+    w = fmax(w, l + kBoundPush * fmax(1.0, fabs(l)));
+  } else if (hu) {
+    w = fmin(w, u - kBoundPush * fmax(1.0, fabs(u)));
+  }
+  return w;
+}
+
+// The caller's problem arrays in the reference's own layouts (`p` and `z` of mpc_control.py:48-50,
+// trajectory_planning.py:38-60).  A lane reads its problem record from here during the problem's first backward sweep;
+// in shared-trajectory mode the window rules of simulation.py:485-499 are applied to one common trajectory instead.
+struct ProblemIn {
+  const double* x_init;       // [B][6]
+  const double* ref_states;   // [B][N+1][6] or null (shared-trajectory mode)
+  const double* ref_inputs;   // [B][N][2]
+  const double* z_warm;       // [B][8N+6] or null: cold start at the reference window (mpc_control.py:58-65)
+  const int32_t* k_index;     // [B]   (shared mode)
+  const double* traj_states;  // [T+1][6]
+  const double* traj_inputs;  // [T][2]
+  int T;
+};
+// reference value (stage k, component j) of problem b: the caller's window, or the window rules of
+// simulation.py:485-499 applied to the shared trajectory
+TT_HD double ref_value(const Params& p, const ProblemIn& in, long long b, int k, int j) {
+  const int N = p.N;
+  if (in.ref_states != nullptr)
+    return (j < NX) ? in.ref_states[(b * (N + 1) + k) * NX + j] : in.ref_inputs[(b * N + k) * NU + (j - NX)];
+  const int T = in.T, kk = in.k_index[b];
+  if (j < NX) return in.traj_states[(long long)((kk < T) ? ((kk + k < T) ? kk + k : T) : T) * NX + j];
+  return (kk >= T) ? 0.0 : in.traj_inputs[(long long)((kk + k < T) ? kk + k : T - 1) * NU + (j - NX)];
+}
+
 // ------------------------------------------------------------------------------------------------
 // statistics gathered by the backward sweep at the current iterate
 // ------------------------------------------------------------------------------------------------
@@ -326,9 +364,18 @@ struct Carry {
 // do_update: apply the step stored in DW with primal step alpha / dual step alpha_du; mu_step, delta_step are the
 // barrier parameter and Hessian regularisation the step was computed with.  delta: regularisation for the new
 // factorisation.  Returns false when some 2x2 pivot block is not positive definite (wrong inertia).
+//
+// fresh: this is the first sweep of a problem that has just been assigned to the lane.  Its data is then taken straight
+// from the caller's arrays (`in`, problem b: reference window, cold/warm starting guess pushed into the interior like
+// Ipopt does, x_init) instead of the slot, and written to the slot by the same store instructions that write the
+// other lanes' updated iterates -- there is no separate "load the problem" phase, and rows are written by all lanes
+// of the warp at once (a lane-by-lane load would write 8 of every 32-byte sector and cost more than the sweep).
+// warp_fresh: some lane of the warp is fresh (then every lane re-stores its reference row, again to keep full rows).
+// x0_bad (out, fresh only): x_init violates a state bound.
 template <bool G, bool DQ>
-TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, bool do_update, double alpha, double alpha_du,
-                          double mu_step, double delta_step, double delta, Stats& st) {
+TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const ProblemIn& in, long long b, bool fresh,
+                          bool warp_fresh, bool& x0_bad, bool do_update, double alpha, double alpha_du, double mu_step,
+                          double delta_step, double delta, Stats& st) {
   const int N = p.N;
   const double dt = p.dt;
   bool ok = true;
@@ -344,14 +391,37 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, bool do_
     for (int j = 0; j < NW; j++) {
       const bool on = (j < NX) || has_u;
       const bool var = (j < NX) ? has_x : has_u;
-      w[j] = on ? ldr(ps, rW + j) : 0.0;
-      ref[j] = on ? ldr(ps, rREF + j) : 0.0;
+      w[j] = (on && !fresh) ? ldr(ps, rW + j) : 0.0;
+      ref[j] = (on && !fresh) ? ldr(ps, rREF + j) : 0.0;
       dw[j] = (do_update && var) ? ldr(ps, rDW + j) : 0.0;
-      zl[j] = (var && has_lo<G>(p, j)) ? ldr(ps, rZL + j) : 0.0;
-      zu[j] = (var && has_up<G>(p, j)) ? ldr(ps, rZU + j) : 0.0;
+      zl[j] = (var && !fresh && has_lo<G>(p, j)) ? ldr(ps, rZL + j) : 0.0;
+      zu[j] = (var && !fresh && has_up<G>(p, j)) ? ldr(ps, rZU + j) : 0.0;
     }
     TT_UNROLL
-    for (int j = 0; j < NX; j++) lam[j] = has_x ? ldr(ps, rLAM + j) : 0.0;
+    for (int j = 0; j < NX; j++) lam[j] = (has_x && !fresh) ? ldr(ps, rLAM + j) : 0.0;
+    if (fresh) {
+      // entering problem: reference window and starting point from the caller's arrays (mpc_control.py:58-65 cold
+      // start or the caller's warm start), pushed into the interior of the relaxed box; z_L = z_U = 1, lambda = 0
+      const long long nz = 8LL * N + 6;
+      TT_UNROLL
+      for (int j = 0; j < NW; j++) {
+        const bool on = (j < NX) || has_u;
+        const bool var = (j < NX) ? has_x : has_u;
+        if (!on) continue;
+        const bool hl = ((p.bl >> j) & 1u) != 0, hu = ((p.bu >> j) & 1u) != 0;
+        ref[j] = ref_value(p, in, b, k, j);
+        if (!var) {  // x_0 is data
+          w[j] = in.x_init[b * NX + j];
+          if ((hl && w[j] < p.lo[j]) || (hu && w[j] > p.up[j])) x0_bad = true;
+        } else {
+          const double g = in.z_warm ? in.z_warm[b * nz + (long long)k * NW + j] : ref[j];
+          w[j] = push_inside(g, p.lo[j], p.up[j], hl, hu);
+          zl[j] = has_lo<G>(p, j) ? 1.0 : 0.0;
+          zu[j] = has_up<G>(p, j) ? 1.0 : 0.0;
+        }
+      }
+    }
+    const bool wb = do_update || fresh;  // this lane (re)writes its iterate in this sweep
     if (has_x) {  // request stage k-1 now
       const double* pn = ps - kStageStride;
       prefetch_rows(pn, rW, do_update ? 2 * NW : NW);  // W (and DW, adjacent rows)
@@ -419,17 +489,31 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, bool do_
         for (int j = 0; j < NX; j++) {
           cy.st(cLPLUS + j, lp[j]);
           lam[j] += alpha * (lp[j] - lam[j]);
-          str(ps, rLAM + j, lam[j]);
         }
       }
       TT_UNROLL
       for (int j = 0; j < NW; j++) {
         const bool var = (j < NX) ? has_x : has_u;
-        if (var) {
-          w[j] += alpha * dw[j];
-          str(ps, rW + j, w[j]);
-        }
+        if (var) w[j] += alpha * dw[j];
       }
+    }
+    // merged write-back of the primal iterate and the equality multipliers: stepped lanes and fresh lanes together
+    if (wb) {
+      TT_UNROLL
+      for (int j = 0; j < NW; j++) {
+        const bool on = (j < NX) || has_u;
+        const bool var = (j < NX) ? has_x : has_u;
+        if (var || (fresh && on)) str(ps, rW + j, w[j]);
+      }
+      if (has_x) {
+        TT_UNROLL
+        for (int j = 0; j < NX; j++) str(ps, rLAM + j, lam[j]);
+      }
+    }
+    if (warp_fresh) {  // reference rows: fresh lanes bring new ones, the others re-store theirs (full-row writes)
+      TT_UNROLL
+      for (int j = 0; j < NW; j++)
+        if ((j < NX) || has_u) str(ps, rREF + j, ref[j]);
     }
 
     TT_FENCE();
@@ -459,10 +543,8 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, bool do_
         double sg = delta, gg = 0.0;
         if (var && has_lo<G>(p, j)) {
           const double sl = w[j] - p.lo[j], rl = tt_rcp(sl);
-          if (do_update) {  // kappa_sigma safeguard, Waechter & Biegler eq. (16)
-            zl[j] = tt_max(tt_min(zl[j], kmu_hi * rl), kmu_lo * rl);
-            str(ps, rZL + j, zl[j]);
-          }
+          if (do_update) zl[j] = tt_max(tt_min(zl[j], kmu_hi * rl), kmu_lo * rl);  // kappa_sigma safeguard, W&B eq. (16)
+          if (wb) str(ps, rZL + j, zl[j]);
           sg += zl[j] * rl;
           gg -= rl;
           prod *= sl;
@@ -473,10 +555,8 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, bool do_
         }
         if (var && has_up<G>(p, j)) {
           const double su = p.up[j] - w[j], ru = tt_rcp(su);
-          if (do_update) {
-            zu[j] = tt_max(tt_min(zu[j], kmu_hi * ru), kmu_lo * ru);
-            str(ps, rZU + j, zu[j]);
-          }
+          if (do_update) zu[j] = tt_max(tt_min(zu[j], kmu_hi * ru), kmu_lo * ru);
+          if (wb) str(ps, rZU + j, zu[j]);
           sg += zu[j] * ru;
           gg += ru;
           prod *= su;
@@ -903,13 +983,14 @@ struct Ipm {
   double f_theta[kFilterMax], f_phi[kFilterMax];
   int f_n, acc_count, ls_fail, iter;
   bool do_update, x0_infeasible;
+  bool fresh;  // the problem has just been assigned to the lane: its first backward sweep reads the caller's arrays
   // hand-over from the backward half of an iteration to its forward / line-search half
   double cur_J, cur_sumlog, cur_theta, cur_cinf, cur_rd, cur_cmax, cur_lam1, cur_delta;
 };
 
 TT_HD bool tt_finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
 
-TT_HD void ipm_begin(const Params& p, Ipm& s, bool x0_infeasible) {
+TT_HD void ipm_begin(const Params& p, Ipm& s) {
   s.mu = p.mu_init;
   s.tau = fmax(kTauMin, 1.0 - s.mu);
   s.theta_max = s.theta_min = 0.0;
@@ -920,14 +1001,16 @@ TT_HD void ipm_begin(const Params& p, Ipm& s, bool x0_infeasible) {
   s.f_n = 0;
   s.acc_count = s.ls_fail = s.iter = 0;
   s.do_update = false;
-  s.x0_infeasible = x0_infeasible;
+  s.x0_infeasible = false;
+  s.fresh = true;
 }
 
 // One interior-point iteration = ipm_backward (apply previous step, statistics, termination tests, barrier update,
 // factorisation) + ipm_step (search direction, line search).  Both return true when the lane is finished (res filled
 // in).  They are separate so that the CUDA kernel can align the two halves across the warps of a CTA.
 template <bool G, bool DQ>
-TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, Ipm& s, Result& res) {
+TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const ProblemIn& in, long long b, bool warp_fresh,
+                        Ipm& s, Result& res) {
   Stats st, st2;
   bool ok = false;
   int status = -1;
@@ -937,9 +1020,12 @@ TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, Ipm& s, Re
   // the sweep is the bulk of the kernel's code and must not be instantiated twice.
   for (int attempt = 0; attempt <= 40; attempt++) {
     const bool first = (attempt == 0);
-    ok = backward_sweep<G, DQ>(p, s0, cy, first && s.do_update, s.alpha, s.alpha_du, first ? s.mu_step : mu, s.delta_step, delta,
-                           first ? st : st2);
+    bool x0_bad = false;
+    ok = backward_sweep<G, DQ>(p, s0, cy, in, b, first && s.fresh, first && warp_fresh, x0_bad, first && s.do_update, s.alpha,
+                               s.alpha_du, first ? s.mu_step : mu, s.delta_step, delta, first ? st : st2);
     if (first) {
+      if (s.fresh) s.x0_infeasible = x0_bad;
+      s.fresh = false;
       const double cmin = p.n_b ? st.cmin : 0.0;
       const double s_d = fmax(kSMax, (st.lam1 + st.z1) / (double)(p.m_eq + p.n_b)) / kSMax;
       const double s_c = p.n_b ? fmax(kSMax, st.z1 / (double)p.n_b) / kSMax : 1.0;
@@ -1086,96 +1172,9 @@ TT_HD bool ipm_step(const Params& p, double* s0, Ipm& s, Result& res) {
 }
 
 template <bool G, bool DQ>
-TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, Ipm& s, Result& res) {
-  if (ipm_backward<G, DQ>(p, s0, cy, s, res)) return true;
+TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, const ProblemIn& in, long long b, Ipm& s, Result& res) {
+  if (ipm_backward<G, DQ>(p, s0, cy, in, b, s.fresh, s, res)) return true;
   return ipm_step<G, DQ>(p, s0, s, res);
-}
-
-// Ipopt's initial push into the interior of the relaxed box (bound_push / bound_frac)
-TT_HD double push_inside(double w, double l, double u, bool hl, bool hu) {
-  if (hl && hu) {
-    const double pl = fmin(kBoundPush * fmax(1.0, fabs(l)), kBoundFrac * (u - l));
-    const double pu = fmin(kBoundPush * fmax(1.0, fabs(u)), kBoundFrac * (u - l));
-    w = fmin(fmax(w, l + pl), u - pu);
-  } else if (hl) {
-    w = fmax(w, l + kBoundPush * fmax(1.0, fabs(l)));
-  } else if (hu) {
-    w = fmin(w, u - kBoundPush * fmax(1.0, fabs(u)));
-  }
-  return w;
-}
-
-// Problem data of one lane -> its scratch slot.  Reads the reference's AoS layouts directly (each lane walks its
-// own contiguous problem record) or, in shared-trajectory mode, applies the window rules of simulation.py:485-499.
-struct ProblemIn {
-  const double* x_init;       // [B][6]
-  const double* ref_states;   // [B][N+1][6] or null (shared-trajectory mode)
-  const double* ref_inputs;   // [B][N][2]
-  const double* z_warm;       // [B][8N+6] or null: cold start at the reference window (mpc_control.py:58-65)
-  const int32_t* k_index;     // [B]   (shared mode)
-  const double* traj_states;  // [T+1][6]
-  const double* traj_inputs;  // [T][2]
-  int T;
-};
-
-// Loading one element (stage k, component j) of problem b is split into the global loads (reference value and
-// starting guess) and the stores into the slot, so that callers can put several loads in flight first.
-struct PackVal {
-  double r, g;
-  bool g_is_r;  // cold start: the guess IS the reference value (no copy: a copy would wait for the load)
-};
-// reference value (stage k, component j) of problem b: the caller's window, or the window rules of
-// simulation.py:485-499 applied to the shared trajectory
-TT_HD double ref_value(const Params& p, const ProblemIn& in, long long b, int k, int j) {
-  const int N = p.N;
-  if (in.ref_states != nullptr)
-    return (j < NX) ? in.ref_states[(b * (N + 1) + k) * NX + j] : in.ref_inputs[(b * N + k) * NU + (j - NX)];
-  const int T = in.T, kk = in.k_index[b];
-  if (j < NX) return in.traj_states[(long long)((kk < T) ? ((kk + k < T) ? kk + k : T) : T) * NX + j];
-  return (kk >= T) ? 0.0 : in.traj_inputs[(long long)((kk + k < T) ? kk + k : T - 1) * NU + (j - NX)];
-}
-TT_HD PackVal pack_load(const Params& p, const ProblemIn& in, long long b, int k, int j) {
-  const int N = p.N;
-  PackVal v;
-  v.r = ref_value(p, in, b, k, j);
-  v.g = 0.0;
-  v.g_is_r = false;
-  if (k == 0 && j < NX)
-    v.g = in.x_init[b * NX + j];  // x_0 is data
-  else if (in.z_warm)
-    v.g = in.z_warm[b * (8LL * N + 6) + (long long)k * NW + j];
-  else
-    v.g_is_r = true;
-  return v;
-}
-// returns true when x_init violates a state bound (the reference NLP is then infeasible)
-TT_HD bool pack_store(const Params& p, double* s0, int k, int j, const PackVal& v) {
-  double* ps = s0 + (size_t)k * kStageStride;
-  const bool hl = ((p.bl >> j) & 1u) != 0, hu = ((p.bu >> j) & 1u) != 0;
-  bool bad = false;
-  double w = v.g_is_r ? v.r : v.g;
-  if (k == 0 && j < NX) {
-    bad = (hl && w < p.lo[j]) || (hu && w > p.up[j]);
-  } else {
-    w = push_inside(w, p.lo[j], p.up[j], hl, hu);
-    if (hl) str(ps, rZL + j, 1.0);
-    if (hu) str(ps, rZU + j, 1.0);
-  }
-  str(ps, rW + j, w);
-  str(ps, rREF + j, v.r);
-  if (j < NX) str(ps, rLAM + j, 0.0);
-  return bad;
-}
-TT_HD bool pack_elem(const Params& p, double* s0, const ProblemIn& in, long long b, int k, int j) {
-  return pack_store(p, s0, k, j, pack_load(p, in, b, k, j));
-}
-
-// single-lane versions (host emulation; the CUDA kernel does the same element loop with 32 cooperating lanes)
-TT_HD bool pack_slot(const Params& p, double* s0, const ProblemIn& in, long long b) {
-  const int nz = 8 * p.N + 6;
-  bool bad = false;
-  for (int e = 0; e < nz; e++) bad |= pack_elem(p, s0, in, b, e >> 3, e & 7);
-  return bad;
 }
 
 // slot -> z_out in the reference's decision-vector layout (trajectory_planning.py:38-60): z[8k+j] = w_k[j]

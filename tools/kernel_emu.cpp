@@ -1,6 +1,6 @@
 // kernel_emu.cpp -- TEST-ONLY host build of the device solver core (ttmpc_core.cuh).
 //
-// Compiles the exact per-lane functions the CUDA solve kernel runs (pack_slot, the backward/forward/trial sweeps,
+// Compiles the exact per-lane functions the CUDA solve kernel runs (the backward/forward/trial sweeps,
 // ipm_iteration, unpack_slot) with plain g++, over the same bank-interleaved scratch layout (with a small bank,
 // -DTTMPC_BANK=64), so that the kernel's logic can be compared with the oracle on a machine without a GPU
 // (tests/test_kernel_emulation.py).  It is NOT part of the product: libttmpc.so does not contain it and has
@@ -27,9 +27,8 @@ static void run(const Params& p, std::vector<double>& scratch, int64_t B, const 
       Result r;
       double carried[kCarry];
       const Carry cy{carried, 1};
-      const bool bad = pack_slot(p, s0, in, b);
-      ipm_begin(p, st, bad);
-      while (!ipm_iteration<G, DQ>(p, s0, cy, st, r)) {
+      ipm_begin(p, st);
+      while (!ipm_iteration<G, DQ>(p, s0, cy, in, b, st, r)) {
       }
       if (z_out) unpack_slot(p, s0, z_out + b * nz);
       if (u0_out) { u0_out[b * 2] = ldr(s0, rW + 6); u0_out[b * 2 + 1] = ldr(s0, rW + 7); }
