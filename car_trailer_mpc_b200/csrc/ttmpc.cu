@@ -320,8 +320,6 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
   const size_t slot = (size_t)blockIdx.x * kSolveThreads + threadIdx.x;
   double* s0 = slot_ptr(scratch, p.N, slot);
   const unsigned lane = threadIdx.x & 31u;
-  double* s_warp = s0 - lane;
-  const int nz = 8 * p.N + 6;
   const ProblemIn in{ea.xmeas, nullptr, nullptr, nullptr, ea.kcur, ea.traj_states, ea.traj_inputs, ea.T};
   long long scen = -1;
   unsigned long long sid = 0;
