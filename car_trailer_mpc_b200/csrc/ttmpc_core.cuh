@@ -381,6 +381,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
   bool ok = true;
   double J = 0.0, sumlog = 0.0, theta = 0.0, cinf = 0.0, rd_inf = 0.0, lam1 = 0.0, z1 = 0.0, cmax = 0.0, cmin = INFINITY;
   const double kmu_hi = kKappaSigma * mu_step, kmu_lo = mu_step * (1.0 / kKappaSigma);
+  const int kk_fresh = (fresh && in.ref_states == nullptr) ? in.k_index[b] : 0;  // shared-trajectory window start
 
   for (int k = N; k >= 0; k--) {
     double* ps = s0 + (size_t)k * kStageStride;
@@ -403,13 +404,25 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
       // entering problem: reference window and starting point from the caller's arrays (mpc_control.py:58-65 cold
       // start or the caller's warm start), pushed into the interior of the relaxed box; z_L = z_U = 1, lambda = 0
       const long long nz = 8LL * N + 6;
+      // stage pointers into the caller's window, or into the shared trajectory (window rules of simulation.py:485-499)
+      const double *rs, *ru;
+      bool zero_u = false;
+      if (in.ref_states != nullptr) {
+        rs = in.ref_states + (b * (N + 1) + k) * NX;
+        ru = in.ref_inputs + (b * N + k) * NU;
+      } else {
+        const int T = in.T;
+        rs = in.traj_states + (long long)((kk_fresh < T) ? ((kk_fresh + k < T) ? kk_fresh + k : T) : T) * NX;
+        ru = in.traj_inputs + (long long)((kk_fresh + k < T) ? kk_fresh + k : T - 1) * NU;
+        zero_u = (kk_fresh >= T);
+      }
       TT_UNROLL
       for (int j = 0; j < NW; j++) {
         const bool on = (j < NX) || has_u;
         const bool var = (j < NX) ? has_x : has_u;
         if (!on) continue;
         const bool hl = ((p.bl >> j) & 1u) != 0, hu = ((p.bu >> j) & 1u) != 0;
-        ref[j] = ref_value(p, in, b, k, j);
+        ref[j] = (j < NX) ? rs[j] : (zero_u ? 0.0 : ru[j - NX]);
         if (!var) {  // x_0 is data
           w[j] = in.x_init[b * NX + j];
           if ((hl && w[j] < p.lo[j]) || (hu && w[j] > p.up[j])) x0_bad = true;
