@@ -302,14 +302,27 @@ struct EpisodeArgs {
   unsigned long long seed;
   double* xmeas;              // [B][6] scratch: measured state handed to the solve
   int32_t* kcur;              // [B]    scratch: window index handed to the solve
+  double* rec;                // [B][kRec] scratch: scenario record between control steps
+  int32_t* steps_done;        // [B]    scratch: number of published control steps per scenario (zeroed by the host)
   double* metrics;            // [B][8]: dist err, |heading err|, |hitch err|, max|psi|, jackknife, failures, mean iters, rms track err
   double* final_state;        // [B][6] or null
 };
 
-// Same persistent-lane machinery as ttmpc_solve_kernel, but a lane keeps its scenario for all `steps` control steps:
-// when a solve terminates the lane applies u_0 to the plant (disturbance model included), updates the episode
-// metrics, forms the next measurement and re-enters the queue of lanes whose slot must be (re)loaded.  No host
-// round trip per step and no per-step barrier across scenarios: stragglers only delay their own lane.
+// Same persistent-lane machinery as ttmpc_solve_kernel, but the unit of work is ONE CONTROL STEP of one scenario:
+// tickets are issued step-major (ticket t = step t / B of scenario t % B), so all scenarios advance together and the
+// lanes stay balanced although scenarios differ in iterations per solve (a lane that kept "its" scenario for the whole
+// episode made the launch end with the slowest scenario: measured 4.6 M instead of 8.4 M solves/s).  The scenario
+// record (state + metric accumulators) lives in global memory; step s+1 of a scenario may only start when step s has
+// been published (`steps_done`), which a lane checks by polling once per round -- it never blocks its warp.  When a
+// solve terminates the lane applies u_0 to the plant (disturbance model included), updates the metrics and publishes.
+// No host round trip and no cross-scenario barrier per step.
+constexpr int kRec = 10;  // x[6], max|psi|, sum sq. tracking error, iterations, failed solves
+__device__ __forceinline__ int ld_volatile_i32(const int32_t* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 template <bool G, bool DQ>
 __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
     ttmpc_episode_kernel(const __grid_constant__ Params p, double* __restrict__ scratch, long long B, EpisodeArgs ea,
@@ -321,68 +334,77 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
   double* s0 = slot_ptr(scratch, p.N, slot);
   const unsigned lane = threadIdx.x & 31u;
   const ProblemIn in{ea.xmeas, nullptr, nullptr, nullptr, ea.kcur, ea.traj_states, ea.traj_inputs, ea.T};
+  const long long total = B * (long long)ea.steps;
   long long scen = -1;
   unsigned long long sid = 0;
-  bool active = false, exhausted = false, need_pack = false;
-  int step = 0, fails = 0;
-  long long iters_sum = 0;
-  double x[NX], max_psi = 0.0, sq_err = 0.0;
+  bool active = false, waiting = false, exhausted = false;
+  int step = 0;
+  double x[NX], max_psi = 0.0, sq_err = 0.0, iters_sum = 0.0, fails = 0.0;
   Ipm st;
   Result res;
   for (;;) {
-    const unsigned need = __ballot_sync(kFull, !active);
+    // ---- lanes without a ticket take the next (scenario, step) tickets
+    const unsigned need = __ballot_sync(kFull, !active && !waiting);
     if (need && !exhausted) {
       const int leader = __ffs(need) - 1;
       unsigned long long base = 0;
       if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(need));
       base = __shfl_sync(kFull, base, leader);
-      if (!active) {
-        const long long cand = (long long)base + __popc(need & ((1u << lane) - 1u));
-        if (cand < B) {
-          scen = cand;
+      if (!active && !waiting) {
+        const long long t = (long long)base + __popc(need & ((1u << lane) - 1u));
+        if (t < total) {
+          step = (int)(t / B);
+          scen = t - (long long)step * B;
           sid = ea.ids ? (unsigned long long)ea.ids[scen] : (unsigned long long)scen;
-          active = true;
-          step = 0;
-          fails = 0;
-          iters_sum = 0;
-          sq_err = 0.0;
-#pragma unroll
-          for (int j = 0; j < NX; j++) x[j] = ea.x0[scen * NX + j];
-          max_psi = fabs(x[3]);
-          need_pack = true;
+          waiting = true;
         }
       }
-      if ((long long)base + __popc(need) >= B) exhausted = true;
+      if ((long long)base + __popc(need) >= total) exhausted = true;
     }
-    // lanes about to solve publish their measurement and window index, then the warp loads the slots
-    if (need_pack) {
+    // ---- a waiting lane starts as soon as the previous step of its scenario has been published
+    if (waiting && ld_volatile_i32(ea.steps_done + scen) >= step) {
+      __threadfence();
+      if (step == 0) {
+#pragma unroll
+        for (int j = 0; j < NX; j++) x[j] = ea.x0[scen * NX + j];
+        max_psi = fabs(x[3]);
+        sq_err = iters_sum = fails = 0.0;
+      } else {
+        const double* r = ea.rec + scen * kRec;
+#pragma unroll
+        for (int j = 0; j < NX; j++) x[j] = __ldcg(r + j);  // written by another SM: bypass the (incoherent) L1
+        max_psi = __ldcg(r + 6);
+        sq_err = __ldcg(r + 7);
+        iters_sum = __ldcg(r + 8);
+        fails = __ldcg(r + 9);
+      }
       const bool meas_noise = (ea.variant == 0) && ea.dist.on && ea.noise_std > 0.0;
 #pragma unroll
       for (int j = 0; j < NX; j++)
         ea.xmeas[scen * NX + j] = x[j] + (meas_noise ? ea.noise_std * counter_normal(ea.seed, 2ull * step, sid, j) : 0.0);
       ea.kcur[scen] = ea.k_seq[step];
+      ipm_begin(p, st);
+      waiting = false;
+      active = true;
     }
-    if (need_pack) ipm_begin(p, st);
     __syncwarp();
-    need_pack = false;
-    __syncwarp();
-    if (!__syncthreads_or(active ? 1 : 0)) break;
+    if (!__syncthreads_or((active || waiting) ? 1 : 0)) break;
 
     bool done = false;
     const bool warp_fresh = __any_sync(kFull, active && st.fresh);
     if (active) done = ipm_backward<G, DQ>(p, s0, cy, in, scen, warp_fresh, st, res);
     __syncthreads();
-    if (active && !done) done = ipm_step<G, DQ>(p, s0, st, res);
+    if (active && !done) done = ipm_step_rr<G, DQ>(p, s0, st, res);
     __syncwarp();
 
     if (done) {
       const bool ok = res.status <= ST_ACCEPTABLE;
       double ua = ldr(s0, rW + 6), uw = ldr(s0, rW + 7);
       if (!ok) {
-        fails++;
+        fails += 1.0;
         if (ea.variant == 1) ua = uw = 0.0;  // simulation_nmpc.py:211: zero control on failure
       }
-      iters_sum += res.iters;
+      iters_sum += (double)res.iters;
       double nz6[NX], y[NX];
       const bool plant_noise = (ea.variant == 1) && ea.dist.on && ea.noise_std > 0.0;
       if (plant_noise) {
@@ -396,9 +418,16 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
       const int kn = min(ea.k_seq[step] + 1, ea.T);
       const double ex = x[0] - ea.traj_states[(long long)kn * NX + 0], ey = x[1] - ea.traj_states[(long long)kn * NX + 1];
       sq_err += ex * ex + ey * ey;
-      step++;
-      if (step < ea.steps) {
-        need_pack = true;
+      if (step + 1 < ea.steps) {
+        double* r = ea.rec + scen * kRec;
+#pragma unroll
+        for (int j = 0; j < NX; j++) __stcg(r + j, x[j]);
+        __stcg(r + 6, max_psi);
+        __stcg(r + 7, sq_err);
+        __stcg(r + 8, iters_sum);
+        __stcg(r + 9, fails);
+        __threadfence();  // publish the record before the step counter
+        *(volatile int32_t*)(ea.steps_done + scen) = step + 1;
       } else {
         const double* goal = ea.traj_states + (long long)ea.T * NX;
         const double kPi = 3.141592653589793, k2Pi = 6.283185307179586;
@@ -412,15 +441,15 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
         mo[2] = fabs(hi - kPi);
         mo[3] = max_psi;
         mo[4] = (max_psi > 1.0471975511965976 + 1e-6) ? 1.0 : 0.0;  // builder-defined jackknife flag
-        mo[5] = (double)fails;
-        mo[6] = (double)iters_sum / (double)ea.steps;
+        mo[5] = fails;
+        mo[6] = iters_sum / (double)ea.steps;
         mo[7] = sqrt(sq_err / (double)ea.steps);
         if (ea.final_state) {
 #pragma unroll
           for (int j = 0; j < NX; j++) ea.final_state[scen * NX + j] = x[j];
         }
-        active = false;
       }
+      active = false;
     }
   }
 }
@@ -847,7 +876,7 @@ int ttmpc_episode_batch(ttmpc_handle* h, int64_t B, const double* x0, const int6
   launch_shape(h, B, &blocks, &threads);
   int rc = ensure_scratch(h, (size_t)blocks * kSolveThreads);
   if (rc) return rc;
-  const size_t need = (size_t)B * (NX * sizeof(double) + sizeof(int32_t));
+  const size_t need = (size_t)B * ((NX + 10) * sizeof(double) + 2 * sizeof(int32_t));
   if (need > h->ep_cap) {
     if (h->ep_buf) cudaFree(h->ep_buf);
     h->ep_buf = nullptr;
@@ -869,7 +898,10 @@ int ttmpc_episode_batch(ttmpc_handle* h, int64_t B, const double* x0, const int6
   ea.variant = variant;
   ea.seed = seed;
   ea.xmeas = (double*)h->ep_buf;
-  ea.kcur = (int32_t*)((char*)h->ep_buf + (size_t)B * NX * sizeof(double));
+  ea.rec = ea.xmeas + (size_t)B * NX;
+  ea.kcur = (int32_t*)(ea.rec + (size_t)B * 10);
+  ea.steps_done = ea.kcur + B;
+  cudaMemsetAsync(ea.steps_done, 0, (size_t)B * sizeof(int32_t), st);
   ea.metrics = metrics_out;
   ea.final_state = final_state_out;
   cudaMemsetAsync(h->counter, 0, 16 * sizeof(unsigned long long), st);

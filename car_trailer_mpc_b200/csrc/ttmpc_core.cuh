@@ -999,6 +999,10 @@ struct Ipm {
   bool fresh;  // the problem has just been assigned to the lane: its first backward sweep reads the caller's arrays
   // hand-over from the backward half of an iteration to its forward / line-search half
   double cur_J, cur_sumlog, cur_theta, cur_cinf, cur_rd, cur_cmax, cur_lam1, cur_delta;
+  // line-search state machine (one trial per round)
+  double ls_a, ls_apr, ls_adu, ls_gd;
+  int ls_bt;
+  bool ls_active;
 };
 
 TT_HD bool tt_finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
@@ -1016,6 +1020,8 @@ TT_HD void ipm_begin(const Params& p, Ipm& s) {
   s.do_update = false;
   s.x0_infeasible = false;
   s.fresh = true;
+  s.ls_active = false;
+  s.ls_bt = 0;
 }
 
 // One interior-point iteration = ipm_backward (apply previous step, statistics, termination tests, barrier update,
@@ -1024,6 +1030,7 @@ TT_HD void ipm_begin(const Params& p, Ipm& s) {
 template <bool G, bool DQ>
 TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const ProblemIn& in, long long b, bool warp_fresh,
                         Ipm& s, Result& res) {
+  if (s.ls_active) return false;  // a rejected trial is being retried with a shorter step: nothing to redo here
   Stats st, st2;
   bool ok = false;
   int status = -1;
@@ -1104,6 +1111,7 @@ TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const Prob
   return false;
 }
 
+// Second half of an iteration: search direction and the complete filter line search (all trials in one call).
 template <bool G, bool DQ>
 TT_HD bool ipm_step(const Params& p, double* s0, Ipm& s, Result& res) {
   const double mu = s.mu, delta = s.cur_delta;
@@ -1179,6 +1187,106 @@ TT_HD bool ipm_step(const Params& p, double* s0, Ipm& s, Result& res) {
   s.alpha_du = si.a_du;
   s.mu_step = mu;
   s.delta_step = delta;
+  s.do_update = true;
+  s.iter++;
+  return false;
+}
+
+// Second half of an iteration, round-robin flavour (used by the closed-loop episode kernel, where noisy measurements
+// produce infeasible instances).  The line search is a per-lane state machine that performs AT MOST ONE trial sweep per
+// call: a lane whose trial point is rejected keeps its direction and comes back with alpha/2 in the next round (its
+// backward and forward sweeps are skipped meanwhile).  In SIMT lockstep a lane that backtracks 30 times would otherwise
+// make the other 31 lanes of its warp wait through 30 extra sweeps; well-posed problems accept their first trial, so
+// this only moves the cost of a struggling (typically infeasible) problem onto that problem.
+template <bool G, bool DQ>
+TT_HD bool ipm_step_rr(const Params& p, double* s0, Ipm& s, Result& res) {
+  const double mu = s.mu;
+  const double theta = s.cur_theta;
+  const double phi = s.cur_J - mu * s.cur_sumlog;
+  bool accepted = false;
+  if (!s.ls_active) {
+    StepInfo si;
+    forward_sweep<G, DQ>(p, s0, mu, s.tau, si);
+    s.ls_apr = si.a_pr;
+    s.ls_adu = si.a_du;
+    s.ls_gd = si.gphi_d;
+    s.ls_a = si.a_pr;
+    s.ls_bt = 0;
+    // Round-off regime (analogue of Ipopt's tiny-step rule in function values): predicted change of phi below its
+    // resolution (or below the c'lambda evaluation noise theta*||lambda||_1) and constraint violation far below tol
+    // -> theta/phi comparisons are noise; take the full step.
+    accepted = (theta <= 1e-2 * p.tol) &&
+               (fabs(si.gphi_d) <= fmax(100.0 * kEps * fmax(1.0, fabs(phi)), theta * s.cur_lam1));
+  }
+  if (!accepted) {
+    // one trial of the filter line search (Waechter & Biegler 2006, Algorithm A)
+    const double a = s.ls_a, gd = s.ls_gd;
+    Trial tr;
+    trial_sweep<G, DQ>(p, s0, a, tr);
+    bool good = tt_finite(tr.J) && tt_finite(tr.sumlog) && tt_finite(tr.theta);
+    const double phi_t = tr.J - mu * tr.sumlog;
+    if (good && tr.theta > s.theta_max) good = false;
+    if (good) {
+      for (int i = 0; i < s.f_n; i++)
+        if (tr.theta >= s.f_theta[i] && phi_t >= s.f_phi[i]) good = false;  // dominated by a filter entry
+    }
+    bool ftype = false;
+    if (good) {
+      // switching condition  a*(-g)^s_phi > delta*theta^s_theta, evaluated in logs (theta = 0: always true)
+      if (theta <= s.theta_min && gd < 0.0 &&
+          (theta <= 0.0 || log(a) + kSPhi * log(-gd) > log(kDeltaSw) + kSTheta * log(theta))) {
+        good = (phi_t - phi - 10.0 * kEps * fabs(phi) <= kEtaPhi * a * gd);
+        ftype = true;
+      } else {
+        good = (tr.theta - (1.0 - kGammaTheta) * theta <= 10.0 * kEps * fabs(theta)) ||
+               (phi_t - (phi - kGammaPhi * theta) <= 10.0 * kEps * fabs(phi));
+      }
+    }
+    if (good) {
+      if (!ftype) {
+        const double ft = (1.0 - kGammaTheta) * theta, fp = phi - kGammaPhi * theta;
+        int m = 0;
+        for (int i = 0; i < s.f_n; i++)
+          if (!(s.f_theta[i] >= ft && s.f_phi[i] >= fp)) {
+            s.f_theta[m] = s.f_theta[i];
+            s.f_phi[m] = s.f_phi[i];
+            m++;
+          }
+        if (m == kFilterMax) m--;
+        s.f_theta[m] = ft;
+        s.f_phi[m] = fp;
+        s.f_n = m + 1;
+      }
+      accepted = true;
+      s.ls_fail = 0;
+    } else if (s.ls_bt < kMaxBacktrack) {
+      s.ls_bt++;
+      s.ls_a = a * kAlphaRed;
+      s.ls_active = true;  // come back next round with half the step
+      return false;
+    } else {
+      // Ipopt would enter feasibility restoration; policy: shortest trial step, cleared filter, give up after 3
+      if (++s.ls_fail >= 3) {
+        // the iterate is unchanged since the last backward sweep: report it
+        res.obj = s.cur_J;
+        res.dual_inf = s.cur_rd;
+        res.constr_viol = s.cur_cinf;
+        res.compl_inf = s.cur_cmax;
+        res.iters = s.iter;
+        res.status = s.x0_infeasible ? (int)ST_INFEASIBLE_X0 : (int)ST_LINESEARCH;
+        return true;
+      }
+      s.ls_a = s.ls_apr * 9.313225746154785e-10;  // kAlphaRed^kMaxBacktrack = 2^-30
+      s.f_n = 0;
+    }
+  } else {
+    s.ls_fail = 0;
+  }
+  s.ls_active = false;
+  s.alpha = s.ls_a;
+  s.alpha_du = s.ls_adu;
+  s.mu_step = mu;
+  s.delta_step = s.cur_delta;
   s.do_update = true;
   s.iter++;
   return false;

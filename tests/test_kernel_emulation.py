@@ -87,3 +87,14 @@ def test_shared_trajectory_mode_in_emulation(traj):
     b = emu.solve_batch(cfg, x, k_index=k, traj_states=S, traj_inputs=U)
     for key in ("z", "u0", "obj", "iters", "status"):
         assert np.array_equal(a[key], b[key]), key
+
+
+def test_round_robin_line_search_equals_loop_line_search():
+    """ipm_step_rr (one trial per round, episode kernel) must walk exactly the same iterates as ipm_step."""
+    cfg = tracking_preset(30); cfg.max_iter = 60
+    sc = pb.make_scenarios(cfg, 96, seed=17, sigma=pb.SIGMA_WIDE * 3.0)   # far off: backtracking and failures occur
+    a = emu.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs)
+    b = emu.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs, force_generic=4)
+    for key in ("z", "u0", "obj", "iters", "status"):
+        assert np.array_equal(a[key], b[key], equal_nan=True), key
+    assert (a["iters"] > 12).any()

@@ -14,6 +14,8 @@
 
 using namespace ttmpc;
 
+static int g_round_robin_ls = 0;
+
 template <bool G, bool DQ>
 static void run(const Params& p, std::vector<double>& scratch, int64_t B, const ProblemIn& in, double* z_out, double* u0_out,
                 double* obj_out, double* kkt_out, int32_t* iters_out, int32_t* status_out) {
@@ -28,7 +30,14 @@ static void run(const Params& p, std::vector<double>& scratch, int64_t B, const 
       double carried[kCarry];
       const Carry cy{carried, 1};
       ipm_begin(p, st);
-      while (!ipm_iteration<G, DQ>(p, s0, cy, in, b, st, r)) {
+      if (g_round_robin_ls) {
+        for (;;) {  // the episode kernel's flavour: at most one line-search trial per round
+          if (ipm_backward<G, DQ>(p, s0, cy, in, b, st.fresh, st, r)) break;
+          if (ipm_step_rr<G, DQ>(p, s0, st, r)) break;
+        }
+      } else {
+        while (!ipm_iteration<G, DQ>(p, s0, cy, in, b, st, r)) {
+        }
       }
       if (z_out) unpack_slot(p, s0, z_out + b * nz);
       if (u0_out) { u0_out[b * 2] = ldr(s0, rW + 6); u0_out[b * 2 + 1] = ldr(s0, rW + 7); }
@@ -51,6 +60,7 @@ extern "C" int ttmpc_emu_solve_batch(const ttmpc_config* cfg, int64_t B, const d
   std::vector<double> scratch(scratch_doubles(p.N, 1), NAN);
   ProblemIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T};
   const bool g = p.generic || (force_generic & 1), dq = p.diag && !(force_generic & 2);
+  g_round_robin_ls = (force_generic & 4) != 0;
   if (g && dq) run<true, true>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
   else if (g) run<true, false>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
   else if (dq) run<false, true>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
