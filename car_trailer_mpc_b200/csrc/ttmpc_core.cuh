@@ -87,6 +87,7 @@ struct Params {
   double Q2[21];             // 2*Q, symmetric packed (SY)
   double R2[3];              // 2*R: (a,a), (a,w), (w,w)
   double lo[NW], up[NW];     // relaxed bounds (bound_relax_factor), x then u
+  double lo_push[NW], up_push[NW];  // lo + push, up - push (bound_push / bound_frac): clamp range of the starting point
   double tol, acc_tol, mu_init, mu_floor;
 };
 
@@ -428,7 +429,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
           if ((hl && w[j] < p.lo[j]) || (hu && w[j] > p.up[j])) x0_bad = true;
         } else {
           const double g = in.z_warm ? in.z_warm[b * nz + (long long)k * NW + j] : ref[j];
-          w[j] = push_inside(g, p.lo[j], p.up[j], hl, hu);
+          w[j] = tt_min(tt_max(g, p.lo_push[j]), p.up_push[j]);  // Ipopt's push into the interior (bounds precomputed)
           zl[j] = has_lo<G>(p, j) ? 1.0 : 0.0;
           zu[j] = has_up<G>(p, j) ? 1.0 : 0.0;
         }
@@ -1340,6 +1341,11 @@ inline int build_params(const ttmpc_config* c, Params* p) {
   for (int i = 0; i < NU; i++) {
     if (c->u_lb[i] > c->u_ub[i]) return TTMPC_E_INVAL;
     relax(c->u_lb[i], c->u_ub[i], &p->lo[NX + i], &p->up[NX + i], &p->bl, &p->bu, NX + i);
+  }
+  for (int j = 0; j < NW; j++) {  // push_inside(g) == clamp(g, lo_push, up_push)
+    const bool hl = ((p->bl >> j) & 1u) != 0, hu = ((p->bu >> j) & 1u) != 0;
+    p->lo_push[j] = hl ? push_inside(-INFINITY, p->lo[j], p->up[j], hl, hu) : -INFINITY;
+    p->up_push[j] = hu ? push_inside(INFINITY, p->lo[j], p->up[j], hl, hu) : INFINITY;
   }
   p->generic = !(p->bl == 0xFCu && p->bu == 0xFCu);
   p->diag = (p->R2[1] == 0.0);

@@ -15,7 +15,7 @@ L.ttmpc_debug_timing(None, 1)
 r = s.solve(x, xs, us); torch.cuda.synchronize()
 out = (ctypes.c_ulonglong * 8)()
 L.ttmpc_debug_timing(out, 0)
-names = ["loop tail (unpack, result scalars)", "ticket fetch", "pack", "barrier 1", "backward half", "barrier 2", "step half (fwd+trials)", "packs (count)"]
+names = ["loop tail (unpack, result scalars)", "ticket fetch", "-", "barrier 1", "backward half", "barrier 2", "step half (fwd+trials)", "active lane-rounds"]
 tot = sum(out[i] for i in range(7))
 for n, v in zip(names, out): print(f"{n:36s} {v:>16d}  {100*v/tot:5.1f}%")
-print("cycles per pack:", out[2] / max(out[7], 1))
+print("warp-rounds:", "active lanes per warp-round = n/a")
