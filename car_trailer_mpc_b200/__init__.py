@@ -3,7 +3,8 @@ Avan1ko/car-trailer-mpc (drop-in for ``controller.solve`` of mpc_control.py / mp
 
 Public surface:
   * :class:`BatchSolver`           -- thin ctypes front end of the C ABI in ``include/ttmpc.h`` (CUDA only).
-  * :class:`MPCTrackingControl`, :class:`TruckTrailerNMPC`, :class:`TruckTrailerModel` -- shims with
+  * :class:`MPCTrackingControl`, :class:`TruckTrailerNMPC`, :class:`MPCTrackingControlFuzzy`,
+    :class:`TruckTrailerModel` -- shims with
     the reference's constructor / ``solve`` signatures.
   * :mod:`problem`                 -- trajectory, windows, layouts, synthetic scenario batches.
   * :mod:`closed_loop`, :mod:`batch_driver` -- headless closed loop and the sweep/CSV driver.
@@ -31,6 +32,10 @@ def __getattr__(name):  # lazy: importing the package must not require the CUDA 
         from .mpc_control_nmpc import TruckTrailerNMPC
 
         return TruckTrailerNMPC
+    if name == "MPCTrackingControlFuzzy":
+        from .mpc_control_fuzzy import MPCTrackingControlFuzzy
+
+        return MPCTrackingControlFuzzy
     if name == "TruckTrailerModel":
         from .truck_trailer_model import TruckTrailerModel
 

@@ -48,6 +48,8 @@ def load():
     L.ttmpc_last_error.restype = ctypes.c_char_p
     L.ttmpc_solve_batch.argtypes = [H, ctypes.c_int64] + [c_dp] * 10 + [ctypes.c_void_p]
     L.ttmpc_solve_batch.restype = ctypes.c_int
+    L.ttmpc_solve_batch_weighted.argtypes = [H, ctypes.c_int64] + [c_dp] * 12 + [ctypes.c_void_p]
+    L.ttmpc_solve_batch_weighted.restype = ctypes.c_int
     L.ttmpc_solve_batch_shared.argtypes = (
         [H, ctypes.c_int64, c_dp, c_dp, c_dp, c_dp, ctypes.c_int32] + [c_dp] * 7 + [ctypes.c_void_p]
     )
@@ -71,6 +73,6 @@ def load():
 
 EXPORTS = [
     "ttmpc_default_config", "ttmpc_create", "ttmpc_destroy", "ttmpc_last_error", "ttmpc_version",
-    "ttmpc_solve_batch", "ttmpc_solve_batch_shared", "ttmpc_shift_warm_start", "ttmpc_plant_step", "ttmpc_episode_batch",
+    "ttmpc_solve_batch", "ttmpc_solve_batch_weighted", "ttmpc_solve_batch_shared", "ttmpc_shift_warm_start", "ttmpc_plant_step", "ttmpc_episode_batch",
     "ttmpc_launch_count", "ttmpc_kernel_name", "ttmpc_measure_fp64_peak",
 ]

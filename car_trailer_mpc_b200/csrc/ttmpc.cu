@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) ttmpc_order_kernel(long long B, const int
   order[pos] = (int32_t)b;
 }
 
-template <bool G, bool DQ>
+template <bool G, bool DQ, bool PW>
 __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
     ttmpc_solve_kernel(const __grid_constant__ Params p, double* __restrict__ scratch, long long B, ProblemIn in, SolveOut out,
                        unsigned long long* __restrict__ counter, const int32_t* __restrict__ order) {
@@ -144,9 +144,9 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
     // ---- one interior-point iteration for every lane that has a problem
     bool done = false;
     const bool warp_fresh = __any_sync(kFull, active && st.fresh);
-    if (active) done = ipm_backward<G, DQ>(p, s0, cy, in, prob, warp_fresh, st, res);
+    if (active) done = ipm_backward<G, DQ, PW>(p, s0, cy, in, prob, warp_fresh, st, res);
     __syncthreads();
-    if (active && !done) done = ipm_step<G, DQ>(p, s0, st, res);
+    if (active && !done) done = ipm_step<G, DQ, PW>(p, s0, cy, st, res);
     __syncwarp();
 
     // ---- finished lanes: scalars by the owner, the decision vector by the whole warp (coalesced z_out rows)
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
   const size_t slot = (size_t)blockIdx.x * kSolveThreads + threadIdx.x;
   double* s0 = slot_ptr(scratch, p.N, slot);
   const unsigned lane = threadIdx.x & 31u;
-  const ProblemIn in{ea.xmeas, nullptr, nullptr, nullptr, ea.kcur, ea.traj_states, ea.traj_inputs, ea.T};
+  const ProblemIn in{ea.xmeas, nullptr, nullptr, nullptr, ea.kcur, ea.traj_states, ea.traj_inputs, ea.T, nullptr, nullptr};
   const long long total = B * (long long)ea.steps;
   long long scen = -1;
   unsigned long long sid = 0;
@@ -392,9 +392,9 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
 
     bool done = false;
     const bool warp_fresh = __any_sync(kFull, active && st.fresh);
-    if (active) done = ipm_backward<G, DQ>(p, s0, cy, in, scen, warp_fresh, st, res);
+    if (active) done = ipm_backward<G, DQ, false>(p, s0, cy, in, scen, warp_fresh, st, res);
     __syncthreads();
-    if (active && !done) done = ipm_step_rr<G, DQ>(p, s0, st, res);
+    if (active && !done) done = ipm_step_rr<G, DQ, false>(p, s0, cy, st, res);
     __syncwarp();
 
     if (done) {
@@ -477,9 +477,11 @@ __global__ void __launch_bounds__(256) ttmpc_dfma_kernel(double* out, double a, 
 // ================================================================================================
 // kernel variant for a configuration: bound pattern (G) x weight structure (DQ)
 typedef void (*solve_kernel_t)(const Params, double*, long long, ProblemIn, SolveOut, unsigned long long*, const int32_t*);
-static solve_kernel_t solve_kernel_for(const Params& p) {
-  if (p.generic) return p.diag ? ttmpc_solve_kernel<true, true> : ttmpc_solve_kernel<true, false>;
-  return p.diag ? ttmpc_solve_kernel<false, true> : ttmpc_solve_kernel<false, false>;
+static solve_kernel_t solve_kernel_for(const Params& p, bool weighted = false) {
+  if (weighted)  // per-problem weight scalings: diagonal Q, R only (checked by the caller)
+    return p.generic ? ttmpc_solve_kernel<true, true, true> : ttmpc_solve_kernel<false, true, true>;
+  if (p.generic) return p.diag ? ttmpc_solve_kernel<true, true, false> : ttmpc_solve_kernel<true, false, false>;
+  return p.diag ? ttmpc_solve_kernel<false, true, false> : ttmpc_solve_kernel<false, false, false>;
 }
 
 typedef void (*episode_kernel_t)(const Params, double*, long long, EpisodeArgs, unsigned long long*);
@@ -662,7 +664,9 @@ static int solve_device(ttmpc_handle* h, long long B, const ProblemIn& in, const
     h->launches[5]++;
     order = ord;
   }
-  solve_kernel_for(h->p)<<<(unsigned)blocks, threads, kSolveSmem, st>>>(h->p, h->scratch, B, in, so, h->counter, order);
+  const bool weighted = in.q_w != nullptr;
+  if (weighted) cudaFuncSetAttribute(solve_kernel_for(h->p, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmem);
+  solve_kernel_for(h->p, weighted)<<<(unsigned)blocks, threads, kSolveSmem, st>>>(h->p, h->scratch, B, in, so, h->counter, order);
   h->launches[0]++;
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "kernel launch", ce);
@@ -678,10 +682,13 @@ static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 static int solve_any(ttmpc_handle* h, int64_t B, const double* x_init, const double* ref_states, const double* ref_inputs,
                      const int32_t* k_index, const double* traj_states, const double* traj_inputs, int32_t T,
                      const double* z_warm, double* z_out, double* u0_out, double* obj_out, double* kkt_out,
-                     int32_t* iters_out, int32_t* status_out, void* stream) {
+                     int32_t* iters_out, int32_t* status_out, void* stream, const double* q_w = nullptr,
+                     const double* r_w = nullptr) {
   if (!h) return TTMPC_E_INVAL;
   h->err[0] = 0;
   if (B < 0 || !x_init) return set_err(h, TTMPC_E_INVAL, "bad batch arguments", cudaSuccess);
+  if ((q_w == nullptr) != (r_w == nullptr)) return set_err(h, TTMPC_E_INVAL, "q_weights and r_weights go together", cudaSuccess);
+  if (q_w && !h->p.diag) return set_err(h, TTMPC_E_INVAL, "per-problem weights need diagonal Q and R", cudaSuccess);
   const bool shared = (ref_states == nullptr);
   if (shared && (!k_index || !traj_states || !traj_inputs || T < 1)) return set_err(h, TTMPC_E_INVAL, "bad trajectory arguments", cudaSuccess);
   if (!shared && !ref_inputs) return set_err(h, TTMPC_E_INVAL, "ref_inputs is null", cudaSuccess);
@@ -692,7 +699,7 @@ static int solve_any(ttmpc_handle* h, int64_t B, const double* x_init, const dou
   const size_t nz = 8 * (size_t)N + 6;
   const bool host = (h->cfg.flags & TTMPC_FLAG_HOST_POINTERS) != 0;
   if (!host) {
-    ProblemIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T};
+    ProblemIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T, q_w, r_w};
     SolveOut so{z_out, u0_out, obj_out, kkt_out, iters_out, status_out};
     int rc = solve_device(h, B, in, so, st);
     if (rc) return rc;
@@ -718,6 +725,8 @@ static int solve_any(ttmpc_handle* h, int64_t B, const double* x_init, const dou
   pl.off_kkt = o; o += al((size_t)B * 3 * 8);
   pl.off_it = o; o += al((size_t)B * 4);
   pl.off_st = o; o += al((size_t)B * 4);
+  const size_t off_qw = o; o += q_w ? al((size_t)B * NX * 8) : 0;
+  const size_t off_rw = o; o += q_w ? al((size_t)B * NU * 8) : 0;
   pl.total = o;
   if (pl.total > h->stage_bytes) {
     if (h->stage) cudaFree(h->stage);
@@ -740,6 +749,10 @@ static int solve_any(ttmpc_handle* h, int64_t B, const double* x_init, const dou
     H2D(pl.off_tu, traj_inputs, (size_t)T * NU * 8);
   }
   if (z_warm) H2D(pl.off_zw, z_warm, (size_t)B * nz * 8);
+  if (q_w) {
+    H2D(off_qw, q_w, (size_t)B * NX * 8);
+    H2D(off_rw, r_w, (size_t)B * NU * 8);
+  }
   ProblemIn in{(const double*)(d + pl.off_x),
             shared ? nullptr : (const double*)(d + pl.off_rs),
             shared ? nullptr : (const double*)(d + pl.off_ru),
@@ -747,7 +760,9 @@ static int solve_any(ttmpc_handle* h, int64_t B, const double* x_init, const dou
             shared ? (const int32_t*)(d + pl.off_k) : nullptr,
             shared ? (const double*)(d + pl.off_ts) : nullptr,
             shared ? (const double*)(d + pl.off_tu) : nullptr,
-            T};
+            T,
+            q_w ? (const double*)(d + off_qw) : nullptr,
+            q_w ? (const double*)(d + off_rw) : nullptr};
   SolveOut so{z_out ? (double*)(d + pl.off_z) : nullptr, (double*)(d + pl.off_u0), (double*)(d + pl.off_obj),
               (double*)(d + pl.off_kkt), (int32_t*)(d + pl.off_it), (int32_t*)(d + pl.off_st)};
   int rc = solve_device(h, B, in, so, st);
@@ -771,6 +786,15 @@ int ttmpc_solve_batch(ttmpc_handle* h, int64_t B, const double* x_init, const do
   if (h && !ref_states) return set_err(h, TTMPC_E_INVAL, "ref_states is null", cudaSuccess);
   return solve_any(h, B, x_init, ref_states, ref_inputs, nullptr, nullptr, nullptr, 0, z_warm, z_out, u0_out, obj_out,
                    kkt_out, iters_out, status_out, cuda_stream);
+}
+
+int ttmpc_solve_batch_weighted(ttmpc_handle* h, int64_t B, const double* x_init, const double* ref_states,
+                               const double* ref_inputs, const double* q_weights, const double* r_weights,
+                               const double* z_warm, double* z_out, double* u0_out, double* obj_out, double* kkt_out,
+                               int32_t* iters_out, int32_t* status_out, void* cuda_stream) {
+  if (h && (!ref_states || !q_weights || !r_weights)) return set_err(h, TTMPC_E_INVAL, "null argument", cudaSuccess);
+  return solve_any(h, B, x_init, ref_states, ref_inputs, nullptr, nullptr, nullptr, 0, z_warm, z_out, u0_out, obj_out,
+                   kkt_out, iters_out, status_out, cuda_stream, q_weights, r_weights);
 }
 
 int ttmpc_solve_batch_shared(ttmpc_handle* h, int64_t B, const double* x_init, const int32_t* k_index,

@@ -283,12 +283,36 @@ TT_HD void A_mul(const Lin& m, const double* d, double* y) {
   y[4] = d[4];
   y[5] = d[5];
 }
+// Loop-carried state of the backward sweep (value function P, p0, p1; x_{k+1}; multipliers of stage k+1).  It is kept
+// OUT of registers on purpose: each piece is needed in one short section of the stage body only, and holding all 55
+// doubles live across the body forces ~900 B of local-memory spills per thread that thrash L1.  On the device this
+// storage is shared memory ([entry][thread], conflict-free); the host emulation uses a plain array.  The last 8
+// entries hold the squares of the per-problem weight scalings (PW kernels: mpc_control_fuzzy.py:21-24).
+constexpr int cP = 0, cP0 = 21, cP1 = 27, cXN = 33, cLNEW = 39, cLOLD = 45, cLPLUS = 49, cQW = 55, cRW = 61, kCarry = 63;
+struct Carry {
+  double* base;
+  int stride;
+  TT_HD double ld(int i) const { return base[i * stride]; }
+  TT_HD void st(int i, double v) const { base[i * stride] = v; }
+};
+
+// per-problem cost weights (PW): Q_w = diag(q) Q diag(q), R_w = diag(r) R diag(r) with diagonal Q, R
+// (mpc_control_fuzzy.py:21-31); the squares q_i^2, r_i^2 sit in the lane's carried storage
+template <bool PW>
+TT_HD double wq(const Params& p, const Carry& cy, int i) {
+  return PW ? p.Q2[SY(i, i)] * cy.ld(cQW + i) : p.Q2[SY(i, i)];
+}
+template <bool PW>
+TT_HD double wr(const Params& p, const Carry& cy, int i) {
+  return PW ? p.R2[2 * i] * cy.ld(cRW + i) : p.R2[2 * i];
+}
+
 // y = Q2 * d  (symmetric packed 6x6; DQ: Q and R are diagonal, as in every driver of the reference)
-template <bool DQ>
-TT_HD void Q2_mul(const Params& p, const double* d, double* y) {
+template <bool DQ, bool PW>
+TT_HD void Q2_mul(const Params& p, const Carry& cy, const double* d, double* y) {
   if (DQ) {
     TT_UNROLL
-    for (int i = 0; i < NX; i++) y[i] = p.Q2[SY(i, i)] * d[i];
+    for (int i = 0; i < NX; i++) y[i] = wq<PW>(p, cy, i) * d[i];
     return;
   }
   TT_UNROLL
@@ -326,6 +350,8 @@ struct ProblemIn {
   const double* traj_states;  // [T+1][6]
   const double* traj_inputs;  // [T][2]
   int T;
+  const double* q_w;          // [B][6] per-problem weight scalings or null (PW kernels)
+  const double* r_w;          // [B][2]
 };
 // reference value (stage k, component j) of problem b: the caller's window, or the window rules of
 // simulation.py:485-499 applied to the shared trajectory
@@ -350,18 +376,6 @@ struct Stats {
 // ------------------------------------------------------------------------------------------------
 // backward sweep
 // ------------------------------------------------------------------------------------------------
-// Loop-carried state of the backward sweep (value function P, p0, p1; x_{k+1}; multipliers of stage k+1).  It is kept
-// OUT of registers on purpose: each piece is needed in one short section of the stage body only, and holding all 55
-// doubles live across the body forces ~900 B of local-memory spills per thread that thrash L1.  On the device this
-// storage is shared memory ([entry][thread], conflict-free); the host emulation uses a plain array.
-constexpr int cP = 0, cP0 = 21, cP1 = 27, cXN = 33, cLNEW = 39, cLOLD = 45, cLPLUS = 49, kCarry = 55;
-struct Carry {
-  double* base;
-  int stride;
-  TT_HD double ld(int i) const { return base[i * stride]; }
-  TT_HD void st(int i, double v) const { base[i * stride] = v; }
-};
-
 // do_update: apply the step stored in DW with primal step alpha / dual step alpha_du; mu_step, delta_step are the
 // barrier parameter and Hessian regularisation the step was computed with.  delta: regularisation for the new
 // factorisation.  Returns false when some 2x2 pivot block is not positive definite (wrong inertia).
@@ -373,7 +387,7 @@ struct Carry {
 // of the warp at once (a lane-by-lane load would write 8 of every 32-byte sector and cost more than the sweep).
 // warp_fresh: some lane of the warp is fresh (then every lane re-stores its reference row, again to keep full rows).
 // x0_bad (out, fresh only): x_init violates a state bound.
-template <bool G, bool DQ>
+template <bool G, bool DQ, bool PW>
 TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const ProblemIn& in, long long b, bool fresh,
                           bool warp_fresh, bool& x0_bad, bool do_update, double alpha, double alpha_du, double mu_step,
                           double delta_step, double delta, Stats& st) {
@@ -383,6 +397,12 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
   double J = 0.0, sumlog = 0.0, theta = 0.0, cinf = 0.0, rd_inf = 0.0, lam1 = 0.0, z1 = 0.0, cmax = 0.0, cmin = INFINITY;
   const double kmu_hi = kKappaSigma * mu_step, kmu_lo = mu_step * (1.0 / kKappaSigma);
   const int kk_fresh = (fresh && in.ref_states == nullptr) ? in.k_index[b] : 0;  // shared-trajectory window start
+  if (PW && fresh) {  // entering problem: its weight scalings (squared) go to the lane's carried storage
+    TT_UNROLL
+    for (int i = 0; i < NX; i++) cy.st(cQW + i, in.q_w[b * NX + i] * in.q_w[b * NX + i]);
+    TT_UNROLL
+    for (int i = 0; i < NU; i++) cy.st(cRW + i, in.r_w[b * NU + i] * in.r_w[b * NU + i]);
+  }
 
   for (int k = N; k >= 0; k--) {
     double* ps = s0 + (size_t)k * kStageStride;
@@ -469,10 +489,10 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
       if (has_x) {
         // costate recursion at the OLD iterate:  lambda+_k = A_k' lambda+_{k+1} - (Hx_k dx_k + ghat_k)
         double hx[NX], g[NX], d6[NX];
-        Q2_mul<DQ>(p, dw, hx);
+        Q2_mul<DQ, PW>(p, cy, dw, hx);
         TT_UNROLL
         for (int j = 0; j < NX; j++) d6[j] = w[j] - ref[j];
-        Q2_mul<DQ>(p, d6, g);
+        Q2_mul<DQ, PW>(p, cy, d6, g);
         TT_UNROLL
         for (int j = 0; j < NX; j++) hx[j] += sigd[j] + g[j] + gb[j];
         double lp[NX];
@@ -537,14 +557,14 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
       double d6[NX];
       TT_UNROLL
       for (int j = 0; j < NX; j++) d6[j] = w[j] - ref[j];
-      Q2_mul<DQ>(p, d6, g0);
+      Q2_mul<DQ, PW>(p, cy, d6, g0);
       double jq = 0.0;
       TT_UNROLL
       for (int j = 0; j < NX; j++) jq += g0[j] * d6[j];
       if (has_u) {
         const double da = w[6] - ref[6], dw_ = w[7] - ref[7];
-        g0[6] = DQ ? p.R2[0] * da : p.R2[0] * da + p.R2[1] * dw_;
-        g0[7] = DQ ? p.R2[2] * dw_ : p.R2[1] * da + p.R2[2] * dw_;
+        g0[6] = DQ ? wr<PW>(p, cy, 0) * da : p.R2[0] * da + p.R2[1] * dw_;
+        g0[7] = DQ ? wr<PW>(p, cy, 1) * dw_ : p.R2[1] * da + p.R2[2] * dw_;
         jq += g0[6] * da + g0[7] * dw_;
       } else {
         g0[6] = g0[7] = 0.0;
@@ -595,7 +615,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
       for (int i = 0; i < NX; i++) {
         TT_UNROLL
         for (int j = i; j < NX; j++)
-          cy.st(cP + SY(i, j), ((DQ && j != i) ? 0.0 : p.Q2[SY(i, j)]) + (j == i ? sig[i] : 0.0));
+          cy.st(cP + SY(i, j), ((DQ && j != i) ? 0.0 : (DQ ? wq<PW>(p, cy, i) : p.Q2[SY(i, j)])) + (j == i ? sig[i] : 0.0));
         cy.st(cP0 + i, g0[i]);
         cy.st(cP1 + i, g1[i]);
         const double r = g0[i] + lam[i] - zl[i] + zu[i];  // dual residual of x_N
@@ -671,9 +691,9 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
       }
       // Rhat = 2R + Sigma_u + delta + B'PB
       const double dt2 = dt * dt;
-      const double r00 = p.R2[0] + sig[6] + dt2 * P[SY(5, 5)];
+      const double r00 = (DQ ? wr<PW>(p, cy, 0) : p.R2[0]) + sig[6] + dt2 * P[SY(5, 5)];
       const double r01 = (DQ ? 0.0 : p.R2[1]) + dt2 * P[SY(5, 4)];
-      const double r11 = p.R2[2] + sig[7] + dt2 * P[SY(4, 4)];
+      const double r11 = (DQ ? wr<PW>(p, cy, 1) : p.R2[2]) + sig[7] + dt2 * P[SY(4, 4)];
       const double det = r00 * r11 - r01 * r01;
       if (!(r00 > 0.0) || !(det > 0.0)) ok = false;
       const double idet = tt_rcp(det);
@@ -725,7 +745,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
             TT_UNROLL
             for (int j = i + 1; j < NX; j++) Pn[SY(i, j)] += p.Q2[SY(i, j)];
           }
-          Pn[SY(i, i)] += p.Q2[SY(i, i)] + sig[i];
+          Pn[SY(i, i)] += (DQ ? wq<PW>(p, cy, i) : p.Q2[SY(i, i)]) + sig[i];
         }
         Pn[SY(2, 2)] += hs.h22;
         Pn[SY(2, 5)] += hs.h25;
@@ -798,8 +818,8 @@ TT_HD void fwd_load(const Params& p, const double* s0, int k, FwdIn& f) {
   for (int j = 0; j < NX; j++) f.xnext[j] = has_u ? ldr(ps + kStageStride, rW + j) : 0.0;
 }
 
-template <bool G, bool DQ>
-TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, StepInfo& si) {
+template <bool G, bool DQ, bool PW>
+TT_HD void forward_sweep(const Params& p, double* s0, const Carry& cy, double mu, double tau, StepInfo& si) {
   const int N = p.N;
   const double dt = p.dt;
   double dx[NX] = {0, 0, 0, 0, 0, 0};
@@ -848,10 +868,10 @@ TT_HD void forward_sweep(const Params& p, double* s0, double mu, double tau, Ste
       double d6[NX];
       TT_UNROLL
       for (int j = 0; j < NX; j++) d6[j] = w[j] - cur.ref[j];
-      Q2_mul<DQ>(p, d6, g);
+      Q2_mul<DQ, PW>(p, cy, d6, g);
       const double da = w[6] - cur.ref[6], dw_ = w[7] - cur.ref[7];
-      g[6] = DQ ? p.R2[0] * da : p.R2[0] * da + p.R2[1] * dw_;
-      g[7] = DQ ? p.R2[2] * dw_ : p.R2[1] * da + p.R2[2] * dw_;
+      g[6] = DQ ? wr<PW>(p, cy, 0) * da : p.R2[0] * da + p.R2[1] * dw_;
+      g[7] = DQ ? wr<PW>(p, cy, 1) * dw_ : p.R2[1] * da + p.R2[2] * dw_;
     }
     TT_UNROLL
     for (int j = 0; j < NW; j++) {
@@ -928,8 +948,8 @@ TT_HD void trial_load(const Params& p, const double* s0, int k, TrialIn& t) {
   }
 }
 
-template <bool G, bool DQ>
-TT_HD void trial_sweep(const Params& p, const double* s0, double alpha, Trial& tr) {
+template <bool G, bool DQ, bool PW>
+TT_HD void trial_sweep(const Params& p, const double* s0, const Carry& cy, double alpha, Trial& tr) {
   const int N = p.N;
   const double dt = p.dt;
   double J = 0.0, sl_ = 0.0, th = 0.0, smin = INFINITY;
@@ -945,7 +965,7 @@ TT_HD void trial_sweep(const Params& p, const double* s0, double alpha, Trial& t
     double d6[NX], g[NX];
     TT_UNROLL
     for (int j = 0; j < NX; j++) d6[j] = w[j] - cur.ref[j];
-    Q2_mul<DQ>(p, d6, g);
+    Q2_mul<DQ, PW>(p, cy, d6, g);
     double jq = 0.0;
     TT_UNROLL
     for (int j = 0; j < NX; j++) jq += g[j] * d6[j];
@@ -967,7 +987,7 @@ TT_HD void trial_sweep(const Params& p, const double* s0, double alpha, Trial& t
     sl_ += log(prod);
     if (has_u) {
       const double da = w[6] - cur.ref[6], dw_ = w[7] - cur.ref[7];
-      jq += DQ ? p.R2[0] * da * da + p.R2[2] * dw_ * dw_
+      jq += DQ ? wr<PW>(p, cy, 0) * da * da + wr<PW>(p, cy, 1) * dw_ * dw_
                : (p.R2[0] * da + p.R2[1] * dw_) * da + (p.R2[1] * da + p.R2[2] * dw_) * dw_;
       double f[4];
       stage_f(p, w, f);
@@ -1028,7 +1048,7 @@ TT_HD void ipm_begin(const Params& p, Ipm& s) {
 // One interior-point iteration = ipm_backward (apply previous step, statistics, termination tests, barrier update,
 // factorisation) + ipm_step (search direction, line search).  Both return true when the lane is finished (res filled
 // in).  They are separate so that the CUDA kernel can align the two halves across the warps of a CTA.
-template <bool G, bool DQ>
+template <bool G, bool DQ, bool PW>
 TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const ProblemIn& in, long long b, bool warp_fresh,
                         Ipm& s, Result& res) {
   if (s.ls_active) return false;  // a rejected trial is being retried with a shorter step: nothing to redo here
@@ -1042,7 +1062,7 @@ TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const Prob
   for (int attempt = 0; attempt <= 40; attempt++) {
     const bool first = (attempt == 0);
     bool x0_bad = false;
-    ok = backward_sweep<G, DQ>(p, s0, cy, in, b, first && s.fresh, first && warp_fresh, x0_bad, first && s.do_update, s.alpha,
+    ok = backward_sweep<G, DQ, PW>(p, s0, cy, in, b, first && s.fresh, first && warp_fresh, x0_bad, first && s.do_update, s.alpha,
                                s.alpha_du, first ? s.mu_step : mu, s.delta_step, delta, first ? st : st2);
     if (first) {
       if (s.fresh) s.x0_infeasible = x0_bad;
@@ -1113,11 +1133,11 @@ TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const Prob
 }
 
 // Second half of an iteration: search direction and the complete filter line search (all trials in one call).
-template <bool G, bool DQ>
-TT_HD bool ipm_step(const Params& p, double* s0, Ipm& s, Result& res) {
+template <bool G, bool DQ, bool PW>
+TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result& res) {
   const double mu = s.mu, delta = s.cur_delta;
   StepInfo si;
-  forward_sweep<G, DQ>(p, s0, mu, s.tau, si);
+  forward_sweep<G, DQ, PW>(p, s0, cy, mu, s.tau, si);
 
   // filter line search (Waechter & Biegler 2006, Algorithm A)
   const double theta = s.cur_theta;
@@ -1131,7 +1151,7 @@ TT_HD bool ipm_step(const Params& p, double* s0, Ipm& s, Result& res) {
   bool accepted = roundoff_step;
   for (int bt = 0; !roundoff_step && bt <= kMaxBacktrack; bt++, a *= kAlphaRed) {
     Trial tr;
-    trial_sweep<G, DQ>(p, s0, a, tr);
+    trial_sweep<G, DQ, PW>(p, s0, cy, a, tr);
     if (!(tt_finite(tr.J) && tt_finite(tr.sumlog) && tt_finite(tr.theta))) continue;
     const double phi_t = tr.J - mu * tr.sumlog;
     if (tr.theta > s.theta_max) continue;
@@ -1199,15 +1219,15 @@ TT_HD bool ipm_step(const Params& p, double* s0, Ipm& s, Result& res) {
 // backward and forward sweeps are skipped meanwhile).  In SIMT lockstep a lane that backtracks 30 times would otherwise
 // make the other 31 lanes of its warp wait through 30 extra sweeps; well-posed problems accept their first trial, so
 // this only moves the cost of a struggling (typically infeasible) problem onto that problem.
-template <bool G, bool DQ>
-TT_HD bool ipm_step_rr(const Params& p, double* s0, Ipm& s, Result& res) {
+template <bool G, bool DQ, bool PW>
+TT_HD bool ipm_step_rr(const Params& p, double* s0, const Carry& cy, Ipm& s, Result& res) {
   const double mu = s.mu;
   const double theta = s.cur_theta;
   const double phi = s.cur_J - mu * s.cur_sumlog;
   bool accepted = false;
   if (!s.ls_active) {
     StepInfo si;
-    forward_sweep<G, DQ>(p, s0, mu, s.tau, si);
+    forward_sweep<G, DQ, PW>(p, s0, cy, mu, s.tau, si);
     s.ls_apr = si.a_pr;
     s.ls_adu = si.a_du;
     s.ls_gd = si.gphi_d;
@@ -1223,7 +1243,7 @@ TT_HD bool ipm_step_rr(const Params& p, double* s0, Ipm& s, Result& res) {
     // one trial of the filter line search (Waechter & Biegler 2006, Algorithm A)
     const double a = s.ls_a, gd = s.ls_gd;
     Trial tr;
-    trial_sweep<G, DQ>(p, s0, a, tr);
+    trial_sweep<G, DQ, PW>(p, s0, cy, a, tr);
     bool good = tt_finite(tr.J) && tt_finite(tr.sumlog) && tt_finite(tr.theta);
     const double phi_t = tr.J - mu * tr.sumlog;
     if (good && tr.theta > s.theta_max) good = false;
@@ -1293,10 +1313,10 @@ TT_HD bool ipm_step_rr(const Params& p, double* s0, Ipm& s, Result& res) {
   return false;
 }
 
-template <bool G, bool DQ>
+template <bool G, bool DQ, bool PW>
 TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, const ProblemIn& in, long long b, Ipm& s, Result& res) {
-  if (ipm_backward<G, DQ>(p, s0, cy, in, b, s.fresh, s, res)) return true;
-  return ipm_step<G, DQ>(p, s0, s, res);
+  if (ipm_backward<G, DQ, PW>(p, s0, cy, in, b, s.fresh, s, res)) return true;
+  return ipm_step<G, DQ, PW>(p, s0, cy, s, res);
 }
 
 // slot -> z_out in the reference's decision-vector layout (trajectory_planning.py:38-60): z[8k+j] = w_k[j]

@@ -91,16 +91,21 @@ class BatchSolver:
         return float(v)
 
     # ------------------------------------------------------------------ solve
-    def solve(self, x_init, ref_states, ref_inputs, z_warm=None, want_z: bool = True, stream=None) -> dict:
-        """Solve B problems with per-problem reference windows (MPCTrackingControl.solve semantics)."""
-        return self._solve(x_init, ref_states, ref_inputs, None, None, None, z_warm, want_z, stream)
+    def solve(self, x_init, ref_states, ref_inputs, z_warm=None, want_z: bool = True, stream=None,
+              q_weights=None, r_weights=None) -> dict:
+        """Solve B problems with per-problem reference windows (MPCTrackingControl.solve semantics).
+
+        ``q_weights [B,6]`` / ``r_weights [B,2]`` (optional, together): per-problem weight scalings
+        ``Q_w = diag(q) Q diag(q)``, ``R_w = diag(r) R diag(r)`` as in mpc_control_fuzzy.py:21-31 (diagonal Q, R only)."""
+        return self._solve(x_init, ref_states, ref_inputs, None, None, None, z_warm, want_z, stream, q_weights, r_weights)
 
     def solve_shared(self, x_init, k_index, traj_states, traj_inputs, z_warm=None, want_z: bool = True, stream=None) -> dict:
         """All problems track one trajectory ``traj_states [T+1,6]``, ``traj_inputs [T,2]``; problem i uses the
         window starting at ``k_index[i]`` with the padding rules of simulation.py:485-499."""
         return self._solve(x_init, None, None, k_index, traj_states, traj_inputs, z_warm, want_z, stream)
 
-    def _solve(self, x_init, ref_states, ref_inputs, k_index, traj_states, traj_inputs, z_warm, want_z, stream):
+    def _solve(self, x_init, ref_states, ref_inputs, k_index, traj_states, traj_inputs, z_warm, want_z, stream,
+               q_weights=None, r_weights=None):
         N = self.cfg.horizon
         nz = 8 * N + 6
         shared = ref_states is None
@@ -124,6 +129,8 @@ class BatchSolver:
             else:
                 prs, pru = chk(ref_states, (B, N + 1, 6)), chk(ref_inputs, (B, N, 2))
             pzw = chk(z_warm, (B, nz)) if z_warm is not None else None
+            pqw = chk(q_weights, (B, 6)) if q_weights is not None else None
+            prw = chk(r_weights, (B, 2)) if r_weights is not None else None
             out = dict(
                 z=torch.empty((B, nz), dtype=torch.float64, device=dev) if want_z else None,
                 u0=torch.empty((B, 2), dtype=torch.float64, device=dev),
@@ -159,6 +166,12 @@ class BatchSolver:
                 z_warm = np.ascontiguousarray(z_warm, dtype=np.float64).reshape(B, nz)
                 pzw = z_warm.ctypes.data
                 keep.append(z_warm)
+            pqw = prw = None
+            if q_weights is not None:
+                q_weights = np.ascontiguousarray(q_weights, dtype=np.float64).reshape(B, 6)
+                r_weights = np.ascontiguousarray(r_weights, dtype=np.float64).reshape(B, 2)
+                pqw, prw = q_weights.ctypes.data, r_weights.ctypes.data
+                keep += [q_weights, r_weights]
             out = dict(
                 z=np.empty((B, nz)) if want_z else None,
                 u0=np.empty((B, 2)),
@@ -173,6 +186,10 @@ class BatchSolver:
         if shared:
             rc = self._L.ttmpc_solve_batch_shared(
                 h, B, px, pk, pts, ptu, T, pzw, ptr(out["z"]), ptr(out["u0"]), ptr(out["obj"]), ptr(out["kkt"]),
+                ptr(out["iters"]), ptr(out["status"]), stream)
+        elif pqw is not None:
+            rc = self._L.ttmpc_solve_batch_weighted(
+                h, B, px, prs, pru, pqw, prw, pzw, ptr(out["z"]), ptr(out["u0"]), ptr(out["obj"]), ptr(out["kkt"]),
                 ptr(out["iters"]), ptr(out["status"]), stream)
         else:
             rc = self._L.ttmpc_solve_batch(

@@ -14,6 +14,8 @@
  *   ttmpc_solve_batch       <- MPCTrackingControl.solve (mpc_control.py:67-110) and
  *                              TruckTrailerNMPC.solve (mpc_control_nmpc.py:90-113),
  *                              B independent problems per call instead of one.
+ *   ttmpc_solve_batch_weighted <- MPCTrackingControlFuzzy.solve (mpc_control_fuzzy.py:121-167): same NLP
+ *                              with per-solve diagonal weight scalings passed as parameters.
  *   ttmpc_solve_batch_shared<- the window extraction of the closed-loop drivers
  *                              (simulation.py:485-499, simulation_nmpc.py:193-204) fused
  *                              with the solve: every problem tracks the same trajectory.
@@ -117,6 +119,14 @@ int ttmpc_solve_batch(ttmpc_handle* h, int64_t B, const double* x_init, const do
                       const double* ref_inputs, const double* z_warm, double* z_out,
                       double* u0_out, double* obj_out, double* kkt_out, int32_t* iters_out,
                       int32_t* status_out, void* cuda_stream);
+
+/* Same as ttmpc_solve_batch with per-problem cost-weight scalings q_weights [B][6], r_weights [B][2]:
+ * Q_w = diag(q) Q diag(q), R_w = diag(r) R diag(r), terminal weight Q_w -- the parametric weights of
+ * MPCTrackingControlFuzzy (mpc_control_fuzzy.py:21-31,51-60).  Needs diagonal Q and R in the config. */
+int ttmpc_solve_batch_weighted(ttmpc_handle* h, int64_t B, const double* x_init, const double* ref_states,
+                               const double* ref_inputs, const double* q_weights, const double* r_weights,
+                               const double* z_warm, double* z_out, double* u0_out, double* obj_out,
+                               double* kkt_out, int32_t* iters_out, int32_t* status_out, void* cuda_stream);
 
 /* Same, but every problem tracks one shared trajectory traj_states[T+1][6], traj_inputs[T][2];
  * problem i uses the window starting at k_index[i] with the three padding regimes of

@@ -130,3 +130,79 @@ def test_nmpc_shim_closed_loop_vs_oracle(traj):
         assert mg["jackknife"] == mr["jackknife"] and mg["failures"] == mr["failures"] and mg["steps"] == mr["steps"] == 500
         assert np.abs(gpu.controls - ref.controls).max() < 1e-4
         assert np.abs(gpu.states - ref.states).max() < 1e-4
+
+
+def test_fuzzy_controller_shim_vs_oracle(traj):
+    """simulation_fuzzy.py configuration (N=40, Q=I, R=10I, tol 1e-3, warm start, fuzzy weight scalings as per-problem
+    kernel inputs) through the MPCTrackingControlFuzzy shim vs the oracle with explicitly scaled Q/R matrices."""
+    import torch
+    from car_trailer_mpc_b200 import MPCTrackingControlFuzzy, TruckTrailerModel, nmpc_preset
+    from car_trailer_mpc_b200.mpc_control_fuzzy import fuzzy_weights
+    from oracle import oracle
+    assert torch.cuda.is_available()
+    S, U = traj
+    N = 40
+    params = dict(PARAMS, horizon=N)
+    ctl = MPCTrackingControlFuzzy(TruckTrailerModel(params), params, np.eye(6), 10 * np.eye(2), SB, IB)
+    base = nmpc_preset(N)
+    base.set_weights(np.eye(6), 10 * np.eye(2))
+    base.set_bounds(SB["lb"], SB["ub"], IB["lb"], IB["ub"])
+
+    class OracleFuzzy:
+        def __init__(self):
+            self._last = None
+            self.last_status = self.last_iterations = None
+
+        def solve(self, x, ref_s, ref_u):
+            q, r = fuzzy_weights(x, ref_s)
+            zw = None if self._last is None else pb.shift_warm_start(self._last, N, True)
+            for qq, rr in ((q, r), (np.ones(6), np.ones(2))):
+                c = base.copy()
+                c.set_weights(np.diag(qq) @ np.eye(6) @ np.diag(qq), np.diag(rr) @ (10 * np.eye(2)) @ np.diag(rr))
+                res = oracle.solve(c, np.asarray(x), np.ascontiguousarray(ref_s.T), np.ascontiguousarray(ref_u.T), z_warm=zw)
+                self.last_status, self.last_iterations = int(res["status"]), int(res["iters"])
+                if self.last_status <= 1:
+                    break
+            if self.last_status > 1:
+                return None, None
+            self._last = res["z"]
+            X, Uu = pb.unpack_z(res["z"], N)
+            return X.T.copy(), Uu.T.copy()
+
+    gpu = cl.simulate_single(ctl, S, U, S[0], 30.0, 0.05, N, params, variant="nmpc")
+    ref = cl.simulate_single(OracleFuzzy(), S, U, S[0], 30.0, 0.05, N, params, variant="nmpc")
+    mg, mr = gpu.metrics(S[-1]), ref.metrics(S[-1])
+    assert mg["steps"] == mr["steps"] == 600 and mg["failures"] == mr["failures"] == 0
+    assert mg["jackknife"] == mr["jackknife"] == False
+    assert np.abs(gpu.controls - ref.controls).max() < 1e-4 and np.abs(gpu.states - ref.states).max() < 1e-4
+    q, r = ctl.last_weights
+    assert q.max() > 1.0 and r.max() > 1.0    # the rule base was active (hitch angle / reversing)
+
+
+def test_weighted_batch_solve_device_and_host_paths():
+    import torch
+    from car_trailer_mpc_b200 import BatchSolver
+    from car_trailer_mpc_b200.mpc_control_fuzzy import fuzzy_weights
+    from oracle import oracle
+    cfg = tracking_preset(40)
+    sc = pb.make_scenarios(cfg, 300, seed=29)
+    qw = np.empty((300, 6)); rw = np.empty((300, 2))
+    for i in range(300):
+        qw[i], rw[i] = fuzzy_weights(sc.x_init[i], sc.ref_states[i].T)
+    s = BatchSolver(cfg, 0)
+    dev = torch.device("cuda:0")
+    a = s.solve(sc.x_init, sc.ref_states, sc.ref_inputs, q_weights=qw, r_weights=rw)
+    t = lambda x: torch.from_numpy(x).to(dev)
+    b = s.solve(t(sc.x_init), t(sc.ref_states), t(sc.ref_inputs), q_weights=t(qw), r_weights=t(rw))
+    torch.cuda.synchronize()
+    assert np.array_equal(a["z"], b["z"].cpu().numpy()) and (a["status"] == 0).all()
+    for i in range(0, 300, 17):
+        c = cfg.copy()
+        c.set_weights(np.diag(qw[i] ** 2), 10 * np.diag(rw[i] ** 2))
+        ref = oracle.solve(c, sc.x_init[i], sc.ref_states[i], sc.ref_inputs[i])
+        assert np.abs(ref["u0"] - a["u0"][i]).max() <= 1e-4 and abs(ref["obj"] - a["obj"][i]) <= 1e-6 * max(1.0, abs(ref["obj"]))
+    unweighted = s.solve(sc.x_init, sc.ref_states, sc.ref_inputs)
+    assert np.abs(unweighted["u0"] - a["u0"]).max() > 1e-3      # the scalings change the solution
+    dense = tracking_preset(40); Q = np.eye(6); Q[0, 1] = Q[1, 0] = 0.2; dense.set_weights(Q, 10 * np.eye(2))
+    with pytest.raises(Exception):
+        BatchSolver(dense, 0).solve(sc.x_init[:4], sc.ref_states[:4], sc.ref_inputs[:4], q_weights=qw[:4], r_weights=rw[:4])

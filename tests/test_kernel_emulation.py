@@ -98,3 +98,25 @@ def test_round_robin_line_search_equals_loop_line_search():
     for key in ("z", "u0", "obj", "iters", "status"):
         assert np.array_equal(a[key], b[key], equal_nan=True), key
     assert (a["iters"] > 12).any()
+
+
+def test_per_problem_weights_match_oracle_with_scaled_matrices():
+    """PW kernels (mpc_control_fuzzy.py's parametric weights): Q_w = diag(q) Q diag(q), R_w = diag(r) R diag(r)."""
+    from car_trailer_mpc_b200.mpc_control_fuzzy import fuzzy_weights
+    cfg = tracking_preset(30)
+    cfg.set_weights(np.diag([1.0, 1.0, 2.0, 3.0, 1.0, 1.0]), np.diag([5.0, 8.0]))
+    sc = pb.make_scenarios(cfg, 24, seed=23, families=False)
+    qw = np.empty((24, 6)); rw = np.empty((24, 2))
+    for i in range(24):
+        qw[i], rw[i] = fuzzy_weights(sc.x_init[i], sc.ref_states[i].T)
+    qw[0], rw[0] = 1.0, 1.0
+    got = emu.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs, q_weights=qw, r_weights=rw)
+    assert (qw > 1.0).any() and (rw > 1.0).any()
+    for i in range(24):
+        c = cfg.copy()
+        c.set_weights(np.diag(qw[i]) @ cfg.Qm() @ np.diag(qw[i]), np.diag(rw[i]) @ cfg.Rm() @ np.diag(rw[i]))
+        ref = oracle.solve(c, sc.x_init[i], sc.ref_states[i], sc.ref_inputs[i])
+        assert ref["status"] == got["status"][i] == 0
+        assert np.abs(ref["u0"] - got["u0"][i]).max() < 1e-7 and abs(ref["obj"] - got["obj"][i]) < 1e-9 * max(1, abs(ref["obj"]))
+    plain = emu.solve_batch(cfg, sc.x_init[:1], sc.ref_states[:1], sc.ref_inputs[:1])
+    assert np.array_equal(plain["z"][0], got["z"][0])   # unit scalings == unweighted kernel

@@ -22,7 +22,7 @@ def lib():
 
 
 def solve_batch(cfg, x_init, ref_states=None, ref_inputs=None, z_warm=None, k_index=None, traj_states=None,
-                traj_inputs=None, force_generic=False):
+                traj_inputs=None, force_generic=False, q_weights=None, r_weights=None):
     N = cfg.horizon
     x = np.ascontiguousarray(x_init, dtype=np.float64).reshape(-1, 6)
     B = x.shape[0]
@@ -36,6 +36,8 @@ def solve_batch(cfg, x_init, ref_states=None, ref_inputs=None, z_warm=None, k_in
         ts = np.ascontiguousarray(traj_states, dtype=np.float64)
         tu = np.ascontiguousarray(traj_inputs, dtype=np.float64)
         T = tu.shape[0]
+    qw = None if q_weights is None else np.ascontiguousarray(q_weights, dtype=np.float64).reshape(B, 6)
+    rw = None if r_weights is None else np.ascontiguousarray(r_weights, dtype=np.float64).reshape(B, 2)
     zw = None if z_warm is None else np.ascontiguousarray(z_warm, dtype=np.float64).reshape(B, 8 * N + 6)
     z = np.empty((B, 8 * N + 6)); u0 = np.empty((B, 2)); obj = np.empty(B); kkt = np.empty((B, 3))
     it = np.empty(B, np.int32); st = np.empty(B, np.int32)
@@ -43,7 +45,7 @@ def solve_batch(cfg, x_init, ref_states=None, ref_inputs=None, z_warm=None, k_in
     P = lambda a, t=dp: None if a is None else a.ctypes.data_as(t)
     rc = lib().ttmpc_emu_solve_batch(ctypes.byref(cfg), ctypes.c_int64(B), P(x), P(xs), P(us), P(ki, ip), P(ts), P(tu),
                                      ctypes.c_int32(T), P(zw), P(z), P(u0), P(obj), P(kkt), P(it, ip), P(st, ip),
-                                     ctypes.c_int(int(force_generic)))
+                                     ctypes.c_int(int(force_generic)), P(qw), P(rw))
     if rc:
         raise RuntimeError(f"emu rc={rc}")
     return dict(z=z, u0=u0, obj=obj, kkt=kkt, iters=it, status=st)

@@ -16,7 +16,7 @@ using namespace ttmpc;
 
 static int g_round_robin_ls = 0;
 
-template <bool G, bool DQ>
+template <bool G, bool DQ, bool PW>
 static void run(const Params& p, std::vector<double>& scratch, int64_t B, const ProblemIn& in, double* z_out, double* u0_out,
                 double* obj_out, double* kkt_out, int32_t* iters_out, int32_t* status_out) {
   const size_t nz = 8 * (size_t)p.N + 6;
@@ -32,11 +32,11 @@ static void run(const Params& p, std::vector<double>& scratch, int64_t B, const 
       ipm_begin(p, st);
       if (g_round_robin_ls) {
         for (;;) {  // the episode kernel's flavour: at most one line-search trial per round
-          if (ipm_backward<G, DQ>(p, s0, cy, in, b, st.fresh, st, r)) break;
-          if (ipm_step_rr<G, DQ>(p, s0, st, r)) break;
+          if (ipm_backward<G, DQ, PW>(p, s0, cy, in, b, st.fresh, st, r)) break;
+          if (ipm_step_rr<G, DQ, PW>(p, s0, cy, st, r)) break;
         }
       } else {
-        while (!ipm_iteration<G, DQ>(p, s0, cy, in, b, st, r)) {
+        while (!ipm_iteration<G, DQ, PW>(p, s0, cy, in, b, st, r)) {
         }
       }
       if (z_out) unpack_slot(p, s0, z_out + b * nz);
@@ -53,17 +53,22 @@ extern "C" int ttmpc_emu_solve_batch(const ttmpc_config* cfg, int64_t B, const d
                                      const double* ref_inputs, const int32_t* k_index, const double* traj_states,
                                      const double* traj_inputs, int32_t T, const double* z_warm, double* z_out,
                                      double* u0_out, double* obj_out, double* kkt_out, int32_t* iters_out,
-                                     int32_t* status_out, int force_generic) {
+                                     int32_t* status_out, int force_generic, const double* q_w, const double* r_w) {
   Params p;
   int rc = build_params(cfg, &p);
   if (rc) return rc;
   std::vector<double> scratch(scratch_doubles(p.N, 1), NAN);
-  ProblemIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T};
+  ProblemIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T, q_w, r_w};
   const bool g = p.generic || (force_generic & 1), dq = p.diag && !(force_generic & 2);
   g_round_robin_ls = (force_generic & 4) != 0;
-  if (g && dq) run<true, true>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
-  else if (g) run<true, false>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
-  else if (dq) run<false, true>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
-  else run<false, false>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
+  if (q_w && p.diag) {
+    if (g) run<true, true, true>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
+    else run<false, true, true>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
+    return 0;
+  }
+  if (g && dq) run<true, true, false>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
+  else if (g) run<true, false, false>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
+  else if (dq) run<false, true, false>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
+  else run<false, false, false>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
   return 0;
 }
