@@ -120,3 +120,24 @@ def test_per_problem_weights_match_oracle_with_scaled_matrices():
         assert np.abs(ref["u0"] - got["u0"][i]).max() < 1e-7 and abs(ref["obj"] - got["obj"][i]) < 1e-9 * max(1, abs(ref["obj"]))
     plain = emu.solve_batch(cfg, sc.x_init[:1], sc.ref_states[:1], sc.ref_inputs[:1])
     assert np.array_equal(plain["z"][0], got["z"][0])   # unit scalings == unweighted kernel
+
+
+def test_core_under_address_sanitizer(tmp_path):
+    """compute-sanitizer is closed on the GPU pool, so the index arithmetic of the solver core (slot layout, carried
+    storage, every kernel variant) is exercised on the host under ASan + UBSan instead."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "emu_asan")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-DTTMPC_BANK=32", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                           "-o", exe, os.path.join(root, "tools", "emu_asan_main.cpp"), os.path.join(root, "tools", "kernel_emu.cpp"), "-lm"])
+    cfg = tracking_preset(12)
+    B = 35
+    sc = pb.make_scenarios(cfg, B, seed=41, sigma=pb.SIGMA_WIDE)
+    import ctypes
+    open(tmp_path / "cfg.bin", "wb").write(bytes(ctypes.string_at(ctypes.byref(cfg), ctypes.sizeof(cfg))))
+    rng = np.random.default_rng(2)
+    for name, arr in (("x", sc.x_init), ("xs", sc.ref_states), ("us", sc.ref_inputs), ("qw", 1 + rng.random((B, 6))), ("rw", 1 + rng.random((B, 2)))):
+        np.ascontiguousarray(arr, dtype=np.float64).tofile(tmp_path / f"{name}.bin")
+    out = subprocess.run([exe, str(tmp_path), "12", str(B)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "checksum" in out.stdout and "nan" not in out.stdout.lower()

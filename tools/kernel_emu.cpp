@@ -57,7 +57,7 @@ extern "C" int ttmpc_emu_solve_batch(const ttmpc_config* cfg, int64_t B, const d
   Params p;
   int rc = build_params(cfg, &p);
   if (rc) return rc;
-  std::vector<double> scratch(scratch_doubles(p.N, 1), NAN);
+  std::vector<double> scratch(scratch_doubles(p.N, (48 + kBank - 1) / kBank), NAN);  // run() uses up to 48 lanes
   ProblemIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T, q_w, r_w};
   const bool g = p.generic || (force_generic & 1), dq = p.diag && !(force_generic & 2);
   g_round_robin_ls = (force_generic & 4) != 0;
