@@ -3,7 +3,7 @@ Avan1ko/car-trailer-mpc (drop-in for ``controller.solve`` of mpc_control.py / mp
 
 Public surface:
   * :class:`BatchSolver`           -- thin ctypes front end of the C ABI in ``include/ttmpc.h`` (CUDA only).
-  * :class:`MPCTrackingControl`, :class:`TruckTrailerNMPC`, :class:`MPCTrackingControlFuzzy`,
+  * :class:`MPCTrackingControl`, :class:`TruckTrailerNMPC`, :class:`MPCTrackingControlFuzzy`, :class:`MPCTrackingControlObs`,
     :class:`TruckTrailerModel` -- shims with
     the reference's constructor / ``solve`` signatures.
   * :mod:`problem`                 -- trajectory, windows, layouts, synthetic scenario batches.
@@ -11,12 +11,14 @@ Public surface:
 """
 from .config import (  # noqa: F401
     Config,
+    Obstacles,
     STATUS_NAMES,
     nmpc_preset,
+    parking_lot_obstacles,
     tracking_preset,
 )
 
-__all__ = ["Config", "tracking_preset", "nmpc_preset", "STATUS_NAMES"]
+__all__ = ["Config", "Obstacles", "tracking_preset", "nmpc_preset", "parking_lot_obstacles", "STATUS_NAMES"]
 
 
 def __getattr__(name):  # lazy: importing the package must not require the CUDA library
@@ -36,6 +38,10 @@ def __getattr__(name):  # lazy: importing the package must not require the CUDA 
         from .mpc_control_fuzzy import MPCTrackingControlFuzzy
 
         return MPCTrackingControlFuzzy
+    if name == "MPCTrackingControlObs":
+        from .mpc_control_obs import MPCTrackingControlObs
+
+        return MPCTrackingControlObs
     if name == "TruckTrailerModel":
         from .truck_trailer_model import TruckTrailerModel
 

@@ -18,6 +18,7 @@ import numpy as np
 NX = 6
 NU = 2
 MAX_HORIZON = 128
+MAX_OBSTACLES = 16
 
 # status codes (include/ttmpc.h)
 ST_CONVERGED, ST_ACCEPTABLE, ST_MAX_ITER, ST_LINESEARCH, ST_NUMERIC, ST_INFEASIBLE_X0 = range(6)
@@ -126,3 +127,46 @@ def nmpc_preset(horizon: int = 30, dt: float = 0.05, max_iter: int = 2000) -> Co
     c.tol = 1e-3
     c.acceptable_tol = 1e-2
     return c
+
+
+class Obstacles(ctypes.Structure):
+    """Plain-old-data twin of ``struct ttmpc_obstacles``: the obstacle list of ``MPCTrackingControlObs``
+    (python-files/mpc_control_obs.py:8-30) as ``{centre x, centre y, width, height}`` rows, the body widths
+    ``params['W1'], params['W2']`` (simulation.py:393) and the safety distance (mpc_control_obs.py:67)."""
+
+    _fields_ = [
+        ("count", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("rect", (ctypes.c_double * 4) * MAX_OBSTACLES),
+        ("W1", ctypes.c_double),
+        ("W2", ctypes.c_double),
+        ("d_min", ctypes.c_double),
+    ]
+
+    @classmethod
+    def from_list(cls, obstacle_list, W1: float = 3.05, W2: float = 2.95, d_min: float = 0.2) -> "Obstacles":
+        """``obstacle_list``: dicts with ``center`` / ``width`` / ``height`` (get_obstacles.py:5-33) or 4-tuples."""
+        if not 1 <= len(obstacle_list) <= MAX_OBSTACLES:
+            raise ValueError(f"between 1 and {MAX_OBSTACLES} obstacles are supported")
+        o = cls()
+        o.count = len(obstacle_list)
+        for i, ob in enumerate(obstacle_list):
+            if isinstance(ob, dict):
+                row = (ob["center"][0], ob["center"][1], ob["width"], ob["height"])
+            else:
+                row = tuple(ob)
+            for j in range(4):
+                o.rect[i][j] = float(row[j])
+        o.W1, o.W2, o.d_min = float(W1), float(W2), float(d_min)
+        return o
+
+    def as_list(self):
+        return [dict(center=(self.rect[i][0], self.rect[i][1]), width=self.rect[i][2], height=self.rect[i][3])
+                for i in range(self.count)]
+
+
+def parking_lot_obstacles():
+    """The 11 rectangles of python-files/obstacles.json as get_obstacles.py:5-33 returns them."""
+    rects = [(-15.0, 10.0, 30.0, 20.0), (75.0, 10.0, 30.0, 20.0)]
+    rects += [(c, 10.0, 5.0, 20.0) for c in (3.5, 9.5, 21.5, 27.5, 33.5, 39.5, 45.5, 51.5, 57.5)]
+    return [dict(center=(r[0], r[1]), width=r[2], height=r[3]) for r in rects]

@@ -20,6 +20,7 @@
 
 #include "../../include/ttmpc.h"
 #include "ttmpc_core.cuh"
+#include "ttmpc_obca.cuh"
 
 using namespace ttmpc;
 
@@ -490,7 +491,63 @@ static episode_kernel_t episode_kernel_for(const Params& p) {
   return p.diag ? ttmpc_episode_kernel<false, true> : ttmpc_episode_kernel<false, false>;
 }
 
-constexpr int kNumKernels = 7;
+// ------------------------------------------------------------------------------------------------
+// obstacle-aware (OBCA) solve: one lane per problem, lanes pull problems from a global queue (ttmpc_obca.cuh)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+    ttmpc_obca_kernel(const __grid_constant__ Params p, const __grid_constant__ obca::ObParams o, double* __restrict__ scratch,
+                      long long B, ProblemIn in, SolveOut out, unsigned long long* counter) {
+  // One warp per CTA.  Every lane owns a scratch slot and works through problems from the global queue; the phases of
+  // an iteration (head / factorisation attempts / direction / line-search trials) are aligned across the warp by
+  // votes, so the lanes always execute the same sweep over consecutive slots (convergent, coalesced) although their
+  // problems are at different iterations.
+  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  obca::Ctx c;
+  c.p = &p, c.o = &o, c.s0 = obca::slot_ptr(scratch, p.N, o.P, lane), c.sstride = (size_t)obca::stage_rows(o.P) * kBank;
+  const long long nz = 8LL * p.N + 6;
+  const unsigned full = 0xffffffffu;
+  obca::Lane L;
+  bool active = false, exhausted = false;
+  long long b = -1;
+  for (;;) {
+    if (!active && !exhausted) {
+      b = (long long)atomicAdd(counter, 1ull);
+      if (b < B) {
+        obca::lane_begin(p, o, obca::init_point(c, in, b), L);
+        active = true;
+      } else {
+        exhausted = true;
+      }
+    }
+    if (!__any_sync(full, active)) break;
+    Result res;
+    bool done = false;
+    if (active) done = obca::lane_head(c, L, res);
+    while (__any_sync(full, active && !done && L.need_factor))
+      if (active && !done && L.need_factor) done = obca::lane_factor_once(c, L, res);
+    if (active && !done && L.need_dir) obca::lane_direction(c, L);
+    while (__any_sync(full, active && !done && L.need_trial))
+      if (active && !done && L.need_trial) done = obca::lane_trial_once(c, L, res);
+    if (active && done) {
+      if (out.z) obca::unpack(p, o, c.s0, out.z + b * nz);
+      if (out.u0) {
+        out.u0[2 * b] = ldr(c.s0, obca::oW + 6);
+        out.u0[2 * b + 1] = ldr(c.s0, obca::oW + 7);
+      }
+      if (out.obj) out.obj[b] = res.obj;
+      if (out.kkt) {
+        out.kkt[3 * b] = res.dual_inf;
+        out.kkt[3 * b + 1] = res.constr_viol;
+        out.kkt[3 * b + 2] = res.compl_inf;
+      }
+      if (out.iters) out.iters[b] = res.iters;
+      if (out.status) out.status[b] = res.status;
+      active = false;
+    }
+  }
+}
+
+constexpr int kNumKernels = 8;
 struct ttmpc_handle {
   ttmpc_config cfg;
   Params p;
@@ -503,6 +560,8 @@ struct ttmpc_handle {
   size_t order_cap;
   void* ep_buf;                 // episode scratch: xmeas [B][6] doubles + kcur [B] int32
   size_t ep_cap;
+  double* ob_scratch;           // OBCA solve: per-lane stage data incl. the (obstacle, body) pairs
+  size_t ob_doubles;
   // staging for the host-pointer path
   void* stage;
   size_t stage_bytes;
@@ -512,7 +571,7 @@ struct ttmpc_handle {
 
 static const char* kKernelNames[kNumKernels] = {"ttmpc_solve_kernel", "ttmpc_shift_kernel", "ttmpc_plant_kernel",
                                                 "ttmpc_dfma_kernel", "ttmpc_classify_kernel", "ttmpc_order_kernel",
-                                                "ttmpc_episode_kernel"};
+                                                "ttmpc_episode_kernel", "ttmpc_obca_kernel"};
 
 static int set_err(ttmpc_handle* h, int code, const char* what, cudaError_t ce) {
   if (h) snprintf(h->err, sizeof h->err, "%s%s%s", what, ce != cudaSuccess ? ": " : "", ce != cudaSuccess ? cudaGetErrorString(ce) : "");
@@ -594,6 +653,7 @@ int ttmpc_destroy(ttmpc_handle* h) {
   if (h->counter) cudaFree(h->counter);
   if (h->order_buf) cudaFree(h->order_buf);
   if (h->ep_buf) cudaFree(h->ep_buf);
+  if (h->ob_scratch) cudaFree(h->ob_scratch);
   delete h;
   return TTMPC_OK;
 }
@@ -648,7 +708,6 @@ static int solve_device(ttmpc_handle* h, long long B, const ProblemIn& in, const
     // more problems than resident lanes: start the (predicted) hardest ones first
     if ((size_t)B > h->order_cap) {
       if (h->order_buf) cudaFree(h->order_buf);
-  if (h->ep_buf) cudaFree(h->ep_buf);
       h->order_buf = nullptr;
       h->order_cap = 0;
       if (cudaMalloc(&h->order_buf, 2 * (size_t)B * sizeof(int32_t)) != cudaSuccess)
@@ -673,6 +732,36 @@ static int solve_device(ttmpc_handle* h, long long B, const ProblemIn& in, const
   return TTMPC_OK;
 }
 
+// OBCA solve on device arrays.  Lanes = one warp per CTA, up to kObcaWarpsPerSm warps per SM; a lane owns
+// (N+1) * (93 + 42 * pairs) doubles of scratch (N = 50, 11 obstacles: 415 KB).
+constexpr int kObcaWarpsPerSm = 4;
+static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B, const ProblemIn& in, const SolveOut& so,
+                       cudaStream_t st) {
+  obca::ObParams o;
+  if (obca::build_obparams(&h->cfg, obs, &o) != TTMPC_OK) return set_err(h, TTMPC_E_INVAL, "bad obstacle set", cudaSuccess);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  long long warps = (B + 31) / 32;
+  const char* env = getenv("TTMPC_OBCA_WARPS_PER_SM");
+  const long long cap = (long long)sms * (env ? atoi(env) : kObcaWarpsPerSm);
+  if (warps > cap) warps = cap;
+  const size_t need = obca::scratch_doubles(h->p.N, o.P, (size_t)warps * 32 / kBank);
+  if (need > h->ob_doubles) {
+    if (h->ob_scratch) cudaFree(h->ob_scratch);
+    h->ob_scratch = nullptr;
+    h->ob_doubles = 0;
+    cudaError_t ce = cudaMalloc(&h->ob_scratch, need * sizeof(double));
+    if (ce != cudaSuccess) return set_err(h, TTMPC_E_NOMEM, "obca scratch cudaMalloc", ce);
+    h->ob_doubles = need;
+  }
+  cudaMemsetAsync(h->counter, 0, 16 * sizeof(unsigned long long), st);
+  ttmpc_obca_kernel<<<(unsigned)warps, 32, 0, st>>>(h->p, o, h->ob_scratch, B, in, so, h->counter);
+  h->launches[7]++;
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "obca kernel launch", ce);
+  return TTMPC_OK;
+}
+
 // host-pointer path: stage everything through one device buffer
 struct StagePlan {
   size_t off_x, off_rs, off_ru, off_zw, off_k, off_ts, off_tu, off_z, off_u0, off_obj, off_kkt, off_it, off_st, total;
@@ -683,7 +772,7 @@ static int solve_any(ttmpc_handle* h, int64_t B, const double* x_init, const dou
                      const int32_t* k_index, const double* traj_states, const double* traj_inputs, int32_t T,
                      const double* z_warm, double* z_out, double* u0_out, double* obj_out, double* kkt_out,
                      int32_t* iters_out, int32_t* status_out, void* stream, const double* q_w = nullptr,
-                     const double* r_w = nullptr) {
+                     const double* r_w = nullptr, const ttmpc_obstacles* obs = nullptr) {
   if (!h) return TTMPC_E_INVAL;
   h->err[0] = 0;
   if (B < 0 || !x_init) return set_err(h, TTMPC_E_INVAL, "bad batch arguments", cudaSuccess);
@@ -701,7 +790,7 @@ static int solve_any(ttmpc_handle* h, int64_t B, const double* x_init, const dou
   if (!host) {
     ProblemIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T, q_w, r_w};
     SolveOut so{z_out, u0_out, obj_out, kkt_out, iters_out, status_out};
-    int rc = solve_device(h, B, in, so, st);
+    int rc = obs ? obca_device(h, obs, B, in, so, st) : solve_device(h, B, in, so, st);
     if (rc) return rc;
     if (h->cfg.flags & TTMPC_FLAG_SYNC) {
       cudaError_t ce = cudaStreamSynchronize(st);
@@ -765,7 +854,7 @@ static int solve_any(ttmpc_handle* h, int64_t B, const double* x_init, const dou
             q_w ? (const double*)(d + off_rw) : nullptr};
   SolveOut so{z_out ? (double*)(d + pl.off_z) : nullptr, (double*)(d + pl.off_u0), (double*)(d + pl.off_obj),
               (double*)(d + pl.off_kkt), (int32_t*)(d + pl.off_it), (int32_t*)(d + pl.off_st)};
-  int rc = solve_device(h, B, in, so, st);
+  int rc = obs ? obca_device(h, obs, B, in, so, st) : solve_device(h, B, in, so, st);
   if (rc) return rc;
   if (z_out) D2H(z_out, pl.off_z, (size_t)B * nz * 8);
   if (u0_out) D2H(u0_out, pl.off_u0, (size_t)B * 2 * 8);
@@ -786,6 +875,23 @@ int ttmpc_solve_batch(ttmpc_handle* h, int64_t B, const double* x_init, const do
   if (h && !ref_states) return set_err(h, TTMPC_E_INVAL, "ref_states is null", cudaSuccess);
   return solve_any(h, B, x_init, ref_states, ref_inputs, nullptr, nullptr, nullptr, 0, z_warm, z_out, u0_out, obj_out,
                    kkt_out, iters_out, status_out, cuda_stream);
+}
+
+int ttmpc_obca_solve_batch(ttmpc_handle* h, const ttmpc_obstacles* obstacles, int64_t B, const double* x_init,
+                           const double* ref_states, const double* ref_inputs, double* z_out, double* u0_out,
+                           double* obj_out, double* kkt_out, int32_t* iters_out, int32_t* status_out, void* cuda_stream) {
+  if (h && (!ref_states || !obstacles)) return set_err(h, TTMPC_E_INVAL, "null argument", cudaSuccess);
+  return solve_any(h, B, x_init, ref_states, ref_inputs, nullptr, nullptr, nullptr, 0, nullptr, z_out, u0_out, obj_out,
+                   kkt_out, iters_out, status_out, cuda_stream, nullptr, nullptr, obstacles);
+}
+
+int ttmpc_obca_solve_batch_shared(ttmpc_handle* h, const ttmpc_obstacles* obstacles, int64_t B, const double* x_init,
+                                  const int32_t* k_index, const double* traj_states, const double* traj_inputs, int32_t T,
+                                  double* z_out, double* u0_out, double* obj_out, double* kkt_out, int32_t* iters_out,
+                                  int32_t* status_out, void* cuda_stream) {
+  if (h && !obstacles) return set_err(h, TTMPC_E_INVAL, "null argument", cudaSuccess);
+  return solve_any(h, B, x_init, nullptr, nullptr, k_index, traj_states, traj_inputs, T, nullptr, z_out, u0_out, obj_out,
+                   kkt_out, iters_out, status_out, cuda_stream, nullptr, nullptr, obstacles);
 }
 
 int ttmpc_solve_batch_weighted(ttmpc_handle* h, int64_t B, const double* x_init, const double* ref_states,

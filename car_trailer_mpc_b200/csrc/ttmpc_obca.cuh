@@ -1,0 +1,1139 @@
+// ttmpc_obca.cuh -- obstacle-aware (OBCA) variant of the per-problem interior-point solver, one lane per problem.
+//
+// Replaces the arithmetic behind `self._solver(...)` of python-files/mpc_control_obs.py:296-305 (CasADi -> Ipopt ->
+// MUMPS on a ~14 000-dimensional KKT system) for the NLP of `MPCTrackingControlObs`:
+//   * states / inputs / dynamics / tracking cost / box bounds as in the plain controller (ttmpc_core.cuh);
+//   * for every stage k = 0..N, every obstacle i and every body (vehicle, trailer) a "pair" of 8 local variables
+//     v = (mu[4], lam[4]) >= 0 and 4 rows (mpc_control_obs.py:65-139)
+//         d0 = g'mu - (A_o p_c(x_k) - b_o)'lam + d_min      <= 0
+//         d1,d2 = G'mu + R(alpha)' A_o' lam                  in [-1e-5, 1e-5]^2
+//         d3 = ||A_o' lam||_2 - 1                            <= 0
+//     with A_o = G = [I; -I], b_o from the obstacle rectangle (:42-63), g / p_c / alpha from the body
+//     (truck_trailer_model.py:31-72).  Rows become equalities d(x,v) - s = 0 with bounded slacks s (Ipopt's treatment
+//     of inequality rows); their multipliers are y.
+//
+// Structure that is exploited: the 8 + 4 + 4 unknowns (v, s, y) of a pair couple to
+// xt = (x, y, theta, psi) of the SAME stage only.  Per pair: eliminate s and y, factor the 8x8 block
+//     K_vv = W_vv + Sigma_v + J_v' D J_v      (D = Sigma_s + delta)
+// by Cholesky and condense onto the stage:  Hx += W_xx + J_x' D J_x - K_xv K_vv^-1 K_vx,  gx += J_x' t - K_xv K_vv^-1 q.
+// The condensed problem has the block-tridiagonal structure of the plain controller and is solved by the same Riccati
+// recursion.  All Cholesky pivots and all 2x2 Riccati pivots positive  <=>  the full KKT matrix has the inertia Ipopt
+// asks for; otherwise the Hessian regularisation delta is raised (Ipopt's sequence) and the factorisation repeated.
+//
+// One iteration = 4 sweeps over the stages:  update_stats (apply the accepted step, KKT statistics), factor (backward:
+// condensation + Riccati), direction (forward: dx, du, dv, ds, step limits), trial (theta / phi for the filter).
+// This first version keeps the sweeps separate and the 6x6 algebra dense; ttmpc_core.cuh is the tuned path.
+#pragma once
+#include "ttmpc_core.cuh"
+
+namespace ttmpc {
+namespace obca {
+
+constexpr int kMaxPairs = 2 * TTMPC_MAX_OBSTACLES;
+// ---- scratch rows of one stage ----
+constexpr int oW = 0, oDW = 8, oREF = 16, oLAM = 24, oLAMP = 30, oZL = 36, oZU = 44, oK = 52, oKFF = 64, oP = 66, oPV = 87;
+constexpr int kBaseRows = 93;
+constexpr int qV = 0, qZV = 8, qS = 16, qY = 20, qZS = 24, qDV = 30, qDS = 38;  // rows of one pair
+constexpr int kPairRows = 42;
+TT_HD int stage_rows(int P) { return kBaseRows + kPairRows * P; }
+inline size_t scratch_doubles(int N, int P, size_t nbanks) {
+  return nbanks * (size_t)(N + 1) * (size_t)stage_rows(P) * kBank;
+}
+TT_HD double* slot_ptr(double* scratch, int N, int P, size_t slot) {
+  const size_t bank = slot / kBank, lane = slot % kBank;
+  return scratch + bank * (size_t)(N + 1) * (size_t)stage_rows(P) * kBank + lane;
+}
+
+struct ObParams {
+  int P;                     // pairs per stage = 2 * obstacles; pair j: obstacle j/2, body j%2 (0 vehicle, 1 trailer)
+  double b[kMaxPairs][4];    // b_o of the pair's obstacle
+  double g[2][4];            // body half-extents (L/2, W/2, L/2, W/2)
+  double hl1, hl2, M;        // L1/2, L2/2, hitch offset
+  double d_min;
+  double v_lo;               // relaxed lower bound of mu, lam (0 - 1e-8)
+  double s_up;               // relaxed upper bound of the slacks of d0 and d3
+  double c2_lo, c2_up;       // relaxed bounds of the slacks of d1, d2
+  double v_push, s_up_push, c2_lo_push, c2_up_push;  // Ipopt's push of the starting point into the interior
+  double mu_guess, lam_guess[4];
+};
+
+inline int build_obparams(const ttmpc_config* c, const ttmpc_obstacles* ob, ObParams* o) {
+  if (ob->count < 1 || ob->count > TTMPC_MAX_OBSTACLES) return TTMPC_E_INVAL;
+  if (!(ob->W1 > 0.0) || !(ob->W2 > 0.0)) return TTMPC_E_INVAL;
+  memset(o, 0, sizeof *o);
+  o->P = 2 * ob->count;
+  for (int i = 0; i < ob->count; i++) {
+    const double cx = ob->rect[i][0], cy = ob->rect[i][1], w = ob->rect[i][2], h = ob->rect[i][3];
+    if (!(w > 0.0) || !(h > 0.0)) return TTMPC_E_INVAL;
+    for (int body = 0; body < 2; body++) {
+      double* b = o->b[2 * i + body];  // mpc_control_obs.py:55-63: b = (w/2, h/2, w/2, h/2) + A_o * centre
+      b[0] = 0.5 * w + cx;
+      b[1] = 0.5 * h + cy;
+      b[2] = 0.5 * w - cx;
+      b[3] = 0.5 * h - cy;
+    }
+  }
+  const double e1[4] = {0.5 * c->L1, 0.5 * ob->W1, 0.5 * c->L1, 0.5 * ob->W1};
+  const double e2[4] = {0.5 * c->L2, 0.5 * ob->W2, 0.5 * c->L2, 0.5 * ob->W2};
+  for (int i = 0; i < 4; i++) o->g[0][i] = e1[i], o->g[1][i] = e2[i];
+  o->hl1 = 0.5 * c->L1;
+  o->hl2 = 0.5 * c->L2;
+  o->M = c->M;
+  o->d_min = ob->d_min;
+  const double hw = 1e-5;  // mpc_control_obs.py:120-123
+  o->v_lo = 0.0 - kBoundRelax;
+  o->s_up = 0.0 + kBoundRelax;
+  o->c2_lo = -hw - kBoundRelax;
+  o->c2_up = hw + kBoundRelax;
+  o->v_push = push_inside(-INFINITY, o->v_lo, INFINITY, true, false);
+  o->s_up_push = push_inside(INFINITY, -INFINITY, o->s_up, false, true);
+  o->c2_lo_push = push_inside(-INFINITY, o->c2_lo, o->c2_up, true, true);
+  o->c2_up_push = push_inside(INFINITY, o->c2_lo, o->c2_up, true, true);
+  o->mu_guess = 100.0;  // mpc_control_obs.py:226-237
+  o->lam_guess[0] = 100.0, o->lam_guess[1] = 105.0, o->lam_guess[2] = 110.0, o->lam_guess[3] = 115.0;
+  return TTMPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one pair: rows, Jacobians and multiplier-weighted Hessian
+// ------------------------------------------------------------------------------------------------
+struct Trig {
+  double x, y, cth, sth, cal, sal;  // al = theta + psi
+};
+TT_HD void stage_trig(const double* x, Trig& t) {
+  t.x = x[0];
+  t.y = x[1];
+  tt_sincos(x[2], t.sth, t.cth);
+  tt_sincos(x[2] + x[3], t.sal, t.cal);
+}
+
+struct PairEval {
+  double d[4];
+  double Jx[4][4];   // wrt xt = (x, y, theta, psi)
+  double Jv[4][8];   // wrt (mu, lam)
+  double hthth, hthps;  // W_xx: (theta,theta) and (theta,psi) = (psi,psi)
+  double Wxl[4][2];     // d2/dxt d(ell), ell = A_o' lam = (lam0 - lam2, lam1 - lam3)
+  double Wll[3];        // ell-space Hessian of the norm row (00, 01, 11)
+};
+
+// rows only (line search)
+TT_HD void pair_rows(const ObParams& o, int body, const double* b, const Trig& t, const double* v, double* d) {
+  const double lx = v[4] - v[6], ly = v[5] - v[7], mx = v[0] - v[2], my = v[1] - v[3];
+  double pcx, pcy, c, s;
+  if (body == 0) {
+    pcx = t.x + t.cth * o.hl1, pcy = t.y + t.sth * o.hl1, c = t.cth, s = t.sth;
+  } else {
+    pcx = t.x - t.cth * o.M - t.cal * o.hl2, pcy = t.y - t.sth * o.M - t.sal * o.hl2, c = t.cal, s = t.sal;
+  }
+  const double* g = o.g[body];
+  d[0] = g[0] * v[0] + g[1] * v[1] + g[2] * v[2] + g[3] * v[3] + (b[0] - pcx) * v[4] + (b[1] - pcy) * v[5] +
+         (b[2] + pcx) * v[6] + (b[3] + pcy) * v[7] + o.d_min;
+  d[1] = mx + c * lx + s * ly;
+  d[2] = my - s * lx + c * ly;
+  d[3] = sqrt(lx * lx + ly * ly) - 1.0;
+}
+
+TT_HD void pair_eval(const ObParams& o, int body, const double* b, const Trig& t, const double* v, const double* y,
+                     PairEval& e) {
+  const double lx = v[4] - v[6], ly = v[5] - v[7], mx = v[0] - v[2], my = v[1] - v[3];
+  double pcx, pcy, ptx, pty, ppx, ppy, pttx, ptty, pppx, pppy, c, s;
+  if (body == 0) {  // truck_trailer_model.py:61-64
+    const double a = o.hl1;
+    pcx = t.x + t.cth * a, pcy = t.y + t.sth * a;
+    ptx = -t.sth * a, pty = t.cth * a, ppx = 0.0, ppy = 0.0;
+    pttx = -t.cth * a, ptty = -t.sth * a, pppx = 0.0, pppy = 0.0;
+    c = t.cth, s = t.sth;
+  } else {  // truck_trailer_model.py:66-72
+    const double h = o.hl2, M = o.M;
+    pcx = t.x - t.cth * M - t.cal * h, pcy = t.y - t.sth * M - t.sal * h;
+    ptx = t.sth * M + t.sal * h, pty = -t.cth * M - t.cal * h;
+    ppx = t.sal * h, ppy = -t.cal * h;
+    pttx = t.cth * M + t.cal * h, ptty = t.sth * M + t.sal * h;
+    pppx = t.cal * h, pppy = t.sal * h;
+    c = t.cal, s = t.sal;
+  }
+  const double tr = body ? 1.0 : 0.0;
+  const double* g = o.g[body];
+  const double e0 = b[0] - pcx, e1 = b[1] - pcy, e2 = b[2] + pcx, e3 = b[3] + pcy;
+  e.d[0] = g[0] * v[0] + g[1] * v[1] + g[2] * v[2] + g[3] * v[3] + e0 * v[4] + e1 * v[5] + e2 * v[6] + e3 * v[7] + o.d_min;
+  e.d[1] = mx + c * lx + s * ly;
+  e.d[2] = my - s * lx + c * ly;
+  const double nrm = sqrt(lx * lx + ly * ly), inr = tt_rcp(nrm);
+  e.d[3] = nrm - 1.0;
+  const double nx = lx * inr, ny = ly * inr;
+  const double r1 = -s * lx + c * ly, r2 = -c * lx - s * ly;
+  TT_UNROLL
+  for (int r = 0; r < 4; r++) {
+    TT_UNROLL
+    for (int j = 0; j < 4; j++) e.Jx[r][j] = 0.0;
+    TT_UNROLL
+    for (int j = 0; j < 8; j++) e.Jv[r][j] = 0.0;
+  }
+  e.Jx[0][0] = -lx, e.Jx[0][1] = -ly, e.Jx[0][2] = -(ptx * lx + pty * ly), e.Jx[0][3] = -(ppx * lx + ppy * ly);
+  e.Jx[1][2] = r1, e.Jx[1][3] = tr * r1;
+  e.Jx[2][2] = r2, e.Jx[2][3] = tr * r2;
+  TT_UNROLL
+  for (int j = 0; j < 4; j++) e.Jv[0][j] = g[j];
+  e.Jv[0][4] = e0, e.Jv[0][5] = e1, e.Jv[0][6] = e2, e.Jv[0][7] = e3;
+  e.Jv[1][0] = 1.0, e.Jv[1][2] = -1.0, e.Jv[1][4] = c, e.Jv[1][5] = s, e.Jv[1][6] = -c, e.Jv[1][7] = -s;
+  e.Jv[2][1] = 1.0, e.Jv[2][3] = -1.0, e.Jv[2][4] = -s, e.Jv[2][5] = c, e.Jv[2][6] = s, e.Jv[2][7] = -c;
+  e.Jv[3][4] = nx, e.Jv[3][5] = ny, e.Jv[3][6] = -nx, e.Jv[3][7] = -ny;
+  // Hessian of y'd
+  const double kap = y[1] * r2 - y[2] * r1;
+  e.hthth = -y[0] * (pttx * lx + ptty * ly) + kap;
+  e.hthps = tr * (-y[0] * (pppx * lx + pppy * ly) + kap);
+  const double ra = -s * y[1] - c * y[2], rb = c * y[1] - s * y[2];
+  e.Wxl[0][0] = -y[0], e.Wxl[0][1] = 0.0;
+  e.Wxl[1][0] = 0.0, e.Wxl[1][1] = -y[0];
+  e.Wxl[2][0] = -y[0] * ptx + ra, e.Wxl[2][1] = -y[0] * pty + rb;
+  e.Wxl[3][0] = -y[0] * ppx + tr * ra, e.Wxl[3][1] = -y[0] * ppy + tr * rb;
+  const double yn = y[3] * inr;
+  e.Wll[0] = yn * (1.0 - nx * nx), e.Wll[1] = -yn * nx * ny, e.Wll[2] = yn * (1.0 - ny * ny);
+}
+
+// barrier quantities of the 4 slacks: D = Sigma_s (+delta), gs = d(barrier)/ds at mu = 1, log-product of the distances
+struct SlackBar {
+  double D[4], gs1[4];
+};
+TT_HD void slack_bar(const ObParams& o, const double* s, const double* zs, double delta, SlackBar& sb) {
+  const double r0 = tt_rcp(o.s_up - s[0]), r3 = tt_rcp(o.s_up - s[3]);
+  const double l1 = tt_rcp(s[1] - o.c2_lo), u1 = tt_rcp(o.c2_up - s[1]);
+  const double l2 = tt_rcp(s[2] - o.c2_lo), u2 = tt_rcp(o.c2_up - s[2]);
+  sb.D[0] = zs[0] * r0 + delta, sb.gs1[0] = r0;
+  sb.D[1] = zs[1] * l1 + zs[2] * u1 + delta, sb.gs1[1] = u1 - l1;
+  sb.D[2] = zs[3] * l2 + zs[4] * u2 + delta, sb.gs1[2] = u2 - l2;
+  sb.D[3] = zs[5] * r3 + delta, sb.gs1[3] = r3;
+}
+
+// In-place Cholesky of the lower triangle of an 8x8 matrix (diagonal stored inverted); false when a pivot is not
+// positive.
+TT_HD bool chol8(double (*K)[8]) {
+  bool ok = true;
+  TT_UNROLL
+  for (int j = 0; j < 8; j++) {
+    double d = K[j][j];
+    TT_UNROLL
+    for (int k = 0; k < j; k++) d -= K[j][k] * K[j][k];
+    if (!(d > 0.0)) ok = false;
+    const double il = tt_rcp(sqrt(d));
+    K[j][j] = il;  // the diagonal holds 1 / L_jj
+    TT_UNROLL
+    for (int i = j + 1; i < 8; i++) {
+      double s = K[i][j];
+      TT_UNROLL
+      for (int k = 0; k < j; k++) s -= K[i][k] * K[j][k];
+      K[i][j] = s * il;
+    }
+  }
+  return ok;
+}
+TT_HD void fsub8(const double (*L)[8], double* x) {  // x <- L^-1 x
+  TT_UNROLL
+  for (int i = 0; i < 8; i++) {
+    double s = x[i];
+    TT_UNROLL
+    for (int k = 0; k < i; k++) s -= L[i][k] * x[k];
+    x[i] = s * L[i][i];
+  }
+}
+TT_HD void bsub8(const double (*L)[8], double* x) {  // x <- L^-T x
+  TT_UNROLL
+  for (int i = 7; i >= 0; i--) {
+    double s = x[i];
+    TT_UNROLL
+    for (int k = i + 1; k < 8; k++) s -= L[k][i] * x[k];
+    x[i] = s * L[i][i];
+  }
+}
+
+// Build K_vv (lower triangle), K_vx (8x4), q (8) and t (4) of one pair at barrier parameter mu.
+//   t = D r_c + mu * gs1,  q = -mu/(v - lo) + J_v' t
+TT_HD void pair_system(const ObParams& o, const PairEval& e, const SlackBar& sb, const double* v, const double* zv,
+                       const double* s, double mu, double delta, double (*K)[8], double (*Kvx)[4], double* q, double* t) {
+  const double ax[4] = {1.0, 0.0, -1.0, 0.0}, ay[4] = {0.0, 1.0, 0.0, -1.0};  // rows of A_o
+  TT_UNROLL
+  for (int r = 0; r < 4; r++) t[r] = sb.D[r] * (e.d[r] - s[r]) + mu * sb.gs1[r];
+  TT_UNROLL
+  for (int i = 0; i < 8; i++) {
+    const double rv = tt_rcp(v[i] - o.v_lo);
+    TT_UNROLL
+    for (int j = 0; j <= i; j++) {
+      double a = 0.0;
+      TT_UNROLL
+      for (int r = 0; r < 4; r++) a += sb.D[r] * e.Jv[r][i] * e.Jv[r][j];
+      if (i >= 4 && j >= 4) {
+        const int ii = i - 4, jj = j - 4;
+        a += ax[ii] * (e.Wll[0] * ax[jj] + e.Wll[1] * ay[jj]) + ay[ii] * (e.Wll[1] * ax[jj] + e.Wll[2] * ay[jj]);
+      }
+      K[i][j] = a;
+    }
+    K[i][i] += zv[i] * rv + delta;
+    double qq = -mu * rv;
+    TT_UNROLL
+    for (int r = 0; r < 4; r++) qq += e.Jv[r][i] * t[r];
+    q[i] = qq;
+    TT_UNROLL
+    for (int c = 0; c < 4; c++) {
+      double a = 0.0;
+      TT_UNROLL
+      for (int r = 0; r < 4; r++) a += sb.D[r] * e.Jv[r][i] * e.Jx[r][c];
+      if (i >= 4) a += ax[i - 4] * e.Wxl[c][0] + ay[i - 4] * e.Wxl[c][1];
+      Kvx[i][c] = a;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-lane solver state
+// ------------------------------------------------------------------------------------------------
+struct Ctx {
+  const Params* p;
+  const ObParams* o;
+  double* s0;   // slot pointer (stage 0, row 0, this lane)
+  size_t sstride;  // doubles between stages
+  TT_HD double* stage(int k) const { return s0 + (size_t)k * sstride; }
+};
+TT_HD double* pair_ptr(double* ps, int j) { return ps + (size_t)(kBaseRows + kPairRows * j) * kBank; }
+
+TT_HD void dense_A(const Lin& m, double (*A)[NX]) {
+  TT_UNROLL
+  for (int i = 0; i < NX; i++) {
+    TT_UNROLL
+    for (int j = 0; j < NX; j++) A[i][j] = (i == j) ? 1.0 : 0.0;
+  }
+  A[0][2] = m.a02, A[0][5] = m.a05, A[1][2] = m.a12, A[1][5] = m.a15, A[2][4] = m.a24, A[2][5] = m.a25;
+  A[3][3] = m.a33, A[3][4] = m.a34, A[3][5] = m.a35;
+}
+
+TT_HD bool var_lo(const Params& p, int j) { return ((p.bl >> j) & 1u) != 0; }
+TT_HD bool var_up(const Params& p, int j) { return ((p.bu >> j) & 1u) != 0; }
+
+// ---- starting point (mpc_control_obs.py:216-239 + Ipopt's slack initialisation and interior push) ----
+TT_HD bool init_point(const Ctx& c, const ProblemIn& in, long long b) {
+  const Params& p = *c.p;
+  const ObParams& o = *c.o;
+  const int N = p.N;
+  bool x0_bad = false;
+  for (int k = 0; k <= N; k++) {
+    double* ps = c.stage(k);
+    double x[NX];
+    for (int j = 0; j < NW; j++) {
+      const bool on = (j < NX) || (k < N);
+      if (!on) continue;
+      const double r = ref_value(p, in, b, k, j);
+      str(ps, oREF + j, r);
+      double w;
+      if (j < NX && k == 0) {
+        w = in.x_init[b * NX + j];
+        if ((var_lo(p, j) && w < p.lo[j]) || (var_up(p, j) && w > p.up[j])) x0_bad = true;
+      } else {
+        w = tt_min(tt_max(r, p.lo_push[j]), p.up_push[j]);
+      }
+      str(ps, oW + j, w);
+      str(ps, oZL + j, 1.0);
+      str(ps, oZU + j, 1.0);
+      if (j < NX) x[j] = w;
+    }
+    for (int j = 0; j < NX; j++) str(ps, oLAM + j, 0.0);
+    Trig t;
+    stage_trig(x, t);
+    for (int pj = 0; pj < o.P; pj++) {
+      double* pp = pair_ptr(ps, pj);
+      double v[8], d[4];
+      for (int i = 0; i < 4; i++) v[i] = tt_max(o.mu_guess, o.v_push), v[4 + i] = tt_max(o.lam_guess[i], o.v_push);
+      pair_rows(o, pj & 1, o.b[pj], t, v, d);
+      for (int i = 0; i < 8; i++) str(pp, qV + i, v[i]), str(pp, qZV + i, 1.0);
+      str(pp, qS + 0, tt_min(d[0], o.s_up_push));
+      str(pp, qS + 1, tt_min(tt_max(d[1], o.c2_lo_push), o.c2_up_push));
+      str(pp, qS + 2, tt_min(tt_max(d[2], o.c2_lo_push), o.c2_up_push));
+      str(pp, qS + 3, tt_min(d[3], o.s_up_push));
+      for (int i = 0; i < 4; i++) str(pp, qY + i, 0.0);
+      for (int i = 0; i < 6; i++) str(pp, qZS + i, 1.0);
+    }
+  }
+  return x0_bad;
+}
+
+TT_HD double clampz(double z, double rs, double hi, double lo) { return tt_max(tt_min(z, hi * rs), lo * rs); }
+
+// ---- sweep 1: apply the accepted step (optional) and gather the KKT statistics at the resulting iterate ----
+TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha_du, double mu_step, double delta_step,
+                        Stats& st) {
+  const Params& p = *c.p;
+  const ObParams& o = *c.o;
+  const int N = p.N;
+  double J = 0.0, sumlog = 0.0, theta = 0.0, cinf = 0.0, rd_inf = 0.0, lam1 = 0.0, z1 = 0.0, cmax = 0.0, cmin = INFINITY;
+  const double khi = kKappaSigma * mu_step, klo = mu_step / kKappaSigma;
+  double xn[NX], ln[NX];  // x_{k+1}, lambda_{k+1} at the new iterate
+  for (int j = 0; j < NX; j++) xn[j] = ln[j] = 0.0;
+  for (int k = N; k >= 0; k--) {
+    double* ps = c.stage(k);
+    const bool has_x = k >= 1, has_u = k < N;
+    double w[NW], ref[NW], zl[NW], zu[NW], lam[NX];
+    for (int j = 0; j < NW; j++) {
+      const bool on = (j < NX) || has_u, var = (j < NX) ? has_x : has_u;
+      w[j] = on ? ldr(ps, oW + j) : 0.0;
+      ref[j] = on ? ldr(ps, oREF + j) : 0.0;
+      zl[j] = (var && var_lo(p, j)) ? ldr(ps, oZL + j) : 0.0;
+      zu[j] = (var && var_up(p, j)) ? ldr(ps, oZU + j) : 0.0;
+      if (do_update && var) {
+        const double d = ldr(ps, oDW + j);
+        if (var_lo(p, j)) {
+          const double rl = tt_rcp(w[j] - p.lo[j]);
+          zl[j] += alpha_du * (rl * (mu_step - zl[j] * d) - zl[j]);
+        }
+        if (var_up(p, j)) {
+          const double ru = tt_rcp(p.up[j] - w[j]);
+          zu[j] += alpha_du * (ru * (mu_step + zu[j] * d) - zu[j]);
+        }
+        w[j] += alpha * d;
+        if (var_lo(p, j)) zl[j] = clampz(zl[j], tt_rcp(w[j] - p.lo[j]), khi, klo);
+        if (var_up(p, j)) zu[j] = clampz(zu[j], tt_rcp(p.up[j] - w[j]), khi, klo);
+        str(ps, oW + j, w[j]);
+        if (var_lo(p, j)) str(ps, oZL + j, zl[j]);
+        if (var_up(p, j)) str(ps, oZU + j, zu[j]);
+      }
+    }
+    for (int j = 0; j < NX; j++) {
+      lam[j] = has_x ? ldr(ps, oLAM + j) : 0.0;
+      if (do_update && has_x) {
+        lam[j] += alpha * (ldr(ps, oLAMP + j) - lam[j]);
+        str(ps, oLAM + j, lam[j]);
+      }
+    }
+    // gradient of the Lagrangian wrt (x_k, u_k), without the pair terms yet
+    double r[NW];
+    {
+      double d6[NX];
+      for (int i = 0; i < NX; i++) d6[i] = w[i] - ref[i];
+      for (int i = 0; i < NX; i++) {
+        double s = 0.0;
+        for (int j = 0; j < NX; j++) s += p.Q2[SY(i, j)] * d6[j];
+        r[i] = s;
+        J += 0.5 * s * d6[i];
+      }
+      if (has_u) {
+        const double da = w[6] - ref[6], dw_ = w[7] - ref[7];
+        r[6] = p.R2[0] * da + p.R2[1] * dw_;
+        r[7] = p.R2[1] * da + p.R2[2] * dw_;
+        J += 0.5 * (r[6] * da + r[7] * dw_);
+      } else {
+        r[6] = r[7] = 0.0;
+      }
+    }
+    double prod = 1.0;
+    for (int j = 0; j < NW; j++) {
+      const bool var = (j < NX) ? has_x : has_u;
+      if (var && var_lo(p, j)) {
+        const double sl = w[j] - p.lo[j], cc = sl * zl[j];
+        prod *= sl, z1 += zl[j], cmax = tt_max(cmax, cc), cmin = tt_min(cmin, cc);
+        r[j] -= zl[j];
+      }
+      if (var && var_up(p, j)) {
+        const double su = p.up[j] - w[j], cc = su * zu[j];
+        prod *= su, z1 += zu[j], cmax = tt_max(cmax, cc), cmin = tt_min(cmin, cc);
+        r[j] += zu[j];
+      }
+    }
+    sumlog += log(prod);  // one logarithm per stage / per pair: the slacks are O(1e-9 .. 1e2), no under/overflow
+    if (has_x)
+      for (int j = 0; j < NX; j++) r[j] += lam[j], lam1 += fabs(lam[j]);
+    if (has_u) {  // defect c_{k+1} and -[A B]' lambda_{k+1}
+      Lin m;
+      stage_lin(p, w, m);
+      const double f[NX] = {m.f0, m.f1, m.f2, m.f3, w[7], w[6]};
+      for (int j = 0; j < NX; j++) {
+        const double ck = xn[j] - w[j] - p.dt * f[j];
+        theta += fabs(ck);
+        cinf = tt_max(cinf, fabs(ck));
+      }
+      double al[NX];
+      At_mul(m, ln, al);
+      for (int j = 0; j < NX; j++) r[j] -= al[j];
+      r[6] -= p.dt * ln[5];
+      r[7] -= p.dt * ln[4];
+    }
+    // pairs
+    Trig t;
+    stage_trig(w, t);
+    for (int pj = 0; pj < o.P; pj++) {
+      double* pp = pair_ptr(ps, pj);
+      double v[8], zv[8], s[4], y[4], zs[6];
+      for (int i = 0; i < 8; i++) v[i] = ldr(pp, qV + i), zv[i] = ldr(pp, qZV + i);
+      for (int i = 0; i < 4; i++) s[i] = ldr(pp, qS + i), y[i] = ldr(pp, qY + i);
+      for (int i = 0; i < 6; i++) zs[i] = ldr(pp, qZS + i);
+      if (do_update) {
+        double ds[4];
+        for (int i = 0; i < 4; i++) ds[i] = ldr(pp, qDS + i);
+        SlackBar sb;
+        slack_bar(o, s, zs, delta_step, sb);
+        for (int i = 0; i < 4; i++) y[i] += alpha * (sb.D[i] * ds[i] + mu_step * sb.gs1[i] - y[i]);  // y+ = D ds + gs
+        // slack multipliers: [d0 up, d1 lo, d1 up, d2 lo, d2 up, d3 up]
+        const int row[6] = {0, 1, 1, 2, 2, 3};
+        const bool upper[6] = {true, false, true, false, true, true};
+        for (int i = 0; i < 6; i++) {
+          const double bd = upper[i] ? ((row[i] == 0 || row[i] == 3) ? o.s_up : o.c2_up) : o.c2_lo;
+          const double dist = upper[i] ? bd - s[row[i]] : s[row[i]] - bd;
+          const double rr = tt_rcp(dist), dd = upper[i] ? ds[row[i]] : -ds[row[i]];
+          zs[i] += alpha_du * (rr * (mu_step + zs[i] * dd) - zs[i]);
+        }
+        for (int i = 0; i < 8; i++) {
+          const double d = ldr(pp, qDV + i), rl = tt_rcp(v[i] - o.v_lo);
+          zv[i] += alpha_du * (rl * (mu_step - zv[i] * d) - zv[i]);
+          v[i] += alpha * d;
+          zv[i] = clampz(zv[i], tt_rcp(v[i] - o.v_lo), khi, klo);
+          str(pp, qV + i, v[i]), str(pp, qZV + i, zv[i]);
+        }
+        for (int i = 0; i < 4; i++) {
+          s[i] += alpha * ds[i];
+          str(pp, qS + i, s[i]), str(pp, qY + i, y[i]);
+        }
+        for (int i = 0; i < 6; i++) {
+          const double bd = upper[i] ? ((row[i] == 0 || row[i] == 3) ? o.s_up : o.c2_up) : o.c2_lo;
+          const double dist = upper[i] ? bd - s[row[i]] : s[row[i]] - bd;
+          zs[i] = clampz(zs[i], tt_rcp(dist), khi, klo);
+          str(pp, qZS + i, zs[i]);
+        }
+      }
+      PairEval e;
+      pair_eval(o, pj & 1, o.b[pj], t, v, y, e);
+      for (int i = 0; i < 4; i++) {
+        const double rc = e.d[i] - s[i];
+        theta += fabs(rc);
+        cinf = tt_max(cinf, fabs(rc));
+        lam1 += fabs(y[i]);
+        if (has_x)
+          for (int cc = 0; cc < 4; cc++) r[cc] += e.Jx[i][cc] * y[i];
+      }
+      double pprod = 1.0;
+      for (int i = 0; i < 8; i++) {
+        double rv = -zv[i];
+        for (int rr = 0; rr < 4; rr++) rv += e.Jv[rr][i] * y[rr];
+        rd_inf = tt_max(rd_inf, fabs(rv));
+        const double sl = v[i] - o.v_lo, cc = sl * zv[i];
+        pprod *= sl, z1 += zv[i], cmax = tt_max(cmax, cc), cmin = tt_min(cmin, cc);
+      }
+      sumlog += log(pprod);
+      {
+        const double dist[6] = {o.s_up - s[0], s[1] - o.c2_lo, o.c2_up - s[1], s[2] - o.c2_lo, o.c2_up - s[2], o.s_up - s[3]};
+        double sprod = 1.0;
+        for (int i = 0; i < 6; i++) {
+          const double cc = dist[i] * zs[i];
+          sprod *= dist[i], z1 += zs[i], cmax = tt_max(cmax, cc), cmin = tt_min(cmin, cc);
+        }
+        sumlog += log(sprod);
+        rd_inf = tt_max(rd_inf, fabs(-y[0] + zs[0]));
+        rd_inf = tt_max(rd_inf, fabs(-y[1] - zs[1] + zs[2]));
+        rd_inf = tt_max(rd_inf, fabs(-y[2] - zs[3] + zs[4]));
+        rd_inf = tt_max(rd_inf, fabs(-y[3] + zs[5]));
+      }
+    }
+    for (int j = 0; j < NW; j++) {
+      const bool var = (j < NX) ? has_x : has_u;
+      if (var) rd_inf = tt_max(rd_inf, fabs(r[j]));
+    }
+    for (int j = 0; j < NX; j++) xn[j] = w[j], ln[j] = lam[j];
+  }
+  st.J = J, st.sumlog = sumlog, st.theta = theta, st.cinf = cinf, st.rd_inf = rd_inf, st.lam1 = lam1, st.z1 = z1;
+  st.cmax = cmax, st.cmin = cmin;
+}
+
+// ---- sweep 2 (backward): condensation of the pairs + Riccati factorisation.  false: wrong inertia ----
+TT_HD bool factor(const Ctx& c, double mu, double delta) {
+  const Params& p = *c.p;
+  const ObParams& o = *c.o;
+  const int N = p.N;
+  const double dt = p.dt;
+  double Pn[NX][NX], pn[NX], xn[NX], ln[NX];
+  for (int i = 0; i < NX; i++) {
+    pn[i] = xn[i] = ln[i] = 0.0;
+    for (int j = 0; j < NX; j++) Pn[i][j] = 0.0;
+  }
+  for (int k = N; k >= 0; k--) {
+    double* ps = c.stage(k);
+    const bool has_x = k >= 1, has_u = k < N;
+    double w[NW], g[NW], sig[NW];
+    {
+      double ref[NW];
+      for (int j = 0; j < NW; j++) {
+        const bool on = (j < NX) || has_u;
+        w[j] = on ? ldr(ps, oW + j) : 0.0;
+        ref[j] = on ? ldr(ps, oREF + j) : 0.0;
+      }
+      for (int i = 0; i < NX; i++) {
+        double s = 0.0;
+        for (int j = 0; j < NX; j++) s += p.Q2[SY(i, j)] * (w[j] - ref[j]);
+        g[i] = s;
+      }
+      g[6] = p.R2[0] * (w[6] - ref[6]) + p.R2[1] * (w[7] - ref[7]);
+      g[7] = p.R2[1] * (w[6] - ref[6]) + p.R2[2] * (w[7] - ref[7]);
+    }
+    for (int j = 0; j < NW; j++) {
+      const bool var = (j < NX) ? has_x : has_u;
+      sig[j] = delta;
+      if (var && var_lo(p, j)) {
+        const double rl = tt_rcp(w[j] - p.lo[j]);
+        sig[j] += ldr(ps, oZL + j) * rl;
+        g[j] -= mu * rl;
+      }
+      if (var && var_up(p, j)) {
+        const double ru = tt_rcp(p.up[j] - w[j]);
+        sig[j] += ldr(ps, oZU + j) * ru;
+        g[j] += mu * ru;
+      }
+    }
+    // ---- pairs: Schur complement onto (x, y, theta, psi) ----
+    double Hadd[4][4], gadd[4];
+    for (int i = 0; i < 4; i++) {
+      gadd[i] = 0.0;
+      for (int j = 0; j < 4; j++) Hadd[i][j] = 0.0;
+    }
+    bool ok = true;
+    Trig t;
+    stage_trig(w, t);
+    for (int pj = 0; pj < o.P; pj++) {
+      double* pp = pair_ptr(ps, pj);
+      double v[8], zv[8], s[4], y[4], zs[6];
+      for (int i = 0; i < 8; i++) v[i] = ldr(pp, qV + i), zv[i] = ldr(pp, qZV + i);
+      for (int i = 0; i < 4; i++) s[i] = ldr(pp, qS + i), y[i] = ldr(pp, qY + i);
+      for (int i = 0; i < 6; i++) zs[i] = ldr(pp, qZS + i);
+      PairEval e;
+      pair_eval(o, pj & 1, o.b[pj], t, v, y, e);
+      SlackBar sb;
+      slack_bar(o, s, zs, delta, sb);
+      double K[8][8], Kvx[8][4], q[8], tt[4];
+      pair_system(o, e, sb, v, zv, s, mu, delta, K, Kvx, q, tt);
+      if (!chol8(K)) ok = false;
+      if (!has_x) continue;  // x_0 is data: the pair only has to have the right inertia
+      fsub8(K, q);
+      double col[4][8];
+      for (int cc = 0; cc < 4; cc++) {
+        for (int i = 0; i < 8; i++) col[cc][i] = Kvx[i][cc];
+        fsub8(K, col[cc]);
+      }
+      for (int a = 0; a < 4; a++) {
+        double ga = 0.0;
+        for (int r = 0; r < 4; r++) ga += e.Jx[r][a] * tt[r];
+        for (int i = 0; i < 8; i++) ga -= col[a][i] * q[i];
+        gadd[a] += ga;
+        for (int bb = 0; bb < 4; bb++) {
+          double h = 0.0;
+          for (int r = 0; r < 4; r++) h += sb.D[r] * e.Jx[r][a] * e.Jx[r][bb];
+          for (int i = 0; i < 8; i++) h -= col[a][i] * col[bb][i];
+          Hadd[a][bb] += h;
+        }
+      }
+      Hadd[2][2] += e.hthth;
+      Hadd[2][3] += e.hthps, Hadd[3][2] += e.hthps;
+      Hadd[3][3] += e.hthps;
+    }
+    if (!ok) return false;
+    if (k == N) {
+      for (int i = 0; i < NX; i++) {
+        for (int j = 0; j < NX; j++) Pn[i][j] = p.Q2[SY(i, j)] + ((i < 4 && j < 4) ? Hadd[i][j] : 0.0);
+        Pn[i][i] += sig[i];
+        pn[i] = g[i] + (i < 4 ? gadd[i] : 0.0);
+      }
+    } else {
+      Lin m;
+      stage_lin(p, w, m);
+      double A[NX][NX];
+      dense_A(m, A);
+      const double f[NX] = {m.f0, m.f1, m.f2, m.f3, w[7], w[6]};
+      double h[NX], cdef[NX];
+      for (int i = 0; i < NX; i++) cdef[i] = xn[i] - w[i] - dt * f[i];
+      for (int i = 0; i < NX; i++) {
+        double s = pn[i];
+        for (int j = 0; j < NX; j++) s -= Pn[i][j] * cdef[j];
+        h[i] = s;
+      }
+      double PA[NX][NX];
+      for (int i = 0; i < NX; i++)
+        for (int j = 0; j < NX; j++) {
+          double s = 0.0;
+          for (int l = 0; l < NX; l++) s += Pn[i][l] * A[l][j];
+          PA[i][j] = s;
+        }
+      // B has two entries: B[5][0] = B[4][1] = dt
+      const double r00 = p.R2[0] + dt * dt * Pn[5][5] + sig[6], r01 = p.R2[1] + dt * dt * Pn[5][4];
+      const double r11 = p.R2[2] + dt * dt * Pn[4][4] + sig[7];
+      const double det = r00 * r11 - r01 * r01;
+      if (!(r00 > 0.0) || !(det > 0.0)) return false;
+      const double idet = tt_rcp(det);
+      const double i00 = r11 * idet, i01 = -r01 * idet, i11 = r00 * idet;
+      double Sh[NU][NX], Kf[NU][NX], kff[NU];
+      for (int j = 0; j < NX; j++) {
+        Sh[0][j] = dt * PA[5][j];
+        Sh[1][j] = dt * PA[4][j];
+        Kf[0][j] = i00 * Sh[0][j] + i01 * Sh[1][j];
+        Kf[1][j] = i01 * Sh[0][j] + i11 * Sh[1][j];
+      }
+      const double bh0 = g[6] + dt * h[5], bh1 = g[7] + dt * h[4];
+      kff[0] = i00 * bh0 + i01 * bh1;
+      kff[1] = i01 * bh0 + i11 * bh1;
+      for (int j = 0; j < NX; j++) str(ps, oK + j, Kf[0][j]), str(ps, oK + NX + j, Kf[1][j]);
+      str(ps, oKFF, kff[0]), str(ps, oKFF + 1, kff[1]);
+      if (has_x) {
+        Hes ho;
+        stage_hess(p, m, ln, ho);
+        double Hx[NX][NX];
+        for (int i = 0; i < NX; i++) {
+          for (int j = 0; j < NX; j++) Hx[i][j] = p.Q2[SY(i, j)] + ((i < 4 && j < 4) ? Hadd[i][j] : 0.0);
+          Hx[i][i] += sig[i];
+        }
+        Hx[2][2] += ho.h22, Hx[2][5] += ho.h25, Hx[5][2] += ho.h25;
+        Hx[3][3] += ho.h33, Hx[3][4] += ho.h34, Hx[4][3] += ho.h34, Hx[3][5] += ho.h35, Hx[5][3] += ho.h35;
+        Hx[4][4] += ho.h44, Hx[4][5] += ho.h45, Hx[5][4] += ho.h45;
+        double Pk[NX][NX], pk[NX];
+        for (int i = 0; i < NX; i++) {
+          for (int j = 0; j < NX; j++) {
+            double s = Hx[i][j];
+            for (int l = 0; l < NX; l++) s += A[l][i] * PA[l][j];
+            s -= Sh[0][i] * Kf[0][j] + Sh[1][i] * Kf[1][j];
+            Pk[i][j] = s;
+          }
+          double s = g[i] + (i < 4 ? gadd[i] : 0.0);
+          for (int l = 0; l < NX; l++) s += A[l][i] * h[l];
+          s -= Sh[0][i] * kff[0] + Sh[1][i] * kff[1];
+          pk[i] = s;
+        }
+        for (int i = 0; i < NX; i++) {
+          pn[i] = pk[i];
+          for (int j = 0; j < NX; j++) Pn[i][j] = 0.5 * (Pk[i][j] + Pk[j][i]);
+        }
+      }
+    }
+    if (has_x) {
+      for (int i = 0; i < NX; i++) {
+        str(ps, oPV + i, pn[i]);
+        for (int j = i; j < NX; j++) str(ps, oP + SY(i, j), Pn[i][j]);
+      }
+      for (int i = 0; i < NX; i++) xn[i] = w[i], ln[i] = ldr(ps, oLAM + i);
+    }
+  }
+  return true;
+}
+
+// ---- sweep 3 (forward): search direction, fraction-to-boundary step sizes, grad(phi)'d ----
+struct Dir {
+  double a_pr, a_du, gphi_d;
+};
+TT_HD void limit_lo(double dist, double d, double z, double mu, double tau, Dir& di) {  // variable with slack `dist` to a lower bound
+  const double r = tt_rcp(dist);
+  if (d < 0.0) di.a_pr = tt_min(di.a_pr, -tau * dist * tt_rcp(d));
+  const double dz = r * (mu - z * d) - z;
+  if (dz < 0.0) di.a_du = tt_min(di.a_du, -tau * z * tt_rcp(dz));
+}
+TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di) {
+  const Params& p = *c.p;
+  const ObParams& o = *c.o;
+  const int N = p.N;
+  di.a_pr = di.a_du = 1.0;
+  di.gphi_d = 0.0;
+  double dx[NX];
+  for (int i = 0; i < NX; i++) dx[i] = 0.0;
+  for (int k = 0; k <= N; k++) {
+    double* ps = c.stage(k);
+    const bool has_x = k >= 1, has_u = k < N;
+    double w[NW], g[NW];
+    {
+      double ref[NW];
+      for (int j = 0; j < NW; j++) {
+        const bool on = (j < NX) || has_u;
+        w[j] = on ? ldr(ps, oW + j) : 0.0;
+        ref[j] = on ? ldr(ps, oREF + j) : 0.0;
+      }
+      for (int i = 0; i < NX; i++) {
+        double s = 0.0;
+        for (int j = 0; j < NX; j++) s += p.Q2[SY(i, j)] * (w[j] - ref[j]);
+        g[i] = s;
+      }
+      g[6] = p.R2[0] * (w[6] - ref[6]) + p.R2[1] * (w[7] - ref[7]);
+      g[7] = p.R2[1] * (w[6] - ref[6]) + p.R2[2] * (w[7] - ref[7]);
+    }
+    double dw[NW];
+    for (int j = 0; j < NX; j++) dw[j] = dx[j];
+    dw[6] = dw[7] = 0.0;
+    if (has_u) {
+      for (int i = 0; i < NU; i++) {
+        double s = -ldr(ps, oKFF + i);
+        for (int j = 0; j < NX; j++) s -= ldr(ps, oK + i * NX + j) * dx[j];
+        dw[NX + i] = s;
+      }
+    }
+    for (int j = 0; j < NW; j++) {
+      const bool var = (j < NX) ? has_x : has_u;
+      if (!var) continue;
+      str(ps, oDW + j, dw[j]);
+      double gb = g[j];
+      if (var_lo(p, j)) {
+        const double dist = w[j] - p.lo[j];
+        gb -= mu * tt_rcp(dist);
+        limit_lo(dist, dw[j], ldr(ps, oZL + j), mu, tau, di);
+      }
+      if (var_up(p, j)) {
+        const double dist = p.up[j] - w[j];
+        gb += mu * tt_rcp(dist);
+        limit_lo(dist, -dw[j], ldr(ps, oZU + j), mu, tau, di);
+      }
+      di.gphi_d += gb * dw[j];
+    }
+    // pairs: dv = -K_vv^-1 (q + K_vx dxt),  ds = J_x dxt + J_v dv + r_c
+    Trig t;
+    stage_trig(w, t);
+    for (int pj = 0; pj < o.P; pj++) {
+      double* pp = pair_ptr(ps, pj);
+      double v[8], zv[8], s[4], y[4], zs[6];
+      for (int i = 0; i < 8; i++) v[i] = ldr(pp, qV + i), zv[i] = ldr(pp, qZV + i);
+      for (int i = 0; i < 4; i++) s[i] = ldr(pp, qS + i), y[i] = ldr(pp, qY + i);
+      for (int i = 0; i < 6; i++) zs[i] = ldr(pp, qZS + i);
+      PairEval e;
+      pair_eval(o, pj & 1, o.b[pj], t, v, y, e);
+      SlackBar sb;
+      slack_bar(o, s, zs, delta, sb);
+      double K[8][8], Kvx[8][4], q[8], tt[4];
+      pair_system(o, e, sb, v, zv, s, mu, delta, K, Kvx, q, tt);
+      chol8(K);
+      double dv[8];
+      for (int i = 0; i < 8; i++) {
+        double a = q[i];
+        for (int cc = 0; cc < 4; cc++) a += Kvx[i][cc] * dx[cc];
+        dv[i] = -a;
+      }
+      fsub8(K, dv);
+      bsub8(K, dv);
+      double ds[4];
+      for (int r = 0; r < 4; r++) {
+        double a = e.d[r] - s[r];
+        for (int cc = 0; cc < 4; cc++) a += e.Jx[r][cc] * dx[cc];
+        for (int i = 0; i < 8; i++) a += e.Jv[r][i] * dv[i];
+        ds[r] = a;
+        str(pp, qDS + r, a);
+        di.gphi_d += mu * sb.gs1[r] * a;
+      }
+      for (int i = 0; i < 8; i++) {
+        str(pp, qDV + i, dv[i]);
+        const double dist = v[i] - o.v_lo;
+        di.gphi_d -= mu * tt_rcp(dist) * dv[i];
+        limit_lo(dist, dv[i], zv[i], mu, tau, di);
+      }
+      limit_lo(o.s_up - s[0], -ds[0], zs[0], mu, tau, di);
+      limit_lo(s[1] - o.c2_lo, ds[1], zs[1], mu, tau, di);
+      limit_lo(o.c2_up - s[1], -ds[1], zs[2], mu, tau, di);
+      limit_lo(s[2] - o.c2_lo, ds[2], zs[3], mu, tau, di);
+      limit_lo(o.c2_up - s[2], -ds[2], zs[4], mu, tau, di);
+      limit_lo(o.s_up - s[3], -ds[3], zs[5], mu, tau, di);
+    }
+    if (has_u) {  // dx_{k+1} = A dx + B du - c_{k+1};  lambda+_{k+1} = -(p_{k+1} + P_{k+1} dx_{k+1})
+      double* pq = c.stage(k + 1);
+      Lin m;
+      stage_lin(p, w, m);
+      const double f[NX] = {m.f0, m.f1, m.f2, m.f3, w[7], w[6]};
+      double nd[NX];
+      A_mul(m, dx, nd);
+      nd[4] += p.dt * dw[7];
+      nd[5] += p.dt * dw[6];
+      for (int i = 0; i < NX; i++) nd[i] -= ldr(pq, oW + i) - w[i] - p.dt * f[i];
+      for (int i = 0; i < NX; i++) {
+        double s = ldr(pq, oPV + i);
+        for (int j = 0; j < NX; j++) s += ldr(pq, oP + SY(i, j)) * nd[j];
+        str(pq, oLAMP + i, -s);
+      }
+      for (int i = 0; i < NX; i++) dx[i] = nd[i];
+    }
+  }
+}
+
+// ---- sweep 4: theta and phi at the trial point w + alpha*dw ----
+struct TrialOut {
+  double J, sumlog, theta;
+  bool inside;  // every bounded quantity strictly inside its bounds
+};
+TT_HD void trial(const Ctx& c, double alpha, TrialOut& tr) {
+  const Params& p = *c.p;
+  const ObParams& o = *c.o;
+  const int N = p.N;
+  double J = 0.0, sumlog = 0.0, theta = 0.0;
+  bool inside = true;
+  double xn[NX];
+  for (int i = 0; i < NX; i++) xn[i] = 0.0;
+  for (int k = N; k >= 0; k--) {
+    double* ps = c.stage(k);
+    const bool has_x = k >= 1, has_u = k < N;
+    double w[NW];
+    for (int j = 0; j < NW; j++) {
+      const bool on = (j < NX) || has_u, var = (j < NX) ? has_x : has_u;
+      w[j] = on ? ldr(ps, oW + j) : 0.0;
+      if (var) w[j] += alpha * ldr(ps, oDW + j);
+    }
+    {
+      double d6[NX];
+      for (int i = 0; i < NX; i++) d6[i] = w[i] - ldr(ps, oREF + i);
+      for (int i = 0; i < NX; i++) {
+        double s = 0.0;
+        for (int j = 0; j < NX; j++) s += p.Q2[SY(i, j)] * d6[j];
+        J += 0.5 * s * d6[i];
+      }
+      if (has_u) {
+        const double da = w[6] - ldr(ps, oREF + 6), dw_ = w[7] - ldr(ps, oREF + 7);
+        J += 0.5 * (da * (p.R2[0] * da + p.R2[1] * dw_) + dw_ * (p.R2[1] * da + p.R2[2] * dw_));
+      }
+    }
+    double prod = 1.0;
+    for (int j = 0; j < NW; j++) {
+      const bool var = (j < NX) ? has_x : has_u;
+      if (var && var_lo(p, j)) {
+        const double sl = w[j] - p.lo[j];
+        if (!(sl > 0.0)) inside = false;
+        prod *= sl;
+      }
+      if (var && var_up(p, j)) {
+        const double su = p.up[j] - w[j];
+        if (!(su > 0.0)) inside = false;
+        prod *= su;
+      }
+    }
+    sumlog += log(prod);
+    if (has_u) {
+      double f[4];
+      stage_f(p, w, f);
+      const double ff[NX] = {f[0], f[1], f[2], f[3], w[7], w[6]};
+      for (int j = 0; j < NX; j++) theta += fabs(xn[j] - w[j] - p.dt * ff[j]);
+    }
+    Trig t;
+    stage_trig(w, t);
+    for (int pj = 0; pj < o.P; pj++) {
+      const double* pp = pair_ptr(ps, pj);
+      double v[8], s[4], d[4];
+      double pprod = 1.0;
+      for (int i = 0; i < 8; i++) {
+        v[i] = ldr(pp, qV + i) + alpha * ldr(pp, qDV + i);
+        const double sl = v[i] - o.v_lo;
+        if (!(sl > 0.0)) inside = false;
+        pprod *= sl;
+      }
+      for (int i = 0; i < 4; i++) s[i] = ldr(pp, qS + i) + alpha * ldr(pp, qDS + i);
+      pair_rows(o, pj & 1, o.b[pj], t, v, d);
+      for (int i = 0; i < 4; i++) theta += fabs(d[i] - s[i]);
+      const double dist[6] = {o.s_up - s[0], s[1] - o.c2_lo, o.c2_up - s[1], s[2] - o.c2_lo, o.c2_up - s[2], o.s_up - s[3]};
+      for (int i = 0; i < 6; i++) {
+        if (!(dist[i] > 0.0)) inside = false;
+        pprod *= dist[i];
+      }
+      sumlog += log(pprod);
+    }
+    for (int j = 0; j < NX; j++) xn[j] = w[j];
+  }
+  tr.J = J, tr.sumlog = sumlog, tr.theta = theta, tr.inside = inside;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the interior-point driver of one lane (same rules as ttmpc_core.cuh's ipm_backward / ipm_step), written as a state
+// machine so that the CUDA kernel can keep the 32 lanes of a warp in the same sweep although their problems are at
+// different iterations:  head (update_stats + termination tests + barrier update)  ->  factor_once until the inertia
+// is right  ->  direction  ->  trial_once until a step is accepted.
+// ------------------------------------------------------------------------------------------------
+struct Lane {
+  double mu, tau, theta_max, theta_min, delta_last, delta;
+  double alpha, alpha_du, mu_step, delta_step;
+  double f_theta[kFilterMax], f_phi[kFilterMax];
+  double theta, phi, lam1;       // at the current iterate (line-search reference)
+  double ls_a;                   // current trial step
+  Dir di;
+  Stats st;
+  int f_n, acc_count, ls_fail, iter, attempt, bt, n_b, m_eq;
+  bool do_update, x0_bad, need_factor, need_dir, need_trial;
+};
+
+TT_HD void lane_begin(const Params& p, const ObParams& o, bool x0_bad, Lane& L) {
+  L.mu = p.mu_init;
+  L.tau = fmax(kTauMin, 1.0 - L.mu);
+  L.theta_max = L.theta_min = L.delta_last = L.delta = 0.0;
+  L.alpha = L.alpha_du = 0.0;
+  L.mu_step = L.mu;
+  L.delta_step = 0.0;
+  L.f_n = L.acc_count = L.ls_fail = L.iter = L.attempt = L.bt = 0;
+  L.n_b = p.n_b + (p.N + 1) * o.P * 14;  // + 8 local variables and 6 slack bounds per pair
+  L.m_eq = p.m_eq + (p.N + 1) * o.P * 4;
+  L.do_update = false;
+  L.x0_bad = x0_bad;
+  L.need_factor = L.need_dir = L.need_trial = false;
+}
+
+TT_HD void lane_result(const Lane& L, int status, Result& res) {
+  if (L.x0_bad && status >= ST_MAX_ITER) status = ST_INFEASIBLE_X0;
+  res.obj = L.st.J, res.dual_inf = L.st.rd_inf, res.constr_viol = L.st.cinf, res.compl_inf = L.st.cmax;
+  res.iters = L.iter, res.status = status;
+}
+
+// head of an iteration; true when the lane is finished (res filled in)
+TT_HD bool lane_head(const Ctx& c, Lane& L, Result& res) {
+  const Params& p = *c.p;
+  Stats& st = L.st;
+  update_stats(c, L.do_update, L.alpha, L.alpha_du, L.mu_step, L.delta_step, st);
+  if (!(tt_finite(st.J) && tt_finite(st.sumlog) && tt_finite(st.theta) && tt_finite(st.rd_inf))) {
+    lane_result(L, ST_NUMERIC, res);
+    return true;
+  }
+  if (L.iter == 0) {
+    L.theta_max = kThetaMaxFact * fmax(1.0, st.theta);
+    L.theta_min = kThetaMinFact * fmax(1.0, st.theta);
+  }
+  const double s_d = fmax(kSMax, (st.lam1 + st.z1) / (double)(L.m_eq + L.n_b)) / kSMax;
+  const double s_c = fmax(kSMax, st.z1 / (double)L.n_b) / kSMax;
+  const double e_dc = fmax(st.rd_inf / s_d, st.cinf);
+  const double E0 = fmax(e_dc, fmax(st.cmax, -st.cmin) / s_c);
+  if (E0 <= p.tol && st.rd_inf <= kDualInfTol && st.cinf <= kConstrViolTol && st.cmax <= kComplInfTol) {
+    lane_result(L, ST_CONVERGED, res);
+    return true;
+  }
+  if (E0 <= p.acc_tol && st.rd_inf <= kAccDualInfTol && st.cinf <= kAccConstrViolTol && st.cmax <= kAccComplInfTol)
+    L.acc_count++;
+  else
+    L.acc_count = 0;
+  if (p.acc_iter > 0 && L.acc_count >= p.acc_iter) {
+    lane_result(L, ST_ACCEPTABLE, res);
+    return true;
+  }
+  if (L.iter >= p.max_iter) {
+    lane_result(L, ST_MAX_ITER, res);
+    return true;
+  }
+  if (L.x0_bad && L.iter >= kX0InfeasibleIters) {
+    lane_result(L, ST_INFEASIBLE_X0, res);
+    return true;
+  }
+  while (L.mu > p.mu_floor && fmax(e_dc, fmax(st.cmax - L.mu, L.mu - st.cmin) / s_c) <= kKappaEps * L.mu) {
+    L.mu = fmax(p.mu_floor, fmin(kKappaMu * L.mu, L.mu * sqrt(L.mu)));  // mu^1.5
+    L.tau = fmax(kTauMin, 1.0 - L.mu);
+    L.f_n = 0;
+  }
+  L.theta = st.theta;
+  L.phi = st.J - L.mu * st.sumlog;
+  L.lam1 = st.lam1;
+  L.delta = 0.0;
+  L.attempt = 0;
+  L.need_factor = true;
+  return false;
+}
+
+// one factorisation attempt; true when the lane is finished (no usable regularisation)
+TT_HD bool lane_factor_once(const Ctx& c, Lane& L, Result& res) {
+  if (factor(c, L.mu, L.delta)) {
+    if (L.delta > 0.0) L.delta_last = L.delta;
+    L.need_factor = false;
+    L.need_dir = true;
+    return false;
+  }
+  if (++L.attempt >= 40) {
+    L.need_factor = false;
+    lane_result(L, ST_NUMERIC, res);
+    return true;
+  }
+  if (L.delta == 0.0)  // Ipopt's delta_w sequence: 1e-4 first, x100 / x8 growth, restart at last/3
+    L.delta = (L.delta_last == 0.0) ? 1e-4 : fmax(1e-20, L.delta_last / 3.0);
+  else
+    L.delta *= (L.delta_last == 0.0) ? 100.0 : 8.0;
+  return false;
+}
+
+TT_HD void lane_accept(Lane& L, double a) {
+  L.do_update = true;
+  L.alpha = a, L.alpha_du = L.di.a_du, L.mu_step = L.mu, L.delta_step = L.delta;
+  L.need_trial = false;
+  L.iter++;
+}
+
+TT_HD void lane_direction(const Ctx& c, Lane& L) {
+  const Params& p = *c.p;
+  direction(c, L.mu, L.tau, L.delta, L.di);
+  L.need_dir = false;
+  // round-off regime (see oracle/ttmpc_oracle.c): neither theta nor phi can be compared reliably -> full step
+  const bool roundoff = (L.theta <= 1e-2 * p.tol) &&
+                        (fabs(L.di.gphi_d) <= fmax(100.0 * kEps * fmax(1.0, fabs(L.phi)), L.theta * L.lam1));
+  if (roundoff) {
+    L.ls_fail = 0;
+    lane_accept(L, L.di.a_pr);
+    return;
+  }
+  L.ls_a = L.di.a_pr;
+  L.bt = 0;
+  L.need_trial = true;
+}
+
+// one line-search trial; true when the lane is finished (third consecutive line-search failure)
+TT_HD bool lane_trial_once(const Ctx& c, Lane& L, Result& res) {
+  const double a = L.ls_a, theta = L.theta, phi = L.phi, gd = L.di.gphi_d;
+  TrialOut tr;
+  trial(c, a, tr);
+  const double phi_t = tr.J - L.mu * tr.sumlog;
+  bool okstep = tr.inside && tt_finite(phi_t) && tt_finite(tr.theta) && tr.theta <= L.theta_max;
+  if (okstep)
+    for (int i = 0; i < L.f_n; i++)
+      if (tr.theta >= L.f_theta[i] && phi_t >= L.f_phi[i]) okstep = false;
+  bool ftype = false;
+  if (okstep) {
+    const bool switching = (gd < 0.0) && (a * pow(-gd, kSPhi) > kDeltaSw * pow(theta, kSTheta));
+    if (theta <= L.theta_min && switching) {
+      okstep = (phi_t - phi - 10.0 * kEps * fabs(phi) <= kEtaPhi * a * gd);
+      ftype = true;
+    } else {
+      okstep = (tr.theta - (1.0 - kGammaTheta) * theta <= 10.0 * kEps * fabs(theta)) ||
+               (phi_t - (phi - kGammaPhi * theta) <= 10.0 * kEps * fabs(phi));
+    }
+  }
+  if (okstep) {
+    if (!ftype) {  // filter augmentation; when full, an entry dominated by the new one (or the oldest) is overwritten
+      const double nt = (1.0 - kGammaTheta) * theta, np_ = phi - kGammaPhi * theta;
+      int slot = -1;
+      for (int i = 0; i < L.f_n; i++)
+        if (L.f_theta[i] >= nt && L.f_phi[i] >= np_) slot = i;
+      if (slot < 0) slot = (L.f_n < kFilterMax) ? L.f_n++ : 0;
+      L.f_theta[slot] = nt, L.f_phi[slot] = np_;
+    }
+    L.ls_fail = 0;
+    lane_accept(L, a);
+    return false;
+  }
+  if (++L.bt <= kMaxBacktrack) {
+    L.ls_a = a * kAlphaRed;
+    return false;
+  }
+  // Ipopt would switch to feasibility restoration here: take the shortest trial step, clear the filter, give up
+  // after 3 consecutive failures (same policy as oracle/ttmpc_oracle.c)
+  if (++L.ls_fail >= 3) {
+    L.need_trial = false;
+    lane_result(L, ST_LINESEARCH, res);
+    return true;
+  }
+  L.f_n = 0;
+  lane_accept(L, a);
+  return false;
+}
+
+// sequential driver (host emulation; the CUDA kernel interleaves the same phases across the lanes of a warp)
+TT_HD void solve_lane(const Params& p, const ObParams& o, double* s0, const ProblemIn& in, long long b, Result& res) {
+  Ctx c;
+  c.p = &p, c.o = &o, c.s0 = s0, c.sstride = (size_t)stage_rows(o.P) * kBank;
+  Lane L;
+  lane_begin(p, o, init_point(c, in, b), L);
+  for (;;) {
+    if (lane_head(c, L, res)) return;
+    while (L.need_factor)
+      if (lane_factor_once(c, L, res)) return;
+    lane_direction(c, L);
+    while (L.need_trial)
+      if (lane_trial_once(c, L, res)) return;
+  }
+}
+
+// states / inputs of the lane's iterate in the plain layout [x_0, u_0, ..., x_N] (what _split_decision_variables of
+// mpc_control_obs.py:241-281 returns; the dual variables mu, lam are not part of the controller's output)
+TT_HD void unpack(const Params& p, const ObParams& o, const double* s0, double* z) {
+  const size_t sstride = (size_t)stage_rows(o.P) * kBank;
+  for (int k = 0; k <= p.N; k++)
+    for (int j = 0; j < ((k < p.N) ? NW : NX); j++) z[k * NW + j] = ldr(s0 + (size_t)k * sstride, oW + j);
+}
+
+}  // namespace obca
+}  // namespace ttmpc

@@ -18,7 +18,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from .config import FLAG_HOST_POINTERS, Config
+from .config import FLAG_HOST_POINTERS, Config, Obstacles
 
 
 def _is_torch(x) -> bool:
@@ -104,8 +104,21 @@ class BatchSolver:
         window starting at ``k_index[i]`` with the padding rules of simulation.py:485-499."""
         return self._solve(x_init, None, None, k_index, traj_states, traj_inputs, z_warm, want_z, stream)
 
+    def solve_obca(self, obstacles, x_init, ref_states, ref_inputs, want_z: bool = True, stream=None) -> dict:
+        """Solve B obstacle-aware problems (``MPCTrackingControlObs.solve``, mpc_control_obs.py:282-322).
+
+        ``obstacles``: :class:`config.Obstacles` or the reference's obstacle list (dicts with center/width/height,
+        get_obstacles.py:5-33).  Always a cold start (mpc_control_obs.py:216-239); ``z`` holds states and inputs."""
+        return self._solve(x_init, ref_states, ref_inputs, None, None, None, None, want_z, stream, obstacles=obstacles)
+
+    def solve_obca_shared(self, obstacles, x_init, k_index, traj_states, traj_inputs, want_z: bool = True, stream=None) -> dict:
+        """:meth:`solve_obca` with the windows taken from one shared trajectory (simulation.py:485-499)."""
+        return self._solve(x_init, None, None, k_index, traj_states, traj_inputs, None, want_z, stream, obstacles=obstacles)
+
     def _solve(self, x_init, ref_states, ref_inputs, k_index, traj_states, traj_inputs, z_warm, want_z, stream,
-               q_weights=None, r_weights=None):
+               q_weights=None, r_weights=None, obstacles=None):
+        if obstacles is not None and not isinstance(obstacles, Obstacles):
+            obstacles = Obstacles.from_list(obstacles)
         N = self.cfg.horizon
         nz = 8 * N + 6
         shared = ref_states is None
@@ -183,7 +196,15 @@ class BatchSolver:
             ptr = lambda a: None if a is None else a.ctypes.data
             stream = None
             h = self._handle(FLAG_HOST_POINTERS)
-        if shared:
+        if obstacles is not None and shared:
+            rc = self._L.ttmpc_obca_solve_batch_shared(
+                h, ctypes.byref(obstacles), B, px, pk, pts, ptu, T, ptr(out["z"]), ptr(out["u0"]), ptr(out["obj"]),
+                ptr(out["kkt"]), ptr(out["iters"]), ptr(out["status"]), stream)
+        elif obstacles is not None:
+            rc = self._L.ttmpc_obca_solve_batch(
+                h, ctypes.byref(obstacles), B, px, prs, pru, ptr(out["z"]), ptr(out["u0"]), ptr(out["obj"]),
+                ptr(out["kkt"]), ptr(out["iters"]), ptr(out["status"]), stream)
+        elif shared:
             rc = self._L.ttmpc_solve_batch_shared(
                 h, B, px, pk, pts, ptu, T, pzw, ptr(out["z"]), ptr(out["u0"]), ptr(out["obj"]), ptr(out["kkt"]),
                 ptr(out["iters"]), ptr(out["status"]), stream)

@@ -52,6 +52,7 @@ extern "C" {
 #define TTMPC_NX 6
 #define TTMPC_NU 2
 #define TTMPC_MAX_HORIZON 128
+#define TTMPC_MAX_OBSTACLES 16
 
 /* error codes */
 #define TTMPC_OK 0
@@ -137,6 +138,33 @@ int ttmpc_solve_batch_shared(ttmpc_handle* h, int64_t B, const double* x_init,
                              const double* traj_inputs, int32_t T, const double* z_warm,
                              double* z_out, double* u0_out, double* obj_out, double* kkt_out,
                              int32_t* iters_out, int32_t* status_out, void* cuda_stream);
+
+/* Obstacle set of the obstacle-aware controller MPCTrackingControlObs (mpc_control_obs.py:8-30): axis-aligned
+ * rectangles {centre x, centre y, width, height} as produced by get_obstacles.py:5-33, body widths W1 / W2
+ * (params['W1'], params['W2'], simulation.py:393; the body lengths are L1, L2 of the config) and the safety distance
+ * d_min (mpc_control_obs.py:67: 0.2). */
+typedef struct ttmpc_obstacles {
+  int32_t count; /* 1..TTMPC_MAX_OBSTACLES */
+  int32_t reserved;
+  double rect[TTMPC_MAX_OBSTACLES][4];
+  double W1, W2, d_min;
+} ttmpc_obstacles;
+
+/* Solve B NLPs of MPCTrackingControlObs.solve (mpc_control_obs.py:282-322): tracking cost and dynamics of
+ * ttmpc_solve_batch plus, for every stage, obstacle and body, the OBCA dual variables mu, lam >= 0 and the three
+ * collision row groups of _collision_constraints (mpc_control_obs.py:65-139).  Always a cold start at the reference
+ * window with mu = 100, lam = (100,105,110,115) (_get_initial_guess, :216-239).  Outputs as ttmpc_solve_batch; z_out
+ * holds the states and inputs only ([B][8N+6]) -- what _split_decision_variables (:241-281) hands back to the
+ * caller; the OBCA duals are internal.  The second form windows one shared trajectory (simulation.py:485-499). */
+int ttmpc_obca_solve_batch(ttmpc_handle* h, const ttmpc_obstacles* obstacles, int64_t B, const double* x_init,
+                           const double* ref_states, const double* ref_inputs, double* z_out, double* u0_out,
+                           double* obj_out, double* kkt_out, int32_t* iters_out, int32_t* status_out,
+                           void* cuda_stream);
+int ttmpc_obca_solve_batch_shared(ttmpc_handle* h, const ttmpc_obstacles* obstacles, int64_t B,
+                                  const double* x_init, const int32_t* k_index, const double* traj_states,
+                                  const double* traj_inputs, int32_t T, double* z_out, double* u0_out,
+                                  double* obj_out, double* kkt_out, int32_t* iters_out, int32_t* status_out,
+                                  void* cuda_stream);
 
 /* Warm-start shift of B decision vectors (device pointers unless HOST flag in cfg):
  * z_shift[i] = shift(z[i]) as TruckTrailerNMPC._shift_solution. `mode` 0 = intended shift

@@ -49,3 +49,45 @@ def solve_batch(cfg, x_init, ref_states=None, ref_inputs=None, z_warm=None, k_in
     if rc:
         raise RuntimeError(f"emu rc={rc}")
     return dict(z=z, u0=u0, obj=obj, kkt=kkt, iters=it, status=st)
+
+
+_OSO = os.path.join(_HERE, "libttmpc_obca_emu.so")
+_olib = None
+
+
+def obca_lib():
+    global _olib
+    if _olib is None:
+        src = os.path.join(_HERE, "obca_emu.cpp")
+        deps = [src] + [os.path.join(_HERE, "..", "car_trailer_mpc_b200", "csrc", f) for f in ("ttmpc_core.cuh", "ttmpc_obca.cuh")]
+        if not os.path.exists(_OSO) or os.path.getmtime(_OSO) < max(os.path.getmtime(f) for f in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-DTTMPC_BANK=64", "-fPIC", "-shared", "-o", _OSO, src, "-lm"])
+        _olib = ctypes.CDLL(_OSO)
+    return _olib
+
+
+def obca_solve_batch(cfg, obstacles, x_init, ref_states=None, ref_inputs=None, k_index=None, traj_states=None,
+                     traj_inputs=None):
+    N = cfg.horizon
+    x = np.ascontiguousarray(x_init, dtype=np.float64).reshape(-1, 6)
+    B = x.shape[0]
+    xs = us = ki = ts = tu = None
+    T = 0
+    if ref_states is not None:
+        xs = np.ascontiguousarray(ref_states, dtype=np.float64).reshape(B, N + 1, 6)
+        us = np.ascontiguousarray(ref_inputs, dtype=np.float64).reshape(B, N, 2)
+    else:
+        ki = np.ascontiguousarray(k_index, dtype=np.int32).reshape(B)
+        ts = np.ascontiguousarray(traj_states, dtype=np.float64)
+        tu = np.ascontiguousarray(traj_inputs, dtype=np.float64)
+        T = tu.shape[0]
+    z = np.empty((B, 8 * N + 6)); u0 = np.empty((B, 2)); obj = np.empty(B); kkt = np.empty((B, 3))
+    it = np.empty(B, np.int32); st = np.empty(B, np.int32)
+    dp = ctypes.POINTER(ctypes.c_double); ip = ctypes.POINTER(ctypes.c_int32)
+    P = lambda a, t=dp: None if a is None else a.ctypes.data_as(t)
+    rc = obca_lib().ttmpc_emu_obca_solve_batch(ctypes.byref(cfg), ctypes.byref(obstacles), ctypes.c_int64(B), P(x), P(xs),
+                                               P(us), P(ki, ip), P(ts), P(tu), ctypes.c_int32(T), P(z), P(u0), P(obj),
+                                               P(kkt), P(it, ip), P(st, ip))
+    if rc:
+        raise RuntimeError(f"obca emu rc={rc}")
+    return dict(z=z, u0=u0, obj=obj, kkt=kkt, iters=it, status=st)

@@ -1,0 +1,57 @@
+"""Device-resident timing of the obstacle-aware (OBCA) solve, SURVEY 8(d) config 4 (development aid + profiles/).
+
+usage: obca_bench.py B N sigma [--check-emu M] [--json out.json]
+Scenarios: window start k ~ U{0..400}, x_init = S[k] + N(0, sigma^2), clipped into the state bounds; all 11 rectangles
+of obstacles.json; shared-trajectory mode.  --check-emu M: compare the first M problems with the host emulation of the
+kernel core (tools/obca_emu.cpp)."""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import numpy as np, torch
+from car_trailer_mpc_b200 import BatchSolver, tracking_preset, Obstacles, parking_lot_obstacles
+from car_trailer_mpc_b200 import problem as pb
+
+ap = argparse.ArgumentParser()
+ap.add_argument("B", type=int); ap.add_argument("N", type=int); ap.add_argument("sigma", type=float)
+ap.add_argument("--check-emu", type=int, default=0); ap.add_argument("--json", default=None)
+ap.add_argument("--steps", type=int, default=1); ap.add_argument("--max-iter", type=int, default=300)
+a = ap.parse_args()
+cfg = tracking_preset(a.N); cfg.max_iter = a.max_iter
+S, U = pb.load_reference_trajectory()
+rng = np.random.default_rng(20251018)
+ks = rng.integers(0, 401, a.B).astype(np.int32)
+lb = np.array(cfg.x_lb[:]); ub = np.array(cfg.x_ub[:])
+x0 = S[np.minimum(ks, 400)] + rng.normal(0, a.sigma, (a.B, 6))
+x0[:, 2:] = np.clip(x0[:, 2:], lb[2:] + 1e-3, ub[2:] - 1e-3)
+obs = Obstacles.from_list(parking_lot_obstacles())
+dev = torch.device("cuda:0")
+s = BatchSolver(cfg, 0)
+tx = torch.from_numpy(x0).to(dev); tk = torch.from_numpy(ks).to(dev); tS = torch.from_numpy(S).to(dev); tU = torch.from_numpy(U).to(dev)
+ts = []
+for i in range(a.steps + 1):
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); r = s.solve_obca_shared(obs, tx, tk, tS, tU); e1.record(); torch.cuda.synchronize()
+    if i > 0 or a.steps == 0: ts.append(e0.elapsed_time(e1))
+    if a.steps == 0: break
+it = r["iters"].cpu().numpy(); st = r["status"].cpu().numpy(); kkt = r["kkt"].cpu().numpy()
+ok = st <= 1
+res = dict(B=a.B, N=a.N, sigma=a.sigma, obstacles=11, ms=float(np.mean(ts)), solves_per_s=a.B / np.mean(ts) * 1e3,
+           status_hist=np.bincount(st, minlength=6).tolist(), iters_mean=float(it.mean()), iters_max=int(it.max()),
+           iters_mean_converged=float(it[ok].mean()) if ok.any() else None,
+           kkt_max_converged=kkt[ok].max(0).tolist() if ok.any() else None)
+print(json.dumps(res))
+if a.json:
+    json.dump(res, open(a.json, "w"), indent=1)
+if a.check_emu:
+    import emu
+    M = a.check_emu
+    t = time.time()
+    e = emu.obca_solve_batch(cfg, obs, x0[:M], k_index=ks[:M], traj_states=S, traj_inputs=U)
+    print("emu time per solve", (time.time() - t) / M)
+    z = r["z"].cpu().numpy()[:M]
+    both = (st[:M] <= 1) & (e["status"] <= 1)
+    print("status gpu", st[:M].tolist()); print("status emu", e["status"].tolist())
+    print("iters gpu", it[:M].tolist()); print("iters emu", e["iters"].tolist())
+    if both.any():
+        print("max |dz| (both converged)", np.abs(z[both] - e["z"][both]).max(), "max |dobj| rel",
+              (np.abs(r["obj"].cpu().numpy()[:M][both] - e["obj"][both]) / np.maximum(1e-12, np.abs(e["obj"][both]))).max())

@@ -1,0 +1,44 @@
+// obca_emu.cpp -- TEST-ONLY host build of the OBCA solver core (ttmpc_obca.cuh).
+//
+// Compiles the exact per-lane functions the CUDA kernel `ttmpc_obca_kernel` runs with plain g++ over the same
+// bank-interleaved scratch layout, so that the kernel logic (pair condensation + Riccati + filter IPM) can be compared
+// with the dense oracle (oracle/obca_oracle.py) on a machine without a GPU.  NOT part of the product.
+#include <math.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "../car_trailer_mpc_b200/csrc/ttmpc_obca.cuh"
+
+using namespace ttmpc;
+
+extern "C" int ttmpc_emu_obca_solve_batch(const ttmpc_config* cfg, const ttmpc_obstacles* obs, int64_t B, const double* x_init,
+                                          const double* ref_states, const double* ref_inputs, const int32_t* k_index,
+                                          const double* traj_states, const double* traj_inputs, int32_t T, double* z_out,
+                                          double* u0_out, double* obj_out, double* kkt_out, int32_t* iters_out,
+                                          int32_t* status_out) {
+  Params p;
+  int rc = build_params(cfg, &p);
+  if (rc) return rc;
+  obca::ObParams o;
+  rc = obca::build_obparams(cfg, obs, &o);
+  if (rc) return rc;
+  const int64_t L = B < 5 ? B : 5;  // a few lanes with refill, on distinct slots of one bank
+  std::vector<double> scratch(obca::scratch_doubles(p.N, o.P, 1), NAN);
+  ProblemIn in{x_init, ref_states, ref_inputs, nullptr, k_index, traj_states, traj_inputs, T, nullptr, nullptr};
+  const size_t nz = 8 * (size_t)p.N + 6;
+  for (int64_t l = 0; l < L; l++) {
+    double* s0 = obca::slot_ptr(scratch.data(), p.N, o.P, (size_t)l);
+    for (int64_t b = l; b < B; b += L) {
+      Result r;
+      obca::solve_lane(p, o, s0, in, b, r);
+      if (z_out) obca::unpack(p, o, s0, z_out + b * nz);
+      if (u0_out) { u0_out[b * 2] = ldr(s0, obca::oW + 6); u0_out[b * 2 + 1] = ldr(s0, obca::oW + 7); }
+      if (obj_out) obj_out[b] = r.obj;
+      if (kkt_out) { kkt_out[b * 3] = r.dual_inf; kkt_out[b * 3 + 1] = r.constr_viol; kkt_out[b * 3 + 2] = r.compl_inf; }
+      if (iters_out) iters_out[b] = r.iters;
+      if (status_out) status_out[b] = r.status;
+    }
+  }
+  return TTMPC_OK;
+}
