@@ -494,24 +494,38 @@ static episode_kernel_t episode_kernel_for(const Params& p) {
 // ------------------------------------------------------------------------------------------------
 // obstacle-aware (OBCA) solve: one lane per problem, lanes pull problems from a global queue (ttmpc_obca.cuh)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+constexpr int kObcaThreads = 256;  // 8 warps = 8 problem slots per CTA
+#ifndef TTMPC_OBCA_MIN_BLOCKS
+#define TTMPC_OBCA_MIN_BLOCKS 1
+#endif
+#ifndef TTMPC_OBCA_LOCKSTEP
+#define TTMPC_OBCA_LOCKSTEP 1
+#endif
+#if TTMPC_OBCA_LOCKSTEP
+#define OB_CTA_ANY(x) __syncthreads_or(x)
+#else
+#define OB_CTA_ANY(x) (x)  // warp-uniform by construction
+#endif
+__global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
     ttmpc_obca_kernel(const __grid_constant__ Params p, const __grid_constant__ obca::ObParams o, double* __restrict__ scratch,
                       long long B, ProblemIn in, SolveOut out, unsigned long long* counter) {
-  // One warp per CTA.  Every lane owns a scratch slot and works through problems from the global queue; the phases of
-  // an iteration (head / factorisation attempts / direction / line-search trials) are aligned across the warp by
-  // votes, so the lanes always execute the same sweep over consecutive slots (convergent, coalesced) although their
-  // problems are at different iterations.
-  const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // One warp per problem, one lane per (obstacle, body) pair (ttmpc_obca.cuh).  Every warp owns a scratch slot and works
+  // through problems taken from the global queue.  The phases of an iteration (head / factorisation attempts /
+  // direction / line-search trials) are aligned across the 8 warps of the CTA with barriers, although their problems
+  // are at different iterations: the kernel is ~250 KB of code and warps in different sweeps thrash the instruction
+  // cache (measured: 10.8 of 14 stalled warps per issue cycle were waiting for instructions).
+  const int lane = threadIdx.x & 31;
+  const size_t slot = ((size_t)blockIdx.x * kObcaThreads + threadIdx.x) >> 5;
   obca::Ctx c;
-  c.p = &p, c.o = &o, c.s0 = obca::slot_ptr(scratch, p.N, o.P, lane), c.sstride = (size_t)obca::stage_rows(o.P) * kBank;
+  c.p = &p, c.o = &o, c.s0 = obca::slot_ptr(scratch, p.N, slot);
   const long long nz = 8LL * p.N + 6;
-  const unsigned full = 0xffffffffu;
   obca::Lane L;
   bool active = false, exhausted = false;
   long long b = -1;
   for (;;) {
     if (!active && !exhausted) {
-      b = (long long)atomicAdd(counter, 1ull);
+      if (lane == 0) b = (long long)atomicAdd(counter, 1ull);
+      b = __shfl_sync(0xffffffffu, b, 0);
       if (b < B) {
         obca::lane_begin(p, o, obca::init_point(c, in, b), L);
         active = true;
@@ -519,29 +533,31 @@ __global__ void __launch_bounds__(32)
         exhausted = true;
       }
     }
-    if (!__any_sync(full, active)) break;
+    if (!OB_CTA_ANY(active)) break;
     Result res;
     bool done = false;
     if (active) done = obca::lane_head(c, L, res);
-    while (__any_sync(full, active && !done && L.need_factor))
+    while (OB_CTA_ANY(active && !done && L.need_factor))
       if (active && !done && L.need_factor) done = obca::lane_factor_once(c, L, res);
     if (active && !done && L.need_dir) obca::lane_direction(c, L);
-    while (__any_sync(full, active && !done && L.need_trial))
+    while (OB_CTA_ANY(active && !done && L.need_trial))
       if (active && !done && L.need_trial) done = obca::lane_trial_once(c, L, res);
     if (active && done) {
-      if (out.z) obca::unpack(p, o, c.s0, out.z + b * nz);
-      if (out.u0) {
-        out.u0[2 * b] = ldr(c.s0, obca::oW + 6);
-        out.u0[2 * b + 1] = ldr(c.s0, obca::oW + 7);
+      if (out.z) obca::unpack(p, c.s0, out.z + b * nz);
+      if (lane == 0) {
+        if (out.u0) {
+          out.u0[2 * b] = obca::bld(c.s0, obca::oW + 6);
+          out.u0[2 * b + 1] = obca::bld(c.s0, obca::oW + 7);
+        }
+        if (out.obj) out.obj[b] = res.obj;
+        if (out.kkt) {
+          out.kkt[3 * b] = res.dual_inf;
+          out.kkt[3 * b + 1] = res.constr_viol;
+          out.kkt[3 * b + 2] = res.compl_inf;
+        }
+        if (out.iters) out.iters[b] = res.iters;
+        if (out.status) out.status[b] = res.status;
       }
-      if (out.obj) out.obj[b] = res.obj;
-      if (out.kkt) {
-        out.kkt[3 * b] = res.dual_inf;
-        out.kkt[3 * b + 1] = res.constr_viol;
-        out.kkt[3 * b + 2] = res.compl_inf;
-      }
-      if (out.iters) out.iters[b] = res.iters;
-      if (out.status) out.status[b] = res.status;
       active = false;
     }
   }
@@ -732,20 +748,20 @@ static int solve_device(ttmpc_handle* h, long long B, const ProblemIn& in, const
   return TTMPC_OK;
 }
 
-// OBCA solve on device arrays.  Lanes = one warp per CTA, up to kObcaWarpsPerSm warps per SM; a lane owns
-// (N+1) * (93 + 42 * pairs) doubles of scratch (N = 50, 11 obstacles: 415 KB).
-constexpr int kObcaWarpsPerSm = 4;
+// OBCA solve on device arrays: one warp per problem slot, kObcaThreads/32 slots per CTA, CTAs sized to the SM count.
+// A slot owns (N+1) * 1440 doubles of scratch (N = 50: 587 KB).
 static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B, const ProblemIn& in, const SolveOut& so,
                        cudaStream_t st) {
   obca::ObParams o;
   if (obca::build_obparams(&h->cfg, obs, &o) != TTMPC_OK) return set_err(h, TTMPC_E_INVAL, "bad obstacle set", cudaSuccess);
-  int sms = 148;
+  int sms = 148, per_sm = 1;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-  long long warps = (B + 31) / 32;
-  const char* env = getenv("TTMPC_OBCA_WARPS_PER_SM");
-  const long long cap = (long long)sms * (env ? atoi(env) : kObcaWarpsPerSm);
-  if (warps > cap) warps = cap;
-  const size_t need = obca::scratch_doubles(h->p.N, o.P, (size_t)warps * 32 / kBank);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ttmpc_obca_kernel, kObcaThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  const int wpc = kObcaThreads / 32;
+  long long blocks = (B + wpc - 1) / wpc;
+  if (blocks > (long long)sms * per_sm) blocks = (long long)sms * per_sm;
+  const size_t need = obca::scratch_doubles(h->p.N, (size_t)blocks * wpc);
   if (need > h->ob_doubles) {
     if (h->ob_scratch) cudaFree(h->ob_scratch);
     h->ob_scratch = nullptr;
@@ -755,7 +771,7 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
     h->ob_doubles = need;
   }
   cudaMemsetAsync(h->counter, 0, 16 * sizeof(unsigned long long), st);
-  ttmpc_obca_kernel<<<(unsigned)warps, 32, 0, st>>>(h->p, o, h->ob_scratch, B, in, so, h->counter);
+  ttmpc_obca_kernel<<<(unsigned)blocks, kObcaThreads, 0, st>>>(h->p, o, h->ob_scratch, B, in, so, h->counter);
   h->launches[7]++;
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "obca kernel launch", ce);

@@ -1,4 +1,5 @@
-// ttmpc_obca.cuh -- obstacle-aware (OBCA) variant of the per-problem interior-point solver, one lane per problem.
+// ttmpc_obca.cuh -- obstacle-aware (OBCA) variant of the interior-point solver: one WARP per problem, one lane per
+// (obstacle, body) pair.
 //
 // Replaces the arithmetic behind `self._solver(...)` of python-files/mpc_control_obs.py:296-305 (CasADi -> Ipopt ->
 // MUMPS on a ~14 000-dimensional KKT system) for the NLP of `MPCTrackingControlObs`:
@@ -22,8 +23,17 @@
 //
 // One iteration = 4 sweeps over the stages:  update_stats (apply the accepted step, KKT statistics), factor (backward:
 // condensation + Riccati), direction (forward: dx, du, dv, ds, step limits), trial (theta / phi for the filter).
-// This first version keeps the sweeps separate and the 6x6 algebra dense; ttmpc_core.cuh is the tuned path.
+//
+// Mapping: the pairs of a stage are independent of each other, so lane j of the warp owns pair j (its 42 scratch rows
+// are lane-interleaved: a row of all pairs is 256 contiguous bytes).  The per-stage (x, u) work -- model, Riccati
+// step, bound terms -- is small next to the pair work and is done redundantly by every lane on warp-uniform values;
+// the pairs' contributions (4x4 Schur complement, gradient, residual statistics, step limits) are combined with
+// butterfly shuffles, which leave bit-identical sums in all lanes, so control flow stays warp-uniform.  Lane 0 stores
+// the shared (x, u) rows.  On the host (tools/obca_emu.cpp, tests only) the pair loop is sequential and the
+// reductions are the identity; the 6x6 algebra is dense here, ttmpc_core.cuh is the tuned path.
 #pragma once
+#include <stdio.h>
+
 #include "ttmpc_core.cuh"
 
 namespace ttmpc {
@@ -34,15 +44,68 @@ constexpr int kMaxPairs = 2 * TTMPC_MAX_OBSTACLES;
 constexpr int oW = 0, oDW = 8, oREF = 16, oLAM = 24, oLAMP = 30, oZL = 36, oZU = 44, oK = 52, oKFF = 64, oP = 66, oPV = 87;
 constexpr int kBaseRows = 93;
 constexpr int qV = 0, qZV = 8, qS = 16, qY = 20, qZS = 24, qDV = 30, qDS = 38;  // rows of one pair
-constexpr int kPairRows = 42;
-TT_HD int stage_rows(int P) { return kBaseRows + kPairRows * P; }
-inline size_t scratch_doubles(int N, int P, size_t nbanks) {
-  return nbanks * (size_t)(N + 1) * (size_t)stage_rows(P) * kBank;
+constexpr int qA = 42, qG = 50;  // K_vv^-1 q (8) and K_vv^-1 K_vx (8x4, row-major): written by factor, read by direction
+constexpr int kPairRows = 82;
+constexpr int kBasePad = 96;                                 // base rows, padded to a multiple of 32 doubles
+constexpr int kLanes = 32;                                   // pair slots per stage (>= kMaxPairs)
+constexpr int kStageDoubles = kBasePad + kPairRows * kLanes;  // 2720 doubles = 21.25 KB per stage and problem slot
+inline size_t scratch_doubles(int N, size_t slots) { return slots * (size_t)(N + 1) * kStageDoubles; }
+TT_HD double* slot_ptr(double* scratch, int N, size_t slot) { return scratch + slot * (size_t)(N + 1) * kStageDoubles; }
+
+// ---- execution policy: warp per problem on the device, sequential on the host ----
+#if defined(__CUDA_ARCH__)
+#define OB_LANE ((int)(threadIdx.x & 31))
+#define OB_FOR_LANES(j, n) for (int j = OB_LANE, once_ = 1; once_ && j < (n); once_ = 0)
+#define OB_NOINLINE __device__ __noinline__
+TT_HD void ob_sync() { __syncwarp(); }
+// the reductions are called ~40 times per iteration: real functions keep the kernel inside the instruction cache
+OB_NOINLINE double ob_sum(double v) {
+  TT_UNROLL
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
-TT_HD double* slot_ptr(double* scratch, int N, int P, size_t slot) {
-  const size_t bank = slot / kBank, lane = slot % kBank;
-  return scratch + bank * (size_t)(N + 1) * (size_t)stage_rows(P) * kBank + lane;
+OB_NOINLINE double ob_max(double v) {
+  TT_UNROLL
+  for (int o = 16; o > 0; o >>= 1) v = tt_max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
 }
+OB_NOINLINE double ob_min(double v) {
+  TT_UNROLL
+  for (int o = 16; o > 0; o >>= 1) v = tt_min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+TT_HD bool ob_all(bool b) { return __all_sync(0xffffffffu, b) != 0; }
+TT_HD bool ob_lane0() { return (threadIdx.x & 31) == 0; }
+#else
+#define OB_NOINLINE inline
+#define OB_FOR_LANES(j, n) for (int j = 0; j < (n); j++)
+TT_HD void ob_sync() {}
+TT_HD double ob_sum(double v) { return v; }
+TT_HD double ob_max(double v) { return v; }
+TT_HD double ob_min(double v) { return v; }
+TT_HD bool ob_all(bool b) { return b; }
+TT_HD bool ob_lane0() { return true; }
+#endif
+// 1/sqrt(x) for a positive pivot: hardware seed + Newton steps (the library sqrt is ~35 instructions with a slow path)
+TT_HD double tt_rsqrt(double x) {
+#if defined(__CUDA_ARCH__) && !defined(TTMPC_OBCA_EXACT_SQRT)
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double hx = 0.5 * x;
+  r = fma(r, fma(-hx * r, r, 0.5), r);
+  r = fma(r, fma(-hx * r, r, 0.5), r);
+  return fma(r, fma(-hx * r, r, 0.5), r);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+// shared (x, u) rows of a stage: plain array, written by lane 0;  pair rows: [row][lane]
+TT_HD double bld(const double* ps, int row) { return ps[row]; }
+TT_HD void bst(double* ps, int row, double v) {
+  if (ob_lane0()) ps[row] = v;
+}
+TT_HD double pld(const double* pp, int row) { return pp[row * kLanes]; }
+TT_HD void pst(double* pp, int row, double v) { pp[row * kLanes] = v; }
 
 struct ObParams {
   int P;                     // pairs per stage = 2 * obstacles; pair j: obstacle j/2, body j%2 (0 vehicle, 1 trailer)
@@ -133,35 +196,51 @@ TT_HD void pair_rows(const ObParams& o, int body, const double* b, const Trig& t
   d[3] = sqrt(lx * lx + ly * ly) - 1.0;
 }
 
+// Arithmetic with a fixed rounding sequence.  The rows d, their Jacobians and the slack barrier terms are evaluated at
+// the same iterate by three separately inlined sweeps (factor, direction, update_stats); nvcc may contract a*b+c into an
+// FMA in one copy and not in another, and the resulting last-bit differences are amplified by Sigma_s ~ 1e10 and
+// multipliers ~ 1e5 into a 1e-4 floor on the dual infeasibility (measured).  Spelling every operation out makes all
+// copies bit-identical; the host build needs nothing (no contraction without -mfma).
+#if defined(__CUDA_ARCH__)
+TT_HD double xm(double a, double b) { return __dmul_rn(a, b); }
+TT_HD double xa(double a, double b) { return __dadd_rn(a, b); }
+TT_HD double xf(double a, double b, double c) { return fma(a, b, c); }
+#else
+TT_HD double xm(double a, double b) { return a * b; }
+TT_HD double xa(double a, double b) { return a + b; }
+TT_HD double xf(double a, double b, double c) { return a * b + c; }
+#endif
+
+template <bool HESS>
 TT_HD void pair_eval(const ObParams& o, int body, const double* b, const Trig& t, const double* v, const double* y,
                      PairEval& e) {
-  const double lx = v[4] - v[6], ly = v[5] - v[7], mx = v[0] - v[2], my = v[1] - v[3];
-  double pcx, pcy, ptx, pty, ppx, ppy, pttx, ptty, pppx, pppy, c, s;
+  const double lx = xa(v[4], -v[6]), ly = xa(v[5], -v[7]), mx = xa(v[0], -v[2]), my = xa(v[1], -v[3]);
+  double pcx, pcy, ptx, pty, ppx, ppy, c, s;
   if (body == 0) {  // truck_trailer_model.py:61-64
     const double a = o.hl1;
-    pcx = t.x + t.cth * a, pcy = t.y + t.sth * a;
-    ptx = -t.sth * a, pty = t.cth * a, ppx = 0.0, ppy = 0.0;
-    pttx = -t.cth * a, ptty = -t.sth * a, pppx = 0.0, pppy = 0.0;
+    pcx = xf(t.cth, a, t.x), pcy = xf(t.sth, a, t.y);
+    ptx = xm(-t.sth, a), pty = xm(t.cth, a), ppx = 0.0, ppy = 0.0;
     c = t.cth, s = t.sth;
   } else {  // truck_trailer_model.py:66-72
     const double h = o.hl2, M = o.M;
-    pcx = t.x - t.cth * M - t.cal * h, pcy = t.y - t.sth * M - t.sal * h;
-    ptx = t.sth * M + t.sal * h, pty = -t.cth * M - t.cal * h;
-    ppx = t.sal * h, ppy = -t.cal * h;
-    pttx = t.cth * M + t.cal * h, ptty = t.sth * M + t.sal * h;
-    pppx = t.cal * h, pppy = t.sal * h;
+    pcx = xf(-t.cal, h, xf(-t.cth, M, t.x)), pcy = xf(-t.sal, h, xf(-t.sth, M, t.y));
+    ptx = xf(t.sal, h, xm(t.sth, M)), pty = xf(-t.cal, h, xm(-t.cth, M));
+    ppx = xm(t.sal, h), ppy = xm(-t.cal, h);
     c = t.cal, s = t.sal;
   }
   const double tr = body ? 1.0 : 0.0;
   const double* g = o.g[body];
-  const double e0 = b[0] - pcx, e1 = b[1] - pcy, e2 = b[2] + pcx, e3 = b[3] + pcy;
-  e.d[0] = g[0] * v[0] + g[1] * v[1] + g[2] * v[2] + g[3] * v[3] + e0 * v[4] + e1 * v[5] + e2 * v[6] + e3 * v[7] + o.d_min;
-  e.d[1] = mx + c * lx + s * ly;
-  e.d[2] = my - s * lx + c * ly;
-  const double nrm = sqrt(lx * lx + ly * ly), inr = tt_rcp(nrm);
-  e.d[3] = nrm - 1.0;
-  const double nx = lx * inr, ny = ly * inr;
-  const double r1 = -s * lx + c * ly, r2 = -c * lx - s * ly;
+  const double e0 = xa(b[0], -pcx), e1 = xa(b[1], -pcy), e2 = xa(b[2], pcx), e3 = xa(b[3], pcy);
+  double acc = o.d_min;
+  acc = xf(g[0], v[0], acc), acc = xf(g[1], v[1], acc), acc = xf(g[2], v[2], acc), acc = xf(g[3], v[3], acc);
+  acc = xf(e0, v[4], acc), acc = xf(e1, v[5], acc), acc = xf(e2, v[6], acc), acc = xf(e3, v[7], acc);
+  e.d[0] = acc;
+  e.d[1] = xf(s, ly, xf(c, lx, mx));
+  e.d[2] = xf(c, ly, xf(-s, lx, my));
+  const double nrm = sqrt(xf(ly, ly, xm(lx, lx))), inr = tt_rcp(nrm);
+  e.d[3] = xa(nrm, -1.0);
+  const double nx = xm(lx, inr), ny = xm(ly, inr);
+  const double r1 = xf(c, ly, xm(-s, lx)), r2 = xf(-s, ly, xm(-c, lx));
   TT_UNROLL
   for (int r = 0; r < 4; r++) {
     TT_UNROLL
@@ -169,16 +248,24 @@ TT_HD void pair_eval(const ObParams& o, int body, const double* b, const Trig& t
     TT_UNROLL
     for (int j = 0; j < 8; j++) e.Jv[r][j] = 0.0;
   }
-  e.Jx[0][0] = -lx, e.Jx[0][1] = -ly, e.Jx[0][2] = -(ptx * lx + pty * ly), e.Jx[0][3] = -(ppx * lx + ppy * ly);
-  e.Jx[1][2] = r1, e.Jx[1][3] = tr * r1;
-  e.Jx[2][2] = r2, e.Jx[2][3] = tr * r2;
+  e.Jx[0][0] = -lx, e.Jx[0][1] = -ly, e.Jx[0][2] = -xf(pty, ly, xm(ptx, lx)), e.Jx[0][3] = -xf(ppy, ly, xm(ppx, lx));
+  e.Jx[1][2] = r1, e.Jx[1][3] = xm(tr, r1);
+  e.Jx[2][2] = r2, e.Jx[2][3] = xm(tr, r2);
   TT_UNROLL
   for (int j = 0; j < 4; j++) e.Jv[0][j] = g[j];
   e.Jv[0][4] = e0, e.Jv[0][5] = e1, e.Jv[0][6] = e2, e.Jv[0][7] = e3;
   e.Jv[1][0] = 1.0, e.Jv[1][2] = -1.0, e.Jv[1][4] = c, e.Jv[1][5] = s, e.Jv[1][6] = -c, e.Jv[1][7] = -s;
   e.Jv[2][1] = 1.0, e.Jv[2][3] = -1.0, e.Jv[2][4] = -s, e.Jv[2][5] = c, e.Jv[2][6] = s, e.Jv[2][7] = -c;
   e.Jv[3][4] = nx, e.Jv[3][5] = ny, e.Jv[3][6] = -nx, e.Jv[3][7] = -ny;
-  // Hessian of y'd
+  if (!HESS) return;
+  // Hessian of y'd (factor sweep only: no second copy to agree with)
+  double pttx, ptty, pppx, pppy;
+  if (body == 0) {
+    pttx = -t.cth * o.hl1, ptty = -t.sth * o.hl1, pppx = 0.0, pppy = 0.0;
+  } else {
+    pttx = t.cth * o.M + t.cal * o.hl2, ptty = t.sth * o.M + t.sal * o.hl2;
+    pppx = t.cal * o.hl2, pppy = t.sal * o.hl2;
+  }
   const double kap = y[1] * r2 - y[2] * r1;
   e.hthth = -y[0] * (pttx * lx + ptty * ly) + kap;
   e.hthps = tr * (-y[0] * (pppx * lx + pppy * ly) + kap);
@@ -191,18 +278,18 @@ TT_HD void pair_eval(const ObParams& o, int body, const double* b, const Trig& t
   e.Wll[0] = yn * (1.0 - nx * nx), e.Wll[1] = -yn * nx * ny, e.Wll[2] = yn * (1.0 - ny * ny);
 }
 
-// barrier quantities of the 4 slacks: D = Sigma_s (+delta), gs = d(barrier)/ds at mu = 1, log-product of the distances
+// barrier quantities of the 4 slacks: D = Sigma_s (+delta), gs = d(barrier)/ds at mu = 1 (fixed rounding sequence, see above)
 struct SlackBar {
   double D[4], gs1[4];
 };
 TT_HD void slack_bar(const ObParams& o, const double* s, const double* zs, double delta, SlackBar& sb) {
-  const double r0 = tt_rcp(o.s_up - s[0]), r3 = tt_rcp(o.s_up - s[3]);
-  const double l1 = tt_rcp(s[1] - o.c2_lo), u1 = tt_rcp(o.c2_up - s[1]);
-  const double l2 = tt_rcp(s[2] - o.c2_lo), u2 = tt_rcp(o.c2_up - s[2]);
-  sb.D[0] = zs[0] * r0 + delta, sb.gs1[0] = r0;
-  sb.D[1] = zs[1] * l1 + zs[2] * u1 + delta, sb.gs1[1] = u1 - l1;
-  sb.D[2] = zs[3] * l2 + zs[4] * u2 + delta, sb.gs1[2] = u2 - l2;
-  sb.D[3] = zs[5] * r3 + delta, sb.gs1[3] = r3;
+  const double r0 = tt_rcp(xa(o.s_up, -s[0])), r3 = tt_rcp(xa(o.s_up, -s[3]));
+  const double l1 = tt_rcp(xa(s[1], -o.c2_lo)), u1 = tt_rcp(xa(o.c2_up, -s[1]));
+  const double l2 = tt_rcp(xa(s[2], -o.c2_lo)), u2 = tt_rcp(xa(o.c2_up, -s[2]));
+  sb.D[0] = xf(zs[0], r0, delta), sb.gs1[0] = r0;
+  sb.D[1] = xf(zs[1], l1, xf(zs[2], u1, delta)), sb.gs1[1] = xa(u1, -l1);
+  sb.D[2] = xf(zs[3], l2, xf(zs[4], u2, delta)), sb.gs1[2] = xa(u2, -l2);
+  sb.D[3] = xf(zs[5], r3, delta), sb.gs1[3] = r3;
 }
 
 // In-place Cholesky of the lower triangle of an 8x8 matrix (diagonal stored inverted); false when a pivot is not
@@ -215,7 +302,7 @@ TT_HD bool chol8(double (*K)[8]) {
     TT_UNROLL
     for (int k = 0; k < j; k++) d -= K[j][k] * K[j][k];
     if (!(d > 0.0)) ok = false;
-    const double il = tt_rcp(sqrt(d));
+    const double il = tt_rsqrt(d);
     K[j][j] = il;  // the diagonal holds 1 / L_jj
     TT_UNROLL
     for (int i = j + 1; i < 8; i++) {
@@ -289,11 +376,10 @@ TT_HD void pair_system(const ObParams& o, const PairEval& e, const SlackBar& sb,
 struct Ctx {
   const Params* p;
   const ObParams* o;
-  double* s0;   // slot pointer (stage 0, row 0, this lane)
-  size_t sstride;  // doubles between stages
-  TT_HD double* stage(int k) const { return s0 + (size_t)k * sstride; }
+  double* s0;   // slot pointer (stage 0 of this problem slot)
+  TT_HD double* stage(int k) const { return s0 + (size_t)k * kStageDoubles; }
 };
-TT_HD double* pair_ptr(double* ps, int j) { return ps + (size_t)(kBaseRows + kPairRows * j) * kBank; }
+TT_HD double* pair_ptr(double* ps, int j) { return ps + kBasePad + j; }
 
 TT_HD void dense_A(const Lin& m, double (*A)[NX]) {
   TT_UNROLL
@@ -321,7 +407,7 @@ TT_HD bool init_point(const Ctx& c, const ProblemIn& in, long long b) {
       const bool on = (j < NX) || (k < N);
       if (!on) continue;
       const double r = ref_value(p, in, b, k, j);
-      str(ps, oREF + j, r);
+      bst(ps, oREF + j, r);
       double w;
       if (j < NX && k == 0) {
         w = in.x_init[b * NX + j];
@@ -329,28 +415,29 @@ TT_HD bool init_point(const Ctx& c, const ProblemIn& in, long long b) {
       } else {
         w = tt_min(tt_max(r, p.lo_push[j]), p.up_push[j]);
       }
-      str(ps, oW + j, w);
-      str(ps, oZL + j, 1.0);
-      str(ps, oZU + j, 1.0);
+      bst(ps, oW + j, w);
+      bst(ps, oZL + j, 1.0);
+      bst(ps, oZU + j, 1.0);
       if (j < NX) x[j] = w;
     }
-    for (int j = 0; j < NX; j++) str(ps, oLAM + j, 0.0);
+    for (int j = 0; j < NX; j++) bst(ps, oLAM + j, 0.0);
     Trig t;
     stage_trig(x, t);
-    for (int pj = 0; pj < o.P; pj++) {
+    OB_FOR_LANES(pj, o.P) {
       double* pp = pair_ptr(ps, pj);
       double v[8], d[4];
       for (int i = 0; i < 4; i++) v[i] = tt_max(o.mu_guess, o.v_push), v[4 + i] = tt_max(o.lam_guess[i], o.v_push);
       pair_rows(o, pj & 1, o.b[pj], t, v, d);
-      for (int i = 0; i < 8; i++) str(pp, qV + i, v[i]), str(pp, qZV + i, 1.0);
-      str(pp, qS + 0, tt_min(d[0], o.s_up_push));
-      str(pp, qS + 1, tt_min(tt_max(d[1], o.c2_lo_push), o.c2_up_push));
-      str(pp, qS + 2, tt_min(tt_max(d[2], o.c2_lo_push), o.c2_up_push));
-      str(pp, qS + 3, tt_min(d[3], o.s_up_push));
-      for (int i = 0; i < 4; i++) str(pp, qY + i, 0.0);
-      for (int i = 0; i < 6; i++) str(pp, qZS + i, 1.0);
+      for (int i = 0; i < 8; i++) pst(pp, qV + i, v[i]), pst(pp, qZV + i, 1.0);
+      pst(pp, qS + 0, tt_min(d[0], o.s_up_push));
+      pst(pp, qS + 1, tt_min(tt_max(d[1], o.c2_lo_push), o.c2_up_push));
+      pst(pp, qS + 2, tt_min(tt_max(d[2], o.c2_lo_push), o.c2_up_push));
+      pst(pp, qS + 3, tt_min(d[3], o.s_up_push));
+      for (int i = 0; i < 4; i++) pst(pp, qY + i, 0.0);
+      for (int i = 0; i < 6; i++) pst(pp, qZS + i, 1.0);
     }
   }
+  ob_sync();
   return x0_bad;
 }
 
@@ -363,21 +450,32 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
   const ObParams& o = *c.o;
   const int N = p.N;
   double J = 0.0, sumlog = 0.0, theta = 0.0, cinf = 0.0, rd_inf = 0.0, lam1 = 0.0, z1 = 0.0, cmax = 0.0, cmin = INFINITY;
+  // the pairs' share of the statistics: per-lane partial results, combined across the warp after the sweep
+  double q_sumlog = 0.0, q_theta = 0.0, q_cinf = 0.0, q_rd = 0.0, q_lam1 = 0.0, q_z1 = 0.0, q_cmax = 0.0, q_cmin = INFINITY;
   const double khi = kKappaSigma * mu_step, klo = mu_step / kKappaSigma;
   double xn[NX], ln[NX];  // x_{k+1}, lambda_{k+1} at the new iterate
   for (int j = 0; j < NX; j++) xn[j] = ln[j] = 0.0;
   for (int k = N; k >= 0; k--) {
     double* ps = c.stage(k);
     const bool has_x = k >= 1, has_u = k < N;
-    double w[NW], ref[NW], zl[NW], zu[NW], lam[NX];
+    double w[NW], ref[NW], zl[NW], zu[NW], lam[NX], dwv[NW], lamp[NX];
     for (int j = 0; j < NW; j++) {
       const bool on = (j < NX) || has_u, var = (j < NX) ? has_x : has_u;
-      w[j] = on ? ldr(ps, oW + j) : 0.0;
-      ref[j] = on ? ldr(ps, oREF + j) : 0.0;
-      zl[j] = (var && var_lo(p, j)) ? ldr(ps, oZL + j) : 0.0;
-      zu[j] = (var && var_up(p, j)) ? ldr(ps, oZU + j) : 0.0;
+      w[j] = on ? bld(ps, oW + j) : 0.0;
+      ref[j] = on ? bld(ps, oREF + j) : 0.0;
+      zl[j] = (var && var_lo(p, j)) ? bld(ps, oZL + j) : 0.0;
+      zu[j] = (var && var_up(p, j)) ? bld(ps, oZU + j) : 0.0;
+      dwv[j] = (do_update && var) ? bld(ps, oDW + j) : 0.0;
+    }
+    for (int j = 0; j < NX; j++) {
+      lam[j] = has_x ? bld(ps, oLAM + j) : 0.0;
+      lamp[j] = (do_update && has_x) ? bld(ps, oLAMP + j) : 0.0;
+    }
+    ob_sync();  // every lane has read the shared rows of this stage before lane 0 overwrites them
+    for (int j = 0; j < NW; j++) {
+      const bool var = (j < NX) ? has_x : has_u;
       if (do_update && var) {
-        const double d = ldr(ps, oDW + j);
+        const double d = dwv[j];
         if (var_lo(p, j)) {
           const double rl = tt_rcp(w[j] - p.lo[j]);
           zl[j] += alpha_du * (rl * (mu_step - zl[j] * d) - zl[j]);
@@ -389,16 +487,15 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
         w[j] += alpha * d;
         if (var_lo(p, j)) zl[j] = clampz(zl[j], tt_rcp(w[j] - p.lo[j]), khi, klo);
         if (var_up(p, j)) zu[j] = clampz(zu[j], tt_rcp(p.up[j] - w[j]), khi, klo);
-        str(ps, oW + j, w[j]);
-        if (var_lo(p, j)) str(ps, oZL + j, zl[j]);
-        if (var_up(p, j)) str(ps, oZU + j, zu[j]);
+        bst(ps, oW + j, w[j]);
+        if (var_lo(p, j)) bst(ps, oZL + j, zl[j]);
+        if (var_up(p, j)) bst(ps, oZU + j, zu[j]);
       }
     }
     for (int j = 0; j < NX; j++) {
-      lam[j] = has_x ? ldr(ps, oLAM + j) : 0.0;
       if (do_update && has_x) {
-        lam[j] += alpha * (ldr(ps, oLAMP + j) - lam[j]);
-        str(ps, oLAM + j, lam[j]);
+        lam[j] += alpha * (lamp[j] - lam[j]);
+        bst(ps, oLAM + j, lam[j]);
       }
     }
     // gradient of the Lagrangian wrt (x_k, u_k), without the pair terms yet
@@ -454,17 +551,18 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
       r[7] -= p.dt * ln[4];
     }
     // pairs
+    double rp[4] = {0.0, 0.0, 0.0, 0.0};  // J_x' y of this lane's pair(s)
     Trig t;
     stage_trig(w, t);
-    for (int pj = 0; pj < o.P; pj++) {
+    OB_FOR_LANES(pj, o.P) {
       double* pp = pair_ptr(ps, pj);
       double v[8], zv[8], s[4], y[4], zs[6];
-      for (int i = 0; i < 8; i++) v[i] = ldr(pp, qV + i), zv[i] = ldr(pp, qZV + i);
-      for (int i = 0; i < 4; i++) s[i] = ldr(pp, qS + i), y[i] = ldr(pp, qY + i);
-      for (int i = 0; i < 6; i++) zs[i] = ldr(pp, qZS + i);
+      for (int i = 0; i < 8; i++) v[i] = pld(pp, qV + i), zv[i] = pld(pp, qZV + i);
+      for (int i = 0; i < 4; i++) s[i] = pld(pp, qS + i), y[i] = pld(pp, qY + i);
+      for (int i = 0; i < 6; i++) zs[i] = pld(pp, qZS + i);
       if (do_update) {
         double ds[4];
-        for (int i = 0; i < 4; i++) ds[i] = ldr(pp, qDS + i);
+        for (int i = 0; i < 4; i++) ds[i] = pld(pp, qDS + i);
         SlackBar sb;
         slack_bar(o, s, zs, delta_step, sb);
         for (int i = 0; i < 4; i++) y[i] += alpha * (sb.D[i] * ds[i] + mu_step * sb.gs1[i] - y[i]);  // y+ = D ds + gs
@@ -478,64 +576,68 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
           zs[i] += alpha_du * (rr * (mu_step + zs[i] * dd) - zs[i]);
         }
         for (int i = 0; i < 8; i++) {
-          const double d = ldr(pp, qDV + i), rl = tt_rcp(v[i] - o.v_lo);
+          const double d = pld(pp, qDV + i), rl = tt_rcp(v[i] - o.v_lo);
           zv[i] += alpha_du * (rl * (mu_step - zv[i] * d) - zv[i]);
           v[i] += alpha * d;
           zv[i] = clampz(zv[i], tt_rcp(v[i] - o.v_lo), khi, klo);
-          str(pp, qV + i, v[i]), str(pp, qZV + i, zv[i]);
+          pst(pp, qV + i, v[i]), pst(pp, qZV + i, zv[i]);
         }
         for (int i = 0; i < 4; i++) {
           s[i] += alpha * ds[i];
-          str(pp, qS + i, s[i]), str(pp, qY + i, y[i]);
+          pst(pp, qS + i, s[i]), pst(pp, qY + i, y[i]);
         }
         for (int i = 0; i < 6; i++) {
           const double bd = upper[i] ? ((row[i] == 0 || row[i] == 3) ? o.s_up : o.c2_up) : o.c2_lo;
           const double dist = upper[i] ? bd - s[row[i]] : s[row[i]] - bd;
           zs[i] = clampz(zs[i], tt_rcp(dist), khi, klo);
-          str(pp, qZS + i, zs[i]);
+          pst(pp, qZS + i, zs[i]);
         }
       }
       PairEval e;
-      pair_eval(o, pj & 1, o.b[pj], t, v, y, e);
+      pair_eval<false>(o, pj & 1, o.b[pj], t, v, y, e);
       for (int i = 0; i < 4; i++) {
         const double rc = e.d[i] - s[i];
-        theta += fabs(rc);
-        cinf = tt_max(cinf, fabs(rc));
-        lam1 += fabs(y[i]);
-        if (has_x)
-          for (int cc = 0; cc < 4; cc++) r[cc] += e.Jx[i][cc] * y[i];
+        q_theta += fabs(rc);
+        q_cinf = tt_max(q_cinf, fabs(rc));
+        q_lam1 += fabs(y[i]);
+        for (int cc = 0; cc < 4; cc++) rp[cc] += e.Jx[i][cc] * y[i];
       }
       double pprod = 1.0;
       for (int i = 0; i < 8; i++) {
         double rv = -zv[i];
         for (int rr = 0; rr < 4; rr++) rv += e.Jv[rr][i] * y[rr];
-        rd_inf = tt_max(rd_inf, fabs(rv));
+        q_rd = tt_max(q_rd, fabs(rv));
         const double sl = v[i] - o.v_lo, cc = sl * zv[i];
-        pprod *= sl, z1 += zv[i], cmax = tt_max(cmax, cc), cmin = tt_min(cmin, cc);
+        pprod *= sl, q_z1 += zv[i], q_cmax = tt_max(q_cmax, cc), q_cmin = tt_min(q_cmin, cc);
       }
-      sumlog += log(pprod);
+      q_sumlog += log(pprod);
       {
         const double dist[6] = {o.s_up - s[0], s[1] - o.c2_lo, o.c2_up - s[1], s[2] - o.c2_lo, o.c2_up - s[2], o.s_up - s[3]};
         double sprod = 1.0;
         for (int i = 0; i < 6; i++) {
           const double cc = dist[i] * zs[i];
-          sprod *= dist[i], z1 += zs[i], cmax = tt_max(cmax, cc), cmin = tt_min(cmin, cc);
+          sprod *= dist[i], q_z1 += zs[i], q_cmax = tt_max(q_cmax, cc), q_cmin = tt_min(q_cmin, cc);
         }
-        sumlog += log(sprod);
-        rd_inf = tt_max(rd_inf, fabs(-y[0] + zs[0]));
-        rd_inf = tt_max(rd_inf, fabs(-y[1] - zs[1] + zs[2]));
-        rd_inf = tt_max(rd_inf, fabs(-y[2] - zs[3] + zs[4]));
-        rd_inf = tt_max(rd_inf, fabs(-y[3] + zs[5]));
+        q_sumlog += log(sprod);
+        q_rd = tt_max(q_rd, fabs(-y[0] + zs[0]));
+        q_rd = tt_max(q_rd, fabs(-y[1] - zs[1] + zs[2]));
+        q_rd = tt_max(q_rd, fabs(-y[2] - zs[3] + zs[4]));
+        q_rd = tt_max(q_rd, fabs(-y[3] + zs[5]));
       }
     }
+    if (has_x)
+      for (int cc = 0; cc < 4; cc++) r[cc] += ob_sum(rp[cc]);
     for (int j = 0; j < NW; j++) {
       const bool var = (j < NX) ? has_x : has_u;
       if (var) rd_inf = tt_max(rd_inf, fabs(r[j]));
     }
     for (int j = 0; j < NX; j++) xn[j] = w[j], ln[j] = lam[j];
   }
-  st.J = J, st.sumlog = sumlog, st.theta = theta, st.cinf = cinf, st.rd_inf = rd_inf, st.lam1 = lam1, st.z1 = z1;
-  st.cmax = cmax, st.cmin = cmin;
+  st.J = J, st.sumlog = sumlog + ob_sum(q_sumlog), st.theta = theta + ob_sum(q_theta);
+  st.cinf = tt_max(cinf, ob_max(q_cinf)), st.rd_inf = tt_max(rd_inf, ob_max(q_rd));
+  st.lam1 = lam1 + ob_sum(q_lam1), st.z1 = z1 + ob_sum(q_z1);
+  st.cmax = tt_max(cmax, ob_max(q_cmax)), st.cmin = tt_min(cmin, ob_min(q_cmin));
+  ob_sync();
 }
 
 // ---- sweep 2 (backward): condensation of the pairs + Riccati factorisation.  false: wrong inertia ----
@@ -557,8 +659,8 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
       double ref[NW];
       for (int j = 0; j < NW; j++) {
         const bool on = (j < NX) || has_u;
-        w[j] = on ? ldr(ps, oW + j) : 0.0;
-        ref[j] = on ? ldr(ps, oREF + j) : 0.0;
+        w[j] = on ? bld(ps, oW + j) : 0.0;
+        ref[j] = on ? bld(ps, oREF + j) : 0.0;
       }
       for (int i = 0; i < NX; i++) {
         double s = 0.0;
@@ -573,12 +675,12 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
       sig[j] = delta;
       if (var && var_lo(p, j)) {
         const double rl = tt_rcp(w[j] - p.lo[j]);
-        sig[j] += ldr(ps, oZL + j) * rl;
+        sig[j] += bld(ps, oZL + j) * rl;
         g[j] -= mu * rl;
       }
       if (var && var_up(p, j)) {
         const double ru = tt_rcp(p.up[j] - w[j]);
-        sig[j] += ldr(ps, oZU + j) * ru;
+        sig[j] += bld(ps, oZU + j) * ru;
         g[j] += mu * ru;
       }
     }
@@ -591,26 +693,41 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
     bool ok = true;
     Trig t;
     stage_trig(w, t);
-    for (int pj = 0; pj < o.P; pj++) {
+    OB_FOR_LANES(pj, o.P) {
       double* pp = pair_ptr(ps, pj);
       double v[8], zv[8], s[4], y[4], zs[6];
-      for (int i = 0; i < 8; i++) v[i] = ldr(pp, qV + i), zv[i] = ldr(pp, qZV + i);
-      for (int i = 0; i < 4; i++) s[i] = ldr(pp, qS + i), y[i] = ldr(pp, qY + i);
-      for (int i = 0; i < 6; i++) zs[i] = ldr(pp, qZS + i);
+      for (int i = 0; i < 8; i++) v[i] = pld(pp, qV + i), zv[i] = pld(pp, qZV + i);
+      for (int i = 0; i < 4; i++) s[i] = pld(pp, qS + i), y[i] = pld(pp, qY + i);
+      for (int i = 0; i < 6; i++) zs[i] = pld(pp, qZS + i);
       PairEval e;
-      pair_eval(o, pj & 1, o.b[pj], t, v, y, e);
+      pair_eval<true>(o, pj & 1, o.b[pj], t, v, y, e);
       SlackBar sb;
       slack_bar(o, s, zs, delta, sb);
       double K[8][8], Kvx[8][4], q[8], tt[4];
       pair_system(o, e, sb, v, zv, s, mu, delta, K, Kvx, q, tt);
       if (!chol8(K)) ok = false;
-      if (!has_x) continue;  // x_0 is data: the pair only has to have the right inertia
+      // u = L^-1 q, Y = L^-1 K_vx for the Schur complement;  a = L^-T u, G = L^-T Y are kept for the direction sweep, which
+      // therefore uses exactly this factorisation (two separately compiled factorisations differ in the last bits, and
+      // with multipliers of 1e5 and Sigma_s of 1e10 that difference is a 1e-4 floor on the dual infeasibility)
       fsub8(K, q);
       double col[4][8];
       for (int cc = 0; cc < 4; cc++) {
         for (int i = 0; i < 8; i++) col[cc][i] = Kvx[i][cc];
         fsub8(K, col[cc]);
       }
+      {
+        double a8[8];
+        for (int i = 0; i < 8; i++) a8[i] = q[i];
+        bsub8(K, a8);
+        for (int i = 0; i < 8; i++) pst(pp, qA + i, a8[i]);
+        if (has_x)
+          for (int cc = 0; cc < 4; cc++) {
+            for (int i = 0; i < 8; i++) a8[i] = col[cc][i];
+            bsub8(K, a8);
+            for (int i = 0; i < 8; i++) pst(pp, qG + 4 * i + cc, a8[i]);
+          }
+      }
+      if (!has_x) continue;  // x_0 is data: no coupling to condense
       for (int a = 0; a < 4; a++) {
         double ga = 0.0;
         for (int r = 0; r < 4; r++) ga += e.Jx[r][a] * tt[r];
@@ -627,7 +744,11 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
       Hadd[2][3] += e.hthps, Hadd[3][2] += e.hthps;
       Hadd[3][3] += e.hthps;
     }
-    if (!ok) return false;
+    if (!ob_all(ok)) return false;
+    for (int a = 0; a < 4; a++) {  // combine the pairs' Schur complements (upper triangle, then mirror)
+      gadd[a] = ob_sum(gadd[a]);
+      for (int bb = a; bb < 4; bb++) Hadd[a][bb] = Hadd[bb][a] = ob_sum(Hadd[a][bb]);
+    }
     if (k == N) {
       for (int i = 0; i < NX; i++) {
         for (int j = 0; j < NX; j++) Pn[i][j] = p.Q2[SY(i, j)] + ((i < 4 && j < 4) ? Hadd[i][j] : 0.0);
@@ -671,8 +792,8 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
       const double bh0 = g[6] + dt * h[5], bh1 = g[7] + dt * h[4];
       kff[0] = i00 * bh0 + i01 * bh1;
       kff[1] = i01 * bh0 + i11 * bh1;
-      for (int j = 0; j < NX; j++) str(ps, oK + j, Kf[0][j]), str(ps, oK + NX + j, Kf[1][j]);
-      str(ps, oKFF, kff[0]), str(ps, oKFF + 1, kff[1]);
+      for (int j = 0; j < NX; j++) bst(ps, oK + j, Kf[0][j]), bst(ps, oK + NX + j, Kf[1][j]);
+      bst(ps, oKFF, kff[0]), bst(ps, oKFF + 1, kff[1]);
       if (has_x) {
         Hes ho;
         stage_hess(p, m, ln, ho);
@@ -705,12 +826,13 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
     }
     if (has_x) {
       for (int i = 0; i < NX; i++) {
-        str(ps, oPV + i, pn[i]);
-        for (int j = i; j < NX; j++) str(ps, oP + SY(i, j), Pn[i][j]);
+        bst(ps, oPV + i, pn[i]);
+        for (int j = i; j < NX; j++) bst(ps, oP + SY(i, j), Pn[i][j]);
       }
-      for (int i = 0; i < NX; i++) xn[i] = w[i], ln[i] = ldr(ps, oLAM + i);
+      for (int i = 0; i < NX; i++) xn[i] = w[i], ln[i] = bld(ps, oLAM + i);
     }
   }
+  ob_sync();
   return true;
 }
 
@@ -730,6 +852,9 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
   const int N = p.N;
   di.a_pr = di.a_du = 1.0;
   di.gphi_d = 0.0;
+  Dir dq;  // the pairs' share: per-lane partial step limits and grad(phi)'d
+  dq.a_pr = dq.a_du = 1.0;
+  dq.gphi_d = 0.0;
   double dx[NX];
   for (int i = 0; i < NX; i++) dx[i] = 0.0;
   for (int k = 0; k <= N; k++) {
@@ -740,8 +865,8 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
       double ref[NW];
       for (int j = 0; j < NW; j++) {
         const bool on = (j < NX) || has_u;
-        w[j] = on ? ldr(ps, oW + j) : 0.0;
-        ref[j] = on ? ldr(ps, oREF + j) : 0.0;
+        w[j] = on ? bld(ps, oW + j) : 0.0;
+        ref[j] = on ? bld(ps, oREF + j) : 0.0;
       }
       for (int i = 0; i < NX; i++) {
         double s = 0.0;
@@ -756,73 +881,69 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
     dw[6] = dw[7] = 0.0;
     if (has_u) {
       for (int i = 0; i < NU; i++) {
-        double s = -ldr(ps, oKFF + i);
-        for (int j = 0; j < NX; j++) s -= ldr(ps, oK + i * NX + j) * dx[j];
+        double s = -bld(ps, oKFF + i);
+        for (int j = 0; j < NX; j++) s -= bld(ps, oK + i * NX + j) * dx[j];
         dw[NX + i] = s;
       }
     }
     for (int j = 0; j < NW; j++) {
       const bool var = (j < NX) ? has_x : has_u;
       if (!var) continue;
-      str(ps, oDW + j, dw[j]);
+      bst(ps, oDW + j, dw[j]);
       double gb = g[j];
       if (var_lo(p, j)) {
         const double dist = w[j] - p.lo[j];
         gb -= mu * tt_rcp(dist);
-        limit_lo(dist, dw[j], ldr(ps, oZL + j), mu, tau, di);
+        limit_lo(dist, dw[j], bld(ps, oZL + j), mu, tau, di);
       }
       if (var_up(p, j)) {
         const double dist = p.up[j] - w[j];
         gb += mu * tt_rcp(dist);
-        limit_lo(dist, -dw[j], ldr(ps, oZU + j), mu, tau, di);
+        limit_lo(dist, -dw[j], bld(ps, oZU + j), mu, tau, di);
       }
       di.gphi_d += gb * dw[j];
     }
     // pairs: dv = -K_vv^-1 (q + K_vx dxt),  ds = J_x dxt + J_v dv + r_c
     Trig t;
     stage_trig(w, t);
-    for (int pj = 0; pj < o.P; pj++) {
+    OB_FOR_LANES(pj, o.P) {
       double* pp = pair_ptr(ps, pj);
-      double v[8], zv[8], s[4], y[4], zs[6];
-      for (int i = 0; i < 8; i++) v[i] = ldr(pp, qV + i), zv[i] = ldr(pp, qZV + i);
-      for (int i = 0; i < 4; i++) s[i] = ldr(pp, qS + i), y[i] = ldr(pp, qY + i);
-      for (int i = 0; i < 6; i++) zs[i] = ldr(pp, qZS + i);
+      double v[8], zv[8], s[4], zs[6];
+      for (int i = 0; i < 8; i++) v[i] = pld(pp, qV + i), zv[i] = pld(pp, qZV + i);
+      for (int i = 0; i < 4; i++) s[i] = pld(pp, qS + i);
+      for (int i = 0; i < 6; i++) zs[i] = pld(pp, qZS + i);
       PairEval e;
-      pair_eval(o, pj & 1, o.b[pj], t, v, y, e);
+      pair_eval<false>(o, pj & 1, o.b[pj], t, v, nullptr, e);
       SlackBar sb;
       slack_bar(o, s, zs, delta, sb);
-      double K[8][8], Kvx[8][4], q[8], tt[4];
-      pair_system(o, e, sb, v, zv, s, mu, delta, K, Kvx, q, tt);
-      chol8(K);
       double dv[8];
       for (int i = 0; i < 8; i++) {
-        double a = q[i];
-        for (int cc = 0; cc < 4; cc++) a += Kvx[i][cc] * dx[cc];
+        double a = pld(pp, qA + i);
+        if (has_x)
+          for (int cc = 0; cc < 4; cc++) a += pld(pp, qG + 4 * i + cc) * dx[cc];
         dv[i] = -a;
       }
-      fsub8(K, dv);
-      bsub8(K, dv);
       double ds[4];
       for (int r = 0; r < 4; r++) {
         double a = e.d[r] - s[r];
         for (int cc = 0; cc < 4; cc++) a += e.Jx[r][cc] * dx[cc];
         for (int i = 0; i < 8; i++) a += e.Jv[r][i] * dv[i];
         ds[r] = a;
-        str(pp, qDS + r, a);
-        di.gphi_d += mu * sb.gs1[r] * a;
+        pst(pp, qDS + r, a);
+        dq.gphi_d += mu * sb.gs1[r] * a;
       }
       for (int i = 0; i < 8; i++) {
-        str(pp, qDV + i, dv[i]);
+        pst(pp, qDV + i, dv[i]);
         const double dist = v[i] - o.v_lo;
-        di.gphi_d -= mu * tt_rcp(dist) * dv[i];
-        limit_lo(dist, dv[i], zv[i], mu, tau, di);
+        dq.gphi_d -= mu * tt_rcp(dist) * dv[i];
+        limit_lo(dist, dv[i], zv[i], mu, tau, dq);
       }
-      limit_lo(o.s_up - s[0], -ds[0], zs[0], mu, tau, di);
-      limit_lo(s[1] - o.c2_lo, ds[1], zs[1], mu, tau, di);
-      limit_lo(o.c2_up - s[1], -ds[1], zs[2], mu, tau, di);
-      limit_lo(s[2] - o.c2_lo, ds[2], zs[3], mu, tau, di);
-      limit_lo(o.c2_up - s[2], -ds[2], zs[4], mu, tau, di);
-      limit_lo(o.s_up - s[3], -ds[3], zs[5], mu, tau, di);
+      limit_lo(o.s_up - s[0], -ds[0], zs[0], mu, tau, dq);
+      limit_lo(s[1] - o.c2_lo, ds[1], zs[1], mu, tau, dq);
+      limit_lo(o.c2_up - s[1], -ds[1], zs[2], mu, tau, dq);
+      limit_lo(s[2] - o.c2_lo, ds[2], zs[3], mu, tau, dq);
+      limit_lo(o.c2_up - s[2], -ds[2], zs[4], mu, tau, dq);
+      limit_lo(o.s_up - s[3], -ds[3], zs[5], mu, tau, dq);
     }
     if (has_u) {  // dx_{k+1} = A dx + B du - c_{k+1};  lambda+_{k+1} = -(p_{k+1} + P_{k+1} dx_{k+1})
       double* pq = c.stage(k + 1);
@@ -833,15 +954,19 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
       A_mul(m, dx, nd);
       nd[4] += p.dt * dw[7];
       nd[5] += p.dt * dw[6];
-      for (int i = 0; i < NX; i++) nd[i] -= ldr(pq, oW + i) - w[i] - p.dt * f[i];
+      for (int i = 0; i < NX; i++) nd[i] -= bld(pq, oW + i) - w[i] - p.dt * f[i];
       for (int i = 0; i < NX; i++) {
-        double s = ldr(pq, oPV + i);
-        for (int j = 0; j < NX; j++) s += ldr(pq, oP + SY(i, j)) * nd[j];
-        str(pq, oLAMP + i, -s);
+        double s = bld(pq, oPV + i);
+        for (int j = 0; j < NX; j++) s += bld(pq, oP + SY(i, j)) * nd[j];
+        bst(pq, oLAMP + i, -s);
       }
       for (int i = 0; i < NX; i++) dx[i] = nd[i];
     }
   }
+  di.a_pr = tt_min(di.a_pr, ob_min(dq.a_pr));
+  di.a_du = tt_min(di.a_du, ob_min(dq.a_du));
+  di.gphi_d += ob_sum(dq.gphi_d);
+  ob_sync();
 }
 
 // ---- sweep 4: theta and phi at the trial point w + alpha*dw ----
@@ -855,6 +980,8 @@ TT_HD void trial(const Ctx& c, double alpha, TrialOut& tr) {
   const int N = p.N;
   double J = 0.0, sumlog = 0.0, theta = 0.0;
   bool inside = true;
+  double q_sumlog = 0.0, q_theta = 0.0;  // the pairs' share (per-lane partials)
+  bool q_inside = true;
   double xn[NX];
   for (int i = 0; i < NX; i++) xn[i] = 0.0;
   for (int k = N; k >= 0; k--) {
@@ -863,19 +990,19 @@ TT_HD void trial(const Ctx& c, double alpha, TrialOut& tr) {
     double w[NW];
     for (int j = 0; j < NW; j++) {
       const bool on = (j < NX) || has_u, var = (j < NX) ? has_x : has_u;
-      w[j] = on ? ldr(ps, oW + j) : 0.0;
-      if (var) w[j] += alpha * ldr(ps, oDW + j);
+      w[j] = on ? bld(ps, oW + j) : 0.0;
+      if (var) w[j] += alpha * bld(ps, oDW + j);
     }
     {
       double d6[NX];
-      for (int i = 0; i < NX; i++) d6[i] = w[i] - ldr(ps, oREF + i);
+      for (int i = 0; i < NX; i++) d6[i] = w[i] - bld(ps, oREF + i);
       for (int i = 0; i < NX; i++) {
         double s = 0.0;
         for (int j = 0; j < NX; j++) s += p.Q2[SY(i, j)] * d6[j];
         J += 0.5 * s * d6[i];
       }
       if (has_u) {
-        const double da = w[6] - ldr(ps, oREF + 6), dw_ = w[7] - ldr(ps, oREF + 7);
+        const double da = w[6] - bld(ps, oREF + 6), dw_ = w[7] - bld(ps, oREF + 7);
         J += 0.5 * (da * (p.R2[0] * da + p.R2[1] * dw_) + dw_ * (p.R2[1] * da + p.R2[2] * dw_));
       }
     }
@@ -902,33 +1029,34 @@ TT_HD void trial(const Ctx& c, double alpha, TrialOut& tr) {
     }
     Trig t;
     stage_trig(w, t);
-    for (int pj = 0; pj < o.P; pj++) {
+    OB_FOR_LANES(pj, o.P) {
       const double* pp = pair_ptr(ps, pj);
       double v[8], s[4], d[4];
       double pprod = 1.0;
       for (int i = 0; i < 8; i++) {
-        v[i] = ldr(pp, qV + i) + alpha * ldr(pp, qDV + i);
+        v[i] = pld(pp, qV + i) + alpha * pld(pp, qDV + i);
         const double sl = v[i] - o.v_lo;
-        if (!(sl > 0.0)) inside = false;
+        if (!(sl > 0.0)) q_inside = false;
         pprod *= sl;
       }
-      for (int i = 0; i < 4; i++) s[i] = ldr(pp, qS + i) + alpha * ldr(pp, qDS + i);
+      for (int i = 0; i < 4; i++) s[i] = pld(pp, qS + i) + alpha * pld(pp, qDS + i);
       pair_rows(o, pj & 1, o.b[pj], t, v, d);
-      for (int i = 0; i < 4; i++) theta += fabs(d[i] - s[i]);
+      for (int i = 0; i < 4; i++) q_theta += fabs(d[i] - s[i]);
       const double dist[6] = {o.s_up - s[0], s[1] - o.c2_lo, o.c2_up - s[1], s[2] - o.c2_lo, o.c2_up - s[2], o.s_up - s[3]};
       for (int i = 0; i < 6; i++) {
-        if (!(dist[i] > 0.0)) inside = false;
+        if (!(dist[i] > 0.0)) q_inside = false;
         pprod *= dist[i];
       }
-      sumlog += log(pprod);
+      q_sumlog += log(pprod);
     }
     for (int j = 0; j < NX; j++) xn[j] = w[j];
   }
-  tr.J = J, tr.sumlog = sumlog, tr.theta = theta, tr.inside = inside;
+  tr.J = J, tr.sumlog = sumlog + ob_sum(q_sumlog), tr.theta = theta + ob_sum(q_theta);
+  tr.inside = inside && ob_all(q_inside);
 }
 
 // ------------------------------------------------------------------------------------------------
-// the interior-point driver of one lane (same rules as ttmpc_core.cuh's ipm_backward / ipm_step), written as a state
+// the interior-point driver of one problem (same rules as ttmpc_core.cuh's ipm_backward / ipm_step), written as a state
 // machine so that the CUDA kernel can keep the 32 lanes of a warp in the same sweep although their problems are at
 // different iterations:  head (update_stats + termination tests + barrier update)  ->  factor_once until the inertia
 // is right  ->  direction  ->  trial_once until a step is accepted.
@@ -1008,6 +1136,11 @@ TT_HD bool lane_head(const Ctx& c, Lane& L, Result& res) {
     L.tau = fmax(kTauMin, 1.0 - L.mu);
     L.f_n = 0;
   }
+#ifdef TTMPC_OBCA_TRACE
+  if (ob_lane0())
+    printf("it %3d mu %.2e J %.12e theta %.3e rd %.3e cinf %.2e cmax %.2e lam1 %.3e z1 %.3e | prev: alpha %.3e adu %.3e delta %.1e\n",
+           L.iter, L.mu, st.J, st.theta, st.rd_inf, st.cinf, st.cmax, st.lam1, st.z1, L.alpha, L.alpha_du, L.delta_step);
+#endif
   L.theta = st.theta;
   L.phi = st.J - L.mu * st.sumlog;
   L.lam1 = st.lam1;
@@ -1114,7 +1247,7 @@ TT_HD bool lane_trial_once(const Ctx& c, Lane& L, Result& res) {
 // sequential driver (host emulation; the CUDA kernel interleaves the same phases across the lanes of a warp)
 TT_HD void solve_lane(const Params& p, const ObParams& o, double* s0, const ProblemIn& in, long long b, Result& res) {
   Ctx c;
-  c.p = &p, c.o = &o, c.s0 = s0, c.sstride = (size_t)stage_rows(o.P) * kBank;
+  c.p = &p, c.o = &o, c.s0 = s0;
   Lane L;
   lane_begin(p, o, init_point(c, in, b), L);
   for (;;) {
@@ -1127,12 +1260,12 @@ TT_HD void solve_lane(const Params& p, const ObParams& o, double* s0, const Prob
   }
 }
 
-// states / inputs of the lane's iterate in the plain layout [x_0, u_0, ..., x_N] (what _split_decision_variables of
+// states / inputs of the problem's iterate in the plain layout [x_0, u_0, ..., x_N] (what _split_decision_variables of
 // mpc_control_obs.py:241-281 returns; the dual variables mu, lam are not part of the controller's output)
-TT_HD void unpack(const Params& p, const ObParams& o, const double* s0, double* z) {
-  const size_t sstride = (size_t)stage_rows(o.P) * kBank;
-  for (int k = 0; k <= p.N; k++)
-    for (int j = 0; j < ((k < p.N) ? NW : NX); j++) z[k * NW + j] = ldr(s0 + (size_t)k * sstride, oW + j);
+TT_HD void unpack(const Params& p, const double* s0, double* z) {
+  for (int k = 0; k <= p.N; k++) {
+    OB_FOR_LANES(j, (k < p.N) ? NW : NX) z[k * NW + j] = bld(s0 + (size_t)k * kStageDoubles, oW + j);
+  }
 }
 
 }  // namespace obca

@@ -34,7 +34,7 @@ def to_np(r):
 
 
 # ----------------------------------------------------------------------------- golden fixtures
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "*.npz"))), ids=os.path.basename)
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "solves_*.npz"))), ids=os.path.basename)
 def test_gpu_matches_golden(path, torch_cuda):
     cfg, g = load_golden(path)
     s = make_solver(cfg)

@@ -39,8 +39,8 @@ cases = [  # (name, N, k0, obstacles, sigma)
     ("n3_k340_11obs", 3, 340, nearest(340, 11), 0.002),
     ("n8_k200_11obs", 8, 200, nearest(200, 11), 0.002),
     ("n30_k290_2obs", 30, 290, nearest(290, 2), 0.002),
-    ("n12_k60_blocked", 12, 60, [blocking_obstacle(60, 12, 6, 0.05)], 0.002),
-    ("n10_k240_blocked2", 10, 240, [blocking_obstacle(240, 10, 5, 0.1)] + nearest(240, 2), 0.002),
+    ("n12_k60_blocked", 12, 60, [blocking_obstacle(60, 12, 6, 0.15)], 0.002),
+    ("n12_k200_blocked3", 12, 200, [blocking_obstacle(200, 12, 6, 0.15)] + nearest(200, 2), 0.002),
 ]
 out = {}
 rng = np.random.default_rng(4)

@@ -23,17 +23,17 @@ extern "C" int ttmpc_emu_obca_solve_batch(const ttmpc_config* cfg, const ttmpc_o
   obca::ObParams o;
   rc = obca::build_obparams(cfg, obs, &o);
   if (rc) return rc;
-  const int64_t L = B < 5 ? B : 5;  // a few lanes with refill, on distinct slots of one bank
-  std::vector<double> scratch(obca::scratch_doubles(p.N, o.P, 1), NAN);
+  const int64_t L = B < 3 ? B : 3;  // a few problem slots with refill
+  std::vector<double> scratch(obca::scratch_doubles(p.N, (size_t)L), NAN);
   ProblemIn in{x_init, ref_states, ref_inputs, nullptr, k_index, traj_states, traj_inputs, T, nullptr, nullptr};
   const size_t nz = 8 * (size_t)p.N + 6;
   for (int64_t l = 0; l < L; l++) {
-    double* s0 = obca::slot_ptr(scratch.data(), p.N, o.P, (size_t)l);
+    double* s0 = obca::slot_ptr(scratch.data(), p.N, (size_t)l);
     for (int64_t b = l; b < B; b += L) {
-      Result r;
+      Result r{};
       obca::solve_lane(p, o, s0, in, b, r);
-      if (z_out) obca::unpack(p, o, s0, z_out + b * nz);
-      if (u0_out) { u0_out[b * 2] = ldr(s0, obca::oW + 6); u0_out[b * 2 + 1] = ldr(s0, obca::oW + 7); }
+      if (z_out) obca::unpack(p, s0, z_out + b * nz);
+      if (u0_out) { u0_out[b * 2] = obca::bld(s0, obca::oW + 6); u0_out[b * 2 + 1] = obca::bld(s0, obca::oW + 7); }
       if (obj_out) obj_out[b] = r.obj;
       if (kkt_out) { kkt_out[b * 3] = r.dual_inf; kkt_out[b * 3 + 1] = r.constr_viol; kkt_out[b * 3 + 2] = r.compl_inf; }
       if (iters_out) iters_out[b] = r.iters;
