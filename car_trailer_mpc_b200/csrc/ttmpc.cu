@@ -499,12 +499,17 @@ constexpr int kObcaThreads = 256;  // 8 warps = 8 problem slots per CTA
 #define TTMPC_OBCA_MIN_BLOCKS 1
 #endif
 #ifndef TTMPC_OBCA_LOCKSTEP
-#define TTMPC_OBCA_LOCKSTEP 1
+#define TTMPC_OBCA_LOCKSTEP 2
 #endif
-#if TTMPC_OBCA_LOCKSTEP
-#define OB_CTA_ANY(x) __syncthreads_or(x)
+#if TTMPC_OBCA_LOCKSTEP == 1
+#define OB_CTA_ANY(x) __syncthreads_or(x)   // every phase aligned
+#define OB_ROUND_ANY(x) __syncthreads_or(x)
+#elif TTMPC_OBCA_LOCKSTEP == 2
+#define OB_CTA_ANY(x) (x)                   // only the start of an iteration aligned
+#define OB_ROUND_ANY(x) __syncthreads_or(x)
 #else
-#define OB_CTA_ANY(x) (x)  // warp-uniform by construction
+#define OB_CTA_ANY(x) (x)                   // warps run free (warp-uniform by construction)
+#define OB_ROUND_ANY(x) (x)
 #endif
 __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
     ttmpc_obca_kernel(const __grid_constant__ Params p, const __grid_constant__ obca::ObParams o, double* __restrict__ scratch,
@@ -533,7 +538,7 @@ __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
         exhausted = true;
       }
     }
-    if (!OB_CTA_ANY(active)) break;
+    if (!OB_ROUND_ANY(active)) break;
     Result res;
     bool done = false;
     if (active) done = obca::lane_head(c, L, res);

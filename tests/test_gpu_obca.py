@@ -128,3 +128,27 @@ def test_full_size_properties_config4():
     far = both & (geometry.clearance(S[np.minimum(ks[:, None] + np.arange(51), 400)], LOT).min(1) > 1.0)
     assert far.sum() > 100
     assert np.abs(g["u0"][far] - plain["u0"][far]).max() <= U0_ABS_TOL
+
+
+def test_closed_loop_with_the_obstacle_aware_controller():
+    """simulation.py:484-531 with USE_OBS_MPC: the headless loop drives MPCTrackingControlObs for 2 s of the manoeuvre
+    (40 control steps: the float-accumulated clock of simulation.py:484 stops short of t = 2.0).  Far from the parking-lot rectangles the collision rows are inactive, so the loop must
+    reproduce the loop run with the plain controller; every solve succeeds and the path keeps its distance."""
+    from car_trailer_mpc_b200 import MPCTrackingControl, MPCTrackingControlObs, TruckTrailerModel
+    from car_trailer_mpc_b200 import closed_loop as cl
+    S, U = pb.load_reference_trajectory()
+    N = 20
+    params = {"M": 0.15, "L1": 7.05, "L2": 12.45, "W1": 3.05, "W2": 2.95, "dt": 0.05, "horizon": N}
+    pi = np.pi
+    sb = {"lb": [-np.inf, -np.inf, -pi, -pi / 3, -pi / 4, -10.0], "ub": [np.inf, np.inf, pi, pi / 3, pi / 4, 10.0]}
+    ib = {"lb": [-5.0, -pi / 2], "ub": [5.0, pi / 2]}
+    args = (TruckTrailerModel(params), params, np.eye(6), 10.0 * np.eye(2), sb, ib)
+    obs_ctl = MPCTrackingControlObs(*args, obstacle_list=parking_lot_obstacles())
+    plain_ctl = MPCTrackingControl(*args)
+    x0 = S[0] + np.array([0.3, -0.2, 0.02, 0.0, 0.0, 0.0])
+    a = cl.simulate_single(obs_ctl, S, U, x0, 2.0, 0.05, N, params)
+    b = cl.simulate_single(plain_ctl, S, U, x0, 2.0, 0.05, N, params)
+    assert a.failures == 0 and b.failures == 0 and len(a.controls) == len(b.controls) >= 40
+    assert np.abs(a.controls - b.controls).max() <= U0_ABS_TOL
+    assert np.abs(a.states - b.states).max() <= 1e-5
+    assert geometry.clearance(a.states, LOT).min() >= 0.2
