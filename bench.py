@@ -378,4 +378,10 @@ def main() -> None:
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE line (the JSON record): libraries that print to fd 1 (NCCL's version banner, for one)
+    # are sent to stderr for the duration of the run, and the record is written to the real stdout at the end.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real_stdout, "w", buffering=1)
     main()
