@@ -172,7 +172,18 @@ def main() -> None:
         raise SystemExit("bench.py: no CUDA device -- the solver has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_bound = False
     if world > 1:
+        # one rank per GPU: run on the CPUs next to that GPU so that the pinned staging buffers of the e2e leg are
+        # first-touched on its NUMA node (8 ranks x 350 MB per step otherwise cross the socket interconnect)
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            numa_bound = True
+        except Exception as exc:  # best effort; the measurement is still valid without it
+            print(f"[bench] rank {rank}: CPU affinity not set ({exc})", file=sys.stderr)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -351,7 +362,7 @@ def main() -> None:
                     "h2d_bytes_per_step": int(x_h.numel() + xs_h.numel() + us_h.numel()) * 8,
                     "d2h_bytes_per_step": int(z_h.numel() + u0_h.numel()) * 8 + int(st_h.numel()) * 4,
                     "ms_per_step": e2e_total_ms / e2e_steps, "steps": e2e_steps,
-                    "mode": "3-stream pipeline over steps (copy-in | solve | copy-out), double-buffered",
+                    "mode": "3-stream pipeline over steps (copy-in | solve | copy-out), double-buffered", "cpu_affinity_to_gpu_numa_node": numa_bound,
                     "serial_ms_per_step": e2e_serial_ms / e2e_steps},
             "gpu_launches": int(launches),
             "kernels": {k: v for k, v in solver.kernel_launches().items() if v},
