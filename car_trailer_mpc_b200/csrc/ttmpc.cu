@@ -494,7 +494,10 @@ static episode_kernel_t episode_kernel_for(const Params& p) {
 // ------------------------------------------------------------------------------------------------
 // obstacle-aware (OBCA) solve: one lane per problem, lanes pull problems from a global queue (ttmpc_obca.cuh)
 // ------------------------------------------------------------------------------------------------
-constexpr int kObcaThreads = 256;  // 8 warps = 8 problem slots per CTA
+#ifndef TTMPC_OBCA_THREADS
+#define TTMPC_OBCA_THREADS 256
+#endif
+constexpr int kObcaThreads = TTMPC_OBCA_THREADS;  // 8 warps = 8 problem slots per CTA
 #ifndef TTMPC_OBCA_MIN_BLOCKS
 #define TTMPC_OBCA_MIN_BLOCKS 1
 #endif

@@ -58,6 +58,18 @@ else:
     wall = time.time() - t0
     rows = torch.stack([out["distance_error"], out["heading_error"].abs(), out["hitch_error"].abs(), out["max_abs_psi"],
                         out["jackknife"].double(), out["failures"].double(), out["mean_iters"], out["rms_tracking_error"]], 1)
+# LQR score of the final state (LQR_cost.py:7-41, simulation.py:563): P from the DARE at the goal linearisation is the same
+# for all scenarios -- solved once on the host, x'Px evaluated on the device, gathered as a ninth metric column
+goal = S[-1]
+try:
+    P = torch.as_tensor(cl.lqr_riccati(cfg, cfg.Qm(), cfg.Rm(), goal, np.zeros(2)), device=dev)
+    dxf = (r["final_state"] if args.device_loop else out["final_state"]) - torch.as_tensor(goal, device=dev)[None]
+    lqr = ((dxf @ P) * dxf).sum(1)
+except Exception as exc:  # the goal has v ~ -0.01: (A, B) is barely controllable and the DARE may fail
+    if rank == 0:
+        print(f"[monte_carlo] LQR score unavailable: {exc}", file=sys.stderr)
+    lqr = torch.full((rows.shape[0],), float("nan"), dtype=torch.float64, device=dev)
+rows = torch.cat([rows, lqr[:, None]], 1)
 allrows = sharding.gather_rows(rows, args.scenarios)          # NCCL all-gather of the per-scenario metric rows
 red = sharding.reduce_metrics({"jackknife": float(out["jackknife"].sum()), "failures": float(out["failures"].sum()),
                                "psi_max": float(out["max_abs_psi"].max()), "iters_max": float(out["max_iters"].max())})
@@ -65,13 +77,12 @@ if rank == 0:
     a = allrows.cpu().numpy()
     steps = out["steps"]
     q = lambda c: [float(np.percentile(a[:, c], p)) for p in (50, 99, 100)]
-    goal = S[-1]
-    P = cl.lqr_riccati(cfg, cfg.Qm(), cfg.Rm(), goal, np.zeros(2)) if False else None
     summary = {"scenarios": args.scenarios, "gpus": world, "steps": steps, "horizon": args.horizon, "disturbances": not args.nominal, "device_loop": bool(args.device_loop),
                "solves": args.scenarios * steps, "wall_s": wall, "solves_per_s": args.scenarios * steps / wall,
                "jackknife_rate": red["jackknife"] / args.scenarios, "solver_failures": red["failures"], "max_abs_psi": red["psi_max"],
                "max_iters": red["iters_max"], "distance_error_p50_p99_max": q(0), "heading_error_p50_p99_max": q(1),
                "hitch_error_p50_p99_max": q(2), "mean_iters_p50_p99_max": q(6), "rms_tracking_error_p50_p99_max": q(7),
+               "lqr_distance_p50_p99_max": q(8),
                "checksum_first_1024": float(a[:1024].sum())}
     print(json.dumps(summary))
     if args.out:
