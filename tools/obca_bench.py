@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("B", type=int); ap.add_argument("N", type=int); ap.add_argument("sigma", type=float)
 ap.add_argument("--check-emu", type=int, default=0); ap.add_argument("--json", default=None)
 ap.add_argument("--steps", type=int, default=1); ap.add_argument("--max-iter", type=int, default=300)
+ap.add_argument("--cpu-sample", type=int, default=0, help="also time the host build of the same solver core on the first M problems (one thread)")
 a = ap.parse_args()
 cfg = tracking_preset(a.N); cfg.max_iter = a.max_iter
 S, U = pb.load_reference_trajectory()
@@ -39,6 +40,15 @@ res = dict(B=a.B, N=a.N, sigma=a.sigma, obstacles=11, ms=float(np.mean(ts)), sol
            status_hist=np.bincount(st, minlength=6).tolist(), iters_mean=float(it.mean()), iters_max=int(it.max()),
            iters_mean_converged=float(it[ok].mean()) if ok.any() else None,
            kkt_max_converged=kkt[ok].max(0).tolist() if ok.any() else None)
+if a.cpu_sample:
+    import emu
+    M = min(a.cpu_sample, a.B)
+    t = time.time()
+    e = emu.obca_solve_batch(cfg, obs, x0[:M], k_index=ks[:M], traj_states=S, traj_inputs=U)
+    dt_cpu = time.time() - t
+    res["cpu_port"] = dict(solves_per_s=M / dt_cpu, cores=1, sample=f"first {M} problems, host build of the kernel's solver core "
+                           "(tools/obca_emu.cpp, g++ -O2, one thread); the reference's CasADi/Ipopt is not installable here",
+                           iters_mean=float(e["iters"].mean()), status_equal_gpu=float((e["status"] == st[:M]).mean()))
 print(json.dumps(res))
 if a.json:
     json.dump(res, open(a.json, "w"), indent=1)
