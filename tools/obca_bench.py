@@ -15,12 +15,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("B", type=int); ap.add_argument("N", type=int); ap.add_argument("sigma", type=float)
 ap.add_argument("--check-emu", type=int, default=0); ap.add_argument("--json", default=None)
 ap.add_argument("--steps", type=int, default=1); ap.add_argument("--max-iter", type=int, default=300)
+ap.add_argument("--kmax", type=int, default=400, help="window starts are uniform in 0..kmax (beyond k = 345 the shipped trajectory rides d_min exactly: perturbed starts there are infeasible)")
 ap.add_argument("--cpu-sample", type=int, default=0, help="also time the host build of the same solver core on the first M problems (one thread)")
 a = ap.parse_args()
 cfg = tracking_preset(a.N); cfg.max_iter = a.max_iter
 S, U = pb.load_reference_trajectory()
 rng = np.random.default_rng(20251018)
-ks = rng.integers(0, 401, a.B).astype(np.int32)
+ks = rng.integers(0, a.kmax + 1, a.B).astype(np.int32)
 lb = np.array(cfg.x_lb[:]); ub = np.array(cfg.x_ub[:])
 x0 = S[np.minimum(ks, 400)] + rng.normal(0, a.sigma, (a.B, 6))
 x0[:, 2:] = np.clip(x0[:, 2:], lb[2:] + 1e-3, ub[2:] - 1e-3)
@@ -36,7 +37,7 @@ for i in range(a.steps + 1):
     if a.steps == 0: break
 it = r["iters"].cpu().numpy(); st = r["status"].cpu().numpy(); kkt = r["kkt"].cpu().numpy()
 ok = st <= 1
-res = dict(B=a.B, N=a.N, sigma=a.sigma, obstacles=11, ms=float(np.mean(ts)), solves_per_s=a.B / np.mean(ts) * 1e3,
+res = dict(B=a.B, N=a.N, sigma=a.sigma, kmax=a.kmax, obstacles=11, ms=float(np.mean(ts)), solves_per_s=a.B / np.mean(ts) * 1e3,
            status_hist=np.bincount(st, minlength=6).tolist(), iters_mean=float(it.mean()), iters_max=int(it.max()),
            iters_mean_converged=float(it[ok].mean()) if ok.any() else None,
            kkt_max_converged=kkt[ok].max(0).tolist() if ok.any() else None)
