@@ -340,6 +340,12 @@ TT_HD void pair_system(const ObParams& o, const PairEval& e, const SlackBar& sb,
   const double ax[4] = {1.0, 0.0, -1.0, 0.0}, ay[4] = {0.0, 1.0, 0.0, -1.0};  // rows of A_o
   TT_UNROLL
   for (int r = 0; r < 4; r++) t[r] = sb.D[r] * (e.d[r] - s[r]) + mu * sb.gs1[r];
+  double DJ[4][8];  // D_r * J_v[r][i]
+  TT_UNROLL
+  for (int r = 0; r < 4; r++) {
+    TT_UNROLL
+    for (int i = 0; i < 8; i++) DJ[r][i] = sb.D[r] * e.Jv[r][i];
+  }
   TT_UNROLL
   for (int i = 0; i < 8; i++) {
     const double rv = tt_rcp(v[i] - o.v_lo);
@@ -347,7 +353,7 @@ TT_HD void pair_system(const ObParams& o, const PairEval& e, const SlackBar& sb,
     for (int j = 0; j <= i; j++) {
       double a = 0.0;
       TT_UNROLL
-      for (int r = 0; r < 4; r++) a += sb.D[r] * e.Jv[r][i] * e.Jv[r][j];
+      for (int r = 0; r < 4; r++) a += DJ[r][i] * e.Jv[r][j];
       if (i >= 4 && j >= 4) {
         const int ii = i - 4, jj = j - 4;
         a += ax[ii] * (e.Wll[0] * ax[jj] + e.Wll[1] * ay[jj]) + ay[ii] * (e.Wll[1] * ax[jj] + e.Wll[2] * ay[jj]);
@@ -363,7 +369,7 @@ TT_HD void pair_system(const ObParams& o, const PairEval& e, const SlackBar& sb,
     for (int c = 0; c < 4; c++) {
       double a = 0.0;
       TT_UNROLL
-      for (int r = 0; r < 4; r++) a += sb.D[r] * e.Jv[r][i] * e.Jx[r][c];
+      for (int r = 0; r < 4; r++) a += DJ[r][i] * e.Jx[r][c];
       if (i >= 4) a += ax[i - 4] * e.Wxl[c][0] + ay[i - 4] * e.Wxl[c][1];
       Kvx[i][c] = a;
     }
@@ -758,8 +764,6 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
     } else {
       Lin m;
       stage_lin(p, w, m);
-      double A[NX][NX];
-      dense_A(m, A);
       const double f[NX] = {m.f0, m.f1, m.f2, m.f3, w[7], w[6]};
       double h[NX], cdef[NX];
       for (int i = 0; i < NX; i++) cdef[i] = xn[i] - w[i] - dt * f[i];
@@ -768,13 +772,8 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
         for (int j = 0; j < NX; j++) s -= Pn[i][j] * cdef[j];
         h[i] = s;
       }
-      double PA[NX][NX];
-      for (int i = 0; i < NX; i++)
-        for (int j = 0; j < NX; j++) {
-          double s = 0.0;
-          for (int l = 0; l < NX; l++) s += Pn[i][l] * A[l][j];
-          PA[i][j] = s;
-        }
+      double PA[NX][NX];  // A = I + dt df/dx has 9 off-diagonal entries: row i of P A is A' applied to row i of P
+      for (int i = 0; i < NX; i++) At_mul(m, Pn[i], PA[i]);
       // B has two entries: B[5][0] = B[4][1] = dt
       const double r00 = p.R2[0] + dt * dt * Pn[5][5] + sig[6], r01 = p.R2[1] + dt * dt * Pn[5][4];
       const double r11 = p.R2[2] + dt * dt * Pn[4][4] + sig[7];
@@ -805,19 +804,16 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
         Hx[2][2] += ho.h22, Hx[2][5] += ho.h25, Hx[5][2] += ho.h25;
         Hx[3][3] += ho.h33, Hx[3][4] += ho.h34, Hx[4][3] += ho.h34, Hx[3][5] += ho.h35, Hx[5][3] += ho.h35;
         Hx[4][4] += ho.h44, Hx[4][5] += ho.h45, Hx[5][4] += ho.h45;
-        double Pk[NX][NX], pk[NX];
-        for (int i = 0; i < NX; i++) {
-          for (int j = 0; j < NX; j++) {
-            double s = Hx[i][j];
-            for (int l = 0; l < NX; l++) s += A[l][i] * PA[l][j];
-            s -= Sh[0][i] * Kf[0][j] + Sh[1][i] * Kf[1][j];
-            Pk[i][j] = s;
-          }
-          double s = g[i] + (i < 4 ? gadd[i] : 0.0);
-          for (int l = 0; l < NX; l++) s += A[l][i] * h[l];
-          s -= Sh[0][i] * kff[0] + Sh[1][i] * kff[1];
-          pk[i] = s;
+        double Pk[NX][NX], pk[NX], ath[NX];
+        for (int j = 0; j < NX; j++) {  // column j of A'(P A)
+          double col[NX], acol[NX];
+          for (int l = 0; l < NX; l++) col[l] = PA[l][j];
+          At_mul(m, col, acol);
+          for (int i = 0; i < NX; i++) Pk[i][j] = Hx[i][j] + acol[i] - (Sh[0][i] * Kf[0][j] + Sh[1][i] * Kf[1][j]);
         }
+        At_mul(m, h, ath);
+        for (int i = 0; i < NX; i++)
+          pk[i] = g[i] + (i < 4 ? gadd[i] : 0.0) + ath[i] - (Sh[0][i] * kff[0] + Sh[1][i] * kff[1]);
         for (int i = 0; i < NX; i++) {
           pn[i] = pk[i];
           for (int j = 0; j < NX; j++) Pn[i][j] = 0.5 * (Pk[i][j] + Pk[j][i]);
