@@ -152,3 +152,32 @@ def test_closed_loop_with_the_obstacle_aware_controller():
     assert np.abs(a.controls - b.controls).max() <= U0_ABS_TOL
     assert np.abs(a.states - b.states).max() <= 1e-5
     assert geometry.clearance(a.states, LOT).min() >= 0.2
+
+
+def test_obca_edge_cases():
+    """Empty batch, the shortest horizon, the maximum obstacle count (16 -> all 32 lanes of the warp busy), a batch that
+    is not a multiple of the CTA's 8 problem slots, and a rejected obstacle set."""
+    import emu
+    from car_trailer_mpc_b200 import _lib
+    S, U = pb.load_reference_trajectory()
+    lot16 = parking_lot_obstacles() + [dict(center=(100.0 + 10 * i, -40.0), width=4.0, height=4.0) for i in range(5)]
+    for N, B, obst in ((1, 3, parking_lot_obstacles()), (7, 13, lot16)):
+        cfg = tracking_preset(N)
+        cfg.max_iter = 300
+        s = solver(cfg)
+        obs = Obstacles.from_list(obst)
+        rng = np.random.default_rng(N)
+        ks = rng.integers(0, 300, B).astype(np.int32)
+        xs, us = pb.windows_batch(S, U, ks, N)
+        x0 = xs[:, 0] + rng.normal(0, 0.002, (B, 6))
+        g = s.solve_obca(obs, x0, xs, us)
+        e = emu.obca_solve_batch(cfg, obs, x0, xs, us)
+        assert np.array_equal(g["status"], e["status"]) and (g["status"] == 0).all()
+        assert np.abs(g["z"] - e["z"]).max() <= Z_TOL
+        empty = s.solve_obca(obs, np.zeros((0, 6)), np.zeros((0, N + 1, 6)), np.zeros((0, N, 2)))
+        assert empty["u0"].shape == (0, 2)
+    bad = Obstacles.from_list([(0.0, 0.0, 0.0, 1.0)])  # zero width
+    with pytest.raises(_lib.TTMPCError):
+        s.solve_obca(bad, x0, xs, us)
+    with pytest.raises(ValueError):
+        Obstacles.from_list([(0.0, 0.0, 1.0, 1.0)] * 17)
