@@ -550,6 +550,7 @@ __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
   const int lane = threadIdx.x & 31;
   const size_t slot = ((size_t)blockIdx.x * kObcaThreads + threadIdx.x) >> 5;
   obca::Ctx c;
+  c.wd.wid = 0, c.wd.nw = 1, c.wd.part = nullptr, c.wd.bcast = nullptr;
   c.p = &p, c.o = &o, c.s0 = obca::slot_ptr(scratch, p.N, slot);
   const long long nz = 8LL * p.N + 6;
   obca::Lane L;
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
       if (lane == 0) b = (long long)atomicAdd(counter, 1ull);
       b = __shfl_sync(0xffffffffu, b, 0);
       if (b < B) {
-        obca::lane_begin(p, o, obca::init_point(c, in, b), L);
+        obca::lane_begin(p, o, obca::init_point<false>(c, in, b), L);
         active = true;
       } else {
         exhausted = true;
@@ -596,7 +597,50 @@ __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
   }
 }
 
-constexpr int kNumKernels = 8;
+// Small batches (the B = 1 call of the MPCTrackingControlObs shim above all): one CTA per problem.  The stages are dealt
+// to the 8 warps for the pair work of every sweep, the recursions over the stages (Riccati, dx, the in-place update) run
+// on warp 0, statistics meet in shared memory (obca::run_* wrappers).  Same arithmetic as ttmpc_obca_kernel: the host
+// build of this decomposition reproduces the single-warp results bit for bit (tests/test_obca_cpu.py).
+__global__ void __launch_bounds__(kObcaThreads, 1)
+    ttmpc_obca_wide_kernel(const __grid_constant__ Params p, const __grid_constant__ obca::ObParams o,
+                           double* __restrict__ scratch, long long B, ProblemIn in, SolveOut out, unsigned long long* counter) {
+  __shared__ double s_part[(kObcaThreads / 32) * obca::kPart];
+  __shared__ double s_bcast[32];
+  __shared__ long long s_b;
+  obca::Ctx c;
+  c.wd.wid = (int)(threadIdx.x >> 5), c.wd.nw = (int)(blockDim.x >> 5), c.wd.part = s_part, c.wd.bcast = s_bcast;
+  c.p = &p, c.o = &o, c.s0 = obca::slot_ptr(scratch, p.N, blockIdx.x);
+  const long long nz = 8LL * p.N + 6;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_b = (long long)atomicAdd(counter, 1ull);
+    __syncthreads();
+    const long long b = s_b;
+    if (b >= B) break;
+    Result res;
+    obca::solve_problem<true>(c, in, b, res);
+    __syncthreads();
+    if (c.wd.wid == 0) {
+      if (out.z) obca::unpack(p, c.s0, out.z + b * nz);
+      if ((threadIdx.x & 31) == 0) {
+        if (out.u0) {
+          out.u0[2 * b] = obca::bld(c.s0, obca::oW + 6);
+          out.u0[2 * b + 1] = obca::bld(c.s0, obca::oW + 7);
+        }
+        if (out.obj) out.obj[b] = res.obj;
+        if (out.kkt) {
+          out.kkt[3 * b] = res.dual_inf;
+          out.kkt[3 * b + 1] = res.constr_viol;
+          out.kkt[3 * b + 2] = res.compl_inf;
+        }
+        if (out.iters) out.iters[b] = res.iters;
+        if (out.status) out.status[b] = res.status;
+      }
+    }
+  }
+}
+
+constexpr int kNumKernels = 9;
 struct ttmpc_handle {
   ttmpc_config cfg;
   Params p;
@@ -620,7 +664,8 @@ struct ttmpc_handle {
 
 static const char* kKernelNames[kNumKernels] = {"ttmpc_solve_kernel", "ttmpc_shift_kernel", "ttmpc_plant_kernel",
                                                 "ttmpc_dfma_kernel", "ttmpc_classify_kernel", "ttmpc_order_kernel",
-                                                "ttmpc_episode_kernel", "ttmpc_obca_kernel"};
+                                                "ttmpc_episode_kernel", "ttmpc_obca_kernel",
+                                                "ttmpc_obca_wide_kernel"};
 
 static int set_err(ttmpc_handle* h, int code, const char* what, cudaError_t ce) {
   if (h) snprintf(h->err, sizeof h->err, "%s%s%s", what, ce != cudaSuccess ? ": " : "", ce != cudaSuccess ? cudaGetErrorString(ce) : "");
@@ -791,9 +836,14 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ttmpc_obca_kernel, kObcaThreads, 0);
   if (per_sm < 1) per_sm = 1;
-  const int wpc = kObcaThreads / 32;
+  // up to 12 problems per SM: one CTA per problem (measured on B200, N = 50: 35 vs 73 ms for one problem, 575 vs 692 ms
+  // for 1 184, equal at 2 048); beyond that: one warp per problem (16 384: 3.8 vs 6.3 s)
+  const char* wenv = getenv("TTMPC_OBCA_WIDE_MAX");
+  const bool wide = B <= (wenv ? atoll(wenv) : 12LL * sms);
+  const int wpc = wide ? 1 : kObcaThreads / 32;
   long long blocks = (B + wpc - 1) / wpc;
-  if (blocks > (long long)sms * per_sm) blocks = (long long)sms * per_sm;
+  const long long cap = (long long)sms * (wide ? 1 : per_sm);
+  if (blocks > cap) blocks = cap;
   const size_t need = obca::scratch_doubles(h->p.N, (size_t)blocks * wpc);
   if (need > h->ob_doubles) {
     if (h->ob_scratch) cudaFree(h->ob_scratch);
@@ -804,8 +854,13 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
     h->ob_doubles = need;
   }
   cudaMemsetAsync(h->counter, 0, 16 * sizeof(unsigned long long), st);
-  ttmpc_obca_kernel<<<(unsigned)blocks, kObcaThreads, 0, st>>>(h->p, o, h->ob_scratch, B, in, so, h->counter);
-  h->launches[7]++;
+  if (wide) {
+    ttmpc_obca_wide_kernel<<<(unsigned)blocks, kObcaThreads, 0, st>>>(h->p, o, h->ob_scratch, B, in, so, h->counter);
+    h->launches[8]++;
+  } else {
+    ttmpc_obca_kernel<<<(unsigned)blocks, kObcaThreads, 0, st>>>(h->p, o, h->ob_scratch, B, in, so, h->counter);
+    h->launches[7]++;
+  }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "obca kernel launch", ce);
   return TTMPC_OK;

@@ -42,13 +42,14 @@ namespace obca {
 constexpr int kMaxPairs = 2 * TTMPC_MAX_OBSTACLES;
 // ---- scratch rows of one stage ----
 constexpr int oW = 0, oDW = 8, oREF = 16, oLAM = 24, oLAMP = 30, oZL = 36, oZU = 44, oK = 52, oKFF = 64, oP = 66, oPV = 87;
-constexpr int kBaseRows = 93;
+constexpr int oRP = 96, oHA = 100;  // wide mode only: the pairs' J_x'y (4) and condensed Hessian / gradient (4 + 10) of the stage
+constexpr int kBaseRows = 114;
 constexpr int qV = 0, qZV = 8, qS = 16, qY = 20, qZS = 24, qDV = 30, qDS = 38;  // rows of one pair
 constexpr int qA = 42, qG = 50;  // K_vv^-1 q (8) and K_vv^-1 K_vx (8x4, row-major): written by factor, read by direction
 constexpr int kPairRows = 82;
-constexpr int kBasePad = 96;                                 // base rows, padded to a multiple of 32 doubles
+constexpr int kBasePad = 128;                                // base rows, padded to a multiple of 32 doubles
 constexpr int kLanes = 32;                                   // pair slots per stage (>= kMaxPairs)
-constexpr int kStageDoubles = kBasePad + kPairRows * kLanes;  // 2720 doubles = 21.25 KB per stage and problem slot
+constexpr int kStageDoubles = kBasePad + kPairRows * kLanes;  // 2752 doubles = 21.5 KB per stage and problem slot
 inline size_t scratch_doubles(int N, size_t slots) { return slots * (size_t)(N + 1) * kStageDoubles; }
 TT_HD double* slot_ptr(double* scratch, int N, size_t slot) { return scratch + slot * (size_t)(N + 1) * kStageDoubles; }
 
@@ -379,7 +380,18 @@ TT_HD void pair_system(const ObParams& o, const PairEval& e, const SlackBar& sb,
 // ------------------------------------------------------------------------------------------------
 // per-lane solver state
 // ------------------------------------------------------------------------------------------------
+// "Wide" execution (one CTA per problem, for small batches where latency matters): the stages are dealt to the warps of
+// the CTA for the pair work (MODE 1 of a sweep: stage k belongs to warp k % nw), the recursions over the stages run on
+// warp 0 (MODE 2) using what the pair phase left in the stage's oRP / oHA rows; per-warp partial statistics go through
+// `part` (shared memory).  MODE 0 is the fused single-warp sweep.
+constexpr int kPart = 16;
+struct Wide {
+  int wid, nw;
+  double* part;   // [nw][kPart]
+  double* bcast;  // [32]: results of warp 0 for the other warps
+};
 struct Ctx {
+  Wide wd;
   const Params* p;
   const ObParams* o;
   double* s0;   // slot pointer (stage 0 of this problem slot)
@@ -401,12 +413,23 @@ TT_HD bool var_lo(const Params& p, int j) { return ((p.bl >> j) & 1u) != 0; }
 TT_HD bool var_up(const Params& p, int j) { return ((p.bu >> j) & 1u) != 0; }
 
 // ---- starting point (mpc_control_obs.py:216-239 + Ipopt's slack initialisation and interior push) ----
-TT_HD bool init_point(const Ctx& c, const ProblemIn& in, long long b) {
-  const Params& p = *c.p;
-  const ObParams& o = *c.o;
+template <bool WIDE>
+TT_HD bool init_point(const Ctx& c0, const ProblemIn& in, long long b) {
+  const Params& p = *c0.p;
+  const ObParams& o = *c0.o;
   const int N = p.N;
   bool x0_bad = false;
+  for (int j = 0; j < NX; j++) {
+    const double w = in.x_init[b * NX + j];
+    if ((var_lo(p, j) && w < p.lo[j]) || (var_up(p, j) && w > p.up[j])) x0_bad = true;
+  }
+  Ctx c = c0;
+#if !defined(__CUDA_ARCH__)
+  for (int wv = 0; wv < (WIDE ? c0.wd.nw : 1); wv++) {  // host: the warps of the CTA one after the other
+  c.wd.wid = wv;
+#endif
   for (int k = 0; k <= N; k++) {
+    if (WIDE && (k % c.wd.nw) != c.wd.wid) continue;
     double* ps = c.stage(k);
     double x[NX];
     for (int j = 0; j < NW; j++) {
@@ -417,7 +440,6 @@ TT_HD bool init_point(const Ctx& c, const ProblemIn& in, long long b) {
       double w;
       if (j < NX && k == 0) {
         w = in.x_init[b * NX + j];
-        if ((var_lo(p, j) && w < p.lo[j]) || (var_up(p, j) && w > p.up[j])) x0_bad = true;
       } else {
         w = tt_min(tt_max(r, p.lo_push[j]), p.up_push[j]);
       }
@@ -443,6 +465,9 @@ TT_HD bool init_point(const Ctx& c, const ProblemIn& in, long long b) {
       for (int i = 0; i < 6; i++) pst(pp, qZS + i, 1.0);
     }
   }
+#if !defined(__CUDA_ARCH__)
+  }
+#endif
   ob_sync();
   return x0_bad;
 }
@@ -450,6 +475,7 @@ TT_HD bool init_point(const Ctx& c, const ProblemIn& in, long long b) {
 TT_HD double clampz(double z, double rs, double hi, double lo) { return tt_max(tt_min(z, hi * rs), lo * rs); }
 
 // ---- sweep 1: apply the accepted step (optional) and gather the KKT statistics at the resulting iterate ----
+template <int MODE>
 TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha_du, double mu_step, double delta_step,
                         Stats& st) {
   const Params& p = *c.p;
@@ -462,6 +488,7 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
   double xn[NX], ln[NX];  // x_{k+1}, lambda_{k+1} at the new iterate
   for (int j = 0; j < NX; j++) xn[j] = ln[j] = 0.0;
   for (int k = N; k >= 0; k--) {
+    if (MODE == 1 && (k % c.wd.nw) != c.wd.wid) continue;
     double* ps = c.stage(k);
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW], ref[NW], zl[NW], zu[NW], lam[NX], dwv[NW], lamp[NX];
@@ -478,6 +505,11 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
       lamp[j] = (do_update && has_x) ? bld(ps, oLAMP + j) : 0.0;
     }
     ob_sync();  // every lane has read the shared rows of this stage before lane 0 overwrites them
+    double r[NW];
+    if (MODE == 1) {  // pair phase: only the new (x, y, theta, psi) of the stage is needed, nothing is stored
+      for (int j = 0; j < NX; j++)
+        if (do_update && has_x) w[j] = fma(alpha, dwv[j], w[j]);
+    } else {
     for (int j = 0; j < NW; j++) {
       const bool var = (j < NX) ? has_x : has_u;
       if (do_update && var) {
@@ -490,7 +522,7 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
           const double ru = tt_rcp(p.up[j] - w[j]);
           zu[j] += alpha_du * (ru * (mu_step + zu[j] * d) - zu[j]);
         }
-        w[j] += alpha * d;
+        w[j] = fma(alpha, d, w[j]);
         if (var_lo(p, j)) zl[j] = clampz(zl[j], tt_rcp(w[j] - p.lo[j]), khi, klo);
         if (var_up(p, j)) zu[j] = clampz(zu[j], tt_rcp(p.up[j] - w[j]), khi, klo);
         bst(ps, oW + j, w[j]);
@@ -505,7 +537,6 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
       }
     }
     // gradient of the Lagrangian wrt (x_k, u_k), without the pair terms yet
-    double r[NW];
     {
       double d6[NX];
       for (int i = 0; i < NX; i++) d6[i] = w[i] - ref[i];
@@ -556,10 +587,12 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
       r[6] -= p.dt * ln[5];
       r[7] -= p.dt * ln[4];
     }
+    }  // MODE != 1
     // pairs
     double rp[4] = {0.0, 0.0, 0.0, 0.0};  // J_x' y of this lane's pair(s)
     Trig t;
     stage_trig(w, t);
+    if (MODE != 2)
     OB_FOR_LANES(pj, o.P) {
       double* pp = pair_ptr(ps, pj);
       double v[8], zv[8], s[4], y[4], zs[6];
@@ -631,13 +664,41 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
         q_rd = tt_max(q_rd, fabs(-y[3] + zs[5]));
       }
     }
+    if (MODE == 1) {
+      if (has_x)
+        for (int cc = 0; cc < 4; cc++) bst(ps, oRP + cc, ob_sum(rp[cc]));
+      continue;
+    }
     if (has_x)
-      for (int cc = 0; cc < 4; cc++) r[cc] += ob_sum(rp[cc]);
+      for (int cc = 0; cc < 4; cc++) r[cc] += (MODE == 2) ? bld(ps, oRP + cc) : ob_sum(rp[cc]);
     for (int j = 0; j < NW; j++) {
       const bool var = (j < NX) ? has_x : has_u;
       if (var) rd_inf = tt_max(rd_inf, fabs(r[j]));
     }
     for (int j = 0; j < NX; j++) xn[j] = w[j], ln[j] = lam[j];
+  }
+  if (MODE == 1) {  // this warp's share of the pair statistics
+    const double v8[8] = {ob_sum(q_sumlog), ob_sum(q_theta), ob_max(q_cinf), ob_max(q_rd), ob_sum(q_lam1), ob_sum(q_z1),
+                          ob_max(q_cmax), ob_min(q_cmin)};
+    if (ob_lane0())
+      for (int i = 0; i < 8; i++) c.wd.part[c.wd.wid * kPart + i] = v8[i];
+    ob_sync();
+    return;
+  }
+  if (MODE == 2) {
+    q_sumlog = q_theta = q_cinf = q_rd = q_lam1 = q_z1 = q_cmax = 0.0;
+    q_cmin = INFINITY;
+    for (int w_ = 0; w_ < c.wd.nw; w_++) {
+      const double* pt = c.wd.part + w_ * kPart;
+      q_sumlog += pt[0], q_theta += pt[1], q_cinf = tt_max(q_cinf, pt[2]), q_rd = tt_max(q_rd, pt[3]);
+      q_lam1 += pt[4], q_z1 += pt[5], q_cmax = tt_max(q_cmax, pt[6]), q_cmin = tt_min(q_cmin, pt[7]);
+    }
+    st.J = J, st.sumlog = sumlog + q_sumlog, st.theta = theta + q_theta;
+    st.cinf = tt_max(cinf, q_cinf), st.rd_inf = tt_max(rd_inf, q_rd);
+    st.lam1 = lam1 + q_lam1, st.z1 = z1 + q_z1;
+    st.cmax = tt_max(cmax, q_cmax), st.cmin = tt_min(cmin, q_cmin);
+    ob_sync();
+    return;
   }
   st.J = J, st.sumlog = sumlog + ob_sum(q_sumlog), st.theta = theta + ob_sum(q_theta);
   st.cinf = tt_max(cinf, ob_max(q_cinf)), st.rd_inf = tt_max(rd_inf, ob_max(q_rd));
@@ -647,6 +708,7 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
 }
 
 // ---- sweep 2 (backward): condensation of the pairs + Riccati factorisation.  false: wrong inertia ----
+template <int MODE>
 TT_HD bool factor(const Ctx& c, double mu, double delta) {
   const Params& p = *c.p;
   const ObParams& o = *c.o;
@@ -657,7 +719,11 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
     pn[i] = xn[i] = ln[i] = 0.0;
     for (int j = 0; j < NX; j++) Pn[i][j] = 0.0;
   }
+  if (MODE == 2)  // the pair phase found a block that is not positive definite
+    for (int w_ = 0; w_ < c.wd.nw; w_++)
+      if (c.wd.part[w_ * kPart] == 0.0) return false;
   for (int k = N; k >= 0; k--) {
+    if (MODE == 1 && (k % c.wd.nw) != c.wd.wid) continue;
     double* ps = c.stage(k);
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW], g[NW], sig[NW];
@@ -699,6 +765,7 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
     bool ok = true;
     Trig t;
     stage_trig(w, t);
+    if (MODE != 2)
     OB_FOR_LANES(pj, o.P) {
       double* pp = pair_ptr(ps, pj);
       double v[8], zv[8], s[4], y[4], zs[6];
@@ -750,10 +817,29 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
       Hadd[2][3] += e.hthps, Hadd[3][2] += e.hthps;
       Hadd[3][3] += e.hthps;
     }
-    if (!ob_all(ok)) return false;
-    for (int a = 0; a < 4; a++) {  // combine the pairs' Schur complements (upper triangle, then mirror)
-      gadd[a] = ob_sum(gadd[a]);
-      for (int bb = a; bb < 4; bb++) Hadd[a][bb] = Hadd[bb][a] = ob_sum(Hadd[a][bb]);
+    if (MODE != 2 && !ob_all(ok)) {
+      if (MODE == 1 && ob_lane0()) c.wd.part[c.wd.wid * kPart] = 0.0;
+      return false;
+    }
+    if (MODE == 2) {  // what the pair phase left for this stage
+      if (has_x)
+        for (int a = 0, q_ = 4; a < 4; a++) {
+          gadd[a] = bld(ps, oHA + a);
+          for (int bb = a; bb < 4; bb++, q_++) Hadd[a][bb] = Hadd[bb][a] = bld(ps, oHA + q_);
+        }
+    } else {
+      for (int a = 0; a < 4; a++) {  // combine the pairs' Schur complements (upper triangle, then mirror)
+        gadd[a] = ob_sum(gadd[a]);
+        for (int bb = a; bb < 4; bb++) Hadd[a][bb] = Hadd[bb][a] = ob_sum(Hadd[a][bb]);
+      }
+    }
+    if (MODE == 1) {
+      if (has_x)
+        for (int a = 0, q_ = 4; a < 4; a++) {
+          bst(ps, oHA + a, gadd[a]);
+          for (int bb = a; bb < 4; bb++, q_++) bst(ps, oHA + q_, Hadd[a][bb]);
+        }
+      continue;
     }
     if (k == N) {
       for (int i = 0; i < NX; i++) {
@@ -828,6 +914,7 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
       for (int i = 0; i < NX; i++) xn[i] = w[i], ln[i] = bld(ps, oLAM + i);
     }
   }
+  if (MODE == 1 && ob_lane0()) c.wd.part[c.wd.wid * kPart] = 1.0;
   ob_sync();
   return true;
 }
@@ -842,6 +929,7 @@ TT_HD void limit_lo(double dist, double d, double z, double mu, double tau, Dir&
   const double dz = r * (mu - z * d) - z;
   if (dz < 0.0) di.a_du = tt_min(di.a_du, -tau * z * tt_rcp(dz));
 }
+template <int MODE>
 TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di) {
   const Params& p = *c.p;
   const ObParams& o = *c.o;
@@ -854,9 +942,12 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
   double dx[NX];
   for (int i = 0; i < NX; i++) dx[i] = 0.0;
   for (int k = 0; k <= N; k++) {
+    if (MODE == 1 && (k % c.wd.nw) != c.wd.wid) continue;
     double* ps = c.stage(k);
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW], g[NW];
+    if (MODE == 1)  // pair phase: dx of the stage was stored by the recursion on warp 0
+      for (int i = 0; i < NX; i++) dx[i] = has_x ? bld(ps, oDW + i) : 0.0;
     {
       double ref[NW];
       for (int j = 0; j < NW; j++) {
@@ -875,6 +966,7 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
     double dw[NW];
     for (int j = 0; j < NX; j++) dw[j] = dx[j];
     dw[6] = dw[7] = 0.0;
+    if (MODE != 1) {
     if (has_u) {
       for (int i = 0; i < NU; i++) {
         double s = -bld(ps, oKFF + i);
@@ -899,9 +991,11 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
       }
       di.gphi_d += gb * dw[j];
     }
+    }  // MODE != 1
     // pairs: dv = -K_vv^-1 (q + K_vx dxt),  ds = J_x dxt + J_v dv + r_c
     Trig t;
     stage_trig(w, t);
+    if (MODE != 2)
     OB_FOR_LANES(pj, o.P) {
       double* pp = pair_ptr(ps, pj);
       double v[8], zv[8], s[4], zs[6];
@@ -941,7 +1035,7 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
       limit_lo(o.c2_up - s[2], -ds[2], zs[4], mu, tau, dq);
       limit_lo(o.s_up - s[3], -ds[3], zs[5], mu, tau, dq);
     }
-    if (has_u) {  // dx_{k+1} = A dx + B du - c_{k+1};  lambda+_{k+1} = -(p_{k+1} + P_{k+1} dx_{k+1})
+    if (MODE != 1 && has_u) {  // dx_{k+1} = A dx + B du - c_{k+1};  lambda+_{k+1} = -(p_{k+1} + P_{k+1} dx_{k+1})
       double* pq = c.stage(k + 1);
       Lin m;
       stage_lin(p, w, m);
@@ -959,9 +1053,18 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
       for (int i = 0; i < NX; i++) dx[i] = nd[i];
     }
   }
-  di.a_pr = tt_min(di.a_pr, ob_min(dq.a_pr));
-  di.a_du = tt_min(di.a_du, ob_min(dq.a_du));
-  di.gphi_d += ob_sum(dq.gphi_d);
+  if (MODE == 1) {  // this warp's share of the pairs' step limits
+    const double v3[3] = {ob_min(dq.a_pr), ob_min(dq.a_du), ob_sum(dq.gphi_d)};
+    if (ob_lane0())
+      for (int i = 0; i < 3; i++) c.wd.part[c.wd.wid * kPart + i] = v3[i];
+    ob_sync();
+    return;
+  }
+  if (MODE == 0) {
+    di.a_pr = tt_min(di.a_pr, ob_min(dq.a_pr));
+    di.a_du = tt_min(di.a_du, ob_min(dq.a_du));
+    di.gphi_d += ob_sum(dq.gphi_d);
+  }
   ob_sync();
 }
 
@@ -970,6 +1073,7 @@ struct TrialOut {
   double J, sumlog, theta;
   bool inside;  // every bounded quantity strictly inside its bounds
 };
+template <int MODE>
 TT_HD void trial(const Ctx& c, double alpha, TrialOut& tr) {
   const Params& p = *c.p;
   const ObParams& o = *c.o;
@@ -981,6 +1085,7 @@ TT_HD void trial(const Ctx& c, double alpha, TrialOut& tr) {
   double xn[NX];
   for (int i = 0; i < NX; i++) xn[i] = 0.0;
   for (int k = N; k >= 0; k--) {
+    if (MODE == 1 && (k % c.wd.nw) != c.wd.wid) continue;
     double* ps = c.stage(k);
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW];
@@ -988,6 +1093,10 @@ TT_HD void trial(const Ctx& c, double alpha, TrialOut& tr) {
       const bool on = (j < NX) || has_u, var = (j < NX) ? has_x : has_u;
       w[j] = on ? bld(ps, oW + j) : 0.0;
       if (var) w[j] += alpha * bld(ps, oDW + j);
+    }
+    if (MODE == 1 && has_u) {  // stage-parallel: the trial state of stage k+1 comes from its rows, not from the sweep
+      const double* pq = c.stage(k + 1);
+      for (int j = 0; j < NX; j++) xn[j] = bld(pq, oW + j) + alpha * bld(pq, oDW + j);
     }
     {
       double d6[NX];
@@ -1049,6 +1158,129 @@ TT_HD void trial(const Ctx& c, double alpha, TrialOut& tr) {
   }
   tr.J = J, tr.sumlog = sumlog + ob_sum(q_sumlog), tr.theta = theta + ob_sum(q_theta);
   tr.inside = inside && ob_all(q_inside);
+  if (MODE == 1) {  // this warp's share
+    if (ob_lane0()) {
+      double* pt = c.wd.part + c.wd.wid * kPart;
+      pt[0] = tr.J, pt[1] = tr.sumlog, pt[2] = tr.theta, pt[3] = tr.inside ? 1.0 : 0.0;
+    }
+    ob_sync();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the sweeps as the driver calls them: fused on one warp (WIDE = false), or dealt out over the warps of a CTA
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+TT_HD void ob_cta_sync() { __syncthreads(); }
+#else
+TT_HD void ob_cta_sync() {}
+#endif
+
+template <bool WIDE>
+TT_HD void run_update_stats(const Ctx& c, bool do_update, double alpha, double alpha_du, double mu_step, double delta_step,
+                            Stats& st) {
+  if (!WIDE) {
+    update_stats<0>(c, do_update, alpha, alpha_du, mu_step, delta_step, st);
+    return;
+  }
+#if defined(__CUDA_ARCH__)
+  ob_cta_sync();
+  update_stats<1>(c, do_update, alpha, alpha_du, mu_step, delta_step, st);
+  ob_cta_sync();
+  if (c.wd.wid == 0) {
+    update_stats<2>(c, do_update, alpha, alpha_du, mu_step, delta_step, st);
+    if (ob_lane0()) *reinterpret_cast<Stats*>(c.wd.bcast) = st;
+  }
+  ob_cta_sync();
+  st = *reinterpret_cast<const Stats*>(c.wd.bcast);
+#else
+  for (int w = 0; w < c.wd.nw; w++) {
+    Ctx cw = c;
+    cw.wd.wid = w;
+    update_stats<1>(cw, do_update, alpha, alpha_du, mu_step, delta_step, st);
+  }
+  update_stats<2>(c, do_update, alpha, alpha_du, mu_step, delta_step, st);
+#endif
+}
+
+template <bool WIDE>
+TT_HD bool run_factor(const Ctx& c, double mu, double delta) {
+  if (!WIDE) return factor<0>(c, mu, delta);
+#if defined(__CUDA_ARCH__)
+  ob_cta_sync();
+  factor<1>(c, mu, delta);
+  ob_cta_sync();
+  if (c.wd.wid == 0) {
+    const bool ok = factor<2>(c, mu, delta);
+    if (ob_lane0()) c.wd.bcast[0] = ok ? 1.0 : 0.0;
+  }
+  ob_cta_sync();
+  return c.wd.bcast[0] != 0.0;
+#else
+  for (int w = 0; w < c.wd.nw; w++) {
+    Ctx cw = c;
+    cw.wd.wid = w;
+    factor<1>(cw, mu, delta);
+  }
+  return factor<2>(c, mu, delta);
+#endif
+}
+
+template <bool WIDE>
+TT_HD void run_direction(const Ctx& c, double mu, double tau, double delta, Dir& di) {
+  if (!WIDE) {
+    direction<0>(c, mu, tau, delta, di);
+    return;
+  }
+  Dir dummy;
+#if defined(__CUDA_ARCH__)
+  ob_cta_sync();
+  if (c.wd.wid == 0) {
+    direction<2>(c, mu, tau, delta, di);
+    if (ob_lane0()) c.wd.bcast[0] = di.a_pr, c.wd.bcast[1] = di.a_du, c.wd.bcast[2] = di.gphi_d;
+  }
+  ob_cta_sync();
+  di.a_pr = c.wd.bcast[0], di.a_du = c.wd.bcast[1], di.gphi_d = c.wd.bcast[2];
+  direction<1>(c, mu, tau, delta, dummy);
+  ob_cta_sync();
+#else
+  direction<2>(c, mu, tau, delta, di);
+  for (int w = 0; w < c.wd.nw; w++) {
+    Ctx cw = c;
+    cw.wd.wid = w;
+    direction<1>(cw, mu, tau, delta, dummy);
+  }
+#endif
+  for (int w = 0; w < c.wd.nw; w++) {
+    const double* pt = c.wd.part + w * kPart;
+    di.a_pr = tt_min(di.a_pr, pt[0]), di.a_du = tt_min(di.a_du, pt[1]), di.gphi_d += pt[2];
+  }
+}
+
+template <bool WIDE>
+TT_HD void run_trial(const Ctx& c, double alpha, TrialOut& tr) {
+  if (!WIDE) {
+    trial<0>(c, alpha, tr);
+    return;
+  }
+#if defined(__CUDA_ARCH__)
+  ob_cta_sync();
+  trial<1>(c, alpha, tr);
+  ob_cta_sync();
+#else
+  for (int w = 0; w < c.wd.nw; w++) {
+    Ctx cw = c;
+    cw.wd.wid = w;
+    trial<1>(cw, alpha, tr);
+  }
+#endif
+  tr.J = tr.sumlog = tr.theta = 0.0;
+  tr.inside = true;
+  for (int w = 0; w < c.wd.nw; w++) {
+    const double* pt = c.wd.part + w * kPart;
+    tr.J += pt[0], tr.sumlog += pt[1], tr.theta += pt[2];
+    if (pt[3] == 0.0) tr.inside = false;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1091,10 +1323,11 @@ TT_HD void lane_result(const Lane& L, int status, Result& res) {
 }
 
 // head of an iteration; true when the lane is finished (res filled in)
+template <bool WIDE = false>
 TT_HD bool lane_head(const Ctx& c, Lane& L, Result& res) {
   const Params& p = *c.p;
   Stats& st = L.st;
-  update_stats(c, L.do_update, L.alpha, L.alpha_du, L.mu_step, L.delta_step, st);
+  run_update_stats<WIDE>(c, L.do_update, L.alpha, L.alpha_du, L.mu_step, L.delta_step, st);
   if (!(tt_finite(st.J) && tt_finite(st.sumlog) && tt_finite(st.theta) && tt_finite(st.rd_inf))) {
     lane_result(L, ST_NUMERIC, res);
     return true;
@@ -1147,8 +1380,9 @@ TT_HD bool lane_head(const Ctx& c, Lane& L, Result& res) {
 }
 
 // one factorisation attempt; true when the lane is finished (no usable regularisation)
+template <bool WIDE = false>
 TT_HD bool lane_factor_once(const Ctx& c, Lane& L, Result& res) {
-  if (factor(c, L.mu, L.delta)) {
+  if (run_factor<WIDE>(c, L.mu, L.delta)) {
     if (L.delta > 0.0) L.delta_last = L.delta;
     L.need_factor = false;
     L.need_dir = true;
@@ -1173,9 +1407,10 @@ TT_HD void lane_accept(Lane& L, double a) {
   L.iter++;
 }
 
+template <bool WIDE = false>
 TT_HD void lane_direction(const Ctx& c, Lane& L) {
   const Params& p = *c.p;
-  direction(c, L.mu, L.tau, L.delta, L.di);
+  run_direction<WIDE>(c, L.mu, L.tau, L.delta, L.di);
   L.need_dir = false;
   // round-off regime (see oracle/ttmpc_oracle.c): neither theta nor phi can be compared reliably -> full step
   const bool roundoff = (L.theta <= 1e-2 * p.tol) &&
@@ -1191,10 +1426,11 @@ TT_HD void lane_direction(const Ctx& c, Lane& L) {
 }
 
 // one line-search trial; true when the lane is finished (third consecutive line-search failure)
+template <bool WIDE = false>
 TT_HD bool lane_trial_once(const Ctx& c, Lane& L, Result& res) {
   const double a = L.ls_a, theta = L.theta, phi = L.phi, gd = L.di.gphi_d;
   TrialOut tr;
-  trial(c, a, tr);
+  run_trial<WIDE>(c, a, tr);
   const double phi_t = tr.J - L.mu * tr.sumlog;
   bool okstep = tr.inside && tt_finite(phi_t) && tt_finite(tr.theta) && tr.theta <= L.theta_max;
   if (okstep)
@@ -1240,20 +1476,28 @@ TT_HD bool lane_trial_once(const Ctx& c, Lane& L, Result& res) {
   return false;
 }
 
-// sequential driver (host emulation; the CUDA kernel interleaves the same phases across the lanes of a warp)
+// sequential driver of one problem: WIDE = false on one warp (ttmpc_obca_kernel interleaves the same phases over its 8
+// problem slots), WIDE = true on all warps of a CTA (ttmpc_obca_wide_kernel; wd describes the CTA)
+template <bool WIDE>
+TT_HD void solve_problem(const Ctx& c, const ProblemIn& in, long long b, Result& res) {
+  Lane L;
+  const bool x0_bad = init_point<WIDE>(c, in, b);
+  if (WIDE) ob_cta_sync();
+  lane_begin(*c.p, *c.o, x0_bad, L);
+  for (;;) {
+    if (lane_head<WIDE>(c, L, res)) return;
+    while (L.need_factor)
+      if (lane_factor_once<WIDE>(c, L, res)) return;
+    lane_direction<WIDE>(c, L);
+    while (L.need_trial)
+      if (lane_trial_once<WIDE>(c, L, res)) return;
+  }
+}
 TT_HD void solve_lane(const Params& p, const ObParams& o, double* s0, const ProblemIn& in, long long b, Result& res) {
   Ctx c;
+  c.wd.wid = 0, c.wd.nw = 1, c.wd.part = nullptr, c.wd.bcast = nullptr;
   c.p = &p, c.o = &o, c.s0 = s0;
-  Lane L;
-  lane_begin(p, o, init_point(c, in, b), L);
-  for (;;) {
-    if (lane_head(c, L, res)) return;
-    while (L.need_factor)
-      if (lane_factor_once(c, L, res)) return;
-    lane_direction(c, L);
-    while (L.need_trial)
-      if (lane_trial_once(c, L, res)) return;
-  }
+  solve_problem<false>(c, in, b, res);
 }
 
 // states / inputs of the problem's iterate in the plain layout [x_0, u_0, ..., x_N] (what _split_decision_variables of

@@ -205,4 +205,18 @@ def test_obca_core_under_address_sanitizer(tmp_path, traj):
         np.ascontiguousarray(arr, dtype=np.float64).tofile(tmp_path / f"{name}.bin")
     out = subprocess.run([exe, str(tmp_path), str(N), str(B)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
-    assert "checksum" in out.stdout and "nan" not in out.stdout.lower()
+    assert "checksum 0 status" in out.stdout and "nan" not in out.stdout.lower()  # fused and wide runs agree exactly
+
+
+@pytest.mark.parametrize("warps", [1, 3, 8])
+def test_cta_per_problem_decomposition_is_bit_identical(warps):
+    """ttmpc_obca_wide_kernel deals the stages of every sweep to the warps of a CTA and runs the recursions on warp 0;
+    the host build of that decomposition must reproduce the single-warp sweeps exactly (same operations, other order
+    of execution only)."""
+    for c in CASES:
+        cfg, obs = case_problem(c)
+        cfg.max_iter = 300
+        a = emu.obca_solve_batch(cfg, obs, c["x_init"][None], c["ref_states"][None], c["ref_inputs"][None])
+        b = emu.obca_solve_batch(cfg, obs, c["x_init"][None], c["ref_states"][None], c["ref_inputs"][None], wide_warps=warps)
+        assert a["status"][0] == b["status"][0] and a["iters"][0] == b["iters"][0]
+        assert np.array_equal(a["z"], b["z"]) and np.array_equal(a["obj"], b["obj"]) and np.array_equal(a["kkt"], b["kkt"])

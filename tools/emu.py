@@ -67,7 +67,9 @@ def obca_lib():
 
 
 def obca_solve_batch(cfg, obstacles, x_init, ref_states=None, ref_inputs=None, k_index=None, traj_states=None,
-                     traj_inputs=None):
+                     traj_inputs=None, wide_warps=0):
+    """wide_warps > 0: the CTA-per-problem flavour of the kernel (stages dealt to that many virtual warps)."""
+    obca_lib().ttmpc_emu_obca_set_wide(ctypes.c_int(int(wide_warps)))
     N = cfg.horizon
     x = np.ascontiguousarray(x_init, dtype=np.float64).reshape(-1, 6)
     B = x.shape[0]

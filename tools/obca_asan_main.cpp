@@ -8,6 +8,7 @@
 
 #include "../include/ttmpc.h"
 
+extern "C" void ttmpc_emu_obca_set_wide(int warps);
 extern "C" int ttmpc_emu_obca_solve_batch(const ttmpc_config*, const ttmpc_obstacles*, int64_t, const double*, const double*,
                                           const double*, const int32_t*, const double*, const double*, int32_t, double*, double*,
                                           double*, double*, int32_t*, int32_t*);
@@ -38,7 +39,12 @@ int main(int argc, char** argv) {
                                  obj.data(), kkt.data(), it.data(), st.data()))
     return 3;
   double sum = 0;
-  for (double v : u0) sum += v;
+  const std::vector<double> u0_fused = u0;
+  ttmpc_emu_obca_set_wide(3);  // the CTA-per-problem decomposition (stages dealt to 3 virtual warps)
+  if (ttmpc_emu_obca_solve_batch(&cfg, &obs, B, x.data(), xs.data(), us.data(), nullptr, nullptr, nullptr, 0, z.data(), u0.data(),
+                                 obj.data(), kkt.data(), it.data(), st.data()))
+    return 3;
+  for (size_t i = 0; i < u0.size(); i++) sum += (u0[i] == u0_fused[i]) ? 0.0 : 1.0;  // bit-identical to the first run
   printf("checksum %.12g status", sum);
   for (int32_t s : st) printf(" %d", s);
   printf("\n");

@@ -12,6 +12,9 @@
 
 using namespace ttmpc;
 
+static int g_wide_warps = 0;
+extern "C" void ttmpc_emu_obca_set_wide(int warps) { g_wide_warps = warps; }
+
 extern "C" int ttmpc_emu_obca_solve_batch(const ttmpc_config* cfg, const ttmpc_obstacles* obs, int64_t B, const double* x_init,
                                           const double* ref_states, const double* ref_inputs, const int32_t* k_index,
                                           const double* traj_states, const double* traj_inputs, int32_t T, double* z_out,
@@ -31,7 +34,15 @@ extern "C" int ttmpc_emu_obca_solve_batch(const ttmpc_config* cfg, const ttmpc_o
     double* s0 = obca::slot_ptr(scratch.data(), p.N, (size_t)l);
     for (int64_t b = l; b < B; b += L) {
       Result r{};
-      obca::solve_lane(p, o, s0, in, b, r);
+      if (g_wide_warps > 0) {  // the CTA-per-problem flavour: stages dealt to `g_wide_warps` virtual warps
+        std::vector<double> part((size_t)g_wide_warps * obca::kPart, NAN), bcast(32, NAN);
+        obca::Ctx c;
+        c.wd.wid = 0, c.wd.nw = g_wide_warps, c.wd.part = part.data(), c.wd.bcast = bcast.data();
+        c.p = &p, c.o = &o, c.s0 = s0;
+        obca::solve_problem<true>(c, in, b, r);
+      } else {
+        obca::solve_lane(p, o, s0, in, b, r);
+      }
       if (z_out) obca::unpack(p, s0, z_out + b * nz);
       if (u0_out) { u0_out[b * 2] = obca::bld(s0, obca::oW + 6); u0_out[b * 2 + 1] = obca::bld(s0, obca::oW + 7); }
       if (obj_out) obj_out[b] = r.obj;
