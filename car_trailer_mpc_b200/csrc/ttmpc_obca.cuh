@@ -212,6 +212,36 @@ TT_HD double xa(double a, double b) { return a + b; }
 TT_HD double xf(double a, double b, double c) { return a * b + c; }
 #endif
 
+// The model and its Jacobian with the same fixed rounding sequence: the factor sweep (Riccati step) and the direction
+// sweep (dx recursion) both linearise stage k; the value function carries the condensed pair Hessians (entries ~1e10), so
+// a last-bit difference between the two copies of A or of the defect comes back as a 1e-5 error in lambda+.
+TT_HD void stage_lin_det(const Params& p, const double* x, Lin& m) {
+  tt_sincos(x[2], m.sth, m.cth);
+  tt_sincos(x[3], m.sps, m.cps);
+  double sph, cph;
+  tt_sincos(x[4], sph, cph);
+  m.t = xm(sph, tt_rcp(cph));
+  m.s2 = xf(m.t, m.t, 1.0);
+  m.v = x[5];
+  m.g1 = xf(p.cML, m.cps, 1.0);
+  const double v = m.v, dt = p.dt;
+  m.f0 = xm(v, m.cth);
+  m.f1 = xm(v, m.sth);
+  m.f2 = xm(xm(v, m.t), p.iL1);
+  m.f3 = xf(-m.f2, m.g1, -xm(xm(v, m.sps), p.iL2));
+  m.a02 = xm(-dt, m.f1);
+  m.a05 = xm(dt, m.cth);
+  m.a12 = xm(dt, m.f0);
+  m.a15 = xm(dt, m.sth);
+  m.a24 = xm(xm(xm(dt, v), m.s2), p.iL1);
+  m.a25 = xm(xm(dt, m.t), p.iL1);
+  m.a33 = xf(dt, xf(xm(m.f2, p.cML), m.sps, -xm(xm(v, m.cps), p.iL2)), 1.0);
+  m.a34 = xm(-m.a24, m.g1);
+  m.a35 = xm(dt, xf(xm(-m.t, p.iL1), m.g1, -xm(m.sps, p.iL2)));
+}
+// defect x_{k+1} - x_k - dt f(x_k, u_k), one component
+TT_HD double defect_det(double xn, double x, double dt, double f) { return xf(-dt, f, xa(xn, -x)); }
+
 template <bool HESS>
 TT_HD void pair_eval(const ObParams& o, int body, const double* b, const Trig& t, const double* v, const double* y,
                      PairEval& e) {
@@ -574,10 +604,10 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
       for (int j = 0; j < NX; j++) r[j] += lam[j], lam1 += fabs(lam[j]);
     if (has_u) {  // defect c_{k+1} and -[A B]' lambda_{k+1}
       Lin m;
-      stage_lin(p, w, m);
+      stage_lin_det(p, w, m);
       const double f[NX] = {m.f0, m.f1, m.f2, m.f3, w[7], w[6]};
       for (int j = 0; j < NX; j++) {
-        const double ck = xn[j] - w[j] - p.dt * f[j];
+        const double ck = defect_det(xn[j], w[j], p.dt, f[j]);
         theta += fabs(ck);
         cinf = tt_max(cinf, fabs(ck));
       }
@@ -849,10 +879,10 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
       }
     } else {
       Lin m;
-      stage_lin(p, w, m);
+      stage_lin_det(p, w, m);
       const double f[NX] = {m.f0, m.f1, m.f2, m.f3, w[7], w[6]};
       double h[NX], cdef[NX];
-      for (int i = 0; i < NX; i++) cdef[i] = xn[i] - w[i] - dt * f[i];
+      for (int i = 0; i < NX; i++) cdef[i] = defect_det(xn[i], w[i], dt, f[i]);
       for (int i = 0; i < NX; i++) {
         double s = pn[i];
         for (int j = 0; j < NX; j++) s -= Pn[i][j] * cdef[j];
@@ -1038,13 +1068,13 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
     if (MODE != 1 && has_u) {  // dx_{k+1} = A dx + B du - c_{k+1};  lambda+_{k+1} = -(p_{k+1} + P_{k+1} dx_{k+1})
       double* pq = c.stage(k + 1);
       Lin m;
-      stage_lin(p, w, m);
+      stage_lin_det(p, w, m);
       const double f[NX] = {m.f0, m.f1, m.f2, m.f3, w[7], w[6]};
       double nd[NX];
       A_mul(m, dx, nd);
       nd[4] += p.dt * dw[7];
       nd[5] += p.dt * dw[6];
-      for (int i = 0; i < NX; i++) nd[i] -= bld(pq, oW + i) - w[i] - p.dt * f[i];
+      for (int i = 0; i < NX; i++) nd[i] -= defect_det(bld(pq, oW + i), w[i], p.dt, f[i]);
       for (int i = 0; i < NX; i++) {
         double s = bld(pq, oPV + i);
         for (int j = 0; j < NX; j++) s += bld(pq, oP + SY(i, j)) * nd[j];
