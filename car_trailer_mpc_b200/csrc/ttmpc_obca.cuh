@@ -414,7 +414,7 @@ TT_HD void pair_system(const ObParams& o, const PairEval& e, const SlackBar& sb,
 // the CTA for the pair work (MODE 1 of a sweep: stage k belongs to warp k % nw), the recursions over the stages run on
 // warp 0 (MODE 2) using what the pair phase left in the stage's oRP / oHA rows; per-warp partial statistics go through
 // `part` (shared memory).  MODE 0 is the fused single-warp sweep.
-constexpr int kPart = 16;
+constexpr int kPart = 20;
 struct Wide {
   int wid, nw;
   double* part;   // [nw][kPart]
@@ -517,8 +517,9 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
   const double khi = kKappaSigma * mu_step, klo = mu_step / kKappaSigma;
   double xn[NX], ln[NX];  // x_{k+1}, lambda_{k+1} at the new iterate
   for (int j = 0; j < NX; j++) xn[j] = ln[j] = 0.0;
+  if (MODE == 3) do_update = false;  // the step was applied by the pair phase
   for (int k = N; k >= 0; k--) {
-    if (MODE == 1 && (k % c.wd.nw) != c.wd.wid) continue;
+    if ((MODE == 1 || MODE == 3) && (k % c.wd.nw) != c.wd.wid) continue;
     double* ps = c.stage(k);
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW], ref[NW], zl[NW], zu[NW], lam[NX], dwv[NW], lamp[NX];
@@ -536,10 +537,8 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
     }
     ob_sync();  // every lane has read the shared rows of this stage before lane 0 overwrites them
     double r[NW];
-    if (MODE == 1) {  // pair phase: only the new (x, y, theta, psi) of the stage is needed, nothing is stored
-      for (int j = 0; j < NX; j++)
-        if (do_update && has_x) w[j] = fma(alpha, dwv[j], w[j]);
-    } else {
+    for (int j = 0; j < NW; j++) r[j] = 0.0;
+    if (MODE != 3) {  // apply the step to the stage's (x, u) rows (stage-local)
     for (int j = 0; j < NW; j++) {
       const bool var = (j < NX) ? has_x : has_u;
       if (do_update && var) {
@@ -566,6 +565,12 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
         bst(ps, oLAM + j, lam[j]);
       }
     }
+    }
+    if (MODE == 3 && has_u) {  // stage-parallel statistics: the neighbour's new rows instead of the sweep's carried copies
+      const double* pq = c.stage(k + 1);
+      for (int j = 0; j < NX; j++) xn[j] = bld(pq, oW + j), ln[j] = bld(pq, oLAM + j);
+    }
+    if (MODE != 1) {
     // gradient of the Lagrangian wrt (x_k, u_k), without the pair terms yet
     {
       double d6[NX];
@@ -617,12 +622,12 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
       r[6] -= p.dt * ln[5];
       r[7] -= p.dt * ln[4];
     }
-    }  // MODE != 1
+    }
     // pairs
     double rp[4] = {0.0, 0.0, 0.0, 0.0};  // J_x' y of this lane's pair(s)
     Trig t;
     stage_trig(w, t);
-    if (MODE != 2)
+    if (MODE != 3)
     OB_FOR_LANES(pj, o.P) {
       double* pp = pair_ptr(ps, pj);
       double v[8], zv[8], s[4], y[4], zs[6];
@@ -700,7 +705,7 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
       continue;
     }
     if (has_x)
-      for (int cc = 0; cc < 4; cc++) r[cc] += (MODE == 2) ? bld(ps, oRP + cc) : ob_sum(rp[cc]);
+      for (int cc = 0; cc < 4; cc++) r[cc] += (MODE == 3) ? bld(ps, oRP + cc) : ob_sum(rp[cc]);
     for (int j = 0; j < NW; j++) {
       const bool var = (j < NX) ? has_x : has_u;
       if (var) rd_inf = tt_max(rd_inf, fabs(r[j]));
@@ -715,18 +720,11 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
     ob_sync();
     return;
   }
-  if (MODE == 2) {
-    q_sumlog = q_theta = q_cinf = q_rd = q_lam1 = q_z1 = q_cmax = 0.0;
-    q_cmin = INFINITY;
-    for (int w_ = 0; w_ < c.wd.nw; w_++) {
-      const double* pt = c.wd.part + w_ * kPart;
-      q_sumlog += pt[0], q_theta += pt[1], q_cinf = tt_max(q_cinf, pt[2]), q_rd = tt_max(q_rd, pt[3]);
-      q_lam1 += pt[4], q_z1 += pt[5], q_cmax = tt_max(q_cmax, pt[6]), q_cmin = tt_min(q_cmin, pt[7]);
+  if (MODE == 3) {  // this warp's share of the (x, u) statistics
+    if (ob_lane0()) {
+      double* pt = c.wd.part + c.wd.wid * kPart + 8;
+      pt[0] = J, pt[1] = sumlog, pt[2] = theta, pt[3] = cinf, pt[4] = rd_inf, pt[5] = lam1, pt[6] = z1, pt[7] = cmax, pt[8] = cmin;
     }
-    st.J = J, st.sumlog = sumlog + q_sumlog, st.theta = theta + q_theta;
-    st.cinf = tt_max(cinf, q_cinf), st.rd_inf = tt_max(rd_inf, q_rd);
-    st.lam1 = lam1 + q_lam1, st.z1 = z1 + q_z1;
-    st.cmax = tt_max(cmax, q_cmax), st.cmin = tt_min(cmin, q_cmin);
     ob_sync();
     return;
   }
@@ -1215,22 +1213,32 @@ TT_HD void run_update_stats(const Ctx& c, bool do_update, double alpha, double a
   }
 #if defined(__CUDA_ARCH__)
   ob_cta_sync();
-  update_stats<1>(c, do_update, alpha, alpha_du, mu_step, delta_step, st);
+  update_stats<1>(c, do_update, alpha, alpha_du, mu_step, delta_step, st);  // step + pairs, stage k on warp k % nw
   ob_cta_sync();
-  if (c.wd.wid == 0) {
-    update_stats<2>(c, do_update, alpha, alpha_du, mu_step, delta_step, st);
-    if (ob_lane0()) *reinterpret_cast<Stats*>(c.wd.bcast) = st;
-  }
+  update_stats<3>(c, do_update, alpha, alpha_du, mu_step, delta_step, st);  // (x, u) statistics, stage-parallel as well
   ob_cta_sync();
-  st = *reinterpret_cast<const Stats*>(c.wd.bcast);
 #else
   for (int w = 0; w < c.wd.nw; w++) {
     Ctx cw = c;
     cw.wd.wid = w;
     update_stats<1>(cw, do_update, alpha, alpha_du, mu_step, delta_step, st);
   }
-  update_stats<2>(c, do_update, alpha, alpha_du, mu_step, delta_step, st);
+  for (int w = 0; w < c.wd.nw; w++) {
+    Ctx cw = c;
+    cw.wd.wid = w;
+    update_stats<3>(cw, do_update, alpha, alpha_du, mu_step, delta_step, st);
+  }
 #endif
+  // every warp combines the shares in the same order: identical statistics everywhere, no broadcast needed
+  st.J = st.sumlog = st.theta = st.cinf = st.rd_inf = st.lam1 = st.z1 = st.cmax = 0.0;
+  st.cmin = INFINITY;
+  for (int w = 0; w < c.wd.nw; w++) {
+    const double* pt = c.wd.part + w * kPart;
+    st.sumlog += pt[0] + pt[9], st.theta += pt[1] + pt[10], st.cinf = tt_max(st.cinf, tt_max(pt[2], pt[11]));
+    st.rd_inf = tt_max(st.rd_inf, tt_max(pt[3], pt[12])), st.lam1 += pt[4] + pt[13], st.z1 += pt[5] + pt[14];
+    st.cmax = tt_max(st.cmax, tt_max(pt[6], pt[15])), st.cmin = tt_min(st.cmin, tt_min(pt[7], pt[16]));
+    st.J += pt[8];
+  }
 }
 
 template <bool WIDE>

@@ -212,11 +212,12 @@ def test_obca_core_under_address_sanitizer(tmp_path, traj):
 def test_cta_per_problem_decomposition_is_bit_identical(warps):
     """ttmpc_obca_wide_kernel deals the stages of every sweep to the warps of a CTA and runs the recursions on warp 0;
     the host build of that decomposition must reproduce the single-warp sweeps exactly (same operations, other order
-    of execution only)."""
+    of execution only; sums of statistics are taken per warp first)."""
     for c in CASES:
         cfg, obs = case_problem(c)
         cfg.max_iter = 300
         a = emu.obca_solve_batch(cfg, obs, c["x_init"][None], c["ref_states"][None], c["ref_inputs"][None])
         b = emu.obca_solve_batch(cfg, obs, c["x_init"][None], c["ref_states"][None], c["ref_inputs"][None], wide_warps=warps)
         assert a["status"][0] == b["status"][0] and a["iters"][0] == b["iters"][0]
-        assert np.array_equal(a["z"], b["z"]) and np.array_equal(a["obj"], b["obj"]) and np.array_equal(a["kkt"], b["kkt"])
+        assert np.array_equal(a["z"], b["z"]) and np.array_equal(a["kkt"], b["kkt"])
+        assert abs(a["obj"][0] - b["obj"][0]) <= 1e-14 * abs(a["obj"][0])  # the reported sum is taken in another order
