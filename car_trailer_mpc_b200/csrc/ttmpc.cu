@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
 // to the 8 warps for the pair work of every sweep, the recursions over the stages (Riccati, dx, the in-place update) run
 // on warp 0, statistics meet in shared memory (obca::run_* wrappers).  Same arithmetic as ttmpc_obca_kernel: the host
 // build of this decomposition reproduces the single-warp results bit for bit (tests/test_obca_cpu.py).
-__global__ void __launch_bounds__(kObcaThreads, 1)
+__global__ void __launch_bounds__(kObcaThreads)
     ttmpc_obca_wide_kernel(const __grid_constant__ Params p, const __grid_constant__ obca::ObParams o,
                            double* __restrict__ scratch, long long B, ProblemIn in, SolveOut out, unsigned long long* counter) {
   __shared__ double s_part[(kObcaThreads / 32) * obca::kPart];
@@ -832,17 +832,19 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
                        cudaStream_t st) {
   obca::ObParams o;
   if (obca::build_obparams(&h->cfg, obs, &o) != TTMPC_OK) return set_err(h, TTMPC_E_INVAL, "bad obstacle set", cudaSuccess);
-  int sms = 148, per_sm = 1;
+  int sms = 148, per_sm = 1, per_sm_wide = 1;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ttmpc_obca_kernel, kObcaThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_wide, ttmpc_obca_wide_kernel, kObcaThreads, 0);
   if (per_sm < 1) per_sm = 1;
+  if (per_sm_wide < 1) per_sm_wide = 1;
   // up to 12 problems per SM: one CTA per problem (measured on B200, N = 50: 35 vs 73 ms for one problem, 575 vs 692 ms
   // for 1 184, equal at 2 048); beyond that: one warp per problem (16 384: 3.8 vs 6.3 s)
   const char* wenv = getenv("TTMPC_OBCA_WIDE_MAX");
   const bool wide = B <= (wenv ? atoll(wenv) : 12LL * sms);
   const int wpc = wide ? 1 : kObcaThreads / 32;
   long long blocks = (B + wpc - 1) / wpc;
-  const long long cap = (long long)sms * (wide ? 1 : per_sm);
+  const long long cap = (long long)sms * (wide ? per_sm_wide : per_sm);
   if (blocks > cap) blocks = cap;
   const size_t need = obca::scratch_doubles(h->p.N, (size_t)blocks * wpc);
   if (need > h->ob_doubles) {
