@@ -42,14 +42,15 @@ namespace obca {
 constexpr int kMaxPairs = 2 * TTMPC_MAX_OBSTACLES;
 // ---- scratch rows of one stage ----
 constexpr int oW = 0, oDW = 8, oREF = 16, oLAM = 24, oLAMP = 30, oZL = 36, oZU = 44, oK = 52, oKFF = 64, oP = 66, oPV = 87;
-constexpr int oRP = 96, oHA = 100;  // wide mode only: the pairs' J_x'y (4) and condensed Hessian / gradient (4 + 10) of the stage
-constexpr int kBaseRows = 114;
+constexpr int oRP = 96;  // wide mode only: the pairs' J_x'y (4) of the stage
+constexpr int oA = 114, oCD = 123, oG = 129, oSIG = 137, oHX = 139;  // wide mode only, left by the pair phase of the factor sweep: A (9), defect (6), gradient (8), Sigma_u (2), Hessian block (21)
+constexpr int kBaseRows = 160;
 constexpr int qV = 0, qZV = 8, qS = 16, qY = 20, qZS = 24, qDV = 30, qDS = 38;  // rows of one pair
 constexpr int qA = 42, qG = 50;  // K_vv^-1 q (8) and K_vv^-1 K_vx (8x4, row-major): written by factor, read by direction
 constexpr int kPairRows = 82;
-constexpr int kBasePad = 128;                                // base rows, padded to a multiple of 32 doubles
+constexpr int kBasePad = 160;                                // base rows, padded to a multiple of 32 doubles
 constexpr int kLanes = 32;                                   // pair slots per stage (>= kMaxPairs)
-constexpr int kStageDoubles = kBasePad + kPairRows * kLanes;  // 2752 doubles = 21.5 KB per stage and problem slot
+constexpr int kStageDoubles = kBasePad + kPairRows * kLanes;  // 2784 doubles = 21.75 KB per stage and problem slot
 inline size_t scratch_doubles(int N, size_t slots) { return slots * (size_t)(N + 1) * kStageDoubles; }
 TT_HD double* slot_ptr(double* scratch, int N, size_t slot) { return scratch + slot * (size_t)(N + 1) * kStageDoubles; }
 
@@ -735,6 +736,26 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
   ob_sync();
 }
 
+// Hessian block of stage k >= 1: 2Q + condensed pairs + Sigma (+delta) [- dt * sum_i lambda_i d2f_i/dx2 for k < N]
+TT_HD void assemble_hx(const Params& p, const double (*Hadd)[4], const double* sig, const Lin* m, const double* ln,
+                       double (*Hx)[NX]) {
+  for (int i = 0; i < NX; i++) {
+    for (int j = 0; j < NX; j++) Hx[i][j] = p.Q2[SY(i, j)] + ((i < 4 && j < 4) ? Hadd[i][j] : 0.0);
+    Hx[i][i] += sig[i];
+  }
+  if (m != nullptr) {
+    Hes ho;
+    stage_hess(p, *m, ln, ho);
+    Hx[2][2] += ho.h22, Hx[2][5] += ho.h25, Hx[5][2] += ho.h25;
+    Hx[3][3] += ho.h33, Hx[3][4] += ho.h34, Hx[4][3] += ho.h34, Hx[3][5] += ho.h35, Hx[5][3] += ho.h35;
+    Hx[4][4] += ho.h44, Hx[4][5] += ho.h45, Hx[5][4] += ho.h45;
+  }
+}
+TT_HD void load_hx(const double* ps, double (*Hx)[NX]) {
+  for (int i = 0; i < NX; i++)
+    for (int j = i; j < NX; j++) Hx[i][j] = Hx[j][i] = bld(ps, oHX + SY(i, j));
+}
+
 // ---- sweep 2 (backward): condensation of the pairs + Riccati factorisation.  false: wrong inertia ----
 template <int MODE>
 TT_HD bool factor(const Ctx& c, double mu, double delta) {
@@ -755,6 +776,9 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
     double* ps = c.stage(k);
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW], g[NW], sig[NW];
+    if (MODE == 2) {  // everything stage-local was prepared by the stage's warp
+      for (int j = 0; j < NW; j++) w[j] = g[j] = sig[j] = 0.0;
+    } else {
     {
       double ref[NW];
       for (int j = 0; j < NW; j++) {
@@ -784,6 +808,7 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
         g[j] += mu * ru;
       }
     }
+    }
     // ---- pairs: Schur complement onto (x, y, theta, psi) ----
     double Hadd[4][4], gadd[4];
     for (int i = 0; i < 4; i++) {
@@ -792,7 +817,7 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
     }
     bool ok = true;
     Trig t;
-    stage_trig(w, t);
+    if (MODE != 2) stage_trig(w, t);
     if (MODE != 2)
     OB_FOR_LANES(pj, o.P) {
       double* pp = pair_ptr(ps, pj);
@@ -849,38 +874,66 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
       if (MODE == 1 && ob_lane0()) c.wd.part[c.wd.wid * kPart] = 0.0;
       return false;
     }
-    if (MODE == 2) {  // what the pair phase left for this stage
-      if (has_x)
-        for (int a = 0, q_ = 4; a < 4; a++) {
-          gadd[a] = bld(ps, oHA + a);
-          for (int bb = a; bb < 4; bb++, q_++) Hadd[a][bb] = Hadd[bb][a] = bld(ps, oHA + q_);
-        }
-    } else {
+    if (MODE != 2) {
       for (int a = 0; a < 4; a++) {  // combine the pairs' Schur complements (upper triangle, then mirror)
         gadd[a] = ob_sum(gadd[a]);
         for (int bb = a; bb < 4; bb++) Hadd[a][bb] = Hadd[bb][a] = ob_sum(Hadd[a][bb]);
       }
     }
+    // ---- stage-local quantities of the Riccati step: A, defect, gradient (wide mode: prepared by the stage's warp in
+    //      MODE 1 and left in the stage's rows together with the Hessian block, so that the serial recursion on warp 0
+    //      only loads them)
+    Lin m;
+    double cdef[NX], gxs[NW], s6 = 0.0, s7 = 0.0;
+    double* gx = (MODE == 2) ? gxs : g;  // gradient incl. the pairs' share: in place where it was computed here
+    if (MODE != 2) {
+      if (MODE == 1 && has_u) {  // the neighbour's rows instead of the sweep's carried copies
+        const double* pq = c.stage(k + 1);
+        for (int i = 0; i < NX; i++) xn[i] = bld(pq, oW + i), ln[i] = bld(pq, oLAM + i);
+      }
+      for (int i = 0; i < 4; i++) g[i] += gadd[i];
+      s6 = sig[6], s7 = sig[7];
+      if (has_u) {
+        stage_lin_det(p, w, m);
+        const double f[NX] = {m.f0, m.f1, m.f2, m.f3, w[7], w[6]};
+        for (int i = 0; i < NX; i++) cdef[i] = defect_det(xn[i], w[i], dt, f[i]);
+      }
+    }
     if (MODE == 1) {
-      if (has_x)
-        for (int a = 0, q_ = 4; a < 4; a++) {
-          bst(ps, oHA + a, gadd[a]);
-          for (int bb = a; bb < 4; bb++, q_++) bst(ps, oHA + q_, Hadd[a][bb]);
-        }
+      if (has_u) {
+        const double a9[9] = {m.a02, m.a05, m.a12, m.a15, m.a24, m.a25, m.a33, m.a34, m.a35};
+        for (int i = 0; i < 9; i++) bst(ps, oA + i, a9[i]);
+        for (int i = 0; i < NX; i++) bst(ps, oCD + i, cdef[i]);
+        bst(ps, oSIG, s6), bst(ps, oSIG + 1, s7);
+      }
+      for (int i = 0; i < NW; i++) bst(ps, oG + i, gx[i]);
+      if (has_x) {
+        double Hx[NX][NX];
+        assemble_hx(p, Hadd, sig, has_u ? &m : nullptr, ln, Hx);
+        for (int i = 0; i < NX; i++)
+          for (int j = i; j < NX; j++) bst(ps, oHX + SY(i, j), Hx[i][j]);
+      }
       continue;
     }
-    if (k == N) {
-      for (int i = 0; i < NX; i++) {
-        for (int j = 0; j < NX; j++) Pn[i][j] = p.Q2[SY(i, j)] + ((i < 4 && j < 4) ? Hadd[i][j] : 0.0);
-        Pn[i][i] += sig[i];
-        pn[i] = g[i] + (i < 4 ? gadd[i] : 0.0);
+    if (MODE == 2) {
+      if (has_u) {
+        m.a02 = bld(ps, oA + 0), m.a05 = bld(ps, oA + 1), m.a12 = bld(ps, oA + 2), m.a15 = bld(ps, oA + 3);
+        m.a24 = bld(ps, oA + 4), m.a25 = bld(ps, oA + 5), m.a33 = bld(ps, oA + 6), m.a34 = bld(ps, oA + 7);
+        m.a35 = bld(ps, oA + 8);
+        for (int i = 0; i < NX; i++) cdef[i] = bld(ps, oCD + i);
+        s6 = bld(ps, oSIG), s7 = bld(ps, oSIG + 1);
       }
+      for (int i = 0; i < NW; i++) gx[i] = bld(ps, oG + i);
+    }
+    // ---- the recursion itself
+    if (k == N) {
+      if (MODE == 2)
+        load_hx(ps, Pn);
+      else
+        assemble_hx(p, Hadd, sig, nullptr, ln, Pn);
+      for (int i = 0; i < NX; i++) pn[i] = gx[i];
     } else {
-      Lin m;
-      stage_lin_det(p, w, m);
-      const double f[NX] = {m.f0, m.f1, m.f2, m.f3, w[7], w[6]};
-      double h[NX], cdef[NX];
-      for (int i = 0; i < NX; i++) cdef[i] = defect_det(xn[i], w[i], dt, f[i]);
+      double h[NX];
       for (int i = 0; i < NX; i++) {
         double s = pn[i];
         for (int j = 0; j < NX; j++) s -= Pn[i][j] * cdef[j];
@@ -889,8 +942,8 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
       double PA[NX][NX];  // A = I + dt df/dx has 9 off-diagonal entries: row i of P A is A' applied to row i of P
       for (int i = 0; i < NX; i++) At_mul(m, Pn[i], PA[i]);
       // B has two entries: B[5][0] = B[4][1] = dt
-      const double r00 = p.R2[0] + dt * dt * Pn[5][5] + sig[6], r01 = p.R2[1] + dt * dt * Pn[5][4];
-      const double r11 = p.R2[2] + dt * dt * Pn[4][4] + sig[7];
+      const double r00 = p.R2[0] + dt * dt * Pn[5][5] + s6, r01 = p.R2[1] + dt * dt * Pn[5][4];
+      const double r11 = p.R2[2] + dt * dt * Pn[4][4] + s7;
       const double det = r00 * r11 - r01 * r01;
       if (!(r00 > 0.0) || !(det > 0.0)) return false;
       const double idet = tt_rcp(det);
@@ -902,22 +955,17 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
         Kf[0][j] = i00 * Sh[0][j] + i01 * Sh[1][j];
         Kf[1][j] = i01 * Sh[0][j] + i11 * Sh[1][j];
       }
-      const double bh0 = g[6] + dt * h[5], bh1 = g[7] + dt * h[4];
+      const double bh0 = gx[6] + dt * h[5], bh1 = gx[7] + dt * h[4];
       kff[0] = i00 * bh0 + i01 * bh1;
       kff[1] = i01 * bh0 + i11 * bh1;
       for (int j = 0; j < NX; j++) bst(ps, oK + j, Kf[0][j]), bst(ps, oK + NX + j, Kf[1][j]);
       bst(ps, oKFF, kff[0]), bst(ps, oKFF + 1, kff[1]);
       if (has_x) {
-        Hes ho;
-        stage_hess(p, m, ln, ho);
         double Hx[NX][NX];
-        for (int i = 0; i < NX; i++) {
-          for (int j = 0; j < NX; j++) Hx[i][j] = p.Q2[SY(i, j)] + ((i < 4 && j < 4) ? Hadd[i][j] : 0.0);
-          Hx[i][i] += sig[i];
-        }
-        Hx[2][2] += ho.h22, Hx[2][5] += ho.h25, Hx[5][2] += ho.h25;
-        Hx[3][3] += ho.h33, Hx[3][4] += ho.h34, Hx[4][3] += ho.h34, Hx[3][5] += ho.h35, Hx[5][3] += ho.h35;
-        Hx[4][4] += ho.h44, Hx[4][5] += ho.h45, Hx[5][4] += ho.h45;
+        if (MODE == 2)
+          load_hx(ps, Hx);
+        else
+          assemble_hx(p, Hadd, sig, &m, ln, Hx);
         double Pk[NX][NX], pk[NX], ath[NX];
         for (int j = 0; j < NX; j++) {  // column j of A'(P A)
           double col[NX], acol[NX];
@@ -926,8 +974,7 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
           for (int i = 0; i < NX; i++) Pk[i][j] = Hx[i][j] + acol[i] - (Sh[0][i] * Kf[0][j] + Sh[1][i] * Kf[1][j]);
         }
         At_mul(m, h, ath);
-        for (int i = 0; i < NX; i++)
-          pk[i] = g[i] + (i < 4 ? gadd[i] : 0.0) + ath[i] - (Sh[0][i] * kff[0] + Sh[1][i] * kff[1]);
+        for (int i = 0; i < NX; i++) pk[i] = gx[i] + ath[i] - (Sh[0][i] * kff[0] + Sh[1][i] * kff[1]);
         for (int i = 0; i < NX; i++) {
           pn[i] = pk[i];
           for (int j = 0; j < NX; j++) Pn[i][j] = 0.5 * (Pk[i][j] + Pk[j][i]);
@@ -939,7 +986,8 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
         bst(ps, oPV + i, pn[i]);
         for (int j = i; j < NX; j++) bst(ps, oP + SY(i, j), Pn[i][j]);
       }
-      for (int i = 0; i < NX; i++) xn[i] = w[i], ln[i] = bld(ps, oLAM + i);
+      if (MODE == 0)
+        for (int i = 0; i < NX; i++) xn[i] = w[i], ln[i] = bld(ps, oLAM + i);
     }
   }
   if (MODE == 1 && ob_lane0()) c.wd.part[c.wd.wid * kPart] = 1.0;
