@@ -737,15 +737,16 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
 }
 
 // Hessian block of stage k >= 1: 2Q + condensed pairs + Sigma (+delta) [- dt * sum_i lambda_i d2f_i/dx2 for k < N]
-TT_HD void assemble_hx(const Params& p, const double (*Hadd)[4], const double* sig, const Lin* m, const double* ln,
+template <bool HES>
+TT_HD void assemble_hx(const Params& p, const double (*Hadd)[4], const double* sig, const Lin& m, const double* ln,
                        double (*Hx)[NX]) {
   for (int i = 0; i < NX; i++) {
     for (int j = 0; j < NX; j++) Hx[i][j] = p.Q2[SY(i, j)] + ((i < 4 && j < 4) ? Hadd[i][j] : 0.0);
     Hx[i][i] += sig[i];
   }
-  if (m != nullptr) {
+  if (HES) {
     Hes ho;
-    stage_hess(p, *m, ln, ho);
+    stage_hess(p, m, ln, ho);
     Hx[2][2] += ho.h22, Hx[2][5] += ho.h25, Hx[5][2] += ho.h25;
     Hx[3][3] += ho.h33, Hx[3][4] += ho.h34, Hx[4][3] += ho.h34, Hx[3][5] += ho.h35, Hx[5][3] += ho.h35;
     Hx[4][4] += ho.h44, Hx[4][5] += ho.h45, Hx[5][4] += ho.h45;
@@ -909,7 +910,10 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
       for (int i = 0; i < NW; i++) bst(ps, oG + i, gx[i]);
       if (has_x) {
         double Hx[NX][NX];
-        assemble_hx(p, Hadd, sig, has_u ? &m : nullptr, ln, Hx);
+        if (has_u)
+          assemble_hx<true>(p, Hadd, sig, m, ln, Hx);
+        else
+          assemble_hx<false>(p, Hadd, sig, m, ln, Hx);
         for (int i = 0; i < NX; i++)
           for (int j = i; j < NX; j++) bst(ps, oHX + SY(i, j), Hx[i][j]);
       }
@@ -930,7 +934,7 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
       if (MODE == 2)
         load_hx(ps, Pn);
       else
-        assemble_hx(p, Hadd, sig, nullptr, ln, Pn);
+        assemble_hx<false>(p, Hadd, sig, m, ln, Pn);
       for (int i = 0; i < NX; i++) pn[i] = gx[i];
     } else {
       double h[NX];
@@ -965,7 +969,7 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
         if (MODE == 2)
           load_hx(ps, Hx);
         else
-          assemble_hx(p, Hadd, sig, &m, ln, Hx);
+          assemble_hx<true>(p, Hadd, sig, m, ln, Hx);
         double Pk[NX][NX], pk[NX], ath[NX];
         for (int j = 0; j < NX; j++) {  // column j of A'(P A)
           double col[NX], acol[NX];
@@ -988,6 +992,219 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
       }
       if (MODE == 0)
         for (int i = 0; i < NX; i++) xn[i] = w[i], ln[i] = bld(ps, oLAM + i);
+    }
+  }
+  if (MODE == 1 && ob_lane0()) c.wd.part[c.wd.wid * kPart] = 1.0;
+  ob_sync();
+  return true;
+}
+
+// The fused single-warp flavour (ttmpc_obca_kernel): kept as its own function -- the split into a stage-local part and a
+// recursion that the wide kernel needs costs this path 7 % (more values live across the pair loop).
+TT_HD bool factor_fused(const Ctx& c, double mu, double delta) {
+  constexpr int MODE = 0;
+  const Params& p = *c.p;
+  const ObParams& o = *c.o;
+  const int N = p.N;
+  const double dt = p.dt;
+  double Pn[NX][NX], pn[NX], xn[NX], ln[NX];
+  for (int i = 0; i < NX; i++) {
+    pn[i] = xn[i] = ln[i] = 0.0;
+    for (int j = 0; j < NX; j++) Pn[i][j] = 0.0;
+  }
+  if (MODE == 2)  // the pair phase found a block that is not positive definite
+    for (int w_ = 0; w_ < c.wd.nw; w_++)
+      if (c.wd.part[w_ * kPart] == 0.0) return false;
+  for (int k = N; k >= 0; k--) {
+    if (MODE == 1 && (k % c.wd.nw) != c.wd.wid) continue;
+    double* ps = c.stage(k);
+    const bool has_x = k >= 1, has_u = k < N;
+    double w[NW], g[NW], sig[NW];
+    {
+      double ref[NW];
+      for (int j = 0; j < NW; j++) {
+        const bool on = (j < NX) || has_u;
+        w[j] = on ? bld(ps, oW + j) : 0.0;
+        ref[j] = on ? bld(ps, oREF + j) : 0.0;
+      }
+      for (int i = 0; i < NX; i++) {
+        double s = 0.0;
+        for (int j = 0; j < NX; j++) s += p.Q2[SY(i, j)] * (w[j] - ref[j]);
+        g[i] = s;
+      }
+      g[6] = p.R2[0] * (w[6] - ref[6]) + p.R2[1] * (w[7] - ref[7]);
+      g[7] = p.R2[1] * (w[6] - ref[6]) + p.R2[2] * (w[7] - ref[7]);
+    }
+    for (int j = 0; j < NW; j++) {
+      const bool var = (j < NX) ? has_x : has_u;
+      sig[j] = delta;
+      if (var && var_lo(p, j)) {
+        const double rl = tt_rcp(w[j] - p.lo[j]);
+        sig[j] += bld(ps, oZL + j) * rl;
+        g[j] -= mu * rl;
+      }
+      if (var && var_up(p, j)) {
+        const double ru = tt_rcp(p.up[j] - w[j]);
+        sig[j] += bld(ps, oZU + j) * ru;
+        g[j] += mu * ru;
+      }
+    }
+    // ---- pairs: Schur complement onto (x, y, theta, psi) ----
+    double Hadd[4][4], gadd[4];
+    for (int i = 0; i < 4; i++) {
+      gadd[i] = 0.0;
+      for (int j = 0; j < 4; j++) Hadd[i][j] = 0.0;
+    }
+    bool ok = true;
+    Trig t;
+    stage_trig(w, t);
+    if (MODE != 2)
+    OB_FOR_LANES(pj, o.P) {
+      double* pp = pair_ptr(ps, pj);
+      double v[8], zv[8], s[4], y[4], zs[6];
+      for (int i = 0; i < 8; i++) v[i] = pld(pp, qV + i), zv[i] = pld(pp, qZV + i);
+      for (int i = 0; i < 4; i++) s[i] = pld(pp, qS + i), y[i] = pld(pp, qY + i);
+      for (int i = 0; i < 6; i++) zs[i] = pld(pp, qZS + i);
+      PairEval e;
+      pair_eval<true>(o, pj & 1, o.b[pj], t, v, y, e);
+      SlackBar sb;
+      slack_bar(o, s, zs, delta, sb);
+      double K[8][8], Kvx[8][4], q[8], tt[4];
+      pair_system(o, e, sb, v, zv, s, mu, delta, K, Kvx, q, tt);
+      if (!chol8(K)) ok = false;
+      // u = L^-1 q, Y = L^-1 K_vx for the Schur complement;  a = L^-T u, G = L^-T Y are kept for the direction sweep, which
+      // therefore uses exactly this factorisation (two separately compiled factorisations differ in the last bits, and
+      // with multipliers of 1e5 and Sigma_s of 1e10 that difference is a 1e-4 floor on the dual infeasibility)
+      fsub8(K, q);
+      double col[4][8];
+      for (int cc = 0; cc < 4; cc++) {
+        for (int i = 0; i < 8; i++) col[cc][i] = Kvx[i][cc];
+        fsub8(K, col[cc]);
+      }
+      {
+        double a8[8];
+        for (int i = 0; i < 8; i++) a8[i] = q[i];
+        bsub8(K, a8);
+        for (int i = 0; i < 8; i++) pst(pp, qA + i, a8[i]);
+        if (has_x)
+          for (int cc = 0; cc < 4; cc++) {
+            for (int i = 0; i < 8; i++) a8[i] = col[cc][i];
+            bsub8(K, a8);
+            for (int i = 0; i < 8; i++) pst(pp, qG + 4 * i + cc, a8[i]);
+          }
+      }
+      if (!has_x) continue;  // x_0 is data: no coupling to condense
+      for (int a = 0; a < 4; a++) {
+        double ga = 0.0;
+        for (int r = 0; r < 4; r++) ga += e.Jx[r][a] * tt[r];
+        for (int i = 0; i < 8; i++) ga -= col[a][i] * q[i];
+        gadd[a] += ga;
+        for (int bb = 0; bb < 4; bb++) {
+          double h = 0.0;
+          for (int r = 0; r < 4; r++) h += sb.D[r] * e.Jx[r][a] * e.Jx[r][bb];
+          for (int i = 0; i < 8; i++) h -= col[a][i] * col[bb][i];
+          Hadd[a][bb] += h;
+        }
+      }
+      Hadd[2][2] += e.hthth;
+      Hadd[2][3] += e.hthps, Hadd[3][2] += e.hthps;
+      Hadd[3][3] += e.hthps;
+    }
+    if (MODE != 2 && !ob_all(ok)) {
+      if (MODE == 1 && ob_lane0()) c.wd.part[c.wd.wid * kPart] = 0.0;
+      return false;
+    }
+    if (MODE == 2) {  // what the pair phase left for this stage
+      if (has_x)
+        for (int a = 0, q_ = 4; a < 4; a++) {
+          gadd[a] = 0.0;
+          for (int bb = a; bb < 4; bb++, q_++) Hadd[a][bb] = Hadd[bb][a] = 0.0;
+        }
+    } else {
+      for (int a = 0; a < 4; a++) {  // combine the pairs' Schur complements (upper triangle, then mirror)
+        gadd[a] = ob_sum(gadd[a]);
+        for (int bb = a; bb < 4; bb++) Hadd[a][bb] = Hadd[bb][a] = ob_sum(Hadd[a][bb]);
+      }
+    }
+    if (MODE == 1) {
+      if (has_x)
+        for (int a = 0, q_ = 4; a < 4; a++) {
+          (void)gadd[a];
+          for (int bb = a; bb < 4; bb++, q_++) (void)Hadd[a][bb];
+        }
+      continue;
+    }
+    if (k == N) {
+      for (int i = 0; i < NX; i++) {
+        for (int j = 0; j < NX; j++) Pn[i][j] = p.Q2[SY(i, j)] + ((i < 4 && j < 4) ? Hadd[i][j] : 0.0);
+        Pn[i][i] += sig[i];
+        pn[i] = g[i] + (i < 4 ? gadd[i] : 0.0);
+      }
+    } else {
+      Lin m;
+      stage_lin_det(p, w, m);
+      const double f[NX] = {m.f0, m.f1, m.f2, m.f3, w[7], w[6]};
+      double h[NX], cdef[NX];
+      for (int i = 0; i < NX; i++) cdef[i] = defect_det(xn[i], w[i], dt, f[i]);
+      for (int i = 0; i < NX; i++) {
+        double s = pn[i];
+        for (int j = 0; j < NX; j++) s -= Pn[i][j] * cdef[j];
+        h[i] = s;
+      }
+      double PA[NX][NX];  // A = I + dt df/dx has 9 off-diagonal entries: row i of P A is A' applied to row i of P
+      for (int i = 0; i < NX; i++) At_mul(m, Pn[i], PA[i]);
+      // B has two entries: B[5][0] = B[4][1] = dt
+      const double r00 = p.R2[0] + dt * dt * Pn[5][5] + sig[6], r01 = p.R2[1] + dt * dt * Pn[5][4];
+      const double r11 = p.R2[2] + dt * dt * Pn[4][4] + sig[7];
+      const double det = r00 * r11 - r01 * r01;
+      if (!(r00 > 0.0) || !(det > 0.0)) return false;
+      const double idet = tt_rcp(det);
+      const double i00 = r11 * idet, i01 = -r01 * idet, i11 = r00 * idet;
+      double Sh[NU][NX], Kf[NU][NX], kff[NU];
+      for (int j = 0; j < NX; j++) {
+        Sh[0][j] = dt * PA[5][j];
+        Sh[1][j] = dt * PA[4][j];
+        Kf[0][j] = i00 * Sh[0][j] + i01 * Sh[1][j];
+        Kf[1][j] = i01 * Sh[0][j] + i11 * Sh[1][j];
+      }
+      const double bh0 = g[6] + dt * h[5], bh1 = g[7] + dt * h[4];
+      kff[0] = i00 * bh0 + i01 * bh1;
+      kff[1] = i01 * bh0 + i11 * bh1;
+      for (int j = 0; j < NX; j++) bst(ps, oK + j, Kf[0][j]), bst(ps, oK + NX + j, Kf[1][j]);
+      bst(ps, oKFF, kff[0]), bst(ps, oKFF + 1, kff[1]);
+      if (has_x) {
+        Hes ho;
+        stage_hess(p, m, ln, ho);
+        double Hx[NX][NX];
+        for (int i = 0; i < NX; i++) {
+          for (int j = 0; j < NX; j++) Hx[i][j] = p.Q2[SY(i, j)] + ((i < 4 && j < 4) ? Hadd[i][j] : 0.0);
+          Hx[i][i] += sig[i];
+        }
+        Hx[2][2] += ho.h22, Hx[2][5] += ho.h25, Hx[5][2] += ho.h25;
+        Hx[3][3] += ho.h33, Hx[3][4] += ho.h34, Hx[4][3] += ho.h34, Hx[3][5] += ho.h35, Hx[5][3] += ho.h35;
+        Hx[4][4] += ho.h44, Hx[4][5] += ho.h45, Hx[5][4] += ho.h45;
+        double Pk[NX][NX], pk[NX], ath[NX];
+        for (int j = 0; j < NX; j++) {  // column j of A'(P A)
+          double col[NX], acol[NX];
+          for (int l = 0; l < NX; l++) col[l] = PA[l][j];
+          At_mul(m, col, acol);
+          for (int i = 0; i < NX; i++) Pk[i][j] = Hx[i][j] + acol[i] - (Sh[0][i] * Kf[0][j] + Sh[1][i] * Kf[1][j]);
+        }
+        At_mul(m, h, ath);
+        for (int i = 0; i < NX; i++)
+          pk[i] = g[i] + (i < 4 ? gadd[i] : 0.0) + ath[i] - (Sh[0][i] * kff[0] + Sh[1][i] * kff[1]);
+        for (int i = 0; i < NX; i++) {
+          pn[i] = pk[i];
+          for (int j = 0; j < NX; j++) Pn[i][j] = 0.5 * (Pk[i][j] + Pk[j][i]);
+        }
+      }
+    }
+    if (has_x) {
+      for (int i = 0; i < NX; i++) {
+        bst(ps, oPV + i, pn[i]);
+        for (int j = i; j < NX; j++) bst(ps, oP + SY(i, j), Pn[i][j]);
+      }
+      for (int i = 0; i < NX; i++) xn[i] = w[i], ln[i] = bld(ps, oLAM + i);
     }
   }
   if (MODE == 1 && ob_lane0()) c.wd.part[c.wd.wid * kPart] = 1.0;
@@ -1291,7 +1508,7 @@ TT_HD void run_update_stats(const Ctx& c, bool do_update, double alpha, double a
 
 template <bool WIDE>
 TT_HD bool run_factor(const Ctx& c, double mu, double delta) {
-  if (!WIDE) return factor<0>(c, mu, delta);
+  if (!WIDE) return factor_fused(c, mu, delta);
 #if defined(__CUDA_ARCH__)
   ob_cta_sync();
   factor<1>(c, mu, delta);
