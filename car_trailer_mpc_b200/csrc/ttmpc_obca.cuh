@@ -1241,7 +1241,9 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
     double w[NW], g[NW];
     if (MODE == 1)  // pair phase: dx of the stage was stored by the recursion on warp 0
       for (int i = 0; i < NX; i++) dx[i] = has_x ? bld(ps, oDW + i) : 0.0;
-    {
+    if (MODE == 2) {  // the recursion needs neither the iterate nor the gradient
+      for (int j = 0; j < NW; j++) w[j] = g[j] = 0.0;
+    } else {
       double ref[NW];
       for (int j = 0; j < NW; j++) {
         const bool on = (j < NX) || has_u;
@@ -1259,8 +1261,9 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
     double dw[NW];
     for (int j = 0; j < NX; j++) dw[j] = dx[j];
     dw[6] = dw[7] = 0.0;
-    if (MODE != 1) {
-    if (has_u) {
+    if (MODE == 1) {
+      if (has_u) dw[6] = bld(ps, oDW + 6), dw[7] = bld(ps, oDW + 7);
+    } else if (has_u) {
       for (int i = 0; i < NU; i++) {
         double s = -bld(ps, oKFF + i);
         for (int j = 0; j < NX; j++) s -= bld(ps, oK + i * NX + j) * dx[j];
@@ -1270,7 +1273,8 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
     for (int j = 0; j < NW; j++) {
       const bool var = (j < NX) ? has_x : has_u;
       if (!var) continue;
-      bst(ps, oDW + j, dw[j]);
+      if (MODE != 1) bst(ps, oDW + j, dw[j]);
+      if (MODE == 2) continue;  // step limits and grad(phi)'d of the (x, u) part: by the stage's warp in MODE 1
       double gb = g[j];
       if (var_lo(p, j)) {
         const double dist = w[j] - p.lo[j];
@@ -1284,10 +1288,9 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
       }
       di.gphi_d += gb * dw[j];
     }
-    }  // MODE != 1
     // pairs: dv = -K_vv^-1 (q + K_vx dxt),  ds = J_x dxt + J_v dv + r_c
     Trig t;
-    stage_trig(w, t);
+    if (MODE != 2) stage_trig(w, t);
     if (MODE != 2)
     OB_FOR_LANES(pj, o.P) {
       double* pp = pair_ptr(ps, pj);
@@ -1331,13 +1334,21 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
     if (MODE != 1 && has_u) {  // dx_{k+1} = A dx + B du - c_{k+1};  lambda+_{k+1} = -(p_{k+1} + P_{k+1} dx_{k+1})
       double* pq = c.stage(k + 1);
       Lin m;
-      stage_lin_det(p, w, m);
-      const double f[NX] = {m.f0, m.f1, m.f2, m.f3, w[7], w[6]};
       double nd[NX];
-      A_mul(m, dx, nd);
+      if (MODE == 2) {  // A and the defect as the factor sweep left them (the very same numbers, see stage_lin_det)
+        m.a02 = bld(ps, oA + 0), m.a05 = bld(ps, oA + 1), m.a12 = bld(ps, oA + 2), m.a15 = bld(ps, oA + 3);
+        m.a24 = bld(ps, oA + 4), m.a25 = bld(ps, oA + 5), m.a33 = bld(ps, oA + 6), m.a34 = bld(ps, oA + 7);
+        m.a35 = bld(ps, oA + 8);
+        A_mul(m, dx, nd);
+        for (int i = 0; i < NX; i++) nd[i] -= bld(ps, oCD + i);
+      } else {
+        stage_lin_det(p, w, m);
+        const double f[NX] = {m.f0, m.f1, m.f2, m.f3, w[7], w[6]};
+        A_mul(m, dx, nd);
+        for (int i = 0; i < NX; i++) nd[i] -= defect_det(bld(pq, oW + i), w[i], p.dt, f[i]);
+      }
       nd[4] += p.dt * dw[7];
       nd[5] += p.dt * dw[6];
-      for (int i = 0; i < NX; i++) nd[i] -= defect_det(bld(pq, oW + i), w[i], p.dt, f[i]);
       for (int i = 0; i < NX; i++) {
         double s = bld(pq, oPV + i);
         for (int j = 0; j < NX; j++) s += bld(pq, oP + SY(i, j)) * nd[j];
@@ -1346,10 +1357,10 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
       for (int i = 0; i < NX; i++) dx[i] = nd[i];
     }
   }
-  if (MODE == 1) {  // this warp's share of the pairs' step limits
-    const double v3[3] = {ob_min(dq.a_pr), ob_min(dq.a_du), ob_sum(dq.gphi_d)};
+  if (MODE == 1) {  // this warp's share: the pairs' step limits (per-lane partials) and those of its stages' (x, u)
+    const double v6[6] = {ob_min(dq.a_pr), ob_min(dq.a_du), ob_sum(dq.gphi_d), di.a_pr, di.a_du, di.gphi_d};
     if (ob_lane0())
-      for (int i = 0; i < 3; i++) c.wd.part[c.wd.wid * kPart + i] = v3[i];
+      for (int i = 0; i < 6; i++) c.wd.part[c.wd.wid * kPart + i] = v6[i];
     ob_sync();
     return;
   }
@@ -1538,25 +1549,24 @@ TT_HD void run_direction(const Ctx& c, double mu, double tau, double delta, Dir&
   Dir dummy;
 #if defined(__CUDA_ARCH__)
   ob_cta_sync();
-  if (c.wd.wid == 0) {
-    direction<2>(c, mu, tau, delta, di);
-    if (ob_lane0()) c.wd.bcast[0] = di.a_pr, c.wd.bcast[1] = di.a_du, c.wd.bcast[2] = di.gphi_d;
-  }
+  if (c.wd.wid == 0) direction<2>(c, mu, tau, delta, dummy);  // the dx / lambda+ recursion
   ob_cta_sync();
-  di.a_pr = c.wd.bcast[0], di.a_du = c.wd.bcast[1], di.gphi_d = c.wd.bcast[2];
-  direction<1>(c, mu, tau, delta, dummy);
+  direction<1>(c, mu, tau, delta, dummy);  // pairs and step limits, stage k on warp k % nw
   ob_cta_sync();
 #else
-  direction<2>(c, mu, tau, delta, di);
+  direction<2>(c, mu, tau, delta, dummy);
   for (int w = 0; w < c.wd.nw; w++) {
     Ctx cw = c;
     cw.wd.wid = w;
     direction<1>(cw, mu, tau, delta, dummy);
   }
 #endif
+  di.a_pr = di.a_du = 1.0;
+  di.gphi_d = 0.0;
   for (int w = 0; w < c.wd.nw; w++) {
     const double* pt = c.wd.part + w * kPart;
-    di.a_pr = tt_min(di.a_pr, pt[0]), di.a_du = tt_min(di.a_du, pt[1]), di.gphi_d += pt[2];
+    di.a_pr = tt_min(di.a_pr, tt_min(pt[0], pt[3])), di.a_du = tt_min(di.a_du, tt_min(pt[1], pt[4]));
+    di.gphi_d += pt[2] + pt[5];
   }
 }
 
