@@ -838,10 +838,10 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_wide, ttmpc_obca_wide_kernel, kObcaThreads, 0);
   if (per_sm < 1) per_sm = 1;
   if (per_sm_wide < 1) per_sm_wide = 1;
-  // up to 12 problems per SM: one CTA per problem (measured on B200, N = 50: 35 vs 73 ms for one problem, 575 vs 692 ms
-  // for 1 184, equal at 2 048); beyond that: one warp per problem (16 384: 3.8 vs 6.3 s)
+  // up to 48 problems per SM: one CTA per problem (measured on B200, N = 50: 21 vs 73 ms for one problem, 376 vs 692 ms
+  // for 1 184, 2.23 vs 2.25 s for 8 192); beyond that: one warp per problem (16 384: 4.1 vs 4.6 s)
   const char* wenv = getenv("TTMPC_OBCA_WIDE_MAX");
-  const bool wide = B <= (wenv ? atoll(wenv) : 12LL * sms);
+  const bool wide = B <= (wenv ? atoll(wenv) : 48LL * sms);
   const int wpc = wide ? 1 : kObcaThreads / 32;
   long long blocks = (B + wpc - 1) / wpc;
   const long long cap = (long long)sms * (wide ? per_sm_wide : per_sm);
