@@ -40,6 +40,17 @@ def test_config_struct_matches_header(L):
             assert a == b, f
 
 
+def test_obstacle_struct_matches_header():
+    """struct ttmpc_obstacles: {int32 count, int32 reserved, double rect[MAX][4], double W1, W2, d_min}."""
+    from car_trailer_mpc_b200.config import MAX_OBSTACLES, Obstacles, parking_lot_obstacles
+    hdr = open(os.path.join(ROOT, "include", "ttmpc.h")).read()
+    assert int(re.search(r"#define TTMPC_MAX_OBSTACLES (\d+)", hdr).group(1)) == MAX_OBSTACLES
+    assert ctypes.sizeof(Obstacles) == 8 + MAX_OBSTACLES * 4 * 8 + 3 * 8
+    assert Obstacles.rect.offset == 8 and Obstacles.W1.offset == 8 + MAX_OBSTACLES * 32
+    o = Obstacles.from_list(parking_lot_obstacles())
+    assert o.count == 11 and o.as_list() == parking_lot_obstacles() and (o.W1, o.W2, o.d_min) == (3.05, 2.95, 0.2)
+
+
 def test_invalid_config_is_rejected(L):
     h = ctypes.c_void_p()
     c = tracking_preset(40); c.horizon = 0
