@@ -50,17 +50,27 @@ def test_gpu_matches_dense_oracle_golden(c):
     assert np.array_equal(xs[0], c["x_init"])
 
 
-def test_gpu_matches_host_build_of_the_core_on_a_seeded_batch():
+@pytest.mark.parametrize("wide_max", ["0", None], ids=["warp_per_problem", "cta_per_problem"])
+def test_gpu_matches_host_build_of_the_core_on_a_seeded_batch(wide_max, monkeypatch):
+    """Both kernels of the obstacle-aware path: TTMPC_OBCA_WIDE_MAX=0 forces ttmpc_obca_kernel (one warp per problem),
+    the default takes ttmpc_obca_wide_kernel (one CTA per problem) for a batch of this size."""
     import emu
     import torch
+    if wide_max is None:
+        monkeypatch.delenv("TTMPC_OBCA_WIDE_MAX", raising=False)
+    else:
+        monkeypatch.setenv("TTMPC_OBCA_WIDE_MAX", wide_max)
     cfg = tracking_preset(20)
     cfg.max_iter = 300
     obs = Obstacles.from_list(parking_lot_obstacles())
     S, U, ks, x0 = scenarios(cfg, 40, seed=7, kmax=400)  # the tail (k > 340) rides the d_min boundary: failures included
     dev = torch.device("cuda:0")
-    g = solver(cfg).solve_obca_shared(obs, torch.from_numpy(x0).to(dev), torch.from_numpy(ks).to(dev),
-                                      torch.from_numpy(S).to(dev), torch.from_numpy(U).to(dev))
+    sv = solver(cfg)
+    g = sv.solve_obca_shared(obs, torch.from_numpy(x0).to(dev), torch.from_numpy(ks).to(dev),
+                             torch.from_numpy(S).to(dev), torch.from_numpy(U).to(dev))
     g = {k: v.cpu().numpy() for k, v in g.items()}
+    launches = sv.kernel_launches()
+    assert launches["ttmpc_obca_kernel" if wide_max == "0" else "ttmpc_obca_wide_kernel"] == 1
     e = emu.obca_solve_batch(cfg, obs, x0, k_index=ks, traj_states=S, traj_inputs=U)
     ok = (g["status"] == 0) & (e["status"] == 0)
     assert ok.sum() >= 30
