@@ -6,6 +6,7 @@ GPU; the resulting .so is git-ignored but travels to the GPU box with the reposi
 from __future__ import annotations
 
 import os
+import shlex
 import shutil
 import subprocess
 import sys
@@ -42,13 +43,15 @@ def is_stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB, SRC]
+    # TTMPC_NVCC_FLAGS: extra flags for experiment builds (e.g. -DTTMPC_SPECULATION=1), TTMPC_BUILD_OUT: their output path
+    out = os.environ.get("TTMPC_BUILD_OUT") or LIB
+    cmd = [nvcc_path(), *NVCC_FLAGS, *shlex.split(os.environ.get("TTMPC_NVCC_FLAGS", "")), "-o", out, SRC]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

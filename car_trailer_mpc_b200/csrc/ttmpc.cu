@@ -171,6 +171,9 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
     bool done = false;
     const bool warp_fresh = __any_sync(kFull, active && st.fresh);
     if (active) done = ipm_backward<G, DQ, PW>(p, s0, cy, in, prob, warp_fresh, st, res);
+#if TTMPC_SPECULATION
+    if (active && !done && st.fresh) atomicAdd(counter + 15, 1ull);  // diagnostic: a speculative step was rejected (restart)
+#endif
     __syncthreads();
     if (active && !done) done = ipm_step<G, DQ, PW>(p, s0, cy, st, res);
     __syncwarp();
@@ -418,7 +421,7 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
 
     bool done = false;
     const bool warp_fresh = __any_sync(kFull, active && st.fresh);
-    if (active) done = ipm_backward<G, DQ, false>(p, s0, cy, in, scen, warp_fresh, st, res);
+    if (active) done = ipm_backward<G, DQ, false, false>(p, s0, cy, in, scen, warp_fresh, st, res);
     __syncthreads();
     if (active && !done) done = ipm_step_rr<G, DQ, false>(p, s0, cy, st, res);
     __syncwarp();
@@ -716,6 +719,12 @@ int ttmpc_create(const ttmpc_config* cfg, int device, ttmpc_handle** out) {
   if (!h) return TTMPC_E_NOMEM;
   memset(h, 0, sizeof *h);
   h->cfg = *cfg;
+#if TTMPC_SPECULATION  // experiment builds: speculative first line-search trial in ttmpc_solve_kernel (0, 1, 2)
+  if (const char* e = getenv("TTMPC_SPECULATE")) {
+    const int v = atoi(e);
+    if (v >= 0 && v <= 2) p.speculate = v;
+  }
+#endif
   h->p = p;
   h->device = device;
   int sms = 0, per_sm = 0;
@@ -823,6 +832,12 @@ static int solve_device(ttmpc_handle* h, long long B, const ProblemIn& in, const
   h->launches[0]++;
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "kernel launch", ce);
+  if (kSpecBuild && getenv("TTMPC_DEBUG_RESTARTS")) {  // diagnostic (synchronises): rejected speculative steps of this launch
+    unsigned long long n = 0;
+    cudaStreamSynchronize(st);
+    cudaMemcpy(&n, h->counter + 15, sizeof n, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "ttmpc: B=%lld restarts=%llu\n", B, n);
+  }
   return TTMPC_OK;
 }
 

@@ -46,10 +46,17 @@
 #ifndef TTMPC_BANK
 #define TTMPC_BANK 32
 #endif
+// 1: compile the speculative first line-search trial into ipm_step / ipm_backward (selected at run time by
+// Params::speculate).  Off in the shipped library: measured +2 % on the classic path for code that only pays off once
+// rejected steps can be rolled back ("Speculative first trial").
+#ifndef TTMPC_SPECULATION
+#define TTMPC_SPECULATION 0
+#endif
 
 namespace ttmpc {
 
 constexpr int NX = 6, NU = 2, NW = 8;
+constexpr bool kSpecBuild = TTMPC_SPECULATION != 0;
 
 // ---- Ipopt 3.14 default constants ----
 constexpr double kBoundRelax = 1e-8, kBoundPush = 1e-2, kBoundFrac = 1e-2, kNlpInf = 1e19;
@@ -89,6 +96,9 @@ struct Params {
   double lo[NW], up[NW];     // relaxed bounds (bound_relax_factor), x then u
   double lo_push[NW], up_push[NW];  // lo + push, up - push (bound_push / bound_frac): clamp range of the starting point
   double tol, acc_tol, mu_init, mu_floor;
+#if TTMPC_SPECULATION
+  int speculate;  // 0: classic trial sweeps; 1, 2: ipm_step takes the first line-search trial point speculatively
+#endif
 };
 
 TT_HD constexpr int SY(int i, int j) { return i <= j ? (i * (13 - i)) / 2 + (j - i) : (j * (13 - j)) / 2 + (i - j); }
@@ -140,6 +150,18 @@ inline size_t scratch_doubles(int N, size_t nbanks) { return nbanks * (size_t)(N
 #else
 #define TT_FENCE() ((void)0)
 #endif
+
+// high word of a double (sign, exponent, top of the mantissa): OR-ing these over a set of values gives a negative
+// integer exactly when one of the values has its sign bit set -- one integer instruction per value
+TT_HD int tt_hiword(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2hiint(x);
+#else
+  int64_t b;
+  memcpy(&b, &x, sizeof b);
+  return (int)(b >> 32);
+#endif
+}
 
 TT_HD double tt_max(double a, double b) { return a > b ? a : b; }
 TT_HD double tt_min(double a, double b) { return a < b ? a : b; }
@@ -371,6 +393,9 @@ struct Stats {
   double J, sumlog, theta, cinf;  // objective, sum ln(slack), ||c||_1, ||c||_inf
   double rd_inf, lam1, z1;        // ||grad L||_inf, ||lambda||_1, ||z_L||_1 + ||z_U||_1
   double cmax, cmin;              // max / min of slack*multiplier
+#if TTMPC_SPECULATION
+  int slack_sign;                 // OR of the high words of all slacks: negative <=> some slack is negative
+#endif
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -395,6 +420,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
   const double dt = p.dt;
   bool ok = true;
   double J = 0.0, sumlog = 0.0, theta = 0.0, cinf = 0.0, rd_inf = 0.0, lam1 = 0.0, z1 = 0.0, cmax = 0.0, cmin = INFINITY;
+  int slack_sign = 0;
   const double kmu_hi = kKappaSigma * mu_step, kmu_lo = mu_step * (1.0 / kKappaSigma);
   const int kk_fresh = (fresh && in.ref_states == nullptr) ? in.k_index[b] : 0;  // shared-trajectory window start
   if (PW && fresh) {  // entering problem: its weight scalings (squared) go to the lane's carried storage
@@ -582,6 +608,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
           sg += zl[j] * rl;
           gg -= rl;
           prod *= sl;
+          if (kSpecBuild) slack_sign |= tt_hiword(sl);
           z1 += zl[j];
           const double c = sl * zl[j];
           cmax = tt_max(cmax, c);
@@ -594,6 +621,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
           sg += zu[j] * ru;
           gg += ru;
           prod *= su;
+          if (kSpecBuild) slack_sign |= tt_hiword(su);
           z1 += zu[j];
           const double c = su * zu[j];
           cmax = tt_max(cmax, c);
@@ -784,6 +812,11 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
   st.z1 = z1;
   st.cmax = cmax;
   st.cmin = cmin;
+#if TTMPC_SPECULATION
+  st.slack_sign = slack_sign;
+#else
+  (void)slack_sign;
+#endif
   return ok;
 }
 
@@ -792,6 +825,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
 // ------------------------------------------------------------------------------------------------
 struct StepInfo {
   double a_pr, a_du, gphi_d;
+  double qmax;  // max_i(-ds_i / s_i): the largest fraction of a slack the full step would consume
 };
 
 // inputs of one stage of the forward sweep
@@ -919,6 +953,7 @@ TT_HD void forward_sweep(const Params& p, double* s0, const Carry& cy, double mu
       x[j] = cur.xnext[j];
     }
   }
+  si.qmax = qmax;
   si.a_pr = (qmax > tau) ? tau / qmax : 1.0;
   si.a_du = (bn > tau * bd) ? tau * bd / bn : 1.0;
   si.gphi_d = gd;
@@ -1024,6 +1059,11 @@ struct Ipm {
   double ls_a, ls_apr, ls_adu, ls_gd;
   int ls_bt;
   bool ls_active;
+  // speculative first trial (ipm_step): `spec` = the step handed to the next backward sweep has not passed the line-search
+  // test yet; `safe` = this problem runs the classic trial sweeps (speculation off, or it was restarted after a rejection)
+#if TTMPC_SPECULATION
+  bool spec, safe;
+#endif
 };
 
 TT_HD bool tt_finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
@@ -1043,12 +1083,53 @@ TT_HD void ipm_begin(const Params& p, Ipm& s) {
   s.fresh = true;
   s.ls_active = false;
   s.ls_bt = 0;
+#if TTMPC_SPECULATION
+  s.spec = false;
+  s.safe = (p.speculate == 0);
+#endif
+}
+
+// One acceptance test of the filter line search (Waechter & Biegler 2006, Algorithm A): trial point (theta_t, phi_t)
+// reached with step a along a direction with grad(phi)'d = gd from the current iterate (theta, phi).  On acceptance
+// with the theta-type rule the filter is augmented.
+TT_HD bool ls_accept(Ipm& s, double theta, double phi, double gd, double a, double theta_t, double phi_t) {
+  if (theta_t > s.theta_max) return false;
+  bool dominated = false;
+  for (int i = 0; i < s.f_n; i++)
+    if (theta_t >= s.f_theta[i] && phi_t >= s.f_phi[i]) dominated = true;
+  if (dominated) return false;
+  // switching condition  a*(-g)^s_phi > delta*theta^s_theta, evaluated in logs (theta = 0: always true)
+  bool good, ftype = false;
+  if (theta <= s.theta_min && gd < 0.0 && (theta <= 0.0 || log(a) + kSPhi * log(-gd) > log(kDeltaSw) + kSTheta * log(theta))) {
+    good = (phi_t - phi - 10.0 * kEps * fabs(phi) <= kEtaPhi * a * gd);
+    ftype = true;
+  } else {
+    good = (theta_t - (1.0 - kGammaTheta) * theta <= 10.0 * kEps * fabs(theta)) ||
+           (phi_t - (phi - kGammaPhi * theta) <= 10.0 * kEps * fabs(phi));
+  }
+  if (!good) return false;
+  if (!ftype) {
+    const double ft = (1.0 - kGammaTheta) * theta, fp = phi - kGammaPhi * theta;
+    int m = 0;
+    for (int i = 0; i < s.f_n; i++)
+      if (!(s.f_theta[i] >= ft && s.f_phi[i] >= fp)) {
+        s.f_theta[m] = s.f_theta[i];
+        s.f_phi[m] = s.f_phi[i];
+        m++;
+      }
+    if (m == kFilterMax) m--;
+    s.f_theta[m] = ft;
+    s.f_phi[m] = fp;
+    s.f_n = m + 1;
+  }
+  return true;
 }
 
 // One interior-point iteration = ipm_backward (apply previous step, statistics, termination tests, barrier update,
 // factorisation) + ipm_step (search direction, line search).  Both return true when the lane is finished (res filled
 // in).  They are separate so that the CUDA kernel can align the two halves across the warps of a CTA.
-template <bool G, bool DQ, bool PW>
+// SPEC = false compiles the test of a speculative step out (callers whose second half never speculates: ipm_step_rr).
+template <bool G, bool DQ, bool PW, bool SPEC = true>
 TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const ProblemIn& in, long long b, bool warp_fresh,
                         Ipm& s, Result& res) {
   if (s.ls_active) return false;  // a rejected trial is being retried with a shorter step: nothing to redo here
@@ -1067,6 +1148,33 @@ TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const Prob
     if (first) {
       if (s.fresh) s.x0_infeasible = x0_bad;
       s.fresh = false;
+#if TTMPC_SPECULATION
+      if (SPEC && s.spec) {
+        // The step just applied was the first trial point of its line search, taken without a trial sweep (ipm_step).
+        // The statistics of this sweep ARE the trial values (J, sum ln s, theta at w + alpha*dw), so the acceptance test
+        // is made now, against the quantities of the previous iterate kept in `s`.  Rejected: the old iterate has been
+        // overwritten, so the problem starts over with classic trial sweeps -- the result is then exactly the classic
+        // algorithm's.  speculate == 2 first forgives a test that failed within the evaluation noise of phi and theta
+        // (near convergence; the classic line search would halve alpha until the noise lets it pass).
+        s.spec = false;
+        const double phi = s.cur_J - s.mu_step * s.cur_sumlog, phi_t = st.J - s.mu_step * st.sumlog;
+        const bool fin = tt_finite(st.J) && tt_finite(st.sumlog) && tt_finite(st.theta) && st.slack_sign >= 0;
+        bool acc = fin && ls_accept(s, s.cur_theta, phi, s.ls_gd, s.alpha, st.theta, phi_t);
+#if defined(TTMPC_SPEC_DEBUG) && defined(__CUDA_ARCH__)
+        if (!acc)
+          printf("REJ b=%lld iter=%d a=%.3g theta=%.3g theta_t=%.3g phi=%.17g dphi=%.3g gd=%.3g mu=%.3g fn=%d thmin=%.3g fin=%d\n", b,
+                 s.iter, s.alpha, s.cur_theta, st.theta, phi, phi_t - phi, s.ls_gd, s.mu_step, s.f_n, s.theta_min, (int)fin);
+#endif
+        if (!acc && fin && p.speculate == 2)
+          acc = (phi_t - phi <= 1e3 * kEps * fmax(1.0, fabs(phi))) && (st.theta <= fmax(s.cur_theta, 1e-2 * p.tol));
+        if (!acc) {
+          ipm_begin(p, s);
+          s.safe = true;
+          return false;  // fresh again: ipm_step skips this round, the next backward sweep re-reads the caller's arrays
+        }
+        s.ls_fail = 0;
+      }
+#endif
       const double cmin = p.n_b ? st.cmin : 0.0;
       const double s_d = fmax(kSMax, (st.lam1 + st.z1) / (double)(p.m_eq + p.n_b)) / kSMax;
       const double s_c = p.n_b ? fmax(kSMax, st.z1 / (double)p.n_b) / kSMax : 1.0;
@@ -1132,6 +1240,7 @@ TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const Prob
   return false;
 }
 
+#if !TTMPC_SPECULATION
 // Second half of an iteration: search direction and the complete filter line search (all trials in one call).
 template <bool G, bool DQ, bool PW>
 TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result& res) {
@@ -1212,6 +1321,75 @@ TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result
   s.iter++;
   return false;
 }
+#else
+// Second half of an iteration: search direction and the filter line search.
+//
+// Speculative first trial (Params::speculate, the solve kernel's default): on well-posed tracking problems the first
+// trial point alpha = a_pr of nearly every line search is accepted (host build, the 65 536 problems of the benchmark
+// batch: 388 k line searches, 0 backtracks, a_pr = 1 in 95.6 %), and the next backward sweep computes J, sum ln s and
+// theta at the updated iterate anyway.  So the step is handed over untested (`spec`) and ipm_backward makes the acceptance test from
+// its own statistics: one sweep over the stages less per iteration.  A rejection restarts the problem with classic trial
+// sweeps (`safe`), see ipm_backward.
+template <bool G, bool DQ, bool PW>
+TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result& res) {
+  if (kSpecBuild && s.fresh) return false;  // restarted by ipm_backward in this round
+  const double mu = s.mu, delta = s.cur_delta;
+  StepInfo si;
+  forward_sweep<G, DQ, PW>(p, s0, cy, mu, s.tau, si);
+
+  // filter line search (Waechter & Biegler 2006, Algorithm A)
+  const double theta = s.cur_theta;
+  const double phi = s.cur_J - mu * s.cur_sumlog;
+  double a = si.a_pr;
+  // Round-off regime (analogue of Ipopt's tiny-step rule in function values): predicted change of phi below its
+  // resolution (or below the c'lambda evaluation noise theta*||lambda||_1) and constraint violation far below tol
+  // -> theta/phi comparisons are noise; take the full step.
+  const bool roundoff_step = (theta <= 1e-2 * p.tol) &&
+                             (fabs(si.gphi_d) <= fmax(100.0 * kEps * fmax(1.0, fabs(phi)), theta * s.cur_lam1));
+  bool accepted = roundoff_step;
+  // Only steps that leave every slack at least 1 % of its value are taken untested (then a_pr = 1): a step cut by the
+  // fraction-to-boundary rule with tau = 1 - mu -> 1 can put a variable ON its bound in floating point (new slack
+  // s*mu below the spacing of w), which the classic search answers by halving alpha (measured on the GPU: all 11
+  // rejected speculative steps of the 65 536-problem benchmark batch were of this kind, alpha = 0.93 ... 0.97).
+  if (kSpecBuild && !roundoff_step && !s.safe && si.qmax <= 0.99) {
+    s.spec = true;  // tested by the next backward sweep
+    s.ls_gd = si.gphi_d;
+    accepted = true;
+  }
+  for (int bt = 0; !accepted && bt <= kMaxBacktrack; bt++, a *= kAlphaRed) {
+    Trial tr;
+    trial_sweep<G, DQ, PW>(p, s0, cy, a, tr);
+    if (!(tt_finite(tr.J) && tt_finite(tr.sumlog) && tt_finite(tr.theta))) continue;
+    if (!ls_accept(s, theta, phi, si.gphi_d, a, tr.theta, tr.J - mu * tr.sumlog)) continue;
+    accepted = true;
+    break;
+  }
+  if (!accepted) {
+    // Ipopt would enter feasibility restoration; policy: shortest trial step, cleared filter, give up after 3
+    if (++s.ls_fail >= 3) {
+      // the iterate is unchanged since the last backward sweep: report it
+      res.obj = s.cur_J;
+      res.dual_inf = s.cur_rd;
+      res.constr_viol = s.cur_cinf;
+      res.compl_inf = s.cur_cmax;
+      res.iters = s.iter;
+      res.status = s.x0_infeasible ? (int)ST_INFEASIBLE_X0 : (int)ST_LINESEARCH;
+      return true;
+    }
+    a = si.a_pr * 9.313225746154785e-10;  // kAlphaRed^kMaxBacktrack = 2^-30
+    s.f_n = 0;
+  } else if (!s.spec) {
+    s.ls_fail = 0;
+  }
+  s.alpha = a;
+  s.alpha_du = si.a_du;
+  s.mu_step = mu;
+  s.delta_step = delta;
+  s.do_update = true;
+  s.iter++;
+  return false;
+}
+#endif  // TTMPC_SPECULATION
 
 // Second half of an iteration, round-robin flavour (used by the closed-loop episode kernel, where noisy measurements
 // produce infeasible instances).  The line search is a per-lane state machine that performs AT MOST ONE trial sweep per
@@ -1368,6 +1546,9 @@ inline int build_params(const ttmpc_config* c, Params* p) {
     p->up_push[j] = hu ? push_inside(INFINITY, p->lo[j], p->up[j], hl, hu) : INFINITY;
   }
   p->generic = !(p->bl == 0xFCu && p->bu == 0xFCu);
+#if TTMPC_SPECULATION
+  p->speculate = 0;  // ttmpc_create reads TTMPC_SPECULATE=1|2
+#endif
   p->diag = (p->R2[1] == 0.0);
   for (int i = 0; i < NX; i++)
     for (int j = i + 1; j < NX; j++)

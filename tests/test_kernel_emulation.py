@@ -100,6 +100,29 @@ def test_round_robin_line_search_equals_loop_line_search():
     assert (a["iters"] > 12).any()
 
 
+def test_speculative_first_trial_walks_the_classic_iterates():
+    """ipm_step hands the first trial point of a line search to the next backward sweep untested and the test is made
+    from that sweep's statistics (a rejection restarts the problem with classic trial sweeps): results must be those of
+    the classic trial-sweep line search bit for bit -- well-posed batches, warm starts, and a far-off batch with
+    backtracking, line-search failures and infeasible x_0.  (force_generic bits 3-4 = Params::speculate; the shipped
+    default is 0, TTMPC_SPECULATE selects the others.)"""
+    cfg = tracking_preset(40); cfg.max_iter = 200
+    sc = pb.make_scenarios(cfg, 192, seed=5, sigma=pb.SIGMA_WIDE)
+    rng = np.random.default_rng(3)
+    far = sc.x_init + rng.normal(0, 1, size=sc.x_init.shape) * np.array([2, 2, 0.5, 0.6, 0.5, 3])
+    cold = emu.solve_batch(cfg, sc.x_init, sc.ref_states, sc.ref_inputs)
+    warm = pb.shift_warm_start(cold["z"], 40, reference_bug=True)
+    seen = set()
+    for x, zw in ((sc.x_init, None), (sc.x_init, warm), (far, None)):
+        a = emu.solve_batch(cfg, x, sc.ref_states, sc.ref_inputs, z_warm=zw)
+        for mode in (1, 2):
+            b = emu.solve_batch(cfg, x, sc.ref_states, sc.ref_inputs, z_warm=zw, force_generic=8 * mode)
+            for key in ("z", "u0", "obj", "iters", "status"):
+                assert np.array_equal(a[key], b[key], equal_nan=True), (mode, key)
+        seen |= set(a["status"].tolist())
+    assert {0, 3, 5} <= seen   # converged, line-search failure and infeasible-x0 instances were all exercised
+
+
 def test_per_problem_weights_match_oracle_with_scaled_matrices():
     """PW kernels (mpc_control_fuzzy.py's parametric weights): Q_w = diag(q) Q diag(q), R_w = diag(r) R diag(r)."""
     from car_trailer_mpc_b200.mpc_control_fuzzy import fuzzy_weights

@@ -10,6 +10,7 @@
 
 #include <vector>
 
+#define TTMPC_SPECULATION 1  // the host build always carries the speculative line search (selected per call)
 #include "../car_trailer_mpc_b200/csrc/ttmpc_core.cuh"
 
 using namespace ttmpc;
@@ -32,7 +33,7 @@ static void run(const Params& p, std::vector<double>& scratch, int64_t B, const 
       ipm_begin(p, st);
       if (g_round_robin_ls) {
         for (;;) {  // the episode kernel's flavour: at most one line-search trial per round
-          if (ipm_backward<G, DQ, PW>(p, s0, cy, in, b, st.fresh, st, r)) break;
+          if (ipm_backward<G, DQ, PW, false>(p, s0, cy, in, b, st.fresh, st, r)) break;
           if (ipm_step_rr<G, DQ, PW>(p, s0, cy, st, r)) break;
         }
       } else {
@@ -61,6 +62,7 @@ extern "C" int ttmpc_emu_solve_batch(const ttmpc_config* cfg, int64_t B, const d
   ProblemIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T, q_w, r_w};
   const bool g = p.generic || (force_generic & 1), dq = p.diag && !(force_generic & 2);
   g_round_robin_ls = (force_generic & 4) != 0;
+  p.speculate = (force_generic >> 3) & 3;  // 0: classic trial sweeps, 1/2: speculative first trial
   if (q_w && p.diag) {
     if (g) run<true, true, true>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
     else run<false, true, true>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
