@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
     // ---- finished lanes: scalars by the owner, the decision vector by the whole warp (coalesced z_out rows)
     if (done) {
       if (out.u0) {
-        out.u0[prob * 2 + 0] = ldr(s0, rW + 6);
-        out.u0[prob * 2 + 1] = ldr(s0, rW + 7);
+        out.u0[prob * 2 + 0] = ldr(s0 + (size_t)ipm_copy(st) * kAltStride, rW + 6);
+        out.u0[prob * 2 + 1] = ldr(s0 + (size_t)ipm_copy(st) * kAltStride, rW + 7);
       }
       if (out.obj) out.obj[prob] = res.obj;
       if (out.kkt) {
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
       for (unsigned m = fin; m; m &= m - 1) {
         const int l = __ffs(m) - 1;
         const long long pb = __shfl_sync(kFull, prob, l);
-        const double* sl = s_warp + l;
+        const double* sl = s_warp + l + (kSpecBuild ? (size_t)__shfl_sync(kFull, ipm_copy(st), l) * kAltStride : 0);
         double* zo = out.z + pb * nz;
         for (int e0 = (int)lane; e0 < nz; e0 += 32 * kCopyUnroll) {
           double v[kCopyUnroll];
@@ -722,7 +722,7 @@ int ttmpc_create(const ttmpc_config* cfg, int device, ttmpc_handle** out) {
 #if TTMPC_SPECULATION  // experiment builds: speculative first line-search trial in ttmpc_solve_kernel (0, 1, 2)
   if (const char* e = getenv("TTMPC_SPECULATE")) {
     const int v = atoi(e);
-    if (v >= 0 && v <= 2) p.speculate = v;
+    if (v >= 0 && v <= 3) p.speculate = v;
   }
 #endif
   h->p = p;

@@ -74,6 +74,7 @@ enum : int { ST_CONVERGED = 0, ST_ACCEPTABLE = 1, ST_MAX_ITER = 2, ST_LINESEARCH
 
 // ---- scratch layout: rows of one stage ----
 constexpr int kBank = TTMPC_BANK;  // slots per bank = element stride between rows
+#if !TTMPC_SPECULATION
 constexpr int rW = 0;              // w_k = (x_k, u_k)                       8
 constexpr int rDW = 8;             // search direction                       8
 constexpr int rREF = 16;           // reference (xbar_k, ubar_k)             8
@@ -81,7 +82,16 @@ constexpr int rLAM = 24;           // multiplier of c_k (defect into x_k)    6
 constexpr int rZL = 30;            // lower-bound multipliers (x 0..5, u 6..7) 8
 constexpr int rZU = 38;            // upper-bound multipliers                8
 constexpr int rKF = 46;            // K (2x6), kff0 (2), kff1 (2)            16
+constexpr int kAlt = 0;
 constexpr int kRows = 62;
+#else
+// experiment layout: the iterate (W, LAM, ZL, ZU) exists in two copies kAlt rows apart; a speculative step reads one
+// and writes the other, so a rejected step leaves the previous iterate intact (Ipm::cur selects the current copy)
+constexpr int rW = 0, rLAM = 8, rZL = 14, rZU = 22, rDW = 30, rREF = 38, rKF = 46;
+constexpr int kAlt = 62;
+constexpr int kRows = 92;
+#endif
+constexpr size_t kAltStride = (size_t)kAlt * kBank;  // element offset of the second copy of the iterate rows
 constexpr size_t kStageStride = (size_t)kRows * kBank;
 
 struct Params {
@@ -415,7 +425,7 @@ struct Stats {
 template <bool G, bool DQ, bool PW>
 TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const ProblemIn& in, long long b, bool fresh,
                           bool warp_fresh, bool& x0_bad, bool do_update, double alpha, double alpha_du, double mu_step,
-                          double delta_step, double delta, Stats& st) {
+                          double delta_step, double delta, Stats& st, int cur = 0, bool to_alt = false) {
   const int N = p.N;
   const double dt = p.dt;
   bool ok = true;
@@ -432,6 +442,9 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
 
   for (int k = N; k >= 0; k--) {
     double* ps = s0 + (size_t)k * kStageStride;
+    // iterate rows (W, LAM, ZL, ZU): copy read / copy written by this sweep (the same unless the step is speculative)
+    const double* pc = kSpecBuild ? ps + (size_t)cur * kAltStride : ps;
+    double* pw = kSpecBuild ? ps + (size_t)(to_alt ? 1 - cur : cur) * kAltStride : ps;
     const bool has_x = (k >= 1);  // x_0 is data
     const bool has_u = (k < N);
     double w[NW], ref[NW], dw[NW], zl[NW], zu[NW], lam[NX];
@@ -439,14 +452,14 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
     for (int j = 0; j < NW; j++) {
       const bool on = (j < NX) || has_u;
       const bool var = (j < NX) ? has_x : has_u;
-      w[j] = (on && !fresh) ? ldr(ps, rW + j) : 0.0;
+      w[j] = (on && !fresh) ? ldr(pc, rW + j) : 0.0;
       ref[j] = (on && !fresh) ? ldr(ps, rREF + j) : 0.0;
       dw[j] = (do_update && var) ? ldr(ps, rDW + j) : 0.0;
-      zl[j] = (var && !fresh && has_lo<G>(p, j)) ? ldr(ps, rZL + j) : 0.0;
-      zu[j] = (var && !fresh && has_up<G>(p, j)) ? ldr(ps, rZU + j) : 0.0;
+      zl[j] = (var && !fresh && has_lo<G>(p, j)) ? ldr(pc, rZL + j) : 0.0;
+      zu[j] = (var && !fresh && has_up<G>(p, j)) ? ldr(pc, rZU + j) : 0.0;
     }
     TT_UNROLL
-    for (int j = 0; j < NX; j++) lam[j] = (has_x && !fresh) ? ldr(ps, rLAM + j) : 0.0;
+    for (int j = 0; j < NX; j++) lam[j] = (has_x && !fresh) ? ldr(pc, rLAM + j) : 0.0;
     if (fresh) {
       // entering problem: reference window and starting point from the caller's arrays (mpc_control.py:58-65 cold
       // start or the caller's warm start), pushed into the interior of the relaxed box; z_L = z_U = 1, lambda = 0
@@ -484,9 +497,16 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
     const bool wb = do_update || fresh;  // this lane (re)writes its iterate in this sweep
     if (has_x) {  // request stage k-1 now
       const double* pn = ps - kStageStride;
-      prefetch_rows(pn, rW, do_update ? 2 * NW : NW);  // W (and DW, adjacent rows)
-      prefetch_rows(pn, rREF, NW + NX);                // REF and LAM (adjacent rows)
-      prefetch_rows(pn, rZL + (G ? 0 : 2), G ? 2 * NW : 14);  // ZL, ZU (default pattern: rows 2..7 of each)
+      if (!kSpecBuild) {
+        prefetch_rows(pn, rW, do_update ? 2 * NW : NW);  // W (and DW, adjacent rows)
+        prefetch_rows(pn, rREF, NW + NX);                // REF and LAM (adjacent rows)
+        prefetch_rows(pn, rZL + (G ? 0 : 2), G ? 2 * NW : 14);  // ZL, ZU (default pattern: rows 2..7 of each)
+      } else {
+        const double* pnc = pc - kStageStride;
+        prefetch_rows(pnc, rW, NW + NX);  // W and LAM (adjacent rows of the current copy)
+        prefetch_rows(pnc, rZL + (G ? 0 : 2), G ? 2 * NW : 14);
+        prefetch_rows(pn, do_update ? rDW : rREF, do_update ? 2 * NW : NW);  // (DW and) REF
+      }
     }
 
     // ---------------------------------------------------------------- (i) apply the previous step
@@ -563,11 +583,11 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
       for (int j = 0; j < NW; j++) {
         const bool on = (j < NX) || has_u;
         const bool var = (j < NX) ? has_x : has_u;
-        if (var || (fresh && on)) str(ps, rW + j, w[j]);
+        if (var || ((fresh || (kSpecBuild && to_alt)) && on)) str(pw, rW + j, w[j]);
       }
       if (has_x) {
         TT_UNROLL
-        for (int j = 0; j < NX; j++) str(ps, rLAM + j, lam[j]);
+        for (int j = 0; j < NX; j++) str(pw, rLAM + j, lam[j]);
       }
     }
     if (warp_fresh) {  // reference rows: fresh lanes bring new ones, the others re-store theirs (full-row writes)
@@ -604,7 +624,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
         if (var && has_lo<G>(p, j)) {
           const double sl = w[j] - p.lo[j], rl = tt_rcp(sl);
           if (do_update) zl[j] = tt_max(tt_min(zl[j], kmu_hi * rl), kmu_lo * rl);  // kappa_sigma safeguard, W&B eq. (16)
-          if (wb) str(ps, rZL + j, zl[j]);
+          if (wb) str(pw, rZL + j, zl[j]);
           sg += zl[j] * rl;
           gg -= rl;
           prod *= sl;
@@ -617,7 +637,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
         if (var && has_up<G>(p, j)) {
           const double su = p.up[j] - w[j], ru = tt_rcp(su);
           if (do_update) zu[j] = tt_max(tt_min(zu[j], kmu_hi * ru), kmu_lo * ru);
-          if (wb) str(ps, rZU + j, zu[j]);
+          if (wb) str(pw, rZU + j, zu[j]);
           sg += zu[j] * ru;
           gg += ru;
           prod *= su;
@@ -833,27 +853,28 @@ struct FwdIn {
   double u[NU], ref[NW], zl[NW], zu[NW], kf[16], xnext[NX];
 };
 template <bool G>
-TT_HD void fwd_load(const Params& p, const double* s0, int k, FwdIn& f) {
+TT_HD void fwd_load(const Params& p, const double* s0, int k, FwdIn& f, int cur = 0) {
   const int N = p.N;
   const double* ps = s0 + (size_t)k * kStageStride;
+  const double* pc = kSpecBuild ? ps + (size_t)cur * kAltStride : ps;  // current copy of the iterate rows
   const bool has_x = (k >= 1), has_u = (k < N);
-  f.u[0] = has_u ? ldr(ps, rW + 6) : 0.0;
-  f.u[1] = has_u ? ldr(ps, rW + 7) : 0.0;
+  f.u[0] = has_u ? ldr(pc, rW + 6) : 0.0;
+  f.u[1] = has_u ? ldr(pc, rW + 7) : 0.0;
   TT_UNROLL
   for (int j = 0; j < NW; j++) {
     const bool var = (j < NX) ? has_x : has_u;
     f.ref[j] = ((j < NX) || has_u) ? ldr(ps, rREF + j) : 0.0;
-    f.zl[j] = (var && has_lo<G>(p, j)) ? ldr(ps, rZL + j) : 0.0;
-    f.zu[j] = (var && has_up<G>(p, j)) ? ldr(ps, rZU + j) : 0.0;
+    f.zl[j] = (var && has_lo<G>(p, j)) ? ldr(pc, rZL + j) : 0.0;
+    f.zu[j] = (var && has_up<G>(p, j)) ? ldr(pc, rZU + j) : 0.0;
   }
   TT_UNROLL
   for (int j = 0; j < 16; j++) f.kf[j] = (has_u && (has_x || j >= 12)) ? ldr(ps, rKF + j) : 0.0;
   TT_UNROLL
-  for (int j = 0; j < NX; j++) f.xnext[j] = has_u ? ldr(ps + kStageStride, rW + j) : 0.0;
+  for (int j = 0; j < NX; j++) f.xnext[j] = has_u ? ldr(pc + kStageStride, rW + j) : 0.0;
 }
 
 template <bool G, bool DQ, bool PW>
-TT_HD void forward_sweep(const Params& p, double* s0, const Carry& cy, double mu, double tau, StepInfo& si) {
+TT_HD void forward_sweep(const Params& p, double* s0, const Carry& cy, double mu, double tau, StepInfo& si, int copy = 0) {
   const int N = p.N;
   const double dt = p.dt;
   double dx[NX] = {0, 0, 0, 0, 0, 0};
@@ -861,18 +882,19 @@ TT_HD void forward_sweep(const Params& p, double* s0, const Carry& cy, double mu
   // fraction-to-boundary: alpha = min(1, tau / max_i(-ds_i/s_i)); the dual maximum is kept as a ratio bn/bd
   double qmax = 0.0, bn = 0.0, bd = 1.0, gd = 0.0;
   TT_UNROLL
-  for (int j = 0; j < NX; j++) x[j] = ldr(s0, rW + j);
+  for (int j = 0; j < NX; j++) x[j] = ldr(kSpecBuild ? s0 + (size_t)copy * kAltStride : s0, rW + j);
   for (int k = 0; k <= N; k++) {
     double* ps = s0 + (size_t)k * kStageStride;
     const bool has_x = (k >= 1), has_u = (k < N);
     FwdIn cur;  // all loads of the stage first (one batch in flight), then the arithmetic
-    fwd_load<G>(p, s0, k, cur);
+    fwd_load<G>(p, s0, k, cur, copy);
     if (has_u) {  // request stage k+1 (and the states of k+2, read one stage ahead)
       const double* pn = ps + kStageStride;
-      prefetch_rows(pn, rW + NX, NU);
-      prefetch_rows(pn + kStageStride, rW, NX);
+      const double* pnc = kSpecBuild ? pn + (size_t)copy * kAltStride : pn;  // current copy of the iterate rows
+      prefetch_rows(pnc, rW + NX, NU);
+      prefetch_rows(pnc + kStageStride, rW, NX);
       prefetch_rows(pn, rREF, NW);
-      prefetch_rows(pn, rZL + (G ? 0 : 2), G ? 2 * NW : 14);
+      prefetch_rows(pnc, rZL + (G ? 0 : 2), G ? 2 * NW : 14);
       prefetch_rows(pn, rKF, 16);
     }
     double w[NW], d[NW];
@@ -970,21 +992,22 @@ struct Trial {
 struct TrialIn {
   double w[NW], dw[NW], ref[NW];
 };
-TT_HD void trial_load(const Params& p, const double* s0, int k, TrialIn& t) {
+TT_HD void trial_load(const Params& p, const double* s0, int k, TrialIn& t, int copy = 0) {
   const double* ps = s0 + (size_t)k * kStageStride;
+  const double* pc = kSpecBuild ? ps + (size_t)copy * kAltStride : ps;  // current copy of the iterate rows
   const bool has_x = (k >= 1), has_u = (k < p.N);
   TT_UNROLL
   for (int j = 0; j < NW; j++) {
     const bool on = (j < NX) ? true : has_u;
     const bool var = (j < NX) ? has_x : has_u;
-    t.w[j] = on ? ldr(ps, rW + j) : 0.0;
+    t.w[j] = on ? ldr(pc, rW + j) : 0.0;
     t.dw[j] = var ? ldr(ps, rDW + j) : 0.0;
     t.ref[j] = on ? ldr(ps, rREF + j) : 0.0;
   }
 }
 
 template <bool G, bool DQ, bool PW>
-TT_HD void trial_sweep(const Params& p, const double* s0, const Carry& cy, double alpha, Trial& tr) {
+TT_HD void trial_sweep(const Params& p, const double* s0, const Carry& cy, double alpha, Trial& tr, int copy = 0) {
   const int N = p.N;
   const double dt = p.dt;
   double J = 0.0, sl_ = 0.0, th = 0.0, smin = INFINITY;
@@ -992,8 +1015,15 @@ TT_HD void trial_sweep(const Params& p, const double* s0, const Carry& cy, doubl
   for (int k = N; k >= 0; k--) {
     const bool has_x = (k >= 1), has_u = (k < N);
     TrialIn cur;
-    trial_load(p, s0, k, cur);
-    if (has_x) prefetch_rows(s0 + (size_t)(k - 1) * kStageStride, rW, 3 * NW);  // W, DW, REF of stage k-1
+    trial_load(p, s0, k, cur, copy);
+    if (has_x) {
+      if (!kSpecBuild) {
+        prefetch_rows(s0 + (size_t)(k - 1) * kStageStride, rW, 3 * NW);  // W, DW, REF of stage k-1
+      } else {
+        prefetch_rows(s0 + (size_t)(k - 1) * kStageStride + (size_t)copy * kAltStride, rW, NW);
+        prefetch_rows(s0 + (size_t)(k - 1) * kStageStride, rDW, 2 * NW);  // DW, REF
+      }
+    }
     double w[NW];
     TT_UNROLL
     for (int j = 0; j < NW; j++) w[j] = cur.w[j] + alpha * cur.dw[j];
@@ -1063,8 +1093,22 @@ struct Ipm {
   // test yet; `safe` = this problem runs the classic trial sweeps (speculation off, or it was restarted after a rejection)
 #if TTMPC_SPECULATION
   bool spec, safe;
+  // speculate == 3 (ping-pong copies of the iterate rows): `cur` = the copy holding the current iterate; `redo` = the
+  // speculative step was rejected, ipm_step resumes the classic line search of the same direction at alpha/2
+  int cur;
+  bool redo;
 #endif
 };
+
+// copy of the iterate rows that holds the lane's current iterate (0 unless a TTMPC_SPECULATION build runs mode 3)
+TT_HD int ipm_copy(const Ipm& s) {
+#if TTMPC_SPECULATION
+  return s.cur;
+#else
+  (void)s;
+  return 0;
+#endif
+}
 
 TT_HD bool tt_finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
 
@@ -1086,6 +1130,8 @@ TT_HD void ipm_begin(const Params& p, Ipm& s) {
 #if TTMPC_SPECULATION
   s.spec = false;
   s.safe = (p.speculate == 0);
+  s.cur = 0;
+  s.redo = false;
 #endif
 }
 
@@ -1143,8 +1189,15 @@ TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const Prob
   for (int attempt = 0; attempt <= 40; attempt++) {
     const bool first = (attempt == 0);
     bool x0_bad = false;
+#if TTMPC_SPECULATION
+    // mode 3: a speculative step is written to the other copy of the iterate rows
+    ok = backward_sweep<G, DQ, PW>(p, s0, cy, in, b, first && s.fresh, first && warp_fresh, x0_bad, first && s.do_update, s.alpha,
+                               s.alpha_du, first ? s.mu_step : mu, s.delta_step, delta, first ? st : st2, s.cur,
+                               SPEC && first && s.spec && p.speculate == 3);
+#else
     ok = backward_sweep<G, DQ, PW>(p, s0, cy, in, b, first && s.fresh, first && warp_fresh, x0_bad, first && s.do_update, s.alpha,
                                s.alpha_du, first ? s.mu_step : mu, s.delta_step, delta, first ? st : st2);
+#endif
     if (first) {
       if (s.fresh) s.x0_infeasible = x0_bad;
       s.fresh = false;
@@ -1167,11 +1220,18 @@ TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const Prob
 #endif
         if (!acc && fin && p.speculate == 2)
           acc = (phi_t - phi <= 1e3 * kEps * fmax(1.0, fabs(phi))) && (st.theta <= fmax(s.cur_theta, 1e-2 * p.tol));
+        if (!acc && p.speculate == 3) {
+          // the previous iterate is intact in copy `cur`: ipm_step resumes the classic search of this direction at alpha/2
+          s.safe = true;
+          s.redo = true;
+          return false;
+        }
         if (!acc) {
           ipm_begin(p, s);
           s.safe = true;
           return false;  // fresh again: ipm_step skips this round, the next backward sweep re-reads the caller's arrays
         }
+        if (p.speculate == 3) s.cur ^= 1;  // the copy written by this sweep is the iterate now
         s.ls_fail = 0;
       }
 #endif
@@ -1330,35 +1390,50 @@ TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result
 // theta at the updated iterate anyway.  So the step is handed over untested (`spec`) and ipm_backward makes the acceptance test from
 // its own statistics: one sweep over the stages less per iteration.  A rejection restarts the problem with classic trial
 // sweeps (`safe`), see ipm_backward.
+// Modes (Params::speculate): 1 = speculate on interior full steps only (max(-ds/s) <= 0.99), a rejection restarts the
+// problem; 2 = 1 + forgiving tests that fail within evaluation noise; 3 = every step is speculated and written to the
+// other copy of the iterate rows, a rejection leaves the previous iterate intact and this function resumes the classic
+// search of the same direction at alpha/2 (`redo`).
 template <bool G, bool DQ, bool PW>
 TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result& res) {
-  if (kSpecBuild && s.fresh) return false;  // restarted by ipm_backward in this round
+  if (s.fresh) return false;  // restarted by ipm_backward in this round
   const double mu = s.mu, delta = s.cur_delta;
+  const bool redo = s.redo;
+  s.redo = false;
   StepInfo si;
-  forward_sweep<G, DQ, PW>(p, s0, cy, mu, s.tau, si);
+  if (!redo) {
+    forward_sweep<G, DQ, PW>(p, s0, cy, mu, s.tau, si, s.cur);
+    s.ls_apr = si.a_pr;
+    s.ls_adu = si.a_du;
+    s.ls_gd = si.gphi_d;
+  } else {  // the direction is still in the DW rows; its step limits were kept
+    si.a_pr = s.ls_apr;
+    si.a_du = s.ls_adu;
+    si.gphi_d = s.ls_gd;
+    si.qmax = 0.0;
+  }
 
   // filter line search (Waechter & Biegler 2006, Algorithm A)
   const double theta = s.cur_theta;
   const double phi = s.cur_J - mu * s.cur_sumlog;
-  double a = si.a_pr;
+  double a = redo ? si.a_pr * kAlphaRed : si.a_pr;
   // Round-off regime (analogue of Ipopt's tiny-step rule in function values): predicted change of phi below its
   // resolution (or below the c'lambda evaluation noise theta*||lambda||_1) and constraint violation far below tol
   // -> theta/phi comparisons are noise; take the full step.
   const bool roundoff_step = (theta <= 1e-2 * p.tol) &&
                              (fabs(si.gphi_d) <= fmax(100.0 * kEps * fmax(1.0, fabs(phi)), theta * s.cur_lam1));
   bool accepted = roundoff_step;
-  // Only steps that leave every slack at least 1 % of its value are taken untested (then a_pr = 1): a step cut by the
-  // fraction-to-boundary rule with tau = 1 - mu -> 1 can put a variable ON its bound in floating point (new slack
-  // s*mu below the spacing of w), which the classic search answers by halving alpha (measured on the GPU: all 11
+  // Modes 1, 2: only steps that leave every slack at least 1 % of its value are taken untested (then a_pr = 1): a step
+  // cut by the fraction-to-boundary rule with tau = 1 - mu -> 1 can put a variable ON its bound in floating point (new
+  // slack s*mu below the spacing of w), which the classic search answers by halving alpha (measured on the GPU: all 11
   // rejected speculative steps of the 65 536-problem benchmark batch were of this kind, alpha = 0.93 ... 0.97).
-  if (kSpecBuild && !roundoff_step && !s.safe && si.qmax <= 0.99) {
+  if (!roundoff_step && !s.safe && (p.speculate == 3 || si.qmax <= 0.99)) {
     s.spec = true;  // tested by the next backward sweep
-    s.ls_gd = si.gphi_d;
     accepted = true;
   }
-  for (int bt = 0; !accepted && bt <= kMaxBacktrack; bt++, a *= kAlphaRed) {
+  for (int bt = redo ? 1 : 0; !accepted && bt <= kMaxBacktrack; bt++, a *= kAlphaRed) {
     Trial tr;
-    trial_sweep<G, DQ, PW>(p, s0, cy, a, tr);
+    trial_sweep<G, DQ, PW>(p, s0, cy, a, tr, s.cur);
     if (!(tt_finite(tr.J) && tt_finite(tr.sumlog) && tt_finite(tr.theta))) continue;
     if (!ls_accept(s, theta, phi, si.gphi_d, a, tr.theta, tr.J - mu * tr.sumlog)) continue;
     accepted = true;
@@ -1372,7 +1447,7 @@ TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result
       res.dual_inf = s.cur_rd;
       res.constr_viol = s.cur_cinf;
       res.compl_inf = s.cur_cmax;
-      res.iters = s.iter;
+      res.iters = redo ? s.iter - 1 : s.iter;  // the rejected speculative step had been counted
       res.status = s.x0_infeasible ? (int)ST_INFEASIBLE_X0 : (int)ST_LINESEARCH;
       return true;
     }
@@ -1386,7 +1461,7 @@ TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result
   s.mu_step = mu;
   s.delta_step = delta;
   s.do_update = true;
-  s.iter++;
+  if (!redo) s.iter++;
   return false;
 }
 #endif  // TTMPC_SPECULATION
@@ -1498,9 +1573,9 @@ TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, const Pro
 }
 
 // slot -> z_out in the reference's decision-vector layout (trajectory_planning.py:38-60): z[8k+j] = w_k[j]
-TT_HD void unpack_slot(const Params& p, const double* s0, double* z) {
+TT_HD void unpack_slot(const Params& p, const double* s0, double* z, int copy = 0) {
   const int nz = 8 * p.N + 6;
-  for (int e = 0; e < nz; e++) z[e] = ldr(s0 + (size_t)(e >> 3) * kStageStride, rW + (e & 7));
+  for (int e = 0; e < nz; e++) z[e] = ldr(s0 + (size_t)(e >> 3) * kStageStride + (size_t)copy * kAltStride, rW + (e & 7));
 }
 
 // ------------------------------------------------------------------------------------------------

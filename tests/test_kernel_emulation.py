@@ -102,7 +102,8 @@ def test_round_robin_line_search_equals_loop_line_search():
 
 def test_speculative_first_trial_walks_the_classic_iterates():
     """ipm_step hands the first trial point of a line search to the next backward sweep untested and the test is made
-    from that sweep's statistics (a rejection restarts the problem with classic trial sweeps): results must be those of
+    from that sweep's statistics (a rejection restarts the problem with classic trial sweeps -- modes 1, 2 -- or resumes
+    the classic search from the intact previous iterate -- mode 3, ping-pong copies): results must be those of
     the classic trial-sweep line search bit for bit -- well-posed batches, warm starts, and a far-off batch with
     backtracking, line-search failures and infeasible x_0.  (force_generic bits 3-4 = Params::speculate; the shipped
     default is 0, TTMPC_SPECULATE selects the others.)"""
@@ -115,7 +116,7 @@ def test_speculative_first_trial_walks_the_classic_iterates():
     seen = set()
     for x, zw in ((sc.x_init, None), (sc.x_init, warm), (far, None)):
         a = emu.solve_batch(cfg, x, sc.ref_states, sc.ref_inputs, z_warm=zw)
-        for mode in (1, 2):
+        for mode in (1, 2, 3):   # 3: every step speculated into the second copy of the iterate rows, rejections resumed
             b = emu.solve_batch(cfg, x, sc.ref_states, sc.ref_inputs, z_warm=zw, force_generic=8 * mode)
             for key in ("z", "u0", "obj", "iters", "status"):
                 assert np.array_equal(a[key], b[key], equal_nan=True), (mode, key)

@@ -11,7 +11,7 @@ mkdir -p gpurun_out; : > $O
 for B in 65536 4096; do
   echo "== shipped library (classic trial sweeps), B=$B" >> $O
   timeout 60 python tools/quick_bench.py $B 40 5 2>&1 | tail -1 >> $O
-  for mode in 0 1 2; do
+  for mode in 0 1 2 3; do
     echo "== experiment library, TTMPC_SPECULATE=$mode, B=$B" >> $O
     TTMPC_LIB=$SPEC TTMPC_SPECULATE=$mode TTMPC_DEBUG_RESTARTS=1 timeout 60 python tools/quick_bench.py $B 40 5 2>&1 | grep -v "^fp64" | uniq | tail -3 >> $O
   done

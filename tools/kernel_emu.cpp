@@ -40,8 +40,9 @@ static void run(const Params& p, std::vector<double>& scratch, int64_t B, const 
         while (!ipm_iteration<G, DQ, PW>(p, s0, cy, in, b, st, r)) {
         }
       }
-      if (z_out) unpack_slot(p, s0, z_out + b * nz);
-      if (u0_out) { u0_out[b * 2] = ldr(s0, rW + 6); u0_out[b * 2 + 1] = ldr(s0, rW + 7); }
+      const double* sc = s0 + (size_t)ipm_copy(st) * kAltStride;  // current copy of the iterate rows
+      if (z_out) unpack_slot(p, s0, z_out + b * nz, ipm_copy(st));
+      if (u0_out) { u0_out[b * 2] = ldr(sc, rW + 6); u0_out[b * 2 + 1] = ldr(sc, rW + 7); }
       if (obj_out) obj_out[b] = r.obj;
       if (kkt_out) { kkt_out[b * 3] = r.dual_inf; kkt_out[b * 3 + 1] = r.constr_viol; kkt_out[b * 3 + 2] = r.compl_inf; }
       if (iters_out) iters_out[b] = r.iters;
