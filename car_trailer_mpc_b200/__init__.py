@@ -42,6 +42,10 @@ def __getattr__(name):  # lazy: importing the package must not require the CUDA 
         from .mpc_control_obs import MPCTrackingControlObs
 
         return MPCTrackingControlObs
+    if name == "SwitchingController":
+        from .mpc_control_switch import SwitchingController
+
+        return SwitchingController
     if name == "TruckTrailerModel":
         from .truck_trailer_model import TruckTrailerModel
 
