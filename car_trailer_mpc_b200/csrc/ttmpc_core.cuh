@@ -83,7 +83,12 @@ constexpr int rZL = 30;            // lower-bound multipliers (x 0..5, u 6..7) 8
 constexpr int rZU = 38;            // upper-bound multipliers                8
 constexpr int rKF = 46;            // K (2x6), kff0 (2), kff1 (2)            16
 constexpr int kAlt = 0;
+#ifdef TTMPC_STAGE_ROWS  // experiment builds: padded stage stride (e.g. 64 rows = 16 KB per stage and warp), DESIGN.md section 8
+constexpr int kRows = TTMPC_STAGE_ROWS;
+static_assert(kRows >= 62, "a stage needs 62 rows");
+#else
 constexpr int kRows = 62;
+#endif
 #else
 // experiment layout: the iterate (W, LAM, ZL, ZU) exists in two copies kAlt rows apart; a speculative step reads one
 // and writes the other, so a rejected step leaves the previous iterate intact (Ipm::cur selects the current copy)
