@@ -105,8 +105,9 @@ def test_speculative_first_trial_walks_the_classic_iterates():
     from that sweep's statistics (a rejection restarts the problem with classic trial sweeps -- modes 1, 2 -- or resumes
     the classic search from the intact previous iterate -- mode 3, ping-pong copies): results must be those of
     the classic trial-sweep line search bit for bit -- well-posed batches, warm starts, and a far-off batch with
-    backtracking, line-search failures and infeasible x_0.  (force_generic bits 3-4 = Params::speculate; the shipped
-    default is 0, TTMPC_SPECULATE selects the others.)"""
+    backtracking, line-search failures and infeasible x_0.  The classic side is the core as the shipped library compiles
+    it; the speculative side is the experiment configuration -DTTMPC_SPECULATION=1 (force_generic bits 3-4 =
+    Params::speculate, a second host library built by tools/emu.py)."""
     cfg = tracking_preset(40); cfg.max_iter = 200
     sc = pb.make_scenarios(cfg, 192, seed=5, sigma=pb.SIGMA_WIDE)
     rng = np.random.default_rng(3)
@@ -152,8 +153,11 @@ def test_core_under_address_sanitizer(tmp_path):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = str(tmp_path / "emu_asan")
-    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-DTTMPC_BANK=32", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
-                           "-o", exe, os.path.join(root, "tools", "emu_asan_main.cpp"), os.path.join(root, "tools", "kernel_emu.cpp"), "-lm"])
+    exe_spec = str(tmp_path / "emu_asan_spec")   # experiment configuration (two-copy scratch layout, speculative modes)
+    for out_, extra in ((exe, []), (exe_spec, ["-DTTMPC_SPECULATION=1"])):
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-DTTMPC_BANK=32", *extra, "-fsanitize=address,undefined",
+                               "-fno-sanitize-recover=all", "-o", out_, os.path.join(root, "tools", "emu_asan_main.cpp"),
+                               os.path.join(root, "tools", "kernel_emu.cpp"), "-lm"])
     cfg = tracking_preset(12)
     B = 35
     sc = pb.make_scenarios(cfg, B, seed=41, sigma=pb.SIGMA_WIDE)
@@ -162,6 +166,7 @@ def test_core_under_address_sanitizer(tmp_path):
     rng = np.random.default_rng(2)
     for name, arr in (("x", sc.x_init), ("xs", sc.ref_states), ("us", sc.ref_inputs), ("qw", 1 + rng.random((B, 6))), ("rw", 1 + rng.random((B, 2)))):
         np.ascontiguousarray(arr, dtype=np.float64).tofile(tmp_path / f"{name}.bin")
-    out = subprocess.run([exe, str(tmp_path), "12", str(B)], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr[-2000:]
-    assert "checksum" in out.stdout and "nan" not in out.stdout.lower()
+    for cmd in ([exe, str(tmp_path), "12", str(B)], [exe_spec, str(tmp_path), "12", str(B), "spec"]):
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert "checksum" in out.stdout and "nan" not in out.stdout.lower()

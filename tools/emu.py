@@ -10,15 +10,32 @@ _SO = os.path.join(_HERE, "libttmpc_emu.so")
 _lib = None
 
 
+_SO_SPEC = os.path.join(_HERE, "libttmpc_emu_spec.so")
+_lib_spec = None
+
+
+def _build(so, extra):
+    src = os.path.join(_HERE, "kernel_emu.cpp")
+    core = os.path.join(_HERE, "..", "car_trailer_mpc_b200", "csrc", "ttmpc_core.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-DTTMPC_BANK=64", *extra, "-fPIC", "-shared", "-o", so, src, "-lm"])
+    return ctypes.CDLL(so)
+
+
 def lib():
+    """The core exactly as the shipped library compiles it (no experiment macros)."""
     global _lib
     if _lib is None:
-        src = os.path.join(_HERE, "kernel_emu.cpp")
-        core = os.path.join(_HERE, "..", "car_trailer_mpc_b200", "csrc", "ttmpc_core.cuh")
-        if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(core)):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-DTTMPC_BANK=64", "-fPIC", "-shared", "-o", _SO, src, "-lm"])
-        _lib = ctypes.CDLL(_SO)
+        _lib = _build(_SO, [])
     return _lib
+
+
+def lib_spec():
+    """The experiment configuration -DTTMPC_SPECULATION=1 (speculative first line-search trial)."""
+    global _lib_spec
+    if _lib_spec is None:
+        _lib_spec = _build(_SO_SPEC, ["-DTTMPC_SPECULATION=1"])
+    return _lib_spec
 
 
 def solve_batch(cfg, x_init, ref_states=None, ref_inputs=None, z_warm=None, k_index=None, traj_states=None,
@@ -43,7 +60,8 @@ def solve_batch(cfg, x_init, ref_states=None, ref_inputs=None, z_warm=None, k_in
     it = np.empty(B, np.int32); st = np.empty(B, np.int32)
     dp = ctypes.POINTER(ctypes.c_double); ip = ctypes.POINTER(ctypes.c_int32)
     P = lambda a, t=dp: None if a is None else a.ctypes.data_as(t)
-    rc = lib().ttmpc_emu_solve_batch(ctypes.byref(cfg), ctypes.c_int64(B), P(x), P(xs), P(us), P(ki, ip), P(ts), P(tu),
+    L = lib_spec() if (int(force_generic) >> 3) & 3 else lib()   # bits 3-4: Params::speculate of the experiment build
+    rc = L.ttmpc_emu_solve_batch(ctypes.byref(cfg), ctypes.c_int64(B), P(x), P(xs), P(us), P(ki, ip), P(ts), P(tu),
                                      ctypes.c_int32(T), P(zw), P(z), P(u0), P(obj), P(kkt), P(it, ip), P(st, ip),
                                      ctypes.c_int(int(force_generic)), P(qw), P(rw))
     if rc:

@@ -35,7 +35,11 @@ int main(int argc, char** argv) {
   std::vector<double> z(B * nz), u0(B * 2), obj(B), kkt(B * 3);
   std::vector<int32_t> it(B), st(B);
   double sum = 0;
-  for (int flags = 0; flags < 8; flags++) {  // generic/specialised bounds x dense/diagonal weights x line-search flavour
+  // generic/specialised bounds x dense/diagonal weights x line-search flavour; with a 5th argument ("spec", experiment
+  // build -DTTMPC_SPECULATION=1) also the three speculative modes (flags 8, 16, 24: the two-copy scratch layout)
+  const int top = argc > 4 ? 11 : 8;
+  for (int i = 0; i < top; i++) {
+    const int flags = i < 8 ? i : 8 * (i - 7);
     int rc = ttmpc_emu_solve_batch(&cfg, B, x.data(), xs.data(), us.data(), nullptr, nullptr, nullptr, 0, nullptr, z.data(), u0.data(),
                                    obj.data(), kkt.data(), it.data(), st.data(), flags, nullptr, nullptr);
     if (rc) return 3;

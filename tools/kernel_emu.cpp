@@ -10,7 +10,6 @@
 
 #include <vector>
 
-#define TTMPC_SPECULATION 1  // the host build always carries the speculative line search (selected per call)
 #include "../car_trailer_mpc_b200/csrc/ttmpc_core.cuh"
 
 using namespace ttmpc;
@@ -63,7 +62,11 @@ extern "C" int ttmpc_emu_solve_batch(const ttmpc_config* cfg, int64_t B, const d
   ProblemIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T, q_w, r_w};
   const bool g = p.generic || (force_generic & 1), dq = p.diag && !(force_generic & 2);
   g_round_robin_ls = (force_generic & 4) != 0;
-  p.speculate = (force_generic >> 3) & 3;  // 0: classic trial sweeps, 1/2: speculative first trial
+#if TTMPC_SPECULATION  // experiment build of the core (tools/emu.py builds it as a second library)
+  p.speculate = (force_generic >> 3) & 3;  // 0: classic trial sweeps, 1..3: speculative first trial
+#else
+  if ((force_generic >> 3) & 3) return TTMPC_E_INVAL;  // this library is the shipped configuration
+#endif
   if (q_w && p.diag) {
     if (g) run<true, true, true>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
     else run<false, true, true>(p, scratch, B, in, z_out, u0_out, obj_out, kkt_out, iters_out, status_out);
