@@ -67,6 +67,8 @@ def load():
     L.ttmpc_episode_batch.argtypes = [H, ctypes.c_int64, c_dp, c_dp, c_dp, c_dp, ctypes.c_int32, c_dp, ctypes.c_int32, c_dp,
                                       ctypes.c_int32, ctypes.c_uint64, c_dp, c_dp, ctypes.c_void_p]
     L.ttmpc_episode_batch.restype = ctypes.c_int
+    L.ttmpc_last_solve_lanes.argtypes = [H]
+    L.ttmpc_last_solve_lanes.restype = ctypes.c_int32
     L.ttmpc_launch_count.argtypes = [H]
     L.ttmpc_launch_count.restype = ctypes.c_int64
     L.ttmpc_kernel_name.argtypes = [H, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]
@@ -81,5 +83,5 @@ EXPORTS = [
     "ttmpc_default_config", "ttmpc_create", "ttmpc_destroy", "ttmpc_last_error", "ttmpc_version",
     "ttmpc_solve_batch", "ttmpc_solve_batch_weighted", "ttmpc_solve_batch_shared",
     "ttmpc_obca_solve_batch", "ttmpc_obca_solve_batch_shared", "ttmpc_shift_warm_start", "ttmpc_plant_step", "ttmpc_episode_batch",
-    "ttmpc_launch_count", "ttmpc_kernel_name", "ttmpc_measure_fp64_peak",
+    "ttmpc_launch_count", "ttmpc_kernel_name", "ttmpc_measure_fp64_peak", "ttmpc_last_solve_lanes",
 ]

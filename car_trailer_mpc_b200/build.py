@@ -15,6 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 SRC = os.path.join(PKG_DIR, "csrc", "ttmpc.cu")
 DEPS = [SRC, os.path.join(PKG_DIR, "csrc", "ttmpc_core.cuh"), os.path.join(PKG_DIR, "csrc", "ttmpc_obca.cuh"),
+        os.path.join(PKG_DIR, "csrc", "ttmpc_team.cuh"),
         os.path.join(ROOT, "include", "ttmpc.h")]
 LIB = os.path.join(PKG_DIR, "libttmpc.so")
 

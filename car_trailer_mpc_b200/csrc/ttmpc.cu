@@ -21,6 +21,7 @@
 #include "../../include/ttmpc.h"
 #include "ttmpc_core.cuh"
 #include "ttmpc_obca.cuh"
+#include "ttmpc_team.cuh"
 
 using namespace ttmpc;
 
@@ -39,15 +40,6 @@ constexpr size_t kSolveSmem = (size_t)kCarry * kSolveThreads * sizeof(double);  
 // ------------------------------------------------------------------------------------------------
 // solve: persistent lanes with per-lane work refill
 // ------------------------------------------------------------------------------------------------
-struct SolveOut {
-  double* z;       // [B][8N+6]
-  double* u0;      // [B][2]
-  double* obj;     // [B]
-  double* kkt;     // [B][3]
-  int32_t* iters;  // [B]
-  int32_t* status; // [B]
-};
-
 // Every thread owns one scratch slot for the whole launch and works through problems taken from a global
 // queue: when its problem terminates it writes the result, pulls the next problem index (one warp-aggregated
 // atomic), loads that problem into its slot and joins the other lanes at the next iteration boundary.  The
@@ -217,6 +209,17 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// solve, team flavour (ttmpc_team.cuh): one warp per CTA, 32/L problems per warp, iterate resident in shared memory
+// ------------------------------------------------------------------------------------------------
+template <int L, bool G, bool DQ>
+__global__ void __launch_bounds__(32)
+    ttmpc_team_kernel(const __grid_constant__ Params p, long long B, ProblemIn in, SolveOut out, unsigned long long* __restrict__ counter,
+                      const int32_t* __restrict__ order) {
+  extern __shared__ __align__(16) double team_smem[];
+  team::cta_body<L, G, DQ>(p, team_smem, B, in, out, counter, order, (int)threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -643,12 +646,29 @@ __global__ void __launch_bounds__(kObcaThreads)
   }
 }
 
-constexpr int kNumKernels = 9;
+typedef void (*team_kernel_t)(const Params, long long, ProblemIn, SolveOut, unsigned long long*, const int32_t*);
+template <int L>
+static team_kernel_t team_kernel_l(const Params& p) {
+  if (p.generic) return p.diag ? ttmpc_team_kernel<L, true, true> : ttmpc_team_kernel<L, true, false>;
+  return p.diag ? ttmpc_team_kernel<L, false, true> : ttmpc_team_kernel<L, false, false>;
+}
+static team_kernel_t team_kernel_for(const Params& p, int L) {
+  return L == 8 ? team_kernel_l<8>(p) : L == 16 ? team_kernel_l<16>(p) : team_kernel_l<32>(p);
+}
+static size_t team_smem_for(const Params& p, int L) {
+  return p.generic ? team::cta_smem_bytes<true>(p.N, L) : team::cta_smem_bytes<false>(p.N, L);
+}
+
+constexpr int kNumKernels = 10;
 struct ttmpc_handle {
   ttmpc_config cfg;
   Params p;
   int device;
   int max_blocks;          // resident CTAs of the persistent solve kernel on this device
+  int sms;                 // multiprocessors of the device
+  size_t smem_optin;       // largest dynamic shared memory a CTA may ask for
+  int team_ctas[3];        // resident CTAs per SM of the team kernel for L = 8, 16, 32 (0: does not fit)
+  int last_team_lanes;     // L of the last team launch (0: the lane kernel ran), for ttmpc_last_kernel
   double* scratch;
   size_t banks;            // scratch capacity in banks of kBank slots
   unsigned long long* counter;  // [0] work queue head, [1..8] class histogram + cursors of the ordering pass
@@ -668,7 +688,7 @@ struct ttmpc_handle {
 static const char* kKernelNames[kNumKernels] = {"ttmpc_solve_kernel", "ttmpc_shift_kernel", "ttmpc_plant_kernel",
                                                 "ttmpc_dfma_kernel", "ttmpc_classify_kernel", "ttmpc_order_kernel",
                                                 "ttmpc_episode_kernel", "ttmpc_obca_kernel",
-                                                "ttmpc_obca_wide_kernel"};
+                                                "ttmpc_obca_wide_kernel", "ttmpc_team_kernel"};
 
 static int set_err(ttmpc_handle* h, int code, const char* what, cudaError_t ce) {
   if (h) snprintf(h->err, sizeof h->err, "%s%s%s", what, ce != cudaSuccess ? ": " : "", ce != cudaSuccess ? cudaGetErrorString(ce) : "");
@@ -677,7 +697,9 @@ static int set_err(ttmpc_handle* h, int code, const char* what, cudaError_t ce) 
 
 extern "C" {
 
-const char* ttmpc_version(void) { return "ttmpc 0.1 (sm_100a, thread-per-problem IPM/Riccati)"; }
+const char* ttmpc_version(void) { return "ttmpc 0.2 (sm_100a; plain solve: warp-cooperative shared-memory IPM/Riccati, lane-per-problem fallback)"; }
+
+int32_t ttmpc_last_solve_lanes(const ttmpc_handle* h) { return h ? h->last_team_lanes : TTMPC_E_INVAL; }
 
 void ttmpc_default_config(ttmpc_config* c, int32_t horizon) {
   memset(c, 0, sizeof *c);
@@ -740,6 +762,22 @@ int ttmpc_create(const ttmpc_config* cfg, int device, ttmpc_handle** out) {
     if (v >= 1 && v < per_sm) per_sm = v;
   }
   h->max_blocks = sms * per_sm;
+  h->sms = sms;
+  {
+    int optin = 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    h->smem_optin = optin > 0 ? (size_t)optin : 0;
+    const int Ls[3] = {8, 16, 32};
+    for (int i = 0; i < 3; i++) {  // team kernel: resident CTAs (= warps) per SM for each group width
+      const size_t smem = team_smem_for(p, Ls[i]);
+      int n = 0;
+      if (smem <= h->smem_optin &&
+          cudaFuncSetAttribute(team_kernel_for(p, Ls[i]), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, team_kernel_for(p, Ls[i]), 32, smem) == cudaSuccess)
+        h->team_ctas[i] = n;
+    }
+    cudaGetLastError();
+  }
   if (cudaMalloc(&h->counter, 16 * sizeof(unsigned long long)) != cudaSuccess) {
     delete h;
     return TTMPC_E_NOMEM;
@@ -799,7 +837,58 @@ static void launch_shape(const ttmpc_handle* h, long long B, long long* blocks, 
   if (*blocks > h->max_blocks) *blocks = h->max_blocks;
 }
 
+// Which flavour of the plain solve runs a batch of B, and with how many lanes per problem (0 = the lane-per-problem
+// kernel).  Model of one round (= one interior-point iteration of every resident problem) of the team kernel on an SM:
+// a warp needs its stage-parallel passes plus the three recursions over the stages back to back (latency), and the
+// FP64 pipes of the four sub-partitions must fit the warps' instructions (throughput); constants measured on B200
+// (profiles/r2_team_lanes_sweep.txt).  TTMPC_KERNEL=lane|team and TTMPC_TEAM_LANES=8|16|32 override.
+static int team_choose_lanes(const ttmpc_handle* h, long long B, bool weighted) {
+  const char* ek = getenv("TTMPC_KERNEL");
+  if (weighted || (ek && !strcmp(ek, "lane"))) return 0;
+  const char* el = getenv("TTMPC_TEAM_LANES");
+  const int forced = el ? atoi(el) : 0;
+  const int Ls[3] = {8, 16, 32};
+  const int N = h->p.N;
+  int best = 0;
+  double best_t = 0.0;
+  for (int i = 0; i < 3; i++) {
+    const int L = Ls[i], ctas = h->team_ctas[i];
+    if (ctas <= 0) continue;
+    if (forced == L) return L;
+    const int ppw = 32 / L, passes = (N + L) / L;
+    const double slots = (double)h->sms * ctas * ppw;
+    const double waves = ceil((double)B / slots);
+    double warps = ceil((double)B / ((double)h->sms * ppw));  // warps per SM that have work
+    if (warps > ctas) warps = ctas;
+    const double latency = passes * 1500.0 + (N + 1) * 300.0;
+    const double pipe = warps * (passes * 1500.0 + (N + 1) * 200.0) / 4.0;
+    const double t = waves * (latency > pipe ? latency : pipe);
+    if (!best || t < best_t) {
+      best = L;
+      best_t = t;
+    }
+  }
+  return best;  // 0: no group width fits the shared memory of this device -> lane kernel
+}
+
+static int team_device(ttmpc_handle* h, int L, long long B, const ProblemIn& in, const SolveOut& so, cudaStream_t st) {
+  const int i = L == 8 ? 0 : L == 16 ? 1 : 2;
+  const int ppw = 32 / L;
+  long long blocks = (B + ppw - 1) / ppw;
+  const long long cap = (long long)h->sms * h->team_ctas[i];
+  if (blocks > cap) blocks = cap;
+  cudaMemsetAsync(h->counter, 0, 16 * sizeof(unsigned long long), st);
+  team_kernel_for(h->p, L)<<<(unsigned)blocks, 32, team_smem_for(h->p, L), st>>>(h->p, B, in, so, h->counter, nullptr);
+  h->launches[9]++;
+  h->last_team_lanes = L;
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "team kernel launch", ce);
+  return TTMPC_OK;
+}
+
 static int solve_device(ttmpc_handle* h, long long B, const ProblemIn& in, const SolveOut& so, cudaStream_t st) {
+  if (const int L = team_choose_lanes(h, B, in.q_w != nullptr)) return team_device(h, L, B, in, so, st);
+  h->last_team_lanes = 0;
   long long blocks;
   int threads;
   launch_shape(h, B, &blocks, &threads);

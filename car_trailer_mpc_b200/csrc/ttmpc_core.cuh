@@ -390,6 +390,15 @@ struct ProblemIn {
   const double* q_w;          // [B][6] per-problem weight scalings or null (PW kernels)
   const double* r_w;          // [B][2]
 };
+// where a finished problem's results go (any pointer may be null)
+struct SolveOut {
+  double* z;       // [B][8N+6]
+  double* u0;      // [B][2]
+  double* obj;     // [B]
+  double* kkt;     // [B][3]
+  int32_t* iters;  // [B]
+  int32_t* status; // [B]
+};
 // reference value (stage k, component j) of problem b: the caller's window, or the window rules of
 // simulation.py:485-499 applied to the shared trajectory
 TT_HD double ref_value(const Params& p, const ProblemIn& in, long long b, int k, int j) {

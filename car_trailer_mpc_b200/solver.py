@@ -70,6 +70,12 @@ class BatchSolver:
     def launch_count(self) -> int:
         return int(sum(self._L.ttmpc_launch_count(h) for h in self._h.values()))
 
+    def last_solve_lanes(self, host: bool = False) -> int:
+        """Kernel flavour of the last plain solve: 8/16/32 = warp-cooperative team kernel with that many lanes per
+        problem, 0 = lane-per-problem kernel (include/ttmpc.h ttmpc_last_solve_lanes)."""
+        h = self._h.get(FLAG_HOST_POINTERS if host else 0)
+        return int(self._L.ttmpc_last_solve_lanes(h)) if h is not None else 0
+
     def kernel_launches(self) -> dict:
         out = {}
         for h in self._h.values():

@@ -195,6 +195,11 @@ int ttmpc_episode_batch(ttmpc_handle* h, int64_t B, const double* x0, const int6
                         const int32_t* k_seq, int32_t steps, const double* disturb, int32_t variant,
                         uint64_t seed, double* metrics_out, double* final_state_out, void* cuda_stream);
 
+/* Which kernel flavour ran the last plain solve of this handle: 8, 16 or 32 = ttmpc_team_kernel with that many lanes
+ * of a warp per problem (iterate resident in shared memory); 0 = ttmpc_solve_kernel (one lane per problem, per-problem
+ * weights).  The library picks by horizon and batch size; TTMPC_KERNEL=lane|team and TTMPC_TEAM_LANES=8|16|32 override. */
+int32_t ttmpc_last_solve_lanes(const ttmpc_handle* h);
+
 /* Number of kernel launches issued through this handle so far (bench accounting). */
 int64_t ttmpc_launch_count(const ttmpc_handle* h);
 

@@ -111,3 +111,48 @@ def obca_solve_batch(cfg, obstacles, x_init, ref_states=None, ref_inputs=None, k
     if rc:
         raise RuntimeError(f"obca emu rc={rc}")
     return dict(z=z, u0=u0, obj=obj, kkt=kkt, iters=it, status=st)
+
+
+_TSO = os.path.join(_HERE, "libttmpc_team_emu.so")
+_tlib = None
+
+
+def team_lib():
+    """Host build of the warp-cooperative solve (csrc/ttmpc_team.cuh): the 32 lanes of a warp run as fibers (tools/team_emu.cpp)."""
+    global _tlib
+    if _tlib is None:
+        src = os.path.join(_HERE, "team_emu.cpp")
+        deps = [src] + [os.path.join(_HERE, "..", "car_trailer_mpc_b200", "csrc", f) for f in ("ttmpc_core.cuh", "ttmpc_team.cuh")]
+        if not os.path.exists(_TSO) or os.path.getmtime(_TSO) < max(os.path.getmtime(f) for f in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", _TSO, src, "-lm"])
+        _tlib = ctypes.CDLL(_TSO)
+    return _tlib
+
+
+def team_solve_batch(cfg, x_init, ref_states=None, ref_inputs=None, z_warm=None, k_index=None, traj_states=None,
+                     traj_inputs=None, lanes=16, flags=0):
+    """lanes: lanes of the warp per problem (8, 16, 32); flags bit 0: generic-bounds variant, bit 1: dense-weights variant."""
+    N = cfg.horizon
+    x = np.ascontiguousarray(x_init, dtype=np.float64).reshape(-1, 6)
+    B = x.shape[0]
+    xs = us = ki = ts = tu = None
+    T = 0
+    if ref_states is not None:
+        xs = np.ascontiguousarray(ref_states, dtype=np.float64).reshape(B, N + 1, 6)
+        us = np.ascontiguousarray(ref_inputs, dtype=np.float64).reshape(B, N, 2)
+    else:
+        ki = np.ascontiguousarray(k_index, dtype=np.int32).reshape(B)
+        ts = np.ascontiguousarray(traj_states, dtype=np.float64)
+        tu = np.ascontiguousarray(traj_inputs, dtype=np.float64)
+        T = tu.shape[0]
+    zw = None if z_warm is None else np.ascontiguousarray(z_warm, dtype=np.float64).reshape(B, 8 * N + 6)
+    z = np.empty((B, 8 * N + 6)); u0 = np.empty((B, 2)); obj = np.empty(B); kkt = np.empty((B, 3))
+    it = np.empty(B, np.int32); st = np.empty(B, np.int32)
+    dp = ctypes.POINTER(ctypes.c_double); ip = ctypes.POINTER(ctypes.c_int32)
+    P = lambda a, t=dp: None if a is None else a.ctypes.data_as(t)
+    rc = team_lib().ttmpc_team_emu_solve_batch(ctypes.byref(cfg), ctypes.c_int64(B), P(x), P(xs), P(us), P(ki, ip), P(ts),
+                                               P(tu), ctypes.c_int32(T), P(zw), P(z), P(u0), P(obj), P(kkt), P(it, ip),
+                                               P(st, ip), ctypes.c_int(int(lanes)), ctypes.c_int(int(flags)))
+    if rc:
+        raise RuntimeError(f"team emu rc={rc}")
+    return dict(z=z, u0=u0, obj=obj, kkt=kkt, iters=it, status=st)
