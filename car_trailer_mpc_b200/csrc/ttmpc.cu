@@ -837,14 +837,43 @@ static void launch_shape(const ttmpc_handle* h, long long B, long long* blocks, 
   if (*blocks > h->max_blocks) *blocks = h->max_blocks;
 }
 
+// Hardest-first permutation of a batch (ttmpc_classify_kernel + ttmpc_order_kernel); *order stays null when disabled.
+static int build_order(ttmpc_handle* h, long long B, const ProblemIn& in, cudaStream_t st, const int32_t** order) {
+  *order = nullptr;
+  if (B >= (1ll << 31) || getenv("TTMPC_NO_ORDER")) return TTMPC_OK;
+  if ((size_t)B > h->order_cap) {
+    if (h->order_buf) cudaFree(h->order_buf);
+    h->order_buf = nullptr;
+    h->order_cap = 0;
+    if (cudaMalloc(&h->order_buf, 2 * (size_t)B * sizeof(int32_t)) != cudaSuccess)
+      return set_err(h, TTMPC_E_NOMEM, "order cudaMalloc", cudaGetLastError());
+    h->order_cap = (size_t)B;
+  }
+  int32_t* cls = h->order_buf;
+  int32_t* ord = h->order_buf + h->order_cap;
+  const long long want = (B * 32 + 255) / 256, cap = (long long)h->sms * 8;
+  ttmpc_classify_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(h->p, B, in, cls, h->counter + 1);
+  h->launches[4]++;
+  ttmpc_order_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, cls, h->counter + 1, ord);
+  h->launches[5]++;
+  *order = ord;
+  return TTMPC_OK;
+}
+
 // Which flavour of the plain solve runs a batch of B, and with how many lanes per problem (0 = the lane-per-problem
-// kernel).  Model of one round (= one interior-point iteration of every resident problem) of the team kernel on an SM:
-// a warp needs its stage-parallel passes plus the three recursions over the stages back to back (latency), and the
-// FP64 pipes of the four sub-partitions must fit the warps' instructions (throughput); constants measured on B200
-// (profiles/r2_team_lanes_sweep.txt).  TTMPC_KERNEL=lane|team and TTMPC_TEAM_LANES=8|16|32 override.
+// kernel).  Measured on B200 (profiles/r2_team_lanes_sweep.txt):
+//   * one round (= one interior-point iteration of every slot of a warp) of the team kernel takes
+//     T1 = 0.6 us * (N+1)  [three recursions over the stages, latency-bound]  +  4.2 us * passes  [stage-parallel
+//     phases]  +  4.3 us [termination tests, barrier update, reductions]; warps sharing a scheduler slow each other
+//     down by ~35 % per extra warp;
+//   * a batch needs ~6 rounds per problem and at least ~15 rounds for its slowest problem;
+//   * the lane kernel needs (N+1) * (86.6 us + 1.06 ns * B): it wins from ~19 000 problems per 148 SMs at N = 40, earlier
+//     for longer horizons (the team kernel's resident problems per SM shrink with N), later for shorter ones.
+// TTMPC_KERNEL=lane|team and TTMPC_TEAM_LANES=8|16|32 override.
 static int team_choose_lanes(const ttmpc_handle* h, long long B, bool weighted) {
   const char* ek = getenv("TTMPC_KERNEL");
   if (weighted || (ek && !strcmp(ek, "lane"))) return 0;
+  const bool force_team = ek && !strcmp(ek, "team");
   const char* el = getenv("TTMPC_TEAM_LANES");
   const int forced = el ? atoi(el) : 0;
   const int Ls[3] = {8, 16, 32};
@@ -857,18 +886,20 @@ static int team_choose_lanes(const ttmpc_handle* h, long long B, bool weighted) 
     if (forced == L) return L;
     const int ppw = 32 / L, passes = (N + L) / L;
     const double slots = (double)h->sms * ctas * ppw;
-    const double waves = ceil((double)B / slots);
     double warps = ceil((double)B / ((double)h->sms * ppw));  // warps per SM that have work
     if (warps > ctas) warps = ctas;
-    const double latency = passes * 1500.0 + (N + 1) * 300.0;
-    const double pipe = warps * (passes * 1500.0 + (N + 1) * 200.0) / 4.0;
-    const double t = waves * (latency > pipe ? latency : pipe);
+    const double share = warps > 4.0 ? 1.0 + 0.35 * (warps / 4.0 - 1.0) : 1.0;
+    const double round_us = (0.6 * (N + 1) + 4.2 * passes + 4.3) * share;
+    const double rounds = 6.0 * (double)B / slots + 5.0;
+    const double t = round_us * (rounds > 15.0 ? rounds : 15.0);
     if (!best || t < best_t) {
       best = L;
       best_t = t;
     }
   }
-  return best;  // 0: no group width fits the shared memory of this device -> lane kernel
+  if (!best || forced || force_team) return best;  // 0: no group width fits the shared memory of this device
+  const double t_lane = (N + 1) * (86.6 + 1.06e-3 * (double)B * (148.0 / h->sms));
+  return best_t <= t_lane ? best : 0;
 }
 
 static int team_device(ttmpc_handle* h, int L, long long B, const ProblemIn& in, const SolveOut& so, cudaStream_t st) {
@@ -878,7 +909,12 @@ static int team_device(ttmpc_handle* h, int L, long long B, const ProblemIn& in,
   const long long cap = (long long)h->sms * h->team_ctas[i];
   if (blocks > cap) blocks = cap;
   cudaMemsetAsync(h->counter, 0, 16 * sizeof(unsigned long long), st);
-  team_kernel_for(h->p, L)<<<(unsigned)blocks, 32, team_smem_for(h->p, L), st>>>(h->p, B, in, so, h->counter, nullptr);
+  const int32_t* order = nullptr;
+  if (B > blocks * ppw) {  // more problems than resident slots: (predicted) hardest first (TTMPC_NO_ORDER=1 disables)
+    int rc = build_order(h, B, in, st, &order);
+    if (rc) return rc;
+  }
+  team_kernel_for(h->p, L)<<<(unsigned)blocks, 32, team_smem_for(h->p, L), st>>>(h->p, B, in, so, h->counter, order);
   h->launches[9]++;
   h->last_team_lanes = L;
   cudaError_t ce = cudaGetLastError();
@@ -896,24 +932,9 @@ static int solve_device(ttmpc_handle* h, long long B, const ProblemIn& in, const
   if (rc) return rc;
   cudaMemsetAsync(h->counter, 0, 16 * sizeof(unsigned long long), st);
   const int32_t* order = nullptr;
-  if (B > blocks * threads && B < (1ll << 31) && !getenv("TTMPC_NO_ORDER")) {
-    // more problems than resident lanes: start the (predicted) hardest ones first
-    if ((size_t)B > h->order_cap) {
-      if (h->order_buf) cudaFree(h->order_buf);
-      h->order_buf = nullptr;
-      h->order_cap = 0;
-      if (cudaMalloc(&h->order_buf, 2 * (size_t)B * sizeof(int32_t)) != cudaSuccess)
-        return set_err(h, TTMPC_E_NOMEM, "order cudaMalloc", cudaGetLastError());
-      h->order_cap = (size_t)B;
-    }
-    int32_t* cls = h->order_buf;
-    int32_t* ord = h->order_buf + h->order_cap;
-    const unsigned gc = (unsigned)((B * 32 + 255) / 256 < 148 * 8 ? (B * 32 + 255) / 256 : 148 * 8);
-    ttmpc_classify_kernel<<<gc, 256, 0, st>>>(h->p, B, in, cls, h->counter + 1);
-    h->launches[4]++;
-    ttmpc_order_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, cls, h->counter + 1, ord);
-    h->launches[5]++;
-    order = ord;
+  if (B > blocks * threads) {  // more problems than resident lanes: start the (predicted) hardest ones first
+    rc = build_order(h, B, in, st, &order);
+    if (rc) return rc;
   }
   const bool weighted = in.q_w != nullptr;
   if (weighted) cudaFuncSetAttribute(solve_kernel_for(h->p, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmem);

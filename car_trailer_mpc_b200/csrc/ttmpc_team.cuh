@@ -85,12 +85,13 @@ struct Lay {
   static constexpr int kRows = G ? 78 : 70;
   static_assert(oZU + nB <= kRows && (kRows % 4) == 2, "stage layout");
 };
-constexpr int kTbuf = 56;  // transpose buffer of the Riccati step: 7 rows x 8 doubles (two of them per slot)
+constexpr int kTeamAux = 3 * 56 + 2;  // per slot: two transpose buffers, the dump area, a zero pair
+constexpr int kTbuf = 56;  // transpose buffer of the Riccati step: 7 rows x 8 doubles (two per slot + one dump area for idle lanes)
 
 // bytes of dynamic shared memory of one CTA (= one warp = 32/L slots)
 template <bool G>
 inline size_t cta_smem_bytes(int N, int L) {
-  return (size_t)(32 / L) * ((size_t)(N + 1) * Lay<G>::kRows + 2 * kTbuf) * sizeof(double);
+  return (size_t)(32 / L) * ((size_t)(N + 1) * Lay<G>::kRows + kTeamAux) * sizeof(double);
 }
 
 // rows [R0, R0+CNT) of a stage <-> registers, 128-bit accesses where the row offset is even
@@ -340,15 +341,13 @@ TT_HD void team_eval(const Params& p, const Slot& sl, const ProblemIn& in, long 
     }
     stv<Y::oG0, NW>(ps, g0);
     stv<Y::oG1, Y::nB>(ps, g1 + Y::b0);
-    {
-      double d[NW];  // diagonal of the stage Hessian without the Lagrangian part and without delta
-      TT_UNROLL
-      for (int j = 0; j < NX; j++) d[j] = p.Q2[SY(j, j)] + sig[j];
-      d[6] = p.R2[0] + sig[6];
-      d[7] = p.R2[2] + sig[7];
-      stv<Y::oDW, NW>(ps, d);
-    }
+    double d[NW];  // diagonal of the stage Hessian (weights + Sigma + Lagrangian part), without delta
+    TT_UNROLL
+    for (int j = 0; j < NX; j++) d[j] = p.Q2[SY(j, j)] + sig[j];
+    d[6] = p.R2[0] + sig[6];
+    d[7] = p.R2[2] + sig[7];
     if (!has_u) {
+      stv<Y::oDW, NW>(ps, d);
       TT_UNROLL
       for (int i = 0; i < NX; i++) rd_inf = tt_max(rd_inf, fabs(g0[i] + lam[i] - zl[i] + zu[i]));  // dual residual of x_N
     } else {
@@ -392,7 +391,11 @@ TT_HD void team_eval(const Params& p, const Slot& sl, const ProblemIn& in, long 
         stage_hess(p, m, lnew, hs);
         const double h7[7] = {hs.h22, hs.h25, hs.h33, hs.h34, hs.h35, hs.h44, hs.h45};
         stv<Y::oH, 7>(ps, h7);
+        d[2] += hs.h22;
+        d[3] += hs.h33;
+        d[4] += hs.h44;
       }
+      stv<Y::oDW, NW>(ps, d);
     }
   }
   st.J = gsum<L>(J);
@@ -433,6 +436,9 @@ TT_HD void team_finalize(const Params& p, const Slot& sl, bool run, double mu) {
 // ------------------------------------------------------------------------------------------------
 // SEQ: backward Riccati recursion with regularisation delta.  Returns false when a 2x2 pivot block is not positive
 // definite (wrong inertia).  Leaves K (2x6) and kff (2) of every stage in the G0/G1 rows.
+// The stage loop is one dependent chain per slot, so it is written without a single lane-dependent branch: what differs
+// between the lanes (which column, which Hessian row, where to store) is selected with FSEL / pointer selects, and lanes
+// that have nothing to store write to the slot's dump area.
 // ------------------------------------------------------------------------------------------------
 template <int L, bool G, bool DQ>
 TT_HD bool team_riccati(const Params& p, const Slot& sl, bool run, double delta) {
@@ -441,109 +447,149 @@ TT_HD bool team_riccati(const Params& p, const Slot& sl, bool run, double delta)
   const double dt = p.dt, dt2 = dt * dt;
   const int c = sl.m;
   const int cr = c < 6 ? c : 6;  // row of the transposed block this lane reads back
+  const bool lt6 = c < 6, is6 = c == 6;
+  const bool wr = run && c < 7;
+  double* const dump = sl.tb + 2 * kTbuf;
   bool ok = true;
+  double q2off[NX];  // row c of 2Q without its diagonal entry (dense weights only)
+  TT_UNROLL
+  for (int j = 0; j < NX; j++) q2off[j] = (!DQ && lt6 && j != c) ? p.Q2[SY(j, lt6 ? c : 0)] : 0.0;
   double Pc[NX], pv = 0.0;  // lane c < 6: column c of P and p[c];  lane 6: p;  other lanes: idle (zeros)
   {
     const double* ps = sl.sb + (size_t)N * Y::kRows;
     double d[NX], gh[NX];
     ldv<Y::oDW, NX>(ps, d);
     ldv<Y::oG0, NX>(ps, gh);
+    const double dc = sel6(d, c) + delta;
     TT_UNROLL
     for (int j = 0; j < NX; j++) {
-      double v = 0.0;
-      if (c < 6) v = (j == c) ? sel6(d, c) + delta : (DQ ? 0.0 : p.Q2[SY(j, cr < 6 ? cr : 0)]);
-      if (c == 6) v = gh[j];
-      Pc[j] = v;
+      const double v = (j == c) ? dc : q2off[j];
+      Pc[j] = lt6 ? v : (is6 ? gh[j] : 0.0);
     }
-    pv = (c < 6) ? sel6(gh, c) : 0.0;
+    pv = lt6 ? sel6(gh, c) : 0.0;
   }
+  const int kofs0 = lt6 ? c : 12, kofs1 = lt6 ? 6 + c : 13;  // K0[c], K1[c]  /  kff
+  // What a lane adds to its new row comes from lane-constant places, so that the stage loop needs no select:
+  //   lanes c < 6, entry j:  j == c -> D[c] (+ delta);  (c,j) an off-diagonal entry of the Lagrangian Hessian block
+  //                          {h25, h34, h35, h45} -> that H row;  otherwise a zero;   entry 6: the gradient g[c]
+  //   lane 6, entry j < 6:   the gradient g[j]
+  //   src[7], src[8]:        g_a, g_omega for lane 6 (the feed-forward right-hand side), zeros elsewhere
+  const double* src[9];
+  int sst[9];
+  double cv[NX];  // constants of the row: delta on the diagonal, off-diagonal weights (dense Q only)
+  {
+    double* const zero = dump + kTbuf;  // two doubles that stay 0.0
+    if (sl.m == 0) zero[0] = zero[1] = 0.0;
+    TT_UNROLL
+    for (int j = 0; j < 9; j++) {
+      int o = -1;
+      if (j < 6) {
+        const int lo = c < j ? c : j, hi = c < j ? j : c;
+        if (lt6 && j == c) o = Y::oDW + c;
+        else if (lt6 && lo == 2 && hi == 5) o = Y::oH + 1;
+        else if (lt6 && lo == 3 && hi == 4) o = Y::oH + 3;
+        else if (lt6 && lo == 3 && hi == 5) o = Y::oH + 4;
+        else if (lt6 && lo == 4 && hi == 5) o = Y::oH + 6;
+        else if (is6) o = Y::oG0 + j;
+      } else if (j == 6) {
+        if (lt6) o = Y::oG0 + c;
+      } else {
+        if (is6) o = Y::oG0 + (j - 1);
+      }
+      src[j] = o >= 0 ? sl.sb + o : zero;
+      sst[j] = o >= 0 ? Y::kRows : 0;
+    }
+    TT_UNROLL
+    for (int j = 0; j < NX; j++) cv[j] = ((lt6 && j == c) ? delta : 0.0) + q2off[j];
+    tw::sync();
+  }
+  double* const dstb0 = wr ? sl.tb + c : dump + (c & 7);          // column c of the transpose buffers
+  double* const dstb1 = wr ? sl.tb + kTbuf + c : dump + (c & 7);
+  double* const kdst0 = wr ? sl.sb + Y::oK + kofs0 : dump;        // K0[c] / kff_a, K1[c] / kff_omega of stage 0
+  double* const kdst1 = wr ? sl.sb + Y::oK + kofs1 : dump + 1;
+  const int kst = wr ? Y::kRows : 0;
   for (int k = N - 1; k >= 0; k--) {
     double* ps = sl.sb + (size_t)k * Y::kRows;
     double* buf = sl.tb + (k & 1) * kTbuf;
-    double a[9], cd[NX], gh[NW], d[NW], h[7];
+    double a[9], cd[NX], gh[NW], d[2];
     ldv<Y::oA, 9>(ps, a);
     ldv<Y::oC, NX>(ps, cd);
     ldv<Y::oG0, NW>(ps, gh);
-    ldv<Y::oDW, NW>(ps, d);
-    if (k >= 1) ldv<Y::oH, 7>(ps, h);
+    ldv<Y::oDW + 6, 2>(ps, d);  // diagonal of R + Sigma_u
     const double a02 = a[0], a05 = a[1], a12 = a[2], a15 = a[3], a24 = a[4], a25 = a[5], a33 = a[6], a34 = a[7], a35 = a[8];
     // U[:,c] = A' P[:,c]  and  h[c] = p[c] - P[:,c]'c
     double U[7];
     U[0] = Pc[0];
     U[1] = Pc[1];
-    U[2] = Pc[2] + a02 * Pc[0] + a12 * Pc[1];
+    U[2] = fma(a02, Pc[0], fma(a12, Pc[1], Pc[2]));
     U[3] = a33 * Pc[3];
-    U[4] = Pc[4] + a24 * Pc[2] + a34 * Pc[3];
-    U[5] = Pc[5] + a05 * Pc[0] + a15 * Pc[1] + a25 * Pc[2] + a35 * Pc[3];
-    U[6] = pv - (Pc[0] * cd[0] + Pc[1] * cd[1] + Pc[2] * cd[2] + Pc[3] * cd[3] + Pc[4] * cd[4] + Pc[5] * cd[5]);
+    U[4] = fma(a24, Pc[2], fma(a34, Pc[3], Pc[4]));
+    U[5] = fma(a05, Pc[0], fma(a15, Pc[1], Pc[5])) + fma(a25, Pc[2], a35 * Pc[3]);
+    U[6] = (pv - fma(Pc[0], cd[0], fma(Pc[1], cd[1], Pc[2] * cd[2]))) - fma(Pc[3], cd[3], fma(Pc[4], cd[4], Pc[5] * cd[5]));
+    {
+      double* dst = (k & 1) ? dstb1 : dstb0;
+      TT_UNROLL
+      for (int r = 0; r < 7; r++) dst[r * 8] = U[r];
+    }
     // Rhat = 2R + Sigma_u + delta + B'PB, inverted by every lane
     const double P44 = tw::shfl(Pc[4], sl.base + 4), P54 = tw::shfl(Pc[5], sl.base + 4), P55 = tw::shfl(Pc[5], sl.base + 5);
-    const double r00 = d[6] + delta + dt2 * P55;
+    const double r00 = d[0] + delta + dt2 * P55;
     const double r01 = (DQ ? 0.0 : p.R2[1]) + dt2 * P54;
-    const double r11 = d[7] + delta + dt2 * P44;
+    const double r11 = d[1] + delta + dt2 * P44;
     const double det = r00 * r11 - r01 * r01;
-    if (!(r00 > 0.0) || !(det > 0.0)) ok = false;
+    ok = ok && (r00 > 0.0) && (det > 0.0);
     const double idet = tt_rcp(det);
     const double i00 = r11 * idet, i01 = -r01 * idet, i11 = r00 * idet;
-    if (run && c < 7) {
-      TT_UNROLL
-      for (int r = 0; r < 7; r++) buf[r * 8 + c] = U[r];
-    }
+    // what this lane adds to its new row (no recursion data: off the dependent chain)
+    double add[9];
+    TT_UNROLL
+    for (int j = 0; j < 9; j++) add[j] = src[j][(size_t)k * sst[j]];
+    TT_UNROLL
+    for (int j = 0; j < NX; j++) add[j] += cv[j];
     tw::sync();
-    double Ur[7], t5[7], t4[7];  // row cr of [U; h'] and its columns 5, 4
+    double Ur[8], t4[7], t5[7];  // row cr of [U; h'] and its columns 4, 5
+#if defined(__CUDA_ARCH__)
+    TT_UNROLL
+    for (int j = 0; j < 4; j++) {
+      const double2 v = *reinterpret_cast<const double2*>(buf + cr * 8 + 2 * j);
+      Ur[2 * j] = v.x;
+      Ur[2 * j + 1] = v.y;
+    }
     TT_UNROLL
     for (int j = 0; j < 7; j++) {
+      const double2 v = *reinterpret_cast<const double2*>(buf + j * 8 + 4);
+      t4[j] = v.x;
+      t5[j] = v.y;
+    }
+#else
+    for (int j = 0; j < 7; j++) {
       Ur[j] = buf[cr * 8 + j];
-      t5[j] = buf[j * 8 + 5];
       t4[j] = buf[j * 8 + 4];
+      t5[j] = buf[j * 8 + 5];
     }
+#endif
     // K (lanes < 6: column c of the gain; lane 6: the feed-forward term)
-    const double S0c = dt * Ur[5] + (c == 6 ? gh[6] : 0.0);
-    const double S1c = dt * Ur[4] + (c == 6 ? gh[7] : 0.0);
+    const double S0c = fma(dt, Ur[5], add[7]);
+    const double S1c = fma(dt, Ur[4], add[8]);
     const double K0c = i00 * S0c + i01 * S1c, K1c = i01 * S0c + i11 * S1c;
-    if (run && c < 6) {
-      ps[Y::oK + c] = K0c;
-      ps[Y::oK + 6 + c] = K1c;
-    }
-    if (run && c == 6) {
-      ps[Y::oKFF] = K0c;
-      ps[Y::oKFF + 1] = K1c;
-    }
-    if (k >= 1) {
-      // row cr of U A (the 7th entry: A'(p - P c))
-      double Pn[7];
-      Pn[0] = Ur[0];
-      Pn[1] = Ur[1];
-      Pn[2] = Ur[2] + a02 * Ur[0] + a12 * Ur[1];
-      Pn[3] = a33 * Ur[3];
-      Pn[4] = Ur[4] + a24 * Ur[2] + a34 * Ur[3];
-      Pn[5] = Ur[5] + a05 * Ur[0] + a15 * Ur[1] + a25 * Ur[2] + a35 * Ur[3];
-      Pn[6] = Ur[6] - (Ur[0] * cd[0] + Ur[1] * cd[1] + Ur[2] * cd[2] + Ur[3] * cd[3] + Ur[4] * cd[4] + Ur[5] * cd[5]);
-      // minus S'K (by symmetry of Rhat^-1: K0[c]*S0[j] + K1[c]*S1[j])
-      const double dK0 = dt * K0c, dK1 = dt * K1c;
-      TT_UNROLL
-      for (int j = 0; j < NX; j++) Pn[j] -= dK0 * t5[j] + dK1 * t4[j];
-      Pn[6] -= K0c * (dt * t5[6] + gh[6]) + K1c * (dt * t4[6] + gh[7]);
-      // plus the stage Hessian row / gradient
-      if (c < 6) {
-        TT_UNROLL
-        for (int j = 0; j < NX; j++) {
-          if (j == c) Pn[j] += d[j] + delta;
-          else if (!DQ) Pn[j] += p.Q2[SY(j, cr < 6 ? cr : 0)];
-        }
-        if (c == 2) { Pn[2] += h[0]; Pn[5] += h[1]; }
-        if (c == 3) { Pn[3] += h[2]; Pn[4] += h[3]; Pn[5] += h[4]; }
-        if (c == 4) { Pn[3] += h[3]; Pn[4] += h[5]; Pn[5] += h[6]; }
-        if (c == 5) { Pn[2] += h[1]; Pn[3] += h[4]; Pn[4] += h[6]; }
-        Pn[6] += sel6(gh, c);
-      } else {
-        TT_UNROLL
-        for (int j = 0; j < NX; j++) Pn[j] += gh[j];
-      }
-      TT_UNROLL
-      for (int j = 0; j < NX; j++) Pc[j] = Pn[j];
-      pv = Pn[6];
-    }
+    kdst0[(size_t)k * kst] = K0c;
+    kdst1[(size_t)k * kst] = K1c;
+    // row cr of U A (7th entry: A'(p - P c)), minus S'K (by symmetry of Rhat^-1: K0[c]*S0[j] + K1[c]*S1[j]), plus `add`
+    const double nK0 = -dt * K0c, nK1 = -dt * K1c;
+    double Pn[7];
+    Pn[0] = Ur[0];
+    Pn[1] = Ur[1];
+    Pn[2] = fma(a02, Ur[0], fma(a12, Ur[1], Ur[2]));
+    Pn[3] = a33 * Ur[3];
+    Pn[4] = fma(a24, Ur[2], fma(a34, Ur[3], Ur[4]));
+    Pn[5] = fma(a05, Ur[0], fma(a15, Ur[1], Ur[5])) + fma(a25, Ur[2], a35 * Ur[3]);
+    Pn[6] = (Ur[6] - fma(Ur[0], cd[0], fma(Ur[1], cd[1], Ur[2] * cd[2]))) - fma(Ur[3], cd[3], fma(Ur[4], cd[4], Ur[5] * cd[5]));
+    TT_UNROLL
+    for (int j = 0; j < NX; j++) Pn[j] = fma(nK0, t5[j], fma(nK1, t4[j], Pn[j] + add[j]));
+    Pn[6] = (Pn[6] + add[6]) - fma(K0c, fma(dt, t5[6], gh[6]), K1c * fma(dt, t4[6], gh[7]));
+    TT_UNROLL
+    for (int j = 0; j < NX; j++) Pc[j] = Pn[j];  // (stage 0 computes a P_0 nobody uses: cheaper than a branch)
+    pv = Pn[6];
   }
   tw::sync();
   return ok;
@@ -587,7 +633,7 @@ TT_HD void team_forward(const Params& p, const Slot& sl, bool run) {
       TT_UNROLL
       for (int j = 0; j < NX; j++) dx[j] = y[j];
     }
-    if (run && sl.m == 0) stv<Y::oDW, NW>(ps, d);  // DW shares its rows with D only, which the Riccati sweep is done with
+    stv<0, NW>((run && sl.m == 0) ? ps + Y::oDW : sl.tb + 2 * kTbuf, d);  // lane 0 stores, the others hit the dump area (no branch)
   }
   tw::sync();
 }
@@ -773,7 +819,7 @@ TT_HD void team_costate(const Params& p, const Slot& sl, bool run, double alpha)
       lp[j] = y[j] - r[j];
       lam[j] += alpha * (lp[j] - lam[j]);
     }
-    if (run && sl.m == 0) stv<Y::oLAM, NX>(ps, lam);  // only lane 0's copy of lambda_k is ever used
+    stv<0, NX>((run && sl.m == 0) ? ps + Y::oLAM : sl.tb + 2 * kTbuf, lam);  // only lane 0's copy of lambda_k is ever used
   }
   tw::sync();
 }
@@ -794,7 +840,7 @@ TT_HD void cta_body(const Params& p, double* smem, long long B, const ProblemIn&
   sl.m = lane % L;
   sl.base = q * L;
   sl.sb = smem + (size_t)q * slot_doubles;
-  sl.tb = smem + (size_t)PPW * slot_doubles + (size_t)q * 2 * kTbuf;
+  sl.tb = smem + (size_t)PPW * slot_doubles + (size_t)q * kTeamAux;
   unsigned leaders = 0;
   for (int i = 0; i < PPW; i++) leaders |= 1u << (i * L);
 
