@@ -12,8 +12,16 @@ B = 65 536): perturbed initial states around the shipped reference trajectory, p
 `MPCTrackingControl` preset (Ipopt defaults, tol 1e-8), cold start.
 
   value     whole-job solves/s with inputs already resident in HBM (CUDA events, max over ranks).
-  e2e       same metric through the public API with HOST (pinned) buffers: H2D of x_init/ref windows, solve,
-            D2H of the full decision vectors + u0/status, all inside the timed region.
+  e2e       same metric through the library's own host-pointer call (ttmpc_solve_batch, TTMPC_FLAG_HOST_POINTERS |
+            TTMPC_FLAG_ASYNC_HOST: the library's three-stream copy-in | solve | copy-out pipeline) on page-locked HOST
+            buffers: every step moves its x_init / reference windows in and the full decision vectors + u0 / status
+            out inside the timed region; timed on the device (CUDA events on the library's copy streams).
+            `e2e_compact` is the same through ttmpc_solve_batch_multi (x_init + window start + trajectory index in,
+            u0 / iterations / status out: 80 B per problem instead of 5.3 KB).
+  strong    the SAME 65 536 scenarios split over the ranks (strong scaling, automatic kernel choice) and
+            `u0_checksum_global`, a checksum of all their first controls computed with one fixed kernel flavour, which
+            must not depend on the number of GPUs.
+  secondary configs 2, 3, 4 of BASELINE.json at reduced step counts (B = 4096 / N = 40, B = 1 latency, N = 100, OBCA).
   roofline  dominant kernel = ttmpc_solve_kernel.  It is bound by the non-tensor FP64 pipe / dependent-issue
             latency, not by HBM or tensor cores; `achieved` = algorithmic FP64 flop
             (mean_iters * (2500 N + 500) per solve) / kernel time, `peak` = the FP64 FMA peak measured in this run
@@ -151,6 +159,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=65536, help="scenarios per step and GPU")
     ap.add_argument("--horizon", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the N = 100 and OBCA legs of the secondary block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -202,9 +211,6 @@ def main() -> None:
     xs_h = torch.from_numpy(sc.ref_states).pin_memory()
     us_h = torch.from_numpy(sc.ref_inputs).pin_memory()
     nz = 8 * N + 6
-    z_h = torch.empty((B, nz), dtype=torch.float64).pin_memory()
-    u0_h = torch.empty((B, 2), dtype=torch.float64).pin_memory()
-    st_h = torch.empty(B, dtype=torch.int32).pin_memory()
     gather_u0 = torch.empty((world * B, 2), dtype=torch.float64, device=dev) if world > 1 else None
     gather_st = torch.empty(world * B, dtype=torch.int32, device=dev) if world > 1 else None
 
@@ -215,60 +221,31 @@ def main() -> None:
             dist.all_gather_into_tensor(gather_st, r["status"])
         return r
 
-    def step_e2e():
-        xa = x_h.to(dev, non_blocking=True)
-        xsa = xs_h.to(dev, non_blocking=True)
-        usa = us_h.to(dev, non_blocking=True)
-        r = solver.solve(xa, xsa, usa)
-        z_h.copy_(r["z"], non_blocking=True)
-        u0_h.copy_(r["u0"], non_blocking=True)
-        st_h.copy_(r["status"], non_blocking=True)
-        return r
+    # e2e through the library's own host-pointer path: page-locked host buffers in, page-locked host buffers out, three
+    # output sets because up to three solves are in flight (TTMPC_FLAG_ASYNC_HOST); device-side timing by the library.
+    def pinned(shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype).pin_memory()
 
-    # e2e, pipelined over steps: copy-in / solve / copy-out on three streams with double-buffered device tensors, so
-    # step s+1's H2D and step s-1's D2H overlap step s's kernel.  Every step still moves its full inputs from pinned
-    # host memory and its full outputs back inside the timed region.
-    s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
-    din = [tuple(torch.empty_like(t, device=dev) for t in (x_h, xs_h, us_h)) for _ in range(2)]
+    out_full = [dict(z=pinned((B, nz)), u0=pinned((B, 2)), obj=pinned((B,)), kkt=pinned((B, 3)), iters=pinned((B,), torch.int32),
+                     status=pinned((B,), torch.int32)) for _ in range(3)]
+    out_compact = [dict(u0=pinned((B, 2)), iters=pinned((B,), torch.int32), status=pinned((B,), torch.int32)) for _ in range(3)]
+    k_h = torch.from_numpy(sc.k_index).pin_memory()
+    ti_h = torch.from_numpy(sc.traj_index).pin_memory()
+    ts_h = torch.from_numpy(sc.traj_states).pin_memory()
+    tu_h = torch.from_numpy(sc.traj_inputs).pin_memory()
 
-    def run_e2e_pipelined(steps: int) -> float:
-        ev_in = [torch.cuda.Event() for _ in range(2)]
-        ev_cmp = [torch.cuda.Event() for _ in range(2)]
-        ev_out = [torch.cuda.Event() for _ in range(2)]
-        cur = torch.cuda.current_stream(dev)
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record(cur)
-        for st_ in (s_in, s_cmp, s_out):
-            st_.wait_event(t0)
+    def run_e2e(steps: int, compact: bool, pipelined: bool = True) -> float:
+        """Device-side ms for `steps` host-buffer solves (first copy-in to last copy-out)."""
+        total = 0.0
         for i in range(steps):
-            b = i % 2
-            with torch.cuda.stream(s_in):
-                if i >= 2:
-                    s_in.wait_event(ev_cmp[b])  # the solve that read this input buffer is done
-                for d_, h_ in zip(din[b], (x_h, xs_h, us_h)):
-                    d_.copy_(h_, non_blocking=True)
-                ev_in[b].record(s_in)
-            with torch.cuda.stream(s_cmp):
-                s_cmp.wait_event(ev_in[b])
-                r_ = solver.solve(*din[b], stream=s_cmp.cuda_stream)
-                ev_cmp[b].record(s_cmp)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_cmp[b])
-                if i >= 1:
-                    s_out.wait_event(ev_out[1 - b])
-                for t_ in (r_["z"], r_["u0"], r_["status"]):
-                    t_.record_stream(s_out)
-                z_h.copy_(r_["z"], non_blocking=True)
-                u0_h.copy_(r_["u0"], non_blocking=True)
-                st_h.copy_(r_["status"], non_blocking=True)
-                ev_out[b].record(s_out)
-        for st_ in (s_in, s_cmp, s_out):
-            e = torch.cuda.Event()
-            e.record(st_)
-            cur.wait_event(e)
-        t1.record(cur)
-        torch.cuda.synchronize(dev)
-        return t0.elapsed_time(t1)
+            if compact:
+                solver.solve_shared(x_h, k_h, ts_h, tu_h, traj_index=ti_h, want_z=False, want_kkt=False, host_async=True,
+                                    out=out_compact[i % 3])
+            else:
+                solver.solve(x_h, xs_h, us_h, host_async=True, out=out_full[i % 3])
+            if not pipelined:
+                total += solver.sync()
+        return total + (solver.sync() if pipelined else 0.0)
 
     def barrier():
         if world > 1:
@@ -295,25 +272,120 @@ def main() -> None:
     sampler.start()
     total_ms, per_ms, r, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.finish()
+    lanes_headline = solver.last_solve_lanes()
     e2e_steps = max(4, min(args.steps, 12))
-    e2e_serial_ms, _, _, _ = timed(step_e2e, e2e_steps, 2)   # one stream: copy-in, solve, copy-out back to back
-    run_e2e_pipelined(2)
+    run_e2e(3, False)
     barrier()
-    e2e_total_ms = run_e2e_pipelined(e2e_steps)
+    e2e_serial_ms = run_e2e(e2e_steps, False, pipelined=False)   # one solve in flight: copy-in, solve, copy-out back to back
     barrier()
+    e2e_total_ms = run_e2e(e2e_steps, False)
+    barrier()
+    run_e2e(3, True)
+    barrier()
+    e2e_compact_ms = run_e2e(e2e_steps, True)
+    barrier()
+    assert torch.equal(out_compact[(e2e_steps - 1) % 3]["u0"], out_full[(e2e_steps - 1) % 3]["u0"]), "compact != full contract"
+
+    # p99 of the step latency over >= 200 consecutive steps; the timed region above stays K steps
+    lat_steps = max(0, 200 - args.steps)
+    if lat_steps:
+        _, per_extra, _, _ = timed(step_resident, lat_steps, 0)
+        per_lat = np.concatenate([per_ms, per_extra])
+    else:
+        per_lat = per_ms
+
+    # ---- strong scaling + sharding invariance: the SAME 65 536 scenarios (rank 0's batch of the N = 1 run) split over the ranks
+    sc0 = sc if rank == 0 else make_batch(cfg, B, 0)
+    lo, hi = rank * B // world, (rank + 1) * B // world
+    xg = [torch.from_numpy(np.ascontiguousarray(a[lo:hi])).to(dev) for a in (sc0.x_init, sc0.ref_states, sc0.ref_inputs)]
+    u0_all = torch.empty((B, 2), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step_strong():
+        r_ = solver.solve(*xg, want_z=False)
+        if world > 1:
+            dist.all_gather_into_tensor(u0_all, r_["u0"])
+        return r_
+
+    strong_ms, _, r_strong, _ = timed(step_strong, max(4, min(args.steps, 10)), 2)
+    strong_ms /= max(4, min(args.steps, 10))
+    strong_lanes = solver.last_solve_lanes()
+    # checksum with ONE kernel flavour on every rank count (the flavours differ in the last bits: other summation order)
+    os.environ["TTMPC_KERNEL"], os.environ["TTMPC_TEAM_LANES"] = "team", "16"
+    r_ck = solver.solve(*xg, want_z=False)
+    os.environ.pop("TTMPC_KERNEL"), os.environ.pop("TTMPC_TEAM_LANES")
+    u0_ck = r_ck["u0"]
+    if world > 1:
+        dist.all_gather_into_tensor(u0_all, u0_ck)
+        u0_ck = u0_all
+    torch.cuda.synchronize()
+    import hashlib
+    checksum = hashlib.sha256(u0_ck.cpu().numpy().tobytes()).hexdigest()[:16]
+
+    # ---- secondary configurations (rank 0 only; each a handful of launches)
+    secondary = {}
+    if rank == 0:
+        def quick(solver_, args_, steps=5, **kw):
+            for _ in range(2):
+                solver_.solve(*args_, **kw)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                rr = solver_.solve(*args_, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / steps, rr
+
+        for Bs in (4096, 1):
+            ms_, rr = quick(solver, (x_d[:Bs].contiguous(), xs_d[:Bs].contiguous(), us_d[:Bs].contiguous()))
+            secondary[f"B{Bs}_N{N}"] = {"ms_per_step": ms_, "solves_per_s": Bs / ms_ * 1e3, "lanes_per_problem": solver.last_solve_lanes(),
+                                         "mean_iters": float(rr["iters"].float().mean())}
+        if not args.no_secondary:
+            cfg100 = tracking_preset(100)
+            cfg100.max_iter = 200
+            s100 = BatchSolver(cfg100, local_rank)
+            sc100 = pb.make_scenarios(cfg100, 8192, seed=1100)
+            a100 = tuple(torch.from_numpy(a).to(dev) for a in (sc100.x_init, sc100.ref_states, sc100.ref_inputs))
+            ms_, rr = quick(s100, a100, steps=3, want_z=False)
+            secondary["B8192_N100"] = {"ms_per_step": ms_, "solves_per_s": 8192 / ms_ * 1e3, "lanes_per_problem": s100.last_solve_lanes(),
+                                       "mean_iters": float(rr["iters"].float().mean())}
+            s100.close()
+            from car_trailer_mpc_b200.config import Obstacles, parking_lot_obstacles
+
+            cfg50 = tracking_preset(50)
+            cfg50.max_iter = 300
+            s50 = BatchSolver(cfg50, local_rank)
+            S_, U_ = pb.load_reference_trajectory(dt=cfg50.dt)
+            rng = np.random.default_rng(4)
+            ko = rng.integers(0, 341, size=2048).astype(np.int32)
+            xo = S_[ko] + rng.normal(0.0, 0.002, size=(2048, 6))
+            obs = Obstacles.from_list(parking_lot_obstacles())
+            ao = (obs, torch.from_numpy(xo).to(dev), torch.from_numpy(ko).to(dev), torch.from_numpy(S_).to(dev), torch.from_numpy(U_).to(dev))
+            s50.solve_obca_shared(*ao, want_z=False)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ro = s50.solve_obca_shared(*ao, want_z=False)
+            e1.record()
+            torch.cuda.synchronize()
+            sto = ro["status"].cpu().numpy()
+            secondary["obca_B2048_N50"] = {"ms_per_step": e0.elapsed_time(e1), "solves_per_s": 2048 / e0.elapsed_time(e1) * 1e3,
+                                           "frac_converged": float((sto <= 1).mean()), "mean_iters": float(ro["iters"].float().mean()),
+                                           "workload": "11 rectangles of obstacles.json, window starts 0..340, sigma 0.002"}
+            s50.close()
 
     iters = r["iters"].cpu().numpy()
     status = r["status"].cpu().numpy()
     kkt = r["kkt"].cpu().numpy()
 
     # max over ranks (device time)
-    t = torch.tensor([total_ms, e2e_total_ms, float(np.percentile(per_ms, 99)), float(np.percentile(per_ms, 50))],
-                     dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_total_ms, float(np.percentile(per_lat, 99)), float(np.percentile(per_lat, 50)), e2e_compact_ms,
+                      e2e_serial_ms, strong_ms], dtype=torch.float64, device=dev)
     agg = torch.tensor([float(iters.sum()), float((status <= 1).sum()), float(B)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    total_ms, e2e_total_ms, p99_ms, p50_ms = [float(v) for v in t.cpu()]
+    total_ms, e2e_total_ms, p99_ms, p50_ms, e2e_compact_ms, e2e_serial_ms, strong_ms = [float(v) for v in t.cpu()]
     iters_sum, ok_sum, b_sum = [float(v) for v in agg.cpu()]
 
     if rank == 0:
@@ -346,7 +418,8 @@ def main() -> None:
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(N, B, world),
-            "p50_step_ms": p50_ms, "p99_step_ms": p99_ms, "control_period_ms": 50.0,
+            "p50_step_ms": p50_ms, "p99_step_ms": p99_ms, "latency_steps": int(len(per_lat)), "control_period_ms": 50.0,
+            "solve_kernel": "ttmpc_team_kernel" if lanes_headline else "ttmpc_solve_kernel", "lanes_per_problem": lanes_headline,
             "mean_iters": mean_iters, "max_iters": int(iters.max()), "frac_success": ok_sum / b_sum,
             "kkt_max": {"dual_inf": float(kkt[status == 0, 0].max()), "constr_viol": float(kkt[status == 0, 1].max()),
                         "compl": float(kkt[status == 0, 2].max())},
@@ -360,10 +433,23 @@ def main() -> None:
             },
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(x_h.numel() + xs_h.numel() + us_h.numel()) * 8,
-                    "d2h_bytes_per_step": int(z_h.numel() + u0_h.numel()) * 8 + int(st_h.numel()) * 4,
+                    "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in out_full[0].values())),
                     "ms_per_step": e2e_total_ms / e2e_steps, "steps": e2e_steps,
-                    "mode": "3-stream pipeline over steps (copy-in | solve | copy-out), double-buffered", "cpu_affinity_to_gpu_numa_node": numa_bound,
-                    "serial_ms_per_step": e2e_serial_ms / e2e_steps},
+                    "mode": "ttmpc_solve_batch with TTMPC_FLAG_HOST_POINTERS|TTMPC_FLAG_ASYNC_HOST on page-locked host buffers: the "
+                            "library's own three-stream copy-in | solve | copy-out pipeline, up to three solves in flight; timed "
+                            "with CUDA events on the library's copy streams (ttmpc_host_pipeline_ms)",
+                    "cpu_affinity_to_gpu_numa_node": numa_bound, "serial_ms_per_step": e2e_serial_ms / e2e_steps},
+            "e2e_compact": {"value": solves_per_step / (e2e_compact_ms / e2e_steps * 1e-3), "unit": UNIT,
+                            "h2d_bytes_per_step": int(x_h.numel()) * 8 + int(k_h.numel() + ti_h.numel()) * 4 + int(ts_h.numel() + tu_h.numel()) * 8,
+                            "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in out_compact[0].values())),
+                            "ms_per_step": e2e_compact_ms / e2e_steps, "steps": e2e_steps,
+                            "mode": "ttmpc_solve_batch_multi, same flags: x_init + window start + trajectory index in, u0 / iterations / "
+                                    "status out; identical first controls (checked in this run)"},
+            "strong": {"B_total": B, "n_gpus": world, "ms_per_step": strong_ms, "solves_per_s": B / (strong_ms * 1e-3),
+                       "lanes_per_problem": strong_lanes,
+                       "note": "the N = 1 run's 65 536 scenarios split over the ranks, automatic kernel choice, u0 gathered with NCCL"},
+            "u0_checksum_global": checksum,
+            "secondary": secondary,
             "gpu_launches": int(launches),
             "kernels": {k: v for k, v in solver.kernel_launches().items() if v},
             "clocks": clocks,

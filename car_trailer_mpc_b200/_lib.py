@@ -54,6 +54,14 @@ def load():
         [H, ctypes.c_int64, c_dp, c_dp, c_dp, c_dp, ctypes.c_int32] + [c_dp] * 7 + [ctypes.c_void_p]
     )
     L.ttmpc_solve_batch_shared.restype = ctypes.c_int
+    L.ttmpc_solve_batch_multi.argtypes = (
+        [H, ctypes.c_int64, c_dp, c_dp, c_dp, c_dp, c_dp, ctypes.c_int32, ctypes.c_int32] + [c_dp] * 7 + [ctypes.c_void_p]
+    )
+    L.ttmpc_solve_batch_multi.restype = ctypes.c_int
+    L.ttmpc_sync.argtypes = [H]
+    L.ttmpc_sync.restype = ctypes.c_int
+    L.ttmpc_host_pipeline_ms.argtypes = [H]
+    L.ttmpc_host_pipeline_ms.restype = ctypes.c_double
     L.ttmpc_obca_solve_batch.argtypes = [H, ctypes.c_void_p, ctypes.c_int64] + [c_dp] * 9 + [ctypes.c_void_p]
     L.ttmpc_obca_solve_batch.restype = ctypes.c_int
     L.ttmpc_obca_solve_batch_shared.argtypes = (
@@ -83,5 +91,5 @@ EXPORTS = [
     "ttmpc_default_config", "ttmpc_create", "ttmpc_destroy", "ttmpc_last_error", "ttmpc_version",
     "ttmpc_solve_batch", "ttmpc_solve_batch_weighted", "ttmpc_solve_batch_shared",
     "ttmpc_obca_solve_batch", "ttmpc_obca_solve_batch_shared", "ttmpc_shift_warm_start", "ttmpc_plant_step", "ttmpc_episode_batch",
-    "ttmpc_launch_count", "ttmpc_kernel_name", "ttmpc_measure_fp64_peak", "ttmpc_last_solve_lanes",
+    "ttmpc_launch_count", "ttmpc_kernel_name", "ttmpc_measure_fp64_peak", "ttmpc_last_solve_lanes", "ttmpc_solve_batch_multi", "ttmpc_sync", "ttmpc_host_pipeline_ms",
 ]

@@ -33,7 +33,7 @@ STATUS_NAMES = {
 
 FLAG_HOST_POINTERS = 0x1
 FLAG_SYNC = 0x2
-FLAG_SHIFT_REFERENCE_BUG = 0x4
+FLAG_ASYNC_HOST = 0x8
 
 
 class Config(ctypes.Structure):

@@ -678,9 +678,25 @@ struct ttmpc_handle {
   size_t ep_cap;
   double* ob_scratch;           // OBCA solve: per-lane stage data incl. the (obstacle, body) pairs
   size_t ob_doubles;
-  // staging for the host-pointer path
+  // staging for the host-pointer helpers (shift, plant step)
   void* stage;
   size_t stage_bytes;
+  // host-pointer solves: a three-deep pipeline copy-in | solve | copy-out on the handle's own streams
+  cudaStream_t s_in, s_c, s_out;
+  struct HostSet {
+    void* buf;
+    size_t bytes;
+    cudaEvent_t ev_in, ev_c, ev_out;
+    bool pending;  // ev_out has been recorded and not waited for yet
+  } sets[3];
+  unsigned long long host_seq;
+  bool pipe_ready;
+  cudaEvent_t ev_t0, ev_t1;  // device-side clock of the pipeline: first copy-in after a drain ... last copy-out
+  bool t0_recorded;
+  float pipe_ms;             // elapsed time of the last drained burst
+  // device-pointer calls on different caller streams are ordered through this event (they share scratch and the queue)
+  cudaEvent_t ev_busy;
+  bool busy_recorded;
   char err[256];
   long long launches[kNumKernels];
 };
@@ -689,6 +705,19 @@ static const char* kKernelNames[kNumKernels] = {"ttmpc_solve_kernel", "ttmpc_shi
                                                 "ttmpc_dfma_kernel", "ttmpc_classify_kernel", "ttmpc_order_kernel",
                                                 "ttmpc_episode_kernel", "ttmpc_obca_kernel",
                                                 "ttmpc_obca_wide_kernel", "ttmpc_team_kernel"};
+
+// Entry points set the handle's device and put the caller's current device back on return.
+struct DeviceGuard {
+  int prev;
+  bool ok;
+  explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+    cudaGetDevice(&prev);
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
 
 static int set_err(ttmpc_handle* h, int code, const char* what, cudaError_t ce) {
   if (h) snprintf(h->err, sizeof h->err, "%s%s%s", what, ce != cudaSuccess ? ": " : "", ce != cudaSuccess ? cudaGetErrorString(ce) : "");
@@ -736,7 +765,8 @@ int ttmpc_create(const ttmpc_config* cfg, int device, ttmpc_handle** out) {
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return TTMPC_E_NODEV;
-  if (cudaSetDevice(device) != cudaSuccess) return TTMPC_E_NODEV;
+  DeviceGuard guard(device);
+  if (!guard.ok) return TTMPC_E_NODEV;
   ttmpc_handle* h = new (std::nothrow) ttmpc_handle;
   if (!h) return TTMPC_E_NOMEM;
   memset(h, 0, sizeof *h);
@@ -788,13 +818,28 @@ int ttmpc_create(const ttmpc_config* cfg, int device, ttmpc_handle** out) {
 
 int ttmpc_destroy(ttmpc_handle* h) {
   if (!h) return TTMPC_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   if (h->scratch) cudaFree(h->scratch);
   if (h->stage) cudaFree(h->stage);
   if (h->counter) cudaFree(h->counter);
   if (h->order_buf) cudaFree(h->order_buf);
   if (h->ep_buf) cudaFree(h->ep_buf);
   if (h->ob_scratch) cudaFree(h->ob_scratch);
+  if (h->pipe_ready) {
+    cudaStreamSynchronize(h->s_out);
+    for (int i = 0; i < 3; i++) {
+      if (h->sets[i].buf) cudaFree(h->sets[i].buf);
+      cudaEventDestroy(h->sets[i].ev_in);
+      cudaEventDestroy(h->sets[i].ev_c);
+      cudaEventDestroy(h->sets[i].ev_out);
+    }
+    cudaEventDestroy(h->ev_t0);
+    cudaEventDestroy(h->ev_t1);
+    cudaStreamDestroy(h->s_in);
+    cudaStreamDestroy(h->s_c);
+    cudaStreamDestroy(h->s_out);
+  }
+  if (h->ev_busy) cudaEventDestroy(h->ev_busy);
   delete h;
   return TTMPC_OK;
 }
@@ -957,8 +1002,7 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
                        cudaStream_t st) {
   obca::ObParams o;
   if (obca::build_obparams(&h->cfg, obs, &o) != TTMPC_OK) return set_err(h, TTMPC_E_INVAL, "bad obstacle set", cudaSuccess);
-  int sms = 148, per_sm = 1, per_sm_wide = 1;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  int sms = h->sms, per_sm = 1, per_sm_wide = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ttmpc_obca_kernel, kObcaThreads, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_wide, ttmpc_obca_wide_kernel, kObcaThreads, 0);
   if (per_sm < 1) per_sm = 1;
@@ -993,111 +1037,199 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
   return TTMPC_OK;
 }
 
-// host-pointer path: stage everything through one device buffer
-struct StagePlan {
-  size_t off_x, off_rs, off_ru, off_zw, off_k, off_ts, off_tu, off_z, off_u0, off_obj, off_kkt, off_it, off_st, total;
-};
+// Device-pointer calls are asynchronous on the caller's stream but share the handle's scratch, work queue and ordering
+// buffers: a call waits for the previous call's kernels (recorded in ev_busy), whatever stream that one ran on.
+static void order_after_previous(ttmpc_handle* h, cudaStream_t st) {
+  if (!h->ev_busy) cudaEventCreateWithFlags(&h->ev_busy, cudaEventDisableTiming);
+  if (h->busy_recorded) cudaStreamWaitEvent(st, h->ev_busy, 0);
+}
+static void mark_busy(ttmpc_handle* h, cudaStream_t st) {
+  if (h->ev_busy && cudaEventRecord(h->ev_busy, st) == cudaSuccess) h->busy_recorded = true;
+}
+
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int host_pipe_init(ttmpc_handle* h) {
+  if (h->pipe_ready) return TTMPC_OK;
+  cudaError_t ce = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->s_c, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+  for (int i = 0; i < 3 && ce == cudaSuccess; i++) {
+    ce = cudaEventCreateWithFlags(&h->sets[i].ev_in, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->sets[i].ev_c, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->sets[i].ev_out, cudaEventDisableTiming);
+  }
+  if (ce == cudaSuccess) ce = cudaEventCreate(&h->ev_t0);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&h->ev_t1);
+  if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "host pipeline streams", ce);
+  h->pipe_ready = true;
+  return TTMPC_OK;
+}
+
+// Wait for every host-pointer solve issued through this handle (TTMPC_FLAG_ASYNC_HOST) to have delivered its outputs.
+static int host_pipe_drain(ttmpc_handle* h) {
+  if (!h->pipe_ready) return TTMPC_OK;
+  cudaError_t ce = cudaSuccess;
+  for (int i = 0; i < 3; i++)
+    if (h->sets[i].pending) {
+      const cudaError_t e = cudaEventSynchronize(h->sets[i].ev_out);
+      if (e != cudaSuccess) ce = e;
+      h->sets[i].pending = false;
+    }
+  if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "host-pointer solve", ce);
+  if (h->t0_recorded) {
+    if (cudaEventSynchronize(h->ev_t1) == cudaSuccess) cudaEventElapsedTime(&h->pipe_ms, h->ev_t0, h->ev_t1);
+    h->t0_recorded = false;
+  }
+  return TTMPC_OK;
+}
 
 static int solve_any(ttmpc_handle* h, int64_t B, const double* x_init, const double* ref_states, const double* ref_inputs,
                      const int32_t* k_index, const double* traj_states, const double* traj_inputs, int32_t T,
                      const double* z_warm, double* z_out, double* u0_out, double* obj_out, double* kkt_out,
                      int32_t* iters_out, int32_t* status_out, void* stream, const double* q_w = nullptr,
-                     const double* r_w = nullptr, const ttmpc_obstacles* obs = nullptr) {
+                     const double* r_w = nullptr, const ttmpc_obstacles* obs = nullptr, const int32_t* traj_index = nullptr,
+                     int32_t F = 1) {
   if (!h) return TTMPC_E_INVAL;
   h->err[0] = 0;
   if (B < 0 || !x_init) return set_err(h, TTMPC_E_INVAL, "bad batch arguments", cudaSuccess);
   if ((q_w == nullptr) != (r_w == nullptr)) return set_err(h, TTMPC_E_INVAL, "q_weights and r_weights go together", cudaSuccess);
   if (q_w && !h->p.diag) return set_err(h, TTMPC_E_INVAL, "per-problem weights need diagonal Q and R", cudaSuccess);
   const bool shared = (ref_states == nullptr);
-  if (shared && (!k_index || !traj_states || !traj_inputs || T < 1)) return set_err(h, TTMPC_E_INVAL, "bad trajectory arguments", cudaSuccess);
+  if (shared && (!k_index || !traj_states || !traj_inputs || T < 1 || F < 1)) return set_err(h, TTMPC_E_INVAL, "bad trajectory arguments", cudaSuccess);
   if (!shared && !ref_inputs) return set_err(h, TTMPC_E_INVAL, "ref_inputs is null", cudaSuccess);
   if (B == 0) return TTMPC_OK;
-  if (cudaSetDevice(h->device) != cudaSuccess) return set_err(h, TTMPC_E_NODEV, "cudaSetDevice", cudaGetLastError());
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return set_err(h, TTMPC_E_NODEV, "cudaSetDevice", cudaGetLastError());
   cudaStream_t st = (cudaStream_t)stream;
   const int N = h->p.N;
   const size_t nz = 8 * (size_t)N + 6;
   const bool host = (h->cfg.flags & TTMPC_FLAG_HOST_POINTERS) != 0;
   if (!host) {
-    ProblemIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T, q_w, r_w};
+    ProblemIn in{x_init, ref_states, ref_inputs, z_warm, k_index, traj_states, traj_inputs, T, q_w, r_w, traj_index};
     SolveOut so{z_out, u0_out, obj_out, kkt_out, iters_out, status_out};
+    order_after_previous(h, st);
     int rc = obs ? obca_device(h, obs, B, in, so, st) : solve_device(h, B, in, so, st);
     if (rc) return rc;
+    mark_busy(h, st);
     if (h->cfg.flags & TTMPC_FLAG_SYNC) {
       cudaError_t ce = cudaStreamSynchronize(st);
       if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "stream synchronize", ce);
     }
     return TTMPC_OK;
   }
-  // ---- host pointers
-  StagePlan pl;
+  // ---- host pointers: copy-in | solve | copy-out pipeline over consecutive calls (three staging sets, three streams).
+  // Without TTMPC_FLAG_ASYNC_HOST the call waits for its own outputs (the B = 1 shim path); with it the call returns as
+  // soon as its work is queued, a call reuses the staging set of the third-last one (waiting for that one's outputs
+  // first), and ttmpc_sync() drains.  The caller's stream argument is not used in host-pointer mode.
+  int rc = host_pipe_init(h);
+  if (rc) return rc;
+  ttmpc_handle::HostSet& hs = h->sets[h->host_seq % 3];
+  h->host_seq++;
+  if (hs.pending) {
+    cudaError_t ce = cudaEventSynchronize(hs.ev_out);
+    hs.pending = false;
+    if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "host-pointer solve", ce);
+  }
   size_t o = 0;
-  pl.off_x = o; o += al((size_t)B * NX * 8);
-  pl.off_rs = o; o += shared ? 0 : al((size_t)B * (N + 1) * NX * 8);
-  pl.off_ru = o; o += shared ? 0 : al((size_t)B * N * NU * 8);
-  pl.off_zw = o; o += z_warm ? al((size_t)B * nz * 8) : 0;
-  pl.off_k = o; o += shared ? al((size_t)B * 4) : 0;
-  pl.off_ts = o; o += shared ? al((size_t)(T + 1) * NX * 8) : 0;
-  pl.off_tu = o; o += shared ? al((size_t)T * NU * 8) : 0;
-  pl.off_z = o; o += al((size_t)B * nz * 8);
-  pl.off_u0 = o; o += al((size_t)B * 2 * 8);
-  pl.off_obj = o; o += al((size_t)B * 8);
-  pl.off_kkt = o; o += al((size_t)B * 3 * 8);
-  pl.off_it = o; o += al((size_t)B * 4);
-  pl.off_st = o; o += al((size_t)B * 4);
+  const size_t off_x = o; o += al((size_t)B * NX * 8);
+  const size_t off_rs = o; o += shared ? 0 : al((size_t)B * (N + 1) * NX * 8);
+  const size_t off_ru = o; o += shared ? 0 : al((size_t)B * N * NU * 8);
+  const size_t off_zw = o; o += z_warm ? al((size_t)B * nz * 8) : 0;
+  const size_t off_k = o; o += shared ? al((size_t)B * 4) : 0;
+  const size_t off_ti = o; o += (shared && traj_index) ? al((size_t)B * 4) : 0;
+  const size_t off_ts = o; o += shared ? al((size_t)F * (T + 1) * NX * 8) : 0;
+  const size_t off_tu = o; o += shared ? al((size_t)F * T * NU * 8) : 0;
+  const size_t off_z = o; o += z_out ? al((size_t)B * nz * 8) : 0;
+  const size_t off_u0 = o; o += al((size_t)B * 2 * 8);
+  const size_t off_obj = o; o += al((size_t)B * 8);
+  const size_t off_kkt = o; o += al((size_t)B * 3 * 8);
+  const size_t off_it = o; o += al((size_t)B * 4);
+  const size_t off_st = o; o += al((size_t)B * 4);
   const size_t off_qw = o; o += q_w ? al((size_t)B * NX * 8) : 0;
   const size_t off_rw = o; o += q_w ? al((size_t)B * NU * 8) : 0;
-  pl.total = o;
-  if (pl.total > h->stage_bytes) {
-    if (h->stage) cudaFree(h->stage);
-    h->stage = nullptr;
-    h->stage_bytes = 0;
-    cudaError_t ce = cudaMalloc(&h->stage, pl.total);
+  if (o > hs.bytes) {
+    if (hs.buf) cudaFree(hs.buf);
+    hs.buf = nullptr;
+    hs.bytes = 0;
+    cudaError_t ce = cudaMalloc(&hs.buf, o);
     if (ce != cudaSuccess) return set_err(h, TTMPC_E_NOMEM, "staging cudaMalloc", ce);
-    h->stage_bytes = pl.total;
+    hs.bytes = o;
   }
-  char* d = (char*)h->stage;
-#define H2D(off, src, bytes) cudaMemcpyAsync(d + (off), (src), (bytes), cudaMemcpyHostToDevice, st)
-#define D2H(dst, off, bytes) cudaMemcpyAsync((dst), d + (off), (bytes), cudaMemcpyDeviceToHost, st)
-  H2D(pl.off_x, x_init, (size_t)B * NX * 8);
+  char* d = (char*)hs.buf;
+  if (!h->t0_recorded) {  // first solve of a burst: start the device-side clock (ttmpc_host_pipeline_ms)
+    cudaStreamWaitEvent(h->s_in, h->ev_t1, 0);
+    cudaEventRecord(h->ev_t0, h->s_in);
+    h->t0_recorded = true;
+  }
+#define H2D(off, src, bytes) cudaMemcpyAsync(d + (off), (src), (bytes), cudaMemcpyHostToDevice, h->s_in)
+#define D2H(dst, off, bytes) cudaMemcpyAsync((dst), d + (off), (bytes), cudaMemcpyDeviceToHost, h->s_out)
+  H2D(off_x, x_init, (size_t)B * NX * 8);
   if (!shared) {
-    H2D(pl.off_rs, ref_states, (size_t)B * (N + 1) * NX * 8);
-    H2D(pl.off_ru, ref_inputs, (size_t)B * N * NU * 8);
+    H2D(off_rs, ref_states, (size_t)B * (N + 1) * NX * 8);
+    H2D(off_ru, ref_inputs, (size_t)B * N * NU * 8);
   } else {
-    H2D(pl.off_k, k_index, (size_t)B * 4);
-    H2D(pl.off_ts, traj_states, (size_t)(T + 1) * NX * 8);
-    H2D(pl.off_tu, traj_inputs, (size_t)T * NU * 8);
+    H2D(off_k, k_index, (size_t)B * 4);
+    if (traj_index) H2D(off_ti, traj_index, (size_t)B * 4);
+    H2D(off_ts, traj_states, (size_t)F * (T + 1) * NX * 8);
+    H2D(off_tu, traj_inputs, (size_t)F * T * NU * 8);
   }
-  if (z_warm) H2D(pl.off_zw, z_warm, (size_t)B * nz * 8);
+  if (z_warm) H2D(off_zw, z_warm, (size_t)B * nz * 8);
   if (q_w) {
     H2D(off_qw, q_w, (size_t)B * NX * 8);
     H2D(off_rw, r_w, (size_t)B * NU * 8);
   }
-  ProblemIn in{(const double*)(d + pl.off_x),
-            shared ? nullptr : (const double*)(d + pl.off_rs),
-            shared ? nullptr : (const double*)(d + pl.off_ru),
-            z_warm ? (const double*)(d + pl.off_zw) : nullptr,
-            shared ? (const int32_t*)(d + pl.off_k) : nullptr,
-            shared ? (const double*)(d + pl.off_ts) : nullptr,
-            shared ? (const double*)(d + pl.off_tu) : nullptr,
-            T,
-            q_w ? (const double*)(d + off_qw) : nullptr,
-            q_w ? (const double*)(d + off_rw) : nullptr};
-  SolveOut so{z_out ? (double*)(d + pl.off_z) : nullptr, (double*)(d + pl.off_u0), (double*)(d + pl.off_obj),
-              (double*)(d + pl.off_kkt), (int32_t*)(d + pl.off_it), (int32_t*)(d + pl.off_st)};
-  int rc = obs ? obca_device(h, obs, B, in, so, st) : solve_device(h, B, in, so, st);
+  cudaEventRecord(hs.ev_in, h->s_in);
+  cudaStreamWaitEvent(h->s_c, hs.ev_in, 0);
+  ProblemIn in{(const double*)(d + off_x),
+               shared ? nullptr : (const double*)(d + off_rs),
+               shared ? nullptr : (const double*)(d + off_ru),
+               z_warm ? (const double*)(d + off_zw) : nullptr,
+               shared ? (const int32_t*)(d + off_k) : nullptr,
+               shared ? (const double*)(d + off_ts) : nullptr,
+               shared ? (const double*)(d + off_tu) : nullptr,
+               T,
+               q_w ? (const double*)(d + off_qw) : nullptr,
+               q_w ? (const double*)(d + off_rw) : nullptr,
+               (shared && traj_index) ? (const int32_t*)(d + off_ti) : nullptr};
+  SolveOut so{z_out ? (double*)(d + off_z) : nullptr, (double*)(d + off_u0), (double*)(d + off_obj),
+              (double*)(d + off_kkt), (int32_t*)(d + off_it), (int32_t*)(d + off_st)};
+  rc = obs ? obca_device(h, obs, B, in, so, h->s_c) : solve_device(h, B, in, so, h->s_c);
   if (rc) return rc;
-  if (z_out) D2H(z_out, pl.off_z, (size_t)B * nz * 8);
-  if (u0_out) D2H(u0_out, pl.off_u0, (size_t)B * 2 * 8);
-  if (obj_out) D2H(obj_out, pl.off_obj, (size_t)B * 8);
-  if (kkt_out) D2H(kkt_out, pl.off_kkt, (size_t)B * 3 * 8);
-  if (iters_out) D2H(iters_out, pl.off_it, (size_t)B * 4);
-  if (status_out) D2H(status_out, pl.off_st, (size_t)B * 4);
+  cudaEventRecord(hs.ev_c, h->s_c);
+  cudaStreamWaitEvent(h->s_out, hs.ev_c, 0);
+  if (z_out) D2H(z_out, off_z, (size_t)B * nz * 8);
+  if (u0_out) D2H(u0_out, off_u0, (size_t)B * 2 * 8);
+  if (obj_out) D2H(obj_out, off_obj, (size_t)B * 8);
+  if (kkt_out) D2H(kkt_out, off_kkt, (size_t)B * 3 * 8);
+  if (iters_out) D2H(iters_out, off_it, (size_t)B * 4);
+  if (status_out) D2H(status_out, off_st, (size_t)B * 4);
 #undef H2D
 #undef D2H
-  cudaError_t ce = cudaStreamSynchronize(st);
+  cudaError_t ce = cudaEventRecord(hs.ev_out, h->s_out);
+  cudaEventRecord(h->ev_t1, h->s_out);
   if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "host-pointer solve", ce);
+  hs.pending = true;
+  if (!(h->cfg.flags & TTMPC_FLAG_ASYNC_HOST)) return host_pipe_drain(h);
   return TTMPC_OK;
+}
+
+int ttmpc_sync(ttmpc_handle* h) {
+  if (!h) return TTMPC_E_INVAL;
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return set_err(h, TTMPC_E_NODEV, "cudaSetDevice", cudaGetLastError());
+  return host_pipe_drain(h);
+}
+
+double ttmpc_host_pipeline_ms(const ttmpc_handle* h) { return h ? (double)h->pipe_ms : -1.0; }
+
+int ttmpc_solve_batch_multi(ttmpc_handle* h, int64_t B, const double* x_init, const int32_t* k_index, const int32_t* traj_index,
+                            const double* traj_states, const double* traj_inputs, int32_t F, int32_t T, const double* z_warm,
+                            double* z_out, double* u0_out, double* obj_out, double* kkt_out, int32_t* iters_out,
+                            int32_t* status_out, void* cuda_stream) {
+  if (h && (!traj_index || F < 1)) return set_err(h, TTMPC_E_INVAL, "bad trajectory-family arguments", cudaSuccess);
+  return solve_any(h, B, x_init, nullptr, nullptr, k_index, traj_states, traj_inputs, T, z_warm, z_out, u0_out, obj_out,
+                   kkt_out, iters_out, status_out, cuda_stream, nullptr, nullptr, nullptr, traj_index, F);
 }
 
 int ttmpc_solve_batch(ttmpc_handle* h, int64_t B, const double* x_init, const double* ref_states, const double* ref_inputs,
@@ -1158,7 +1290,8 @@ static int with_staging(ttmpc_handle* h, size_t bytes) {
 int ttmpc_shift_warm_start(ttmpc_handle* h, int64_t B, const double* z, double* z_shift, int32_t mode, void* cuda_stream) {
   if (!h || B < 0 || !z || !z_shift || (mode != 0 && mode != 1)) return h ? set_err(h, TTMPC_E_INVAL, "bad shift arguments", cudaSuccess) : TTMPC_E_INVAL;
   if (B == 0) return TTMPC_OK;
-  if (cudaSetDevice(h->device) != cudaSuccess) return set_err(h, TTMPC_E_NODEV, "cudaSetDevice", cudaGetLastError());
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return set_err(h, TTMPC_E_NODEV, "cudaSetDevice", cudaGetLastError());
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const int N = h->p.N;
   const size_t bytes = (size_t)B * (8 * (size_t)N + 6) * 8;
@@ -1173,7 +1306,8 @@ int ttmpc_shift_warm_start(ttmpc_handle* h, int64_t B, const double* z, double* 
     cudaMemcpyAsync((void*)zi, z, bytes, cudaMemcpyHostToDevice, st);
   }
   const long long total = (long long)B * (8LL * N + 6);
-  const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  const long long gcap = (long long)h->sms * 16;
+  const unsigned grid = (unsigned)((total + 255) / 256 < gcap ? (total + 255) / 256 : gcap);
   ttmpc_shift_kernel<<<grid, 256, 0, st>>>(N, B, zi, zo, mode);
   h->launches[1]++;
   if (host) cudaMemcpyAsync(z_shift, zo, bytes, cudaMemcpyDeviceToHost, st);
@@ -1187,7 +1321,8 @@ int ttmpc_plant_step(ttmpc_handle* h, int64_t B, const double* q, const double* 
                      const double* noise, double noise_scale, double* q_next, void* cuda_stream) {
   if (!h || B < 0 || !q || !u || !q_next) return h ? set_err(h, TTMPC_E_INVAL, "bad plant arguments", cudaSuccess) : TTMPC_E_INVAL;
   if (B == 0) return TTMPC_OK;
-  if (cudaSetDevice(h->device) != cudaSuccess) return set_err(h, TTMPC_E_NODEV, "cudaSetDevice", cudaGetLastError());
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return set_err(h, TTMPC_E_NODEV, "cudaSetDevice", cudaGetLastError());
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const bool host = (h->cfg.flags & TTMPC_FLAG_HOST_POINTERS) != 0;
   const double *dq = q, *du = u, *dn = noise;
@@ -1228,7 +1363,8 @@ int ttmpc_episode_batch(ttmpc_handle* h, int64_t B, const double* x0, const int6
     return set_err(h, TTMPC_E_INVAL, "bad episode arguments", cudaSuccess);
   if (h->cfg.flags & TTMPC_FLAG_HOST_POINTERS) return set_err(h, TTMPC_E_INVAL, "episodes need device pointers", cudaSuccess);
   if (B == 0) return TTMPC_OK;
-  if (cudaSetDevice(h->device) != cudaSuccess) return set_err(h, TTMPC_E_NODEV, "cudaSetDevice", cudaGetLastError());
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return set_err(h, TTMPC_E_NODEV, "cudaSetDevice", cudaGetLastError());
   cudaStream_t st = (cudaStream_t)cuda_stream;
   cudaError_t ce = cudaFuncSetAttribute(episode_kernel_for(h->p), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmem);
   if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "episode kernel attribute", ce);
@@ -1276,10 +1412,10 @@ int ttmpc_episode_batch(ttmpc_handle* h, int64_t B, const double* x0, const int6
 
 double ttmpc_measure_fp64_peak(ttmpc_handle* h, void* cuda_stream) {
   if (!h) return (double)TTMPC_E_INVAL;
-  if (cudaSetDevice(h->device) != cudaSuccess) return (double)TTMPC_E_NODEV;
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return (double)TTMPC_E_NODEV;
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  const int sms = h->sms;
   double* dout = nullptr;
   if (cudaMalloc(&dout, 8) != cudaSuccess) return (double)TTMPC_E_NOMEM;
   cudaEvent_t e0, e1;

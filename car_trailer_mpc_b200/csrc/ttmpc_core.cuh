@@ -389,7 +389,15 @@ struct ProblemIn {
   int T;
   const double* q_w;          // [B][6] per-problem weight scalings or null (PW kernels)
   const double* r_w;          // [B][2]
+  const int32_t* traj_index;  // [B] or null (shared mode with F trajectories: traj_states [F][T+1][6], traj_inputs [F][T][2])
 };
+// first state / input record of the trajectory problem b tracks (shared-trajectory mode)
+TT_HD const double* traj_s(const ProblemIn& in, long long b) {
+  return in.traj_index ? in.traj_states + (long long)in.traj_index[b] * (in.T + 1) * NX : in.traj_states;
+}
+TT_HD const double* traj_u(const ProblemIn& in, long long b) {
+  return in.traj_index ? in.traj_inputs + (long long)in.traj_index[b] * in.T * NU : in.traj_inputs;
+}
 // where a finished problem's results go (any pointer may be null)
 struct SolveOut {
   double* z;       // [B][8N+6]
@@ -406,8 +414,8 @@ TT_HD double ref_value(const Params& p, const ProblemIn& in, long long b, int k,
   if (in.ref_states != nullptr)
     return (j < NX) ? in.ref_states[(b * (N + 1) + k) * NX + j] : in.ref_inputs[(b * N + k) * NU + (j - NX)];
   const int T = in.T, kk = in.k_index[b];
-  if (j < NX) return in.traj_states[(long long)((kk < T) ? ((kk + k < T) ? kk + k : T) : T) * NX + j];
-  return (kk >= T) ? 0.0 : in.traj_inputs[(long long)((kk + k < T) ? kk + k : T - 1) * NU + (j - NX)];
+  if (j < NX) return traj_s(in, b)[(long long)((kk < T) ? ((kk + k < T) ? kk + k : T) : T) * NX + j];
+  return (kk >= T) ? 0.0 : traj_u(in, b)[(long long)((kk + k < T) ? kk + k : T - 1) * NU + (j - NX)];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -486,8 +494,8 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
         ru = in.ref_inputs + (b * N + k) * NU;
       } else {
         const int T = in.T;
-        rs = in.traj_states + (long long)((kk_fresh < T) ? ((kk_fresh + k < T) ? kk_fresh + k : T) : T) * NX;
-        ru = in.traj_inputs + (long long)((kk_fresh + k < T) ? kk_fresh + k : T - 1) * NU;
+        rs = traj_s(in, b) + (long long)((kk_fresh < T) ? ((kk_fresh + k < T) ? kk_fresh + k : T) : T) * NX;
+        ru = traj_u(in, b) + (long long)((kk_fresh + k < T) ? kk_fresh + k : T - 1) * NU;
         zero_u = (kk_fresh >= T);
       }
       TT_UNROLL

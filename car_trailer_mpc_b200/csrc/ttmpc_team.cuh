@@ -180,8 +180,8 @@ TT_HD RefAt ref_at(const Params& p, const ProblemIn& in, long long b, int kk, in
     r.ru = in.ref_inputs + (b * N + (k < N ? k : N - 1)) * NU;
   } else {
     const int T = in.T;
-    r.rs = in.traj_states + (long long)((kk < T) ? ((kk + k < T) ? kk + k : T) : T) * NX;
-    r.ru = in.traj_inputs + (long long)((kk + k < T) ? kk + k : T - 1) * NU;
+    r.rs = traj_s(in, b) + (long long)((kk < T) ? ((kk + k < T) ? kk + k : T) : T) * NX;
+    r.ru = traj_u(in, b) + (long long)((kk + k < T) ? kk + k : T - 1) * NU;
     r.zero_u = (kk >= T);
   }
   return r;

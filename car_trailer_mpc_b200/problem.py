@@ -209,6 +209,10 @@ class ScenarioBatch:
     ref_inputs: np.ndarray  # [B, N, 2]
     k_index: np.ndarray  # [B] int32 window start
     family: np.ndarray  # [B] int32 test-case family (-1 = untransformed trajectory)
+    # the same windows in the compact (shared-trajectory) form: problem i tracks traj_states[traj_index[i]] from k_index[i]
+    traj_index: np.ndarray | None = None  # [B] int32
+    traj_states: np.ndarray | None = None  # [F, T+1, 6]
+    traj_inputs: np.ndarray | None = None  # [F, T, 2]
 
 
 SIGMA_NARROW = np.full(6, 0.02)  # the reference's own noise level (simulation.py:29)
@@ -240,6 +244,8 @@ def make_scenarios(
     k = rng.integers(0, T + 1, size=B).astype(np.int32)
     noise = rng.normal(0.0, 1.0, size=(B, 6)) * np.asarray(sigma, dtype=np.float64)
     fam = np.full(B, -1, dtype=np.int32)
+    tix = np.zeros(B, dtype=np.int32)
+    stack = [S]  # trajectory 0: untransformed
     xs = np.empty((B, N + 1, 6))
     us = np.empty((B, N, 2))
     lb = np.array(cfg.x_lb[:])
@@ -259,10 +265,14 @@ def make_scenarios(
             src = S if Sm is None else Sm
             xs[sel], us[sel] = windows_batch(src, U, k[sel], N)
             fam[sel] = -1 if Sm is None else f
+            if Sm is not None:
+                tix[sel] = len(stack)
+                stack.append(Sm)
     else:
         xs, us = windows_batch(S, U, k, N)
     x_init = xs[:, 0, :] + noise
     for i in range(6):
         if math.isfinite(lb[i]) or math.isfinite(ub[i]):
             x_init[:, i] = np.clip(x_init[:, i], lb[i] + 1e-3, ub[i] - 1e-3)
-    return ScenarioBatch(np.ascontiguousarray(x_init), xs, us, k, fam)
+    return ScenarioBatch(np.ascontiguousarray(x_init), xs, us, k, fam, tix, np.ascontiguousarray(np.stack(stack)),
+                         np.ascontiguousarray(np.broadcast_to(U, (len(stack),) + U.shape)))

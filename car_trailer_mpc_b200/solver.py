@@ -18,7 +18,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from .config import FLAG_HOST_POINTERS, Config, Obstacles
+from .config import FLAG_ASYNC_HOST, FLAG_HOST_POINTERS, Config, Obstacles
 
 
 def _is_torch(x) -> bool:
@@ -98,17 +98,29 @@ class BatchSolver:
 
     # ------------------------------------------------------------------ solve
     def solve(self, x_init, ref_states, ref_inputs, z_warm=None, want_z: bool = True, stream=None,
-              q_weights=None, r_weights=None) -> dict:
+              q_weights=None, r_weights=None, host_async: bool = False, out=None) -> dict:
         """Solve B problems with per-problem reference windows (MPCTrackingControl.solve semantics).
 
         ``q_weights [B,6]`` / ``r_weights [B,2]`` (optional, together): per-problem weight scalings
-        ``Q_w = diag(q) Q diag(q)``, ``R_w = diag(r) R diag(r)`` as in mpc_control_fuzzy.py:21-31 (diagonal Q, R only)."""
-        return self._solve(x_init, ref_states, ref_inputs, None, None, None, z_warm, want_z, stream, q_weights, r_weights)
+        ``Q_w = diag(q) Q diag(q)``, ``R_w = diag(r) R diag(r)`` as in mpc_control_fuzzy.py:21-31 (diagonal Q, R only).
 
-    def solve_shared(self, x_init, k_index, traj_states, traj_inputs, z_warm=None, want_z: bool = True, stream=None) -> dict:
+        Host arrays (numpy, or torch CPU tensors -- page-locked ones make the copies asynchronous) go through the
+        library's copy-in | solve | copy-out pipeline.  ``host_async=True`` returns as soon as the work is queued (up to
+        three solves in flight); the outputs are valid after :meth:`sync`.  ``out``: dict of preallocated output arrays
+        to reuse (same keys as the result)."""
+        return self._solve(x_init, ref_states, ref_inputs, None, None, None, z_warm, want_z, stream, q_weights, r_weights,
+                           host_async=host_async, out=out)
+
+    def solve_shared(self, x_init, k_index, traj_states, traj_inputs, z_warm=None, want_z: bool = True, stream=None,
+                     traj_index=None, host_async: bool = False, out=None, want_kkt: bool = True) -> dict:
         """All problems track one trajectory ``traj_states [T+1,6]``, ``traj_inputs [T,2]``; problem i uses the
-        window starting at ``k_index[i]`` with the padding rules of simulation.py:485-499."""
-        return self._solve(x_init, None, None, k_index, traj_states, traj_inputs, z_warm, want_z, stream)
+        window starting at ``k_index[i]`` with the padding rules of simulation.py:485-499.
+
+        With ``traj_index [B]`` (int32) the trajectories are a stack ``traj_states [F,T+1,6]``, ``traj_inputs [F,T,2]``
+        and problem i tracks trajectory ``traj_index[i]`` (the batch driver's scenario families).  ``want_z=False,
+        want_kkt=False`` is the compact contract: 56 B in, 24 B out per problem."""
+        return self._solve(x_init, None, None, k_index, traj_states, traj_inputs, z_warm, want_z, stream,
+                           traj_index=traj_index, host_async=host_async, out=out, want_kkt=want_kkt)
 
     def solve_obca(self, obstacles, x_init, ref_states, ref_inputs, want_z: bool = True, stream=None) -> dict:
         """Solve B obstacle-aware problems (``MPCTrackingControlObs.solve``, mpc_control_obs.py:282-322).
@@ -121,109 +133,121 @@ class BatchSolver:
         """:meth:`solve_obca` with the windows taken from one shared trajectory (simulation.py:485-499)."""
         return self._solve(x_init, None, None, k_index, traj_states, traj_inputs, None, want_z, stream, obstacles=obstacles)
 
+    def sync(self) -> float:
+        """Wait for every ``host_async`` solve queued so far (``ttmpc_sync``); returns the device-side duration of that
+        burst in ms (first copy-in to last copy-out, CUDA events on the library's copy streams)."""
+        h = self._h.get(FLAG_HOST_POINTERS | FLAG_ASYNC_HOST)
+        if h is None:
+            return 0.0
+        self._check(h, self._L.ttmpc_sync(h), "ttmpc_sync")
+        return float(self._L.ttmpc_host_pipeline_ms(h))
+
     def _solve(self, x_init, ref_states, ref_inputs, k_index, traj_states, traj_inputs, z_warm, want_z, stream,
-               q_weights=None, r_weights=None, obstacles=None):
+               q_weights=None, r_weights=None, obstacles=None, traj_index=None, host_async=False, out=None, want_kkt=True):
         if obstacles is not None and not isinstance(obstacles, Obstacles):
             obstacles = Obstacles.from_list(obstacles)
+        if (q_weights is None) != (r_weights is None):
+            raise ValueError("q_weights and r_weights go together")
         N = self.cfg.horizon
         nz = 8 * N + 6
         shared = ref_states is None
-        if _is_torch(x_init):
+        if shared and (k_index is None or traj_states is None or traj_inputs is None):
+            raise ValueError("shared-trajectory mode needs k_index, traj_states and traj_inputs")
+        if traj_index is not None and (not shared or obstacles is not None or q_weights is not None):
+            raise ValueError("traj_index is only available for the plain shared-trajectory solve")
+        on_device = _is_torch(x_init) and x_init.device.type == "cuda"
+        keep = []
+        if on_device:
             import torch
 
             dev = x_init.device
-            assert dev.type == "cuda" and dev.index == self.device, "tensors must live on the solver's device"
+            if dev.index != self.device:
+                raise ValueError(f"tensors must live on the solver's device cuda:{self.device}, got {dev}")
+            f64, i32 = torch.float64, torch.int32
 
-            def chk(t, shape, dtype=torch.float64):
-                assert t.dtype == dtype and t.is_contiguous() and t.device == dev and tuple(t.shape) == shape, (
-                    f"expected contiguous {dtype} tensor of shape {shape} on {dev}, got {t.dtype} {tuple(t.shape)}")
+            def arg(t, shape, dtype=f64, name="array"):
+                if not (_is_torch(t) and t.dtype == dtype and t.is_contiguous() and t.device == dev and tuple(t.shape) == tuple(shape)):
+                    raise ValueError(f"{name}: expected a contiguous {dtype} tensor of shape {tuple(shape)} on {dev}, got "
+                                     f"{getattr(t, 'dtype', type(t))} {tuple(getattr(t, 'shape', ()))} on {getattr(t, 'device', '?')}")
                 return t.data_ptr()
 
-            B = x_init.shape[0]
-            px = chk(x_init, (B, 6))
-            if shared:
-                T = traj_inputs.shape[0]
-                pk = chk(k_index, (B,), torch.int32)
-                pts, ptu = chk(traj_states, (T + 1, 6)), chk(traj_inputs, (T, 2))
-            else:
-                prs, pru = chk(ref_states, (B, N + 1, 6)), chk(ref_inputs, (B, N, 2))
-            pzw = chk(z_warm, (B, nz)) if z_warm is not None else None
-            pqw = chk(q_weights, (B, 6)) if q_weights is not None else None
-            prw = chk(r_weights, (B, 2)) if r_weights is not None else None
-            out = dict(
-                z=torch.empty((B, nz), dtype=torch.float64, device=dev) if want_z else None,
-                u0=torch.empty((B, 2), dtype=torch.float64, device=dev),
-                obj=torch.empty(B, dtype=torch.float64, device=dev),
-                kkt=torch.empty((B, 3), dtype=torch.float64, device=dev),
-                iters=torch.empty(B, dtype=torch.int32, device=dev),
-                status=torch.empty(B, dtype=torch.int32, device=dev),
-            )
-            ptr = lambda t: None if t is None else t.data_ptr()
+            def new(shape, dtype=f64):
+                return torch.empty(shape, dtype=dtype, device=dev)
+
             if stream is None:
                 stream = torch.cuda.current_stream(dev).cuda_stream
             h = self._handle(0)
         else:
-            x_init = np.ascontiguousarray(x_init, dtype=np.float64).reshape(-1, 6)
-            B = x_init.shape[0]
-            px = x_init.ctypes.data
-            keep = [x_init]
-            if shared:
-                traj_states = np.ascontiguousarray(traj_states, dtype=np.float64)
-                traj_inputs = np.ascontiguousarray(traj_inputs, dtype=np.float64)
-                k_index = np.ascontiguousarray(k_index, dtype=np.int32).reshape(B)
-                T = traj_inputs.shape[0]
-                assert traj_states.shape == (T + 1, 6) and traj_inputs.shape == (T, 2)
-                pk, pts, ptu = k_index.ctypes.data, traj_states.ctypes.data, traj_inputs.ctypes.data
-                keep += [traj_states, traj_inputs, k_index]
-            else:
-                ref_states = np.ascontiguousarray(ref_states, dtype=np.float64).reshape(B, N + 1, 6)
-                ref_inputs = np.ascontiguousarray(ref_inputs, dtype=np.float64).reshape(B, N, 2)
-                prs, pru = ref_states.ctypes.data, ref_inputs.ctypes.data
-                keep += [ref_states, ref_inputs]
-            pzw = None
-            if z_warm is not None:
-                z_warm = np.ascontiguousarray(z_warm, dtype=np.float64).reshape(B, nz)
-                pzw = z_warm.ctypes.data
-                keep.append(z_warm)
-            pqw = prw = None
-            if q_weights is not None:
-                q_weights = np.ascontiguousarray(q_weights, dtype=np.float64).reshape(B, 6)
-                r_weights = np.ascontiguousarray(r_weights, dtype=np.float64).reshape(B, 2)
-                pqw, prw = q_weights.ctypes.data, r_weights.ctypes.data
-                keep += [q_weights, r_weights]
-            out = dict(
-                z=np.empty((B, nz)) if want_z else None,
-                u0=np.empty((B, 2)),
-                obj=np.empty(B),
-                kkt=np.empty((B, 3)),
-                iters=np.empty(B, dtype=np.int32),
-                status=np.empty(B, dtype=np.int32),
-            )
-            ptr = lambda a: None if a is None else a.ctypes.data
+            f64, i32 = np.float64, np.int32
+
+            def arg(t, shape, dtype=f64, name="array"):
+                if _is_torch(t):  # torch CPU tensor (page-locked or not): used in place
+                    import torch
+
+                    want = torch.float64 if dtype is np.float64 else torch.int32
+                    if not (t.device.type == "cpu" and t.dtype == want and t.is_contiguous() and tuple(t.shape) == tuple(shape)):
+                        raise ValueError(f"{name}: expected a contiguous CPU {dtype.__name__} tensor of shape {tuple(shape)}")
+                    keep.append(t)
+                    return t.data_ptr()
+                a = np.ascontiguousarray(t, dtype=dtype)
+                if a.size != int(np.prod(shape)):
+                    raise ValueError(f"{name}: expected {int(np.prod(shape))} elements (shape {tuple(shape)}), got {a.shape}")
+                keep.append(a)
+                return a.ctypes.data
+
+            def new(shape, dtype=f64):
+                return np.empty(shape, dtype=dtype)
+
             stream = None
-            h = self._handle(FLAG_HOST_POINTERS)
-        if obstacles is not None and shared:
-            rc = self._L.ttmpc_obca_solve_batch_shared(
-                h, ctypes.byref(obstacles), B, px, pk, pts, ptu, T, ptr(out["z"]), ptr(out["u0"]), ptr(out["obj"]),
-                ptr(out["kkt"]), ptr(out["iters"]), ptr(out["status"]), stream)
-        elif obstacles is not None:
-            rc = self._L.ttmpc_obca_solve_batch(
-                h, ctypes.byref(obstacles), B, px, prs, pru, ptr(out["z"]), ptr(out["u0"]), ptr(out["obj"]),
-                ptr(out["kkt"]), ptr(out["iters"]), ptr(out["status"]), stream)
-        elif shared:
-            rc = self._L.ttmpc_solve_batch_shared(
-                h, B, px, pk, pts, ptu, T, pzw, ptr(out["z"]), ptr(out["u0"]), ptr(out["obj"]), ptr(out["kkt"]),
-                ptr(out["iters"]), ptr(out["status"]), stream)
-        elif pqw is not None:
-            rc = self._L.ttmpc_solve_batch_weighted(
-                h, B, px, prs, pru, pqw, prw, pzw, ptr(out["z"]), ptr(out["u0"]), ptr(out["obj"]), ptr(out["kkt"]),
-                ptr(out["iters"]), ptr(out["status"]), stream)
+            h = self._handle(FLAG_HOST_POINTERS | (FLAG_ASYNC_HOST if host_async else 0))
+        B = int(x_init.shape[0]) if hasattr(x_init, "shape") and len(x_init.shape) == 2 else int(np.asarray(x_init).size // 6)
+        px = arg(x_init, (B, 6), name="x_init")
+        F = 1
+        if shared:
+            ts_shape = tuple(traj_states.shape) if hasattr(traj_states, "shape") else np.asarray(traj_states).shape
+            if traj_index is not None:
+                if len(ts_shape) != 3:
+                    raise ValueError("with traj_index the trajectories are stacks traj_states [F,T+1,6], traj_inputs [F,T,2]")
+                F, T = int(ts_shape[0]), int(ts_shape[1]) - 1
+                pts, ptu = arg(traj_states, (F, T + 1, 6), name="traj_states"), arg(traj_inputs, (F, T, 2), name="traj_inputs")
+                pti = arg(traj_index, (B,), i32, name="traj_index")
+            else:
+                T = int(ts_shape[0]) - 1
+                pts, ptu = arg(traj_states, (T + 1, 6), name="traj_states"), arg(traj_inputs, (T, 2), name="traj_inputs")
+            pk = arg(k_index, (B,), i32, name="k_index")
         else:
-            rc = self._L.ttmpc_solve_batch(
-                h, B, px, prs, pru, pzw, ptr(out["z"]), ptr(out["u0"]), ptr(out["obj"]), ptr(out["kkt"]),
-                ptr(out["iters"]), ptr(out["status"]), stream)
+            prs, pru = arg(ref_states, (B, N + 1, 6), name="ref_states"), arg(ref_inputs, (B, N, 2), name="ref_inputs")
+        pzw = arg(z_warm, (B, nz), name="z_warm") if z_warm is not None else None
+        pqw = arg(q_weights, (B, 6), name="q_weights") if q_weights is not None else None
+        prw = arg(r_weights, (B, 2), name="r_weights") if r_weights is not None else None
+        shapes = dict(z=((B, nz), f64), u0=((B, 2), f64), obj=((B,), f64), kkt=((B, 3), f64), iters=((B,), i32), status=((B,), i32))
+        res, ptrs = {}, {}
+        for key, (shape, dtype) in shapes.items():
+            if (key == "z" and not want_z) or (key in ("kkt", "obj") and not want_kkt):
+                res[key], ptrs[key] = None, None
+                continue
+            buf = out.get(key) if out is not None else None
+            if buf is None:
+                buf = new(shape, dtype)
+            ptrs[key] = arg(buf, shape, dtype, name=f"out[{key}]")
+            res[key] = buf
+        o = [ptrs[k] for k in ("z", "u0", "obj", "kkt", "iters", "status")]
+        if obstacles is not None and shared:
+            rc = self._L.ttmpc_obca_solve_batch_shared(h, ctypes.byref(obstacles), B, px, pk, pts, ptu, T, *o, stream)
+        elif obstacles is not None:
+            rc = self._L.ttmpc_obca_solve_batch(h, ctypes.byref(obstacles), B, px, prs, pru, *o, stream)
+        elif shared and traj_index is not None:
+            rc = self._L.ttmpc_solve_batch_multi(h, B, px, pk, pti, pts, ptu, F, T, pzw, *o, stream)
+        elif shared:
+            rc = self._L.ttmpc_solve_batch_shared(h, B, px, pk, pts, ptu, T, pzw, *o, stream)
+        elif pqw is not None:
+            rc = self._L.ttmpc_solve_batch_weighted(h, B, px, prs, pru, pqw, prw, pzw, *o, stream)
+        else:
+            rc = self._L.ttmpc_solve_batch(h, B, px, prs, pru, pzw, *o, stream)
         self._check(h, rc, "ttmpc_solve_batch")
-        return out
+        if host_async and not on_device:
+            self._inflight = (getattr(self, "_inflight", []) + [keep])[-4:]  # inputs must outlive the queued copies
+        return res
 
     # ------------------------------------------------------------------ helpers of the closed-loop drivers
     def shift_warm_start(self, z, reference_bug: bool = False, stream=None):

@@ -19,6 +19,8 @@
  *   ttmpc_solve_batch_shared<- the window extraction of the closed-loop drivers
  *                              (simulation.py:485-499, simulation_nmpc.py:193-204) fused
  *                              with the solve: every problem tracks the same trajectory.
+ *   ttmpc_solve_batch_multi <- the same for F rigidly transformed copies of one trajectory: the batch
+ *                              driver fed by compare_sweep.py / test_cases.json (scenario families).
  *   ttmpc_shift_warm_start  <- TruckTrailerNMPC._shift_solution (mpc_control_nmpc.py:69-88).
  *   ttmpc_plant_step        <- update()/f_dyn of the drivers (simulation.py:34-48,167-199,
  *                              simulation_nmpc.py:94-105) for on-device closed loops.
@@ -34,9 +36,13 @@
  * All arithmetic is IEEE double.  No torch types, no C++ types: plain pointers and sizes.
  * Unless TTMPC_FLAG_HOST_POINTERS is set, every array pointer is a CUDA device pointer
  * owned by the caller (e.g. torch.Tensor.data_ptr()); the library only owns its private
- * scratch.  Calls are asynchronous on the supplied stream unless TTMPC_FLAG_SYNC is set
- * (host-pointer calls are always synchronous).  A handle must not be used concurrently
- * from several threads; distinct handles are independent.
+ * scratch.  Calls are asynchronous on the supplied stream unless TTMPC_FLAG_SYNC is set;
+ * consecutive calls through one handle are ordered on the device even when they are given
+ * different streams (they share the handle's scratch).  Host-pointer calls are synchronous
+ * unless TTMPC_FLAG_ASYNC_HOST is set (then ttmpc_sync() waits for the outputs); they run on
+ * the handle's own streams and ignore the stream argument.  Every entry point leaves the
+ * caller's current CUDA device unchanged.  A handle must not be used concurrently from
+ * several threads; distinct handles are independent.
  *
  * Return value: 0 on success, negative TTMPC_E_* otherwise; never throws, never exits.
  */
@@ -73,8 +79,12 @@ extern "C" {
 /* flags */
 #define TTMPC_FLAG_HOST_POINTERS 0x1u /* array arguments are host pointers (B=1 shim path)      */
 #define TTMPC_FLAG_SYNC 0x2u          /* cudaStreamSynchronize before returning                 */
-#define TTMPC_FLAG_SHIFT_REFERENCE_BUG 0x4u /* ttmpc_shift_warm_start reproduces the mis-sliced
-                                               tail of mpc_control_nmpc.py:83-87 bit for bit    */
+#define TTMPC_FLAG_ASYNC_HOST 0x8u    /* with HOST_POINTERS: a solve returns once its copy-in, kernels and
+                                         copy-out are queued on the handle's three internal streams; up to three
+                                         solves are in flight (a call first waits for the third-last one), so the
+                                         copy-in of batch t+1 and the copy-out of batch t-1 overlap the solve of
+                                         batch t.  Host buffers must stay untouched until ttmpc_sync() and should
+                                         be page-locked (pageable memory makes the copies synchronous).           */
 
 typedef struct ttmpc_config {
   int32_t horizon;          /* N, params['horizon'] (simulation.py:390), 1..TTMPC_MAX_HORIZON   */
@@ -138,6 +148,24 @@ int ttmpc_solve_batch_shared(ttmpc_handle* h, int64_t B, const double* x_init,
                              const double* traj_inputs, int32_t T, const double* z_warm,
                              double* z_out, double* u0_out, double* obj_out, double* kkt_out,
                              int32_t* iters_out, int32_t* status_out, void* cuda_stream);
+
+/* Shared-trajectory solve over F trajectories -- the batch driver's contract (compare_sweep.py shape: the scenario
+ * families of test_cases.json enter as rigid transforms of one reference trajectory): traj_states [F][T+1][6],
+ * traj_inputs [F][T][2]; problem i tracks trajectory traj_index[i] from window start k_index[i] (padding rules of
+ * simulation.py:485-499).  Per problem 56 B go in (x_init, k_index, traj_index) and, with z_out = obj_out = kkt_out =
+ * NULL, 24 B come out (u0, iterations, status). */
+int ttmpc_solve_batch_multi(ttmpc_handle* h, int64_t B, const double* x_init, const int32_t* k_index,
+                            const int32_t* traj_index, const double* traj_states, const double* traj_inputs,
+                            int32_t F, int32_t T, const double* z_warm, double* z_out, double* u0_out,
+                            double* obj_out, double* kkt_out, int32_t* iters_out, int32_t* status_out,
+                            void* cuda_stream);
+
+/* Wait until every host-pointer solve queued through this handle (TTMPC_FLAG_ASYNC_HOST) has delivered its outputs. */
+int ttmpc_sync(ttmpc_handle* h);
+
+/* Device-side duration (CUDA events on the handle's copy streams) of the last burst of host-pointer solves that
+ * ttmpc_sync() -- or a synchronous host-pointer call -- waited for: from the first copy-in to the last copy-out, ms. */
+double ttmpc_host_pipeline_ms(const ttmpc_handle* h);
 
 /* Obstacle set of the obstacle-aware controller MPCTrackingControlObs (mpc_control_obs.py:8-30): axis-aligned
  * rectangles {centre x, centre y, width, height} as produced by get_obstacles.py:5-33, body widths W1 / W2
