@@ -247,6 +247,8 @@ def simulate_batch(solver, S, U, x0, T_sim: float, dt: float, disturbance: dict 
     kidx = torch.empty(B, dtype=torch.int32, device=dev)
     z_prev = None
     hist = []
+    consec = torch.zeros(B, dtype=torch.int32, device=dev)   # consecutive failed solves (simulation_nmpc.py:207-216)
+    stopped = torch.zeros(B, dtype=torch.bool, device=dev)
     for step, k in enumerate(ks):
         kidx.fill_(int(k))
         meas = state
@@ -267,14 +269,19 @@ def simulate_batch(solver, S, U, x0, T_sim: float, dt: float, disturbance: dict 
         if variant == "nmpc" and disturbance is not None and std > 0:
             noise = (std * counter_normal(seed, 2 * step + 1, ids, 6)).contiguous()
             scale = dt
-        state = solver.plant_step(state, u.contiguous(), disturbance, noise, scale)
-        fails += (~ok).to(torch.int32)
-        iters_sum += r["iters"].to(torch.int64)
+        new_state = solver.plant_step(state, u.contiguous(), disturbance, noise, scale)
+        live = ~stopped   # a stopped run ("Too many consecutive NMPC failures", simulation_nmpc.py:212-216) stays where it is
+        state = torch.where(live[:, None], new_state, state)
+        fails += (live & ~ok).to(torch.int32)
+        iters_sum += torch.where(live, r["iters"], torch.zeros_like(r["iters"])).to(torch.int64)
         iters_max = torch.maximum(iters_max, r["iters"])
         max_psi = torch.maximum(max_psi, state[:, 3].abs())
         max_phi = torch.maximum(max_phi, state[:, 4].abs())
         ref_next = S_d[min(int(k) + 1, T)]
-        sq_err += ((state[:, :2] - ref_next[:2]) ** 2).sum(1)
+        sq_err += torch.where(live, ((state[:, :2] - ref_next[:2]) ** 2).sum(1), torch.zeros_like(sq_err))
+        if variant == "nmpc":
+            consec = torch.where(ok, torch.zeros_like(consec), consec + live.to(torch.int32))
+            stopped = stopped | (consec > 20)
         if record_every and step % record_every == 0:
             hist.append(state.clone())
     goal = S_d[T]

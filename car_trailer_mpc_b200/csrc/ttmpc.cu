@@ -348,7 +348,7 @@ struct EpisodeArgs {
 // been published (`steps_done`), which a lane checks by polling once per round -- it never blocks its warp.  When a
 // solve terminates the lane applies u_0 to the plant (disturbance model included), updates the metrics and publishes.
 // No host round trip and no cross-scenario barrier per step.
-constexpr int kRec = 10;  // x[6], max|psi|, sum sq. tracking error, iterations, failed solves
+constexpr int kRec = 11;  // x[6], max|psi|, sum sq. tracking error, iterations, failed solves, consecutive failed solves
 __device__ __forceinline__ int ld_volatile_i32(const int32_t* p) {
   int v;
   asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -369,9 +369,9 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
   const long long total = B * (long long)ea.steps;
   long long scen = -1;
   unsigned long long sid = 0;
-  bool active = false, waiting = false, exhausted = false;
+  bool active = false, waiting = false, exhausted = false, skip = false;
   int step = 0;
-  double x[NX], max_psi = 0.0, sq_err = 0.0, iters_sum = 0.0, fails = 0.0;
+  double x[NX], max_psi = 0.0, sq_err = 0.0, iters_sum = 0.0, fails = 0.0, consec = 0.0;
   Ipm st;
   Result res;
   for (;;) {
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
 #pragma unroll
         for (int j = 0; j < NX; j++) x[j] = ea.x0[scen * NX + j];
         max_psi = fabs(x[3]);
-        sq_err = iters_sum = fails = 0.0;
+        sq_err = iters_sum = fails = consec = 0.0;
       } else {
         const double* r = ea.rec + scen * kRec;
 #pragma unroll
@@ -409,7 +409,11 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
         sq_err = __ldcg(r + 7);
         iters_sum = __ldcg(r + 8);
         fails = __ldcg(r + 9);
+        consec = __ldcg(r + 10);
       }
+      // simulation_nmpc.py:212-216: more than 20 consecutive failed solves stop the run -- the remaining control steps
+      // of such a scenario are no-ops (the vehicle stays where it is, nothing is accumulated)
+      skip = (ea.variant == 1) && (consec > 20.0);
       const bool meas_noise = (ea.variant == 0) && ea.dist.on && ea.noise_std > 0.0;
 #pragma unroll
       for (int j = 0; j < NX; j++)
@@ -424,32 +428,38 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
 
     bool done = false;
     const bool warp_fresh = __any_sync(kFull, active && st.fresh);
-    if (active) done = ipm_backward<G, DQ, false, false>(p, s0, cy, in, scen, warp_fresh, st, res);
+    if (active && !skip) done = ipm_backward<G, DQ, false, false>(p, s0, cy, in, scen, warp_fresh, st, res);
     __syncthreads();
-    if (active && !done) done = ipm_step_rr<G, DQ, false>(p, s0, cy, st, res);
+    if (active && !done && !skip) done = ipm_step_rr<G, DQ, false>(p, s0, cy, st, res);
+    if (active && skip) done = true;
     __syncwarp();
 
     if (done) {
-      const bool ok = res.status <= ST_ACCEPTABLE;
-      double ua = ldr(s0, rW + 6), uw = ldr(s0, rW + 7);
-      if (!ok) {
-        fails += 1.0;
-        if (ea.variant == 1) ua = uw = 0.0;  // simulation_nmpc.py:211: zero control on failure
-      }
-      iters_sum += (double)res.iters;
-      double nz6[NX], y[NX];
-      const bool plant_noise = (ea.variant == 1) && ea.dist.on && ea.noise_std > 0.0;
-      if (plant_noise) {
+      if (!skip) {
+        const bool ok = res.status <= ST_ACCEPTABLE;
+        double ua = ldr(s0, rW + 6), uw = ldr(s0, rW + 7);
+        if (!ok) {
+          fails += 1.0;
+          consec += 1.0;
+          if (ea.variant == 1) ua = uw = 0.0;  // simulation_nmpc.py:211: zero control on failure
+        } else {
+          consec = 0.0;
+        }
+        iters_sum += (double)res.iters;
+        double nz6[NX], y[NX];
+        const bool plant_noise = (ea.variant == 1) && ea.dist.on && ea.noise_std > 0.0;
+        if (plant_noise) {
 #pragma unroll
-        for (int j = 0; j < NX; j++) nz6[j] = ea.noise_std * counter_normal(ea.seed, 2ull * step + 1ull, sid, j);
-      }
-      plant_step_dev(p, x, ua, uw, ea.dist, plant_noise ? nz6 : nullptr, p.dt, y);
+          for (int j = 0; j < NX; j++) nz6[j] = ea.noise_std * counter_normal(ea.seed, 2ull * step + 1ull, sid, j);
+        }
+        plant_step_dev(p, x, ua, uw, ea.dist, plant_noise ? nz6 : nullptr, p.dt, y);
 #pragma unroll
-      for (int j = 0; j < NX; j++) x[j] = y[j];
-      max_psi = fmax(max_psi, fabs(x[3]));
-      const int kn = min(ea.k_seq[step] + 1, ea.T);
-      const double ex = x[0] - ea.traj_states[(long long)kn * NX + 0], ey = x[1] - ea.traj_states[(long long)kn * NX + 1];
-      sq_err += ex * ex + ey * ey;
+        for (int j = 0; j < NX; j++) x[j] = y[j];
+        max_psi = fmax(max_psi, fabs(x[3]));
+        const int kn = min(ea.k_seq[step] + 1, ea.T);
+        const double ex = x[0] - ea.traj_states[(long long)kn * NX + 0], ey = x[1] - ea.traj_states[(long long)kn * NX + 1];
+        sq_err += ex * ex + ey * ey;
+      }
       if (step + 1 < ea.steps) {
         double* r = ea.rec + scen * kRec;
 #pragma unroll
@@ -458,6 +468,7 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
         __stcg(r + 7, sq_err);
         __stcg(r + 8, iters_sum);
         __stcg(r + 9, fails);
+        __stcg(r + 10, consec);
         __threadfence();  // publish the record before the step counter
         *(volatile int32_t*)(ea.steps_done + scen) = step + 1;
       } else {
@@ -1373,7 +1384,7 @@ int ttmpc_episode_batch(ttmpc_handle* h, int64_t B, const double* x0, const int6
   launch_shape(h, B, &blocks, &threads);
   int rc = ensure_scratch(h, (size_t)blocks * kSolveThreads);
   if (rc) return rc;
-  const size_t need = (size_t)B * ((NX + 10) * sizeof(double) + 2 * sizeof(int32_t));
+  const size_t need = (size_t)B * ((NX + kRec) * sizeof(double) + 2 * sizeof(int32_t));
   if (need > h->ep_cap) {
     if (h->ep_buf) cudaFree(h->ep_buf);
     h->ep_buf = nullptr;
@@ -1396,7 +1407,7 @@ int ttmpc_episode_batch(ttmpc_handle* h, int64_t B, const double* x0, const int6
   ea.seed = seed;
   ea.xmeas = (double*)h->ep_buf;
   ea.rec = ea.xmeas + (size_t)B * NX;
-  ea.kcur = (int32_t*)(ea.rec + (size_t)B * 10);
+  ea.kcur = (int32_t*)(ea.rec + (size_t)B * kRec);
   ea.steps_done = ea.kcur + B;
   cudaMemsetAsync(ea.steps_done, 0, (size_t)B * sizeof(int32_t), st);
   ea.metrics = metrics_out;

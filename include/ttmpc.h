@@ -210,7 +210,9 @@ int ttmpc_plant_step(ttmpc_handle* h, int64_t B, const double* q, const double* 
 
 /* B closed-loop episodes entirely on the device: the `while t <= T_sim` loop of simulation.py:484-560 (variant 0:
  * measurement noise on the state handed to the controller, simulation.py:513-517) or simulation_nmpc.py:192-255
- * (variant 1: plant noise*dt, zero control on a failed solve) for B independent vehicles tracking one trajectory.
+ * (variant 1: plant noise*dt, zero control on a failed solve, and -- simulation_nmpc.py:212-216 -- the run of a vehicle
+ * stops after more than 20 consecutive failed solves: it stays where it is for the remaining steps; unlike
+ * TruckTrailerNMPC every solve is a cold start at the window) for B independent vehicles tracking one trajectory.
  * Per control step s the window starts at k_seq[s] (the float-accumulated floor(t/dt) sequence, built on the host);
  * every solve is a cold start at the window (mpc_control.py:58-65).  disturb = HOST array {friction_coeff,
  * slippage_coeff, lateral_slip_gain, slip_angle_max, process_noise_std} (DISTURBANCE_PARAMS, simulation.py:26-32) or

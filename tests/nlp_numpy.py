@@ -83,10 +83,15 @@ def bounds(cfg):
     return lb, ub
 
 
-def kkt_certificate(cfg, z, x_init, Xr, Ur, active_tol=1e-6):
+def kkt_certificate(cfg, z, x_init, Xr, Ur, active_tol=1e-6, with_compl=False):
     """Solver-independent first-order check: with the active set read off z, find multipliers by
     least squares and return (stationarity residual inf-norm, constraint violation, bound violation,
-    most negative bound multiplier sign violation)."""
+    most negative bound multiplier sign violation [, complementarity max(multiplier * slack)]).
+
+    An interior-point solution at barrier parameter mu carries a multiplier mu/slack on every bounded variable, so
+    with a tight `active_tol` a variable that sits 3e-6 off its bound leaves mu/3e-6 ~ 3e-4 in the stationarity
+    residual; a wider active set (1e-3) lets such variables have a multiplier and `with_compl` then checks that
+    multiplier * slack is of the order of mu."""
     lb, ub = bounds(cfg)
     g = cost_grad(cfg, z, Xr, Ur)
     J = constraints_jac(cfg, z, x_init)
@@ -107,4 +112,8 @@ def kkt_certificate(cfg, z, x_init, Xr, Ur, active_tol=1e-6):
     neg = float(min(0.0, mult_b.min())) if mult_b.size else 0.0
     viol = np.abs(constraints(cfg, z, x_init)).max()
     bviol = max(0.0, float((lb - z)[np.isfinite(lb)].max()), float((z - ub)[np.isfinite(ub)].max()))
+    if with_compl:
+        slack = np.concatenate([(z - lb)[act_l], (ub - z)[act_u]])
+        compl = float(np.max(np.abs(mult_b) * np.maximum(slack, 0.0))) if mult_b.size else 0.0
+        return stat, viol, bviol, neg, compl
     return stat, viol, bviol, neg

@@ -88,6 +88,8 @@ def test_device_episode_kernel_vs_host_driven_loop(traj):
     rng = np.random.default_rng(9)
     B = 200   # more scenarios than one warp, ragged
     x0 = S[0][None] + rng.normal(0, 0.03, size=(B, 6)) * np.array([1, 1, 0.2, 0.2, 0.1, 1])
+    x0[7, 4] = 0.9    # steering angle beyond its bound, standing still: every solve fails, zero control keeps it there ->
+    x0[7, 5] = 0.0    # the nmpc variant stops this run after 21 consecutive failures (simulation_nmpc.py:212-216)
     x0_d = torch.from_numpy(x0).to(dev)
     ids = torch.arange(1000, 1000 + B, device=dev, dtype=torch.int64)
     solver = BatchSolver(cfg, 0)
@@ -107,6 +109,8 @@ def test_device_episode_kernel_vs_host_driven_loop(traj):
         assert np.array_equal(m[:, 5].astype(int), host["failures"].cpu().numpy())
         assert np.abs(m[:, 6] - host["mean_iters"].cpu().numpy()).max() < 0.05
         assert np.abs(m[:, 7] - host["rms_tracking_error"].cpu().numpy()).max() < 1e-6
+        if variant == "nmpc":
+            assert int(m[7, 5]) == 21 and int(host["failures"][7]) == 21     # stopped, not 81 failed steps
 
 
 def test_nmpc_shim_closed_loop_vs_oracle(traj):
