@@ -129,6 +129,9 @@ def nmpc_preset(horizon: int = 30, dt: float = 0.05, max_iter: int = 2000) -> Co
     return c
 
 
+OBCA_NO_RECOVERY = 1  # TTMPC_OBCA_NO_RECOVERY
+
+
 class Obstacles(ctypes.Structure):
     """Plain-old-data twin of ``struct ttmpc_obstacles``: the obstacle list of ``MPCTrackingControlObs``
     (python-files/mpc_control_obs.py:8-30) as ``{centre x, centre y, width, height}`` rows, the body widths
@@ -136,7 +139,7 @@ class Obstacles(ctypes.Structure):
 
     _fields_ = [
         ("count", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("flags", ctypes.c_int32),  # 0 or OBCA_NO_RECOVERY
         ("rect", (ctypes.c_double * 4) * MAX_OBSTACLES),
         ("W1", ctypes.c_double),
         ("W2", ctypes.c_double),
@@ -144,7 +147,8 @@ class Obstacles(ctypes.Structure):
     ]
 
     @classmethod
-    def from_list(cls, obstacle_list, W1: float = 3.05, W2: float = 2.95, d_min: float = 0.2) -> "Obstacles":
+    def from_list(cls, obstacle_list, W1: float = 3.05, W2: float = 2.95, d_min: float = 0.2,
+                  recover: bool = True) -> "Obstacles":
         """``obstacle_list``: dicts with ``center`` / ``width`` / ``height`` (get_obstacles.py:5-33) or 4-tuples."""
         if not 1 <= len(obstacle_list) <= MAX_OBSTACLES:
             raise ValueError(f"between 1 and {MAX_OBSTACLES} obstacles are supported")
@@ -158,6 +162,7 @@ class Obstacles(ctypes.Structure):
             for j in range(4):
                 o.rect[i][j] = float(row[j])
         o.W1, o.W2, o.d_min = float(W1), float(W2), float(d_min)
+        o.flags = 0 if recover else OBCA_NO_RECOVERY
         return o
 
     def as_list(self):

@@ -120,13 +120,19 @@ struct ObParams {
   double c2_lo, c2_up;       // relaxed bounds of the slacks of d1, d2
   double v_push, s_up_push, c2_lo_push, c2_up_push;  // Ipopt's push of the starting point into the interior
   double mu_guess, lam_guess[4];
+  int recover;               // recover from an exhausted line search with a fresh start at the current iterate
 };
+
+// a start is called colliding when a body is closer than d_min - kSepTol to an obstacle (the rows themselves tolerate
+// 1e-5 on the rotation rows and 1e-8 on the bounds)
+constexpr double kSepTol = 1e-4;
 
 inline int build_obparams(const ttmpc_config* c, const ttmpc_obstacles* ob, ObParams* o) {
   if (ob->count < 1 || ob->count > TTMPC_MAX_OBSTACLES) return TTMPC_E_INVAL;
   if (!(ob->W1 > 0.0) || !(ob->W2 > 0.0)) return TTMPC_E_INVAL;
   memset(o, 0, sizeof *o);
   o->P = 2 * ob->count;
+  o->recover = (ob->flags & TTMPC_OBCA_NO_RECOVERY) ? 0 : 1;
   for (int i = 0; i < ob->count; i++) {
     const double cx = ob->rect[i][0], cy = ob->rect[i][1], w = ob->rect[i][2], h = ob->rect[i][3];
     if (!(w > 0.0) || !(h > 0.0)) return TTMPC_E_INVAL;
@@ -196,6 +202,57 @@ TT_HD void pair_rows(const ObParams& o, int body, const double* b, const Trig& t
   d[1] = mx + c * lx + s * ly;
   d[2] = my - s * lx + c * ly;
   d[3] = sqrt(lx * lx + ly * ly) - 1.0;
+}
+
+// Feasibility restoration of one pair's block for a FIXED pose: the (mu, lam) that minimise the violation of the pair's
+// rows.  With ell = A_o' lam = kappa n (n a unit vector, 0 < kappa <= 1) and the minimal representation
+// lam = (ell_x+, ell_y+, ell_x-, ell_y-), mu = (m_x+, m_y+, m_x-, m_y-), m = -R' ell, rows d1, d2 vanish and
+// d0 = d_min - kappa sep(n), sep(n) = min_{q in body} n.q - max_{p in obstacle} n.p, the separation of the two
+// rectangles along n (OBCA's duals are the multipliers of that distance problem).  The separation is largest -- equal to
+// the distance of the rectangles when they are disjoint -- for a face normal of either rectangle or a vertex-to-vertex
+// direction: 24 candidates.  kappa is centred between the norm row (kappa <= 1) and the distance row (kappa >= d_min/sep).
+// Returns max_n sep(n).
+TT_HD double pair_restore(const ObParams& o, int body, const double* b, const Trig& t, double* v) {
+  double pcx, pcy, c, s;
+  if (body == 0) {
+    pcx = t.x + t.cth * o.hl1, pcy = t.y + t.sth * o.hl1, c = t.cth, s = t.sth;
+  } else {
+    pcx = t.x - t.cth * o.M - t.cal * o.hl2, pcy = t.y - t.sth * o.M - t.sal * o.hl2, c = t.cal, s = t.sal;
+  }
+  const double hl = o.g[body][0], hw = o.g[body][1];
+  // obstacle corners (b = (x_max, y_max, -x_min, -y_min)) and body corners
+  const double ox[2] = {-b[2], b[0]}, oy[2] = {-b[3], b[1]};
+  double bx[4], by[4];
+  for (int i = 0; i < 4; i++) {
+    const double sl = (i & 1) ? hl : -hl, sw = (i & 2) ? hw : -hw;
+    bx[i] = pcx + c * sl - s * sw, by[i] = pcy + s * sl + c * sw;
+  }
+  double best = -INFINITY, bnx = 1.0, bny = 0.0;
+  for (int cand = 0; cand < 24; cand++) {
+    double nx, ny;
+    if (cand < 4) {
+      nx = (cand == 0) ? 1.0 : (cand == 1) ? -1.0 : 0.0, ny = (cand == 2) ? 1.0 : (cand == 3) ? -1.0 : 0.0;
+    } else if (cand < 8) {
+      const double sg = (cand & 1) ? -1.0 : 1.0;
+      nx = (cand < 6) ? sg * c : -sg * s, ny = (cand < 6) ? sg * s : sg * c;
+    } else {
+      const int i = (cand - 8) & 3, j = (cand - 8) >> 2;
+      const double dx = bx[i] - ox[j & 1], dy = by[i] - oy[j >> 1];
+      const double nn = sqrt(dx * dx + dy * dy);
+      if (!(nn > 1e-12)) continue;
+      nx = dx / nn, ny = dy / nn;
+    }
+    const double mx = -(c * nx + s * ny), my = -(-s * nx + c * ny);
+    const double hO = b[0] * tt_max(nx, 0.0) + b[1] * tt_max(ny, 0.0) + b[2] * tt_max(-nx, 0.0) + b[3] * tt_max(-ny, 0.0);
+    const double sep = nx * pcx + ny * pcy - (hl * fabs(mx) + hw * fabs(my)) - hO;
+    if (sep > best) best = sep, bnx = nx, bny = ny;
+  }
+  const double kappa = (best > o.d_min) ? 0.5 * (1.0 + o.d_min / best) : 1.0;
+  const double lx = kappa * bnx, ly = kappa * bny;
+  const double mx = -(c * lx + s * ly), my = -(-s * lx + c * ly);
+  v[0] = tt_max(mx, 0.0), v[1] = tt_max(my, 0.0), v[2] = tt_max(-mx, 0.0), v[3] = tt_max(-my, 0.0);
+  v[4] = tt_max(lx, 0.0), v[5] = tt_max(ly, 0.0), v[6] = tt_max(-lx, 0.0), v[7] = tt_max(-ly, 0.0);
+  return best;  // the distance of the two rectangles when they are disjoint (<= 0: they overlap)
 }
 
 // Arithmetic with a fixed rounding sequence.  The rows d, their Jacobians and the slack barrier terms are evaluated at
@@ -454,6 +511,17 @@ TT_HD bool init_point(const Ctx& c0, const ProblemIn& in, long long b) {
     const double w = in.x_init[b * NX + j];
     if ((var_lo(p, j) && w < p.lo[j]) || (var_up(p, j) && w > p.up[j])) x0_bad = true;
   }
+  {  // Stage 0 is data, so its collision rows involve the stage's own duals only: they can be met iff every body keeps
+     // d_min to every obstacle at x_init (strong duality of the distance problem).  Otherwise the NLP has no feasible
+     // point (the reference prints "Cannot find a solution!"); same policy as an x_init outside its box.
+    double x[NX], dummy[8];
+    for (int j = 0; j < NX; j++) x[j] = in.x_init[b * NX + j];
+    Trig t;
+    stage_trig(x, t);
+    double worst = INFINITY;
+    OB_FOR_LANES(pj, o.P) worst = tt_min(worst, pair_restore(o, pj & 1, o.b[pj], t, dummy));
+    if (ob_min(worst) < o.d_min - kSepTol) x0_bad = true;
+  }
   Ctx c = c0;
 #if !defined(__CUDA_ARCH__)
   for (int wv = 0; wv < (WIDE ? c0.wd.nw : 1); wv++) {  // host: the warps of the CTA one after the other
@@ -501,6 +569,59 @@ TT_HD bool init_point(const Ctx& c0, const ProblemIn& in, long long b) {
 #endif
   ob_sync();
   return x0_bad;
+}
+
+// ---- recovery from a jammed line search: a fresh interior-point start AT THE CURRENT PRIMAL ITERATE -- every
+// variable pushed back into the interior of its bounds exactly like a starting point (Ipopt's bound_push / bound_frac),
+// slacks re-seated on their rows, all multipliers back to their initial values.  (Ipopt would enter its feasibility
+// restoration phase here and, on return, also resets the multipliers)
+template <bool WIDE>
+TT_HD void restart_point(const Ctx& c0) {
+  const Params& p = *c0.p;
+  const ObParams& o = *c0.o;
+  const int N = p.N;
+  Ctx c = c0;
+#if !defined(__CUDA_ARCH__)
+  for (int wv = 0; wv < (WIDE ? c0.wd.nw : 1); wv++) {  // host: the warps of the CTA one after the other
+  c.wd.wid = wv;
+#endif
+  for (int k = 0; k <= N; k++) {
+    if (WIDE && (k % c.wd.nw) != c.wd.wid) continue;
+    double* ps = c.stage(k);
+    double x[NX];
+    for (int j = 0; j < NW; j++) {
+      const bool on = (j < NX) || (k < N);
+      if (!on) continue;
+      double w = bld(ps, oW + j);
+      if (!(j < NX && k == 0)) w = tt_min(tt_max(w, p.lo_push[j]), p.up_push[j]);
+      ob_sync();
+      bst(ps, oW + j, w);
+      bst(ps, oZL + j, 1.0);
+      bst(ps, oZU + j, 1.0);
+      if (j < NX) x[j] = w;
+    }
+    for (int j = 0; j < NX; j++) bst(ps, oLAM + j, 0.0);
+    Trig t;
+    stage_trig(x, t);
+    OB_FOR_LANES(pj, o.P) {
+      double* pp = pair_ptr(ps, pj);
+      double v[8], d[4];
+      pair_restore(o, pj & 1, o.b[pj], t, v);
+      for (int i = 0; i < 8; i++) v[i] = tt_max(v[i], o.v_push);
+      pair_rows(o, pj & 1, o.b[pj], t, v, d);
+      for (int i = 0; i < 8; i++) pst(pp, qV + i, v[i]), pst(pp, qZV + i, 1.0);
+      pst(pp, qS + 0, tt_min(d[0], o.s_up_push));
+      pst(pp, qS + 1, tt_min(tt_max(d[1], o.c2_lo_push), o.c2_up_push));
+      pst(pp, qS + 2, tt_min(tt_max(d[2], o.c2_lo_push), o.c2_up_push));
+      pst(pp, qS + 3, tt_min(d[3], o.s_up_push));
+      for (int i = 0; i < 4; i++) pst(pp, qY + i, 0.0);
+      for (int i = 0; i < 6; i++) pst(pp, qZS + i, 1.0);
+    }
+  }
+#if !defined(__CUDA_ARCH__)
+  }
+#endif
+  ob_sync();
 }
 
 TT_HD double clampz(double z, double rs, double hi, double lo) { return tt_max(tt_min(z, hi * rs), lo * rs); }
@@ -1611,8 +1732,11 @@ struct Lane {
   Dir di;
   Stats st;
   int f_n, acc_count, ls_fail, iter, attempt, bt, n_b, m_eq;
+  int restarts;                  // recoveries from a jammed line search so far
   bool do_update, x0_bad, need_factor, need_dir, need_trial;
+  bool reinit;                   // the next head re-initialises the filter's theta limits (first iteration / after a recovery)
 };
+constexpr int kMaxRestarts = 3;
 
 TT_HD void lane_begin(const Params& p, const ObParams& o, bool x0_bad, Lane& L) {
   L.mu = p.mu_init;
@@ -1622,6 +1746,8 @@ TT_HD void lane_begin(const Params& p, const ObParams& o, bool x0_bad, Lane& L) 
   L.mu_step = L.mu;
   L.delta_step = 0.0;
   L.f_n = L.acc_count = L.ls_fail = L.iter = L.attempt = L.bt = 0;
+  L.restarts = 0;
+  L.reinit = true;
   L.n_b = p.n_b + (p.N + 1) * o.P * 14;  // + 8 local variables and 6 slack bounds per pair
   L.m_eq = p.m_eq + (p.N + 1) * o.P * 4;
   L.do_update = false;
@@ -1645,9 +1771,10 @@ TT_HD bool lane_head(const Ctx& c, Lane& L, Result& res) {
     lane_result(L, ST_NUMERIC, res);
     return true;
   }
-  if (L.iter == 0) {
+  if (L.reinit) {
     L.theta_max = kThetaMaxFact * fmax(1.0, st.theta);
     L.theta_min = kThetaMinFact * fmax(1.0, st.theta);
+    L.reinit = false;
   }
   const double s_d = fmax(kSMax, (st.lam1 + st.z1) / (double)(L.m_eq + L.n_b)) / kSMax;
   const double s_c = fmax(kSMax, st.z1 / (double)L.n_b) / kSMax;
@@ -1777,8 +1904,22 @@ TT_HD bool lane_trial_once(const Ctx& c, Lane& L, Result& res) {
     L.ls_a = a * kAlphaRed;
     return false;
   }
-  // Ipopt would switch to feasibility restoration here: take the shortest trial step, clear the filter, give up
-  // after 3 consecutive failures (same policy as oracle/ttmpc_oracle.c)
+  // The line search is exhausted: Ipopt would switch to feasibility restoration here.  Recovery (the same rule in
+  // oracle/obca_oracle.py): a fresh interior-point start at the current primal iterate (restart_point), at most
+  // kMaxRestarts times; then the shortest trial step with a cleared filter, giving up after 3 consecutive failures.
+  if (c.o->recover && L.restarts < kMaxRestarts) {
+    L.restarts++;
+    restart_point<WIDE>(c);
+    L.mu = c.p->mu_init;
+    L.tau = fmax(kTauMin, 1.0 - L.mu);
+    L.delta_last = 0.0;
+    L.f_n = L.acc_count = L.ls_fail = 0;
+    L.do_update = false;
+    L.reinit = true;
+    L.need_trial = false;
+    L.iter++;
+    return false;
+  }
   if (++L.ls_fail >= 3) {
     L.need_trial = false;
     lane_result(L, ST_LINESEARCH, res);

@@ -171,9 +171,14 @@ double ttmpc_host_pipeline_ms(const ttmpc_handle* h);
  * rectangles {centre x, centre y, width, height} as produced by get_obstacles.py:5-33, body widths W1 / W2
  * (params['W1'], params['W2'], simulation.py:393; the body lengths are L1, L2 of the config) and the safety distance
  * d_min (mpc_control_obs.py:67: 0.2). */
+/* A line search that runs out of backtracking steps is where Ipopt enters its feasibility-restoration phase
+ * (mpc_control_obs.py:193-197 leaves Ipopt's defaults on).  Default here: the solve recovers with a fresh interior-point
+ * start at the current primal iterate, up to 3 times per solve.  With this flag the solve takes the
+ * shortest trial step instead and reports TTMPC_ST_LINESEARCH after three consecutive failures (round-1 behaviour). */
+#define TTMPC_OBCA_NO_RECOVERY 1
 typedef struct ttmpc_obstacles {
   int32_t count; /* 1..TTMPC_MAX_OBSTACLES */
-  int32_t reserved;
+  int32_t flags; /* 0, or TTMPC_OBCA_NO_RECOVERY */
   double rect[TTMPC_MAX_OBSTACLES][4];
   double W1, W2, d_min;
 } ttmpc_obstacles;

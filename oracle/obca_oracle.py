@@ -21,8 +21,15 @@ tests or golden vectors for this path.  This file resta
     CUDA path eliminates the per-(stage, obstacle, body) blocks and runs a Riccati recursion; agreement between the
     two is the parity test.
 
-x_0 is data (x_0 = x_init is eliminated), as in oracle/ttmpc_oracle.c.  Sizes this finishes in seconds: horizon
-<= 12 with <= 11 obstacles, or horizon 40 with 1-2 obstacles.
+x_0 is data (x_0 = x_init is eliminated), as in oracle/ttmpc_oracle.c.  Sizes the dense path finishes in seconds:
+horizon <= 12 with <= 11 obstacles, or horizon 40 with 1-2 obstacles.
+
+``solve(..., linear_solver="banded")`` is the same algorithm with a linear solver that reaches the reference's own size
+(simulation.py:390: horizon 50, the 11 rectangles of obstacles.json -- an 18 664 x 18 664 KKT matrix): the unknowns are
+ordered stage by stage, which makes the KKT matrix block tridiagonal (366 x 366 blocks), and a generic block LDL' is run
+over it -- every pivot block (a Schur complement) is factorised dense by LAPACK, the inertia of the whole matrix is the
+sum of the pivot blocks' inertias (Haynsworth).  Still no knowledge of the (obstacle, body) pair structure, no Riccati
+recursion, nothing shared with the CUDA path; tests/test_obca_cpu.py checks that it walks the dense path's iterates.
 """
 from __future__ import annotations
 
@@ -42,6 +49,8 @@ D_MIN = 0.2  # mpc_control_obs.py:67
 C2_HALF_WIDTH = 1e-5  # mpc_control_obs.py:120-123
 MU_GUESS = 100.0
 LAM_GUESS = np.array([100.0, 105.0, 110.0, 115.0])  # mpc_control_obs.py:226-237
+MAX_RESTARTS = 3  # recoveries from an exhausted line search per solve
+SEP_TOL = 1e-4    # a start is colliding when a body is closer than d_min - SEP_TOL to an obstacle
 
 
 def model_f(q, u, L1, L2, M):
@@ -140,6 +149,38 @@ class Pair:
         c2 = m + np.array([c * ell[0] + s * ell[1], -s * ell[0] + c * ell[1]])
         c3 = np.sqrt(ell @ ell) - 1.0
         return np.array([c1, c2[0], c2[1], c3])
+
+    def corners(self, xt):
+        """the body's corners (truck_trailer_model.py:31-72) and the obstacle's, as rows"""
+        pc, _, _, alpha = self.centre(xt)
+        R = np.array([[np.cos(alpha), -np.sin(alpha)], [np.sin(alpha), np.cos(alpha)]])
+        loc = np.array([[sx * self.g[0], sy * self.g[1]] for sy in (-1, 1) for sx in (-1, 1)])
+        box = np.array([[x, y] for y in (-self.b[3], self.b[1]) for x in (-self.b[2], self.b[0])])
+        return pc + loc @ R.T, box, R
+
+    def restore(self, xt):
+        """Recovery of the pair's block for a fixed pose: the duals are the multipliers of the
+        distance problem between the two rectangles.  For a unit vector n, sep(n) = min over the body of n.q - max over
+        the obstacle of n.p; it is largest (= the distance when the rectangles are disjoint) for a face normal of either
+        rectangle or a vertex-to-vertex direction.  With ell = A_o' lam = kappa n and m = G' mu = -R' ell in their
+        minimal non-negative representation, rows c2 vanish and c1 = d_min - kappa sep; kappa is centred between
+        c3 (kappa <= 1) and c1 (kappa >= d_min / sep).  Returns (v, sep)."""
+        body, box, R = self.corners(xt)
+        cand = [np.array(a, float) for a in ((1, 0), (-1, 0), (0, 1), (0, -1))]
+        cand += [sg * R[:, i] for i in (0, 1) for sg in (1.0, -1.0)]
+        for q in body:
+            for pt in box:
+                d = q - pt
+                if np.linalg.norm(d) > 1e-12:
+                    cand.append(d / np.linalg.norm(d))
+        seps = [(body @ n).min() - (box @ n).max() for n in cand]
+        i = int(np.argmax(seps))
+        sep, n = seps[i], cand[i]
+        kappa = 0.5 * (1.0 + D_MIN / sep) if sep > D_MIN else 1.0
+        ell = kappa * n
+        m = -R.T @ ell
+        pos = lambda a: np.array([max(a[0], 0.0), max(a[1], 0.0), max(-a[0], 0.0), max(-a[1], 0.0)])
+        return np.concatenate([pos(m), pos(ell)]), sep
 
     def jac(self, xt, v):
         """Jx (4x4) wrt xt, Jv (4x8) wrt (mu, lam)"""
@@ -288,6 +329,27 @@ class ObcaNlp:
                 w[self.isl(k, j)] = pr.rows(xt, w[self.iv(k, j)])
         return self.push_inside(w)
 
+    def restored_point(self, w, x_init):
+        """Recovery from an exhausted line search (where Ipopt would enter feasibility restoration): states and inputs
+        stay, the OBCA duals of every pair are replaced by the exact minimiser of their rows' violation for the
+        current pose (Pair.restore), slacks are re-seated on their rows, everything is pushed inside like a starting
+        point."""
+        w = self.push_inside(w)
+        for k in range(self.N + 1):
+            xt = self.state(w, k, x_init)[:4]
+            for j, pr in enumerate(self.pairs):
+                w[self.iv(k, j)] = pr.restore(xt)[0]
+        w = self.push_inside(w)
+        for k in range(self.N + 1):
+            xt = self.state(w, k, x_init)[:4]
+            for j, pr in enumerate(self.pairs):
+                w[self.isl(k, j)] = pr.rows(xt, w[self.iv(k, j)])
+        return self.push_inside(w)
+
+    def start_clearance(self, x_init):
+        """smallest body-obstacle distance at x_init: stage 0 is data, so below d_min the NLP has no feasible point"""
+        return min(pr.restore(np.asarray(x_init, float)[:4])[1] for pr in self.pairs)
+
     def objective(self, w, x_init, ref_states, ref_inputs):
         J = 0.0
         for k in range(1, self.N + 1):  # the k = 0 term is a constant of the data x_init (kept for reporting below)
@@ -363,6 +425,156 @@ class ObcaNlp:
         return H
 
 
+def stage_blocks(nlp: "ObcaNlp", w, y, x_init):
+    """Per stage k: (H_k, Jp_k, Jd_k) = Hessian of the Lagrangian w.r.t. the stage's variables, Jacobian of the stage's
+    collision rows, Jacobian of the dynamics rows c_{k+1} w.r.t. the stage's variables (None for k = N).  The same
+    formulas as ObcaNlp.jacobian / hessian, written into stage-local matrices."""
+    out = []
+    B = np.zeros((6, 2))
+    B[4, 1] = B[5, 0] = nlp.dt
+    P = nlp.P
+    for k in range(nlp.N + 1):
+        o, nk = nlp.off[k], (nlp.off[k + 1] if k < nlp.N else nlp.n) - nlp.off[k]
+        H = np.zeros((nk, nk))
+        Jp = np.zeros((4 * P, nk))
+        lx = nlp.ix(k) - o if k >= 1 else None
+        if k >= 1:
+            H[np.ix_(lx, lx)] += 2.0 * nlp.Q
+        if k < nlp.N:
+            lu_ = nlp.iu(k) - o
+            H[np.ix_(lu_, lu_)] += 2.0 * nlp.R
+        Jd = None
+        if k < nlp.N:
+            Jd = np.zeros((6, nk))
+            xp = nlp.state(w, k, x_init)
+            if k >= 1:
+                Jd[:, lx] = -(np.eye(6) + nlp.dt * model_jac(xp, nlp.L1, nlp.L2, nlp.M))
+                H[np.ix_(lx, lx)] -= nlp.dt * model_hess(xp, y[nlp.ic_dyn(k + 1)], nlp.L1, nlp.L2, nlp.M)
+            Jd[:, lu_] = -B
+        xt = nlp.state(w, k, x_init)[:4]
+        for j, pr in enumerate(nlp.pairs):
+            iv, isl = nlp.iv(k, j) - o, nlp.isl(k, j) - o
+            v = w[nlp.iv(k, j)]
+            Jx, Jv = pr.jac(xt, v)
+            r = np.arange(4 * j, 4 * j + 4)
+            Jp[np.ix_(r, iv)] = Jv
+            Jp[np.ix_(r, isl)] = -np.eye(4)
+            Wxx, Wxv, Wvv = pr.hess(xt, v, y[nlp.ic_pair(k, j)])
+            H[np.ix_(iv, iv)] += Wvv
+            if k >= 1:
+                Jp[np.ix_(r, lx[:4])] = Jx
+                H[np.ix_(lx[:4], lx[:4])] += Wxx
+                H[np.ix_(lx[:4], iv)] += Wxv
+                H[np.ix_(iv, lx[:4])] += Wxv.T
+        out.append((H, Jp, Jd))
+    return out
+
+
+class BandedKKT:
+    """Block-tridiagonal LDL' of K = [[H + diag(d), J'], [J, 0]] with the unknowns ordered stage by stage:
+    block k = (w_k, y_pair_k, y_dyn_k) -- the multipliers of c_k = x_k - x_{k-1} - dt f(x_{k-1}, u_{k-1}) sit with x_k,
+    on which that row has an identity Jacobian, so every pivot block has full-rank constraint rows.  Consecutive
+    blocks are coupled through d c_k / d w_{k-1} only."""
+
+    def __init__(self, nlp: "ObcaNlp", blocks, diag):
+        self.nlp = nlp
+        N, P = nlp.N, nlp.P
+        self.wi, self.yi, self.lu, self.Jd = [], [], [], []
+        neg = zero = 0
+        for k in range(N + 1):
+            H, Jp, Jd = blocks[k]
+            o = nlp.off[k]
+            nk = H.shape[0]
+            wi = np.arange(o, o + nk)
+            yi = np.concatenate([nlp.ic_pair(k, j) for j in range(P)] + ([nlp.ic_dyn(k)] if k >= 1 else []))
+            if k >= 1:
+                E = np.zeros((6, nk))
+                E[:, nlp.ix(k) - o] = np.eye(6)
+                Jk = np.vstack([Jp, E])
+            else:
+                Jk = Jp
+            mk = Jk.shape[0]
+            Dk = np.zeros((nk + mk, nk + mk))
+            Dk[:nk, :nk] = H + np.diag(diag[wi])
+            Dk[:nk, nk:] = Jk.T
+            Dk[nk:, :nk] = Jk
+            if k >= 1:  # Schur complement of the previous pivot block: lands on the (y_dyn_k, y_dyn_k) corner
+                Jprev = self.Jd[k - 1]
+                npv = Jprev.shape[1]
+                rhs = np.zeros((self.lu[k - 1][0].shape[0], 6))
+                rhs[:npv, :] = Jprev.T
+                X = sla.lu_solve(self.lu[k - 1], rhs)[:npv, :]
+                corr = Jprev @ X
+                Dk[-6:, -6:] -= 0.5 * (corr + corr.T)
+            l_, d_, perm = sla.ldl(Dk, lower=True)
+            ng, zr = _inertia(l_, d_, perm)
+            neg += ng
+            zero += zr
+            self.wi.append(wi)
+            self.yi.append(yi)
+            self.lu.append(sla.lu_factor(Dk))
+            self.Jd.append(Jd)
+        self.neg, self.zero = neg, zero
+
+    def solve(self, rhs):
+        """rhs, solution in the global ordering (w; y)"""
+        nlp = self.nlp
+        n, N = nlp.n, nlp.N
+        b = [np.concatenate([rhs[self.wi[k]], rhs[n + self.yi[k]]]) for k in range(N + 1)]
+        for k in range(1, N + 1):  # forward: b_k -= C_k S_{k-1}^-1 b_{k-1}
+            Jprev = self.Jd[k - 1]
+            t = sla.lu_solve(self.lu[k - 1], b[k - 1])
+            b[k][-6:] -= Jprev @ t[:Jprev.shape[1]]
+        x = [None] * (N + 1)
+        x[N] = sla.lu_solve(self.lu[N], b[N])
+        for k in range(N - 1, -1, -1):  # backward: x_k = S_k^-1 (b_k - C_{k+1}' x_{k+1})
+            r = b[k].copy()
+            r[:self.Jd[k].shape[1]] -= self.Jd[k].T @ x[k + 1][-6:]
+            x[k] = sla.lu_solve(self.lu[k], r)
+        sol = np.zeros_like(rhs)
+        for k in range(N + 1):
+            nk = len(self.wi[k])
+            sol[self.wi[k]] = x[k][:nk]
+            sol[n + self.yi[k]] = x[k][nk:]
+        return sol
+
+
+def banded_matvec(nlp: "ObcaNlp", blocks, diag, vec):
+    """K @ vec without assembling K"""
+    n, N, P = nlp.n, nlp.N, nlp.P
+    out = np.zeros_like(vec)
+    for k in range(N + 1):
+        H, Jp, Jd = blocks[k]
+        o = nlp.off[k]
+        nk = H.shape[0]
+        wi = np.arange(o, o + nk)
+        yp = np.concatenate([nlp.ic_pair(k, j) for j in range(P)])
+        out[wi] += (H + np.diag(diag[wi])) @ vec[wi] + Jp.T @ vec[n + yp]
+        out[n + yp] += Jp @ vec[wi]
+        if Jd is not None:
+            yd = nlp.ic_dyn(k + 1)
+            out[wi] += Jd.T @ vec[n + yd]
+            out[n + yd] += Jd @ vec[wi] + vec[nlp.ix(k + 1)]
+            out[nlp.ix(k + 1)] += vec[n + yd]
+    return out
+
+
+def banded_jt_times(nlp: "ObcaNlp", blocks, y):
+    """J' y"""
+    out = np.zeros(nlp.n)
+    N, P = nlp.N, nlp.P
+    for k in range(N + 1):
+        H, Jp, Jd = blocks[k]
+        wi = np.arange(nlp.off[k], nlp.off[k] + H.shape[0])
+        yp = np.concatenate([nlp.ic_pair(k, j) for j in range(P)])
+        out[wi] += Jp.T @ y[yp]
+        if Jd is not None:
+            yd = nlp.ic_dyn(k + 1)
+            out[wi] += Jd.T @ y[yd]
+            out[nlp.ix(k + 1)] += y[yd]
+    return out
+
+
 def _inertia(lu, d, piv):
     """number of negative / zero eigenvalues of the block-diagonal D of an LDL' factorisation"""
     ev = np.linalg.eigvalsh(d) if False else None
@@ -383,7 +595,7 @@ def _inertia(lu, d, piv):
 
 
 def solve(nlp: ObcaNlp, x_init, ref_states, ref_inputs, tol=1e-8, acc_tol=1e-6, acc_iter=15, max_iter=5000,
-          mu_init=0.1, verbose=False):
+          mu_init=0.1, verbose=False, linear_solver="dense", recover=True):
     """Returns dict(states[N+1,6], inputs[N,2], obj, iters, status, kkt=(dual_inf, constr_viol, compl), w)."""
     x_init = np.asarray(x_init, float)
     ref_states = np.asarray(ref_states, float).reshape(nlp.N + 1, 6)
@@ -404,6 +616,9 @@ def solve(nlp: ObcaNlp, x_init, ref_states, ref_inputs, tol=1e-8, acc_tol=1e-6, 
     status = -1
     theta_max = theta_min = 0.0
     x0_bad = bool(np.any(x_init < nlp.x_lb) or np.any(x_init > nlp.x_ub))
+    x0_bad = x0_bad or nlp.start_clearance(x_init) < D_MIN - SEP_TOL  # stage 0 collides: no feasible point
+    restarts = 0
+    reinit = True
 
     def slacks(wv):
         return np.where(hl, wv - nlp.lo, 1.0), np.where(hu, nlp.up - wv, 1.0)
@@ -418,16 +633,23 @@ def solve(nlp: ObcaNlp, x_init, ref_states, ref_inputs, tol=1e-8, acc_tol=1e-6, 
     while True:
         c = nlp.constraints(w, x_init)
         g = nlp.grad(w, ref_states, ref_inputs)
-        Jm = nlp.jacobian(w, x_init)
+        banded = linear_solver == "banded"
+        if banded:
+            blocks = stage_blocks(nlp, w, y, x_init)
+            Jty = banded_jt_times(nlp, blocks, y)
+        else:
+            Jm = nlp.jacobian(w, x_init)
+            Jty = Jm.T @ y
         sl, su = slacks(w)
         theta = np.abs(c).sum()
         if not np.isfinite(theta) or not np.all(np.isfinite(w)):
             status = 4
             break
-        if it == 0:
+        if reinit:
             theta_max = THETA_MAX_FACT * max(1.0, theta)
             theta_min = THETA_MIN_FACT * max(1.0, theta)
-        rd = g + Jm.T @ y - zl + zu
+            reinit = False
+        rd = g + Jty - zl + zu
         rd_inf = np.abs(rd).max()
         cinf = np.abs(c).max()
         comp = np.concatenate([(sl * zl)[hl], (su * zu)[hu]])
@@ -466,17 +688,22 @@ def solve(nlp: ObcaNlp, x_init, ref_states, ref_inputs, tol=1e-8, acc_tol=1e-6, 
         # ---- KKT system, dense LDL', inertia-correcting regularisation ----
         sig = np.where(hl, zl / sl, 0.0) + np.where(hu, zu / su, 0.0)
         gphi = g - np.where(hl, mu / sl, 0.0) + np.where(hu, mu / su, 0.0)
-        H = nlp.hessian(w, y, x_init)
-        K = np.zeros((n + m, n + m))
-        K[:n, n:] = Jm.T
-        K[n:, :n] = Jm
         rhs = -np.concatenate([gphi, c])
+        if not banded:
+            H = nlp.hessian(w, y, x_init)
+            K = np.zeros((n + m, n + m))
+            K[:n, n:] = Jm.T
+            K[n:, :n] = Jm
         delta = 0.0
         ok = False
         for _ in range(40):
-            K[:n, :n] = H + np.diag(sig + delta)
-            lu, d, perm = sla.ldl(K, lower=True)
-            neg, zero = _inertia(lu, d, perm)
+            if banded:
+                fac = BandedKKT(nlp, blocks, sig + delta)
+                neg, zero = fac.neg, fac.zero
+            else:
+                K[:n, :n] = H + np.diag(sig + delta)
+                lu, d, perm = sla.ldl(K, lower=True)
+                neg, zero = _inertia(lu, d, perm)
             if neg == m and zero == 0:
                 ok = True
                 break
@@ -489,8 +716,12 @@ def solve(nlp: ObcaNlp, x_init, ref_states, ref_inputs, tol=1e-8, acc_tol=1e-6, 
             break
         if delta > 0:
             delta_last = delta
-        sol = np.linalg.solve(K, rhs)
-        sol += np.linalg.solve(K, rhs - K @ sol)  # one step of iterative refinement
+        if banded:
+            sol = fac.solve(rhs)
+            sol += fac.solve(rhs - banded_matvec(nlp, blocks, sig + delta, sol))  # one step of iterative refinement
+        else:
+            sol = np.linalg.solve(K, rhs)
+            sol += np.linalg.solve(K, rhs - K @ sol)  # one step of iterative refinement
         dw, yp = sol[:n], sol[n:]
         dzl = np.where(hl, mu / sl - zl - zl / sl * dw, 0.0)
         dzu = np.where(hu, mu / su - zu + zu / su * dw, 0.0)
@@ -534,6 +765,22 @@ def solve(nlp: ObcaNlp, x_init, ref_states, ref_inputs, tol=1e-8, acc_tol=1e-6, 
                 alpha *= ALPHA_RED
         if verbose:
             print(f"      delta {delta:.1e} a_pr {a_pr:.3e} a_du {a_du:.3e} alpha {alpha:.3e} gphi_d {gphi_d:.3e} acc {accepted}")
+        if not accepted and recover and restarts < MAX_RESTARTS:
+            # the line search is exhausted: Ipopt would enter feasibility restoration.  Recovery: restored point, all
+            # multipliers and the barrier parameter back to their initial values, empty filter.
+            restarts += 1
+            w = nlp.restored_point(w, x_init)
+            y = np.zeros(m)
+            zl = np.where(hl, 1.0, 0.0)
+            zu = np.where(hu, 1.0, 0.0)
+            mu = mu_init
+            tau = max(TAU_MIN, 1.0 - mu)
+            delta_last = 0.0
+            filt = []
+            acc_count = ls_fail = 0
+            reinit = True
+            it += 1
+            continue
         if not accepted:
             ls_fail += 1
             if ls_fail >= 3:
@@ -557,4 +804,4 @@ def solve(nlp: ObcaNlp, x_init, ref_states, ref_inputs, tol=1e-8, acc_tol=1e-6, 
     states = np.vstack([x_init] + [w[nlp.ix(k)] for k in range(1, nlp.N + 1)])
     inputs = np.vstack([w[nlp.iu(k)] for k in range(nlp.N)])
     return dict(states=states, inputs=inputs, obj=nlp.objective(w, x_init, ref_states, ref_inputs), iters=it,
-                status=status, kkt=(rd_inf, cinf, cmax), w=w, y=y)
+                status=status, kkt=(rd_inf, cinf, cmax), w=w, y=y, restarts=restarts)

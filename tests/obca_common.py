@@ -12,9 +12,12 @@ GOLD_OBCA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "
 Z_TOL = 1e-6
 
 
-def golden_cases():
-    g = np.load(GOLD_OBCA)
-    names = sorted({k.split("/")[0] for k in g.files})
+GOLD_OBCA_FULL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "obca_cases_full.npz")
+
+
+def golden_cases(path=GOLD_OBCA):
+    g = np.load(path)
+    names = sorted({k.split("/")[0] for k in g.files if "/" in k})
     out = []
     for n in names:
         c = {k.split("/")[1]: g[k] for k in g.files if k.startswith(n + "/")}

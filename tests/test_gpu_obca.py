@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import geometry
-from obca_common import Z_TOL, case_problem, golden_cases, split_z
+from obca_common import GOLD_OBCA_FULL, Z_TOL, case_problem, golden_cases, split_z
 from parity import OBJ_REL_TOL, U0_ABS_TOL, VIOL_TOL
 
 from car_trailer_mpc_b200 import problem as pb
@@ -20,6 +20,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 
 pytestmark = pytest.mark.gpu
 CASES = golden_cases()
+FULL = golden_cases(GOLD_OBCA_FULL)
 LOT = [(o["center"][0], o["center"][1], o["width"], o["height"]) for o in parking_lot_obstacles()]
 
 
@@ -48,6 +49,29 @@ def test_gpu_matches_dense_oracle_golden(c):
     assert abs(r["obj"][0] - c["obj"]) <= OBJ_REL_TOL * abs(c["obj"])
     assert np.abs(xs - c["states"]).max() <= Z_TOL and np.abs(us - c["inputs"]).max() <= Z_TOL
     assert np.array_equal(xs[0], c["x_init"])
+
+
+@pytest.mark.parametrize("wide_max", ["0", None], ids=["warp_per_problem", "cta_per_problem"])
+@pytest.mark.parametrize("c", FULL, ids=[c["name"] for c in FULL])
+def test_gpu_matches_oracle_at_the_reference_size(c, wide_max, monkeypatch):
+    """Config 4's own size (simulation.py:390: horizon 50 / 40, the 11 rectangles of obstacles.json, one case with a twelfth
+    obstacle and active rows, one in which the oracle recovers from an exhausted line search): both GPU kernels, through
+    the C ABI, against the oracle's block-tridiagonal LDL' solutions (tools/make_golden_obca_full.py)."""
+    if wide_max is None:
+        monkeypatch.delenv("TTMPC_OBCA_WIDE_MAX", raising=False)
+    else:
+        monkeypatch.setenv("TTMPC_OBCA_WIDE_MAX", wide_max)
+    cfg, obs = case_problem(c)
+    cfg.max_iter = 400
+    sv = solver(cfg)
+    r = sv.solve_obca(obs, c["x_init"][None], c["ref_states"][None], c["ref_inputs"][None])
+    assert sv.kernel_launches()["ttmpc_obca_kernel" if wide_max == "0" else "ttmpc_obca_wide_kernel"] == 1
+    assert r["status"][0] == 0
+    xs, us = split_z(r["z"][0], cfg.horizon)
+    assert np.abs(r["u0"][0] - c["inputs"][0]).max() <= U0_ABS_TOL
+    assert abs(r["obj"][0] - c["obj"]) <= OBJ_REL_TOL * abs(c["obj"])
+    assert np.abs(xs - c["states"]).max() <= Z_TOL and np.abs(us - c["inputs"]).max() <= Z_TOL
+    assert r["kkt"][0][1] <= VIOL_TOL
 
 
 @pytest.mark.parametrize("wide_max", ["0", None], ids=["warp_per_problem", "cta_per_problem"])

@@ -41,7 +41,7 @@ def test_config_struct_matches_header(L):
 
 
 def test_obstacle_struct_matches_header():
-    """struct ttmpc_obstacles: {int32 count, int32 reserved, double rect[MAX][4], double W1, W2, d_min}."""
+    """struct ttmpc_obstacles: {int32 count, int32 flags, double rect[MAX][4], double W1, W2, d_min}."""
     from car_trailer_mpc_b200.config import MAX_OBSTACLES, Obstacles, parking_lot_obstacles
     hdr = open(os.path.join(ROOT, "include", "ttmpc.h")).read()
     assert int(re.search(r"#define TTMPC_MAX_OBSTACLES (\d+)", hdr).group(1)) == MAX_OBSTACLES
