@@ -32,7 +32,16 @@ namespace {
 #endif
 constexpr int kSolveThreads = TTMPC_SOLVE_THREADS;
 constexpr int kCopyUnroll = 6;
-constexpr size_t kSolveSmem = (size_t)kCarry * kSolveThreads * sizeof(double);  // 56 320 B of dynamic shared memory  // problem load / result store: global loads in flight per lane
+constexpr size_t kSolveSmem = (size_t)kCarry * kSolveThreads * sizeof(double);  // the lanes' carried state (backward sweep)
+// ttmpc_solve_kernel stages the rows of the stage its warps are about to process in shared memory (StageBulk): per warp a
+// 12 KB buffer, an mbarrier and its phase word, behind the carried state -- 227 392 B, one CTA per SM
+#ifndef TTMPC_STAGE_BULK
+#define TTMPC_STAGE_BULK 0
+#endif
+constexpr bool kBulkStage = (TTMPC_STAGE_BULK != 0) && !kSpecBuild;
+constexpr int kSolveWarps = kSolveThreads / 32;
+constexpr size_t kBulkSmem = kSolveSmem + (size_t)kSolveWarps * (kStageBufDoubles * sizeof(double) + 16);
+constexpr size_t kSolveKernelSmem = kBulkStage ? kBulkSmem : kSolveSmem;
 #ifndef TTMPC_MIN_BLOCKS
 #define TTMPC_MIN_BLOCKS 1
 #endif
@@ -125,7 +134,7 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
     ttmpc_solve_kernel(const __grid_constant__ Params p, double* __restrict__ scratch, long long B, ProblemIn in, SolveOut out,
                        unsigned long long* __restrict__ counter, const int32_t* __restrict__ order) {
   constexpr unsigned kFull = 0xffffffffu;
-  extern __shared__ double carried[];  // loop-carried state of the backward sweep, [kCarry entries][thread]
+  extern __shared__ __align__(128) double carried[];  // loop-carried state of the backward sweep, [kCarry entries][thread]
   const Carry cy{carried + threadIdx.x, kSolveThreads};
   const size_t slot = (size_t)blockIdx.x * kSolveThreads + threadIdx.x;
   double* s0 = slot_ptr(scratch, p.N, slot);
@@ -136,6 +145,18 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
   bool active = false, exhausted = false;
   Ipm st;
   Result res;
+#if TTMPC_STAGE_BULK && !TTMPC_SPECULATION
+  StageBulk sg;
+  {
+    const unsigned wid = threadIdx.x >> 5;
+    double* bufs = carried + (size_t)kCarry * kSolveThreads;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(bufs + (size_t)kSolveWarps * kStageBufDoubles);
+    unsigned* phases = reinterpret_cast<unsigned*>(bars + kSolveWarps);
+    sg.init(bufs + (size_t)wid * kStageBufDoubles, bars + wid, phases + wid, lane);
+  }
+#else
+  StageDirect sg;
+#endif
   for (;;) {
     // ---- refill: lanes without work take the next problems from the queue (one atomic per warp)
     const unsigned need = __ballot_sync(kFull, !active);
@@ -162,12 +183,14 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
     // ---- one interior-point iteration for every lane that has a problem
     bool done = false;
     const bool warp_fresh = __any_sync(kFull, active && st.fresh);
-    if (active) done = ipm_backward<G, DQ, PW>(p, s0, cy, in, prob, warp_fresh, st, res);
+    const unsigned grp1 = __ballot_sync(kFull, active);  // the lanes that run this round's sweeps together
+    if (active) done = ipm_backward<G, DQ, PW, true>(p, s0, cy, sg, grp1, in, prob, warp_fresh, st, res);
 #if TTMPC_SPECULATION
     if (active && !done && st.fresh) atomicAdd(counter + 15, 1ull);  // diagnostic: a speculative step was rejected (restart)
 #endif
     __syncthreads();
-    if (active && !done) done = ipm_step<G, DQ, PW>(p, s0, cy, st, res);
+    const unsigned grp2 = __ballot_sync(kFull, active && !done);
+    if (active && !done) done = ipm_step<G, DQ, PW>(p, s0, cy, sg, grp2, st, res);
     __syncwarp();
 
     // ---- finished lanes: scalars by the owner, the decision vector by the whole warp (coalesced z_out rows)
@@ -198,7 +221,8 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
 #pragma unroll
           for (int u = 0; u < kCopyUnroll; u++) {
             const int e = e0 + 32 * u;
-            if (e < nz) v[u] = ldr(sl + (size_t)(e >> 3) * kStageStride, rW + (e & 7));
+            // read-once stream: straight from L2 (ld.cg), the iterate rows stay out of L1
+            if (e < nz) v[u] = __ldcg(sl + (size_t)(e >> 3) * kStageStride + (size_t)(rW + (e & 7)) * kBank);
           }
 #pragma unroll
           for (int u = 0; u < kCopyUnroll; u++) {
@@ -428,7 +452,8 @@ __global__ void __launch_bounds__(kSolveThreads, TTMPC_MIN_BLOCKS)
 
     bool done = false;
     const bool warp_fresh = __any_sync(kFull, active && st.fresh);
-    if (active && !skip) done = ipm_backward<G, DQ, false, false>(p, s0, cy, in, scen, warp_fresh, st, res);
+    StageDirect sg;
+    if (active && !skip) done = ipm_backward<G, DQ, false, false>(p, s0, cy, sg, 1u, in, scen, warp_fresh, st, res);
     __syncthreads();
     if (active && !done && !skip) done = ipm_step_rr<G, DQ, false>(p, s0, cy, st, res);
     if (active && skip) done = true;
@@ -792,8 +817,9 @@ int ttmpc_create(const ttmpc_config* cfg, int device, ttmpc_handle** out) {
   h->device = device;
   int sms = 0, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  ce = cudaFuncSetAttribute(solve_kernel_for(p), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmem);
-  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel_for(p), kSolveThreads, kSolveSmem);
+  ce = cudaFuncSetAttribute(solve_kernel_for(p), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveKernelSmem);
+  if (ce == cudaSuccess)
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel_for(p), kSolveThreads, kSolveKernelSmem);
   if (ce != cudaSuccess || sms <= 0 || per_sm <= 0) {
     delete h;
     return TTMPC_E_CUDA;
@@ -993,8 +1019,9 @@ static int solve_device(ttmpc_handle* h, long long B, const ProblemIn& in, const
     if (rc) return rc;
   }
   const bool weighted = in.q_w != nullptr;
-  if (weighted) cudaFuncSetAttribute(solve_kernel_for(h->p, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmem);
-  solve_kernel_for(h->p, weighted)<<<(unsigned)blocks, threads, kSolveSmem, st>>>(h->p, h->scratch, B, in, so, h->counter, order);
+  if (weighted)
+    cudaFuncSetAttribute(solve_kernel_for(h->p, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveKernelSmem);
+  solve_kernel_for(h->p, weighted)<<<(unsigned)blocks, threads, kSolveKernelSmem, st>>>(h->p, h->scratch, B, in, so, h->counter, order);
   h->launches[0]++;
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "kernel launch", ce);

@@ -145,12 +145,228 @@ TT_HD void prefetch_rows(const double* ps, int row0, int n) {
 #endif
 }
 
+// The same request spread over the lanes of the warp: rows [row0, row0+n) of the warp tile's stage are 2n consecutive
+// 128-byte lines, and a prefetch brings a line into the SM's L1 (or into L2) no matter which lane asks for it -- so each
+// lane asks for every 32nd line instead of every lane asking for its 8 bytes of every row (46 -> 3 instructions per
+// stage of the backward sweep).  Only a hint: the lanes currently converged share the lines among themselves.
+// LEVEL 1: L1, 2: L2.  `pl`: the calling lane's pointer to row 0 of the stage.
+template <int LEVEL>
+TT_HD void prefetch_lines(const double* pl, int row0, int n) {
+#if defined(__CUDA_ARCH__) && !defined(TTMPC_NO_PREFETCH)
+  const unsigned lane = threadIdx.x & 31u, m = __activemask();
+  const int rank = __popc(m & ((1u << lane) - 1u)), cnt = __popc(m);
+  const double* base = pl - lane + (size_t)row0 * kBank;
+  for (int i = rank; i < 2 * n; i += cnt) {
+    if (LEVEL == 1)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)i * 16));
+    else
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * 16));
+  }
+#else
+  (void)pl; (void)row0; (void)n;
+#endif
+}
+
 // pointer to (stage 0, row 0) of a slot inside a scratch allocation of `nbanks` banks
 TT_HD double* slot_ptr(double* scratch, int N, size_t slot) {
   const size_t bank = slot / kBank, lane = slot % kBank;
   return scratch + bank * (size_t)(N + 1) * kStageStride + lane;
 }
 inline size_t scratch_doubles(int N, size_t nbanks) { return nbanks * (size_t)(N + 1) * kStageStride; }
+
+// ------------------------------------------------------------------------------------------------
+// How a sweep gets the rows of the stage it is about to process ("stager").
+//
+// StageDirect: every lane loads its rows from global memory, the next stage is requested with L1 prefetches (host
+// build, episode kernel, speculation experiments).
+//
+// StageBulk (sm_100a, ttmpc_solve_kernel): the rows a sweep reads of one stage of a warp tile are one to three
+// CONTIGUOUS blocks of global memory (a row of the tile is 32 lanes x 8 B = 256 B, rows follow each other, stages
+// follow each other).  One elected lane asks the copy engine for them with cp.async.bulk (TMA, 1-D) into the warp's
+// staging buffer in shared memory, completion is signalled on the warp's mbarrier, and the lanes then read their
+// column with conflict-free LDS -- the same (row * 32 + lane) indexing as in global memory.  The request for the NEXT
+// stage is issued as soon as the current stage's rows are in registers, so it has a whole stage body to arrive; no
+// LDG / prefetch instruction per row, nothing goes through L1 (which the per-SM working set of 8 warps x 12 KB per
+// stage x 2 stages overflowed: ncu L1 hit rate 11 %, long-scoreboard 1.9 of 6.3 stall cycles per issue).
+// Stores stay plain STG (only the lanes that own a problem write).  Ordering: a sweep begins with
+// fence.proxy.async (this thread's earlier generic-proxy stores before the async-proxy reads that follow) and a
+// __syncwarp over the lanes taking part; the buffer is re-filled only after a __syncwarp that follows the lanes' reads.
+// The lanes taking part (`mask`) are whatever subset of the warp runs the sweep -- the callers keep their loops
+// uniform over that subset (ballot) so that the mask is always exact.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStageBufRows = 48;  // largest request: forward sweep, rows {6,7}, {16..23}, {30..67} of a stage
+constexpr size_t kStageBufDoubles = (size_t)kStageBufRows * 32;
+
+#ifndef TTMPC_PF_MODE
+#define TTMPC_PF_MODE 0
+#endif
+struct StageDirect {
+  static constexpr bool kBulk = false;
+  // which lanes of `mask` still want another pass of a loop: the direct path needs no agreement, a lane speaks for itself
+  TT_HD unsigned ballot(unsigned, bool pred) const { return pred ? 1u : 0u; }
+  TT_HD void sweep_begin(unsigned) const {}
+  TT_HD void sweep_end() const {}
+  template <int KIND>
+  TT_HD const double* acquire(const double* ps) const { return ps; }
+  // the direct path reads the stage's own rows: no remapping
+  static TT_HD constexpr int fwd_row(int r) { return r; }
+  // requests (the arguments say which stage and which optional parts)
+  // TTMPC_PF_MODE (experiment switch): 0 = every lane prefetches its own 8 bytes of every row (round 1);
+  // 1 = the lines are shared out among the lanes; 2 = 1 + the stage after next is requested into L2
+  template <bool G>
+  TT_HD void request_bwd(const double* pn, bool do_update, bool far = false) const {
+    if (TTMPC_PF_MODE == 0) {
+      prefetch_rows(pn, 0 /*rW*/, do_update ? 16 : 8);                // W (and DW, adjacent rows)
+      prefetch_rows(pn, 16 /*rREF*/, 8 + 6);                          // REF and LAM (adjacent rows)
+      prefetch_rows(pn, 30 /*rZL*/ + (G ? 0 : 2), G ? 16 : 14);       // ZL, ZU (default pattern: rows 2..7 of each)
+    } else {
+      if (do_update) {
+        prefetch_lines<1>(pn, 0, 46);  // W, DW, REF, LAM, ZL, ZU are adjacent
+      } else {
+        prefetch_lines<1>(pn, 0, 8);
+        prefetch_lines<1>(pn, 16, 30);
+      }
+      if (TTMPC_PF_MODE == 2 && far) prefetch_lines<2>(pn - kStageStride, 0, 46);
+    }
+  }
+  template <bool G>
+  TT_HD void request_fwd(const double* pn, bool last, bool far = false) const {
+    (void)last;
+    if (TTMPC_PF_MODE == 0) {
+      prefetch_rows(pn, 6, 2);                                        // u
+      prefetch_rows(pn + kStageStride, 0, 6);                         // x of the stage after (read one stage ahead)
+      prefetch_rows(pn, 16, 8);                                       // REF
+      prefetch_rows(pn, 30 + (G ? 0 : 2), G ? 16 : 14);               // ZL, ZU
+      prefetch_rows(pn, 46, 16);                                      // K, k_ff
+    } else {
+      prefetch_lines<1>(pn, 6, 2);
+      prefetch_lines<1>(pn, 16, 8);
+      prefetch_lines<1>(pn, 30, last ? 32 : 38);  // ZL, ZU, K, k_ff and the x rows of the stage after are adjacent
+      if (TTMPC_PF_MODE == 2 && far) prefetch_lines<2>(pn + kStageStride, 16, 46);
+    }
+  }
+  TT_HD void request_trial(const double* pn, bool far = false) const {  // W, DW, REF
+    if (TTMPC_PF_MODE == 0) {
+      prefetch_rows(pn, 0, 24);
+    } else {
+      prefetch_lines<1>(pn, 0, 24);
+      if (TTMPC_PF_MODE == 2 && far) prefetch_lines<2>(pn - kStageStride, 0, 24);
+    }
+  }
+  TT_HD void first_bwd(const double*, bool) const {}
+  TT_HD void first_fwd(const double*, bool) const {}
+  TT_HD void first_trial(const double*) const {}
+};
+
+// experiment switch: bit 0 / 1 / 2 = the backward / forward / trial sweep uses the bulk path
+#ifndef TTMPC_BULK_KINDS
+#define TTMPC_BULK_KINDS 7
+#endif
+#if defined(__CUDACC__)
+struct StageBulk {
+  static constexpr bool kBulk = true;
+  double* buf;            // this warp's staging buffer (generic pointer to its first row) + lane
+  unsigned buf_s, bar_s;  // shared-space addresses of the buffer's first row and of the warp's mbarrier
+  unsigned* phase_w;      // the mbarrier's current phase parity, kept in shared memory between sweeps
+  unsigned lane;
+  unsigned mask, phase;
+  bool leader;
+
+  __device__ __forceinline__ void init(double* warp_buf, unsigned long long* warp_bar, unsigned* warp_phase, unsigned lane_) {
+    buf = warp_buf + lane_;
+    buf_s = (unsigned)__cvta_generic_to_shared(warp_buf);
+    bar_s = (unsigned)__cvta_generic_to_shared(warp_bar);
+    phase_w = warp_phase;
+    lane = lane_;
+    if (lane_ == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+      *warp_phase = 0u;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+  }
+  __device__ __forceinline__ unsigned ballot(unsigned m, bool pred) const { return __ballot_sync(m, pred); }
+  __device__ __forceinline__ void sweep_begin(unsigned m) {
+    mask = m;
+    leader = (lane == (unsigned)(__ffs(m) - 1));
+    __threadfence();  // the lanes' stores of the previous sweep must have reached L2, which is where the copy engine reads
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    __syncwarp(mask);
+    phase = *(volatile unsigned*)phase_w;
+  }
+  __device__ __forceinline__ void sweep_end() {
+    __syncwarp(mask);
+    if (leader) *(volatile unsigned*)phase_w = phase;
+    __syncwarp(mask);
+  }
+  template <int KIND>
+  __device__ __forceinline__ const double* acquire(const double* ps) {
+    if (!((TTMPC_BULK_KINDS >> KIND) & 1)) return ps;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TT_DONE;\n"
+        "bra TT_WAIT;\n"
+        "TT_DONE:\n"
+        "}\n" ::"r"(bar_s),
+        "r"(phase)
+        : "memory");
+    phase ^= 1u;
+    return buf;
+  }
+  static __device__ __forceinline__ constexpr int fwd_row(int r) {
+    return !((TTMPC_BULK_KINDS >> 1) & 1) ? r : (r < 8 ? r - 6 : (r < 24 ? r - 16 + 2 : r - 30 + 10));
+  }
+  __device__ __forceinline__ void expect(unsigned bytes) const {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+  }
+  // rows [row0, row0 + n) of the warp tile's stage that starts at `tile` -> buffer rows [dst, dst + n)
+  __device__ __forceinline__ void copy(const double* tile, int row0, int n, int dst) const {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     buf_s + (unsigned)dst * 256u),
+                 "l"(tile + (size_t)row0 * 32), "r"((unsigned)n * 256u), "r"(bar_s)
+                 : "memory");
+  }
+  // `pn`: the lane's pointer to row 0 of the stage to request.  The __syncwarp makes sure every lane has read what it
+  // needs of the buffer's current contents.
+  template <bool G>
+  __device__ __forceinline__ void request_bwd(const double* pn, bool do_update, bool far = false) const {
+    if (!((TTMPC_BULK_KINDS >> 0) & 1)) return StageDirect().template request_bwd<G>(pn, do_update, far);
+    __syncwarp(mask);
+    if (leader) {
+      expect(46u * 256u);
+      copy(pn - lane, 0, 46, 0);  // W, DW, REF, LAM, ZL, ZU
+    }
+  }
+  template <bool G>
+  __device__ __forceinline__ void request_fwd(const double* pn, bool last, bool far = false) const {
+    if (!((TTMPC_BULK_KINDS >> 1) & 1)) return StageDirect().template request_fwd<G>(pn, last, far);
+    __syncwarp(mask);
+    if (leader) {
+      const int n3 = last ? 32 : 38;  // ZL, ZU, K, k_ff (+ x of the stage after, which the last stage does not have)
+      expect((unsigned)(2 + 8 + n3) * 256u);
+      copy(pn - lane, 6, 2, 0);
+      copy(pn - lane, 16, 8, 2);
+      copy(pn - lane, 30, n3, 10);
+    }
+  }
+  __device__ __forceinline__ void request_trial(const double* pn, bool far = false) const {
+    if (!((TTMPC_BULK_KINDS >> 2) & 1)) return StageDirect().request_trial(pn, far);
+    __syncwarp(mask);
+    if (leader) {
+      expect(24u * 256u);
+      copy(pn - lane, 0, 24, 0);  // W, DW, REF
+    }
+  }
+  template <bool G>
+  __device__ __forceinline__ void first_bwd_t(const double* p0) const { request_bwd<G>(p0, true); }
+  __device__ __forceinline__ void first_bwd(const double* p0, bool) const { request_bwd<false>(p0, true); }
+  __device__ __forceinline__ void first_fwd(const double* p0, bool last) const { request_fwd<false>(p0, last); }
+  __device__ __forceinline__ void first_trial(const double* p0) const { request_trial(p0); }
+};
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // lean math: the library sincos / division are ~100 / ~15 instructions each with 64-bit constants materialised by
@@ -444,10 +660,11 @@ struct Stats {
 // of the warp at once (a lane-by-lane load would write 8 of every 32-byte sector and cost more than the sweep).
 // warp_fresh: some lane of the warp is fresh (then every lane re-stores its reference row, again to keep full rows).
 // x0_bad (out, fresh only): x_init violates a state bound.
-template <bool G, bool DQ, bool PW>
-TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const ProblemIn& in, long long b, bool fresh,
-                          bool warp_fresh, bool& x0_bad, bool do_update, double alpha, double alpha_du, double mu_step,
-                          double delta_step, double delta, Stats& st, int cur = 0, bool to_alt = false) {
+template <bool G, bool DQ, bool PW, class SG>
+TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, SG& sg, unsigned mask, const ProblemIn& in, long long b,
+                          bool fresh, bool warp_fresh, bool& x0_bad, bool do_update, double alpha, double alpha_du,
+                          double mu_step, double delta_step, double delta, Stats& st, int cur = 0, bool to_alt = false) {
+  static_assert(!(SG::kBulk && kSpecBuild), "the bulk stager knows the shipped row layout only");
   const int N = p.N;
   const double dt = p.dt;
   bool ok = true;
@@ -462,10 +679,13 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
     for (int i = 0; i < NU; i++) cy.st(cRW + i, in.r_w[b * NU + i] * in.r_w[b * NU + i]);
   }
 
+  sg.sweep_begin(mask);
+  sg.first_bwd(s0 + (size_t)N * kStageStride, do_update);
   for (int k = N; k >= 0; k--) {
     double* ps = s0 + (size_t)k * kStageStride;
+    const double* pl = sg.template acquire<0>(ps);  // where this stage's rows are read from (global memory, or the staged copy)
     // iterate rows (W, LAM, ZL, ZU): copy read / copy written by this sweep (the same unless the step is speculative)
-    const double* pc = kSpecBuild ? ps + (size_t)cur * kAltStride : ps;
+    const double* pc = kSpecBuild ? ps + (size_t)cur * kAltStride : pl;
     double* pw = kSpecBuild ? ps + (size_t)(to_alt ? 1 - cur : cur) * kAltStride : ps;
     const bool has_x = (k >= 1);  // x_0 is data
     const bool has_u = (k < N);
@@ -475,8 +695,8 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
       const bool on = (j < NX) || has_u;
       const bool var = (j < NX) ? has_x : has_u;
       w[j] = (on && !fresh) ? ldr(pc, rW + j) : 0.0;
-      ref[j] = (on && !fresh) ? ldr(ps, rREF + j) : 0.0;
-      dw[j] = (do_update && var) ? ldr(ps, rDW + j) : 0.0;
+      ref[j] = (on && !fresh) ? ldr(pl, rREF + j) : 0.0;
+      dw[j] = (do_update && var) ? ldr(pl, rDW + j) : 0.0;
       zl[j] = (var && !fresh && has_lo<G>(p, j)) ? ldr(pc, rZL + j) : 0.0;
       zu[j] = (var && !fresh && has_up<G>(p, j)) ? ldr(pc, rZU + j) : 0.0;
     }
@@ -520,9 +740,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
     if (has_x) {  // request stage k-1 now
       const double* pn = ps - kStageStride;
       if (!kSpecBuild) {
-        prefetch_rows(pn, rW, do_update ? 2 * NW : NW);  // W (and DW, adjacent rows)
-        prefetch_rows(pn, rREF, NW + NX);                // REF and LAM (adjacent rows)
-        prefetch_rows(pn, rZL + (G ? 0 : 2), G ? 2 * NW : 14);  // ZL, ZU (default pattern: rows 2..7 of each)
+        sg.template request_bwd<G>(pn, do_update, k >= 2);
       } else {
         const double* pnc = pc - kStageStride;
         prefetch_rows(pnc, rW, NW + NX);  // W and LAM (adjacent rows of the current copy)
@@ -845,6 +1063,7 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, const Pr
       }
     }
   }
+  sg.sweep_end();
   st.J = J;
   st.sumlog = sumlog;
   st.theta = theta;
@@ -874,29 +1093,31 @@ struct StepInfo {
 struct FwdIn {
   double u[NU], ref[NW], zl[NW], zu[NW], kf[16], xnext[NX];
 };
-template <bool G>
-TT_HD void fwd_load(const Params& p, const double* s0, int k, FwdIn& f, int cur = 0) {
+// `ps`: where the stage's rows are read from (SG::fwd_row maps a row of the stage -- rows >= kRows are rows of the stage
+// after -- to its place there)
+template <bool G, class SG>
+TT_HD void fwd_load(const Params& p, const double* ps, int k, FwdIn& f, int cur = 0) {
   const int N = p.N;
-  const double* ps = s0 + (size_t)k * kStageStride;
   const double* pc = kSpecBuild ? ps + (size_t)cur * kAltStride : ps;  // current copy of the iterate rows
   const bool has_x = (k >= 1), has_u = (k < N);
-  f.u[0] = has_u ? ldr(pc, rW + 6) : 0.0;
-  f.u[1] = has_u ? ldr(pc, rW + 7) : 0.0;
+  f.u[0] = has_u ? ldr(pc, SG::fwd_row(rW + 6)) : 0.0;
+  f.u[1] = has_u ? ldr(pc, SG::fwd_row(rW + 7)) : 0.0;
   TT_UNROLL
   for (int j = 0; j < NW; j++) {
     const bool var = (j < NX) ? has_x : has_u;
-    f.ref[j] = ((j < NX) || has_u) ? ldr(ps, rREF + j) : 0.0;
-    f.zl[j] = (var && has_lo<G>(p, j)) ? ldr(pc, rZL + j) : 0.0;
-    f.zu[j] = (var && has_up<G>(p, j)) ? ldr(pc, rZU + j) : 0.0;
+    f.ref[j] = ((j < NX) || has_u) ? ldr(ps, SG::fwd_row(rREF + j)) : 0.0;
+    f.zl[j] = (var && has_lo<G>(p, j)) ? ldr(pc, SG::fwd_row(rZL + j)) : 0.0;
+    f.zu[j] = (var && has_up<G>(p, j)) ? ldr(pc, SG::fwd_row(rZU + j)) : 0.0;
   }
   TT_UNROLL
-  for (int j = 0; j < 16; j++) f.kf[j] = (has_u && (has_x || j >= 12)) ? ldr(ps, rKF + j) : 0.0;
+  for (int j = 0; j < 16; j++) f.kf[j] = (has_u && (has_x || j >= 12)) ? ldr(ps, SG::fwd_row(rKF + j)) : 0.0;
   TT_UNROLL
-  for (int j = 0; j < NX; j++) f.xnext[j] = has_u ? ldr(pc + kStageStride, rW + j) : 0.0;
+  for (int j = 0; j < NX; j++) f.xnext[j] = has_u ? ldr(pc, SG::fwd_row(kRows + rW + j)) : 0.0;
 }
 
-template <bool G, bool DQ, bool PW>
-TT_HD void forward_sweep(const Params& p, double* s0, const Carry& cy, double mu, double tau, StepInfo& si, int copy = 0) {
+template <bool G, bool DQ, bool PW, class SG>
+TT_HD void forward_sweep(const Params& p, double* s0, const Carry& cy, SG& sg, unsigned mask, double mu, double tau, StepInfo& si,
+                         int copy = 0) {
   const int N = p.N;
   const double dt = p.dt;
   double dx[NX] = {0, 0, 0, 0, 0, 0};
@@ -905,19 +1126,25 @@ TT_HD void forward_sweep(const Params& p, double* s0, const Carry& cy, double mu
   double qmax = 0.0, bn = 0.0, bd = 1.0, gd = 0.0;
   TT_UNROLL
   for (int j = 0; j < NX; j++) x[j] = ldr(kSpecBuild ? s0 + (size_t)copy * kAltStride : s0, rW + j);
+  sg.sweep_begin(mask);
+  sg.first_fwd(s0, N == 0);
   for (int k = 0; k <= N; k++) {
     double* ps = s0 + (size_t)k * kStageStride;
     const bool has_x = (k >= 1), has_u = (k < N);
     FwdIn cur;  // all loads of the stage first (one batch in flight), then the arithmetic
-    fwd_load<G>(p, s0, k, cur, copy);
+    fwd_load<G, SG>(p, sg.template acquire<1>(ps), k, cur, copy);
     if (has_u) {  // request stage k+1 (and the states of k+2, read one stage ahead)
       const double* pn = ps + kStageStride;
-      const double* pnc = kSpecBuild ? pn + (size_t)copy * kAltStride : pn;  // current copy of the iterate rows
-      prefetch_rows(pnc, rW + NX, NU);
-      prefetch_rows(pnc + kStageStride, rW, NX);
-      prefetch_rows(pn, rREF, NW);
-      prefetch_rows(pnc, rZL + (G ? 0 : 2), G ? 2 * NW : 14);
-      prefetch_rows(pn, rKF, 16);
+      if (!kSpecBuild) {
+        sg.template request_fwd<G>(pn, k + 1 == N, k + 2 < N);
+      } else {
+        const double* pnc = pn + (size_t)copy * kAltStride;  // current copy of the iterate rows
+        prefetch_rows(pnc, rW + NX, NU);
+        prefetch_rows(pnc + kStageStride, rW, NX);
+        prefetch_rows(pn, rREF, NW);
+        prefetch_rows(pnc, rZL + (G ? 0 : 2), G ? 2 * NW : 14);
+        prefetch_rows(pn, rKF, 16);
+      }
     }
     double w[NW], d[NW];
     TT_UNROLL
@@ -997,6 +1224,7 @@ TT_HD void forward_sweep(const Params& p, double* s0, const Carry& cy, double mu
       x[j] = cur.xnext[j];
     }
   }
+  sg.sweep_end();
   si.qmax = qmax;
   si.a_pr = (qmax > tau) ? tau / qmax : 1.0;
   si.a_du = (bn > tau * bd) ? tau * bd / bn : 1.0;
@@ -1014,8 +1242,7 @@ struct Trial {
 struct TrialIn {
   double w[NW], dw[NW], ref[NW];
 };
-TT_HD void trial_load(const Params& p, const double* s0, int k, TrialIn& t, int copy = 0) {
-  const double* ps = s0 + (size_t)k * kStageStride;
+TT_HD void trial_load(const Params& p, const double* ps, int k, TrialIn& t, int copy = 0) {
   const double* pc = kSpecBuild ? ps + (size_t)copy * kAltStride : ps;  // current copy of the iterate rows
   const bool has_x = (k >= 1), has_u = (k < p.N);
   TT_UNROLL
@@ -1028,19 +1255,22 @@ TT_HD void trial_load(const Params& p, const double* s0, int k, TrialIn& t, int 
   }
 }
 
-template <bool G, bool DQ, bool PW>
-TT_HD void trial_sweep(const Params& p, const double* s0, const Carry& cy, double alpha, Trial& tr, int copy = 0) {
+template <bool G, bool DQ, bool PW, class SG>
+TT_HD void trial_sweep(const Params& p, const double* s0, const Carry& cy, SG& sg, unsigned mask, double alpha, Trial& tr,
+                       int copy = 0) {
   const int N = p.N;
   const double dt = p.dt;
   double J = 0.0, sl_ = 0.0, th = 0.0, smin = INFINITY;
   double xn[NX];
+  sg.sweep_begin(mask);
+  sg.first_trial(s0 + (size_t)N * kStageStride);
   for (int k = N; k >= 0; k--) {
     const bool has_x = (k >= 1), has_u = (k < N);
     TrialIn cur;
-    trial_load(p, s0, k, cur, copy);
+    trial_load(p, sg.template acquire<2>(s0 + (size_t)k * kStageStride), k, cur, copy);
     if (has_x) {
       if (!kSpecBuild) {
-        prefetch_rows(s0 + (size_t)(k - 1) * kStageStride, rW, 3 * NW);  // W, DW, REF of stage k-1
+        sg.request_trial(s0 + (size_t)(k - 1) * kStageStride, k >= 2);  // W, DW, REF of stage k-1
       } else {
         prefetch_rows(s0 + (size_t)(k - 1) * kStageStride + (size_t)copy * kAltStride, rW, NW);
         prefetch_rows(s0 + (size_t)(k - 1) * kStageStride, rDW, 2 * NW);  // DW, REF
@@ -1085,6 +1315,7 @@ TT_HD void trial_sweep(const Params& p, const double* s0, const Carry& cy, doubl
     TT_UNROLL
     for (int j = 0; j < NX; j++) xn[j] = w[j];
   }
+  sg.sweep_end();
   tr.J = J;
   tr.sumlog = (smin > 0.0) ? sl_ : NAN;  // a non-positive slack must never pass as a product of two negatives
   tr.theta = th;
@@ -1197,9 +1428,10 @@ TT_HD bool ls_accept(Ipm& s, double theta, double phi, double gd, double a, doub
 // factorisation) + ipm_step (search direction, line search).  Both return true when the lane is finished (res filled
 // in).  They are separate so that the CUDA kernel can align the two halves across the warps of a CTA.
 // SPEC = false compiles the test of a speculative step out (callers whose second half never speculates: ipm_step_rr).
-template <bool G, bool DQ, bool PW, bool SPEC = true>
-TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const ProblemIn& in, long long b, bool warp_fresh,
-                        Ipm& s, Result& res) {
+// sg, grp: the stager and the lanes of the warp that make this call together (StageBulk; ignored by StageDirect).
+template <bool G, bool DQ, bool PW, bool SPEC = true, class SG = StageDirect>
+TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, SG& sg, unsigned grp, const ProblemIn& in, long long b,
+                        bool warp_fresh, Ipm& s, Result& res) {
   if (s.ls_active) return false;  // a rejected trial is being retried with a shorter step: nothing to redo here
   Stats st, st2;
   bool ok = false;
@@ -1207,18 +1439,24 @@ TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const Prob
   double mu = s.mu, delta = 0.0;
   // attempt 0: apply the previous step + statistics + factorisation.  attempts >= 1 (rare): inertia correction,
   // refactor with growing delta until every 2x2 pivot block is positive definite.  One call site on purpose:
-  // the sweep is the bulk of the kernel's code and must not be instantiated twice.
+  // the sweep is the bulk of the kernel's code and must not be instantiated twice.  The loop is kept uniform over the
+  // lanes of `grp`: a lane whose factorisation succeeded idles through the passes the others still need (`again`).
+  bool again = true;
+  unsigned m_pass = grp;
   for (int attempt = 0; attempt <= 40; attempt++) {
+    if (again) do {
+    again = false;
     const bool first = (attempt == 0);
     bool x0_bad = false;
 #if TTMPC_SPECULATION
     // mode 3: a speculative step is written to the other copy of the iterate rows
-    ok = backward_sweep<G, DQ, PW>(p, s0, cy, in, b, first && s.fresh, first && warp_fresh, x0_bad, first && s.do_update, s.alpha,
-                               s.alpha_du, first ? s.mu_step : mu, s.delta_step, delta, first ? st : st2, s.cur,
-                               SPEC && first && s.spec && p.speculate == 3);
+    ok = backward_sweep<G, DQ, PW>(p, s0, cy, sg, m_pass, in, b, first && s.fresh, first && warp_fresh, x0_bad,
+                               first && s.do_update, s.alpha, s.alpha_du, first ? s.mu_step : mu, s.delta_step, delta,
+                               first ? st : st2, s.cur, SPEC && first && s.spec && p.speculate == 3);
 #else
-    ok = backward_sweep<G, DQ, PW>(p, s0, cy, in, b, first && s.fresh, first && warp_fresh, x0_bad, first && s.do_update, s.alpha,
-                               s.alpha_du, first ? s.mu_step : mu, s.delta_step, delta, first ? st : st2);
+    ok = backward_sweep<G, DQ, PW>(p, s0, cy, sg, m_pass, in, b, first && s.fresh, first && warp_fresh, x0_bad,
+                               first && s.do_update, s.alpha, s.alpha_du, first ? s.mu_step : mu, s.delta_step, delta,
+                               first ? st : st2);
 #endif
     if (first) {
       if (s.fresh) s.x0_infeasible = x0_bad;
@@ -1298,6 +1536,10 @@ TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const Prob
       delta = (s.delta_last == 0.0) ? 1e-4 : fmax(1e-20, s.delta_last / 3.0);
     else
       delta *= (s.delta_last == 0.0) ? 100.0 : 8.0;
+    again = true;
+    } while (0);
+    m_pass = sg.ballot(grp, again);
+    if (!m_pass) break;
   }
   if (status < 0 && !ok) status = ST_NUMERIC;
   if (delta > 0.0 && ok) s.delta_last = delta;
@@ -1324,11 +1566,11 @@ TT_HD bool ipm_backward(const Params& p, double* s0, const Carry& cy, const Prob
 
 #if !TTMPC_SPECULATION
 // Second half of an iteration: search direction and the complete filter line search (all trials in one call).
-template <bool G, bool DQ, bool PW>
-TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result& res) {
+template <bool G, bool DQ, bool PW, class SG = StageDirect>
+TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, SG& sg, unsigned grp, Ipm& s, Result& res) {
   const double mu = s.mu, delta = s.cur_delta;
   StepInfo si;
-  forward_sweep<G, DQ, PW>(p, s0, cy, mu, s.tau, si);
+  forward_sweep<G, DQ, PW>(p, s0, cy, sg, grp, mu, s.tau, si);
 
   // filter line search (Waechter & Biegler 2006, Algorithm A)
   const double theta = s.cur_theta;
@@ -1340,9 +1582,16 @@ TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result
   const bool roundoff_step = (theta <= 1e-2 * p.tol) &&
                              (fabs(si.gphi_d) <= fmax(100.0 * kEps * fmax(1.0, fabs(phi)), theta * s.cur_lam1));
   bool accepted = roundoff_step;
-  for (int bt = 0; !roundoff_step && bt <= kMaxBacktrack; bt++, a *= kAlphaRed) {
+  // the trials are kept uniform over the lanes of `grp`: a lane whose step has been accepted idles through the trials the
+  // others still need (`trying`)
+  bool trying = !roundoff_step;
+  double a_bt = si.a_pr;  // step of trial number bt
+  for (int bt = 0; bt <= kMaxBacktrack; bt++, a_bt *= kAlphaRed) {
+    const unsigned m_pass = sg.ballot(grp, trying);
+    if (!m_pass) break;
+    if (!trying) continue;
     Trial tr;
-    trial_sweep<G, DQ, PW>(p, s0, cy, a, tr);
+    trial_sweep<G, DQ, PW>(p, s0, cy, sg, m_pass, a_bt, tr);
     if (!(tt_finite(tr.J) && tt_finite(tr.sumlog) && tt_finite(tr.theta))) continue;
     const double phi_t = tr.J - mu * tr.sumlog;
     if (tr.theta > s.theta_max) continue;
@@ -1353,8 +1602,8 @@ TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result
     // switching condition  a*(-g)^s_phi > delta*theta^s_theta, evaluated in logs (theta = 0: always true)
     bool good, ftype = false;
     if (theta <= s.theta_min && si.gphi_d < 0.0 &&
-        (theta <= 0.0 || log(a) + kSPhi * log(-si.gphi_d) > log(kDeltaSw) + kSTheta * log(theta))) {
-      good = (phi_t - phi - 10.0 * kEps * fabs(phi) <= kEtaPhi * a * si.gphi_d);
+        (theta <= 0.0 || log(a_bt) + kSPhi * log(-si.gphi_d) > log(kDeltaSw) + kSTheta * log(theta))) {
+      good = (phi_t - phi - 10.0 * kEps * fabs(phi) <= kEtaPhi * a_bt * si.gphi_d);
       ftype = true;
     } else {
       good = (tr.theta - (1.0 - kGammaTheta) * theta <= 10.0 * kEps * fabs(theta)) ||
@@ -1376,7 +1625,8 @@ TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result
       s.f_n = m + 1;
     }
     accepted = true;
-    break;
+    trying = false;
+    a = a_bt;
   }
   if (!accepted) {
     // Ipopt would enter feasibility restoration; policy: shortest trial step, cleared filter, give up after 3
@@ -1416,15 +1666,15 @@ TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result
 // problem; 2 = 1 + forgiving tests that fail within evaluation noise; 3 = every step is speculated and written to the
 // other copy of the iterate rows, a rejection leaves the previous iterate intact and this function resumes the classic
 // search of the same direction at alpha/2 (`redo`).
-template <bool G, bool DQ, bool PW>
-TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result& res) {
+template <bool G, bool DQ, bool PW, class SG = StageDirect>
+TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, SG& sg, unsigned grp, Ipm& s, Result& res) {
   if (s.fresh) return false;  // restarted by ipm_backward in this round
   const double mu = s.mu, delta = s.cur_delta;
   const bool redo = s.redo;
   s.redo = false;
   StepInfo si;
   if (!redo) {
-    forward_sweep<G, DQ, PW>(p, s0, cy, mu, s.tau, si, s.cur);
+    forward_sweep<G, DQ, PW>(p, s0, cy, sg, grp, mu, s.tau, si, s.cur);
     s.ls_apr = si.a_pr;
     s.ls_adu = si.a_du;
     s.ls_gd = si.gphi_d;
@@ -1455,7 +1705,7 @@ TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result
   }
   for (int bt = redo ? 1 : 0; !accepted && bt <= kMaxBacktrack; bt++, a *= kAlphaRed) {
     Trial tr;
-    trial_sweep<G, DQ, PW>(p, s0, cy, a, tr, s.cur);
+    trial_sweep<G, DQ, PW>(p, s0, cy, sg, grp, a, tr, s.cur);
     if (!(tt_finite(tr.J) && tt_finite(tr.sumlog) && tt_finite(tr.theta))) continue;
     if (!ls_accept(s, theta, phi, si.gphi_d, a, tr.theta, tr.J - mu * tr.sumlog)) continue;
     accepted = true;
@@ -1496,13 +1746,15 @@ TT_HD bool ipm_step(const Params& p, double* s0, const Carry& cy, Ipm& s, Result
 // this only moves the cost of a struggling (typically infeasible) problem onto that problem.
 template <bool G, bool DQ, bool PW>
 TT_HD bool ipm_step_rr(const Params& p, double* s0, const Carry& cy, Ipm& s, Result& res) {
+  StageDirect sg;
+  const unsigned grp = 1u;
   const double mu = s.mu;
   const double theta = s.cur_theta;
   const double phi = s.cur_J - mu * s.cur_sumlog;
   bool accepted = false;
   if (!s.ls_active) {
     StepInfo si;
-    forward_sweep<G, DQ, PW>(p, s0, cy, mu, s.tau, si);
+    forward_sweep<G, DQ, PW>(p, s0, cy, sg, grp, mu, s.tau, si);
     s.ls_apr = si.a_pr;
     s.ls_adu = si.a_du;
     s.ls_gd = si.gphi_d;
@@ -1518,7 +1770,7 @@ TT_HD bool ipm_step_rr(const Params& p, double* s0, const Carry& cy, Ipm& s, Res
     // one trial of the filter line search (Waechter & Biegler 2006, Algorithm A)
     const double a = s.ls_a, gd = s.ls_gd;
     Trial tr;
-    trial_sweep<G, DQ, PW>(p, s0, cy, a, tr);
+    trial_sweep<G, DQ, PW>(p, s0, cy, sg, grp, a, tr);
     bool good = tt_finite(tr.J) && tt_finite(tr.sumlog) && tt_finite(tr.theta);
     const double phi_t = tr.J - mu * tr.sumlog;
     if (good && tr.theta > s.theta_max) good = false;
@@ -1590,8 +1842,9 @@ TT_HD bool ipm_step_rr(const Params& p, double* s0, const Carry& cy, Ipm& s, Res
 
 template <bool G, bool DQ, bool PW>
 TT_HD bool ipm_iteration(const Params& p, double* s0, const Carry& cy, const ProblemIn& in, long long b, Ipm& s, Result& res) {
-  if (ipm_backward<G, DQ, PW>(p, s0, cy, in, b, s.fresh, s, res)) return true;
-  return ipm_step<G, DQ, PW>(p, s0, cy, s, res);
+  StageDirect sg;
+  if (ipm_backward<G, DQ, PW>(p, s0, cy, sg, 1u, in, b, s.fresh, s, res)) return true;
+  return ipm_step<G, DQ, PW>(p, s0, cy, sg, 1u, s, res);
 }
 
 // slot -> z_out in the reference's decision-vector layout (trajectory_planning.py:38-60): z[8k+j] = w_k[j]

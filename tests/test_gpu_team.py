@@ -3,6 +3,7 @@ and the warp-cooperative team kernel with 8 / 16 / 32 lanes per problem) against
 them, the compact multi-trajectory contract, the asynchronous host-pointer pipeline, stream ordering, and a
 solver-independent KKT certificate computed on the GPU's own output."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -235,3 +236,28 @@ def test_gpu_reaches_the_slsqp_minimiser_on_every_configuration(flavour, monkeyp
         r = s.solve(g["x_init"], g["ref_states"], g["ref_inputs"])
         assert (s.last_solve_lanes(host=True) == 0) == (flavour == "lane")
         check_against_slsqp(cfg, g, r, f"{flavour}/{name}")
+
+
+def test_bulk_staged_experiment_build_is_bit_identical():
+    """The cp.async.bulk staging of the warp tile (StageBulk, -DTTMPC_STAGE_BULK=1; measured slower and not shipped,
+    profiles/r2_bulk_stage_ab.txt) must give the shipped kernel's bits: same u0 for 16 384 problems, for any slot
+    assignment.  Needs the experiment library (tools/ab/libttmpc_bulk.so, built with
+    TTMPC_NVCC_FLAGS=-DTTMPC_STAGE_BULK=1 TTMPC_BUILD_OUT=... python -m car_trailer_mpc_b200.build --force)."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "tools", "ab", "libttmpc_bulk.so")
+    if not os.path.exists(lib):
+        pytest.skip("experiment library not built")
+    out = {}
+    for name, env in (("shipped", {}), ("bulk", {"TTMPC_LIB": lib})):
+        e = dict(os.environ, **env)
+        e.pop("TTMPC_LIB", None) if not env else None
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "perm_check.py"), "16384", "40"], env=e, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        m = re.search(r"mismatches=(\d+) .* u0_sha=(\w+) lanes=(\d+)", r.stdout)
+        assert m, r.stdout
+        assert int(m.group(1)) == 0 and int(m.group(3)) == 0  # permutation-invariant, lane kernel
+        out[name] = m.group(2)
+    assert out["shipped"] == out["bulk"]

@@ -30,9 +30,10 @@ static void run(const Params& p, std::vector<double>& scratch, int64_t B, const 
       double carried[kCarry];
       const Carry cy{carried, 1};
       ipm_begin(p, st);
+      StageDirect sg;
       if (g_round_robin_ls) {
         for (;;) {  // the episode kernel's flavour: at most one line-search trial per round
-          if (ipm_backward<G, DQ, PW, false>(p, s0, cy, in, b, st.fresh, st, r)) break;
+          if (ipm_backward<G, DQ, PW, false>(p, s0, cy, sg, 1u, in, b, st.fresh, st, r)) break;
           if (ipm_step_rr<G, DQ, PW>(p, s0, cy, st, r)) break;
         }
       } else {
