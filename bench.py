@@ -408,9 +408,10 @@ def main() -> None:
         hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         bytes_per_launch = B * algorithmic_bytes_per_solve(N)
         hbm_achieved = bytes_per_launch / (kernel_ms * 1e-3) * 1e-9
-        traffic = None
+        traffic = traffic_src = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_kernel_traffic.json")))["dram_bytes_per_launch"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "solve_kernel_traffic.json")))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         except Exception:
             pass
         line = {
@@ -425,7 +426,7 @@ def main() -> None:
                         "compl": float(kkt[status == 0, 2].max())},
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "traffic": traffic,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "note": "non-tensor FP64 pipe; algorithmic flop = mean_iters*(2500*N+500) per solve (SURVEY 8(d)); peak = "
                         "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                 "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
