@@ -81,13 +81,19 @@ constexpr int rREF = 16;           // reference (xbar_k, ubar_k)             8
 constexpr int rLAM = 24;           // multiplier of c_k (defect into x_k)    6
 constexpr int rZL = 30;            // lower-bound multipliers (x 0..5, u 6..7) 8
 constexpr int rZU = 38;            // upper-bound multipliers                8
-constexpr int rKF = 46;            // K (2x6), kff0 (2), kff1 (2)            16
+constexpr int rKF = 46;            // K (2x6), kff0 (2), kff1 (2)            16 (8 with TTMPC_KF_F32)
 constexpr int kAlt = 0;
+// TTMPC_KF_F32 (experiment switch): the feedback gains K and k_ff -- written by the backward sweep, read once by the
+// forward sweep, used for nothing but the search direction -- are stored as pairs of floats in 8 rows instead of 16.
+#ifndef TTMPC_KF_F32
+#define TTMPC_KF_F32 0
+#endif
+constexpr int kKfRows = TTMPC_KF_F32 ? 8 : 16;
 #ifdef TTMPC_STAGE_ROWS  // experiment builds: padded stage stride (e.g. 64 rows = 16 KB per stage and warp), DESIGN.md section 8
 constexpr int kRows = TTMPC_STAGE_ROWS;
-static_assert(kRows >= 62, "a stage needs 62 rows");
+static_assert(kRows >= 46 + kKfRows, "a stage needs 46 rows + the gains");
 #else
-constexpr int kRows = 62;
+constexpr int kRows = 46 + kKfRows;
 #endif
 #else
 // experiment layout: the iterate (W, LAM, ZL, ZU) exists in two copies kAlt rows apart; a speculative step reads one
@@ -129,6 +135,26 @@ TT_HD bool has_up(const Params& p, int j) {
 
 TT_HD double ldr(const double* ps, int row) { return ps[(size_t)row * kBank]; }
 TT_HD void str(double* ps, int row, double v) { ps[(size_t)row * kBank] = v; }
+// two values rounded to float in one 8-byte element (TTMPC_KF_F32)
+TT_HD double pack2f(double a, double b) {
+  const float fa = (float)a, fb = (float)b;
+  uint32_t ia, ib;
+  memcpy(&ia, &fa, 4);
+  memcpy(&ib, &fb, 4);
+  const uint64_t u = ((uint64_t)ib << 32) | ia;
+  double d;
+  memcpy(&d, &u, 8);
+  return d;
+}
+TT_HD void unpack2f(double d, double& a, double& b) {
+  uint64_t u;
+  memcpy(&u, &d, 8);
+  const uint32_t ia = (uint32_t)u, ib = (uint32_t)(u >> 32);
+  float fa, fb;
+  memcpy(&fa, &ia, 4);
+  memcpy(&fb, &ib, 4);
+  a = fa, b = fb;
+}
 
 // L1 prefetch of rows [row0, row0+n) of a stage: the sweeps walk the stages sequentially with fully predictable
 // addresses, so the next stage is requested while the current one is being computed (no registers tied up).
@@ -237,11 +263,11 @@ struct StageDirect {
       prefetch_rows(pn + kStageStride, 0, 6);                         // x of the stage after (read one stage ahead)
       prefetch_rows(pn, 16, 8);                                       // REF
       prefetch_rows(pn, 30 + (G ? 0 : 2), G ? 16 : 14);               // ZL, ZU
-      prefetch_rows(pn, 46, 16);                                      // K, k_ff
+      prefetch_rows(pn, 46, kKfRows);                                 // K, k_ff
     } else {
       prefetch_lines<1>(pn, 6, 2);
       prefetch_lines<1>(pn, 16, 8);
-      prefetch_lines<1>(pn, 30, last ? 32 : 38);  // ZL, ZU, K, k_ff and the x rows of the stage after are adjacent
+      prefetch_lines<1>(pn, 30, (last ? 16 : 22) + kKfRows);  // ZL, ZU, K, k_ff and the x rows of the stage after are adjacent
       if (TTMPC_PF_MODE == 2 && far) prefetch_lines<2>(pn + kStageStride, 16, 46);
     }
   }
@@ -664,7 +690,7 @@ template <bool G, bool DQ, bool PW, class SG>
 TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, SG& sg, unsigned mask, const ProblemIn& in, long long b,
                           bool fresh, bool warp_fresh, bool& x0_bad, bool do_update, double alpha, double alpha_du,
                           double mu_step, double delta_step, double delta, Stats& st, int cur = 0, bool to_alt = false) {
-  static_assert(!(SG::kBulk && kSpecBuild), "the bulk stager knows the shipped row layout only");
+  static_assert(!(SG::kBulk && (kSpecBuild || TTMPC_KF_F32)), "the bulk stager knows the shipped row layout only");
   const int N = p.N;
   const double dt = p.dt;
   bool ok = true;
@@ -999,15 +1025,25 @@ TT_HD bool backward_sweep(const Params& p, double* s0, const Carry& cy, SG& sg, 
       const double b1a = g1[6] + dt * p1[5], b1w = g1[7] + dt * p1[4];
       const double k0a = i00 * b0a + i01 * b0w, k0w = i01 * b0a + i11 * b0w;
       const double k1a = i00 * b1a + i01 * b1w, k1w = i01 * b1a + i11 * b1w;
-      TT_UNROLL
-      for (int j = 0; j < NX; j++) {
-        str(ps, rKF + j, K0[j]);
-        str(ps, rKF + NX + j, K1[j]);
+      if (TTMPC_KF_F32) {
+        TT_UNROLL
+        for (int j = 0; j < 3; j++) {
+          str(ps, rKF + j, pack2f(K0[2 * j], K0[2 * j + 1]));
+          str(ps, rKF + 3 + j, pack2f(K1[2 * j], K1[2 * j + 1]));
+        }
+        str(ps, rKF + 6, pack2f(k0a, k0w));
+        str(ps, rKF + 7, pack2f(k1a, k1w));
+      } else {
+        TT_UNROLL
+        for (int j = 0; j < NX; j++) {
+          str(ps, rKF + j, K0[j]);
+          str(ps, rKF + NX + j, K1[j]);
+        }
+        str(ps, rKF + 12, k0a);
+        str(ps, rKF + 13, k0w);
+        str(ps, rKF + 14, k1a);
+        str(ps, rKF + 15, k1w);
       }
-      str(ps, rKF + 12, k0a);
-      str(ps, rKF + 13, k0w);
-      str(ps, rKF + 14, k1a);
-      str(ps, rKF + 15, k1w);
 
       if (has_x) {
         Hes hs;
@@ -1109,8 +1145,16 @@ TT_HD void fwd_load(const Params& p, const double* ps, int k, FwdIn& f, int cur 
     f.zl[j] = (var && has_lo<G>(p, j)) ? ldr(pc, SG::fwd_row(rZL + j)) : 0.0;
     f.zu[j] = (var && has_up<G>(p, j)) ? ldr(pc, SG::fwd_row(rZU + j)) : 0.0;
   }
-  TT_UNROLL
-  for (int j = 0; j < 16; j++) f.kf[j] = (has_u && (has_x || j >= 12)) ? ldr(ps, SG::fwd_row(rKF + j)) : 0.0;
+  if (TTMPC_KF_F32) {
+    TT_UNROLL
+    for (int j = 0; j < 8; j++) {
+      f.kf[2 * j] = f.kf[2 * j + 1] = 0.0;
+      if (has_u && (has_x || j >= 6)) unpack2f(ldr(ps, SG::fwd_row(rKF + j)), f.kf[2 * j], f.kf[2 * j + 1]);
+    }
+  } else {
+    TT_UNROLL
+    for (int j = 0; j < 16; j++) f.kf[j] = (has_u && (has_x || j >= 12)) ? ldr(ps, SG::fwd_row(rKF + j)) : 0.0;
+  }
   TT_UNROLL
   for (int j = 0; j < NX; j++) f.xnext[j] = has_u ? ldr(pc, SG::fwd_row(kRows + rW + j)) : 0.0;
 }

@@ -16,7 +16,7 @@ from .solver import BatchSolver
 
 class TruckTrailerNMPC(MPCTrackingControl):
     def __init__(self, dynamics, params, Q, R, state_bound, input_bound, device: int = 0,
-                 shift_reference_bug: bool = False):
+                 shift_reference_bug: bool = True):
         self._dynamics = dynamics
         self._horizon = int(params["horizon"])
         self._num_state = 6
@@ -25,7 +25,8 @@ class TruckTrailerNMPC(MPCTrackingControl):
                                                nmpc_preset(self._horizon))
         self._solver = BatchSolver(self._cfg, device)
         self._last_solution = None  # warm start between calls (mpc_control_nmpc.py:15)
-        # True reproduces the reference's mis-sliced tail (mpc_control_nmpc.py:83-87) bit for bit
+        # True (default, as in MPCTrackingControlFuzzy -- both reference classes slice the same way) reproduces the
+        # reference's mis-sliced warm-start tail (mpc_control_nmpc.py:83-87) bit for bit; False = the intended shift
         self._shift_reference_bug = bool(shift_reference_bug)
         self.last_status = None
         self.last_iterations = None
