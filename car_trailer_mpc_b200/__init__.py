@@ -4,7 +4,7 @@ Avan1ko/car-trailer-mpc (drop-in for ``controller.solve`` of mpc_control.py / mp
 Public surface:
   * :class:`BatchSolver`           -- thin ctypes front end of the C ABI in ``include/ttmpc.h`` (CUDA only).
   * :class:`MPCTrackingControl`, :class:`TruckTrailerNMPC`, :class:`MPCTrackingControlFuzzy`, :class:`MPCTrackingControlObs`,
-    :class:`TruckTrailerModel` -- shims with
+    :class:`TrajectoryOptimization` (the offline planner), :class:`TruckTrailerModel` -- shims with
     the reference's constructor / ``solve`` signatures.
   * :mod:`problem`                 -- trajectory, windows, layouts, synthetic scenario batches.
   * :mod:`closed_loop`, :mod:`batch_driver` -- headless closed loop and the sweep/CSV driver.
@@ -15,10 +15,11 @@ from .config import (  # noqa: F401
     STATUS_NAMES,
     nmpc_preset,
     parking_lot_obstacles,
+    planner_preset,
     tracking_preset,
 )
 
-__all__ = ["Config", "Obstacles", "tracking_preset", "nmpc_preset", "parking_lot_obstacles", "STATUS_NAMES"]
+__all__ = ["Config", "Obstacles", "tracking_preset", "nmpc_preset", "planner_preset", "parking_lot_obstacles", "STATUS_NAMES"]
 
 
 def __getattr__(name):  # lazy: importing the package must not require the CUDA library
@@ -42,6 +43,10 @@ def __getattr__(name):  # lazy: importing the package must not require the CUDA 
         from .mpc_control_obs import MPCTrackingControlObs
 
         return MPCTrackingControlObs
+    if name == "TrajectoryOptimization":
+        from .trajectory_optimization import TrajectoryOptimization
+
+        return TrajectoryOptimization
     if name == "SwitchingController":
         from .mpc_control_switch import SwitchingController
 

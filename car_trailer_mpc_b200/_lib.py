@@ -68,6 +68,9 @@ def load():
         [H, ctypes.c_void_p, ctypes.c_int64, c_dp, c_dp, c_dp, c_dp, ctypes.c_int32] + [c_dp] * 6 + [ctypes.c_void_p]
     )
     L.ttmpc_obca_solve_batch_shared.restype = ctypes.c_int
+    L.ttmpc_plan_batch.argtypes = ([H, ctypes.c_void_p, ctypes.c_int64, c_dp, ctypes.c_void_p, ctypes.c_double, ctypes.c_double]
+                                   + [c_dp] * 7 + [ctypes.c_void_p])
+    L.ttmpc_plan_batch.restype = ctypes.c_int
     L.ttmpc_shift_warm_start.argtypes = [H, ctypes.c_int64, c_dp, c_dp, ctypes.c_int32, ctypes.c_void_p]
     L.ttmpc_shift_warm_start.restype = ctypes.c_int
     L.ttmpc_plant_step.argtypes = [H, ctypes.c_int64, c_dp, c_dp, c_dp, c_dp, ctypes.c_double, c_dp, ctypes.c_void_p]
@@ -91,5 +94,5 @@ EXPORTS = [
     "ttmpc_default_config", "ttmpc_create", "ttmpc_destroy", "ttmpc_last_error", "ttmpc_version",
     "ttmpc_solve_batch", "ttmpc_solve_batch_weighted", "ttmpc_solve_batch_shared",
     "ttmpc_obca_solve_batch", "ttmpc_obca_solve_batch_shared", "ttmpc_shift_warm_start", "ttmpc_plant_step", "ttmpc_episode_batch",
-    "ttmpc_launch_count", "ttmpc_kernel_name", "ttmpc_measure_fp64_peak", "ttmpc_last_solve_lanes", "ttmpc_solve_batch_multi", "ttmpc_sync", "ttmpc_host_pipeline_ms",
+    "ttmpc_launch_count", "ttmpc_kernel_name", "ttmpc_measure_fp64_peak", "ttmpc_last_solve_lanes", "ttmpc_solve_batch_multi", "ttmpc_sync", "ttmpc_host_pipeline_ms", "ttmpc_plan_batch",
 ]

@@ -112,6 +112,20 @@ def tracking_preset(horizon: int = 40, dt: float = 0.05, max_iter: int = 5000) -
     return c
 
 
+def planner_preset(horizon: int = 200, dt: float = 0.1, max_iter: int = 5000) -> Config:
+    """``TrajectoryOptimization`` as configured by trajectory_animation.py:41-79 (Q = I, R = 10 I, heading unbounded,
+    speed in [-5, 10]) and trajectory_optimization.py:196-199 (Ipopt defaults, max_iter 5000)."""
+    c = tracking_preset(horizon, dt, max_iter)
+    inf = math.inf
+    c.set_bounds(
+        [-inf, -inf, -inf, -math.pi / 3.0, -math.pi / 4.0, -5.0],
+        [inf, inf, inf, math.pi / 3.0, math.pi / 4.0, 10.0],
+        [-5.0, -math.pi / 2.0],
+        [5.0, math.pi / 2.0],
+    )
+    return c
+
+
 def nmpc_preset(horizon: int = 30, dt: float = 0.05, max_iter: int = 2000) -> Config:
     """``TruckTrailerNMPC`` as configured by simulation_nmpc.py:124-148 + mpc_control_nmpc.py:36-45."""
     c = tracking_preset(horizon, dt, max_iter)

@@ -18,6 +18,8 @@
 
 #include <new>
 
+#include <vector>
+
 #include "../../include/ttmpc.h"
 #include "ttmpc_core.cuh"
 #include "ttmpc_obca.cuh"
@@ -582,8 +584,8 @@ constexpr int kObcaThreads = TTMPC_OBCA_THREADS;  // 8 warps = 8 problem slots p
 #define OB_ROUND_ANY(x) (x)
 #endif
 __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
-    ttmpc_obca_kernel(const __grid_constant__ Params p, const __grid_constant__ obca::ObParams o, double* __restrict__ scratch,
-                      long long B, ProblemIn in, SolveOut out, unsigned long long* counter) {
+    ttmpc_obca_kernel(const __grid_constant__ Params p, const __grid_constant__ Params pT, const __grid_constant__ obca::ObParams o,
+                      double* __restrict__ scratch, long long B, ProblemIn in, SolveOut out, unsigned long long* counter) {
   // One warp per problem, one lane per (obstacle, body) pair (ttmpc_obca.cuh).  Every warp owns a scratch slot and works
   // through problems taken from the global queue.  The phases of an iteration (head / factorisation attempts /
   // direction / line-search trials) are aligned across the 8 warps of the CTA with barriers, although their problems
@@ -593,7 +595,7 @@ __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
   const size_t slot = ((size_t)blockIdx.x * kObcaThreads + threadIdx.x) >> 5;
   obca::Ctx c;
   c.wd.wid = 0, c.wd.nw = 1, c.wd.part = nullptr, c.wd.bcast = nullptr;
-  c.p = &p, c.o = &o, c.s0 = obca::slot_ptr(scratch, p.N, slot);
+  c.p = &p, c.pT = &pT, c.o = &o, c.s0 = obca::slot_ptr(scratch, p.N, slot);
   const long long nz = 8LL * p.N + 6;
   obca::Lane L;
   bool active = false, exhausted = false;
@@ -603,7 +605,7 @@ __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
       if (lane == 0) b = (long long)atomicAdd(counter, 1ull);
       b = __shfl_sync(0xffffffffu, b, 0);
       if (b < B) {
-        obca::lane_begin(p, o, obca::init_point<false>(c, in, b), L);
+        obca::lane_begin(p, pT, o, obca::init_point<false>(c, in, b), L);
         active = true;
       } else {
         exhausted = true;
@@ -644,14 +646,15 @@ __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
 // on warp 0, statistics meet in shared memory (obca::run_* wrappers).  Same arithmetic as ttmpc_obca_kernel: the host
 // build of this decomposition reproduces the single-warp results bit for bit (tests/test_obca_cpu.py).
 __global__ void __launch_bounds__(kObcaThreads)
-    ttmpc_obca_wide_kernel(const __grid_constant__ Params p, const __grid_constant__ obca::ObParams o,
-                           double* __restrict__ scratch, long long B, ProblemIn in, SolveOut out, unsigned long long* counter) {
+    ttmpc_obca_wide_kernel(const __grid_constant__ Params p, const __grid_constant__ Params pT,
+                           const __grid_constant__ obca::ObParams o, double* __restrict__ scratch, long long B, ProblemIn in,
+                           SolveOut out, unsigned long long* counter) {
   __shared__ double s_part[(kObcaThreads / 32) * obca::kPart];
   __shared__ double s_bcast[32];
   __shared__ long long s_b;
   obca::Ctx c;
   c.wd.wid = (int)(threadIdx.x >> 5), c.wd.nw = (int)(blockDim.x >> 5), c.wd.part = s_part, c.wd.bcast = s_bcast;
-  c.p = &p, c.o = &o, c.s0 = obca::slot_ptr(scratch, p.N, blockIdx.x);
+  c.p = &p, c.pT = &pT, c.o = &o, c.s0 = obca::slot_ptr(scratch, p.N, blockIdx.x);
   const long long nz = 8LL * p.N + 6;
   for (;;) {
     __syncthreads();
@@ -699,6 +702,9 @@ constexpr int kNumKernels = 10;
 struct ttmpc_handle {
   ttmpc_config cfg;
   Params p;
+  const Params* plan_pT = nullptr;  // set for the duration of a ttmpc_plan_batch call: terminal-stage parameters
+  double* plan_dev = nullptr;       // device copy of the planner's one-record reference trajectory (goal, goal | 0 0) + k_index
+  size_t plan_dev_bytes = 0;
   int device;
   int max_blocks;          // resident CTAs of the persistent solve kernel on this device
   int sms;                 // multiprocessors of the device
@@ -1040,6 +1046,7 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
                        cudaStream_t st) {
   obca::ObParams o;
   if (obca::build_obparams(&h->cfg, obs, &o) != TTMPC_OK) return set_err(h, TTMPC_E_INVAL, "bad obstacle set", cudaSuccess);
+  const Params& pT = h->plan_pT ? *h->plan_pT : h->p;  // terminal-stage parameters (the planner's box and weight)
   int sms = h->sms, per_sm = 1, per_sm_wide = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ttmpc_obca_kernel, kObcaThreads, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_wide, ttmpc_obca_wide_kernel, kObcaThreads, 0);
@@ -1064,10 +1071,10 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
   }
   cudaMemsetAsync(h->counter, 0, 16 * sizeof(unsigned long long), st);
   if (wide) {
-    ttmpc_obca_wide_kernel<<<(unsigned)blocks, kObcaThreads, 0, st>>>(h->p, o, h->ob_scratch, B, in, so, h->counter);
+    ttmpc_obca_wide_kernel<<<(unsigned)blocks, kObcaThreads, 0, st>>>(h->p, pT, o, h->ob_scratch, B, in, so, h->counter);
     h->launches[8]++;
   } else {
-    ttmpc_obca_kernel<<<(unsigned)blocks, kObcaThreads, 0, st>>>(h->p, o, h->ob_scratch, B, in, so, h->counter);
+    ttmpc_obca_kernel<<<(unsigned)blocks, kObcaThreads, 0, st>>>(h->p, pT, o, h->ob_scratch, B, in, so, h->counter);
     h->launches[7]++;
   }
   cudaError_t ce = cudaGetLastError();
@@ -1293,6 +1300,61 @@ int ttmpc_obca_solve_batch_shared(ttmpc_handle* h, const ttmpc_obstacles* obstac
   if (h && !obstacles) return set_err(h, TTMPC_E_INVAL, "null argument", cudaSuccess);
   return solve_any(h, B, x_init, nullptr, nullptr, k_index, traj_states, traj_inputs, T, nullptr, z_out, u0_out, obj_out,
                    kkt_out, iters_out, status_out, cuda_stream, nullptr, nullptr, obstacles);
+}
+
+// The offline planner's NLP (TrajectoryOptimization, trajectory_optimization.py:9-331) on the obstacle-aware solver: the
+// tracking cost with the goal as the reference of every stage and zero reference inputs (:175-183), terminal weight
+// terminal_weight * Q (:181: 100), |x_N - goal| <= terminal_box (:168-173: 1e-2) as bounds of the terminal stage, the
+// caller's initial trajectory (:227-274) as the starting point.  Runs as a shared-trajectory OBCA solve over the
+// one-record trajectory (goal, goal) -- every window is "past the end": last state, zero input (simulation.py:485-499).
+int ttmpc_plan_batch(ttmpc_handle* h, const ttmpc_obstacles* obstacles, int64_t B, const double* x_init, const double* goal,
+                     double terminal_weight, double terminal_box, const double* z_guess, double* z_out, double* u0_out,
+                     double* obj_out, double* kkt_out, int32_t* iters_out, int32_t* status_out, void* cuda_stream) {
+  if (!h) return TTMPC_E_INVAL;
+  if (!obstacles || !goal || !(terminal_weight > 0.0) || !(terminal_box >= 0.0) || B < 0)
+    return set_err(h, TTMPC_E_INVAL, "bad planner arguments", cudaSuccess);
+  if (B == 0) return TTMPC_OK;
+  ttmpc_config ct = h->cfg;  // the terminal stage: Q_f = terminal_weight * Q, box around the goal inside the state bounds
+  for (int i = 0; i < 36; i++) ct.Q[i] *= terminal_weight;
+  if (terminal_box > 0.0)
+    for (int i = 0; i < NX; i++) {
+      ct.x_lb[i] = fmax(ct.x_lb[i], goal[i] - terminal_box);
+      ct.x_ub[i] = fmin(ct.x_ub[i], goal[i] + terminal_box);
+    }
+  Params pT;
+  if (build_params(&ct, &pT) != TTMPC_OK) return set_err(h, TTMPC_E_INVAL, "goal outside the state bounds", cudaSuccess);
+  const bool host = (h->cfg.flags & TTMPC_FLAG_HOST_POINTERS) != 0;
+  double traj[2 * NX + NU];  // states (goal, goal), inputs (0, 0)
+  for (int i = 0; i < NX; i++) traj[i] = traj[NX + i] = goal[i];
+  traj[2 * NX] = traj[2 * NX + 1] = 0.0;
+  std::vector<int32_t> kz((size_t)B, 0);
+  const double *ts = traj, *tu = traj + 2 * NX;
+  const int32_t* ki = kz.data();
+  if (!host) {  // device-pointer mode: the small reference record and the window starts live in a handle-owned buffer
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return set_err(h, TTMPC_E_NODEV, "cudaSetDevice", cudaGetLastError());
+    const size_t need = 256 + (size_t)B * sizeof(int32_t);
+    if (need > h->plan_dev_bytes) {
+      if (h->plan_dev) cudaFree(h->plan_dev);
+      h->plan_dev = nullptr, h->plan_dev_bytes = 0;
+      if (cudaMalloc(&h->plan_dev, need) != cudaSuccess) return set_err(h, TTMPC_E_NOMEM, "planner buffer", cudaGetLastError());
+      h->plan_dev_bytes = need;
+    }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    order_after_previous(h, st);  // the previous call may still read this buffer
+    cudaMemcpyAsync(h->plan_dev, traj, sizeof traj, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync((char*)h->plan_dev + 256, 0, (size_t)B * sizeof(int32_t), st);
+    cudaStreamSynchronize(st);  // `traj` is a stack array
+    ts = h->plan_dev, tu = h->plan_dev + 2 * NX;
+    ki = reinterpret_cast<const int32_t*>((char*)h->plan_dev + 256);
+  }
+  h->plan_pT = &pT;
+  const int rc = solve_any(h, B, x_init, nullptr, nullptr, ki, ts, tu, 1, z_guess, z_out, u0_out, obj_out, kkt_out, iters_out,
+                           status_out, cuda_stream, nullptr, nullptr, obstacles);
+  int rc2 = TTMPC_OK;
+  if (host && (h->cfg.flags & TTMPC_FLAG_ASYNC_HOST)) rc2 = host_pipe_drain(h);  // `traj`, `kz`, `pT` are locals
+  h->plan_pT = nullptr;
+  return rc ? rc : rc2;
 }
 
 int ttmpc_solve_batch_weighted(ttmpc_handle* h, int64_t B, const double* x_init, const double* ref_states,

@@ -481,6 +481,8 @@ struct Wide {
 struct Ctx {
   Wide wd;
   const Params* p;
+  const Params* pT;  // parameters of the terminal stage (bounds, weight): == p for the controllers; the offline planner
+                     // (trajectory_optimization.py:168-183) has a box around the goal and 100 Q there
   const ObParams* o;
   double* s0;   // slot pointer (stage 0 of this problem slot)
   TT_HD double* stage(int k) const { return s0 + (size_t)k * kStageDoubles; }
@@ -503,13 +505,13 @@ TT_HD bool var_up(const Params& p, int j) { return ((p.bu >> j) & 1u) != 0; }
 // ---- starting point (mpc_control_obs.py:216-239 + Ipopt's slack initialisation and interior push) ----
 template <bool WIDE>
 TT_HD bool init_point(const Ctx& c0, const ProblemIn& in, long long b) {
-  const Params& p = *c0.p;
+  const Params& p0 = *c0.p;
   const ObParams& o = *c0.o;
-  const int N = p.N;
+  const int N = p0.N;
   bool x0_bad = false;
   for (int j = 0; j < NX; j++) {
     const double w = in.x_init[b * NX + j];
-    if ((var_lo(p, j) && w < p.lo[j]) || (var_up(p, j) && w > p.up[j])) x0_bad = true;
+    if ((var_lo(p0, j) && w < p0.lo[j]) || (var_up(p0, j) && w > p0.up[j])) x0_bad = true;
   }
   {  // Stage 0 is data, so its collision rows involve the stage's own duals only: they can be met iff every body keeps
      // d_min to every obstacle at x_init (strong duality of the distance problem).  Otherwise the NLP has no feasible
@@ -530,6 +532,7 @@ TT_HD bool init_point(const Ctx& c0, const ProblemIn& in, long long b) {
   for (int k = 0; k <= N; k++) {
     if (WIDE && (k % c.wd.nw) != c.wd.wid) continue;
     double* ps = c.stage(k);
+    const Params& p = (k == N) ? *c0.pT : p0;  // the terminal stage may have its own bounds and weight
     double x[NX];
     for (int j = 0; j < NW; j++) {
       const bool on = (j < NX) || (k < N);
@@ -539,8 +542,10 @@ TT_HD bool init_point(const Ctx& c0, const ProblemIn& in, long long b) {
       double w;
       if (j < NX && k == 0) {
         w = in.x_init[b * NX + j];
-      } else {
-        w = tt_min(tt_max(r, p.lo_push[j]), p.up_push[j]);
+      } else {  // cold start at the reference window (mpc_control_obs.py:216-239), or the caller's guess of states and
+                // inputs (the planner's initial trajectory, trajectory_optimization.py:227-274); Ipopt's interior push
+        const double g = in.z_warm ? in.z_warm[b * (8LL * N + 6) + (long long)k * NW + j] : r;
+        w = tt_min(tt_max(g, p.lo_push[j]), p.up_push[j]);
       }
       bst(ps, oW + j, w);
       bst(ps, oZL + j, 1.0);
@@ -577,9 +582,9 @@ TT_HD bool init_point(const Ctx& c0, const ProblemIn& in, long long b) {
 // restoration phase here and, on return, also resets the multipliers)
 template <bool WIDE>
 TT_HD void restart_point(const Ctx& c0) {
-  const Params& p = *c0.p;
+  const Params& p0 = *c0.p;
   const ObParams& o = *c0.o;
-  const int N = p.N;
+  const int N = p0.N;
   Ctx c = c0;
 #if !defined(__CUDA_ARCH__)
   for (int wv = 0; wv < (WIDE ? c0.wd.nw : 1); wv++) {  // host: the warps of the CTA one after the other
@@ -588,6 +593,7 @@ TT_HD void restart_point(const Ctx& c0) {
   for (int k = 0; k <= N; k++) {
     if (WIDE && (k % c.wd.nw) != c.wd.wid) continue;
     double* ps = c.stage(k);
+    const Params& p = (k == N) ? *c0.pT : p0;  // the terminal stage may have its own bounds and weight
     double x[NX];
     for (int j = 0; j < NW; j++) {
       const bool on = (j < NX) || (k < N);
@@ -630,9 +636,9 @@ TT_HD double clampz(double z, double rs, double hi, double lo) { return tt_max(t
 template <int MODE>
 TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha_du, double mu_step, double delta_step,
                         Stats& st) {
-  const Params& p = *c.p;
+  const Params& p0 = *c.p;
   const ObParams& o = *c.o;
-  const int N = p.N;
+  const int N = p0.N;
   double J = 0.0, sumlog = 0.0, theta = 0.0, cinf = 0.0, rd_inf = 0.0, lam1 = 0.0, z1 = 0.0, cmax = 0.0, cmin = INFINITY;
   // the pairs' share of the statistics: per-lane partial results, combined across the warp after the sweep
   double q_sumlog = 0.0, q_theta = 0.0, q_cinf = 0.0, q_rd = 0.0, q_lam1 = 0.0, q_z1 = 0.0, q_cmax = 0.0, q_cmin = INFINITY;
@@ -643,6 +649,7 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
   for (int k = N; k >= 0; k--) {
     if ((MODE == 1 || MODE == 3) && (k % c.wd.nw) != c.wd.wid) continue;
     double* ps = c.stage(k);
+    const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW], ref[NW], zl[NW], zu[NW], lam[NX], dwv[NW], lamp[NX];
     for (int j = 0; j < NW; j++) {
@@ -881,10 +888,10 @@ TT_HD void load_hx(const double* ps, double (*Hx)[NX]) {
 // ---- sweep 2 (backward): condensation of the pairs + Riccati factorisation.  false: wrong inertia ----
 template <int MODE>
 TT_HD bool factor(const Ctx& c, double mu, double delta) {
-  const Params& p = *c.p;
+  const Params& p0 = *c.p;
   const ObParams& o = *c.o;
-  const int N = p.N;
-  const double dt = p.dt;
+  const int N = p0.N;
+  const double dt = p0.dt;
   double Pn[NX][NX], pn[NX], xn[NX], ln[NX];
   for (int i = 0; i < NX; i++) {
     pn[i] = xn[i] = ln[i] = 0.0;
@@ -896,6 +903,7 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
   for (int k = N; k >= 0; k--) {
     if (MODE == 1 && (k % c.wd.nw) != c.wd.wid) continue;
     double* ps = c.stage(k);
+    const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW], g[NW], sig[NW];
     if (MODE == 2) {  // everything stage-local was prepared by the stage's warp
@@ -1124,10 +1132,10 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
 // recursion that the wide kernel needs costs this path 7 % (more values live across the pair loop).
 TT_HD bool factor_fused(const Ctx& c, double mu, double delta) {
   constexpr int MODE = 0;
-  const Params& p = *c.p;
+  const Params& p0 = *c.p;
   const ObParams& o = *c.o;
-  const int N = p.N;
-  const double dt = p.dt;
+  const int N = p0.N;
+  const double dt = p0.dt;
   double Pn[NX][NX], pn[NX], xn[NX], ln[NX];
   for (int i = 0; i < NX; i++) {
     pn[i] = xn[i] = ln[i] = 0.0;
@@ -1139,6 +1147,7 @@ TT_HD bool factor_fused(const Ctx& c, double mu, double delta) {
   for (int k = N; k >= 0; k--) {
     if (MODE == 1 && (k % c.wd.nw) != c.wd.wid) continue;
     double* ps = c.stage(k);
+    const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW], g[NW], sig[NW];
     {
@@ -1345,9 +1354,9 @@ TT_HD void limit_lo(double dist, double d, double z, double mu, double tau, Dir&
 }
 template <int MODE>
 TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di) {
-  const Params& p = *c.p;
+  const Params& p0 = *c.p;
   const ObParams& o = *c.o;
-  const int N = p.N;
+  const int N = p0.N;
   di.a_pr = di.a_du = 1.0;
   di.gphi_d = 0.0;
   Dir dq;  // the pairs' share: per-lane partial step limits and grad(phi)'d
@@ -1358,6 +1367,7 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
   for (int k = 0; k <= N; k++) {
     if (MODE == 1 && (k % c.wd.nw) != c.wd.wid) continue;
     double* ps = c.stage(k);
+    const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW], g[NW];
     if (MODE == 1)  // pair phase: dx of the stage was stored by the recursion on warp 0
@@ -1500,9 +1510,9 @@ struct TrialOut {
 };
 template <int MODE>
 TT_HD void trial(const Ctx& c, double alpha, TrialOut& tr) {
-  const Params& p = *c.p;
+  const Params& p0 = *c.p;
   const ObParams& o = *c.o;
-  const int N = p.N;
+  const int N = p0.N;
   double J = 0.0, sumlog = 0.0, theta = 0.0;
   bool inside = true;
   double q_sumlog = 0.0, q_theta = 0.0;  // the pairs' share (per-lane partials)
@@ -1512,6 +1522,7 @@ TT_HD void trial(const Ctx& c, double alpha, TrialOut& tr) {
   for (int k = N; k >= 0; k--) {
     if (MODE == 1 && (k % c.wd.nw) != c.wd.wid) continue;
     double* ps = c.stage(k);
+    const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW];
     for (int j = 0; j < NW; j++) {
@@ -1738,7 +1749,13 @@ struct Lane {
 };
 constexpr int kMaxRestarts = 3;
 
-TT_HD void lane_begin(const Params& p, const ObParams& o, bool x0_bad, Lane& L) {
+// number of bounds of the state part of a stage
+TT_HD int state_bounds(const Params& p) {
+  int n = 0;
+  for (int j = 0; j < NX; j++) n += (var_lo(p, j) ? 1 : 0) + (var_up(p, j) ? 1 : 0);
+  return n;
+}
+TT_HD void lane_begin(const Params& p, const Params& pT, const ObParams& o, bool x0_bad, Lane& L) {
   L.mu = p.mu_init;
   L.tau = fmax(kTauMin, 1.0 - L.mu);
   L.theta_max = L.theta_min = L.delta_last = L.delta = 0.0;
@@ -1749,6 +1766,7 @@ TT_HD void lane_begin(const Params& p, const ObParams& o, bool x0_bad, Lane& L) 
   L.restarts = 0;
   L.reinit = true;
   L.n_b = p.n_b + (p.N + 1) * o.P * 14;  // + 8 local variables and 6 slack bounds per pair
+  L.n_b += state_bounds(pT) - state_bounds(p);  // the terminal stage's own bound pattern
   L.m_eq = p.m_eq + (p.N + 1) * o.P * 4;
   L.do_update = false;
   L.x0_bad = x0_bad;
@@ -1937,7 +1955,7 @@ TT_HD void solve_problem(const Ctx& c, const ProblemIn& in, long long b, Result&
   Lane L;
   const bool x0_bad = init_point<WIDE>(c, in, b);
   if (WIDE) ob_cta_sync();
-  lane_begin(*c.p, *c.o, x0_bad, L);
+  lane_begin(*c.p, *c.pT, *c.o, x0_bad, L);
   for (;;) {
     if (lane_head<WIDE>(c, L, res)) return;
     while (L.need_factor)
@@ -1947,10 +1965,11 @@ TT_HD void solve_problem(const Ctx& c, const ProblemIn& in, long long b, Result&
       if (lane_trial_once<WIDE>(c, L, res)) return;
   }
 }
-TT_HD void solve_lane(const Params& p, const ObParams& o, double* s0, const ProblemIn& in, long long b, Result& res) {
+TT_HD void solve_lane(const Params& p, const Params& pT, const ObParams& o, double* s0, const ProblemIn& in, long long b,
+                      Result& res) {
   Ctx c;
   c.wd.wid = 0, c.wd.nw = 1, c.wd.part = nullptr, c.wd.bcast = nullptr;
-  c.p = &p, c.o = &o, c.s0 = s0;
+  c.p = &p, c.pT = &pT, c.o = &o, c.s0 = s0;
   solve_problem<false>(c, in, b, res);
 }
 

@@ -133,6 +133,15 @@ class BatchSolver:
         """:meth:`solve_obca` with the windows taken from one shared trajectory (simulation.py:485-499)."""
         return self._solve(x_init, None, None, k_index, traj_states, traj_inputs, None, want_z, stream, obstacles=obstacles)
 
+    def plan(self, obstacles, x_init, goal, terminal_weight: float = 100.0, terminal_box: float = 1e-2, z_guess=None,
+             want_z: bool = True, stream=None) -> dict:
+        """The offline planner's NLP (``TrajectoryOptimization.plan``, trajectory_optimization.py:311-331) for B start
+        states ``x_init [B,6]`` towards one ``goal [6]``: goal-tracking cost with terminal weight ``terminal_weight * Q``
+        (:175-183), ``|x_N - goal| <= terminal_box`` (:168-173), all collision rows; ``z_guess [B,8N+6]``: the initial
+        trajectory (states and inputs in the z layout; None = every state at the goal)."""
+        return self._solve(x_init, None, None, None, None, None, z_guess, want_z, stream, obstacles=obstacles,
+                           plan=(np.ascontiguousarray(goal, dtype=np.float64).reshape(6), float(terminal_weight), float(terminal_box)))
+
     def sync(self) -> float:
         """Wait for every ``host_async`` solve queued so far (``ttmpc_sync``); returns the device-side duration of that
         burst in ms (first copy-in to last copy-out, CUDA events on the library's copy streams)."""
@@ -143,14 +152,17 @@ class BatchSolver:
         return float(self._L.ttmpc_host_pipeline_ms(h))
 
     def _solve(self, x_init, ref_states, ref_inputs, k_index, traj_states, traj_inputs, z_warm, want_z, stream,
-               q_weights=None, r_weights=None, obstacles=None, traj_index=None, host_async=False, out=None, want_kkt=True):
+               q_weights=None, r_weights=None, obstacles=None, traj_index=None, host_async=False, out=None, want_kkt=True,
+               plan=None):
         if obstacles is not None and not isinstance(obstacles, Obstacles):
             obstacles = Obstacles.from_list(obstacles)
         if (q_weights is None) != (r_weights is None):
             raise ValueError("q_weights and r_weights go together")
         N = self.cfg.horizon
         nz = 8 * N + 6
-        shared = ref_states is None
+        shared = ref_states is None and plan is None
+        if plan is not None and obstacles is None:
+            raise ValueError("the planner needs an obstacle set")
         if shared and (k_index is None or traj_states is None or traj_inputs is None):
             raise ValueError("shared-trajectory mode needs k_index, traj_states and traj_inputs")
         if traj_index is not None and (not shared or obstacles is not None or q_weights is not None):
@@ -215,7 +227,7 @@ class BatchSolver:
                 T = int(ts_shape[0]) - 1
                 pts, ptu = arg(traj_states, (T + 1, 6), name="traj_states"), arg(traj_inputs, (T, 2), name="traj_inputs")
             pk = arg(k_index, (B,), i32, name="k_index")
-        else:
+        elif plan is None:
             prs, pru = arg(ref_states, (B, N + 1, 6), name="ref_states"), arg(ref_inputs, (B, N, 2), name="ref_inputs")
         pzw = arg(z_warm, (B, nz), name="z_warm") if z_warm is not None else None
         pqw = arg(q_weights, (B, 6), name="q_weights") if q_weights is not None else None
@@ -232,7 +244,10 @@ class BatchSolver:
             ptrs[key] = arg(buf, shape, dtype, name=f"out[{key}]")
             res[key] = buf
         o = [ptrs[k] for k in ("z", "u0", "obj", "kkt", "iters", "status")]
-        if obstacles is not None and shared:
+        if plan is not None:
+            keep.append(plan[0])
+            rc = self._L.ttmpc_plan_batch(h, ctypes.byref(obstacles), B, px, plan[0].ctypes.data, plan[1], plan[2], pzw, *o, stream)
+        elif obstacles is not None and shared:
             rc = self._L.ttmpc_obca_solve_batch_shared(h, ctypes.byref(obstacles), B, px, pk, pts, ptu, T, *o, stream)
         elif obstacles is not None:
             rc = self._L.ttmpc_obca_solve_batch(h, ctypes.byref(obstacles), B, px, prs, pru, *o, stream)

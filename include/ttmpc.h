@@ -57,7 +57,7 @@ extern "C" {
 
 #define TTMPC_NX 6
 #define TTMPC_NU 2
-#define TTMPC_MAX_HORIZON 128
+#define TTMPC_MAX_HORIZON 256
 #define TTMPC_MAX_OBSTACLES 16
 
 /* error codes */
@@ -198,6 +198,21 @@ int ttmpc_obca_solve_batch_shared(ttmpc_handle* h, const ttmpc_obstacles* obstac
                                   const double* traj_inputs, int32_t T, double* z_out, double* u0_out,
                                   double* obj_out, double* kkt_out, int32_t* iters_out, int32_t* status_out,
                                   void* cuda_stream);
+
+/* The offline planner TrajectoryOptimization.plan(initial_state, goal_state) (trajectory_optimization.py:311-331; driver:
+ * trajectory_animation.py:41-110 with horizon 200, dt 0.1, the 11 rectangles) for B start states towards one goal: the
+ * obstacle-aware NLP above with
+ *   cost   sum_{k<N} u_k'R u_k + (x_k - goal)'Q(x_k - goal)  +  (x_N - goal)' (terminal_weight Q) (x_N - goal)   (:175-183),
+ *   final-state constraint |x_N - goal| <= terminal_box                                                 (:168-173),
+ *   starting point z_guess [B][8N+6] = the caller's initial trajectory (states and inputs in the z layout; :227-274
+ *   builds it from the Hybrid-A* waypoints, :208-225 as a straight line) or NULL = every state at the goal, zero inputs;
+ *   the OBCA duals start at the reference's constants either way.
+ * goal: host pointer to 6 doubles (configuration, like the obstacle set).  The final-state constraint is held as bounds
+ * of the terminal stage (the reference's range row has a slack that equals x_N - goal).  Outputs as
+ * ttmpc_obca_solve_batch.  One problem runs on one CTA (N = 200, 11 obstacles: 37 k variables). */
+int ttmpc_plan_batch(ttmpc_handle* h, const ttmpc_obstacles* obstacles, int64_t B, const double* x_init, const double* goal,
+                     double terminal_weight, double terminal_box, const double* z_guess, double* z_out, double* u0_out,
+                     double* obj_out, double* kkt_out, int32_t* iters_out, int32_t* status_out, void* cuda_stream);
 
 /* Warm-start shift of B decision vectors (device pointers unless HOST flag in cfg):
  * z_shift[i] = shift(z[i]) as TruckTrailerNMPC._shift_solution. `mode` 0 = intended shift

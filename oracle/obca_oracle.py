@@ -233,8 +233,14 @@ class Pair:
 class ObcaNlp:
     """Index bookkeeping + evaluation of the OBCA NLP with slacks (all variables of stage k contiguous)."""
 
-    def __init__(self, N, dt, L1, L2, M, W1, W2, Q, R, x_lb, x_ub, u_lb, u_ub, obstacles):
+    def __init__(self, N, dt, L1, L2, M, W1, W2, Q, R, x_lb, x_ub, u_lb, u_ub, obstacles, terminal_weight=1.0,
+                 terminal_box=None):
+        """terminal_weight, terminal_box: the offline planner's variant of the NLP (trajectory_optimization.py): terminal
+        cost weight Q_f = terminal_weight * Q (:181: 100) and, with terminal_box = (goal, half_width), the final-state
+        constraint |x_N - goal| <= half_width (:168-173: 1e-2) -- a linear range row whose slack equals x_N - goal, stated
+        here as bounds on x_N (intersected with the state bounds)."""
         self.N, self.dt, self.L1, self.L2, self.M = N, dt, L1, L2, M
+        self.term_w = float(terminal_weight)
         self.Q = 0.5 * (np.asarray(Q, float).reshape(6, 6) + np.asarray(Q, float).reshape(6, 6).T)
         self.R = 0.5 * (np.asarray(R, float).reshape(2, 2) + np.asarray(R, float).reshape(2, 2).T)
         geom = (L1, L2, M, W1, W2)
@@ -258,6 +264,10 @@ class ObcaNlp:
             if k >= 1:
                 lo[self.ix(k)] = x_lb
                 up[self.ix(k)] = x_ub
+                if k == N and terminal_box is not None:
+                    goal, half = np.asarray(terminal_box[0], float), float(terminal_box[1])
+                    lo[self.ix(k)] = np.maximum(np.asarray(x_lb, float), goal - half)
+                    up[self.ix(k)] = np.minimum(np.asarray(x_ub, float), goal + half)
             if k < N:
                 lo[self.iu(k)] = u_lb
                 up[self.iu(k)] = u_ub
@@ -273,6 +283,9 @@ class ObcaNlp:
         self.lo = np.where(self.has_lo, lo - BOUND_RELAX * np.maximum(1.0, np.abs(lo)), -np.inf)
         self.up = np.where(self.has_up, up + BOUND_RELAX * np.maximum(1.0, np.abs(up)), np.inf)
         self.x_lb, self.x_ub = np.asarray(x_lb, float), np.asarray(x_ub, float)
+
+    def Qk(self, k):
+        return self.term_w * self.Q if k == self.N else self.Q
 
     def ix(self, k):
         assert k >= 1
@@ -315,11 +328,12 @@ class ObcaNlp:
     def initial_point(self, x_init, ref_states, ref_inputs, z_warm=None):
         """mpc_control_obs.py:216-239; slacks start at the row values (Ipopt), everything pushed inside its bounds"""
         w = np.zeros(self.n)
+        gx, gu = (ref_states, ref_inputs) if z_warm is None else z_warm  # (states [N+1,6], inputs [N,2]) guess of the caller
         for k in range(self.N + 1):
             if k >= 1:
-                w[self.ix(k)] = ref_states[k]
+                w[self.ix(k)] = gx[k]
             if k < self.N:
-                w[self.iu(k)] = ref_inputs[k]
+                w[self.iu(k)] = gu[k]
             for j in range(self.P):
                 w[self.iv(k, j)] = np.concatenate([np.full(4, MU_GUESS), LAM_GUESS])
         w = self.push_inside(w)
@@ -354,7 +368,7 @@ class ObcaNlp:
         J = 0.0
         for k in range(1, self.N + 1):  # the k = 0 term is a constant of the data x_init (kept for reporting below)
             d = w[self.ix(k)] - ref_states[k]
-            J += d @ self.Q @ d
+            J += d @ self.Qk(k) @ d
         for k in range(self.N):
             d = w[self.iu(k)] - ref_inputs[k]
             J += d @ self.R @ d
@@ -364,7 +378,7 @@ class ObcaNlp:
     def grad(self, w, ref_states, ref_inputs):
         g = np.zeros(self.n)
         for k in range(1, self.N + 1):
-            g[self.ix(k)] = 2.0 * self.Q @ (w[self.ix(k)] - ref_states[k])
+            g[self.ix(k)] = 2.0 * self.Qk(k) @ (w[self.ix(k)] - ref_states[k])
         for k in range(self.N):
             g[self.iu(k)] = 2.0 * self.R @ (w[self.iu(k)] - ref_inputs[k])
         return g
@@ -405,7 +419,7 @@ class ObcaNlp:
     def hessian(self, w, y, x_init):
         H = np.zeros((self.n, self.n))
         for k in range(1, self.N + 1):
-            H[np.ix_(self.ix(k), self.ix(k))] += 2.0 * self.Q
+            H[np.ix_(self.ix(k), self.ix(k))] += 2.0 * self.Qk(k)
         for k in range(self.N):
             H[np.ix_(self.iu(k), self.iu(k))] += 2.0 * self.R
         for k in range(2, self.N + 1):  # dynamics rows k depend nonlinearly on x_{k-1}
@@ -439,7 +453,7 @@ def stage_blocks(nlp: "ObcaNlp", w, y, x_init):
         Jp = np.zeros((4 * P, nk))
         lx = nlp.ix(k) - o if k >= 1 else None
         if k >= 1:
-            H[np.ix_(lx, lx)] += 2.0 * nlp.Q
+            H[np.ix_(lx, lx)] += 2.0 * nlp.Qk(k)
         if k < nlp.N:
             lu_ = nlp.iu(k) - o
             H[np.ix_(lu_, lu_)] += 2.0 * nlp.R
@@ -595,14 +609,14 @@ def _inertia(lu, d, piv):
 
 
 def solve(nlp: ObcaNlp, x_init, ref_states, ref_inputs, tol=1e-8, acc_tol=1e-6, acc_iter=15, max_iter=5000,
-          mu_init=0.1, verbose=False, linear_solver="dense", recover=True):
+          mu_init=0.1, verbose=False, linear_solver="dense", recover=True, guess=None):
     """Returns dict(states[N+1,6], inputs[N,2], obj, iters, status, kkt=(dual_inf, constr_viol, compl), w)."""
     x_init = np.asarray(x_init, float)
     ref_states = np.asarray(ref_states, float).reshape(nlp.N + 1, 6)
     ref_inputs = np.asarray(ref_inputs, float).reshape(nlp.N, 2)
     n, m = nlp.n, nlp.m
     hl, hu = nlp.has_lo, nlp.has_up
-    w = nlp.initial_point(x_init, ref_states, ref_inputs)
+    w = nlp.initial_point(x_init, ref_states, ref_inputs, guess)
     y = np.zeros(m)
     zl = np.where(hl, 1.0, 0.0)
     zu = np.where(hu, 1.0, 0.0)

@@ -84,6 +84,34 @@ def obca_lib():
     return _olib
 
 
+def plan_terminal_config(cfg, goal, terminal_weight, terminal_box):
+    """configuration of the terminal stage of the planner's NLP, as ttmpc_plan_batch builds it"""
+    import copy
+    ct = copy.deepcopy(cfg)
+    for i in range(36):
+        ct.Q[i] = cfg.Q[i] * terminal_weight
+    if terminal_box > 0:
+        for i in range(6):
+            ct.x_lb[i] = max(cfg.x_lb[i], goal[i] - terminal_box)
+            ct.x_ub[i] = min(cfg.x_ub[i], goal[i] + terminal_box)
+    return ct
+
+
+def obca_plan_batch(cfg, obstacles, x_init, goal, terminal_weight=100.0, terminal_box=1e-2, z_guess=None, wide_warps=0):
+    """host build of ttmpc_plan_batch (csrc/ttmpc.cu): same one-record shared trajectory, same terminal-stage parameters"""
+    goal = np.ascontiguousarray(goal, dtype=np.float64).reshape(6)
+    x = np.ascontiguousarray(x_init, dtype=np.float64).reshape(-1, 6)
+    ct = plan_terminal_config(cfg, goal, terminal_weight, terminal_box)
+    zg = None if z_guess is None else np.ascontiguousarray(z_guess, dtype=np.float64).reshape(x.shape[0], 8 * cfg.horizon + 6)
+    dp = ctypes.POINTER(ctypes.c_double)
+    obca_lib().ttmpc_emu_obca_set_plan(ctypes.byref(ct), None if zg is None else zg.ctypes.data_as(dp))
+    try:
+        return obca_solve_batch(cfg, obstacles, x, k_index=np.zeros(x.shape[0], np.int32), traj_states=np.stack([goal, goal]),
+                                traj_inputs=np.zeros((1, 2)), wide_warps=wide_warps)
+    finally:
+        obca_lib().ttmpc_emu_obca_set_plan(None, None)
+
+
 def obca_solve_batch(cfg, obstacles, x_init, ref_states=None, ref_inputs=None, k_index=None, traj_states=None,
                      traj_inputs=None, wide_warps=0):
     """wide_warps > 0: the CTA-per-problem flavour of the kernel (stages dealt to that many virtual warps)."""

@@ -15,6 +15,16 @@ using namespace ttmpc;
 static int g_wide_warps = 0;
 extern "C" void ttmpc_emu_obca_set_wide(int warps) { g_wide_warps = warps; }
 
+static ttmpc_config g_term_cfg;
+static bool g_have_term = false;
+static const double* g_guess = nullptr;
+// planner variant (ttmpc_plan_batch): terminal-stage configuration and the caller's initial trajectory for the next call
+extern "C" void ttmpc_emu_obca_set_plan(const ttmpc_config* term_cfg, const double* z_guess) {
+  g_have_term = term_cfg != nullptr;
+  if (term_cfg) g_term_cfg = *term_cfg;
+  g_guess = z_guess;
+}
+
 extern "C" int ttmpc_emu_obca_solve_batch(const ttmpc_config* cfg, const ttmpc_obstacles* obs, int64_t B, const double* x_init,
                                           const double* ref_states, const double* ref_inputs, const int32_t* k_index,
                                           const double* traj_states, const double* traj_inputs, int32_t T, double* z_out,
@@ -26,9 +36,14 @@ extern "C" int ttmpc_emu_obca_solve_batch(const ttmpc_config* cfg, const ttmpc_o
   obca::ObParams o;
   rc = obca::build_obparams(cfg, obs, &o);
   if (rc) return rc;
+  Params pT = p;
+  if (g_have_term) {
+    rc = build_params(&g_term_cfg, &pT);
+    if (rc) return rc;
+  }
   const int64_t L = B < 3 ? B : 3;  // a few problem slots with refill
   std::vector<double> scratch(obca::scratch_doubles(p.N, (size_t)L), NAN);
-  ProblemIn in{x_init, ref_states, ref_inputs, nullptr, k_index, traj_states, traj_inputs, T, nullptr, nullptr};
+  ProblemIn in{x_init, ref_states, ref_inputs, g_guess, k_index, traj_states, traj_inputs, T, nullptr, nullptr};
   const size_t nz = 8 * (size_t)p.N + 6;
   for (int64_t l = 0; l < L; l++) {
     double* s0 = obca::slot_ptr(scratch.data(), p.N, (size_t)l);
@@ -38,10 +53,10 @@ extern "C" int ttmpc_emu_obca_solve_batch(const ttmpc_config* cfg, const ttmpc_o
         std::vector<double> part((size_t)g_wide_warps * obca::kPart, NAN), bcast(32, NAN);
         obca::Ctx c;
         c.wd.wid = 0, c.wd.nw = g_wide_warps, c.wd.part = part.data(), c.wd.bcast = bcast.data();
-        c.p = &p, c.o = &o, c.s0 = s0;
+        c.p = &p, c.pT = &pT, c.o = &o, c.s0 = s0;
         obca::solve_problem<true>(c, in, b, r);
       } else {
-        obca::solve_lane(p, o, s0, in, b, r);
+        obca::solve_lane(p, pT, o, s0, in, b, r);
       }
       if (z_out) obca::unpack(p, s0, z_out + b * nz);
       if (u0_out) { u0_out[b * 2] = obca::bld(s0, obca::oW + 6); u0_out[b * 2 + 1] = obca::bld(s0, obca::oW + 7); }
