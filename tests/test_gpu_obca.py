@@ -223,3 +223,17 @@ def test_obca_edge_cases():
         s.solve_obca(bad, x0, xs, us)
     with pytest.raises(ValueError):
         Obstacles.from_list([(0.0, 0.0, 1.0, 1.0)] * 17)
+
+
+@pytest.mark.parametrize("name", ["n6_k300_2obs", "n12_k60_blocked"])
+def test_gpu_reaches_the_slsqp_minimiser_of_the_obstacle_aware_nlp(name):
+    """The GPU's output against an algorithm that shares nothing with Ipopt's rules (tools/make_golden_slsqp_obca.py)."""
+    g = np.load(os.path.join(os.path.dirname(GOLD_OBCA_FULL), "slsqp_obca.npz"))
+    c = next(x for x in CASES if x["name"] == name)
+    cfg, obs = case_problem(c)
+    r = solver(cfg).solve_obca(obs, c["x_init"][None], c["ref_states"][None], c["ref_inputs"][None])
+    assert r["status"][0] == 0 and int(g[name + "/success"]) == 1
+    xs, us = split_z(r["z"][0], cfg.horizon)
+    assert np.abs(r["u0"][0] - g[name + "/inputs"][0]).max() <= U0_ABS_TOL
+    assert np.abs(xs - g[name + "/states"]).max() <= 1e-5 and np.abs(us - g[name + "/inputs"]).max() <= 1e-5
+    assert abs(r["obj"][0] - float(g[name + "/obj"])) <= 5e-6 * abs(r["obj"][0])

@@ -294,3 +294,25 @@ def test_cta_per_problem_decomposition_is_bit_identical(warps):
         assert a["status"][0] == b["status"][0] and a["iters"][0] == b["iters"][0]
         assert np.array_equal(a["z"], b["z"]) and np.array_equal(a["kkt"], b["kkt"])
         assert abs(a["obj"][0] - b["obj"][0]) <= 1e-14 * abs(a["obj"][0])  # the reported sum is taken in another order
+
+
+# objective: SLSQP stops at the resolution of its finite-difference gradients on the case with active rows
+SLSQP_OBJ_REL_TOL = 5e-6
+
+
+@pytest.mark.parametrize("name", ["n6_k300_2obs", "n12_k60_blocked"])
+def test_oracle_and_kernel_core_reach_the_slsqp_minimiser(name):
+    """Independent algorithm for the obstacle-aware NLP: SciPy SLSQP on the literal inequality form of
+    mpc_control_obs.py:65-176 (tools/make_golden_slsqp_obca.py: no slacks, no barrier, no code shared with the oracle).
+    The dense oracle's golden solution and the kernel core (host build) must be that minimiser -- first control within the
+    north-star tolerance, states and inputs within 1e-5; one of the two cases has active collision rows."""
+    g = np.load(os.path.join(os.path.dirname(GOLD_OBCA_FULL), "slsqp_obca.npz"))
+    assert int(g[name + "/success"]) == 1
+    c = next(x for x in CASES if x["name"] == name)
+    cfg, obs = case_problem(c)
+    r = emu.obca_solve_batch(cfg, obs, c["x_init"][None], c["ref_states"][None], c["ref_inputs"][None])
+    xs, us = split_z(r["z"][0], cfg.horizon)
+    for X, U, J in ((c["states"], c["inputs"], float(c["obj"])), (xs, us, float(r["obj"][0]))):
+        assert np.abs(U[0] - g[name + "/inputs"][0]).max() <= U0_ABS_TOL
+        assert np.abs(X - g[name + "/states"]).max() <= 1e-5 and np.abs(U - g[name + "/inputs"]).max() <= 1e-5
+        assert abs(J - float(g[name + "/obj"])) <= SLSQP_OBJ_REL_TOL * abs(J)
