@@ -74,6 +74,15 @@ enum : int { ST_CONVERGED = 0, ST_ACCEPTABLE = 1, ST_MAX_ITER = 2, ST_LINESEARCH
 
 // ---- scratch layout: rows of one stage ----
 constexpr int kBank = TTMPC_BANK;  // slots per bank = element stride between rows
+// TTMPC_KF_F32 (experiment switch): the feedback gains K and k_ff -- written by the backward sweep, read once by the
+// forward sweep, used for nothing but the search direction -- are stored as pairs of floats in 8 rows instead of 16.
+#ifndef TTMPC_KF_F32
+#define TTMPC_KF_F32 0
+#endif
+constexpr int kKfRows = TTMPC_KF_F32 ? 8 : 16;
+#if TTMPC_SPECULATION && TTMPC_KF_F32
+#error "TTMPC_KF_F32 is an experiment of the shipped row layout"
+#endif
 #if !TTMPC_SPECULATION
 constexpr int rW = 0;              // w_k = (x_k, u_k)                       8
 constexpr int rDW = 8;             // search direction                       8
@@ -83,12 +92,6 @@ constexpr int rZL = 30;            // lower-bound multipliers (x 0..5, u 6..7) 8
 constexpr int rZU = 38;            // upper-bound multipliers                8
 constexpr int rKF = 46;            // K (2x6), kff0 (2), kff1 (2)            16 (8 with TTMPC_KF_F32)
 constexpr int kAlt = 0;
-// TTMPC_KF_F32 (experiment switch): the feedback gains K and k_ff -- written by the backward sweep, read once by the
-// forward sweep, used for nothing but the search direction -- are stored as pairs of floats in 8 rows instead of 16.
-#ifndef TTMPC_KF_F32
-#define TTMPC_KF_F32 0
-#endif
-constexpr int kKfRows = TTMPC_KF_F32 ? 8 : 16;
 #ifdef TTMPC_STAGE_ROWS  // experiment builds: padded stage stride (e.g. 64 rows = 16 KB per stage and warp), DESIGN.md section 8
 constexpr int kRows = TTMPC_STAGE_ROWS;
 static_assert(kRows >= 46 + kKfRows, "a stage needs 46 rows + the gains");

@@ -228,7 +228,7 @@ def test_obca_edge_cases():
 @pytest.mark.parametrize("name", ["n6_k300_2obs", "n12_k60_blocked"])
 def test_gpu_reaches_the_slsqp_minimiser_of_the_obstacle_aware_nlp(name):
     """The GPU's output against an algorithm that shares nothing with Ipopt's rules (tools/make_golden_slsqp_obca.py)."""
-    g = np.load(os.path.join(os.path.dirname(GOLD_OBCA_FULL), "slsqp_obca.npz"))
+    g = np.load(os.path.join(os.path.dirname(GOLD_OBCA_FULL), "obca_slsqp.npz"))
     c = next(x for x in CASES if x["name"] == name)
     cfg, obs = case_problem(c)
     r = solver(cfg).solve_obca(obs, c["x_init"][None], c["ref_states"][None], c["ref_inputs"][None])

@@ -247,8 +247,9 @@ def test_bulk_staged_experiment_build_is_bit_identical():
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     lib = os.path.join(root, "tools", "ab", "libttmpc_bulk.so")
-    if not os.path.exists(lib):
-        pytest.skip("experiment library not built")
+    srcs = [os.path.join(root, "car_trailer_mpc_b200", "csrc", f) for f in ("ttmpc.cu", "ttmpc_core.cuh", "ttmpc_obca.cuh", "ttmpc_team.cuh")]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(f) for f in srcs + [os.path.join(root, "include", "ttmpc.h")]):
+        pytest.skip("experiment library not built (or older than the sources)")
     out = {}
     for name, env in (("shipped", {}), ("bulk", {"TTMPC_LIB": lib})):
         e = dict(os.environ, **env)

@@ -306,7 +306,7 @@ def test_oracle_and_kernel_core_reach_the_slsqp_minimiser(name):
     mpc_control_obs.py:65-176 (tools/make_golden_slsqp_obca.py: no slacks, no barrier, no code shared with the oracle).
     The dense oracle's golden solution and the kernel core (host build) must be that minimiser -- first control within the
     north-star tolerance, states and inputs within 1e-5; one of the two cases has active collision rows."""
-    g = np.load(os.path.join(os.path.dirname(GOLD_OBCA_FULL), "slsqp_obca.npz"))
+    g = np.load(os.path.join(os.path.dirname(GOLD_OBCA_FULL), "obca_slsqp.npz"))
     assert int(g[name + "/success"]) == 1
     c = next(x for x in CASES if x["name"] == name)
     cfg, obs = case_problem(c)

@@ -2,7 +2,7 @@
 of mpc_control_obs.py -- decision variables (x_k, u_k, mu_k, lam_k) with x_0 pinned by an equality, the collision rows of
 :65-139 as INEQUALITIES (no slacks, no barrier), bounds of :141-176 -- written here from the reference's formulas with
 numpy only.  Neither the oracle nor the kernels are involved; gradients are SLSQP's own finite differences except for the
-cost.   python tools/make_golden_slsqp_obca.py   -> tests/golden/slsqp_obca.npz
+cost.   python tools/make_golden_slsqp_obca.py   -> tests/golden/obca_slsqp.npz
 Cases: two of tests/golden/obca_cases.npz's problems (inputs copied from there: x_init, window, rectangles) -- a
 2-obstacle case without active rows and the case whose solution is pressed against a blocking obstacle (SLSQP stops there
 with "positive directional derivative for linesearch", i.e. at the resolution of its finite differences: feasible to 6e-13,
@@ -133,5 +133,5 @@ if __name__ == "__main__":
         out[name + "/success"] = int(res.status in (0, 8) and viol < 1e-7)  # 8: positive directional derivative (precision reached)
         out[name + "/slsqp_status"] = int(res.status)
         out[name + "/nit"] = res.nit
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "slsqp_obca.npz"), scipy_version=scipy.__version__,
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "obca_slsqp.npz"), scipy_version=scipy.__version__,
                         generator="tools/make_golden_slsqp_obca.py", git_commit=commit, seed=77, **out)
