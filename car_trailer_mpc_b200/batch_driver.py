@@ -37,14 +37,15 @@ def run_one(preset: str, horizon: int, batch: int, sigma: str, families: bool, d
     dev = torch.device("cuda", device)
     s = BatchSolver(cfg, device)
     x, xs, us = (torch.from_numpy(a).to(dev) for a in (sc.x_init, sc.ref_states, sc.ref_inputs))
-    r = s.solve(x, xs, us, want_z=False)  # warm-up
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(repeats):
-        r = s.solve(x, xs, us, want_z=False)
-    e1.record()
-    torch.cuda.synchronize(dev)
+    with torch.cuda.device(dev):  # events and the current stream belong to --device, not to the process's default device
+        r = s.solve(x, xs, us, want_z=False)  # warm-up
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(repeats):
+            r = s.solve(x, xs, us, want_z=False)
+        e1.record()
+        torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / repeats
     st = r["status"].cpu().numpy()
     it = r["iters"].cpu().numpy()

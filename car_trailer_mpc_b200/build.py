@@ -35,9 +35,12 @@ def nvcc_path() -> str:
 
 
 def is_stale() -> bool:
-    if not os.path.exists(LIB):
+    out = os.environ.get("TTMPC_BUILD_OUT") or LIB  # experiment builds are judged by their own output file
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(LIB)
+    if os.environ.get("TTMPC_NVCC_FLAGS") and out == LIB:
+        return True  # extra flags aimed at the shipped library: always rebuild
+    t = os.path.getmtime(out)
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 

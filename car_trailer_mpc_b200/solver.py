@@ -271,7 +271,9 @@ class BatchSolver:
         if _is_torch(z):
             import torch
 
-            assert z.dtype == torch.float64 and z.is_contiguous() and z.shape[-1] == nz
+            if not (z.dtype == torch.float64 and z.is_contiguous() and z.shape[-1] == nz and z.device.type == "cuda"
+                    and z.device.index == self.device):
+                raise ValueError(f"shift_warm_start: z must be a contiguous float64 tensor [..., {nz}] on cuda:{self.device}")
             out = torch.empty_like(z)
             if stream is None:
                 stream = torch.cuda.current_stream(z.device).cuda_stream
@@ -333,7 +335,13 @@ class BatchSolver:
         if _is_torch(q):
             import torch
 
-            assert q.dtype == torch.float64 and q.is_contiguous() and u.is_contiguous()
+            B = q.shape[0] if q.dim() == 2 else -1
+            for name, t, shape in (("q", q, (B, 6)), ("u", u, (B, 2)), ("noise", noise, (B, 6))):
+                if t is None and name == "noise":
+                    continue
+                if not (_is_torch(t) and t.dtype == torch.float64 and t.is_contiguous() and t.device == q.device
+                        and tuple(t.shape) == shape and t.device.type == "cuda" and t.device.index == self.device):
+                    raise ValueError(f"plant_step: {name} must be a contiguous float64 tensor of shape {shape} on cuda:{self.device}")
             out = torch.empty_like(q)
             if stream is None:
                 stream = torch.cuda.current_stream(q.device).cuda_stream
