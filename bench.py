@@ -58,7 +58,7 @@ def algorithmic_bytes_per_solve(N: int) -> int:
 
 class ClockSampler:
     """Samples SM clocks / throttle reasons of one GPU while the timed region runs: one long-lived
-    `nvidia-smi -lms 50` process (a fresh nvidia-smi per sample would take longer than a whole timed region)."""
+    `nvidia-smi -lms 100` process (a fresh nvidia-smi per sample would take longer than a whole timed region)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.proc.stdout.readline()  # first sample = process is up; the timed region starts after this
         except Exception:
             self.proc = None
@@ -78,7 +78,7 @@ class ClockSampler:
     def finish(self) -> dict:
         samples = []
         if self.proc is not None:
-            time.sleep(0.06)
+            time.sleep(0.11)
             self.proc.terminate()
             try:
                 out, _ = self.proc.communicate(timeout=5)
@@ -419,7 +419,7 @@ def main() -> None:
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(N, B, world),
-            "p50_step_ms": p50_ms, "p99_step_ms": p99_ms, "latency_steps": int(len(per_lat)), "control_period_ms": 50.0,
+            "p50_step_ms": p50_ms, "p99_step_ms": p99_ms, "timed_step_ms": [round(float(v), 3) for v in per_ms], "latency_steps": int(len(per_lat)), "control_period_ms": 50.0,
             "solve_kernel": "ttmpc_team_kernel" if lanes_headline else "ttmpc_solve_kernel", "lanes_per_problem": lanes_headline,
             "mean_iters": mean_iters, "max_iters": int(iters.max()), "frac_success": ok_sum / b_sum,
             "kkt_max": {"dual_inf": float(kkt[status == 0, 0].max()), "constr_viol": float(kkt[status == 0, 1].max()),

@@ -17,7 +17,7 @@ import numpy as np
 
 NX = 6
 NU = 2
-MAX_HORIZON = 128
+MAX_HORIZON = 256
 MAX_OBSTACLES = 16
 
 # status codes (include/ttmpc.h)
