@@ -573,6 +573,9 @@ constexpr int kObcaThreads = TTMPC_OBCA_THREADS;  // 8 warps = 8 problem slots p
 #ifndef TTMPC_OBCA_LOCKSTEP
 #define TTMPC_OBCA_LOCKSTEP 2
 #endif
+#ifndef TTMPC_OBCA_ALIGN
+#define TTMPC_OBCA_ALIGN 1
+#endif
 #if TTMPC_OBCA_LOCKSTEP == 1
 #define OB_CTA_ANY(x) __syncthreads_or(x)   // every phase aligned
 #define OB_ROUND_ANY(x) __syncthreads_or(x)
@@ -600,6 +603,7 @@ __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
   obca::Lane L;
   bool active = false, exhausted = false;
   long long b = -1;
+  unsigned round = 0;
   for (;;) {
     if (!active && !exhausted) {
       if (lane == 0) b = (long long)atomicAdd(counter, 1ull);
@@ -611,7 +615,13 @@ __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
         exhausted = true;
       }
     }
-    if (!OB_ROUND_ANY(active)) break;
+    // the start of an iteration is aligned across the CTA every TTMPC_OBCA_ALIGN-th round (1: every round); in between
+    // the warps run on, so that one warp's extra factorisation or line-search trial is not waited for by the other seven
+    if ((round++ % TTMPC_OBCA_ALIGN) == 0) {
+      if (!OB_ROUND_ANY(active)) break;
+    } else if (!active) {
+      continue;
+    }
     Result res;
     bool done = false;
     if (active) done = obca::lane_head(c, L, res);
