@@ -529,8 +529,8 @@ TT_HD bool init_point(const Ctx& c0, const ProblemIn& in, long long b) {
   for (int wv = 0; wv < (WIDE ? c0.wd.nw : 1); wv++) {  // host: the warps of the CTA one after the other
   c.wd.wid = wv;
 #endif
-  for (int k = 0; k <= N; k++) {
-    if (WIDE && (k % c.wd.nw) != c.wd.wid) continue;
+  // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
+  for (int k = (WIDE) ? c.wd.wid : 0, kstep = (WIDE) ? c.wd.nw : 1; k <= N; k += kstep) {
     double* ps = c.stage(k);
     const Params& p = (k == N) ? *c0.pT : p0;  // the terminal stage may have its own bounds and weight
     double x[NX];
@@ -590,8 +590,8 @@ TT_HD void restart_point(const Ctx& c0) {
   for (int wv = 0; wv < (WIDE ? c0.wd.nw : 1); wv++) {  // host: the warps of the CTA one after the other
   c.wd.wid = wv;
 #endif
-  for (int k = 0; k <= N; k++) {
-    if (WIDE && (k % c.wd.nw) != c.wd.wid) continue;
+  // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
+  for (int k = (WIDE) ? c.wd.wid : 0, kstep = (WIDE) ? c.wd.nw : 1; k <= N; k += kstep) {
     double* ps = c.stage(k);
     const Params& p = (k == N) ? *c0.pT : p0;  // the terminal stage may have its own bounds and weight
     double x[NX];
@@ -646,8 +646,8 @@ TT_HD void update_stats(const Ctx& c, bool do_update, double alpha, double alpha
   double xn[NX], ln[NX];  // x_{k+1}, lambda_{k+1} at the new iterate
   for (int j = 0; j < NX; j++) xn[j] = ln[j] = 0.0;
   if (MODE == 3) do_update = false;  // the step was applied by the pair phase
-  for (int k = N; k >= 0; k--) {
-    if ((MODE == 1 || MODE == 3) && (k % c.wd.nw) != c.wd.wid) continue;
+  // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
+  for (int k = (MODE == 1 || MODE == 3) ? N - ((N - c.wd.wid) % c.wd.nw + c.wd.nw) % c.wd.nw : N, kstep = (MODE == 1 || MODE == 3) ? c.wd.nw : 1; k >= 0; k -= kstep) {
     double* ps = c.stage(k);
     const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
@@ -900,8 +900,8 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
   if (MODE == 2)  // the pair phase found a block that is not positive definite
     for (int w_ = 0; w_ < c.wd.nw; w_++)
       if (c.wd.part[w_ * kPart] == 0.0) return false;
-  for (int k = N; k >= 0; k--) {
-    if (MODE == 1 && (k % c.wd.nw) != c.wd.wid) continue;
+  // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
+  for (int k = (MODE == 1) ? N - ((N - c.wd.wid) % c.wd.nw + c.wd.nw) % c.wd.nw : N, kstep = (MODE == 1) ? c.wd.nw : 1; k >= 0; k -= kstep) {
     double* ps = c.stage(k);
     const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
@@ -1144,8 +1144,8 @@ TT_HD bool factor_fused(const Ctx& c, double mu, double delta) {
   if (MODE == 2)  // the pair phase found a block that is not positive definite
     for (int w_ = 0; w_ < c.wd.nw; w_++)
       if (c.wd.part[w_ * kPart] == 0.0) return false;
-  for (int k = N; k >= 0; k--) {
-    if (MODE == 1 && (k % c.wd.nw) != c.wd.wid) continue;
+  // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
+  for (int k = (MODE == 1) ? N - ((N - c.wd.wid) % c.wd.nw + c.wd.nw) % c.wd.nw : N, kstep = (MODE == 1) ? c.wd.nw : 1; k >= 0; k -= kstep) {
     double* ps = c.stage(k);
     const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
@@ -1364,8 +1364,8 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
   dq.gphi_d = 0.0;
   double dx[NX];
   for (int i = 0; i < NX; i++) dx[i] = 0.0;
-  for (int k = 0; k <= N; k++) {
-    if (MODE == 1 && (k % c.wd.nw) != c.wd.wid) continue;
+  // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
+  for (int k = (MODE == 1) ? c.wd.wid : 0, kstep = (MODE == 1) ? c.wd.nw : 1; k <= N; k += kstep) {
     double* ps = c.stage(k);
     const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
@@ -1519,8 +1519,8 @@ TT_HD void trial(const Ctx& c, double alpha, TrialOut& tr) {
   bool q_inside = true;
   double xn[NX];
   for (int i = 0; i < NX; i++) xn[i] = 0.0;
-  for (int k = N; k >= 0; k--) {
-    if (MODE == 1 && (k % c.wd.nw) != c.wd.wid) continue;
+  // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
+  for (int k = (MODE == 1) ? N - ((N - c.wd.wid) % c.wd.nw + c.wd.nw) % c.wd.nw : N, kstep = (MODE == 1) ? c.wd.nw : 1; k >= 0; k -= kstep) {
     double* ps = c.stage(k);
     const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
