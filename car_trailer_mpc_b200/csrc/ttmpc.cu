@@ -662,8 +662,14 @@ __global__ void __launch_bounds__(kObcaThreads)
   __shared__ double s_part[(kObcaThreads / 32) * obca::kPart];
   __shared__ double s_bcast[32];
   __shared__ long long s_b;
+  __shared__ int s_flag[TTMPC_MAX_HORIZON + 1];  // stage hand-over of the pipelined factor / direction sweeps
+  int sweep_epoch = 0;
+  for (int i = threadIdx.x; i <= TTMPC_MAX_HORIZON; i += blockDim.x) s_flag[i] = 0;
   obca::Ctx c;
   c.wd.wid = (int)(threadIdx.x >> 5), c.wd.nw = (int)(blockDim.x >> 5), c.wd.part = s_part, c.wd.bcast = s_bcast;
+#ifndef TTMPC_OBCA_NO_PIPELINE
+  c.wd.flag = s_flag, c.wd.epoch = &sweep_epoch;
+#endif
   c.p = &p, c.pT = &pT, c.o = &o, c.s0 = obca::slot_ptr(scratch, p.N, blockIdx.x);
   const long long nz = 8LL * p.N + 6;
   for (;;) {

@@ -477,7 +477,16 @@ struct Wide {
   int wid, nw;
   double* part;   // [nw][kPart]
   double* bcast;  // [32]: results of warp 0 for the other warps
+  // Pipelined factor / direction sweeps of the CTA-per-problem kernel: the stage-local (pair) work of these two sweeps
+  // is dealt to warps 1 .. nw-1 (dn = nw-1, di = wid-1) while warp 0 runs the recursion over the stages CONCURRENTLY;
+  // a stage is handed from one to the other through flag[k] (shared memory) = +-epoch, so the recursion trails the pair
+  // work (factor) or leads it (direction) by a few stages instead of waiting for all of it at a CTA barrier.
+  int dn = 0, di = 0;     // dn > 0: the stages of a MODE-1 sweep are dealt to dn warps, this warp being number di
+  int* flag = nullptr;    // [N+1]
+  int* epoch = nullptr;   // this warp's sweep counter (the same in every warp: control flow is CTA-uniform)
 };
+TT_HD int deal_n(const Wide& w) { return w.dn > 0 ? w.dn : w.nw; }
+TT_HD int deal_i(const Wide& w) { return w.dn > 0 ? w.di : w.wid; }
 struct Ctx {
   Wide wd;
   const Params* p;
@@ -488,6 +497,37 @@ struct Ctx {
   TT_HD double* stage(int k) const { return s0 + (size_t)k * kStageDoubles; }
 };
 TT_HD double* pair_ptr(double* ps, int j) { return ps + kBasePad + j; }
+
+// hand-over of stage k between the warps of a pipelined sweep (no-ops unless Wide::flag is set: device, wide kernel)
+TT_HD void ob_publish(const Ctx& c, int k, bool ok) {
+#if defined(__CUDA_ARCH__)
+  if (c.wd.flag == nullptr) return;
+  __threadfence_block();  // this warp's stores to the stage's rows before the flag
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) ((volatile int*)c.wd.flag)[k] = ok ? *c.wd.epoch : -*c.wd.epoch;
+#else
+  (void)c; (void)k; (void)ok;
+#endif
+}
+// true: stage k is ready; false: its owner found a pair block that is not positive definite
+TT_HD bool ob_await(const Ctx& c, int k) {
+#if defined(__CUDA_ARCH__)
+  if (c.wd.flag == nullptr) return true;
+  const int ep = *c.wd.epoch;
+  int v;
+  for (;;) {
+    v = ((volatile int*)c.wd.flag)[k];
+    if (v == ep || v == -ep) break;
+    __nanosleep(64);
+  }
+  __syncwarp();
+  __threadfence_block();
+  return v == ep;
+#else
+  (void)c; (void)k;
+  return true;
+#endif
+}
 
 TT_HD void dense_A(const Lin& m, double (*A)[NX]) {
   TT_UNROLL
@@ -897,15 +937,16 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
     pn[i] = xn[i] = ln[i] = 0.0;
     for (int j = 0; j < NX; j++) Pn[i][j] = 0.0;
   }
-  if (MODE == 2)  // the pair phase found a block that is not positive definite
+  if (MODE == 2 && c.wd.flag == nullptr)  // the pair phase found a block that is not positive definite
     for (int w_ = 0; w_ < c.wd.nw; w_++)
       if (c.wd.part[w_ * kPart] == 0.0) return false;
   // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
-  for (int k = (MODE == 1) ? N - ((N - c.wd.wid) % c.wd.nw + c.wd.nw) % c.wd.nw : N, kstep = (MODE == 1) ? c.wd.nw : 1; k >= 0; k -= kstep) {
+  for (int k = (MODE == 1) ? N - ((N - deal_i(c.wd)) % deal_n(c.wd) + deal_n(c.wd)) % deal_n(c.wd) : N, kstep = (MODE == 1) ? deal_n(c.wd) : 1; k >= 0; k -= kstep) {
     double* ps = c.stage(k);
     const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW], g[NW], sig[NW];
+    if (MODE == 2 && !ob_await(c, k)) return false;  // pipelined: the stage's warp has left its blocks (or found one not PD)
     if (MODE == 2) {  // everything stage-local was prepared by the stage's warp
       for (int j = 0; j < NW; j++) w[j] = g[j] = sig[j] = 0.0;
     } else {
@@ -1002,6 +1043,7 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
     }
     if (MODE != 2 && !ob_all(ok)) {
       if (MODE == 1 && ob_lane0()) c.wd.part[c.wd.wid * kPart] = 0.0;
+      if (MODE == 1) ob_publish(c, k, false);
       return false;
     }
     if (MODE != 2) {
@@ -1046,6 +1088,7 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
         for (int i = 0; i < NX; i++)
           for (int j = i; j < NX; j++) bst(ps, oHX + SY(i, j), Hx[i][j]);
       }
+      ob_publish(c, k, true);  // pipelined: the recursion on warp 0 may take this stage now
       continue;
     }
     if (MODE == 2) {
@@ -1365,8 +1408,9 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
   double dx[NX];
   for (int i = 0; i < NX; i++) dx[i] = 0.0;
   // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
-  for (int k = (MODE == 1) ? c.wd.wid : 0, kstep = (MODE == 1) ? c.wd.nw : 1; k <= N; k += kstep) {
+  for (int k = (MODE == 1) ? deal_i(c.wd) : 0, kstep = (MODE == 1) ? deal_n(c.wd) : 1; k <= N; k += kstep) {
     double* ps = c.stage(k);
+    if (MODE == 1) ob_await(c, k);  // pipelined: the recursion on warp 0 has stored this stage's dx, du
     const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW], g[NW];
@@ -1419,6 +1463,7 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
       }
       di.gphi_d += gb * dw[j];
     }
+    if (MODE == 2) ob_publish(c, k, true);  // pipelined: dx_k, du_k are in the stage's rows, its warp may take the pairs
     // pairs: dv = -K_vv^-1 (q + K_vx dxt),  ds = J_x dxt + J_v dv + r_c
     Trig t;
     if (MODE != 2) stage_trig(w, t);
@@ -1654,6 +1699,19 @@ TT_HD bool run_factor(const Ctx& c, double mu, double delta) {
   if (!WIDE) return factor_fused(c, mu, delta);
 #if defined(__CUDA_ARCH__)
   ob_cta_sync();
+  if (c.wd.flag != nullptr && c.wd.nw >= 3) {  // pipelined: warps 1.. condense the pairs, warp 0 trails them with the recursion
+    ++*c.wd.epoch;
+    Ctx cw = c;
+    cw.wd.dn = c.wd.nw - 1, cw.wd.di = c.wd.wid - 1;
+    if (c.wd.wid == 0) {
+      const bool ok = factor<2>(cw, mu, delta);
+      if (ob_lane0()) c.wd.bcast[0] = ok ? 1.0 : 0.0;
+    } else {
+      factor<1>(cw, mu, delta);
+    }
+    ob_cta_sync();
+    return c.wd.bcast[0] != 0.0;
+  }
   factor<1>(c, mu, delta);
   ob_cta_sync();
   if (c.wd.wid == 0) {
@@ -1681,10 +1739,26 @@ TT_HD void run_direction(const Ctx& c, double mu, double tau, double delta, Dir&
   Dir dummy;
 #if defined(__CUDA_ARCH__)
   ob_cta_sync();
-  if (c.wd.wid == 0) direction<2>(c, mu, tau, delta, dummy);  // the dx / lambda+ recursion
-  ob_cta_sync();
-  direction<1>(c, mu, tau, delta, dummy);  // pairs and step limits, stage k on warp k % nw
-  ob_cta_sync();
+  if (c.wd.flag != nullptr && c.wd.nw >= 3) {  // pipelined: warp 0 leads with the recursion, warps 1.. follow with the pairs
+    ++*c.wd.epoch;
+    Ctx cw = c;
+    cw.wd.dn = c.wd.nw - 1, cw.wd.di = c.wd.wid - 1;
+    if (c.wd.wid == 0) {
+      direction<2>(cw, mu, tau, delta, dummy);
+      if (ob_lane0()) {  // warp 0 has no share of the step limits
+        double* pt = c.wd.part;
+        pt[0] = pt[1] = pt[3] = pt[4] = 1.0, pt[2] = pt[5] = 0.0;
+      }
+    } else {
+      direction<1>(cw, mu, tau, delta, dummy);
+    }
+    ob_cta_sync();
+  } else {
+    if (c.wd.wid == 0) direction<2>(c, mu, tau, delta, dummy);  // the dx / lambda+ recursion
+    ob_cta_sync();
+    direction<1>(c, mu, tau, delta, dummy);  // pairs and step limits, stage k on warp k % nw
+    ob_cta_sync();
+  }
 #else
   direction<2>(c, mu, tau, delta, dummy);
   for (int w = 0; w < c.wd.nw; w++) {
