@@ -658,11 +658,14 @@ __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
 __global__ void __launch_bounds__(kObcaThreads)
     ttmpc_obca_wide_kernel(const __grid_constant__ Params p, const __grid_constant__ Params pT,
                            const __grid_constant__ obca::ObParams o, double* __restrict__ scratch, long long B, ProblemIn in,
-                           SolveOut out, unsigned long long* counter) {
+                           SolveOut out, unsigned long long* counter, int rec_in_smem) {
   __shared__ double s_part[(kObcaThreads / 32) * obca::kPart];
   __shared__ double s_bcast[32];
   __shared__ long long s_b;
   __shared__ int s_flag[TTMPC_MAX_HORIZON + 1];  // stage hand-over of the pipelined factor / direction sweeps
+  // recursion blocks of all stages (obca::kRecRows doubles each) when the launch asked for the room: what the pair
+  // warps hand to the recursion on warp 0 and the Riccati factors it leaves for the direction sweep stay on chip
+  extern __shared__ double s_rec[];
   int sweep_epoch = 0;
   for (int i = threadIdx.x; i <= TTMPC_MAX_HORIZON; i += blockDim.x) s_flag[i] = 0;
   obca::Ctx c;
@@ -671,6 +674,7 @@ __global__ void __launch_bounds__(kObcaThreads)
   c.wd.flag = s_flag, c.wd.epoch = &sweep_epoch;
 #endif
   c.p = &p, c.pT = &pT, c.o = &o, c.s0 = obca::slot_ptr(scratch, p.N, blockIdx.x);
+  c.r0 = rec_in_smem ? s_rec : nullptr;
   const long long nz = 8LL * p.N + 6;
   for (;;) {
     __syncthreads();
@@ -1087,7 +1091,15 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
   }
   cudaMemsetAsync(h->counter, 0, 16 * sizeof(unsigned long long), st);
   if (wide) {
-    ttmpc_obca_wide_kernel<<<(unsigned)blocks, kObcaThreads, 0, st>>>(h->p, pT, o, h->ob_scratch, B, in, so, h->counter);
+    // the recursion blocks of all stages in shared memory when they fit (N = 50: 36 KB, N = 256: 181 KB)
+    size_t rec_bytes = (size_t)(h->p.N + 1) * obca::kRecRows * sizeof(double);
+    cudaFuncAttributes fa;
+    if (getenv("TTMPC_OBCA_REC_GLOBAL") || cudaFuncGetAttributes(&fa, ttmpc_obca_wide_kernel) != cudaSuccess ||
+        rec_bytes + fa.sharedSizeBytes > h->smem_optin ||
+        cudaFuncSetAttribute(ttmpc_obca_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_bytes) != cudaSuccess)
+      rec_bytes = 0;
+    ttmpc_obca_wide_kernel<<<(unsigned)blocks, kObcaThreads, rec_bytes, st>>>(h->p, pT, o, h->ob_scratch, B, in, so, h->counter,
+                                                                              rec_bytes ? 1 : 0);
     h->launches[8]++;
   } else {
     ttmpc_obca_kernel<<<(unsigned)blocks, kObcaThreads, 0, st>>>(h->p, pT, o, h->ob_scratch, B, in, so, h->counter);

@@ -41,10 +41,18 @@ namespace obca {
 
 constexpr int kMaxPairs = 2 * TTMPC_MAX_OBSTACLES;
 // ---- scratch rows of one stage ----
-constexpr int oW = 0, oDW = 8, oREF = 16, oLAM = 24, oLAMP = 30, oZL = 36, oZU = 44, oK = 52, oKFF = 64, oP = 66, oPV = 87;
-constexpr int oRP = 96;  // wide mode only: the pairs' J_x'y (4) of the stage
-constexpr int oA = 114, oCD = 123, oG = 129, oSIG = 137, oHX = 139;  // wide mode only, left by the pair phase of the factor sweep: A (9), defect (6), gradient (8), Sigma_u (2), Hessian block (21)
+constexpr int oW = 0, oDW = 8, oREF = 16, oLAM = 24, oLAMP = 30, oZL = 36, oZU = 44;
+// The "recursion block" of a stage: everything that only the two recursions over the stages touch -- the Riccati
+// factors K (12), k_ff (2), P (21), p (6), and (wide mode only, left by the pair phase of the factor sweep for the
+// recursion on warp 0) A (9), defect (6), gradient (8), Sigma_u (2), Hessian block (21).  Rows are relative to
+// Ctx::rstage(k): rows [oREC, oREC + kRecRows) of the stage in global scratch, or -- CTA-per-problem kernel, when
+// (N + 1) * kRecRows doubles fit -- a block in SHARED memory, so that the serial recursion never waits for L2.
+constexpr int rK = 0, rKFF = 12, rP = 14, rPV = 35, rA = 41, rCD = 50, rG = 56, rSIG = 64, rHX = 66;
+constexpr int kRecRows = 88;
+constexpr int oREC = 52;
+constexpr int oRP = 140;  // wide mode only: the pairs' J_x'y (4) of the stage
 constexpr int kBaseRows = 160;
+static_assert(oREC + kRecRows <= oRP && oRP + 4 <= kBaseRows, "base rows overlap");
 constexpr int qV = 0, qZV = 8, qS = 16, qY = 20, qZS = 24, qDV = 30, qDS = 38;  // rows of one pair
 constexpr int qA = 42, qG = 50;  // K_vv^-1 q (8) and K_vv^-1 K_vx (8x4, row-major): written by factor, read by direction
 constexpr int kPairRows = 82;
@@ -494,7 +502,9 @@ struct Ctx {
                      // (trajectory_optimization.py:168-183) has a box around the goal and 100 Q there
   const ObParams* o;
   double* s0;   // slot pointer (stage 0 of this problem slot)
+  double* r0 = nullptr;  // recursion blocks of all stages in shared memory (CTA-per-problem kernel), else null
   TT_HD double* stage(int k) const { return s0 + (size_t)k * kStageDoubles; }
+  TT_HD double* rstage(int k) const { return r0 ? r0 + (size_t)k * kRecRows : s0 + (size_t)k * kStageDoubles + oREC; }
 };
 TT_HD double* pair_ptr(double* ps, int j) { return ps + kBasePad + j; }
 
@@ -920,9 +930,9 @@ TT_HD void assemble_hx(const Params& p, const double (*Hadd)[4], const double* s
     Hx[4][4] += ho.h44, Hx[4][5] += ho.h45, Hx[5][4] += ho.h45;
   }
 }
-TT_HD void load_hx(const double* ps, double (*Hx)[NX]) {
+TT_HD void load_hx(const double* pr, double (*Hx)[NX]) {
   for (int i = 0; i < NX; i++)
-    for (int j = i; j < NX; j++) Hx[i][j] = Hx[j][i] = bld(ps, oHX + SY(i, j));
+    for (int j = i; j < NX; j++) Hx[i][j] = Hx[j][i] = bld(pr, rHX + SY(i, j));
 }
 
 // ---- sweep 2 (backward): condensation of the pairs + Riccati factorisation.  false: wrong inertia ----
@@ -943,6 +953,7 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
   // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
   for (int k = (MODE == 1) ? N - ((N - deal_i(c.wd)) % deal_n(c.wd) + deal_n(c.wd)) % deal_n(c.wd) : N, kstep = (MODE == 1) ? deal_n(c.wd) : 1; k >= 0; k -= kstep) {
     double* ps = c.stage(k);
+    double* pr = c.rstage(k);
     const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW], g[NW], sig[NW];
@@ -1074,11 +1085,11 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
     if (MODE == 1) {
       if (has_u) {
         const double a9[9] = {m.a02, m.a05, m.a12, m.a15, m.a24, m.a25, m.a33, m.a34, m.a35};
-        for (int i = 0; i < 9; i++) bst(ps, oA + i, a9[i]);
-        for (int i = 0; i < NX; i++) bst(ps, oCD + i, cdef[i]);
-        bst(ps, oSIG, s6), bst(ps, oSIG + 1, s7);
+        for (int i = 0; i < 9; i++) bst(pr, rA + i, a9[i]);
+        for (int i = 0; i < NX; i++) bst(pr, rCD + i, cdef[i]);
+        bst(pr, rSIG, s6), bst(pr, rSIG + 1, s7);
       }
-      for (int i = 0; i < NW; i++) bst(ps, oG + i, gx[i]);
+      for (int i = 0; i < NW; i++) bst(pr, rG + i, gx[i]);
       if (has_x) {
         double Hx[NX][NX];
         if (has_u)
@@ -1086,25 +1097,25 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
         else
           assemble_hx<false>(p, Hadd, sig, m, ln, Hx);
         for (int i = 0; i < NX; i++)
-          for (int j = i; j < NX; j++) bst(ps, oHX + SY(i, j), Hx[i][j]);
+          for (int j = i; j < NX; j++) bst(pr, rHX + SY(i, j), Hx[i][j]);
       }
       ob_publish(c, k, true);  // pipelined: the recursion on warp 0 may take this stage now
       continue;
     }
     if (MODE == 2) {
       if (has_u) {
-        m.a02 = bld(ps, oA + 0), m.a05 = bld(ps, oA + 1), m.a12 = bld(ps, oA + 2), m.a15 = bld(ps, oA + 3);
-        m.a24 = bld(ps, oA + 4), m.a25 = bld(ps, oA + 5), m.a33 = bld(ps, oA + 6), m.a34 = bld(ps, oA + 7);
-        m.a35 = bld(ps, oA + 8);
-        for (int i = 0; i < NX; i++) cdef[i] = bld(ps, oCD + i);
-        s6 = bld(ps, oSIG), s7 = bld(ps, oSIG + 1);
+        m.a02 = bld(pr, rA + 0), m.a05 = bld(pr, rA + 1), m.a12 = bld(pr, rA + 2), m.a15 = bld(pr, rA + 3);
+        m.a24 = bld(pr, rA + 4), m.a25 = bld(pr, rA + 5), m.a33 = bld(pr, rA + 6), m.a34 = bld(pr, rA + 7);
+        m.a35 = bld(pr, rA + 8);
+        for (int i = 0; i < NX; i++) cdef[i] = bld(pr, rCD + i);
+        s6 = bld(pr, rSIG), s7 = bld(pr, rSIG + 1);
       }
-      for (int i = 0; i < NW; i++) gx[i] = bld(ps, oG + i);
+      for (int i = 0; i < NW; i++) gx[i] = bld(pr, rG + i);
     }
     // ---- the recursion itself
     if (k == N) {
       if (MODE == 2)
-        load_hx(ps, Pn);
+        load_hx(pr, Pn);
       else
         assemble_hx<false>(p, Hadd, sig, m, ln, Pn);
       for (int i = 0; i < NX; i++) pn[i] = gx[i];
@@ -1134,12 +1145,12 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
       const double bh0 = gx[6] + dt * h[5], bh1 = gx[7] + dt * h[4];
       kff[0] = i00 * bh0 + i01 * bh1;
       kff[1] = i01 * bh0 + i11 * bh1;
-      for (int j = 0; j < NX; j++) bst(ps, oK + j, Kf[0][j]), bst(ps, oK + NX + j, Kf[1][j]);
-      bst(ps, oKFF, kff[0]), bst(ps, oKFF + 1, kff[1]);
+      for (int j = 0; j < NX; j++) bst(pr, rK + j, Kf[0][j]), bst(pr, rK + NX + j, Kf[1][j]);
+      bst(pr, rKFF, kff[0]), bst(pr, rKFF + 1, kff[1]);
       if (has_x) {
         double Hx[NX][NX];
         if (MODE == 2)
-          load_hx(ps, Hx);
+          load_hx(pr, Hx);
         else
           assemble_hx<true>(p, Hadd, sig, m, ln, Hx);
         double Pk[NX][NX], pk[NX], ath[NX];
@@ -1159,8 +1170,8 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
     }
     if (has_x) {
       for (int i = 0; i < NX; i++) {
-        bst(ps, oPV + i, pn[i]);
-        for (int j = i; j < NX; j++) bst(ps, oP + SY(i, j), Pn[i][j]);
+        bst(pr, rPV + i, pn[i]);
+        for (int j = i; j < NX; j++) bst(pr, rP + SY(i, j), Pn[i][j]);
       }
       if (MODE == 0)
         for (int i = 0; i < NX; i++) xn[i] = w[i], ln[i] = bld(ps, oLAM + i);
@@ -1190,6 +1201,7 @@ TT_HD bool factor_fused(const Ctx& c, double mu, double delta) {
   // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
   for (int k = (MODE == 1) ? N - ((N - c.wd.wid) % c.wd.nw + c.wd.nw) % c.wd.nw : N, kstep = (MODE == 1) ? c.wd.nw : 1; k >= 0; k -= kstep) {
     double* ps = c.stage(k);
+    double* pr = c.rstage(k);
     const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW], g[NW], sig[NW];
@@ -1343,8 +1355,8 @@ TT_HD bool factor_fused(const Ctx& c, double mu, double delta) {
       const double bh0 = g[6] + dt * h[5], bh1 = g[7] + dt * h[4];
       kff[0] = i00 * bh0 + i01 * bh1;
       kff[1] = i01 * bh0 + i11 * bh1;
-      for (int j = 0; j < NX; j++) bst(ps, oK + j, Kf[0][j]), bst(ps, oK + NX + j, Kf[1][j]);
-      bst(ps, oKFF, kff[0]), bst(ps, oKFF + 1, kff[1]);
+      for (int j = 0; j < NX; j++) bst(pr, rK + j, Kf[0][j]), bst(pr, rK + NX + j, Kf[1][j]);
+      bst(pr, rKFF, kff[0]), bst(pr, rKFF + 1, kff[1]);
       if (has_x) {
         Hes ho;
         stage_hess(p, m, ln, ho);
@@ -1374,8 +1386,8 @@ TT_HD bool factor_fused(const Ctx& c, double mu, double delta) {
     }
     if (has_x) {
       for (int i = 0; i < NX; i++) {
-        bst(ps, oPV + i, pn[i]);
-        for (int j = i; j < NX; j++) bst(ps, oP + SY(i, j), Pn[i][j]);
+        bst(pr, rPV + i, pn[i]);
+        for (int j = i; j < NX; j++) bst(pr, rP + SY(i, j), Pn[i][j]);
       }
       for (int i = 0; i < NX; i++) xn[i] = w[i], ln[i] = bld(ps, oLAM + i);
     }
@@ -1410,6 +1422,7 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
   // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
   for (int k = (MODE == 1) ? deal_i(c.wd) : 0, kstep = (MODE == 1) ? deal_n(c.wd) : 1; k <= N; k += kstep) {
     double* ps = c.stage(k);
+    double* pr = c.rstage(k);
     if (MODE == 1) ob_await(c, k);  // pipelined: the recursion on warp 0 has stored this stage's dx, du
     const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
@@ -1440,8 +1453,8 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
       if (has_u) dw[6] = bld(ps, oDW + 6), dw[7] = bld(ps, oDW + 7);
     } else if (has_u) {
       for (int i = 0; i < NU; i++) {
-        double s = -bld(ps, oKFF + i);
-        for (int j = 0; j < NX; j++) s -= bld(ps, oK + i * NX + j) * dx[j];
+        double s = -bld(pr, rKFF + i);
+        for (int j = 0; j < NX; j++) s -= bld(pr, rK + i * NX + j) * dx[j];
         dw[NX + i] = s;
       }
     }
@@ -1509,14 +1522,15 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
     }
     if (MODE != 1 && has_u) {  // dx_{k+1} = A dx + B du - c_{k+1};  lambda+_{k+1} = -(p_{k+1} + P_{k+1} dx_{k+1})
       double* pq = c.stage(k + 1);
+      double* prq = c.rstage(k + 1);
       Lin m;
       double nd[NX];
       if (MODE == 2) {  // A and the defect as the factor sweep left them (the very same numbers, see stage_lin_det)
-        m.a02 = bld(ps, oA + 0), m.a05 = bld(ps, oA + 1), m.a12 = bld(ps, oA + 2), m.a15 = bld(ps, oA + 3);
-        m.a24 = bld(ps, oA + 4), m.a25 = bld(ps, oA + 5), m.a33 = bld(ps, oA + 6), m.a34 = bld(ps, oA + 7);
-        m.a35 = bld(ps, oA + 8);
+        m.a02 = bld(pr, rA + 0), m.a05 = bld(pr, rA + 1), m.a12 = bld(pr, rA + 2), m.a15 = bld(pr, rA + 3);
+        m.a24 = bld(pr, rA + 4), m.a25 = bld(pr, rA + 5), m.a33 = bld(pr, rA + 6), m.a34 = bld(pr, rA + 7);
+        m.a35 = bld(pr, rA + 8);
         A_mul(m, dx, nd);
-        for (int i = 0; i < NX; i++) nd[i] -= bld(ps, oCD + i);
+        for (int i = 0; i < NX; i++) nd[i] -= bld(pr, rCD + i);
       } else {
         stage_lin_det(p, w, m);
         const double f[NX] = {m.f0, m.f1, m.f2, m.f3, w[7], w[6]};
@@ -1526,8 +1540,8 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
       nd[4] += p.dt * dw[7];
       nd[5] += p.dt * dw[6];
       for (int i = 0; i < NX; i++) {
-        double s = bld(pq, oPV + i);
-        for (int j = 0; j < NX; j++) s += bld(pq, oP + SY(i, j)) * nd[j];
+        double s = bld(prq, rPV + i);
+        for (int j = 0; j < NX; j++) s += bld(prq, rP + SY(i, j)) * nd[j];
         bst(pq, oLAMP + i, -s);
       }
       for (int i = 0; i < NX; i++) dx[i] = nd[i];
