@@ -705,6 +705,67 @@ __global__ void __launch_bounds__(kObcaThreads)
   }
 }
 
+// Very small batches (the single solve of the MPCTrackingControlObs shim, the offline planner): one THREAD-BLOCK CLUSTER
+// per problem.  The stages are dealt to the warps of all CTAs of the cluster (N = 50 on a cluster of 8: one stage per
+// warp and sweep), CTAs exchange stage rows through global scratch / L2 and the recursion blocks + statistics through
+// distributed shared memory, phase boundaries are cluster barriers (obca::Wide).  Launched with a run-time cluster
+// dimension (cudaLaunchKernelEx); grid = clusters x cluster size, scratch slot = cluster.
+constexpr int kObcaMaxCluster = 16;
+__global__ void __launch_bounds__(kObcaThreads)
+    ttmpc_obca_cluster_kernel(const __grid_constant__ Params p, const __grid_constant__ Params pT,
+                              const __grid_constant__ obca::ObParams o, double* __restrict__ scratch, long long B, ProblemIn in,
+                              SolveOut out, unsigned long long* counter, int rec_in_smem) {
+  __shared__ double s_part[(kObcaThreads / 32) * obca::kPart];
+  __shared__ double s_csub[kObcaMaxCluster * obca::kPart];
+  __shared__ double s_bcast[32];
+  __shared__ long long s_b;
+  extern __shared__ double s_rec[];
+  unsigned crank, csize, cid;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
+  obca::Ctx c;
+  const int lnw = (int)(blockDim.x >> 5), lw = (int)(threadIdx.x >> 5);
+  c.wd.nc = (int)csize, c.wd.crank = (int)crank, c.wd.lw = lw, c.wd.lnw = lnw;
+  c.wd.wid = (int)crank * lnw + lw, c.wd.nw = (int)csize * lnw;
+  c.wd.part = s_part - (size_t)crank * lnw * obca::kPart;  // part[wid * kPart] is this warp's record
+  c.wd.csub = s_csub, c.wd.bcast = s_bcast;
+  c.p = &p, c.pT = &pT, c.o = &o, c.s0 = obca::slot_ptr(scratch, p.N, cid);
+  c.r0 = rec_in_smem ? (crank == 0 ? s_rec : obca::ob_map_rank(s_rec, 0)) : nullptr;
+  const long long nz = 8LL * p.N + 6;
+  for (;;) {
+    obca::ob_cluster_sync();  // everybody is done with the previous problem (and has read its s_b)
+    if (crank == 0 && threadIdx.x == 0) {
+      const long long nb = (long long)atomicAdd(counter, 1ull);
+      for (unsigned r = 0; r < csize; r++) *(long long*)obca::ob_map_rank((double*)&s_b, (int)r) = nb;
+    }
+    obca::ob_cluster_sync();
+    const long long b = s_b;
+    if (b >= B) break;
+    Result res;
+    obca::solve_problem<true>(c, in, b, res);
+    obca::ob_cluster_sync();
+    if (c.wd.wid == 0) {
+      if (out.z) obca::unpack(p, c.s0, out.z + b * nz);
+      if ((threadIdx.x & 31) == 0) {
+        if (out.u0) {
+          out.u0[2 * b] = obca::bld(c.s0, obca::oW + 6);
+          out.u0[2 * b + 1] = obca::bld(c.s0, obca::oW + 7);
+        }
+        if (out.obj) out.obj[b] = res.obj;
+        if (out.kkt) {
+          out.kkt[3 * b] = res.dual_inf;
+          out.kkt[3 * b + 1] = res.constr_viol;
+          out.kkt[3 * b + 2] = res.compl_inf;
+        }
+        if (out.iters) out.iters[b] = res.iters;
+        if (out.status) out.status[b] = res.status;
+      }
+    }
+  }
+  obca::ob_cluster_sync();  // nobody leaves while a neighbour may still write into its shared memory
+}
+
 typedef void (*team_kernel_t)(const Params, long long, ProblemIn, SolveOut, unsigned long long*, const int32_t*);
 template <int L>
 static team_kernel_t team_kernel_l(const Params& p) {
@@ -718,7 +779,7 @@ static size_t team_smem_for(const Params& p, int L) {
   return p.generic ? team::cta_smem_bytes<true>(p.N, L) : team::cta_smem_bytes<false>(p.N, L);
 }
 
-constexpr int kNumKernels = 10;
+constexpr int kNumKernels = 11;
 struct ttmpc_handle {
   ttmpc_config cfg;
   Params p;
@@ -766,7 +827,8 @@ struct ttmpc_handle {
 static const char* kKernelNames[kNumKernels] = {"ttmpc_solve_kernel", "ttmpc_shift_kernel", "ttmpc_plant_kernel",
                                                 "ttmpc_dfma_kernel", "ttmpc_classify_kernel", "ttmpc_order_kernel",
                                                 "ttmpc_episode_kernel", "ttmpc_obca_kernel",
-                                                "ttmpc_obca_wide_kernel", "ttmpc_team_kernel"};
+                                                "ttmpc_obca_wide_kernel", "ttmpc_team_kernel",
+                                                "ttmpc_obca_cluster_kernel"};
 
 // Entry points set the handle's device and put the caller's current device back on return.
 struct DeviceGuard {
@@ -1076,10 +1138,25 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
   // for 1 184, 2.23 vs 2.25 s for 8 192); beyond that: one warp per problem (16 384: 4.1 vs 4.6 s)
   const char* wenv = getenv("TTMPC_OBCA_WIDE_MAX");
   const bool wide = B <= (wenv ? atoll(wenv) : 48LL * sms);
+  // a handful of problems (fewer than SMs / cluster size): one thread-block cluster per problem -- the largest cluster
+  // (8, 4, 2 CTAs) that leaves every problem its own cluster and most warps a stage.  TTMPC_OBCA_CLUSTER=0 switches
+  // this off, =2/4/8/16 forces a size (16 is the non-portable maximum).
+  int csz = 0;
+  if (wide) {
+    const char* cenv = getenv("TTMPC_OBCA_CLUSTER");
+    if (cenv) {
+      const int v = atoi(cenv);
+      if (v == 2 || v == 4 || v == 8 || v == 16) csz = v;
+    } else {
+      for (int cs = 8; cs >= 2 && !csz; cs >>= 1)
+        if (B * cs <= sms && (kObcaThreads / 32) * cs / 2 < h->p.N + 1) csz = cs;
+    }
+  }
   const int wpc = wide ? 1 : kObcaThreads / 32;
   long long blocks = (B + wpc - 1) / wpc;
   const long long cap = (long long)sms * (wide ? per_sm_wide : per_sm);
   if (blocks > cap) blocks = cap;
+  if (csz && blocks * csz > cap) blocks = cap / csz > 0 ? cap / csz : 1;
   const size_t need = obca::scratch_doubles(h->p.N, (size_t)blocks * wpc);
   if (need > h->ob_doubles) {
     if (h->ob_scratch) cudaFree(h->ob_scratch);
@@ -1090,7 +1167,41 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
     h->ob_doubles = need;
   }
   cudaMemsetAsync(h->counter, 0, 16 * sizeof(unsigned long long), st);
-  if (wide) {
+  bool launched = false;
+  if (wide && csz) {
+    size_t rec_bytes = (size_t)(h->p.N + 1) * obca::kRecRows * sizeof(double);
+    cudaFuncAttributes fa;
+    if (getenv("TTMPC_OBCA_REC_GLOBAL") || cudaFuncGetAttributes(&fa, ttmpc_obca_cluster_kernel) != cudaSuccess ||
+        rec_bytes + fa.sharedSizeBytes > h->smem_optin ||
+        cudaFuncSetAttribute(ttmpc_obca_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_bytes) != cudaSuccess)
+      rec_bytes = 0;
+    bool ok = true;
+    if (csz > 8) ok = cudaFuncSetAttribute(ttmpc_obca_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.blockDim = dim3(kObcaThreads), lc.dynamicSmemBytes = rec_bytes, lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)csz, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    lc.attrs = at, lc.numAttrs = 1;
+    int max_clusters = 0;
+    lc.gridDim = dim3((unsigned)(blocks * csz));
+    if (ok) ok = cudaOccupancyMaxActiveClusters(&max_clusters, ttmpc_obca_cluster_kernel, &lc) == cudaSuccess && max_clusters >= 1;
+    if (ok) {
+      if (blocks > max_clusters) blocks = max_clusters;  // persistent clusters pull problems from the queue
+      lc.gridDim = dim3((unsigned)(blocks * csz));
+      const int rec_flag = rec_bytes ? 1 : 0;
+      ok = cudaLaunchKernelEx(&lc, ttmpc_obca_cluster_kernel, h->p, pT, o, h->ob_scratch, B, in, so, h->counter, rec_flag) == cudaSuccess;
+    }
+    if (ok) {
+      h->launches[10]++;
+      launched = true;
+    } else {
+      cudaGetLastError();  // this device / configuration takes no such cluster: the CTA-per-problem kernel below
+    }
+  }
+  if (launched) {
+  } else if (wide) {
     // the recursion blocks of all stages in shared memory when they fit (N = 50: 36 KB, N = 256: 181 KB)
     size_t rec_bytes = (size_t)(h->p.N + 1) * obca::kRecRows * sizeof(double);
     cudaFuncAttributes fa;

@@ -492,6 +492,16 @@ struct Wide {
   int dn = 0, di = 0;     // dn > 0: the stages of a MODE-1 sweep are dealt to dn warps, this warp being number di
   int* flag = nullptr;    // [N+1]
   int* epoch = nullptr;   // this warp's sweep counter (the same in every warp: control flow is CTA-uniform)
+  // Cluster-per-problem kernel (ttmpc_obca_cluster_kernel): nc > 1 CTAs of a thread-block cluster work on one problem.
+  // wid / nw then count the warps of the whole cluster (stage k -> warp k mod nw, on CTA (k mod nw) / warps per CTA),
+  // `part` is this CTA's array biased so that part[wid * kPart] is the warp's own record, the recursions run on warp 0
+  // of CTA 0 with the recursion blocks in THAT CTA's shared memory (the other CTAs write theirs through distributed
+  // shared memory), per-CTA subtotals of the statistics are exchanged through `csub` (every CTA holds all nc records),
+  // and every phase boundary is a cluster barrier (release / acquire: it also drops the L1 lines of rows that another
+  // SM has rewritten in global scratch).
+  int nc = 0, crank = 0;  // CTAs per cluster (0 / 1: no cluster), rank of this CTA
+  int lw = 0, lnw = 0;    // warp index inside the CTA, warps per CTA
+  double* csub = nullptr; // [nc][kPart] in this CTA's shared memory
 };
 TT_HD int deal_n(const Wide& w) { return w.dn > 0 ? w.dn : w.nw; }
 TT_HD int deal_i(const Wide& w) { return w.dn > 0 ? w.di : w.wid; }
@@ -537,6 +547,74 @@ TT_HD bool ob_await(const Ctx& c, int k) {
   (void)c; (void)k;
   return true;
 #endif
+}
+
+// ---- thread-block cluster primitives (device only; no-ops / identity on the host, where nc is never > 1) ----
+TT_HD void ob_cluster_sync() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#endif
+}
+// the address of `p` (a generic pointer into this CTA's shared memory) in the shared memory of CTA `rank` of the cluster
+TT_HD double* ob_map_rank(double* p, int rank) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long out;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)p), "r"(rank));
+  return (double*)out;
+#else
+  (void)rank;
+  return p;
+#endif
+}
+// barrier over everything that works on the problem: the CTA, or the cluster
+TT_HD void ob_sync_all(const Ctx& c) {
+#if defined(__CUDA_ARCH__)
+  if (c.wd.nc > 1)
+    ob_cluster_sync();
+  else
+    __syncthreads();
+#else
+  (void)c;
+#endif
+}
+// How a slot of the per-warp records is combined: 2 bits per slot (0 sum, 1 max, 2 min), slot i at bits 2i.
+// update_stats: [sumlog theta cinf rd lam1 z1 cmax cmin | J sumlog theta cinf rd lam1 z1 cmax cmin]
+constexpr unsigned long long kOpsStats = 0x0ull | (1ull << 4) | (1ull << 6) | (1ull << 12) | (2ull << 14) | (1ull << 22) | (1ull << 24) |
+                                         (1ull << 30) | (2ull << 32);
+constexpr unsigned long long kOpsDir = 2ull | (2ull << 2) | (2ull << 6) | (2ull << 8);  // [a_pr a_du gphi_d | a_pr a_du gphi_d]
+constexpr unsigned long long kOpsTrial = 2ull << 6;                                      // [J sumlog theta inside]
+constexpr unsigned long long kOpsFactor = 2ull;                                          // [every pair block positive definite]
+struct PartView {
+  const double* p;  // records of kPart doubles
+  int n;
+};
+// After a stage-parallel sweep whose warps left their records in `part`: barrier, then the records to combine IN
+// ORDER (every warp of the CTA / cluster combines the same numbers in the same order: identical statistics everywhere
+// without a broadcast).  One CTA: its nw warp records.  Cluster: warp 0 of every CTA folds the CTA's records slot by
+// slot (`ops`) and writes the subtotal into every CTA's csub[rank]; after the cluster barrier the nc subtotals.
+TT_HD PartView ob_gather(const Ctx& c, unsigned long long ops) {
+#if defined(__CUDA_ARCH__)
+  if (c.wd.nc > 1) {
+    __syncthreads();
+    if (c.wd.lw == 0) {
+      const int i = (int)(threadIdx.x & 31);
+      if (i < kPart) {
+        const double* pl = c.wd.part + (size_t)(c.wd.wid) * kPart + i;  // wid of warp 0 of this CTA: its first record
+        const int op = (int)((ops >> (2 * i)) & 3ull);
+        double v = pl[0];
+        for (int w = 1; w < c.wd.lnw; w++) {
+          const double x = pl[w * kPart];
+          v = (op == 0) ? v + x : (op == 1) ? tt_max(v, x) : tt_min(v, x);
+        }
+        for (int r = 0; r < c.wd.nc; r++) ob_map_rank(c.wd.csub, r)[c.wd.crank * kPart + i] = v;
+      }
+    }
+    ob_cluster_sync();
+    return PartView{c.wd.csub, c.wd.nc};
+  }
+  __syncthreads();
+#endif
+  return PartView{c.wd.part, c.wd.nw};
 }
 
 TT_HD void dense_A(const Lin& m, double (*A)[NX]) {
@@ -947,7 +1025,7 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
     pn[i] = xn[i] = ln[i] = 0.0;
     for (int j = 0; j < NX; j++) Pn[i][j] = 0.0;
   }
-  if (MODE == 2 && c.wd.flag == nullptr)  // the pair phase found a block that is not positive definite
+  if (MODE == 2 && c.wd.flag == nullptr && c.wd.nc <= 1)  // the pair phase found a block that is not positive definite
     for (int w_ = 0; w_ < c.wd.nw; w_++)
       if (c.wd.part[w_ * kPart] == 0.0) return false;
   // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
@@ -1679,11 +1757,11 @@ TT_HD void run_update_stats(const Ctx& c, bool do_update, double alpha, double a
     return;
   }
 #if defined(__CUDA_ARCH__)
-  ob_cta_sync();
+  ob_sync_all(c);
   update_stats<1>(c, do_update, alpha, alpha_du, mu_step, delta_step, st);  // step + pairs, stage k on warp k % nw
-  ob_cta_sync();
+  ob_sync_all(c);
   update_stats<3>(c, do_update, alpha, alpha_du, mu_step, delta_step, st);  // (x, u) statistics, stage-parallel as well
-  ob_cta_sync();
+  const PartView pv = ob_gather(c, kOpsStats);
 #else
   for (int w = 0; w < c.wd.nw; w++) {
     Ctx cw = c;
@@ -1695,12 +1773,13 @@ TT_HD void run_update_stats(const Ctx& c, bool do_update, double alpha, double a
     cw.wd.wid = w;
     update_stats<3>(cw, do_update, alpha, alpha_du, mu_step, delta_step, st);
   }
+  const PartView pv{c.wd.part, c.wd.nw};
 #endif
   // every warp combines the shares in the same order: identical statistics everywhere, no broadcast needed
   st.J = st.sumlog = st.theta = st.cinf = st.rd_inf = st.lam1 = st.z1 = st.cmax = 0.0;
   st.cmin = INFINITY;
-  for (int w = 0; w < c.wd.nw; w++) {
-    const double* pt = c.wd.part + w * kPart;
+  for (int w = 0; w < pv.n; w++) {
+    const double* pt = pv.p + w * kPart;
     st.sumlog += pt[0] + pt[9], st.theta += pt[1] + pt[10], st.cinf = tt_max(st.cinf, tt_max(pt[2], pt[11]));
     st.rd_inf = tt_max(st.rd_inf, tt_max(pt[3], pt[12])), st.lam1 += pt[4] + pt[13], st.z1 += pt[5] + pt[14];
     st.cmax = tt_max(st.cmax, tt_max(pt[6], pt[15])), st.cmin = tt_min(st.cmin, tt_min(pt[7], pt[16]));
@@ -1712,7 +1791,7 @@ template <bool WIDE>
 TT_HD bool run_factor(const Ctx& c, double mu, double delta) {
   if (!WIDE) return factor_fused(c, mu, delta);
 #if defined(__CUDA_ARCH__)
-  ob_cta_sync();
+  ob_sync_all(c);
   if (c.wd.flag != nullptr && c.wd.nw >= 3) {  // pipelined: warps 1.. condense the pairs, warp 0 trails them with the recursion
     ++*c.wd.epoch;
     Ctx cw = c;
@@ -1724,6 +1803,19 @@ TT_HD bool run_factor(const Ctx& c, double mu, double delta) {
       factor<1>(cw, mu, delta);
     }
     ob_cta_sync();
+    return c.wd.bcast[0] != 0.0;
+  }
+  if (c.wd.nc > 1) {  // cluster: pair phase on every warp of the cluster, then the recursion on warp 0 of CTA 0
+    factor<1>(c, mu, delta);
+    const PartView pv = ob_gather(c, kOpsFactor);
+    for (int w = 0; w < pv.n; w++)
+      if (pv.p[w * kPart] == 0.0) return false;  // some pair block is not positive definite (the same verdict everywhere)
+    if (c.wd.wid == 0) {
+      const bool ok = factor<2>(c, mu, delta);
+      const int i = (int)(threadIdx.x & 31);
+      if (i < c.wd.nc) ob_map_rank(c.wd.bcast, i)[0] = ok ? 1.0 : 0.0;
+    }
+    ob_cluster_sync();
     return c.wd.bcast[0] != 0.0;
   }
   factor<1>(c, mu, delta);
@@ -1752,7 +1844,8 @@ TT_HD void run_direction(const Ctx& c, double mu, double tau, double delta, Dir&
   }
   Dir dummy;
 #if defined(__CUDA_ARCH__)
-  ob_cta_sync();
+  ob_sync_all(c);
+  PartView pv{c.wd.part, c.wd.nw};
   if (c.wd.flag != nullptr && c.wd.nw >= 3) {  // pipelined: warp 0 leads with the recursion, warps 1.. follow with the pairs
     ++*c.wd.epoch;
     Ctx cw = c;
@@ -1769,9 +1862,9 @@ TT_HD void run_direction(const Ctx& c, double mu, double tau, double delta, Dir&
     ob_cta_sync();
   } else {
     if (c.wd.wid == 0) direction<2>(c, mu, tau, delta, dummy);  // the dx / lambda+ recursion
-    ob_cta_sync();
+    ob_sync_all(c);
     direction<1>(c, mu, tau, delta, dummy);  // pairs and step limits, stage k on warp k % nw
-    ob_cta_sync();
+    pv = ob_gather(c, kOpsDir);
   }
 #else
   direction<2>(c, mu, tau, delta, dummy);
@@ -1780,11 +1873,12 @@ TT_HD void run_direction(const Ctx& c, double mu, double tau, double delta, Dir&
     cw.wd.wid = w;
     direction<1>(cw, mu, tau, delta, dummy);
   }
+  const PartView pv{c.wd.part, c.wd.nw};
 #endif
   di.a_pr = di.a_du = 1.0;
   di.gphi_d = 0.0;
-  for (int w = 0; w < c.wd.nw; w++) {
-    const double* pt = c.wd.part + w * kPart;
+  for (int w = 0; w < pv.n; w++) {
+    const double* pt = pv.p + w * kPart;
     di.a_pr = tt_min(di.a_pr, tt_min(pt[0], pt[3])), di.a_du = tt_min(di.a_du, tt_min(pt[1], pt[4]));
     di.gphi_d += pt[2] + pt[5];
   }
@@ -1797,20 +1891,21 @@ TT_HD void run_trial(const Ctx& c, double alpha, TrialOut& tr) {
     return;
   }
 #if defined(__CUDA_ARCH__)
-  ob_cta_sync();
+  ob_sync_all(c);
   trial<1>(c, alpha, tr);
-  ob_cta_sync();
+  const PartView pv = ob_gather(c, kOpsTrial);
 #else
   for (int w = 0; w < c.wd.nw; w++) {
     Ctx cw = c;
     cw.wd.wid = w;
     trial<1>(cw, alpha, tr);
   }
+  const PartView pv{c.wd.part, c.wd.nw};
 #endif
   tr.J = tr.sumlog = tr.theta = 0.0;
   tr.inside = true;
-  for (int w = 0; w < c.wd.nw; w++) {
-    const double* pt = c.wd.part + w * kPart;
+  for (int w = 0; w < pv.n; w++) {
+    const double* pt = pv.p + w * kPart;
     tr.J += pt[0], tr.sumlog += pt[1], tr.theta += pt[2];
     if (pt[3] == 0.0) tr.inside = false;
   }
@@ -2042,7 +2137,7 @@ template <bool WIDE>
 TT_HD void solve_problem(const Ctx& c, const ProblemIn& in, long long b, Result& res) {
   Lane L;
   const bool x0_bad = init_point<WIDE>(c, in, b);
-  if (WIDE) ob_cta_sync();
+  if (WIDE) ob_sync_all(c);
   lane_begin(*c.p, *c.pT, *c.o, x0_bad, L);
   for (;;) {
     if (lane_head<WIDE>(c, L, res)) return;

@@ -38,3 +38,21 @@ def split_z(z, N):
     xs = np.stack([z[..., 8 * k:8 * k + 6] for k in range(N + 1)], axis=-2)
     us = np.stack([z[..., 8 * k + 6:8 * k + 8] for k in range(N)], axis=-2)
     return xs, us
+
+
+# the three kernels of the obstacle-aware path and the environment that forces each of them (ttmpc.cu: obca_device)
+OBCA_FLAVOURS = ["warp_per_problem", "cta_per_problem", "cluster_per_problem"]
+OBCA_KERNEL = {"warp_per_problem": "ttmpc_obca_kernel", "cta_per_problem": "ttmpc_obca_wide_kernel",
+               "cluster_per_problem": "ttmpc_obca_cluster_kernel"}
+
+
+def force_obca_kernel(monkeypatch, flavour, cluster="8"):
+    monkeypatch.delenv("TTMPC_OBCA_WIDE_MAX", raising=False)
+    monkeypatch.delenv("TTMPC_OBCA_CLUSTER", raising=False)
+    if flavour == "warp_per_problem":
+        monkeypatch.setenv("TTMPC_OBCA_WIDE_MAX", "0")
+    elif flavour == "cta_per_problem":
+        monkeypatch.setenv("TTMPC_OBCA_CLUSTER", "0")
+    else:
+        monkeypatch.setenv("TTMPC_OBCA_CLUSTER", cluster)
+    return OBCA_KERNEL[flavour]

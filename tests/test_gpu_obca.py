@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import geometry
-from obca_common import GOLD_OBCA_FULL, Z_TOL, case_problem, golden_cases, split_z
+from obca_common import GOLD_OBCA_FULL, OBCA_FLAVOURS, Z_TOL, case_problem, force_obca_kernel, golden_cases, split_z
 from parity import OBJ_REL_TOL, U0_ABS_TOL, VIOL_TOL
 
 from car_trailer_mpc_b200 import problem as pb
@@ -51,21 +51,18 @@ def test_gpu_matches_dense_oracle_golden(c):
     assert np.array_equal(xs[0], c["x_init"])
 
 
-@pytest.mark.parametrize("wide_max", ["0", None], ids=["warp_per_problem", "cta_per_problem"])
+@pytest.mark.parametrize("flavour", OBCA_FLAVOURS)
 @pytest.mark.parametrize("c", FULL, ids=[c["name"] for c in FULL])
-def test_gpu_matches_oracle_at_the_reference_size(c, wide_max, monkeypatch):
+def test_gpu_matches_oracle_at_the_reference_size(c, flavour, monkeypatch):
     """Config 4's own size (simulation.py:390: horizon 50 / 40, the 11 rectangles of obstacles.json, one case with a twelfth
     obstacle and active rows, one in which the oracle recovers from an exhausted line search): both GPU kernels, through
     the C ABI, against the oracle's block-tridiagonal LDL' solutions (tools/make_golden_obca_full.py)."""
-    if wide_max is None:
-        monkeypatch.delenv("TTMPC_OBCA_WIDE_MAX", raising=False)
-    else:
-        monkeypatch.setenv("TTMPC_OBCA_WIDE_MAX", wide_max)
+    kernel = force_obca_kernel(monkeypatch, flavour)
     cfg, obs = case_problem(c)
     cfg.max_iter = 400
     sv = solver(cfg)
     r = sv.solve_obca(obs, c["x_init"][None], c["ref_states"][None], c["ref_inputs"][None])
-    assert sv.kernel_launches()["ttmpc_obca_kernel" if wide_max == "0" else "ttmpc_obca_wide_kernel"] == 1
+    assert sv.kernel_launches()[kernel] == 1
     assert r["status"][0] == 0
     xs, us = split_z(r["z"][0], cfg.horizon)
     assert np.abs(r["u0"][0] - c["inputs"][0]).max() <= U0_ABS_TOL
@@ -74,16 +71,13 @@ def test_gpu_matches_oracle_at_the_reference_size(c, wide_max, monkeypatch):
     assert r["kkt"][0][1] <= VIOL_TOL
 
 
-@pytest.mark.parametrize("wide_max", ["0", None], ids=["warp_per_problem", "cta_per_problem"])
-def test_gpu_matches_host_build_of_the_core_on_a_seeded_batch(wide_max, monkeypatch):
+@pytest.mark.parametrize("flavour", OBCA_FLAVOURS)
+def test_gpu_matches_host_build_of_the_core_on_a_seeded_batch(flavour, monkeypatch):
     """Both kernels of the obstacle-aware path: TTMPC_OBCA_WIDE_MAX=0 forces ttmpc_obca_kernel (one warp per problem),
     the default takes ttmpc_obca_wide_kernel (one CTA per problem) for a batch of this size."""
     import emu
     import torch
-    if wide_max is None:
-        monkeypatch.delenv("TTMPC_OBCA_WIDE_MAX", raising=False)
-    else:
-        monkeypatch.setenv("TTMPC_OBCA_WIDE_MAX", wide_max)
+    kernel = force_obca_kernel(monkeypatch, flavour)
     cfg = tracking_preset(20)
     cfg.max_iter = 300
     obs = Obstacles.from_list(parking_lot_obstacles())
@@ -94,7 +88,7 @@ def test_gpu_matches_host_build_of_the_core_on_a_seeded_batch(wide_max, monkeypa
                              torch.from_numpy(S).to(dev), torch.from_numpy(U).to(dev))
     g = {k: v.cpu().numpy() for k, v in g.items()}
     launches = sv.kernel_launches()
-    assert launches["ttmpc_obca_kernel" if wide_max == "0" else "ttmpc_obca_wide_kernel"] == 1
+    assert launches[kernel] == 1
     e = emu.obca_solve_batch(cfg, obs, x0, k_index=ks, traj_states=S, traj_inputs=U)
     ok = (g["status"] == 0) & (e["status"] == 0)
     assert ok.sum() >= 30

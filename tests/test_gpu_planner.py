@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import geometry
-from obca_common import Z_TOL, golden_cases, split_z
+from obca_common import OBCA_FLAVOURS, Z_TOL, force_obca_kernel, golden_cases, split_z
 from parity import OBJ_REL_TOL, U0_ABS_TOL
 
 from car_trailer_mpc_b200 import planner_preset
@@ -27,21 +27,18 @@ def guess_z(c):
     return z
 
 
-@pytest.mark.parametrize("wide_max", ["0", None], ids=["warp_per_problem", "cta_per_problem"])
+@pytest.mark.parametrize("flavour", OBCA_FLAVOURS)
 @pytest.mark.parametrize("c", CASES, ids=[c["name"] for c in CASES])
-def test_gpu_matches_oracle_on_the_planner_nlp(c, wide_max, monkeypatch):
+def test_gpu_matches_oracle_on_the_planner_nlp(c, flavour, monkeypatch):
     from car_trailer_mpc_b200 import BatchSolver
-    if wide_max is None:
-        monkeypatch.delenv("TTMPC_OBCA_WIDE_MAX", raising=False)
-    else:
-        monkeypatch.setenv("TTMPC_OBCA_WIDE_MAX", wide_max)
+    kernel = force_obca_kernel(monkeypatch, flavour)
     N = int(c["horizon"])
     cfg = planner_preset(N)
     cfg.max_iter = 1000
     sv = BatchSolver(cfg, 0)
     obs = Obstacles.from_list([tuple(r) for r in c["rects"]])
     r = sv.plan(obs, c["x_init"][None], c["goal"], 100.0, 1e-2, guess_z(c)[None])  # host pointers
-    assert sv.kernel_launches()["ttmpc_obca_kernel" if wide_max == "0" else "ttmpc_obca_wide_kernel"] == 1
+    assert sv.kernel_launches()[kernel] == 1
     assert r["status"][0] == 0
     xs, us = split_z(r["z"][0], N)
     assert np.abs(r["u0"][0] - c["inputs"][0]).max() <= U0_ABS_TOL
