@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
       if (lane == 0) b = (long long)atomicAdd(counter, 1ull);
       b = __shfl_sync(0xffffffffu, b, 0);
       if (b < B) {
-        obca::lane_begin(p, pT, o, obca::init_point<false>(c, in, b), L);
+        obca::lane_begin(p, pT, o, obca::init_point<0>(c, in, b), L);
         active = true;
       } else {
         exhausted = true;
@@ -675,6 +675,7 @@ __global__ void __launch_bounds__(kObcaThreads)
 #endif
   c.p = &p, c.pT = &pT, c.o = &o, c.s0 = obca::slot_ptr(scratch, p.N, blockIdx.x);
   c.r0 = rec_in_smem ? s_rec : nullptr;
+  c.rx = (rec_in_smem & 2) ? s_rec + (size_t)(p.N + 1) * obca::kRecRows : nullptr;
   const long long nz = 8LL * p.N + 6;
   for (;;) {
     __syncthreads();
@@ -683,7 +684,7 @@ __global__ void __launch_bounds__(kObcaThreads)
     const long long b = s_b;
     if (b >= B) break;
     Result res;
-    obca::solve_problem<true>(c, in, b, res);
+    obca::solve_problem<1>(c, in, b, res);
     __syncthreads();
     if (c.wd.wid == 0) {
       if (out.z) obca::unpack(p, c.s0, out.z + b * nz);
@@ -732,6 +733,7 @@ __global__ void __launch_bounds__(kObcaThreads)
   c.wd.csub = s_csub, c.wd.bcast = s_bcast;
   c.p = &p, c.pT = &pT, c.o = &o, c.s0 = obca::slot_ptr(scratch, p.N, cid);
   c.r0 = rec_in_smem ? (crank == 0 ? s_rec : obca::ob_map_rank(s_rec, 0)) : nullptr;
+  c.rx = (rec_in_smem & 2) ? s_rec + (size_t)(p.N + 1) * obca::kRecRows : nullptr;
   const long long nz = 8LL * p.N + 6;
   for (;;) {
     obca::ob_cluster_sync();  // everybody is done with the previous problem (and has read its s_b)
@@ -743,7 +745,7 @@ __global__ void __launch_bounds__(kObcaThreads)
     const long long b = s_b;
     if (b >= B) break;
     Result res;
-    obca::solve_problem<true>(c, in, b, res);
+    obca::solve_problem<2>(c, in, b, res);
     obca::ob_cluster_sync();
     if (c.wd.wid == 0) {
       if (out.z) obca::unpack(p, c.s0, out.z + b * nz);
@@ -1169,14 +1171,9 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
   cudaMemsetAsync(h->counter, 0, 16 * sizeof(unsigned long long), st);
   bool launched = false;
   if (wide && csz) {
-    size_t rec_bytes = (size_t)(h->p.N + 1) * obca::kRecRows * sizeof(double);
-    cudaFuncAttributes fa;
-    if (getenv("TTMPC_OBCA_REC_GLOBAL") || cudaFuncGetAttributes(&fa, ttmpc_obca_cluster_kernel) != cudaSuccess ||
-        rec_bytes + fa.sharedSizeBytes > h->smem_optin ||
-        cudaFuncSetAttribute(ttmpc_obca_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_bytes) != cudaSuccess)
-      rec_bytes = 0;
-    bool ok = true;
-    if (csz > 8) ok = cudaFuncSetAttribute(ttmpc_obca_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    const size_t rec_bytes = ((size_t)(h->p.N + 1) * obca::kRecRows + obca::kRecXchg) * sizeof(double);
+    bool ok = cudaFuncSetAttribute(ttmpc_obca_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_bytes) == cudaSuccess;
+    if (ok && csz > 8) ok = cudaFuncSetAttribute(ttmpc_obca_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof lc);
     lc.blockDim = dim3(kObcaThreads), lc.dynamicSmemBytes = rec_bytes, lc.stream = st;
@@ -1190,7 +1187,7 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
     if (ok) {
       if (blocks > max_clusters) blocks = max_clusters;  // persistent clusters pull problems from the queue
       lc.gridDim = dim3((unsigned)(blocks * csz));
-      const int rec_flag = rec_bytes ? 1 : 0;
+      const int rec_flag = 3;  // recursion blocks and the exchange buffer of the lane-parallel Riccati recursion in shared memory
       ok = cudaLaunchKernelEx(&lc, ttmpc_obca_cluster_kernel, h->p, pT, o, h->ob_scratch, B, in, so, h->counter, rec_flag) == cudaSuccess;
     }
     if (ok) {
@@ -1203,14 +1200,10 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
   if (launched) {
   } else if (wide) {
     // the recursion blocks of all stages in shared memory when they fit (N = 50: 36 KB, N = 256: 181 KB)
-    size_t rec_bytes = (size_t)(h->p.N + 1) * obca::kRecRows * sizeof(double);
-    cudaFuncAttributes fa;
-    if (getenv("TTMPC_OBCA_REC_GLOBAL") || cudaFuncGetAttributes(&fa, ttmpc_obca_wide_kernel) != cudaSuccess ||
-        rec_bytes + fa.sharedSizeBytes > h->smem_optin ||
-        cudaFuncSetAttribute(ttmpc_obca_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_bytes) != cudaSuccess)
-      rec_bytes = 0;
-    ttmpc_obca_wide_kernel<<<(unsigned)blocks, kObcaThreads, rec_bytes, st>>>(h->p, pT, o, h->ob_scratch, B, in, so, h->counter,
-                                                                              rec_bytes ? 1 : 0);
+    const size_t rec_bytes = ((size_t)(h->p.N + 1) * obca::kRecRows + obca::kRecXchg) * sizeof(double);
+    cudaError_t ca = cudaFuncSetAttribute(ttmpc_obca_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_bytes);
+    if (ca != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "obca kernel: shared memory for the recursion blocks", ca);
+    ttmpc_obca_wide_kernel<<<(unsigned)blocks, kObcaThreads, rec_bytes, st>>>(h->p, pT, o, h->ob_scratch, B, in, so, h->counter, 3);
     h->launches[8]++;
   } else {
     ttmpc_obca_kernel<<<(unsigned)blocks, kObcaThreads, 0, st>>>(h->p, pT, o, h->ob_scratch, B, in, so, h->counter);
@@ -1218,6 +1211,21 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
   }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "obca kernel launch", ce);
+#ifdef TTMPC_OBCA_TIMING  // development build: cycles between the phase boundaries as seen by thread 0 of block 0
+  {
+    cudaStreamSynchronize(st);
+    long long t[16];
+    cudaMemcpyFromSymbol(t, obca::g_ob_t, sizeof t);
+    static const char* nm[13] = {"driver->stats", "stats pairs", "stats xu+gather", "->factor", "factor pairs+gather", "factor recursion",
+                                 "factor bcast sync", "->direction", "direction recursion", "direction sync", "direction pairs+gather",
+                                 "->trial", "trial+gather"};
+    long long tot = 0;
+    for (int i = 0; i < 13; i++) tot += t[i];
+    for (int i = 0; i < 13; i++) fprintf(stderr, "  %-24s %10lld cycles %5.1f %%\n", nm[i], t[i], 100.0 * t[i] / (tot > 0 ? tot : 1));
+    memset(t, 0, sizeof t);
+    cudaMemcpyToSymbol(obca::g_ob_t, t, sizeof t);
+  }
+#endif
   return TTMPC_OK;
 }
 

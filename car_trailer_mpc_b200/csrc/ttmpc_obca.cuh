@@ -49,6 +49,7 @@ constexpr int oW = 0, oDW = 8, oREF = 16, oLAM = 24, oLAMP = 30, oZL = 36, oZU =
 // (N + 1) * kRecRows doubles fit -- a block in SHARED memory, so that the serial recursion never waits for L2.
 constexpr int rK = 0, rKFF = 12, rP = 14, rPV = 35, rA = 41, rCD = 50, rG = 56, rSIG = 64, rHX = 66;
 constexpr int kRecRows = 88;
+constexpr int kRecXchg = 48;  // exchange buffer of factor_rec_lanes: a 6x6 block + a 6-vector
 constexpr int oREC = 52;
 constexpr int oRP = 140;  // wide mode only: the pairs' J_x'y (4) of the stage
 constexpr int kBaseRows = 160;
@@ -515,6 +516,7 @@ struct Ctx {
   double* r0 = nullptr;  // recursion blocks of all stages in shared memory (CTA-per-problem kernel), else null
   TT_HD double* stage(int k) const { return s0 + (size_t)k * kStageDoubles; }
   TT_HD double* rstage(int k) const { return r0 ? r0 + (size_t)k * kRecRows : s0 + (size_t)k * kStageDoubles + oREC; }
+  double* rx = nullptr;  // kRecXchg doubles of shared memory for the lane-parallel Riccati recursion (factor_rec_lanes), else null
 };
 TT_HD double* pair_ptr(double* ps, int j) { return ps + kBasePad + j; }
 
@@ -566,16 +568,18 @@ TT_HD double* ob_map_rank(double* p, int rank) {
   return p;
 #endif
 }
-// barrier over everything that works on the problem: the CTA, or the cluster
+// barrier over everything that works on the problem: the CTA (WIDE 1), or the cluster (WIDE 2).  WIDE is a template
+// parameter all the way down so that each kernel carries its own flavour of the sweeps only (the sweeps are ~300 KB
+// of code per copy; the instruction cache is the first-order effect in these kernels).
+template <int WIDE>
 TT_HD void ob_sync_all(const Ctx& c) {
 #if defined(__CUDA_ARCH__)
-  if (c.wd.nc > 1)
+  if (WIDE == 2)
     ob_cluster_sync();
   else
     __syncthreads();
-#else
-  (void)c;
 #endif
+  (void)c;
 }
 // How a slot of the per-warp records is combined: 2 bits per slot (0 sum, 1 max, 2 min), slot i at bits 2i.
 // update_stats: [sumlog theta cinf rd lam1 z1 cmax cmin | J sumlog theta cinf rd lam1 z1 cmax cmin]
@@ -592,9 +596,10 @@ struct PartView {
 // ORDER (every warp of the CTA / cluster combines the same numbers in the same order: identical statistics everywhere
 // without a broadcast).  One CTA: its nw warp records.  Cluster: warp 0 of every CTA folds the CTA's records slot by
 // slot (`ops`) and writes the subtotal into every CTA's csub[rank]; after the cluster barrier the nc subtotals.
+template <int WIDE>
 TT_HD PartView ob_gather(const Ctx& c, unsigned long long ops) {
 #if defined(__CUDA_ARCH__)
-  if (c.wd.nc > 1) {
+  if (WIDE == 2) {
     __syncthreads();
     if (c.wd.lw == 0) {
       const int i = (int)(threadIdx.x & 31);
@@ -631,7 +636,7 @@ TT_HD bool var_lo(const Params& p, int j) { return ((p.bl >> j) & 1u) != 0; }
 TT_HD bool var_up(const Params& p, int j) { return ((p.bu >> j) & 1u) != 0; }
 
 // ---- starting point (mpc_control_obs.py:216-239 + Ipopt's slack initialisation and interior push) ----
-template <bool WIDE>
+template <int WIDE>
 TT_HD bool init_point(const Ctx& c0, const ProblemIn& in, long long b) {
   const Params& p0 = *c0.p;
   const ObParams& o = *c0.o;
@@ -708,7 +713,7 @@ TT_HD bool init_point(const Ctx& c0, const ProblemIn& in, long long b) {
 // variable pushed back into the interior of its bounds exactly like a starting point (Ipopt's bound_push / bound_frac),
 // slacks re-seated on their rows, all multipliers back to their initial values.  (Ipopt would enter its feasibility
 // restoration phase here and, on return, also resets the multipliers)
-template <bool WIDE>
+template <int WIDE>
 TT_HD void restart_point(const Ctx& c0) {
   const Params& p0 = *c0.p;
   const ObParams& o = *c0.o;
@@ -1013,6 +1018,115 @@ TT_HD void load_hx(const double* pr, double (*Hx)[NX]) {
     for (int j = i; j < NX; j++) Hx[i][j] = Hx[j][i] = bld(pr, rHX + SY(i, j));
 }
 
+#if defined(__CUDA_ARCH__)
+TT_HD double pick6(const double* a, int i) {
+  double v = a[0];
+  TT_UNROLL
+  for (int j = 1; j < NX; j++) v = (i == j) ? a[j] : v;
+  return v;
+}
+// The Riccati recursion of the CTA- / cluster-per-problem kernels (what factor<2> does redundantly in every lane of
+// warp 0) with the 6x6 algebra dealt to lanes 0..5: lane i carries row i of the value function P (= column i, P is kept
+// exactly symmetric) and entry i of p, computes row i of P A and entry i of h, and -- after one exchange through 42
+// doubles of shared memory -- column i of A'(P A) - S'K and entry i of the new p; a second exchange symmetrises.  Same
+// formulas element by element as factor<2>, a quarter of the instructions on the one warp everything else waits for.
+// Needs the recursion blocks in shared memory (Ctx::r0) and the exchange buffer Ctx::rx.
+__device__ __noinline__ bool factor_rec_lanes(const Ctx& c) {
+  const Params& p0 = *c.p;
+  const int N = p0.N;
+  const double dt = p0.dt;
+  const int lane = (int)(threadIdx.x & 31), li = lane < NX ? lane : NX - 1;
+  const bool act = lane < NX;
+  double* T = c.rx;
+  double* Hs = c.rx + 36;
+  double Prow[NX], pn_i = 0.0;
+  TT_UNROLL
+  for (int j = 0; j < NX; j++) Prow[j] = 0.0;
+  if (c.wd.flag == nullptr && c.wd.nc <= 1)  // the pair phase found a block that is not positive definite
+    for (int w_ = 0; w_ < c.wd.nw; w_++)
+      if (c.wd.part[w_ * kPart] == 0.0) return false;
+  for (int k = N; k >= 0; k--) {
+    double* pr = c.rstage(k);
+    const Params& p = (k == N) ? *c.pT : p0;
+    const bool has_x = k >= 1;
+    if (!ob_await(c, k)) return false;  // pipelined: the stage's warp has left its blocks (or found one not PD)
+    const double gx_i = pr[rG + li];
+    if (k == N) {
+      TT_UNROLL
+      for (int j = 0; j < NX; j++) Prow[j] = pr[rHX + SY(li, j)];
+      pn_i = gx_i;
+    } else {
+      Lin m;
+      m.a02 = pr[rA + 0], m.a05 = pr[rA + 1], m.a12 = pr[rA + 2], m.a15 = pr[rA + 3];
+      m.a24 = pr[rA + 4], m.a25 = pr[rA + 5], m.a33 = pr[rA + 6], m.a34 = pr[rA + 7];
+      m.a35 = pr[rA + 8];
+      double cdef[NX];
+      TT_UNROLL
+      for (int j = 0; j < NX; j++) cdef[j] = pr[rCD + j];
+      const double s6 = pr[rSIG], s7 = pr[rSIG + 1], g6 = pr[rG + 6], g7 = pr[rG + 7];
+      double h_i = pn_i;
+      TT_UNROLL
+      for (int j = 0; j < NX; j++) h_i -= Prow[j] * cdef[j];
+      double PArow[NX];
+      At_mul(m, Prow, PArow);
+      __syncwarp();  // the previous stage's reads of the exchange buffer are done
+      if (act) {
+        TT_UNROLL
+        for (int j = 0; j < NX; j++) T[li * NX + j] = PArow[j];
+        Hs[li] = h_i;
+      }
+      __syncwarp();
+      double PA4[NX], PA5[NX], PAcol[NX], h[NX];
+      TT_UNROLL
+      for (int j = 0; j < NX; j++) PA4[j] = T[4 * NX + j], PA5[j] = T[5 * NX + j], PAcol[j] = T[j * NX + li], h[j] = Hs[j];
+      const double P55 = __shfl_sync(0xffffffffu, Prow[5], 5), P54 = __shfl_sync(0xffffffffu, Prow[4], 5);
+      const double P44 = __shfl_sync(0xffffffffu, Prow[4], 4);
+      // B has two entries: B[5][0] = B[4][1] = dt
+      const double r00 = p.R2[0] + dt * dt * P55 + s6, r01 = p.R2[1] + dt * dt * P54;
+      const double r11 = p.R2[2] + dt * dt * P44 + s7;
+      const double det = r00 * r11 - r01 * r01;
+      if (!(r00 > 0.0) || !(det > 0.0)) return false;
+      const double idet = tt_rcp(det);
+      const double i00 = r11 * idet, i01 = -r01 * idet, i11 = r00 * idet;
+      const double Sh0_l = dt * PAcol[5], Sh1_l = dt * PAcol[4];
+      const double Kf0_l = i00 * Sh0_l + i01 * Sh1_l, Kf1_l = i01 * Sh0_l + i11 * Sh1_l;
+      const double bh0 = g6 + dt * h[5], bh1 = g7 + dt * h[4];
+      const double kff0 = i00 * bh0 + i01 * bh1, kff1 = i01 * bh0 + i11 * bh1;
+      if (act) pr[rK + li] = Kf0_l, pr[rK + NX + li] = Kf1_l;
+      if (lane == 0) pr[rKFF] = kff0, pr[rKFF + 1] = kff1;
+      if (has_x) {
+        double acol[NX], ath[NX], Pkcol[NX];
+        At_mul(m, PAcol, acol);  // column li of A'(P A)
+        TT_UNROLL
+        for (int i = 0; i < NX; i++) {
+          const double Sh0i = dt * PA5[i], Sh1i = dt * PA4[i];
+          Pkcol[i] = pr[rHX + SY(i, li)] + acol[i] - (Sh0i * Kf0_l + Sh1i * Kf1_l);
+        }
+        At_mul(m, h, ath);
+        const double pk_i = gx_i + pick6(ath, li) - (Sh0_l * kff0 + Sh1_l * kff1);
+        __syncwarp();  // every lane has taken what it needs of P A
+        if (act) {
+          TT_UNROLL
+          for (int i = 0; i < NX; i++) T[i * NX + li] = Pkcol[i];
+        }
+        __syncwarp();
+        TT_UNROLL
+        for (int i = 0; i < NX; i++) Prow[i] = 0.5 * (T[li * NX + i] + Pkcol[i]);  // (Pk[li][i] + Pk[i][li]) / 2
+        pn_i = pk_i;
+      }
+    }
+    if (has_x && act) {
+      pr[rPV + li] = pn_i;
+      TT_UNROLL
+      for (int j = 0; j < NX; j++)
+        if (j >= li) pr[rP + SY(li, j)] = Prow[j];
+    }
+  }
+  __syncwarp();
+  return true;
+}
+#endif
+
 // ---- sweep 2 (backward): condensation of the pairs + Riccati factorisation.  false: wrong inertia ----
 template <int MODE>
 TT_HD bool factor(const Ctx& c, double mu, double delta) {
@@ -1020,6 +1134,9 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
   const ObParams& o = *c.o;
   const int N = p0.N;
   const double dt = p0.dt;
+#if defined(__CUDA_ARCH__) && !defined(TTMPC_OBCA_REC_REDUNDANT)
+  if (MODE == 2) return factor_rec_lanes(c);  // the device kernels always have Ctx::r0 / rx in shared memory
+#endif
   double Pn[NX][NX], pn[NX], xn[NX], ln[NX];
   for (int i = 0; i < NX; i++) {
     pn[i] = xn[i] = ln[i] = 0.0;
@@ -1505,8 +1622,16 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
     const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
     const bool has_x = k >= 1, has_u = k < N;
     double w[NW], g[NW];
-    if (MODE == 1)  // pair phase: dx of the stage was stored by the recursion on warp 0
+    if (MODE == 1) {  // pair phase: dx of the stage was stored by the recursion on warp 0
       for (int i = 0; i < NX; i++) dx[i] = has_x ? bld(ps, oDW + i) : 0.0;
+      if (has_x) {  // lambda+_k = -(p_k + P_k dx_k) is local to the stage: here, not on the serial path of warp 0
+        for (int i = 0; i < NX; i++) {
+          double s = bld(pr, rPV + i);
+          for (int j = 0; j < NX; j++) s += bld(pr, rP + SY(i, j)) * dx[j];
+          bst(ps, oLAMP + i, -s);
+        }
+      }
+    }
     if (MODE == 2) {  // the recursion needs neither the iterate nor the gradient
       for (int j = 0; j < NW; j++) w[j] = g[j] = 0.0;
     } else {
@@ -1617,11 +1742,12 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
       }
       nd[4] += p.dt * dw[7];
       nd[5] += p.dt * dw[6];
-      for (int i = 0; i < NX; i++) {
-        double s = bld(prq, rPV + i);
-        for (int j = 0; j < NX; j++) s += bld(prq, rP + SY(i, j)) * nd[j];
-        bst(pq, oLAMP + i, -s);
-      }
+      if (MODE != 2)  // MODE 2: left to the warp of stage k+1 (MODE 1)
+        for (int i = 0; i < NX; i++) {
+          double s = bld(prq, rPV + i);
+          for (int j = 0; j < NX; j++) s += bld(prq, rP + SY(i, j)) * nd[j];
+          bst(pq, oLAMP + i, -s);
+        }
       for (int i = 0; i < NX; i++) dx[i] = nd[i];
     }
   }
@@ -1743,13 +1869,30 @@ TT_HD void trial(const Ctx& c, double alpha, TrialOut& tr) {
 // ------------------------------------------------------------------------------------------------
 // the sweeps as the driver calls them: fused on one warp (WIDE = false), or dealt out over the warps of a CTA
 // ------------------------------------------------------------------------------------------------
+// Development switch -DTTMPC_OBCA_TIMING: thread 0 of block 0 accumulates the clock cycles between the phase boundaries
+// of the CTA- / cluster-per-problem kernels (what the critical path is made of); printed by ttmpc.cu after the solve.
+#if defined(__CUDACC__) && defined(TTMPC_OBCA_TIMING)
+__device__ long long g_ob_t[16];
+__device__ long long g_ob_last;
+#endif
+#if defined(__CUDA_ARCH__) && defined(TTMPC_OBCA_TIMING)
+#define OB_T(i)                                          \
+  do {                                                   \
+    if (threadIdx.x == 0 && blockIdx.x == 0) {           \
+      const long long now_ = clock64();                  \
+      g_ob_t[i] += now_ - g_ob_last, g_ob_last = now_;   \
+    }                                                    \
+  } while (0)
+#else
+#define OB_T(i) ((void)0)
+#endif
 #if defined(__CUDA_ARCH__)
 TT_HD void ob_cta_sync() { __syncthreads(); }
 #else
 TT_HD void ob_cta_sync() {}
 #endif
 
-template <bool WIDE>
+template <int WIDE>
 TT_HD void run_update_stats(const Ctx& c, bool do_update, double alpha, double alpha_du, double mu_step, double delta_step,
                             Stats& st) {
   if (!WIDE) {
@@ -1757,11 +1900,14 @@ TT_HD void run_update_stats(const Ctx& c, bool do_update, double alpha, double a
     return;
   }
 #if defined(__CUDA_ARCH__)
-  ob_sync_all(c);
+  ob_sync_all<WIDE>(c);
+  OB_T(0);
   update_stats<1>(c, do_update, alpha, alpha_du, mu_step, delta_step, st);  // step + pairs, stage k on warp k % nw
-  ob_sync_all(c);
+  ob_sync_all<WIDE>(c);
+  OB_T(1);
   update_stats<3>(c, do_update, alpha, alpha_du, mu_step, delta_step, st);  // (x, u) statistics, stage-parallel as well
-  const PartView pv = ob_gather(c, kOpsStats);
+  const PartView pv = ob_gather<WIDE>(c, kOpsStats);
+  OB_T(2);
 #else
   for (int w = 0; w < c.wd.nw; w++) {
     Ctx cw = c;
@@ -1787,12 +1933,30 @@ TT_HD void run_update_stats(const Ctx& c, bool do_update, double alpha, double a
   }
 }
 
-template <bool WIDE>
+template <int WIDE>
 TT_HD bool run_factor(const Ctx& c, double mu, double delta) {
   if (!WIDE) return factor_fused(c, mu, delta);
 #if defined(__CUDA_ARCH__)
-  ob_sync_all(c);
-  if (c.wd.flag != nullptr && c.wd.nw >= 3) {  // pipelined: warps 1.. condense the pairs, warp 0 trails them with the recursion
+  ob_sync_all<WIDE>(c);
+  if (WIDE == 2) {  // cluster: pair phase on every warp of the cluster, then the recursion on warp 0 of CTA 0
+    OB_T(3);
+    factor<1>(c, mu, delta);
+    const PartView pv = ob_gather<WIDE>(c, kOpsFactor);
+    OB_T(4);
+    for (int w = 0; w < pv.n; w++)
+      if (pv.p[w * kPart] == 0.0) return false;  // some pair block is not positive definite (the same verdict everywhere)
+    if (c.wd.wid == 0) {
+      const bool ok = factor<2>(c, mu, delta);
+      const int i = (int)(threadIdx.x & 31);
+      if (i < c.wd.nc) ob_map_rank(c.wd.bcast, i)[0] = ok ? 1.0 : 0.0;
+    }
+    OB_T(5);
+    ob_cluster_sync();
+    OB_T(6);
+    return c.wd.bcast[0] != 0.0;
+  }
+#ifndef TTMPC_OBCA_NO_PIPELINE
+  {  // pipelined: warps 1.. condense the pairs, warp 0 trails them with the recursion
     ++*c.wd.epoch;
     Ctx cw = c;
     cw.wd.dn = c.wd.nw - 1, cw.wd.di = c.wd.wid - 1;
@@ -1805,19 +1969,7 @@ TT_HD bool run_factor(const Ctx& c, double mu, double delta) {
     ob_cta_sync();
     return c.wd.bcast[0] != 0.0;
   }
-  if (c.wd.nc > 1) {  // cluster: pair phase on every warp of the cluster, then the recursion on warp 0 of CTA 0
-    factor<1>(c, mu, delta);
-    const PartView pv = ob_gather(c, kOpsFactor);
-    for (int w = 0; w < pv.n; w++)
-      if (pv.p[w * kPart] == 0.0) return false;  // some pair block is not positive definite (the same verdict everywhere)
-    if (c.wd.wid == 0) {
-      const bool ok = factor<2>(c, mu, delta);
-      const int i = (int)(threadIdx.x & 31);
-      if (i < c.wd.nc) ob_map_rank(c.wd.bcast, i)[0] = ok ? 1.0 : 0.0;
-    }
-    ob_cluster_sync();
-    return c.wd.bcast[0] != 0.0;
-  }
+#else
   factor<1>(c, mu, delta);
   ob_cta_sync();
   if (c.wd.wid == 0) {
@@ -1826,6 +1978,7 @@ TT_HD bool run_factor(const Ctx& c, double mu, double delta) {
   }
   ob_cta_sync();
   return c.wd.bcast[0] != 0.0;
+#endif
 #else
   for (int w = 0; w < c.wd.nw; w++) {
     Ctx cw = c;
@@ -1836,7 +1989,7 @@ TT_HD bool run_factor(const Ctx& c, double mu, double delta) {
 #endif
 }
 
-template <bool WIDE>
+template <int WIDE>
 TT_HD void run_direction(const Ctx& c, double mu, double tau, double delta, Dir& di) {
   if (!WIDE) {
     direction<0>(c, mu, tau, delta, di);
@@ -1844,9 +1997,10 @@ TT_HD void run_direction(const Ctx& c, double mu, double tau, double delta, Dir&
   }
   Dir dummy;
 #if defined(__CUDA_ARCH__)
-  ob_sync_all(c);
+  ob_sync_all<WIDE>(c);
   PartView pv{c.wd.part, c.wd.nw};
-  if (c.wd.flag != nullptr && c.wd.nw >= 3) {  // pipelined: warp 0 leads with the recursion, warps 1.. follow with the pairs
+#ifndef TTMPC_OBCA_NO_PIPELINE
+  if (WIDE == 1) {  // pipelined: warp 0 leads with the recursion, warps 1.. follow with the pairs
     ++*c.wd.epoch;
     Ctx cw = c;
     cw.wd.dn = c.wd.nw - 1, cw.wd.di = c.wd.wid - 1;
@@ -1860,11 +2014,17 @@ TT_HD void run_direction(const Ctx& c, double mu, double tau, double delta, Dir&
       direction<1>(cw, mu, tau, delta, dummy);
     }
     ob_cta_sync();
-  } else {
-    if (c.wd.wid == 0) direction<2>(c, mu, tau, delta, dummy);  // the dx / lambda+ recursion
-    ob_sync_all(c);
-    direction<1>(c, mu, tau, delta, dummy);  // pairs and step limits, stage k on warp k % nw
-    pv = ob_gather(c, kOpsDir);
+  } else
+#endif
+  {
+    OB_T(7);
+    if (c.wd.wid == 0) direction<2>(c, mu, tau, delta, dummy);  // the dx recursion
+    OB_T(8);
+    ob_sync_all<WIDE>(c);
+    OB_T(9);
+    direction<1>(c, mu, tau, delta, dummy);  // pairs, lambda+ and step limits, stage k on warp k % nw
+    pv = ob_gather<WIDE>(c, kOpsDir);
+    OB_T(10);
   }
 #else
   direction<2>(c, mu, tau, delta, dummy);
@@ -1884,16 +2044,18 @@ TT_HD void run_direction(const Ctx& c, double mu, double tau, double delta, Dir&
   }
 }
 
-template <bool WIDE>
+template <int WIDE>
 TT_HD void run_trial(const Ctx& c, double alpha, TrialOut& tr) {
   if (!WIDE) {
     trial<0>(c, alpha, tr);
     return;
   }
 #if defined(__CUDA_ARCH__)
-  ob_sync_all(c);
+  ob_sync_all<WIDE>(c);
+  OB_T(11);
   trial<1>(c, alpha, tr);
-  const PartView pv = ob_gather(c, kOpsTrial);
+  const PartView pv = ob_gather<WIDE>(c, kOpsTrial);
+  OB_T(12);
 #else
   for (int w = 0; w < c.wd.nw; w++) {
     Ctx cw = c;
@@ -1963,7 +2125,7 @@ TT_HD void lane_result(const Lane& L, int status, Result& res) {
 }
 
 // head of an iteration; true when the lane is finished (res filled in)
-template <bool WIDE = false>
+template <int WIDE = 0>
 TT_HD bool lane_head(const Ctx& c, Lane& L, Result& res) {
   const Params& p = *c.p;
   Stats& st = L.st;
@@ -2021,7 +2183,7 @@ TT_HD bool lane_head(const Ctx& c, Lane& L, Result& res) {
 }
 
 // one factorisation attempt; true when the lane is finished (no usable regularisation)
-template <bool WIDE = false>
+template <int WIDE = 0>
 TT_HD bool lane_factor_once(const Ctx& c, Lane& L, Result& res) {
   if (run_factor<WIDE>(c, L.mu, L.delta)) {
     if (L.delta > 0.0) L.delta_last = L.delta;
@@ -2048,7 +2210,7 @@ TT_HD void lane_accept(Lane& L, double a) {
   L.iter++;
 }
 
-template <bool WIDE = false>
+template <int WIDE = 0>
 TT_HD void lane_direction(const Ctx& c, Lane& L) {
   const Params& p = *c.p;
   run_direction<WIDE>(c, L.mu, L.tau, L.delta, L.di);
@@ -2067,7 +2229,7 @@ TT_HD void lane_direction(const Ctx& c, Lane& L) {
 }
 
 // one line-search trial; true when the lane is finished (third consecutive line-search failure)
-template <bool WIDE = false>
+template <int WIDE = 0>
 TT_HD bool lane_trial_once(const Ctx& c, Lane& L, Result& res) {
   const double a = L.ls_a, theta = L.theta, phi = L.phi, gd = L.di.gphi_d;
   TrialOut tr;
@@ -2133,11 +2295,11 @@ TT_HD bool lane_trial_once(const Ctx& c, Lane& L, Result& res) {
 
 // sequential driver of one problem: WIDE = false on one warp (ttmpc_obca_kernel interleaves the same phases over its 8
 // problem slots), WIDE = true on all warps of a CTA (ttmpc_obca_wide_kernel; wd describes the CTA)
-template <bool WIDE>
+template <int WIDE>
 TT_HD void solve_problem(const Ctx& c, const ProblemIn& in, long long b, Result& res) {
   Lane L;
   const bool x0_bad = init_point<WIDE>(c, in, b);
-  if (WIDE) ob_sync_all(c);
+  if (WIDE) ob_sync_all<WIDE>(c);
   lane_begin(*c.p, *c.pT, *c.o, x0_bad, L);
   for (;;) {
     if (lane_head<WIDE>(c, L, res)) return;
@@ -2153,7 +2315,7 @@ TT_HD void solve_lane(const Params& p, const Params& pT, const ObParams& o, doub
   Ctx c;
   c.wd.wid = 0, c.wd.nw = 1, c.wd.part = nullptr, c.wd.bcast = nullptr;
   c.p = &p, c.pT = &pT, c.o = &o, c.s0 = s0;
-  solve_problem<false>(c, in, b, res);
+  solve_problem<0>(c, in, b, res);
 }
 
 // states / inputs of the problem's iterate in the plain layout [x_0, u_0, ..., x_N] (what _split_decision_variables of

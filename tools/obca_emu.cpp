@@ -54,7 +54,7 @@ extern "C" int ttmpc_emu_obca_solve_batch(const ttmpc_config* cfg, const ttmpc_o
         obca::Ctx c;
         c.wd.wid = 0, c.wd.nw = g_wide_warps, c.wd.part = part.data(), c.wd.bcast = bcast.data();
         c.p = &p, c.pT = &pT, c.o = &o, c.s0 = s0;
-        obca::solve_problem<true>(c, in, b, r);
+        obca::solve_problem<1>(c, in, b, r);
       } else {
         obca::solve_lane(p, pT, o, s0, in, b, r);
       }
