@@ -567,6 +567,11 @@ static episode_kernel_t episode_kernel_for(const Params& p) {
 #define TTMPC_OBCA_THREADS 256
 #endif
 constexpr int kObcaThreads = TTMPC_OBCA_THREADS;  // 8 warps = 8 problem slots per CTA
+// threads of the CTA-per-problem kernel (experiment switch: 384 = 12 warps at 168 registers)
+#ifndef TTMPC_OBCA_WIDE_THREADS
+#define TTMPC_OBCA_WIDE_THREADS TTMPC_OBCA_THREADS
+#endif
+constexpr int kObcaWideThreads = TTMPC_OBCA_WIDE_THREADS;
 #ifndef TTMPC_OBCA_MIN_BLOCKS
 #define TTMPC_OBCA_MIN_BLOCKS 1
 #endif
@@ -655,11 +660,11 @@ __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
 // to the 8 warps for the pair work of every sweep, the recursions over the stages (Riccati, dx, the in-place update) run
 // on warp 0, statistics meet in shared memory (obca::run_* wrappers).  Same arithmetic as ttmpc_obca_kernel: the host
 // build of this decomposition reproduces the single-warp results bit for bit (tests/test_obca_cpu.py).
-__global__ void __launch_bounds__(kObcaThreads)
+__global__ void __launch_bounds__(kObcaWideThreads)
     ttmpc_obca_wide_kernel(const __grid_constant__ Params p, const __grid_constant__ Params pT,
                            const __grid_constant__ obca::ObParams o, double* __restrict__ scratch, long long B, ProblemIn in,
                            SolveOut out, unsigned long long* counter, int rec_in_smem) {
-  __shared__ double s_part[(kObcaThreads / 32) * obca::kPart];
+  __shared__ double s_part[(kObcaWideThreads / 32) * obca::kPart];
   __shared__ double s_bcast[32];
   __shared__ long long s_b;
   __shared__ int s_flag[TTMPC_MAX_HORIZON + 1];  // stage hand-over of the pipelined factor / direction sweeps
@@ -1133,16 +1138,18 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
   const Params& pT = h->plan_pT ? *h->plan_pT : h->p;  // terminal-stage parameters (the planner's box and weight)
   int sms = h->sms, per_sm = 1, per_sm_wide = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ttmpc_obca_kernel, kObcaThreads, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_wide, ttmpc_obca_wide_kernel, kObcaThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_wide, ttmpc_obca_wide_kernel, kObcaWideThreads, 0);
   if (per_sm < 1) per_sm = 1;
   if (per_sm_wide < 1) per_sm_wide = 1;
-  // up to 48 problems per SM: one CTA per problem (measured on B200, N = 50: 21 vs 73 ms for one problem, 376 vs 692 ms
-  // for 1 184, 2.23 vs 2.25 s for 8 192); beyond that: one warp per problem (16 384: 4.1 vs 4.6 s)
+  // One CTA per problem at every batch size (measured on B200, N = 50, recursion blocks in shared memory, lane-parallel
+  // Riccati recursion: 2 048 problems 0.43 vs 0.83 s, 8 192: 1.62 vs 2.01 s, 16 384: 3.00 vs 3.59 s for one warp per
+  // problem).  TTMPC_OBCA_WIDE_MAX=<n> sends batches above n to the warp-per-problem kernel (0: always).
   const char* wenv = getenv("TTMPC_OBCA_WIDE_MAX");
-  const bool wide = B <= (wenv ? atoll(wenv) : 48LL * sms);
+  const bool wide = !wenv || B <= atoll(wenv);
   // a handful of problems (fewer than SMs / cluster size): one thread-block cluster per problem -- the largest cluster
-  // (8, 4, 2 CTAs) that leaves every problem its own cluster and most warps a stage.  TTMPC_OBCA_CLUSTER=0 switches
-  // this off, =2/4/8/16 forces a size (16 is the non-portable maximum).
+  // (16, 8, 4, 2 CTAs) that leaves every problem its own cluster and most warps a stage; a size the device does not
+  // take (16 is the non-portable maximum) falls back to the next smaller one.  TTMPC_OBCA_CLUSTER=0 switches this off,
+  // =2/4/8/16 forces a size.
   int csz = 0;
   if (wide) {
     const char* cenv = getenv("TTMPC_OBCA_CLUSTER");
@@ -1150,7 +1157,7 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
       const int v = atoi(cenv);
       if (v == 2 || v == 4 || v == 8 || v == 16) csz = v;
     } else {
-      for (int cs = 8; cs >= 2 && !csz; cs >>= 1)
+      for (int cs = 16; cs >= 2 && !csz; cs >>= 1)
         if (B * cs <= sms && (kObcaThreads / 32) * cs / 2 < h->p.N + 1) csz = cs;
     }
   }
@@ -1158,7 +1165,6 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
   long long blocks = (B + wpc - 1) / wpc;
   const long long cap = (long long)sms * (wide ? per_sm_wide : per_sm);
   if (blocks > cap) blocks = cap;
-  if (csz && blocks * csz > cap) blocks = cap / csz > 0 ? cap / csz : 1;
   const size_t need = obca::scratch_doubles(h->p.N, (size_t)blocks * wpc);
   if (need > h->ob_doubles) {
     if (h->ob_scratch) cudaFree(h->ob_scratch);
@@ -1170,7 +1176,10 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
   }
   cudaMemsetAsync(h->counter, 0, 16 * sizeof(unsigned long long), st);
   bool launched = false;
-  if (wide && csz) {
+  const long long blocks_wide = blocks;
+  for (; wide && csz >= 2 && !launched; csz >>= 1) {
+    blocks = blocks_wide;
+    if (blocks * csz > cap) blocks = cap / csz > 0 ? cap / csz : 1;
     const size_t rec_bytes = ((size_t)(h->p.N + 1) * obca::kRecRows + obca::kRecXchg) * sizeof(double);
     bool ok = cudaFuncSetAttribute(ttmpc_obca_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_bytes) == cudaSuccess;
     if (ok && csz > 8) ok = cudaFuncSetAttribute(ttmpc_obca_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
@@ -1197,13 +1206,14 @@ static int obca_device(ttmpc_handle* h, const ttmpc_obstacles* obs, long long B,
       cudaGetLastError();  // this device / configuration takes no such cluster: the CTA-per-problem kernel below
     }
   }
+  if (!launched) blocks = blocks_wide;
   if (launched) {
   } else if (wide) {
     // the recursion blocks of all stages in shared memory when they fit (N = 50: 36 KB, N = 256: 181 KB)
     const size_t rec_bytes = ((size_t)(h->p.N + 1) * obca::kRecRows + obca::kRecXchg) * sizeof(double);
     cudaError_t ca = cudaFuncSetAttribute(ttmpc_obca_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_bytes);
     if (ca != cudaSuccess) return set_err(h, TTMPC_E_CUDA, "obca kernel: shared memory for the recursion blocks", ca);
-    ttmpc_obca_wide_kernel<<<(unsigned)blocks, kObcaThreads, rec_bytes, st>>>(h->p, pT, o, h->ob_scratch, B, in, so, h->counter, 3);
+    ttmpc_obca_wide_kernel<<<(unsigned)blocks, kObcaWideThreads, rec_bytes, st>>>(h->p, pT, o, h->ob_scratch, B, in, so, h->counter, 3);
     h->launches[8]++;
   } else {
     ttmpc_obca_kernel<<<(unsigned)blocks, kObcaThreads, 0, st>>>(h->p, pT, o, h->ob_scratch, B, in, so, h->counter);
