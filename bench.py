@@ -57,8 +57,10 @@ def algorithmic_bytes_per_solve(N: int) -> int:
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons of one GPU while the timed region runs: one long-lived
-    `nvidia-smi -lms 100` process (a fresh nvidia-smi per sample would take longer than a whole timed region)."""
+    """Samples SM clocks / throttle reasons of one GPU while the timed region runs.  In-process NVML calls from a thread
+    (a few microseconds each, every 10 ms); a looping `nvidia-smi -lms` process -- the first implementation -- was seen
+    to stall one step of a 20-step timed region by ~50 ms on some boxes (profiles/r2_bench_1gpu_final.json keeps such a
+    run), which is the measurement disturbing the measured.  Falls back to that process only if NVML cannot be loaded."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -66,8 +68,54 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.proc = None
+        self.thread = None
+        self.stop = False
+        self.sm, self.mx, self.reasons = [], [], set()
+
+    def _nvml_loop(self, nv, h):
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        try:
+            import threading
+
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber the devices: address the GPU by the UUID torch reports for it
+            h = None
+            try:
+                import torch
+
+                u = str(torch.cuda.get_device_properties(self.index).uuid)
+                h = nv.nvmlDeviceGetHandleByUUID(u if u.startswith("GPU-") else "GPU-" + u)
+            except Exception:
+                h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [v for v in vis.split(",") if v.strip().isdigit()]
+                h = nv.nvmlDeviceGetHandleByIndex(int(ids[self.index]) if self.index < len(ids) else self.index)
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))  # first sample before the timed region
+            self.sm.clear()
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -76,6 +124,11 @@ class ClockSampler:
             self.proc = None
 
     def finish(self) -> dict:
+        if self.thread is not None:
+            self.stop = True
+            self.thread.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         samples = []
         if self.proc is not None:
             time.sleep(0.11)
@@ -91,7 +144,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for s in samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
 def workload_config(N: int, B: int, world: int) -> dict:
@@ -372,6 +425,21 @@ def main() -> None:
             secondary["obca_B2048_N50"] = {"ms_per_step": e0.elapsed_time(e1), "solves_per_s": 2048 / e0.elapsed_time(e1) * 1e3,
                                            "frac_converged": float((sto <= 1).mean()), "mean_iters": float(ro["iters"].float().mean()),
                                            "workload": "11 rectangles of obstacles.json, window starts 0..340, sigma 0.002"}
+            # the single solve of the MPCTrackingControlObs shim (how the reference itself uses this controller, once per
+            # 50 ms control period): one thread-block cluster per problem
+            a1 = (obs, ao[1][:1].contiguous(), ao[2][:1].contiguous(), ao[3], ao[4])
+            s50.solve_obca_shared(*a1, want_z=False)
+            torch.cuda.synchronize()
+            n0 = dict(s50.kernel_launches())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                r1 = s50.solve_obca_shared(*a1, want_z=False)
+            e1.record()
+            torch.cuda.synchronize()
+            n1 = s50.kernel_launches()
+            secondary["obca_B1_N50"] = {"ms_per_step": e0.elapsed_time(e1) / 3, "iters": int(r1["iters"][0]), "status": int(r1["status"][0]),
+                                        "kernel": [k for k in n1 if n1[k] > n0.get(k, 0)]}
             s50.close()
 
     iters = r["iters"].cpu().numpy()
