@@ -1031,99 +1031,217 @@ TT_HD double pick6(const double* a, int i) {
 // doubles of shared memory -- column i of A'(P A) - S'K and entry i of the new p; a second exchange symmetrises.  Same
 // formulas element by element as factor<2>, a quarter of the instructions on the one warp everything else waits for.
 // Needs the recursion blocks in shared memory (Ctx::r0) and the exchange buffer Ctx::rx.
+// what the recursion reads of one stage's recursion block (the calling lane's view): 9 entries of A, defect (6),
+// Sigma_u (2), g_u (2), g_i, column i of the Hessian block -- plain arrays (a struct kept them in local memory)
+#define OB_REC_LOAD(A_, CD_, SG_, GI_, HX_, PR_)                                   \
+  do {                                                                             \
+    TT_UNROLL                                                                      \
+    for (int i_ = 0; i_ < 9; i_++) A_[i_] = (PR_)[rA + i_];                        \
+    TT_UNROLL                                                                      \
+    for (int j_ = 0; j_ < NX; j_++) CD_[j_] = (PR_)[rCD + j_];                     \
+    SG_[0] = (PR_)[rSIG], SG_[1] = (PR_)[rSIG + 1], SG_[2] = (PR_)[rG + 6], SG_[3] = (PR_)[rG + 7]; \
+    GI_ = (PR_)[rG + li];                                                          \
+    TT_UNROLL                                                                      \
+    for (int i_ = 0; i_ < NX; i_++) HX_[i_] = (PR_)[ohx[i_]];                      \
+  } while (0)
 __device__ __noinline__ bool factor_rec_lanes(const Ctx& c) {
+  // everything the loop needs of the context in registers: `c` lives in local memory, and the compiler has to assume
+  // that the stores through generic pointers below may change it
   const Params& p0 = *c.p;
   const int N = p0.N;
-  const double dt = p0.dt;
+  const double dt = p0.dt, dt2 = p0.dt * p0.dt;
+  const double R2a = p0.R2[0], R2b = p0.R2[1], R2c = p0.R2[2];
   const int lane = (int)(threadIdx.x & 31), li = lane < NX ? lane : NX - 1;
-  const bool act = lane < NX;
-  double* T = c.rx;
-  double* Hs = c.rx + 36;
+  double* const r0 = c.r0;
+  double* const T = c.rx;
+  // both live in this CTA's shared memory (the recursions run on warp 0 of the CTA that owns the blocks): LDS / STS
+  // instead of generic accesses, which cost two extra uniform-register moves each on this one warp
+  __builtin_assume(__isShared(r0));
+  __builtin_assume(__isShared(T));
+  double* const Trow = T + li * NX;  // row li of the exchange block
+  double* const Tcol = T + li;       // column li: Tcol[i * NX]
+  double* const Hs = T + 36;
+  volatile int* const flag = c.wd.flag;
+  const int ep = flag ? *c.wd.epoch : 0;
+  int ohx[NX];  // offsets of column / row li of a packed symmetric block
+  TT_UNROLL
+  for (int i = 0; i < NX; i++) ohx[i] = rHX + SY(i, li);
   double Prow[NX], pn_i = 0.0;
   TT_UNROLL
   for (int j = 0; j < NX; j++) Prow[j] = 0.0;
-  if (c.wd.flag == nullptr && c.wd.nc <= 1)  // the pair phase found a block that is not positive definite
+  if (flag == nullptr && c.wd.nc <= 1)  // the pair phase found a block that is not positive definite
     for (int w_ = 0; w_ < c.wd.nw; w_++)
       if (c.wd.part[w_ * kPart] == 0.0) return false;
+  if (!ob_await(c, N)) return false;  // pipelined: the stage's warp has left its blocks (or found one not PD)
+  double ia[9], icd[NX], isg[4], igi, ihx[NX];
+  OB_REC_LOAD(ia, icd, isg, igi, ihx, r0 + (size_t)N * kRecRows);
   for (int k = N; k >= 0; k--) {
-    double* pr = c.rstage(k);
-    const Params& p = (k == N) ? *c.pT : p0;
+    double* const pr = r0 + (size_t)k * kRecRows;
     const bool has_x = k >= 1;
-    if (!ob_await(c, k)) return false;  // pipelined: the stage's warp has left its blocks (or found one not PD)
-    const double gx_i = pr[rG + li];
+    // the next stage's block is requested before this stage's arithmetic (one warp: nothing else hides the latency).
+    // Pipelined kernel: the recursion trails the pair warps, so the block is normally there; if it is not, wait here.
+    double na[9], ncd[NX], nsg[4], ngi, nhx[NX];
+    {
+      const int kn = k > 0 ? k - 1 : 0;
+      if (flag && k > 0) {
+        if (!ob_await(c, kn)) return false;
+      }
+      OB_REC_LOAD(na, ncd, nsg, ngi, nhx, r0 + (size_t)kn * kRecRows);
+    }
+    const double gx_i = igi;
     if (k == N) {
       TT_UNROLL
-      for (int j = 0; j < NX; j++) Prow[j] = pr[rHX + SY(li, j)];
+      for (int j = 0; j < NX; j++) Prow[j] = ihx[j];
       pn_i = gx_i;
     } else {
       Lin m;
-      m.a02 = pr[rA + 0], m.a05 = pr[rA + 1], m.a12 = pr[rA + 2], m.a15 = pr[rA + 3];
-      m.a24 = pr[rA + 4], m.a25 = pr[rA + 5], m.a33 = pr[rA + 6], m.a34 = pr[rA + 7];
-      m.a35 = pr[rA + 8];
-      double cdef[NX];
-      TT_UNROLL
-      for (int j = 0; j < NX; j++) cdef[j] = pr[rCD + j];
-      const double s6 = pr[rSIG], s7 = pr[rSIG + 1], g6 = pr[rG + 6], g7 = pr[rG + 7];
+      m.a02 = ia[0], m.a05 = ia[1], m.a12 = ia[2], m.a15 = ia[3];
+      m.a24 = ia[4], m.a25 = ia[5], m.a33 = ia[6], m.a34 = ia[7];
+      m.a35 = ia[8];
       double h_i = pn_i;
       TT_UNROLL
-      for (int j = 0; j < NX; j++) h_i -= Prow[j] * cdef[j];
+      for (int j = 0; j < NX; j++) h_i -= Prow[j] * icd[j];
       double PArow[NX];
       At_mul(m, Prow, PArow);
       __syncwarp();  // the previous stage's reads of the exchange buffer are done
-      if (act) {
-        TT_UNROLL
-        for (int j = 0; j < NX; j++) T[li * NX + j] = PArow[j];
-        Hs[li] = h_i;
-      }
-      __syncwarp();
-      double PA4[NX], PA5[NX], PAcol[NX], h[NX];
       TT_UNROLL
-      for (int j = 0; j < NX; j++) PA4[j] = T[4 * NX + j], PA5[j] = T[5 * NX + j], PAcol[j] = T[j * NX + li], h[j] = Hs[j];
+      for (int j = 0; j < NX; j++) Trow[j] = PArow[j];  // (lanes 6..31 repeat lane 5: same addresses, same values -- no branch)
+      Hs[li] = h_i;
+      // the 2x2 pivot needs P44, P45, P55 only: while the exchange is under way
       const double P55 = __shfl_sync(0xffffffffu, Prow[5], 5), P54 = __shfl_sync(0xffffffffu, Prow[4], 5);
       const double P44 = __shfl_sync(0xffffffffu, Prow[4], 4);
       // B has two entries: B[5][0] = B[4][1] = dt
-      const double r00 = p.R2[0] + dt * dt * P55 + s6, r01 = p.R2[1] + dt * dt * P54;
-      const double r11 = p.R2[2] + dt * dt * P44 + s7;
+      const double r00 = R2a + dt2 * P55 + isg[0], r01 = R2b + dt2 * P54;
+      const double r11 = R2c + dt2 * P44 + isg[1];
       const double det = r00 * r11 - r01 * r01;
       if (!(r00 > 0.0) || !(det > 0.0)) return false;
       const double idet = tt_rcp(det);
       const double i00 = r11 * idet, i01 = -r01 * idet, i11 = r00 * idet;
+      __syncwarp();
+      double PA4[NX], PA5[NX], PAcol[NX], h[NX];
+      TT_UNROLL
+      for (int j = 0; j < NX; j++) PA4[j] = T[4 * NX + j], PA5[j] = T[5 * NX + j], PAcol[j] = Tcol[j * NX], h[j] = Hs[j];
       const double Sh0_l = dt * PAcol[5], Sh1_l = dt * PAcol[4];
       const double Kf0_l = i00 * Sh0_l + i01 * Sh1_l, Kf1_l = i01 * Sh0_l + i11 * Sh1_l;
-      const double bh0 = g6 + dt * h[5], bh1 = g7 + dt * h[4];
+      const double bh0 = isg[2] + dt * h[5], bh1 = isg[3] + dt * h[4];
       const double kff0 = i00 * bh0 + i01 * bh1, kff1 = i01 * bh0 + i11 * bh1;
-      if (act) pr[rK + li] = Kf0_l, pr[rK + NX + li] = Kf1_l;
-      if (lane == 0) pr[rKFF] = kff0, pr[rKFF + 1] = kff1;
+      pr[rK + li] = Kf0_l, pr[rK + NX + li] = Kf1_l;
+      pr[rKFF] = kff0, pr[rKFF + 1] = kff1;
       if (has_x) {
         double acol[NX], ath[NX], Pkcol[NX];
         At_mul(m, PAcol, acol);  // column li of A'(P A)
         TT_UNROLL
         for (int i = 0; i < NX; i++) {
           const double Sh0i = dt * PA5[i], Sh1i = dt * PA4[i];
-          Pkcol[i] = pr[rHX + SY(i, li)] + acol[i] - (Sh0i * Kf0_l + Sh1i * Kf1_l);
+          Pkcol[i] = ihx[i] + acol[i] - (Sh0i * Kf0_l + Sh1i * Kf1_l);
         }
         At_mul(m, h, ath);
         const double pk_i = gx_i + pick6(ath, li) - (Sh0_l * kff0 + Sh1_l * kff1);
         __syncwarp();  // every lane has taken what it needs of P A
-        if (act) {
-          TT_UNROLL
-          for (int i = 0; i < NX; i++) T[i * NX + li] = Pkcol[i];
-        }
+        TT_UNROLL
+        for (int i = 0; i < NX; i++) Tcol[i * NX] = Pkcol[i];
         __syncwarp();
         TT_UNROLL
-        for (int i = 0; i < NX; i++) Prow[i] = 0.5 * (T[li * NX + i] + Pkcol[i]);  // (Pk[li][i] + Pk[i][li]) / 2
+        for (int i = 0; i < NX; i++) Prow[i] = 0.5 * (Trow[i] + Pkcol[i]);  // (Pk[li][i] + Pk[i][li]) / 2
         pn_i = pk_i;
       }
     }
-    if (has_x && act) {
+    if (has_x) {
       pr[rPV + li] = pn_i;
       TT_UNROLL
       for (int j = 0; j < NX; j++)
-        if (j >= li) pr[rP + SY(li, j)] = Prow[j];
+        if (j >= li) pr[ohx[j] - rHX + rP] = Prow[j];
     }
+    TT_UNROLL
+    for (int i = 0; i < 9; i++) ia[i] = na[i];
+    TT_UNROLL
+    for (int j = 0; j < NX; j++) icd[j] = ncd[j], ihx[j] = nhx[j];
+    isg[0] = nsg[0], isg[1] = nsg[1], isg[2] = nsg[2], isg[3] = nsg[3];
+    igi = ngi;
   }
   __syncwarp();
   return true;
+}
+// The dx / du recursion of the direction sweep on warp 0 of the CTA- / cluster-per-problem kernels (what direction<2>
+// does): same formulas, the context in registers and the next stage's gains requested before this stage's arithmetic.
+__device__ __noinline__ void direction_rec(const Ctx& c) {
+  const int N = c.p->N;
+  const double dt = c.p->dt;
+  const double* const r0 = c.r0;
+  double* const s0 = c.s0;
+  __builtin_assume(__isShared(r0));  // see factor_rec_lanes
+  __builtin_assume(__isGlobal(s0));
+  const bool l0 = (threadIdx.x & 31) == 0;
+  volatile int* const flag = c.wd.flag;  // pipelined CTA kernel: stage hand-over to the pair warps
+  const int ep = flag ? *c.wd.epoch : 0;
+  double dx[NX];
+  TT_UNROLL
+  for (int i = 0; i < NX; i++) dx[i] = 0.0;
+  // gains, A and defect of the current stage; the next stage's are requested before this stage's arithmetic.  Plain
+  // arrays copied element by element: a struct assignment kept both copies in local memory (measured 3x slower).
+  double K[2 * NX], kff[2], a[9], cd[NX];
+  TT_UNROLL
+  for (int i = 0; i < 2 * NX; i++) K[i] = r0[rK + i];
+  kff[0] = r0[rKFF], kff[1] = r0[rKFF + 1];
+  TT_UNROLL
+  for (int i = 0; i < 9; i++) a[i] = r0[rA + i];
+  TT_UNROLL
+  for (int j = 0; j < NX; j++) cd[j] = r0[rCD + j];
+  for (int k = 0; k <= N; k++) {
+    double* const ps = s0 + (size_t)k * kStageDoubles;
+    const bool has_x = k >= 1, has_u = k < N;
+    const double* const pn = r0 + (size_t)((k + 1 < N) ? k + 1 : k) * kRecRows;  // (the last two stages: a harmless re-read)
+    double nK[2 * NX], nkff[2], na[9], ncd[NX];
+    TT_UNROLL
+    for (int i = 0; i < 2 * NX; i++) nK[i] = pn[rK + i];
+    nkff[0] = pn[rKFF], nkff[1] = pn[rKFF + 1];
+    TT_UNROLL
+    for (int i = 0; i < 9; i++) na[i] = pn[rA + i];
+    TT_UNROLL
+    for (int j = 0; j < NX; j++) ncd[j] = pn[rCD + j];
+    double du[NU] = {0.0, 0.0};
+    if (has_u) {
+      TT_UNROLL
+      for (int i = 0; i < NU; i++) {
+        double sacc = -kff[i];
+        TT_UNROLL
+        for (int j = 0; j < NX; j++) sacc -= K[i * NX + j] * dx[j];
+        du[i] = sacc;
+      }
+    }
+    if (has_x) {  // every lane stores the same values to the same addresses: one transaction, no branch on the lane
+      TT_UNROLL
+      for (int j = 0; j < NX; j++) ps[oDW + j] = dx[j];
+    }
+    if (has_u) ps[oDW + NX] = du[0], ps[oDW + NX + 1] = du[1];
+    if (flag) {  // pipelined: dx_k, du_k are in the stage's rows, its warp may take the pairs (cf. ob_publish)
+      __threadfence_block();
+      __syncwarp();
+      if (l0) flag[k] = ep;
+    }
+    if (has_u) {  // dx_{k+1} = A dx + B du - c_{k+1}
+      Lin m;
+      m.a02 = a[0], m.a05 = a[1], m.a12 = a[2], m.a15 = a[3];
+      m.a24 = a[4], m.a25 = a[5], m.a33 = a[6], m.a34 = a[7];
+      m.a35 = a[8];
+      double nd[NX];
+      A_mul(m, dx, nd);
+      TT_UNROLL
+      for (int i = 0; i < NX; i++) nd[i] -= cd[i];
+      nd[4] += dt * du[1];
+      nd[5] += dt * du[0];
+      TT_UNROLL
+      for (int i = 0; i < NX; i++) dx[i] = nd[i];
+    }
+    TT_UNROLL
+    for (int i = 0; i < 2 * NX; i++) K[i] = nK[i];
+    kff[0] = nkff[0], kff[1] = nkff[1];
+    TT_UNROLL
+    for (int i = 0; i < 9; i++) a[i] = na[i];
+    TT_UNROLL
+    for (int j = 0; j < NX; j++) cd[j] = ncd[j];
+  }
+  __syncwarp();
 }
 #endif
 
@@ -1609,6 +1727,12 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
   const int N = p0.N;
   di.a_pr = di.a_du = 1.0;
   di.gphi_d = 0.0;
+#if defined(__CUDA_ARCH__) && !defined(TTMPC_OBCA_REC_REDUNDANT)
+  if (MODE == 2) {  // the device kernels run the recursion from the recursion blocks in shared memory
+    direction_rec(c);
+    return;
+  }
+#endif
   Dir dq;  // the pairs' share: per-lane partial step limits and grad(phi)'d
   dq.a_pr = dq.a_du = 1.0;
   dq.gphi_d = 0.0;
