@@ -144,6 +144,7 @@ def nmpc_preset(horizon: int = 30, dt: float = 0.05, max_iter: int = 2000) -> Co
 
 
 OBCA_NO_RECOVERY = 1  # TTMPC_OBCA_NO_RECOVERY
+OBCA_GEOMETRIC_START = 2  # TTMPC_OBCA_GEOMETRIC_START (opt-in: not the reference's starting point for the OBCA duals)
 
 
 class Obstacles(ctypes.Structure):
@@ -162,7 +163,7 @@ class Obstacles(ctypes.Structure):
 
     @classmethod
     def from_list(cls, obstacle_list, W1: float = 3.05, W2: float = 2.95, d_min: float = 0.2,
-                  recover: bool = True) -> "Obstacles":
+                  recover: bool = True, geometric_start: bool = False) -> "Obstacles":
         """``obstacle_list``: dicts with ``center`` / ``width`` / ``height`` (get_obstacles.py:5-33) or 4-tuples."""
         if not 1 <= len(obstacle_list) <= MAX_OBSTACLES:
             raise ValueError(f"between 1 and {MAX_OBSTACLES} obstacles are supported")
@@ -176,7 +177,7 @@ class Obstacles(ctypes.Structure):
             for j in range(4):
                 o.rect[i][j] = float(row[j])
         o.W1, o.W2, o.d_min = float(W1), float(W2), float(d_min)
-        o.flags = 0 if recover else OBCA_NO_RECOVERY
+        o.flags = (0 if recover else OBCA_NO_RECOVERY) | (OBCA_GEOMETRIC_START if geometric_start else 0)
         return o
 
     def as_list(self):

@@ -614,7 +614,9 @@ __global__ void __launch_bounds__(kObcaThreads, TTMPC_OBCA_MIN_BLOCKS)
       if (lane == 0) b = (long long)atomicAdd(counter, 1ull);
       b = __shfl_sync(0xffffffffu, b, 0);
       if (b < B) {
-        obca::lane_begin(p, pT, o, obca::init_point<0>(c, in, b), L);
+        const bool x0_bad = obca::init_point<0>(c, in, b);
+        if (o.geo_start) obca::restart_point<0>(c);  // TTMPC_OBCA_GEOMETRIC_START, as in solve_problem
+        obca::lane_begin(p, pT, o, x0_bad, L);
         active = true;
       } else {
         exhausted = true;

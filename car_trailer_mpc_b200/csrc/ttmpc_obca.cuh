@@ -130,6 +130,7 @@ struct ObParams {
   double v_push, s_up_push, c2_lo_push, c2_up_push;  // Ipopt's push of the starting point into the interior
   double mu_guess, lam_guess[4];
   int recover;               // recover from an exhausted line search with a fresh start at the current iterate
+  int geo_start;             // TTMPC_OBCA_GEOMETRIC_START: the duals start at the distance problem's multipliers
 };
 
 // a start is called colliding when a body is closer than d_min - kSepTol to an obstacle (the rows themselves tolerate
@@ -142,6 +143,7 @@ inline int build_obparams(const ttmpc_config* c, const ttmpc_obstacles* ob, ObPa
   memset(o, 0, sizeof *o);
   o->P = 2 * ob->count;
   o->recover = (ob->flags & TTMPC_OBCA_NO_RECOVERY) ? 0 : 1;
+  o->geo_start = (ob->flags & TTMPC_OBCA_GEOMETRIC_START) ? 1 : 0;
   for (int i = 0; i < ob->count; i++) {
     const double cx = ob->rect[i][0], cy = ob->rect[i][1], w = ob->rect[i][2], h = ob->rect[i][3];
     if (!(w > 0.0) || !(h > 0.0)) return TTMPC_E_INVAL;
@@ -2423,6 +2425,7 @@ template <int WIDE>
 TT_HD void solve_problem(const Ctx& c, const ProblemIn& in, long long b, Result& res) {
   Lane L;
   const bool x0_bad = init_point<WIDE>(c, in, b);
+  if (c.o->geo_start) restart_point<WIDE>(c);  // stage-local: every warp re-seats the stages it has just written
   if (WIDE) ob_sync_all<WIDE>(c);
   lane_begin(*c.p, *c.pT, *c.o, x0_bad, L);
   for (;;) {

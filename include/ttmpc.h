@@ -176,9 +176,15 @@ double ttmpc_host_pipeline_ms(const ttmpc_handle* h);
  * start at the current primal iterate, up to 3 times per solve.  With this flag the solve takes the
  * shortest trial step instead and reports TTMPC_ST_LINESEARCH after three consecutive failures (round-1 behaviour). */
 #define TTMPC_OBCA_NO_RECOVERY 1
+/* Opt-in, NOT the reference's behaviour: start the OBCA duals at the multipliers of the distance problem between each
+ * body and obstacle for the pose of the starting trajectory (the closed form the recovery uses)
+ * instead of the reference's constants mu = 100, lam = (100,105,110,115) (mpc_control_obs.py:226-237), whose rows start
+ * 5e6 away from feasibility.  Same NLP, same tolerances, same states and inputs at convergence; a third of the
+ * iterations.  Off by default because the reference's starting point is part of what its iterate path looks like. */
+#define TTMPC_OBCA_GEOMETRIC_START 2
 typedef struct ttmpc_obstacles {
   int32_t count; /* 1..TTMPC_MAX_OBSTACLES */
-  int32_t flags; /* 0, or TTMPC_OBCA_NO_RECOVERY */
+  int32_t flags; /* 0, or TTMPC_OBCA_NO_RECOVERY | TTMPC_OBCA_GEOMETRIC_START */
   double rect[TTMPC_MAX_OBSTACLES][4];
   double W1, W2, d_min;
 } ttmpc_obstacles;

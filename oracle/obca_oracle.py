@@ -609,7 +609,7 @@ def _inertia(lu, d, piv):
 
 
 def solve(nlp: ObcaNlp, x_init, ref_states, ref_inputs, tol=1e-8, acc_tol=1e-6, acc_iter=15, max_iter=5000,
-          mu_init=0.1, verbose=False, linear_solver="dense", recover=True, guess=None):
+          mu_init=0.1, verbose=False, linear_solver="dense", recover=True, guess=None, geometric_start=False):
     """Returns dict(states[N+1,6], inputs[N,2], obj, iters, status, kkt=(dual_inf, constr_viol, compl), w)."""
     x_init = np.asarray(x_init, float)
     ref_states = np.asarray(ref_states, float).reshape(nlp.N + 1, 6)
@@ -617,6 +617,8 @@ def solve(nlp: ObcaNlp, x_init, ref_states, ref_inputs, tol=1e-8, acc_tol=1e-6, 
     n, m = nlp.n, nlp.m
     hl, hu = nlp.has_lo, nlp.has_up
     w = nlp.initial_point(x_init, ref_states, ref_inputs, guess)
+    if geometric_start:  # TTMPC_OBCA_GEOMETRIC_START: the duals start at the distance problems' multipliers (not the reference's)
+        w = nlp.restored_point(w, x_init)
     y = np.zeros(m)
     zl = np.where(hl, 1.0, 0.0)
     zu = np.where(hu, 1.0, 0.0)

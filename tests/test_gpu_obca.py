@@ -231,3 +231,51 @@ def test_gpu_reaches_the_slsqp_minimiser_of_the_obstacle_aware_nlp(name):
     assert np.abs(r["u0"][0] - g[name + "/inputs"][0]).max() <= U0_ABS_TOL
     assert np.abs(xs - g[name + "/states"]).max() <= 1e-5 and np.abs(us - g[name + "/inputs"]).max() <= 1e-5
     assert abs(r["obj"][0] - float(g[name + "/obj"])) <= 5e-6 * abs(r["obj"][0])
+
+
+@pytest.mark.parametrize("flavour", OBCA_FLAVOURS)
+def test_geometric_start_of_the_duals(flavour, monkeypatch):
+    """TTMPC_OBCA_GEOMETRIC_START (opt-in, not the reference's starting point): on the golden cases at the reference's
+    size every kernel converges in fewer iterations, to the golden solution or -- the NLP is not convex -- to another
+    KKT point that is at least as good (lower objective, dynamics defect and true clearance checked); on a seeded batch
+    the iteration count drops by more than half with no loss of converged instances."""
+    import torch
+    kernel = force_obca_kernel(monkeypatch, flavour)
+    n_conv = 0
+    for c in FULL + CASES:
+        cfg, _ = case_problem(c)
+        cfg.max_iter = 400
+        rects = [tuple(r) for r in c["rects"]]
+        sv = solver(cfg)
+        ref = sv.solve_obca(Obstacles.from_list(rects), c["x_init"][None], c["ref_states"][None], c["ref_inputs"][None])
+        geo = sv.solve_obca(Obstacles.from_list(rects, geometric_start=True), c["x_init"][None], c["ref_states"][None],
+                            c["ref_inputs"][None])
+        assert sv.kernel_launches()[kernel] == 2
+        if geo["status"][0] != 0:
+            # not uniformly better: the case with a twelfth obstacle across the path (active rows everywhere) heads for a
+            # cheaper region from this start and jams in the line search -- the one known exception among the goldens
+            assert c["name"] == "n50_k60_12obs_blocked" and geo["status"][0] == 3
+            continue
+        n_conv += 1
+        assert geo["iters"][0] < ref["iters"][0]
+        xs, us = split_z(geo["z"][0], cfg.horizon)
+        same = np.abs(xs - c["states"]).max() <= Z_TOL and np.abs(us - c["inputs"]).max() <= Z_TOL
+        assert same or geo["obj"][0] <= c["obj"] * (1 + 1e-9)
+        assert np.abs(pb.dynamics_defect(cfg, xs[None], us[None])).max() <= 1e-6
+        assert geometry.clearance(xs, rects).min() >= 0.2 - 1e-4
+    assert n_conv >= len(FULL + CASES) - 1
+    cfg = tracking_preset(30)
+    cfg.max_iter = 300
+    S, U, ks, x0 = scenarios(cfg, 64, seed=11)
+    dev = torch.device("cuda:0")
+    sv = solver(cfg)
+    args = (torch.from_numpy(x0).to(dev), torch.from_numpy(ks).to(dev), torch.from_numpy(S).to(dev), torch.from_numpy(U).to(dev))
+    ref = sv.solve_obca_shared(Obstacles.from_list(parking_lot_obstacles()), *args)
+    geo = sv.solve_obca_shared(Obstacles.from_list(parking_lot_obstacles(), geometric_start=True), *args)
+    rs, gs = ref["status"].cpu().numpy(), geo["status"].cpu().numpy()
+    assert (gs <= 1).sum() >= (rs <= 1).sum()
+    assert geo["iters"].float().mean().item() < 0.5 * ref["iters"].float().mean().item()
+    both = (rs == 0) & (gs == 0)
+    dz = (geo["z"] - ref["z"]).abs().amax(dim=1).cpu().numpy()
+    better = (geo["obj"] <= ref["obj"] * (1 + 1e-9)).cpu().numpy()
+    assert ((dz <= Z_TOL) | better)[both].mean() >= 0.9  # same KKT point, or a better one, on at least nine out of ten

@@ -316,3 +316,24 @@ def test_oracle_and_kernel_core_reach_the_slsqp_minimiser(name):
         assert np.abs(U[0] - g[name + "/inputs"][0]).max() <= U0_ABS_TOL
         assert np.abs(X - g[name + "/states"]).max() <= 1e-5 and np.abs(U - g[name + "/inputs"]).max() <= 1e-5
         assert abs(J - float(g[name + "/obj"])) <= SLSQP_OBJ_REL_TOL * abs(J)
+
+
+def test_geometric_start_of_the_duals_same_solution_fewer_iterations():
+    """TTMPC_OBCA_GEOMETRIC_START (opt-in; NOT the reference's starting point): the OBCA duals start at the multipliers
+    of the distance problems for the pose of the starting trajectory instead of mu = 100, lam = (100..115).  Oracle and
+    host build of the kernel core implement the same rule, reach the golden solution of the reference start on a case
+    away from the passage, and need a fraction of the iterations."""
+    c = next(x for x in CASES if x["name"] == "n12_k200_blocked3")
+    cfg, obs = case_problem(c)
+    obs_geo = Obstacles.from_list([tuple(r) for r in c["rects"]], geometric_start=True)
+    nlp = make_nlp(cfg, c["rects"])
+    ref = ob.solve(nlp, c["x_init"], c["ref_states"], c["ref_inputs"])
+    geo = ob.solve(nlp, c["x_init"], c["ref_states"], c["ref_inputs"], geometric_start=True)
+    assert ref["status"] == 0 and geo["status"] == 0 and geo["iters"] < ref["iters"]
+    assert np.abs(geo["states"] - c["states"]).max() <= Z_TOL and np.abs(geo["inputs"] - c["inputs"]).max() <= Z_TOL
+    e_ref = emu.obca_solve_batch(cfg, obs, c["x_init"][None], c["ref_states"][None], c["ref_inputs"][None])
+    e_geo = emu.obca_solve_batch(cfg, obs_geo, c["x_init"][None], c["ref_states"][None], c["ref_inputs"][None])
+    assert e_geo["status"][0] == 0 and e_geo["iters"][0] < e_ref["iters"][0]
+    xs, us = split_z(e_geo["z"][0], cfg.horizon)
+    assert np.abs(xs - geo["states"]).max() <= Z_TOL and np.abs(us - geo["inputs"]).max() <= Z_TOL
+    assert abs(e_geo["obj"][0] - c["obj"]) <= OBJ_REL_TOL * abs(c["obj"])

@@ -16,6 +16,7 @@ ap.add_argument("B", type=int); ap.add_argument("N", type=int); ap.add_argument(
 ap.add_argument("--check-emu", type=int, default=0); ap.add_argument("--json", default=None)
 ap.add_argument("--steps", type=int, default=1); ap.add_argument("--max-iter", type=int, default=300)
 ap.add_argument("--kmax", type=int, default=400, help="window starts are uniform in 0..kmax (beyond k = 345 the shipped trajectory rides d_min exactly: perturbed starts there are infeasible)")
+ap.add_argument("--geo-start", action="store_true", help="TTMPC_OBCA_GEOMETRIC_START (opt-in, not the reference's starting point)")
 ap.add_argument("--no-recovery", action="store_true", help="TTMPC_OBCA_NO_RECOVERY: the round-1 behaviour (no recovery from an exhausted line search)")
 ap.add_argument("--cpu-sample", type=int, default=0, help="also time the host build of the same solver core on the first M problems (one thread)")
 a = ap.parse_args()
@@ -26,7 +27,7 @@ ks = rng.integers(0, a.kmax + 1, a.B).astype(np.int32)
 lb = np.array(cfg.x_lb[:]); ub = np.array(cfg.x_ub[:])
 x0 = S[np.minimum(ks, 400)] + rng.normal(0, a.sigma, (a.B, 6))
 x0[:, 2:] = np.clip(x0[:, 2:], lb[2:] + 1e-3, ub[2:] - 1e-3)
-obs = Obstacles.from_list(parking_lot_obstacles(), recover=not a.no_recovery)
+obs = Obstacles.from_list(parking_lot_obstacles(), recover=not a.no_recovery, geometric_start=a.geo_start)
 dev = torch.device("cuda:0")
 s = BatchSolver(cfg, 0)
 tx = torch.from_numpy(x0).to(dev); tk = torch.from_numpy(ks).to(dev); tS = torch.from_numpy(S).to(dev); tU = torch.from_numpy(U).to(dev)
