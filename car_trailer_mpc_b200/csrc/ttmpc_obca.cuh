@@ -493,6 +493,9 @@ struct Wide {
   // a stage is handed from one to the other through flag[k] (shared memory) = +-epoch, so the recursion trails the pair
   // work (factor) or leads it (direction) by a few stages instead of waiting for all of it at a CTA barrier.
   int dn = 0, di = 0;     // dn > 0: the stages of a MODE-1 sweep are dealt to dn warps, this warp being number di
+  int klo = 0, khi = -1;  // ... and only the stages klo .. khi (khi < 0: N) are dealt: stage k to warp (k - klo) mod dn.
+                          // The pipelined sweeps give warp 0, which runs the (short) recursion, a few stages of pair work
+                          // of its own at the far end of the sweep: klo .. khi = its contiguous share with dn = 1
   int* flag = nullptr;    // [N+1]
   int* epoch = nullptr;   // this warp's sweep counter (the same in every warp: control flow is CTA-uniform)
   // Cluster-per-problem kernel (ttmpc_obca_cluster_kernel): nc > 1 CTAs of a thread-block cluster work on one problem.
@@ -508,6 +511,12 @@ struct Wide {
 };
 TT_HD int deal_n(const Wide& w) { return w.dn > 0 ? w.dn : w.nw; }
 TT_HD int deal_i(const Wide& w) { return w.dn > 0 ? w.di : w.wid; }
+TT_HD int deal_hi(const Wide& w, int N) { return w.khi >= 0 ? w.khi : N; }
+// the last (highest) stage of this warp's share, walking down in steps of deal_n to klo
+TT_HD int deal_top(const Wide& w, int N) {
+  const int n = deal_n(w), hi = deal_hi(w, N);
+  return hi - ((hi - w.klo - deal_i(w)) % n + n) % n;
+}
 struct Ctx {
   Wide wd;
   const Params* p;
@@ -1266,7 +1275,7 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
     for (int w_ = 0; w_ < c.wd.nw; w_++)
       if (c.wd.part[w_ * kPart] == 0.0) return false;
   // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
-  for (int k = (MODE == 1) ? N - ((N - deal_i(c.wd)) % deal_n(c.wd) + deal_n(c.wd)) % deal_n(c.wd) : N, kstep = (MODE == 1) ? deal_n(c.wd) : 1; k >= 0; k -= kstep) {
+  for (int k = (MODE == 1) ? deal_top(c.wd, N) : N, kstep = (MODE == 1) ? deal_n(c.wd) : 1, kend = (MODE == 1) ? c.wd.klo : 0; k >= kend; k -= kstep) {
     double* ps = c.stage(k);
     double* pr = c.rstage(k);
     const Params& p = (k == N) ? *c.pT : p0;  // the terminal stage may have its own bounds and weight
@@ -1741,7 +1750,7 @@ TT_HD void direction(const Ctx& c, double mu, double tau, double delta, Dir& di)
   double dx[NX];
   for (int i = 0; i < NX; i++) dx[i] = 0.0;
   // the stages of this warp (k = wid mod nw) when the stages are dealt out, every stage otherwise -- no modulo per stage
-  for (int k = (MODE == 1) ? deal_i(c.wd) : 0, kstep = (MODE == 1) ? deal_n(c.wd) : 1; k <= N; k += kstep) {
+  for (int k = (MODE == 1) ? c.wd.klo + deal_i(c.wd) : 0, kstep = (MODE == 1) ? deal_n(c.wd) : 1, kend = (MODE == 1) ? deal_hi(c.wd, N) : N; k <= kend; k += kstep) {
     double* ps = c.stage(k);
     double* pr = c.rstage(k);
     if (MODE == 1) ob_await(c, k);  // pipelined: the recursion on warp 0 has stored this stage's dx, du
@@ -2018,6 +2027,20 @@ TT_HD void ob_cta_sync() { __syncthreads(); }
 TT_HD void ob_cta_sync() {}
 #endif
 
+// stages of pair work that warp 0 takes in the pipelined factor / direction sweeps of the CTA-per-problem kernel besides
+// its recursion.  Measured (N = 50, -DTTMPC_OBCA_OWN_STAGES=5: a tenth of the stages, which would balance 8 warps if the
+// recursion cost what its cycle count says): 8 192 problems 1.549 s against 1.533 s with none, one problem 20.0 against
+// 19.2 ms -- the recursion no longer overlaps the pair work of the other warps, and that costs more than the eighth pair
+// warp gains.  Default: none (experiment switch).
+TT_HD int pipeline_own_stages(int N) {
+  (void)N;
+#ifdef TTMPC_OBCA_OWN_STAGES
+  return TTMPC_OBCA_OWN_STAGES;
+#else
+  return 0;
+#endif
+}
+
 template <int WIDE>
 TT_HD void run_update_stats(const Ctx& c, bool do_update, double alpha, double alpha_du, double mu_step, double delta_step,
                             Stats& st) {
@@ -2082,15 +2105,20 @@ TT_HD bool run_factor(const Ctx& c, double mu, double delta) {
     return c.wd.bcast[0] != 0.0;
   }
 #ifndef TTMPC_OBCA_NO_PIPELINE
-  {  // pipelined: warps 1.. condense the pairs, warp 0 trails them with the recursion
+  {  // pipelined: warps 1.. condense the pairs from stage N down, warp 0 trails them with the recursion -- after it has
+     // condensed the pairs of the FIRST few stages itself (the ones the recursion needs last): its recursion is a tenth
+     // of a warp's pair work, and seven pair warps instead of eight was a tenth of the sweep
     ++*c.wd.epoch;
     Ctx cw = c;
-    cw.wd.dn = c.wd.nw - 1, cw.wd.di = c.wd.wid - 1;
+    const int own = pipeline_own_stages(c.p->N);
+    if (c.wd.wid == 0)
+      cw.wd.dn = 1, cw.wd.di = 0, cw.wd.klo = 0, cw.wd.khi = own - 1;
+    else
+      cw.wd.dn = c.wd.nw - 1, cw.wd.di = c.wd.wid - 1, cw.wd.klo = own, cw.wd.khi = c.p->N;
+    if (c.wd.wid != 0 || own > 0) factor<1>(cw, mu, delta);  // one copy of the pair sweep for all warps
     if (c.wd.wid == 0) {
       const bool ok = factor<2>(cw, mu, delta);
       if (ob_lane0()) c.wd.bcast[0] = ok ? 1.0 : 0.0;
-    } else {
-      factor<1>(cw, mu, delta);
     }
     ob_cta_sync();
     return c.wd.bcast[0] != 0.0;
@@ -2126,19 +2154,17 @@ TT_HD void run_direction(const Ctx& c, double mu, double tau, double delta, Dir&
   ob_sync_all<WIDE>(c);
   PartView pv{c.wd.part, c.wd.nw};
 #ifndef TTMPC_OBCA_NO_PIPELINE
-  if (WIDE == 1) {  // pipelined: warp 0 leads with the recursion, warps 1.. follow with the pairs
+  if (WIDE == 1) {  // pipelined: warp 0 leads with the recursion, warps 1.. follow with the pairs from stage 0 up; warp 0
+                    // then takes the pairs of the LAST few stages itself (see run_factor)
     ++*c.wd.epoch;
     Ctx cw = c;
-    cw.wd.dn = c.wd.nw - 1, cw.wd.di = c.wd.wid - 1;
-    if (c.wd.wid == 0) {
-      direction<2>(cw, mu, tau, delta, dummy);
-      if (ob_lane0()) {  // warp 0 has no share of the step limits
-        double* pt = c.wd.part;
-        pt[0] = pt[1] = pt[3] = pt[4] = 1.0, pt[2] = pt[5] = 0.0;
-      }
-    } else {
-      direction<1>(cw, mu, tau, delta, dummy);
-    }
+    const int N_ = c.p->N, own = pipeline_own_stages(N_);
+    if (c.wd.wid == 0)
+      cw.wd.dn = 1, cw.wd.di = 0, cw.wd.klo = N_ - own + 1, cw.wd.khi = N_;
+    else
+      cw.wd.dn = c.wd.nw - 1, cw.wd.di = c.wd.wid - 1, cw.wd.klo = 0, cw.wd.khi = N_ - own;
+    if (c.wd.wid == 0) direction<2>(cw, mu, tau, delta, dummy);
+    direction<1>(cw, mu, tau, delta, dummy);  // (warp 0 with own == 0: an empty share, neutral step limits)
     ob_cta_sync();
   } else
 #endif
