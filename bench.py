@@ -109,7 +109,8 @@ class ClockSampler:
                 ids = [v for v in vis.split(",") if v.strip().isdigit()]
                 h = nv.nvmlDeviceGetHandleByIndex(int(ids[self.index]) if self.index < len(ids) else self.index)
             self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
-            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))  # first sample before the timed region
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))  # first calls before the timed region
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
             self.sm.clear()
             self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
             self.thread.start()
@@ -122,6 +123,12 @@ class ClockSampler:
             self.proc.stdout.readline()  # first sample = process is up; the timed region starts after this
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Forget the samples taken so far (NVML path; the nvidia-smi fallback reports everything it printed)."""
+        if self.thread is not None:
+            self.sm = []
+            self.reasons = set()
 
     def finish(self) -> dict:
         if self.thread is not None:
@@ -213,9 +220,8 @@ def main() -> None:
     ap.add_argument("--horizon", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--settle", type=float, default=1.0,
-                    help="seconds of untimed solves before the W warm-up steps: a GPU that idled through this process's "
-                         "set-up changes its power state tens of milliseconds into the first load, and that stall landed "
-                         "in the second timed step of two out of six runs (profiles/r2_bench_1gpu_outlier_step.json)")
+                    help="seconds of untimed solves before the W warm-up steps (clocks and power state settle under the very "
+                         "load that is timed)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the N = 100 and OBCA legs of the secondary block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -310,13 +316,17 @@ def main() -> None:
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
+        # The warm-up holds its result across the next call exactly like the timed loop does (`r = fn()`): the solve
+        # returns freshly allocated output tensors, so the loop needs TWO output sets in torch's caching allocator, and
+        # when the second one was first asked for inside the timed region (step index 1) its cudaMalloc -- a device
+        # synchronisation of 10..100 ms -- landed there (profiles/r2_bench_1gpu_outlier_step.json).
+        r = None
         for _ in range(warmup):
-            fn()
+            r = fn()
         barrier()
         l_before = solver.launch_count()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         ev[0].record()
-        r = None
         for i in range(steps):
             r = fn()
             ev[i + 1].record()
@@ -325,12 +335,14 @@ def main() -> None:
         total = ev[0].elapsed_time(ev[steps])
         return total, per, r, solver.launch_count() - l_before
 
-    t_settle = time.time() + max(0.0, args.settle)
-    while time.time() < t_settle:  # untimed: lets clocks and power state settle under this very load (see --settle)
-        step_resident()
-        torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.start()  # before the settle phase: the sampler's own start-up (first NVML calls) is not inside the timed region
+    t_settle = time.time() + max(0.0, args.settle)
+    r_keep = None
+    while time.time() < t_settle:  # untimed: lets clocks and power state settle under this very load (see --settle)
+        r_keep = step_resident()
+        torch.cuda.synchronize()
+    sampler.mark()   # report the samples from here on: warm-up steps + timed region
     total_ms, per_ms, r, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.finish()
     lanes_headline = solver.last_solve_lanes()
@@ -390,8 +402,9 @@ def main() -> None:
     secondary = {}
     if rank == 0:
         def quick(solver_, args_, steps=5, **kw):
-            for _ in range(2):
-                solver_.solve(*args_, **kw)
+            rr = None
+            for _ in range(2):  # results held across the next call, as in the timed loop (see timed())
+                rr = solver_.solve(*args_, **kw)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
