@@ -58,9 +58,8 @@ def algorithmic_bytes_per_solve(N: int) -> int:
 
 class ClockSampler:
     """Samples SM clocks / throttle reasons of one GPU while the timed region runs.  In-process NVML calls from a thread
-    (a few microseconds each, every 10 ms); a looping `nvidia-smi -lms` process -- the first implementation -- was seen
-    to stall one step of a 20-step timed region by ~50 ms on some boxes (profiles/r2_bench_1gpu_final.json keeps such a
-    run), which is the measurement disturbing the measured.  Falls back to that process only if NVML cannot be loaded."""
+    (a few microseconds each, every 10 ms), started before the untimed settle phase; falls back to one long-lived
+    `nvidia-smi -lms 100` process if NVML cannot be loaded."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
