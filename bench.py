@@ -336,11 +336,10 @@ def main() -> None:
 
     sampler = ClockSampler(local_rank)
     sampler.start()  # before the settle phase: the sampler's own start-up (first NVML calls) is not inside the timed region
-    t_settle = time.time() + max(0.0, args.settle)
     r_keep = None
-    while time.time() < t_settle:  # untimed: lets clocks and power state settle under this very load (see --settle)
-        r_keep = step_resident()
-        torch.cuda.synchronize()
+    for _ in range(max(0, int(round(args.settle * 150.0)))):  # untimed, ~6.5 ms each: clocks and power state settle under this
+        r_keep = step_resident()                              # very load; a COUNT, not a time: every rank runs the same collectives
+    torch.cuda.synchronize()
     sampler.mark()   # report the samples from here on: warm-up steps + timed region
     total_ms, per_ms, r, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.finish()
