@@ -36,7 +36,10 @@ class TrajectoryOptimization:
     TERMINAL_WEIGHT = 100.0  # trajectory_optimization.py:181
     TERMINAL_BOX = 1e-2      # trajectory_optimization.py:170-171
 
-    def __init__(self, dynamics, params, Q, R, state_bound, input_bound, obstacle_list, device: int = 0, waypoints=None):
+    def __init__(self, dynamics, params, Q, R, state_bound, input_bound, obstacle_list, device: int = 0, waypoints=None,
+                 geometric_start: bool = False):
+        """``geometric_start`` (not in the reference, off by default): TTMPC_OBCA_GEOMETRIC_START, the OBCA duals start at the
+        distance problems' multipliers for the poses of the initial trajectory (see mpc_control_obs.py of this package)."""
         self._dynamics = dynamics
         self._horizon = int(params["horizon"])
         for key in ("W1", "W2"):
@@ -44,7 +47,8 @@ class TrajectoryOptimization:
                 raise KeyError(f"params['{key}'] missing (trajectory_animation.py:49-53)")
         self._cfg = config_from_reference_args(dynamics, params, Q, R, state_bound, input_bound, planner_preset(self._horizon))
         self.obstacle_list = list(obstacle_list)
-        self._obstacles = Obstacles.from_list(self.obstacle_list, W1=float(params["W1"]), W2=float(params["W2"]))
+        self._obstacles = Obstacles.from_list(self.obstacle_list, W1=float(params["W1"]), W2=float(params["W2"]),
+                                              geometric_start=geometric_start)
         self._solver = BatchSolver(self._cfg, device)
         self._waypoints = waypoints
         self.last_status = self.last_iterations = self.last_objective = None

@@ -8,6 +8,7 @@ import numpy as np, torch
 from car_trailer_mpc_b200 import BatchSolver, planner_preset, Obstacles, parking_lot_obstacles
 from car_trailer_mpc_b200 import problem as pb
 ap = argparse.ArgumentParser(); ap.add_argument("B", type=int, nargs="?", default=1); ap.add_argument("--json", default=None)
+ap.add_argument("--geo-start", action="store_true", help="TTMPC_OBCA_GEOMETRIC_START (opt-in, not the reference's starting duals)")
 ap.add_argument("--cpu", action="store_true", help="also time the host build of the same core on one problem (one thread)")
 a = ap.parse_args()
 N = 200
@@ -18,7 +19,7 @@ zg = np.zeros(8 * N + 6)
 for k in range(N + 1): zg[8 * k:8 * k + 4] = S[k, :4]
 rng = np.random.default_rng(0)
 X0 = x0[None] + np.concatenate([np.zeros((1, 6)), rng.normal(0, 1e-3, (a.B - 1, 6))])
-obs = Obstacles.from_list(parking_lot_obstacles())
+obs = Obstacles.from_list(parking_lot_obstacles(), geometric_start=a.geo_start)
 dev = torch.device("cuda:0")
 s = BatchSolver(cfg, 0)
 tx, tz = torch.from_numpy(X0).to(dev), torch.from_numpy(np.tile(zg, (a.B, 1))).to(dev)
