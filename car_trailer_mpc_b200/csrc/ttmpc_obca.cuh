@@ -1084,21 +1084,14 @@ __device__ __noinline__ bool factor_rec_lanes(const Ctx& c) {
     for (int w_ = 0; w_ < c.wd.nw; w_++)
       if (c.wd.part[w_ * kPart] == 0.0) return false;
   if (!ob_await(c, N)) return false;  // pipelined: the stage's warp has left its blocks (or found one not PD)
-  double ia[9], icd[NX], isg[4], igi, ihx[NX];
-  OB_REC_LOAD(ia, icd, isg, igi, ihx, r0 + (size_t)N * kRecRows);
   for (int k = N; k >= 0; k--) {
     double* const pr = r0 + (size_t)k * kRecRows;
     const bool has_x = k >= 1;
-    // the next stage's block is requested before this stage's arithmetic (one warp: nothing else hides the latency).
-    // Pipelined kernel: the recursion trails the pair warps, so the block is normally there; if it is not, wait here.
-    double na[9], ncd[NX], nsg[4], ngi, nhx[NX];
-    {
-      const int kn = k > 0 ? k - 1 : 0;
-      if (flag && k > 0) {
-        if (!ob_await(c, kn)) return false;
-      }
-      OB_REC_LOAD(na, ncd, nsg, ngi, nhx, r0 + (size_t)kn * kRecRows);
+    if (flag && k < N) {  // pipelined: the stage's warp has left its blocks (or found one not PD); stage N: awaited above
+      if (!ob_await(c, k)) return false;
     }
+    double ia[9], icd[NX], isg[4], igi, ihx[NX];  // (loaded here, not a stage ahead: see direction_rec)
+    OB_REC_LOAD(ia, icd, isg, igi, ihx, pr);
     const double gx_i = igi;
     if (k == N) {
       TT_UNROLL
@@ -1163,12 +1156,6 @@ __device__ __noinline__ bool factor_rec_lanes(const Ctx& c) {
       for (int j = 0; j < NX; j++)
         if (j >= li) pr[ohx[j] - rHX + rP] = Prow[j];
     }
-    TT_UNROLL
-    for (int i = 0; i < 9; i++) ia[i] = na[i];
-    TT_UNROLL
-    for (int j = 0; j < NX; j++) icd[j] = ncd[j], ihx[j] = nhx[j];
-    isg[0] = nsg[0], isg[1] = nsg[1], isg[2] = nsg[2], isg[3] = nsg[3];
-    igi = ngi;
   }
   __syncwarp();
   return true;
@@ -1188,28 +1175,21 @@ __device__ __noinline__ void direction_rec(const Ctx& c) {
   double dx[NX];
   TT_UNROLL
   for (int i = 0; i < NX; i++) dx[i] = 0.0;
-  // gains, A and defect of the current stage; the next stage's are requested before this stage's arithmetic.  Plain
-  // arrays copied element by element: a struct assignment kept both copies in local memory (measured 3x slower).
-  double K[2 * NX], kff[2], a[9], cd[NX];
-  TT_UNROLL
-  for (int i = 0; i < 2 * NX; i++) K[i] = r0[rK + i];
-  kff[0] = r0[rKFF], kff[1] = r0[rKFF + 1];
-  TT_UNROLL
-  for (int i = 0; i < 9; i++) a[i] = r0[rA + i];
-  TT_UNROLL
-  for (int j = 0; j < NX; j++) cd[j] = r0[rCD + j];
+  // gains, A and defect of the stage straight from the recursion block at the top of its body.  (Requesting the next
+  // stage's block a stage ahead was measured slower on this single warp: the 29 x 2 register moves of the double buffer
+  // cost more issue slots than the ~40 cycles of LDS latency they hid; a struct for the buffer ended up in local memory.)
   for (int k = 0; k <= N; k++) {
     double* const ps = s0 + (size_t)k * kStageDoubles;
     const bool has_x = k >= 1, has_u = k < N;
-    const double* const pn = r0 + (size_t)((k + 1 < N) ? k + 1 : k) * kRecRows;  // (the last two stages: a harmless re-read)
-    double nK[2 * NX], nkff[2], na[9], ncd[NX];
+    const double* const pr = r0 + (size_t)(has_u ? k : k - (N > 0 ? 1 : 0)) * kRecRows;  // (stage N has no gains: re-read N-1)
+    double K[2 * NX], kff[2], a[9], cd[NX];
     TT_UNROLL
-    for (int i = 0; i < 2 * NX; i++) nK[i] = pn[rK + i];
-    nkff[0] = pn[rKFF], nkff[1] = pn[rKFF + 1];
+    for (int i = 0; i < 2 * NX; i++) K[i] = pr[rK + i];
+    kff[0] = pr[rKFF], kff[1] = pr[rKFF + 1];
     TT_UNROLL
-    for (int i = 0; i < 9; i++) na[i] = pn[rA + i];
+    for (int i = 0; i < 9; i++) a[i] = pr[rA + i];
     TT_UNROLL
-    for (int j = 0; j < NX; j++) ncd[j] = pn[rCD + j];
+    for (int j = 0; j < NX; j++) cd[j] = pr[rCD + j];
     double du[NU] = {0.0, 0.0};
     if (has_u) {
       TT_UNROLL
@@ -1244,13 +1224,6 @@ __device__ __noinline__ void direction_rec(const Ctx& c) {
       TT_UNROLL
       for (int i = 0; i < NX; i++) dx[i] = nd[i];
     }
-    TT_UNROLL
-    for (int i = 0; i < 2 * NX; i++) K[i] = nK[i];
-    kff[0] = nkff[0], kff[1] = nkff[1];
-    TT_UNROLL
-    for (int i = 0; i < 9; i++) a[i] = na[i];
-    TT_UNROLL
-    for (int j = 0; j < NX; j++) cd[j] = ncd[j];
   }
   __syncwarp();
 }
