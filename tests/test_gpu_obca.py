@@ -279,3 +279,36 @@ def test_geometric_start_of_the_duals(flavour, monkeypatch):
     dz = (geo["z"] - ref["z"]).abs().amax(dim=1).cpu().numpy()
     better = (geo["obj"] <= ref["obj"] * (1 + 1e-9)).cpu().numpy()
     assert ((dz <= Z_TOL) | better)[both].mean() >= 0.9  # same KKT point, or a better one, on at least nine out of ten
+
+
+@pytest.mark.parametrize("size", ["2", "4", "16"])
+def test_cluster_sizes(size, monkeypatch):
+    """The cluster-per-problem kernel at the other cluster sizes (the flavour tests force 8; 16 is the non-portable maximum
+    and falls back to 8 on a device that does not take it): a golden case at the reference's size, and a small batch that
+    makes the persistent clusters pull several problems each from the queue."""
+    import torch
+    c = next(x for x in FULL if x["name"] == "n50_k200_11obs")
+    kernel = force_obca_kernel(monkeypatch, "cluster_per_problem", cluster=size)
+    cfg, obs = case_problem(c)
+    cfg.max_iter = 400
+    sv = solver(cfg)
+    r = sv.solve_obca(obs, c["x_init"][None], c["ref_states"][None], c["ref_inputs"][None])
+    assert sv.kernel_launches()[kernel] == 1
+    assert r["status"][0] == 0
+    xs, us = split_z(r["z"][0], cfg.horizon)
+    assert np.abs(xs - c["states"]).max() <= Z_TOL and np.abs(us - c["inputs"]).max() <= Z_TOL
+    assert abs(r["obj"][0] - c["obj"]) <= OBJ_REL_TOL * abs(c["obj"])
+    # 24 problems, horizon 20: more problems than clusters fit at sizes 8 / 16 -- same results as one CTA per problem
+    cfg = tracking_preset(20)
+    cfg.max_iter = 300
+    S, U, ks, x0 = scenarios(cfg, 24, seed=5)
+    dev = torch.device("cuda:0")
+    args = (torch.from_numpy(x0).to(dev), torch.from_numpy(ks).to(dev), torch.from_numpy(S).to(dev), torch.from_numpy(U).to(dev))
+    sv = solver(cfg)
+    a = sv.solve_obca_shared(Obstacles.from_list(parking_lot_obstacles()), *args)
+    assert sv.kernel_launches()[kernel] == 1
+    monkeypatch.setenv("TTMPC_OBCA_CLUSTER", "0")
+    b = sv.solve_obca_shared(Obstacles.from_list(parking_lot_obstacles()), *args)
+    assert sv.kernel_launches()["ttmpc_obca_wide_kernel"] == 1
+    assert torch.equal(a["status"], b["status"]) and torch.equal(a["iters"], b["iters"])  # same arithmetic, same order
+    assert torch.equal(a["z"], b["z"])
