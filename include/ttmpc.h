@@ -192,7 +192,10 @@ typedef struct ttmpc_obstacles {
 /* Solve B NLPs of MPCTrackingControlObs.solve (mpc_control_obs.py:282-322): tracking cost and dynamics of
  * ttmpc_solve_batch plus, for every stage, obstacle and body, the OBCA dual variables mu, lam >= 0 and the three
  * collision row groups of _collision_constraints (mpc_control_obs.py:65-139).  Always a cold start at the reference
- * window with mu = 100, lam = (100,105,110,115) (_get_initial_guess, :216-239).  Outputs as ttmpc_solve_batch; z_out
+ * window with mu = 100, lam = (100,105,110,115) (_get_initial_guess, :216-239) unless TTMPC_OBCA_GEOMETRIC_START is set.
+ * Three kernels, chosen per call (ttmpc_kernel_name): one thread-block cluster per problem while every problem gets
+ * its own cluster (the single solve of the shim: 8.7 ms at horizon 50 with 11 obstacles), one CTA per problem otherwise;
+ * one warp per problem only on request (environment).  Outputs as ttmpc_solve_batch; z_out
  * holds the states and inputs only ([B][8N+6]) -- what _split_decision_variables (:241-281) hands back to the
  * caller; the OBCA duals are internal.  The second form windows one shared trajectory (simulation.py:485-499). */
 int ttmpc_obca_solve_batch(ttmpc_handle* h, const ttmpc_obstacles* obstacles, int64_t B, const double* x_init,
@@ -212,7 +215,8 @@ int ttmpc_obca_solve_batch_shared(ttmpc_handle* h, const ttmpc_obstacles* obstac
  *   final-state constraint |x_N - goal| <= terminal_box                                                 (:168-173),
  *   starting point z_guess [B][8N+6] = the caller's initial trajectory (states and inputs in the z layout; :227-274
  *   builds it from the Hybrid-A* waypoints, :208-225 as a straight line) or NULL = every state at the goal, zero inputs;
- *   the OBCA duals start at the reference's constants either way.
+ *   the OBCA duals start at the reference's constants either way (or, with TTMPC_OBCA_GEOMETRIC_START, at the distance
+ *   problems' multipliers for the poses of that trajectory).
  * goal: host pointer to 6 doubles (configuration, like the obstacle set).  The final-state constraint is held as bounds
  * of the terminal stage (the reference's range row has a slack that equals x_N - goal).  Outputs as
  * ttmpc_obca_solve_batch.  One problem runs on one CTA (N = 200, 11 obstacles: 37 k variables). */
