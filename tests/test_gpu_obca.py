@@ -190,6 +190,40 @@ def test_closed_loop_with_the_obstacle_aware_controller():
     assert geometry.clearance(a.states, LOT).min() >= 0.2
 
 
+def test_closed_loop_with_the_geometric_start():
+    """The same 2 s of the manoeuvre with ``MPCTrackingControlObs(..., geometric_start=True)`` (opt-in, not the reference's
+    dual guesses): no solve crawls or fails, every solve takes a fraction of the iterations, and -- the collision rows being
+    inactive out here -- the loop equals the plain controller's."""
+    from car_trailer_mpc_b200 import MPCTrackingControl, MPCTrackingControlObs, TruckTrailerModel
+    from car_trailer_mpc_b200 import closed_loop as cl
+    S, U = pb.load_reference_trajectory()
+    N = 20
+    params = {"M": 0.15, "L1": 7.05, "L2": 12.45, "W1": 3.05, "W2": 2.95, "dt": 0.05, "horizon": N}
+    pi = np.pi
+    sb = {"lb": [-np.inf, -np.inf, -pi, -pi / 3, -pi / 4, -10.0], "ub": [np.inf, np.inf, pi, pi / 3, pi / 4, 10.0]}
+    ib = {"lb": [-5.0, -pi / 2], "ub": [5.0, pi / 2]}
+    args = (TruckTrailerModel(params), params, np.eye(6), 10.0 * np.eye(2), sb, ib)
+    geo_ctl = MPCTrackingControlObs(*args, obstacle_list=parking_lot_obstacles(), geometric_start=True)
+    plain_ctl = MPCTrackingControl(*args)
+    x0 = S[0] + np.array([0.3, -0.2, 0.02, 0.0, 0.0, 0.0])
+    iters = []
+    solve = geo_ctl.solve
+
+    def counting_solve(*a, **k):
+        out = solve(*a, **k)
+        iters.append(geo_ctl.last_iterations)
+        return out
+
+    geo_ctl.solve = counting_solve
+    a = cl.simulate_single(geo_ctl, S, U, x0, 2.0, 0.05, N, params)
+    b = cl.simulate_single(plain_ctl, S, U, x0, 2.0, 0.05, N, params)
+    assert a.failures == 0 and b.failures == 0 and len(a.controls) == len(b.controls) >= 40
+    assert max(iters) <= 40  # the reference start needs 20 .. 200 on these solves
+    assert np.abs(a.controls - b.controls).max() <= U0_ABS_TOL
+    assert np.abs(a.states - b.states).max() <= 1e-5
+    assert geometry.clearance(a.states, LOT).min() >= 0.2
+
+
 def test_obca_edge_cases():
     """Empty batch, the shortest horizon, the maximum obstacle count (16 -> all 32 lanes of the warp busy), a batch that
     is not a multiple of the CTA's 8 problem slots, and a rejected obstacle set."""
