@@ -49,6 +49,14 @@ def test_obstacle_struct_matches_header():
     assert Obstacles.rect.offset == 8 and Obstacles.W1.offset == 8 + MAX_OBSTACLES * 32
     o = Obstacles.from_list(parking_lot_obstacles())
     assert o.count == 11 and o.as_list() == parking_lot_obstacles() and (o.W1, o.W2, o.d_min) == (3.05, 2.95, 0.2)
+    # flag values of the header == the Python constants; the reference's behaviour (recovery on, reference start) is 0
+    from car_trailer_mpc_b200.config import OBCA_GEOMETRIC_START, OBCA_NO_RECOVERY
+    assert int(re.search(r"#define TTMPC_OBCA_NO_RECOVERY (\d+)", hdr).group(1)) == OBCA_NO_RECOVERY
+    assert int(re.search(r"#define TTMPC_OBCA_GEOMETRIC_START (\d+)", hdr).group(1)) == OBCA_GEOMETRIC_START
+    assert o.flags == 0
+    assert Obstacles.from_list(parking_lot_obstacles(), recover=False).flags == OBCA_NO_RECOVERY
+    assert Obstacles.from_list(parking_lot_obstacles(), geometric_start=True).flags == OBCA_GEOMETRIC_START
+    assert Obstacles.from_list(parking_lot_obstacles(), recover=False, geometric_start=True).flags == 3
 
 
 def test_invalid_config_is_rejected(L):
