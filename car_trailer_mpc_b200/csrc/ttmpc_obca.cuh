@@ -589,6 +589,9 @@ TT_HD void ob_sync_all(const Ctx& c) {
     ob_cluster_sync();
   else
     __syncthreads();
+#ifdef TTMPC_OBCA_FLUSH_TEST  // experiment: what the L1 invalidation of a cluster-scope acquire costs (CTA-per-problem kernel)
+  if (WIDE == 1) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+#endif
 #endif
   (void)c;
 }
