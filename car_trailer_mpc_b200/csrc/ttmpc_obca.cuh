@@ -433,6 +433,43 @@ TT_HD void bsub8(const double (*L)[8], double* x) {  // x <- L^-T x
   }
 }
 
+// The same substitutions for several right-hand sides at once, written row by row: the chains of the right-hand sides
+// are independent of each other, and in this order they interleave in the instruction stream (one lane of one warp runs
+// a pair's whole factorisation: instruction-level parallelism is the only parallelism it has).  Per right-hand side the
+// operations and their order are those of fsub8 / bsub8: bit-identical results.
+template <int NR>
+TT_HD void fsub8n(const double (*L)[8], double* const (&x)[NR]) {
+  TT_UNROLL
+  for (int i = 0; i < 8; i++) {
+    double sacc[NR];
+    TT_UNROLL
+    for (int r = 0; r < NR; r++) sacc[r] = x[r][i];
+    TT_UNROLL
+    for (int k = 0; k < i; k++) {
+      TT_UNROLL
+      for (int r = 0; r < NR; r++) sacc[r] -= L[i][k] * x[r][k];
+    }
+    TT_UNROLL
+    for (int r = 0; r < NR; r++) x[r][i] = sacc[r] * L[i][i];
+  }
+}
+template <int NR>
+TT_HD void bsub8n(const double (*L)[8], double* const (&x)[NR]) {
+  TT_UNROLL
+  for (int i = 7; i >= 0; i--) {
+    double sacc[NR];
+    TT_UNROLL
+    for (int r = 0; r < NR; r++) sacc[r] = x[r][i];
+    TT_UNROLL
+    for (int k = i + 1; k < 8; k++) {
+      TT_UNROLL
+      for (int r = 0; r < NR; r++) sacc[r] -= L[k][i] * x[r][k];
+    }
+    TT_UNROLL
+    for (int r = 0; r < NR; r++) x[r][i] = sacc[r] * L[i][i];
+  }
+}
+
 // Build K_vv (lower triangle), K_vx (8x4), q (8) and t (4) of one pair at barrier parameter mu.
 //   t = D r_c + mu * gs1,  q = -mu/(v - lo) + J_v' t
 TT_HD void pair_system(const ObParams& o, const PairEval& e, const SlackBar& sb, const double* v, const double* zv,
@@ -1317,12 +1354,36 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
       // u = L^-1 q, Y = L^-1 K_vx for the Schur complement;  a = L^-T u, G = L^-T Y are kept for the direction sweep, which
       // therefore uses exactly this factorisation (two separately compiled factorisations differ in the last bits, and
       // with multipliers of 1e5 and Sigma_s of 1e10 that difference is a 1e-4 floor on the dual infeasibility)
-      fsub8(K, q);
       double col[4][8];
-      for (int cc = 0; cc < 4; cc++) {
+      for (int cc = 0; cc < 4; cc++)
         for (int i = 0; i < 8; i++) col[cc][i] = Kvx[i][cc];
-        fsub8(K, col[cc]);
+#ifndef TTMPC_OBCA_SERIAL_SUBST
+      {
+        double* const rhs[5] = {q, col[0], col[1], col[2], col[3]};
+        fsub8n<5>(K, rhs);  // the five forward substitutions interleaved
       }
+      {
+        double a8[8], b8[8];
+        for (int i = 0; i < 8; i++) a8[i] = q[i];
+        if (has_x) {  // back substitutions in pairs (two more right-hand sides live at a time, not five)
+          for (int i = 0; i < 8; i++) b8[i] = col[0][i];
+          double* const r2[2] = {a8, b8};
+          bsub8n<2>(K, r2);
+          for (int i = 0; i < 8; i++) pst(pp, qA + i, a8[i]), pst(pp, qG + 4 * i + 0, b8[i]);
+          for (int i = 0; i < 8; i++) a8[i] = col[1][i], b8[i] = col[2][i];
+          bsub8n<2>(K, r2);
+          for (int i = 0; i < 8; i++) pst(pp, qG + 4 * i + 1, a8[i]), pst(pp, qG + 4 * i + 2, b8[i]);
+          for (int i = 0; i < 8; i++) a8[i] = col[3][i];
+          bsub8(K, a8);
+          for (int i = 0; i < 8; i++) pst(pp, qG + 4 * i + 3, a8[i]);
+        } else {
+          bsub8(K, a8);
+          for (int i = 0; i < 8; i++) pst(pp, qA + i, a8[i]);
+        }
+      }
+#else
+      fsub8(K, q);
+      for (int cc = 0; cc < 4; cc++) fsub8(K, col[cc]);
       {
         double a8[8];
         for (int i = 0; i < 8; i++) a8[i] = q[i];
@@ -1335,6 +1396,7 @@ TT_HD bool factor(const Ctx& c, double mu, double delta) {
             for (int i = 0; i < 8; i++) pst(pp, qG + 4 * i + cc, a8[i]);
           }
       }
+#endif
       if (!has_x) continue;  // x_0 is data: no coupling to condense
       for (int a = 0; a < 4; a++) {
         double ga = 0.0;
@@ -1560,12 +1622,36 @@ TT_HD bool factor_fused(const Ctx& c, double mu, double delta) {
       // u = L^-1 q, Y = L^-1 K_vx for the Schur complement;  a = L^-T u, G = L^-T Y are kept for the direction sweep, which
       // therefore uses exactly this factorisation (two separately compiled factorisations differ in the last bits, and
       // with multipliers of 1e5 and Sigma_s of 1e10 that difference is a 1e-4 floor on the dual infeasibility)
-      fsub8(K, q);
       double col[4][8];
-      for (int cc = 0; cc < 4; cc++) {
+      for (int cc = 0; cc < 4; cc++)
         for (int i = 0; i < 8; i++) col[cc][i] = Kvx[i][cc];
-        fsub8(K, col[cc]);
+#ifndef TTMPC_OBCA_SERIAL_SUBST
+      {
+        double* const rhs[5] = {q, col[0], col[1], col[2], col[3]};
+        fsub8n<5>(K, rhs);  // the five forward substitutions interleaved
       }
+      {
+        double a8[8], b8[8];
+        for (int i = 0; i < 8; i++) a8[i] = q[i];
+        if (has_x) {  // back substitutions in pairs (two more right-hand sides live at a time, not five)
+          for (int i = 0; i < 8; i++) b8[i] = col[0][i];
+          double* const r2[2] = {a8, b8};
+          bsub8n<2>(K, r2);
+          for (int i = 0; i < 8; i++) pst(pp, qA + i, a8[i]), pst(pp, qG + 4 * i + 0, b8[i]);
+          for (int i = 0; i < 8; i++) a8[i] = col[1][i], b8[i] = col[2][i];
+          bsub8n<2>(K, r2);
+          for (int i = 0; i < 8; i++) pst(pp, qG + 4 * i + 1, a8[i]), pst(pp, qG + 4 * i + 2, b8[i]);
+          for (int i = 0; i < 8; i++) a8[i] = col[3][i];
+          bsub8(K, a8);
+          for (int i = 0; i < 8; i++) pst(pp, qG + 4 * i + 3, a8[i]);
+        } else {
+          bsub8(K, a8);
+          for (int i = 0; i < 8; i++) pst(pp, qA + i, a8[i]);
+        }
+      }
+#else
+      fsub8(K, q);
+      for (int cc = 0; cc < 4; cc++) fsub8(K, col[cc]);
       {
         double a8[8];
         for (int i = 0; i < 8; i++) a8[i] = q[i];
@@ -1578,6 +1664,7 @@ TT_HD bool factor_fused(const Ctx& c, double mu, double delta) {
             for (int i = 0; i < 8; i++) pst(pp, qG + 4 * i + cc, a8[i]);
           }
       }
+#endif
       if (!has_x) continue;  // x_0 is data: no coupling to condense
       for (int a = 0; a < 4; a++) {
         double ga = 0.0;
